@@ -1,0 +1,132 @@
+"""ctypes doors onto the test-infrastructure libraries (oracle restatement and, when present,
+the compiled unmodified reference).  Imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs ONLY -- never by the product package."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+YUV_420, YUV_444, YUV_400 = 1, 3, 4
+
+_u8p = C.POINTER(C.c_uint8)
+
+
+class SjoParams(C.Structure):
+    _fields_ = [("yuv_mode", C.c_int), ("method", C.c_int), ("pix_fmt", C.c_int),
+                ("quant", (C.c_uint8 * 64) * 2), ("min_quant", (C.c_uint8 * 64) * 2),
+                ("q_bias", C.c_int), ("qdelta_max_luma", C.c_int), ("qdelta_max_chroma", C.c_int)]
+
+
+def build_oracle():
+    """(Re)build oracle/liboracle.so and, where /root/reference exists, oracle/_ref."""
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True, capture_output=True)
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        L = C.CDLL(path)
+        L.sjo_encode.restype = C.c_size_t
+        L.sjo_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(SjoParams),
+                                 C.POINTER(_u8p)]
+        L.sjo_sjpeg_encode.restype = C.c_size_t
+        L.sjo_sjpeg_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                       C.c_int, C.POINTER(_u8p)]
+        L.sjo_free.argtypes = [_u8p]
+        L.sjo_default_params.argtypes = [C.POINTER(SjoParams), C.c_float, C.c_int, C.c_int]
+        L.sjo_make_rgb.argtypes = [C.c_char, C.c_int, C.c_int, C.c_uint32, C.c_void_p]
+        L.sjo_image_to_coeffs.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+        L.sjo_image_to_samples.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+        L.sjo_quantize_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_void_p]
+        L.sjo_trellis_quantize_image.argtypes = L.sjo_quantize_image.argtypes
+        L.sjo_collect_histograms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.sjo_analyse_histo.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.sjo_symbol_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.sjo_build_optimal_table.restype = C.c_int
+        L.sjo_build_optimal_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.sjo_quality_to_matrices.argtypes = [C.c_float, C.c_void_p]
+        L.sjo_geometry.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int)] * 5
+        _oracle = L
+    return _oracle
+
+
+def ref():
+    """The compiled unmodified reference, or None when oracle/_ref was not shipped/built."""
+    global _ref
+    if _ref is None:
+        path = os.path.join(ORACLE_DIR, "_ref", "libsjpeg_ref.so")
+        if not os.path.exists(path):
+            if os.path.isdir("/root/reference/src"):
+                build_oracle()
+            if not os.path.exists(path):
+                return None
+        L = C.CDLL(path)
+        L.SjpegEncode.restype = C.c_size_t
+        L.SjpegEncode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(_u8p), C.c_float,
+                                  C.c_int, C.c_int]
+        L.SjpegFreeBuffer.argtypes = [_u8p]
+        L.ref_encode_param.restype = C.c_size_t
+        L.ref_encode_param.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_float] + [C.c_int] * 6 + [C.POINTER(_u8p)]
+        _ref = L
+    return _ref
+
+
+def make_rgb(gen, w, h, seed=7654321):
+    out = np.empty((h, w, 3), dtype=np.uint8)
+    oracle().sjo_make_rgb(gen.encode(), w, h, seed, out.ctypes.data)
+    return out
+
+
+def _base_ptr(img, stride):
+    """address of row 0 for a (possibly negative) stride over a contiguous buffer"""
+    return img.ctypes.data
+
+
+def oracle_encode(rgb, w, h, stride, quality, method, yuv_mode, base=None):
+    out = _u8p()
+    ptr = base if base is not None else rgb.ctypes.data
+    n = oracle().sjo_sjpeg_encode(ptr, w, h, stride, quality, method, yuv_mode, C.byref(out))
+    if n == 0:
+        return None
+    data = C.string_at(out, n)
+    oracle().sjo_free(out)
+    return data
+
+
+def oracle_encode_params(rgb, w, h, stride, params, base=None):
+    out = _u8p()
+    ptr = base if base is not None else rgb.ctypes.data
+    n = oracle().sjo_encode(ptr, w, h, stride, C.byref(params), C.byref(out))
+    if n == 0:
+        return None
+    data = C.string_at(out, n)
+    oracle().sjo_free(out)
+    return data
+
+
+def ref_encode(rgb, w, h, stride, quality, method, yuv_mode, base=None):
+    out = _u8p()
+    ptr = base if base is not None else rgb.ctypes.data
+    n = ref().SjpegEncode(ptr, w, h, stride, C.byref(out), quality, method, yuv_mode)
+    if n == 0:
+        return None
+    data = C.string_at(out, n)
+    ref().SjpegFreeBuffer(out)
+    return data
+
+
+def md5(data):
+    return hashlib.md5(data).hexdigest().upper()
