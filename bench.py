@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 baseline-JPEG encode path.
+
+Metric (BASELINE.json): Mpixels/s encode, 3840x2160 synthetic RGB, quality 75, yuv420, method 0
+(configs[1]); frames are generator "B" of SURVEY.md 8(d) with seeds 7654321+f.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over a batch of FRAMES_PER_STEP distinct 4K frames (398 MB
+of input per rank, > the 126 MB L2, so every step reads its pixels from HBM).
+  value     device-resident throughput: inputs already in HBM, JPEG left in HBM, timed with CUDA
+            events bracketed by barrier + synchronize, max over ranks; whole-job aggregate.
+  e2e       same metric through the C ABI with HOST buffers (pinned input, host output): the
+            host->device and device->host copies are inside the timed region.
+  roofline  the fused convert+fDCT+quantise kernel alone (sjb_bench_f1), algorithmic bytes
+            (3 B/px read + 3 B/px int16 coefficients written for 4:2:0) / measured duration,
+            against MEASURED_PEAKS.json's HBM copy bandwidth.
+  cpu_baseline  the compiled unmodified reference (oracle/_ref, "reference") or the oracle port
+            ("port") timed on the box's host cores, frame-parallel, on a bounded sample.
+--impl reference times that CPU implementation as its own arm (rank 0 only under torchrun).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H, QUALITY, METHOD = 3840, 2160, 75.0, 0
+FRAMES_PER_STEP = 16
+WORKLOAD = "3840x2160 synthetic RGB (gen B) q75 yuv420 method0 (BASELINE.json configs[1])"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fp:
+            return float(json.load(fp)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip().split(",")
+                self.samples.append((float(out[0]), float(out[1])))
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons)}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_throughput(frames, seconds_budget=12.0):
+    """Frame-parallel encode on all host cores with the reference's own code (oracle/_ref) or,
+    if that library did not travel, the oracle port.  Returns (Mpix/s, kind, cores, sample)."""
+    import oracle_lib as O
+    kind = "reference" if O.ref() is not None else "port"
+    enc = O.ref_encode if kind == "reference" else O.oracle_encode
+    cores = os.cpu_count() or 1
+    nthreads = min(cores, 64)
+    # one frame per thread per round; rounds sized to the time budget from a probe
+    t0 = time.perf_counter()
+    enc(frames[0], W, H, 3 * W, QUALITY, METHOD, O.YUV_420)
+    probe = time.perf_counter() - t0
+    rounds = max(1, min(8, int(seconds_budget / max(probe * 1.5, 1e-3))))
+    done = [0] * nthreads
+
+    def work(t):
+        for r in range(rounds):
+            enc(frames[(t + r) % len(frames)], W, H, 3 * W, QUALITY, METHOD, O.YUV_420)
+            done[t] += 1
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    n = sum(done)
+    sample = "%d threads x %d frames of %s, frame-parallel SjpegEncode (ctypes releases the GIL), %.1f s" % (
+        nthreads, rounds, "3840x2160", dt)
+    return n * W * H / dt / 1e6, kind, nthreads, sample, dt, n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib as O
+    frames = [O.make_rgb("B", W, H, 7654321 + f) for f in range(4)]
+    for _ in range(max(0, min(args.warmup, 1))):
+        O.ref_encode(frames[0], W, H, 3 * W, QUALITY, METHOD, O.YUV_420) if O.ref() else None
+    vals = []
+    total_dt = 0.0
+    for _ in range(args.steps):
+        v, kind, cores, sample, dt, n = cpu_reference_throughput(frames, seconds_budget=60.0 / max(args.steps, 1))
+        vals.append(v)
+        total_dt += dt
+    value = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": "Mpixels/sec encode (4K RGB q75 yuv420)", "value": round(value, 2),
+            "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(1000 * total_dt / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": round(value, 2), "unit": "Mpix/s", "cores": cores, "kind": kind,
+                             "sample": sample},
+            "e2e": {"value": round(value, 2), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import oracle_lib as O
+    import sjpeg_b200 as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the encode path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    ctx = S.Context(local)
+    params = S.default_params(QUALITY, METHOD, S.YUV_420)
+    n = FRAMES_PER_STEP
+    # frames are the unit of sharding: every rank encodes its own frames, no
+    # data-path collective; seeds differ per rank so the work is not identical
+    frames = [O.make_rgb("B", W, H, 7654321 + rank * n + f) for f in range(n)]
+    dev = [torch.from_numpy(f.reshape(-1)).cuda() for f in frames]
+    dev_ptrs = [t.data_ptr() for t in dev]
+
+    # correctness gate on this rank: frame 0 through the host API equals the oracle
+    got = ctx.encode(frames[0], W, H, 3 * W, params)
+    want = O.oracle_encode(frames[0], W, H, 3 * W, QUALITY, METHOD, O.YUV_420)
+    if got != want:
+        raise SystemExit("bench.py: GPU output differs from the oracle; refusing to time it")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident value ------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        ctx.bench_device(dev_ptrs, W, H, 3 * W, params, 1)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    total_ms, _, jpeg_bytes, launches = ctx.bench_device(dev_ptrs, W, H, 3 * W, params, args.steps)
+    barrier()
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    pixels_all = world * n * args.steps * W * H
+    value = pixels_all / (total_ms_max * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with host buffers -------------------------------------
+    pinned = []
+    for f in frames:
+        p = S.lib().sjb_host_alloc(f.nbytes)
+        C.memmove(p, f.ctypes.data, f.nbytes)
+        pinned.append(p)
+    cap = 4 << 20
+    outs = [S.lib().sjb_host_alloc(cap) for _ in range(n)]
+    sizes = ctx.encode_batch(pinned, False, W, H, 3 * W, params, outs, False, cap)      # warm-up
+    ctx.encode_batch(pinned, False, W, H, 3 * W, params, outs, False, cap)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sizes = ctx.encode_batch(pinned, False, W, H, 3 * W, params, outs, False, cap)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    sampler.stop.set()
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = pixels_all / float(t.item()) / 1e6
+    out0 = (C.c_uint8 * sizes[0]).from_address(outs[0])
+    if bytes(out0) != want:
+        raise SystemExit("bench.py: batch output differs from the oracle")
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the fused kernel (rank 0) ----------------------------------------------
+    peak, peak_kind = load_peaks()
+    ctx.bench_f1(dev_ptrs, W, H, 3 * W, params, 2)
+    f1_ms = ctx.bench_f1(dev_ptrs, W, H, 3 * W, params, max(args.steps, 5))
+    algo_bytes = 3 * W * H + 128 * (W // 16) * (H // 16) * 6      # RGB read + int16 coefficients written
+    achieved = algo_bytes / (f1_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "f1_traffic.json")) as fp:
+            traffic = json.load(fp).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- CPU baseline (rank 0, N == 1 only) --------------------------------------------------
+    cpu = None
+    if world == 1:
+        v, kind, cores, sample, _, _ = cpu_reference_throughput(frames[:4])
+        cpu = {"value": round(v, 2), "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample}
+
+    line = {
+        "metric": "Mpixels/sec encode (4K RGB q75 yuv420)", "value": round(value, 1), "unit": "Mpix/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(total_ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": n, "bytes_in_per_step_per_gpu": n * 3 * W * H,
+                   "l2_policy": "inputs larger than L2 (16 distinct frames = 398 MB per rank)",
+                   "jpeg_bytes_frame0": int(jpeg_bytes), "bit_exact_vs_oracle": True, "parallelism": "frames sharded across ranks, no collective"},
+        "e2e": {"value": round(e2e_value, 1), "unit": "Mpix/s", "h2d_bytes_per_step": n * 3 * W * H,
+                "d2h_bytes_per_step": int(sum(sizes)), "api": "sjb_encode_batch, pinned host input, host output"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "f1_fast_kernel<420> (convert+fDCT+quantise)",
+                     "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": traffic, "peak_source": peak_kind, "algorithmic_bytes_per_launch": algo_bytes,
+                     "ms_per_launch": round(f1_ms, 5)},
+        "cpu_baseline": cpu,
+        "clocks": sampler.summary(),
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,135 @@
+/*
+ * sjpeg_b200.h -- C ABI of the B200 (sm_100a) baseline-JPEG encode path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  It is what a
+ * maintainer of webmproject/sjpeg would bind in place of the per-MCU CPU loops
+ *   Encoder::Encode()              /root/reference/src/enc.cc:391-448
+ *   SinglePassScan[Optimized]()    /root/reference/src/enc.cc:276-386
+ *   CollectHistograms()            /root/reference/src/histogram.cc:317-339
+ * (see INTEGRATION.md for the reference-side stub).  The classic entry points SjpegEncode() /
+ * SjpegCompress() / sjpeg::Encode() (include/sjpeg.h, mirroring /root/reference/src/sjpeg.h)
+ * are thin wrappers over sjb_encode().
+ *
+ * All functions return SJB_OK (0) or a negative error; none throws.  There is no CPU fallback:
+ * without a CUDA device every compute entry point returns SJB_ERR_CUDA.
+ */
+#ifndef SJPEG_B200_H_
+#define SJPEG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  SJB_OK = 0,
+  SJB_ERR_ARG = -1,       /* null pointer, bad dimension / stride / mode (api.cc:35-36, enc.cc:406) */
+  SJB_ERR_CUDA = -2,      /* CUDA runtime error or no device */
+  SJB_ERR_NOMEM = -3,     /* host or device allocation failed */
+  SJB_ERR_CAPACITY = -4   /* caller's output buffer too small (out_size still reports the need) */
+};
+
+/* values of SjpegYUVMode, /root/reference/src/sjpeg.h:54-60 (AUTO and SHARP are not on this path) */
+enum { SJB_YUV_420 = 1, SJB_YUV_444 = 3, SJB_YUV_400 = 4 };
+/* PixelFormat of /root/reference/src/sjpegi.h (kRGBInput, kBGRAInput, kRGBAInput) */
+enum { SJB_PIX_RGB = 0, SJB_PIX_BGRA = 1, SJB_PIX_RGBA = 2 };
+
+/* Encoder settings after EncoderParam -> Encoder::InitFromParam (api.cc:145-181). */
+typedef struct sjb_params {
+  int yuv_mode;             /* SJB_YUV_*                                                   */
+  int method;               /* 0..8, clamped (enc.cc:121-129)                              */
+  int pix_fmt;              /* SJB_PIX_*                                                   */
+  uint8_t quant[2][64];     /* luma / chroma matrices, natural order (Encoder::quants_[].quant_) */
+  uint8_t min_quant[2][64]; /* lower bounds (Encoder::quants_[].min_quant_), 1 = none      */
+  int q_bias;               /* AC rounding bias, enc.cc:46 default 0x78                    */
+  int qdelta_max_luma;      /* enc.cc:48 default 12                                        */
+  int qdelta_max_chroma;    /* enc.cc:49 default 1                                         */
+} sjb_params;
+
+typedef struct sjb_context sjb_context;   /* one per (thread, device): stream + scratch */
+
+uint32_t sjb_version(void);
+/* number of CUDA devices visible, or 0 */
+int sjb_device_count(void);
+
+int sjb_context_create(int device, sjb_context** ctx);
+void sjb_context_destroy(sjb_context* ctx);
+/* last CUDA error text of this context (empty string if none) */
+const char* sjb_last_error(const sjb_context* ctx);
+
+/* Defaults of Encoder::Encoder + SetQuality + SetCompressionMethod (enc.cc:66-129): what
+ * SjpegEncode(rgb,w,h,stride,&out,quality,method,yuv_mode) uses (api.cc:32-49). */
+void sjb_params_default(sjb_params* p, float quality, int method, int yuv_mode);
+/* GetQFactor + SetQuantMatrix (quantize.cc:77-96) */
+void sjb_quality_to_matrices(float quality, uint8_t out[2][64]);
+
+/* Upper bound of the JPEG size for these dimensions (for sizing 'out'). */
+size_t sjb_max_output_size(int width, int height, int yuv_mode);
+
+/*
+ * Whole encode of one picture = Encoder::Encode() (enc.cc:391-448) for passes == 1.
+ *   pix           first row of the picture; host pointer, or device pointer if pix_on_device
+ *   stride        bytes between rows, may be negative, |stride| >= bytes_per_pixel * width
+ *   out           host buffer of out_capacity bytes (device buffer if out_on_device)
+ *   out_size      receives the JPEG size
+ */
+int sjb_encode(sjb_context* ctx, const uint8_t* pix, int pix_on_device, int width, int height,
+               long long stride, const sjb_params* params, uint8_t* out, int out_on_device,
+               size_t out_capacity, size_t* out_size);
+
+/* Copies the JPEG produced by the most recent sjb_encode() of this context (it stays resident in
+ * device memory until the next encode).  Lets a caller learn the size first -- sjb_encode with
+ * out == NULL returns SJB_ERR_CAPACITY and the size -- and then fetch into an exact allocation. */
+int sjb_fetch_output(sjb_context* ctx, uint8_t* out, int out_on_device, size_t out_capacity);
+
+/*
+ * Batch of independent pictures with identical geometry and settings (config 5 of BASELINE.json:
+ * frames are the unit of sharding).  pix[i] / out[i] as above; sizes[i] receives each size.
+ * Work of different frames is overlapped on the context's streams.
+ */
+int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix_on_device, int width,
+                     int height, long long stride, const sjb_params* params, uint8_t* const* out,
+                     int out_on_device, size_t out_capacity, size_t* sizes);
+
+/* Pinned host memory helpers (for callers that want async copies at PCIe speed). */
+void* sjb_host_alloc(size_t bytes);
+void sjb_host_free(void* p);
+
+/* ---- stage-level entry points (used by the parity tests and the benchmark) ---------------- */
+
+/* F1 only: colour convert + fDCT (+ quantise).  coef (host, int16[nb_blocks*64]):
+ *   quantise = 0: unquantised x16 coefficients, natural order
+ *   quantise = 1: quantised values in zig-zag order; nzmask (host, uint64[nb_blocks], may be NULL)
+ * Blocks are in scan order: MCU raster, Y.. U V inside an MCU (enc.cc:286-305). */
+int sjb_stage_coefficients(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
+                           const sjb_params* params, int quantise, int16_t* coef, uint64_t* nzmask);
+/* histogram.cc:99-108 over the whole picture: counts = int32[2][64][129] (host) */
+int sjb_stage_histogram(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
+                        const sjb_params* params, int32_t* counts);
+/* entropy.cc:208-227 over the whole picture for the plain quantiser: freq_ac[2][256], freq_dc[2][12] */
+int sjb_stage_symbol_stats(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
+                           const sjb_params* params, uint32_t* freq_ac, uint32_t* freq_dc);
+
+/* Time (ms, CUDA events on the context's stream) of the kernels of the last sjb_encode call:
+ * [0] F1 (all launches), [1] entropy stage (E1..E4), [2] whole device pipeline. */
+int sjb_last_timings(const sjb_context* ctx, float ms[3]);
+
+/* Device-resident benchmark loop: encodes the n device pictures round-robin 'iters' times with
+ * inputs and outputs staying in HBM; returns total elapsed ms (CUDA events) and, optionally, the
+ * average duration of the fused F1 kernel per picture in f1_ms. */
+int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int width, int height,
+                     long long stride, const sjb_params* params, int iters, float* total_ms,
+                     float* f1_ms, size_t* jpeg_bytes, unsigned long long* launches);
+
+/* Times ONLY the fused F1 kernel (convert + fDCT + quantise): launches it back to back over the
+ * n device pictures, 'iters' rounds, on one stream; ms_per_launch = CUDA-event time / (n*iters).
+ * n pictures larger than L2 in total keep the input cold. */
+int sjb_bench_f1(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int width, int height,
+                 long long stride, const sjb_params* params, int iters, float* ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SJPEG_B200_H_ */

@@ -1,0 +1,287 @@
+// block_ops.cuh -- per-8x8-block integer arithmetic of the encode path, written once as
+// __host__ __device__ inline functions so that the exact same code runs inside the sm_100a
+// kernels (kernels.cu) and, compiled by g++, inside the CPU emulation used by the no-GPU tests
+// (tests/emul/emul_main.cc).  Everything here is int32 arithmetic that reproduces the reference's
+// scalar C path bit for bit:
+//   colour conversion   /root/reference/src/colors_rgb.cc:785-879
+//   integer fDCT        /root/reference/src/fdct.cc:67-209, 596-609
+//   quantiser           /root/reference/src/quantize.cc:116-148, 288-320
+//   DC diff / run-level /root/reference/src/entropy.cc:133-198
+//   bit accumulator     /root/reference/src/bit_writer.h:172-209
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SJB_HD __host__ __device__ __forceinline__
+#else
+#define SJB_HD inline
+#endif
+
+namespace sjb {
+
+enum { kYuv420 = 1, kYuv444 = 3, kYuv400 = 4 };   // numbering of sjpeg.h:54-60
+enum { kFmtRGB = 0, kFmtBGRA = 1, kFmtRGBA = 2 };
+
+// Per-matrix quantiser constants, natural coefficient order.  For a coefficient x:
+//   q = (x * iq + (x < 0 ? cneg : cpos)) >> 20        (arithmetic shift)
+// equals sign(x) * (((|x| + bias) * iquant) >> 16 >> 4) of quantize.cc:116-121, with
+// cpos = bias*iquant and cneg = 2^20 - 1 - cpos; and q != 0 <=> |x| >= qthresh (quantize.cc:144-147),
+// so the reference's threshold test needs no separate compare.
+struct QuantTab {
+  int32_t iq[64];
+  int32_t cpos[64];
+  int32_t cneg[64];
+};
+struct QuantTabs {
+  QuantTab m[2];   // 0 = luma, 1 = chroma
+};
+
+// Huffman code tables, packed as the reference does: (code << 16) | length  (entropy.cc:98-112)
+struct CodeTabs {
+  uint32_t dc[2][16];    // 12 used
+  uint32_t ac[2][256];
+};
+
+// zig-zag index -> natural index (T.81 figure 5; quantize.cc:32-41)
+#define SJB_ZIGZAG_INIT                                                                       \
+  { 0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, \
+    20, 13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,  \
+    58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 }
+
+// ---------------------------------------------------------------------------------------------
+// colour conversion.  16-bit fixed point BT.601, colors_rgb.cc:17-32.
+// ---------------------------------------------------------------------------------------------
+SJB_HD int rgb_to_y(int r, int g, int b) {          // colors_rgb.cc:785-795 ; range [-128,127]
+  return (19595 * r + 38469 * g + 7471 * b + (32768 - (128 << 16))) >> 16;
+}
+SJB_HD int rgb_to_u(int r, int g, int b) {          // colors_rgb.cc:809-819 (4:4:4)
+  return (-11059 * r - 21709 * g + 32768 * b + 32768) >> 16;
+}
+SJB_HD int rgb_to_v(int r, int g, int b) {
+  return (32768 * r - 27439 * g - 5329 * b + 32768) >> 16;
+}
+SJB_HD int rgb4_to_u(int sr, int sg, int sb) {      // colors_rgb.cc:797-806 : sums of a 2x2 quad
+  return (-11059 * sr - 21709 * sg + 32768 * sb + 131072) >> 18;
+}
+SJB_HD int rgb4_to_v(int sr, int sg, int sb) {
+  return (32768 * sr - 27439 * sg - 5329 * sb + 131072) >> 18;
+}
+
+// ---------------------------------------------------------------------------------------------
+// integer fDCT, output = 16 x the JPEG-normalised DCT.  Column pass first (fdct.cc:67-144 with
+// the C macros of :150-157), then the row pass with four constant tables (fdct.cc:174-209).
+// All intermediate stores of the reference are int16; for samples in [-128,128] every stored
+// value stays inside int16 (|DC| <= 16384), so keeping int32 registers is exact.
+// ---------------------------------------------------------------------------------------------
+SJB_HD int mulhi16(int a, int c) { return (a * c) >> 16; }
+
+SJB_HD void column_dct8(int& x0, int& x1, int& x2, int& x3, int& x4, int& x5, int& x6, int& x7) {
+  int m0 = x0 - x7, m7 = x0 + x7;
+  int m2 = x2 - x5, m5 = x2 + x5;
+  int m3 = x3 - x4, m4 = x3 + x4;
+  int m1 = x1 - x6, m6 = x1 + x6;
+  { const int t = m7 - m4; m4 = m7 + m4; m7 = t; }
+  { const int t = m6 - m5; m5 = m6 + m5; m6 = t; }
+  m4 <<= 3; m5 <<= 3;
+  x0 = m4 + m5;
+  x4 = m4 - m5;
+  m7 <<= 3; m6 <<= 3; m3 <<= 3; m0 <<= 3;
+  x2 = mulhi16(27146, m6) + m7;                   // kTan2
+  x6 = mulhi16(27146, m7) - m6;
+  m2 <<= 4; m1 <<= 4;
+  { const int t = m1 - m2; m2 = m1 + m2; m1 = t; }
+  m2 = mulhi16(m2, 23170);                        // k2Sqrt2
+  m1 = mulhi16(m1, 23170);
+  { const int t = m3 - m1; m1 = m3 + m1; m3 = t; }
+  { const int t = m0 - m2; m2 = m0 + m2; m0 = t; }
+  const int s3 = m3, s1 = m1;
+  m3 = mulhi16(m3, -21746) + s3 + 1;              // kTan3m1, CORRECT_LSB
+  m1 = mulhi16(m1, 13036) + m2 + 1;               // kTan1,   CORRECT_LSB
+  const int t4 = mulhi16(-21746, m0) + m0;
+  const int t5 = mulhi16(13036, m2);
+  x1 = m1;
+  x3 = m0 - m3;
+  x5 = s3 + t4;
+  x7 = t5 - s1;
+}
+
+// row tables of fdct.cc:28-35, selected at compile time
+template <int T> struct RowTab;
+template <> struct RowTab<0> { enum { C1 = 22725, C2 = 21407, C3 = 19266, C4 = 16384, C5 = 12873, C6 = 8867, C7 = 4520 }; };
+template <> struct RowTab<1> { enum { C1 = 31521, C2 = 29692, C3 = 26722, C4 = 22725, C5 = 17855, C6 = 12299, C7 = 6270 }; };
+template <> struct RowTab<2> { enum { C1 = 29692, C2 = 27969, C3 = 25172, C4 = 21407, C5 = 16819, C6 = 11585, C7 = 5906 }; };
+template <> struct RowTab<3> { enum { C1 = 26722, C2 = 25172, C3 = 22654, C4 = 19266, C5 = 15137, C6 = 10426, C7 = 5315 }; };
+
+template <int T>
+SJB_HD void row_dct8(int& x0, int& x1, int& x2, int& x3, int& x4, int& x5, int& x6, int& x7) {
+  typedef RowTab<T> K;
+  const int a0 = x0 + x7, b0 = x0 - x7;
+  const int a1 = x1 + x6, b1 = x1 - x6;
+  const int a2 = x2 + x5, b2 = x2 - x5;
+  const int a3 = x3 + x4, b3 = x3 - x4;
+  const int c0 = a0 + a3, c1 = a0 - a3, c2 = a1 + a2, c3 = a1 - a2;
+  x0 = (K::C4 * (c0 + c2)) >> 16;
+  x4 = (K::C4 * (c0 - c2)) >> 16;
+  x2 = (K::C2 * c1 + K::C6 * c3) >> 16;
+  x6 = (K::C6 * c1 - K::C2 * c3) >> 16;
+  x1 = (K::C1 * b0 + K::C3 * b1 + K::C5 * b2 + K::C7 * b3) >> 16;
+  x3 = (K::C3 * b0 - K::C7 * b1 - K::C1 * b2 - K::C5 * b3) >> 16;
+  x5 = (K::C5 * b0 - K::C1 * b1 + K::C7 * b2 + K::C3 * b3) >> 16;
+  x7 = (K::C7 * b0 - K::C5 * b1 + K::C3 * b2 - K::C1 * b3) >> 16;
+}
+
+// whole block, natural order v[8*row + col], in place.  fdct.cc:596-609
+SJB_HD void fdct64(int (&v)[64]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int c = 0; c < 8; ++c) {
+    column_dct8(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
+  }
+  row_dct8<0>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+  row_dct8<1>(v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+  row_dct8<2>(v[16], v[17], v[18], v[19], v[20], v[21], v[22], v[23]);
+  row_dct8<3>(v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]);
+  row_dct8<0>(v[32], v[33], v[34], v[35], v[36], v[37], v[38], v[39]);
+  row_dct8<3>(v[40], v[41], v[42], v[43], v[44], v[45], v[46], v[47]);
+  row_dct8<2>(v[48], v[49], v[50], v[51], v[52], v[53], v[54], v[55]);
+  row_dct8<1>(v[56], v[57], v[58], v[59], v[60], v[61], v[62], v[63]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// quantiser (see QuantTab)
+// ---------------------------------------------------------------------------------------------
+SJB_HD int quantize_coeff(int x, int iq, int cpos, int cneg) {
+  return (x * iq + (x < 0 ? cneg : cpos)) >> 20;
+}
+
+// number of bits of v >= 0 (0 for v == 0); sjpegi.h:186-198
+SJB_HD int bit_length(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return 32 - __clz((int)v);
+#else
+  return v ? 32 - __builtin_clz(v) : 0;
+#endif
+}
+SJB_HD int find_first_set64(uint64_t m) {   // index of lowest set bit, m != 0
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)m) - 1;
+#else
+  return __builtin_ctzll(m);
+#endif
+}
+
+// JPEG "size + amplitude bits" of a non-zero value: negative numbers are sent as value-1 in n
+// bits (one's complement).  quantize.cc:298-303, entropy.cc:133-150.
+SJB_HD void size_and_bits(int v, int* n, uint32_t* bits) {
+  const int m = v >> 31;
+  const uint32_t a = (uint32_t)((v ^ m) - m);
+  *n = bit_length(a);
+  *bits = (uint32_t)(v + m) & ((1u << *n) - 1u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block -> Huffman symbols.  zz = 64 quantised values in zig-zag order, nzmask bit i set when
+// zz[i] != 0 (bit 0 ignored), dc_pred = quantised DC of the previous block of the same component.
+// Sink receives (code_bits, length) in stream order; the two uses are bit counting and packing.
+// Follows entropy.cc:161-198 (CodeBlock) with run/levels recomputed on the fly as
+// quantize.cc:288-320 emits them.
+// ---------------------------------------------------------------------------------------------
+template <class Load, class Sink>
+SJB_HD void code_block(Load load_coeff, uint64_t nzmask, int dc, int dc_pred, const uint32_t* dc_codes,
+                       const uint32_t* ac_codes, Sink& sink) {
+  {
+    const int diff = dc - dc_pred;
+    int n = 0;
+    uint32_t bits = 0;
+    if (diff != 0) size_and_bits(diff, &n, &bits);
+    const uint32_t c = dc_codes[n];
+    // code then n suffix bits; at most 16 + 11 bits
+    sink.put(((c >> 16) << n) | bits, (int)(c & 0xff) + n);
+  }
+  uint64_t m = nzmask & ~1ull;
+  int prev = 0;   // zig-zag position of the previous non-zero coefficient (0 = DC slot)
+  while (m) {
+    const int i = find_first_set64(m);
+    m &= m - 1;
+    int run = i - prev - 1;
+    prev = i;
+    const uint32_t zrl = ac_codes[0xf0];
+    while (run >= 16) {                    // ZRL escapes, entropy.cc:176-179
+      sink.put(zrl >> 16, (int)(zrl & 0xff));
+      run -= 16;
+    }
+    int n;
+    uint32_t bits;
+    size_and_bits(load_coeff(i), &n, &bits);
+    const uint32_t c = ac_codes[(run << 4) | n];
+    sink.put(((c >> 16) << n) | bits, (int)(c & 0xff) + n);
+  }
+  if (prev < 63) {                         // EOB, entropy.cc:195-197
+    const uint32_t c = ac_codes[0x00];
+    sink.put(c >> 16, (int)(c & 0xff));
+  }
+}
+
+struct BitCountSink {
+  uint32_t total;
+  SJB_HD void put(uint32_t, int len) { total += (uint32_t)len; }
+};
+
+// symbol statistics of a block (entropy.cc:208-227); Add(table_slot) where slot < 256 is an AC
+// symbol and 256 + n a DC size.
+template <class Load, class Add>
+SJB_HD void block_symbol_stats(Load load_coeff, uint64_t nzmask, int dc, int dc_pred, Add& add) {
+  {
+    const int diff = dc - dc_pred;
+    const int m = diff >> 31;
+    add.one(256 + bit_length((uint32_t)((diff ^ m) - m)));
+  }
+  uint64_t m = nzmask & ~1ull;
+  int prev = 0;
+  while (m) {
+    const int i = find_first_set64(m);
+    m &= m - 1;
+    const int run = i - prev - 1;
+    prev = i;
+    if (run >> 4) add.many(0xf0, run >> 4);
+    const int v = load_coeff(i);
+    const int s = v >> 31;
+    add.one(((run & 15) << 4) | bit_length((uint32_t)((v ^ s) - s)));
+  }
+  if (prev < 63) add.one(0x00);
+}
+
+// ---------------------------------------------------------------------------------------------
+// MSB-first bit packing into 32-bit words (word w holds stream bits 32w..32w+31, bit 32w in the
+// MSB).  A block starts at an arbitrary bit offset: its first and last words are shared with the
+// neighbouring blocks and are merged with OR; words in between are owned and stored plainly.
+// Out must provide or_word(index, value) and set_word(index, value).
+// ---------------------------------------------------------------------------------------------
+template <class Out>
+struct BitPackSink {
+  Out& out;
+  uint64_t acc;      // pending bits, top aligned
+  int n;             // number of pending bits (< 32 between calls), includes the lead-in gap
+  uint64_t word;     // index of the word the top of acc belongs to
+  bool shared;       // true while the next word to emit is shared with the previous block
+  SJB_HD BitPackSink(Out& o, uint64_t bit_offset)
+      : out(o), acc(0), n((int)(bit_offset & 31)), word(bit_offset >> 5), shared((bit_offset & 31) != 0) {}
+  SJB_HD void put(uint32_t bits, int len) {     // len <= 27, bits < 2^len
+    acc |= (uint64_t)bits << (64 - n - len);
+    n += len;
+    if (n >= 32) {
+      const uint32_t w = (uint32_t)(acc >> 32);
+      if (shared) out.or_word(word, w); else out.set_word(word, w);
+      shared = false;
+      acc <<= 32;
+      n -= 32;
+      ++word;
+    }
+  }
+  SJB_HD void finish() {
+    if (n > 0) out.or_word(word, (uint32_t)(acc >> 32));
+  }
+};
+
+}  // namespace sjb

@@ -1,0 +1,970 @@
+// kernels.cu -- hand-written sm_100a kernels of the baseline-JPEG encode path.
+//
+//   F1  colour convert + 4:2:0 downsample + integer fDCT + quantise, one 8x8 block per thread,
+//       everything in registers (fully unrolled; the zig-zag reorder is a compile-time register
+//       permutation).  Fast path: per-warp double-buffered strips of 8 pixel rows x 768 bytes
+//       staged into shared memory with bulk-async copies (TMA engine, cp.async.bulk + mbarrier).
+//       Generic path: clamped byte loads, handles edges / odd strides / BGRA / RGBA.
+//   Q1  re-quantise stored raw coefficients (adaptive quantisation, methods >= 3)
+//   H1  coefficient histogram (methods >= 3), shared-memory privatised
+//   T1  trellis quantiser (methods 7, 8), one block per thread
+//   S1  Huffman symbol statistics (optimised tables)
+//   E1  bits per block + tile sums, E2 scan of tile sums, E3 bit packing at scanned offsets
+//   E4  0xFF byte stuffing: count / scan / scatter, padding and EOI
+//
+// Reference behaviour each stage reproduces is cited in block_ops.cuh and at each kernel.
+#include "kernels.cuh"
+
+#include <cuda_runtime.h>
+
+namespace sjb {
+
+namespace {
+
+// -------------------------------------------------------------------------------------------
+// small device helpers
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) {
+  return (static_cast<uint32_t>(lo) & 0xffffu) | (static_cast<uint32_t>(hi) << 16);
+}
+
+// CTA-wide exclusive scan of one uint32 per thread (blockDim.x multiple of 32, <= 1024).
+// Returns the exclusive prefix; *total receives the CTA sum.  scratch: 33 words of smem.
+__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* scratch, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) scratch[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = (lane < nwarps) ? scratch[lane] : 0;
+    uint32_t wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += t;
+    }
+    scratch[lane] = wi - w;            // exclusive warp offsets
+    if (lane == 31) scratch[32] = wi;  // grand total
+  }
+  __syncthreads();
+  const uint32_t res = scratch[warp] + incl - v;
+  *total = scratch[32];
+  __syncthreads();   // scratch reusable afterwards
+  return res;
+}
+
+// -------------------------------------------------------------------------------------------
+// block output: 64 int32 registers -> 128 bytes
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_block_natural(const int (&v)[64], int16_t* dst) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    d[i] = make_uint4(pack16(v[8 * i], v[8 * i + 1]), pack16(v[8 * i + 2], v[8 * i + 3]),
+                      pack16(v[8 * i + 4], v[8 * i + 5]), pack16(v[8 * i + 6], v[8 * i + 7]));
+  }
+}
+
+// quantise (QuantTab) + zig-zag + non-zero bitmap.  quantize.cc:288-320 without the run/level
+// emission, which E1/E3 redo from the bitmap.
+__device__ __forceinline__ void quantize_store_block(const int (&v)[64], const QuantTab& t,
+                                                     int16_t* dst, uint64_t* nzmask) {
+  constexpr int zz[64] = SJB_ZIGZAG_INIT;
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  uint32_t mlo = 0, mhi = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = zz[8 * i + j];
+      q[j] = quantize_coeff(v[n], t.iq[n], t.cpos[n], t.cneg[n]);
+      const uint32_t bit = 1u << ((8 * i + j) & 31);
+      if (8 * i + j < 32) mlo |= (q[j] != 0) ? bit : 0u; else mhi |= (q[j] != 0) ? bit : 0u;
+    }
+    d[i] = make_uint4(pack16(q[0], q[1]), pack16(q[2], q[3]), pack16(q[4], q[5]), pack16(q[6], q[7]));
+  }
+  *nzmask = (static_cast<uint64_t>(mhi) << 32) | mlo;
+}
+
+// -------------------------------------------------------------------------------------------
+// F1 generic: one thread per block, clamped byte loads
+// -------------------------------------------------------------------------------------------
+struct PixelReader {
+  const uint8_t* base;
+  long long stride;
+  int w1, h1, pstep, ro, bo;   // last valid x / y, bytes per pixel, offsets of R and B
+  __device__ __forceinline__ void get(int x, int y, int* r, int* g, int* b) const {
+    x = min(x, w1);
+    y = min(y, h1);
+    const uint8_t* p = base + y * stride + static_cast<long long>(x) * pstep;
+    *r = p[ro];
+    *g = p[1];
+    *b = p[bo];
+  }
+};
+
+__device__ __forceinline__ void luma_samples(const PixelReader& px, int x0, int y0, int (&v)[64]) {
+#pragma unroll
+  for (int y = 0; y < 8; ++y) {
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      int r, g, b;
+      px.get(x0 + x, y0 + y, &r, &g, &b);
+      v[8 * y + x] = rgb_to_y(r, g, b);
+    }
+  }
+}
+
+template <bool kRaw>
+__global__ void __launch_bounds__(128)
+f1_generic_kernel(ImageDesc img, int mx0, int my0, int mx1, int my1, int mcu_blocks,
+                  const __grid_constant__ QuantTabs qt, int16_t* __restrict__ coef,
+                  uint64_t* __restrict__ nzmask) {
+  const int rect_w = mx1 - mx0;
+  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long nb = static_cast<long long>(rect_w) * (my1 - my0) * mcu_blocks;
+  if (t >= nb) return;
+  const int k = static_cast<int>(t % mcu_blocks);
+  const long long m = t / mcu_blocks;
+  const int mx = mx0 + static_cast<int>(m % rect_w), my = my0 + static_cast<int>(m / rect_w);
+  const size_t g = (static_cast<size_t>(my) * img.mcus_x + mx) * mcu_blocks + k;
+
+  PixelReader px;
+  px.base = img.pix;
+  px.stride = img.stride;
+  px.w1 = img.width - 1;
+  px.h1 = img.height - 1;
+  px.pstep = (img.pix_fmt == kFmtRGB) ? 3 : 4;
+  px.ro = (img.pix_fmt == kFmtBGRA) ? 2 : 0;
+  px.bo = (img.pix_fmt == kFmtBGRA) ? 0 : 2;
+
+  int v[64];
+  int chroma = 0;
+  if (img.yuv_mode == kYuv420) {
+    const int X = 16 * mx, Y = 16 * my;
+    if (k < 4) {
+      // AverageExtraLuma (encoders.cc:107-125): luma blocks wholly outside the picture are
+      // flattened to the rounded mean of a neighbour block's samples.
+      const int sub_w = img.width - X, sub_h = img.height - Y;
+      int src = -1;
+      if (k == 1 && sub_w <= 8) src = 0;
+      if (k >= 2 && sub_h <= 8) src = (sub_w > 8) ? 1 : 0;
+      else if (k == 3 && sub_w <= 8) src = 2;
+      if (src < 0) {
+        luma_samples(px, X + 8 * (k & 1), Y + 8 * (k >> 1), v);
+      } else {
+        luma_samples(px, X + 8 * (src & 1), Y + 8 * (src >> 1), v);
+        int sum = 0;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) sum += v[i];
+        const int dc = (sum + 32) >> 6;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = dc;
+      }
+    } else {
+      chroma = 1;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) {
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          int sr = 0, sg = 0, sb = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            int r, gg, b;
+            px.get(X + 2 * x + (q & 1), Y + 2 * y + (q >> 1), &r, &gg, &b);
+            sr += r; sg += gg; sb += b;
+          }
+          v[8 * y + x] = (k == 4) ? rgb4_to_u(sr, sg, sb) : rgb4_to_v(sr, sg, sb);
+        }
+      }
+    }
+  } else {
+    const int X = 8 * mx, Y = 8 * my;
+    chroma = (k > 0);
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        int r, gg, b;
+        px.get(X + x, Y + y, &r, &gg, &b);
+        v[8 * y + x] = (k == 0) ? rgb_to_y(r, gg, b) : (k == 1) ? rgb_to_u(r, gg, b) : rgb_to_v(r, gg, b);
+      }
+    }
+  }
+  fdct64(v);
+  if (kRaw) {
+    store_block_natural(v, coef + g * 64);
+  } else {
+    if (chroma) quantize_store_block(v, qt.m[1], coef + g * 64, nzmask + g);
+    else        quantize_store_block(v, qt.m[0], coef + g * 64, nzmask + g);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// F1 fast path.  Work unit of a warp = a strip of 8 pixel rows x 256 pixels (32 block columns,
+// 768 bytes per row), staged by 8 bulk-async row copies into one of the warp's two smem slots.
+//   4:2:0 : a tile = two vertically adjacent strips = 16 MCUs; lane = 2*mcu + half; each lane
+//           converts+transforms luma block `half` (top strip) and `2+half` (bottom strip), the
+//           2x2-summed chroma goes through a per-warp smem exchange, then lane half=0 does the U
+//           block and half=1 the V block of its MCU.
+//   4:4:4 : a strip = 32 MCUs, lane = MCU, three passes over the staged pixels (Y, U, V).
+//   4:0:0 : as 4:4:4, Y only.
+// Warps are fully independent (own slots, own mbarriers): no CTA-wide barrier in the main loop.
+// -------------------------------------------------------------------------------------------
+enum { kStripRowBytes = 768, kStripBytes = 8 * kStripRowBytes, kUvMcuBytes = 288,
+       kUvBytes = 16 * kUvMcuBytes, kFastWarps = 4,
+       kWarpSmem = 2 * kStripBytes + kUvBytes + 16 };
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// bytes of one 24-byte block row held in six 32-bit words
+#define SJB_BYTE(w, i) (((w)[(i) >> 2] >> (8 * ((i) & 3))) & 0xffu)
+
+__device__ __forceinline__ void load_row24(uint32_t addr, uint32_t (&w)[6]) {
+  // three 64-bit shared loads; lane stride is 24 bytes => conflict-free per half-warp
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(addr));
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+8];" : "=r"(w[2]), "=r"(w[3]) : "r"(addr));
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+16];" : "=r"(w[4]), "=r"(w[5]) : "r"(addr));
+}
+
+// 4:2:0 strip: 8x8 pixels -> 64 luma samples + 4x4 U and V (2x2 sums).  colors_rgb.cc:850-879
+__device__ __forceinline__ void convert_strip_420(uint32_t addr, int (&y)[64], int (&u)[16], int (&v)[16]) {
+#pragma unroll
+  for (int rp = 0; rp < 4; ++rp) {
+    uint32_t a[6], b[6];
+    load_row24(addr + (2 * rp) * kStripRowBytes, a);
+    load_row24(addr + (2 * rp + 1) * kStripRowBytes, b);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int sr = 0, sg = 0, sb = 0;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int x = 2 * q + e;
+        const int r0 = SJB_BYTE(a, 3 * x), g0 = SJB_BYTE(a, 3 * x + 1), b0 = SJB_BYTE(a, 3 * x + 2);
+        const int r1 = SJB_BYTE(b, 3 * x), g1 = SJB_BYTE(b, 3 * x + 1), b1 = SJB_BYTE(b, 3 * x + 2);
+        y[16 * rp + x] = rgb_to_y(r0, g0, b0);
+        y[16 * rp + 8 + x] = rgb_to_y(r1, g1, b1);
+        sr += r0 + r1; sg += g0 + g1; sb += b0 + b1;
+      }
+      u[4 * rp + q] = rgb4_to_u(sr, sg, sb);
+      v[4 * rp + q] = rgb4_to_v(sr, sg, sb);
+    }
+  }
+}
+
+// 4:4:4 / 4:0:0 strip: one component of 8x8 pixels.  colors_rgb.cc:809-848
+template <int kComp>
+__device__ __forceinline__ void convert_strip_444(uint32_t addr, int (&s)[64]) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    uint32_t a[6];
+    load_row24(addr + r * kStripRowBytes, a);
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const int rr = SJB_BYTE(a, 3 * x), gg = SJB_BYTE(a, 3 * x + 1), bb = SJB_BYTE(a, 3 * x + 2);
+      s[8 * r + x] = (kComp == 0) ? rgb_to_y(rr, gg, bb) : (kComp == 1) ? rgb_to_u(rr, gg, bb) : rgb_to_v(rr, gg, bb);
+    }
+  }
+}
+
+template <bool kRaw>
+__device__ __forceinline__ void finish_block(int (&v)[64], const QuantTab& t, int16_t* coef,
+                                             uint64_t* nzmask, size_t g) {
+  fdct64(v);
+  if (kRaw) store_block_natural(v, coef + g * 64);
+  else quantize_store_block(v, t, coef + g * 64, nzmask + g);
+}
+
+template <int kMode, bool kRaw>
+__global__ void __launch_bounds__(kFastWarps * 32)
+f1_fast_kernel(ImageDesc img, int mx_full, int my0, int my1, const __grid_constant__ QuantTabs qt,
+               int16_t* __restrict__ coef, uint64_t* __restrict__ nzmask) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* wsm = smem_raw + warp * kWarpSmem;
+  const uint32_t slot0 = smem_addr(wsm);
+  const uint32_t uvbuf = slot0 + 2 * kStripBytes;
+  const uint32_t bar0 = uvbuf + kUvBytes;          // two 8-byte mbarriers
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  constexpr bool k420 = (kMode == kYuv420);
+  constexpr int kMcuBlocks = k420 ? 6 : (kMode == kYuv444 ? 3 : 1);
+  constexpr int kMcusPerItem = k420 ? 16 : 32;          // MCUs per work item along x
+  constexpr int kStripsPerItem = k420 ? 2 : 1;
+  const int chunks_x = (mx_full + kMcusPerItem - 1) / kMcusPerItem;
+  const long long items = static_cast<long long>(chunks_x) * (my1 - my0);
+  const long long gwarp = blockIdx.x * static_cast<long long>(kFastWarps) + warp;
+  const long long nwarps = gridDim.x * static_cast<long long>(kFastWarps);
+  if (gwarp >= items) return;
+  const long long my_items = (items - gwarp + nwarps - 1) / nwarps;
+  const long long strips = my_items * kStripsPerItem;
+
+  // issue the bulk copies of strip number h (in this warp's sequence) into slot h&1
+  auto issue = [&](long long h) {
+    const long long item = gwarp + (h / kStripsPerItem) * nwarps;
+    const int cx = static_cast<int>(item % chunks_x), ry = my0 + static_cast<int>(item / chunks_x);
+    const int mcus = min(kMcusPerItem, mx_full - cx * kMcusPerItem);
+    const uint32_t row_bytes = static_cast<uint32_t>(mcus) * (k420 ? 48u : 24u);
+    const int py = (k420 ? 16 * ry + 8 * static_cast<int>(h & 1) : 8 * ry);
+    const uint32_t bar = bar0 + 8 * static_cast<uint32_t>(h & 1);
+    if (lane == 0) mbar_expect_tx(bar, 8 * row_bytes);
+    __syncwarp();
+    if (lane < 8) {
+      const uint8_t* src = img.pix + (py + lane) * img.stride + static_cast<long long>(cx) * kStripRowBytes;
+      bulk_g2s(slot0 + static_cast<uint32_t>(h & 1) * kStripBytes + lane * kStripRowBytes, src, row_bytes, bar);
+    }
+  };
+
+  issue(0);
+  if (strips > 1) issue(1);
+
+  int u[16], v[16];   // 4:2:0 chroma partials of the current strip
+  for (long long h = 0; h < strips; ++h) {
+    const long long item = gwarp + (h / kStripsPerItem) * nwarps;
+    const int cx = static_cast<int>(item % chunks_x), ry = my0 + static_cast<int>(item / chunks_x);
+    const int mcus = min(kMcusPerItem, mx_full - cx * kMcusPerItem);
+    const int slot = static_cast<int>(h & 1);
+    mbar_wait(bar0 + 8 * slot, static_cast<uint32_t>((h >> 1) & 1));
+    const uint32_t src = slot0 + slot * kStripBytes + lane * 24;
+    const size_t mcu0 = static_cast<size_t>(ry) * img.mcus_x + static_cast<size_t>(cx) * kMcusPerItem;
+
+    if (k420) {
+      const int m = lane >> 1, half = lane & 1, bottom = static_cast<int>(h & 1);
+      const bool active = m < mcus;
+      int y[64];
+      convert_strip_420(src, y, u, v);
+      __syncwarp();
+      if (h + 2 < strips) issue(h + 2);     // the slot is consumed: refill it right away
+      // chroma partials -> exchange buffer: rows interleaved U,V (16 bytes each)
+      const uint32_t uvm = uvbuf + m * kUvMcuBytes;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const uint32_t a = uvm + (4 * bottom + r) * 32 + half * 8;
+        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(pack16(u[4 * r], u[4 * r + 1])),
+                     "r"(pack16(u[4 * r + 2], u[4 * r + 3])) : "memory");
+        asm volatile("st.shared.v2.u32 [%0+16], {%1,%2};" ::"r"(a), "r"(pack16(v[4 * r], v[4 * r + 1])),
+                     "r"(pack16(v[4 * r + 2], v[4 * r + 3])) : "memory");
+      }
+      if (active) finish_block<kRaw>(y, qt.m[0], coef, nzmask, (mcu0 + m) * 6 + 2 * bottom + half);
+      if (bottom) {
+        __syncwarp();
+        int c[64];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          uint32_t w0, w1, w2, w3;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                       : "r"(uvm + r * 32 + half * 16));
+          c[8 * r + 0] = static_cast<int16_t>(w0 & 0xffff); c[8 * r + 1] = static_cast<int>(w0) >> 16;
+          c[8 * r + 2] = static_cast<int16_t>(w1 & 0xffff); c[8 * r + 3] = static_cast<int>(w1) >> 16;
+          c[8 * r + 4] = static_cast<int16_t>(w2 & 0xffff); c[8 * r + 5] = static_cast<int>(w2) >> 16;
+          c[8 * r + 6] = static_cast<int16_t>(w3 & 0xffff); c[8 * r + 7] = static_cast<int>(w3) >> 16;
+        }
+        __syncwarp();   // exchange buffer free for the next tile
+        if (active) finish_block<kRaw>(c, qt.m[1], coef, nzmask, (mcu0 + m) * 6 + 4 + half);
+      }
+    } else {
+      const bool active = lane < mcus;
+      {
+        int s[64];
+        convert_strip_444<0>(src, s);
+        if (active) finish_block<kRaw>(s, qt.m[0], coef, nzmask, (mcu0 + lane) * kMcuBlocks);
+      }
+      if (kMode == kYuv444) {
+        {
+          int s[64];
+          convert_strip_444<1>(src, s);
+          if (active) finish_block<kRaw>(s, qt.m[1], coef, nzmask, (mcu0 + lane) * 3 + 1);
+        }
+        {
+          int s[64];
+          convert_strip_444<2>(src, s);
+          if (active) finish_block<kRaw>(s, qt.m[1], coef, nzmask, (mcu0 + lane) * 3 + 2);
+        }
+      }
+      __syncwarp();
+      if (h + 2 < strips) issue(h + 2);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Q1: quantise stored raw coefficients in place
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_block_natural(const int16_t* src, int (&v)[64]) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 w = s[i];
+    v[8 * i + 0] = static_cast<int16_t>(w.x & 0xffff); v[8 * i + 1] = static_cast<int>(w.x) >> 16;
+    v[8 * i + 2] = static_cast<int16_t>(w.y & 0xffff); v[8 * i + 3] = static_cast<int>(w.y) >> 16;
+    v[8 * i + 4] = static_cast<int16_t>(w.z & 0xffff); v[8 * i + 5] = static_cast<int>(w.z) >> 16;
+    v[8 * i + 6] = static_cast<int16_t>(w.w & 0xffff); v[8 * i + 7] = static_cast<int>(w.w) >> 16;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+requantize_kernel(int16_t* __restrict__ coef, uint64_t* __restrict__ nzmask, size_t nb_blocks,
+                  int mcu_blocks, int luma_blocks, const __grid_constant__ QuantTabs qt) {
+  const size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (g >= nb_blocks) return;
+  int v[64];
+  load_block_natural(coef + g * 64, v);
+  if (static_cast<int>(g % mcu_blocks) >= luma_blocks) quantize_store_block(v, qt.m[1], coef + g * 64, nzmask + g);
+  else quantize_store_block(v, qt.m[0], coef + g * 64, nzmask + g);
+}
+
+// -------------------------------------------------------------------------------------------
+// H1: histogram of |coef| >> 2 (histogram.cc:99-108).  Per-CTA privatised copy of the 64x128
+// bins of ONE matrix at a time would need two passes; instead each CTA keeps both matrices'
+// bins for the positions it is working on: 64 KB of shared memory, flushed with atomicAdd.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+histogram_kernel(const int16_t* __restrict__ raw, size_t nb_blocks, int mcu_blocks, int luma_blocks,
+                 int32_t* __restrict__ counts) {
+  extern __shared__ int32_t hist[];   // [2][64][128]
+  for (int i = threadIdx.x; i < 2 * 64 * 128; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  // 8 lanes per block, each lane owns 8 consecutive natural positions (one 16-byte load):
+  // coalesced, and the 8 lanes of a block hit different rows of the table.
+  const size_t lanes_total = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; t < nb_blocks * 8;
+       t += lanes_total) {
+    const size_t g = t >> 3;
+    const int part = static_cast<int>(t & 7);
+    const int m = (static_cast<int>(g % mcu_blocks) >= luma_blocks) ? 1 : 0;
+    const uint4 w = reinterpret_cast<const uint4*>(raw + g * 64)[part];
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = (j & 1) ? (static_cast<int>(ww[j >> 1]) >> 16) : static_cast<int16_t>(ww[j >> 1] & 0xffff);
+      const int a = abs(c) >> 2;
+      if (a < 128) atomicAdd(&hist[(m * 64 + part * 8 + j) * 128 + a], 1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * 64 * 128; i += blockDim.x) {
+    const int c = hist[i];
+    if (c) atomicAdd(&counts[(i >> 7) * 129 + (i & 127)], c);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Entropy stage helpers
+// -------------------------------------------------------------------------------------------
+struct ScanGeom {
+  int mcu_blocks, luma_blocks;
+};
+
+// quantised DC of the previous block of the same component in scan order (enc.cc:286-305:
+// MCU raster order, blocks interleaved; predictors reset once per image, entropy.cc:155-159)
+__device__ __forceinline__ int dc_predictor(const int16_t* zz, size_t g, int k, int mcu_blocks, int luma_blocks) {
+  size_t prev;
+  if (k < luma_blocks) {
+    if (k > 0) prev = g - 1;
+    else if (g == 0) return 0;
+    else prev = g - mcu_blocks + luma_blocks - 1;
+  } else {
+    if (g < static_cast<size_t>(mcu_blocks)) return 0;
+    prev = g - mcu_blocks;
+  }
+  return zz[prev * 64];
+}
+
+struct CoefLoader {
+  const int16_t* p;
+  __device__ __forceinline__ int operator()(int i) const { return p[i]; }
+};
+
+__device__ __forceinline__ void load_code_tables(const CodeTabs* tabs, CodeTabs* sh) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(tabs);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(sh);
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(CodeTabs) / 4); i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+}
+
+// E1 (entropy.cc:161-198 as a length count)
+__global__ void __launch_bounds__(kTileBlocks)
+block_bits_kernel(const int16_t* __restrict__ zz, const uint64_t* __restrict__ nzmask, size_t nb_blocks,
+                  int mcu_blocks, int luma_blocks, const CodeTabs* __restrict__ tabs,
+                  uint32_t* __restrict__ block_bits, uint32_t* __restrict__ tile_sums) {
+  __shared__ CodeTabs sh;
+  __shared__ uint32_t scratch[33];
+  load_code_tables(tabs, &sh);
+  const size_t g = blockIdx.x * static_cast<size_t>(kTileBlocks) + threadIdx.x;
+  uint32_t bits = 0;
+  if (g < nb_blocks) {
+    const int k = static_cast<int>(g % mcu_blocks);
+    const int c = (k >= luma_blocks) ? 1 : 0;
+    const int16_t* b = zz + g * 64;
+    BitCountSink sink = {0};
+    code_block(CoefLoader{b}, nzmask[g], b[0], dc_predictor(zz, g, k, mcu_blocks, luma_blocks),
+               sh.dc[c], sh.ac[c], sink);
+    bits = sink.total;
+    block_bits[g] = bits;
+  }
+  uint32_t total;
+  cta_exclusive_scan(bits, scratch, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// S1 (entropy.cc:208-227)
+struct SmemStats {
+  uint32_t* f;   // [272] of the block's table class
+  __device__ __forceinline__ void one(int slot) { atomicAdd(&f[slot], 1u); }
+  __device__ __forceinline__ void many(int slot, int n) { atomicAdd(&f[slot], static_cast<uint32_t>(n)); }
+};
+
+__global__ void __launch_bounds__(kTileBlocks)
+symbol_stats_kernel(const int16_t* __restrict__ zz, const uint64_t* __restrict__ nzmask, size_t nb_blocks,
+                    int mcu_blocks, int luma_blocks, uint32_t* __restrict__ freq) {
+  __shared__ uint32_t f[2][272];
+  for (int i = threadIdx.x; i < 2 * 272; i += blockDim.x) (&f[0][0])[i] = 0;
+  __syncthreads();
+  const size_t stride = static_cast<size_t>(gridDim.x) * kTileBlocks;
+  for (size_t g = blockIdx.x * static_cast<size_t>(kTileBlocks) + threadIdx.x; g < nb_blocks; g += stride) {
+    const int k = static_cast<int>(g % mcu_blocks);
+    const int c = (k >= luma_blocks) ? 1 : 0;
+    const int16_t* b = zz + g * 64;
+    SmemStats add = {f[c]};
+    block_symbol_stats(CoefLoader{b}, nzmask[g], b[0], dc_predictor(zz, g, k, mcu_blocks, luma_blocks), add);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * 272; i += blockDim.x) {
+    const uint32_t c = (&f[0][0])[i];
+    if (c) atomicAdd(&freq[i], c);
+  }
+}
+
+// E2: one CTA scans all tile sums (tiles are few: nb_blocks / 256)
+__global__ void __launch_bounds__(1024)
+scan_tiles_kernel(const uint32_t* __restrict__ tile_sums, size_t nb_tiles,
+                  unsigned long long* __restrict__ tile_offsets, StreamInfo* __restrict__ info) {
+  __shared__ uint32_t scratch[33];
+  unsigned long long base = 0;
+  for (size_t i0 = 0; i0 < nb_tiles; i0 += blockDim.x) {
+    const size_t i = i0 + threadIdx.x;
+    const uint32_t v = (i < nb_tiles) ? tile_sums[i] : 0;
+    uint32_t total;
+    const uint32_t ex = cta_exclusive_scan(v, scratch, &total);
+    if (i < nb_tiles) tile_offsets[i] = base + ex;
+    base += total;
+  }
+  if (threadIdx.x == 0) info->total_bits = base;
+}
+
+// E3: pack (bit_writer.h:201-209 without the serial accumulator)
+struct StreamOut {
+  uint32_t* words;
+  __device__ __forceinline__ void or_word(uint64_t i, uint32_t v) { if (v) atomicOr(&words[i], v); }
+  __device__ __forceinline__ void set_word(uint64_t i, uint32_t v) { words[i] = v; }
+};
+
+__global__ void __launch_bounds__(kTileBlocks)
+pack_kernel(const int16_t* __restrict__ zz, const uint64_t* __restrict__ nzmask, size_t nb_blocks,
+            int mcu_blocks, int luma_blocks, const CodeTabs* __restrict__ tabs,
+            const uint32_t* __restrict__ block_bits, const unsigned long long* __restrict__ tile_offsets,
+            uint32_t* __restrict__ stream) {
+  __shared__ CodeTabs sh;
+  __shared__ uint32_t scratch[33];
+  load_code_tables(tabs, &sh);
+  const size_t g = blockIdx.x * static_cast<size_t>(kTileBlocks) + threadIdx.x;
+  const uint32_t bits = (g < nb_blocks) ? block_bits[g] : 0;
+  uint32_t total;
+  const uint32_t ex = cta_exclusive_scan(bits, scratch, &total);
+  if (g >= nb_blocks) return;
+  const int k = static_cast<int>(g % mcu_blocks);
+  const int c = (k >= luma_blocks) ? 1 : 0;
+  const int16_t* b = zz + g * 64;
+  StreamOut out = {stream};
+  BitPackSink<StreamOut> sink(out, tile_offsets[blockIdx.x] + ex);
+  code_block(CoefLoader{b}, nzmask[g], b[0], dc_predictor(zz, g, k, mcu_blocks, luma_blocks),
+             sh.dc[c], sh.ac[c], sink);
+  sink.finish();
+}
+
+// -------------------------------------------------------------------------------------------
+// E4: byte stuffing (bit_writer.h:172-196, bit_writer.cc:107-116, headers.cc:262-268).
+// The word stream holds ceil(total_bits/8) bytes, MSB-first inside each word; the last byte is
+// padded with 1-bits.  Every 0xFF byte is followed by 0x00.  Tile = 4096 stream bytes per CTA
+// iteration, 16 bytes per thread.
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 load_stream16(const uint32_t* stream, unsigned long long byte0,
+                                               unsigned long long nbytes, unsigned long long total_bits) {
+  uint4 w = make_uint4(0, 0, 0, 0);
+  if (byte0 < nbytes) {
+    w = *reinterpret_cast<const uint4*>(stream + (byte0 >> 2));
+    const unsigned pad = static_cast<unsigned>((0 - total_bits) & 7);
+    if (pad && nbytes - byte0 <= 16) {             // the padded byte is in here
+      const unsigned last = static_cast<unsigned>(nbytes - 1 - byte0);
+      const uint32_t m = ((1u << pad) - 1u) << (8 * (3 - (last & 3)));
+      if ((last >> 2) == 0) w.x |= m; else if ((last >> 2) == 1) w.y |= m; else if ((last >> 2) == 2) w.z |= m; else w.w |= m;
+    }
+  }
+  return w;
+}
+__device__ __forceinline__ int count_ff(uint32_t w) {
+  // a byte is 0xFF iff all its bits are set
+  uint32_t t = w & (w >> 4);
+  t &= t >> 2;
+  t &= t >> 1;
+  return __popc(t & 0x01010101u);
+}
+__device__ __forceinline__ int valid_bytes(unsigned long long byte0, unsigned long long nbytes) {
+  return (byte0 >= nbytes) ? 0 : static_cast<int>(min(16ull, nbytes - byte0));
+}
+__device__ __forceinline__ int count_ff16(uint4 w, int valid) {
+  // bytes past 'valid' are zero in the stream (never written), so they never count
+  (void)valid;
+  return count_ff(w.x) + count_ff(w.y) + count_ff(w.z) + count_ff(w.w);
+}
+
+__global__ void __launch_bounds__(256)
+ff_count_kernel(const uint32_t* __restrict__ stream, const StreamInfo* __restrict__ info,
+                uint32_t* __restrict__ ff_tile_sums) {
+  __shared__ uint32_t scratch[33];
+  const unsigned long long total_bits = info->total_bits;
+  const unsigned long long nbytes = (total_bits + 7) >> 3;
+  const unsigned long long tiles = (nbytes + kStuffTileBytes - 1) / kStuffTileBytes;
+  for (unsigned long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const unsigned long long byte0 = t * kStuffTileBytes + threadIdx.x * 16ull;
+    const uint4 w = load_stream16(stream, byte0, nbytes, total_bits);
+    uint32_t total;
+    cta_exclusive_scan(static_cast<uint32_t>(count_ff16(w, valid_bytes(byte0, nbytes))), scratch, &total);
+    if (threadIdx.x == 0) ff_tile_sums[t] = total;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+ff_scan_kernel(const uint32_t* __restrict__ ff_tile_sums, unsigned long long* __restrict__ ff_tile_offsets,
+               StreamInfo* __restrict__ info, unsigned long long header_len) {
+  __shared__ uint32_t scratch[33];
+  const unsigned long long nbytes = (info->total_bits + 7) >> 3;
+  const unsigned long long tiles = (nbytes + kStuffTileBytes - 1) / kStuffTileBytes;
+  unsigned long long base = 0;
+  for (unsigned long long i0 = 0; i0 < tiles; i0 += blockDim.x) {
+    const unsigned long long i = i0 + threadIdx.x;
+    const uint32_t v = (i < tiles) ? ff_tile_sums[i] : 0;
+    uint32_t total;
+    const uint32_t ex = cta_exclusive_scan(v, scratch, &total);
+    if (i < tiles) ff_tile_offsets[i] = base + ex;
+    base += total;
+  }
+  if (threadIdx.x == 0) {
+    info->stuffed_bytes = base;
+    info->out_size = header_len + nbytes + base + 2;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+stuff_kernel(uint32_t* __restrict__ stream, const unsigned long long* __restrict__ ff_tile_offsets,
+             const StreamInfo* __restrict__ info, uint8_t* __restrict__ out) {
+  __shared__ uint32_t scratch[33];
+  const unsigned long long total_bits = info->total_bits;
+  const unsigned long long nbytes = (total_bits + 7) >> 3;
+  const unsigned long long tiles = (nbytes + kStuffTileBytes - 1) / kStuffTileBytes;
+  for (unsigned long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const unsigned long long byte0 = t * kStuffTileBytes + threadIdx.x * 16ull;
+    const int valid = valid_bytes(byte0, nbytes);
+    const uint4 w = load_stream16(stream, byte0, nbytes, total_bits);
+    uint32_t total;
+    const uint32_t ex = cta_exclusive_scan(static_cast<uint32_t>(count_ff16(w, valid)), scratch, &total);
+    if (valid > 0) {
+      // self-cleaning: the stream buffer must be all zero for the next encode's atomicOr
+      *reinterpret_cast<uint4*>(stream + (byte0 >> 2)) = make_uint4(0, 0, 0, 0);
+      uint8_t* dst = out + byte0 + ff_tile_offsets[t] + ex;
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i < valid) {
+          const uint32_t b = (ww[i >> 2] >> (8 * (3 - (i & 3)))) & 0xffu;
+          *dst++ = static_cast<uint8_t>(b);
+          if (b == 0xffu) *dst++ = 0;
+        }
+      }
+      if (byte0 + valid == nbytes) {   // EOI
+        dst[0] = 0xff;
+        dst[1] = 0xd9;
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// T1: trellis quantisation, one block per thread (quantize.cc:325-457).  Node arrays live in
+// local memory; scores are uint32 and wrap exactly like the reference's score_t.
+// -------------------------------------------------------------------------------------------
+struct TrellisNode {
+  uint32_t score, disto;
+  int16_t prev;       // index of best predecessor
+  uint8_t pos, nbits;
+  uint16_t code;
+  uint8_t rank, run;
+};
+
+__global__ void __launch_bounds__(64)
+trellis_kernel(int16_t* __restrict__ coef, uint64_t* __restrict__ nzmask, size_t nb_blocks,
+               int mcu_blocks, int luma_blocks, const __grid_constant__ QuantTabs qt,
+               const uint8_t* __restrict__ quant, const CodeTabs* __restrict__ tabs) {
+  __shared__ uint8_t ac_len[2][256];
+  __shared__ uint8_t qm[2][64];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) ac_len[i >> 8][i & 255] = static_cast<uint8_t>(tabs->ac[i >> 8][i & 255] & 0xff);
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) qm[i >> 6][i & 63] = quant[i];
+  __syncthreads();
+  const size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (g >= nb_blocks) return;
+  const int c = (static_cast<int>(g % mcu_blocks) >= luma_blocks) ? 1 : 0;
+  const QuantTab& t = qt.m[c];
+  const uint8_t* len = ac_len[c];
+  constexpr int zz[64] = SJB_ZIGZAG_INIT;
+  int16_t* blk = coef + g * 64;
+
+  TrellisNode nodes[1 + 2 * 63];
+  uint32_t disto0[64];
+  int16_t in[64];
+  {
+    const uint4* s = reinterpret_cast<const uint4*>(blk);
+    uint4* d = reinterpret_cast<uint4*>(in);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = s[i];
+  }
+  nodes[0].score = 0; nodes[0].disto = 0; nodes[0].prev = -1; nodes[0].pos = 0; nodes[0].nbits = 0;
+  nodes[0].code = 0; nodes[0].rank = 0; nodes[0].run = 0;
+  int cur = 1;
+  disto0[0] = 0;
+  for (int i = 1; i < 64; ++i) {
+    const int j = zz[i];
+    const uint32_t q = static_cast<uint32_t>(qm[c][j]) << 4;
+    const uint32_t lambda = q * q / 32u;
+    const int x = in[j];
+    const int sign = x >> 31;
+    const int V = (x ^ sign) - sign;
+    disto0[i] = static_cast<uint32_t>(V * V) + disto0[i - 1];
+    int v = (V * t.iq[j] + t.cpos[j]) >> 20;
+    if (v == 0) continue;
+    int nbits = bit_length(static_cast<uint32_t>(v));
+    for (int k = 0; k < 2; ++k) {
+      const int err = V - v * static_cast<int>(q);
+      TrellisNode n;
+      n.code = static_cast<uint16_t>((v ^ sign) & ((1 << nbits) - 1));
+      n.pos = static_cast<uint8_t>(i);
+      n.nbits = static_cast<uint8_t>(nbits);
+      n.score = 0xffffffffu;
+      n.prev = -1; n.rank = 0; n.run = 0;
+      // SearchBestPrev, quantize.cc:350-383
+      const uint32_t base = static_cast<uint32_t>(err * err) + disto0[i - 1];
+      n.disto = static_cast<uint32_t>(err * err);
+      bool found = false;
+      for (int p = cur - 1; p >= 0; --p) {
+        const int run = i - 1 - nodes[p].pos;
+        if (run < 0) continue;
+        uint32_t bits = static_cast<uint32_t>(nbits) + static_cast<uint32_t>(run >> 4) * len[0xf0];
+        const uint32_t d = base - disto0[nodes[p].pos];
+        if (d + lambda * bits >= n.score) break;
+        bits += len[((run & 15) << 4) | nbits];
+        const uint32_t score = d + lambda * bits + nodes[p].score;
+        if (score < n.score) {
+          n.score = score; n.disto = d; n.prev = static_cast<int16_t>(p);
+          n.rank = static_cast<uint8_t>(nodes[p].rank + 1); n.run = static_cast<uint8_t>(run);
+          found = true;
+        }
+      }
+      if (found) nodes[cur++] = n;
+      --nbits;
+      if (nbits <= 0) break;
+      v = (1 << nbits) - 1;
+    }
+  }
+  int best = 0;
+  if (cur != 1) {
+    uint32_t best_score = 0xffffffffu;
+    for (int p = cur - 1; p >= 0; --p) {
+      const uint32_t s = nodes[p].score + (disto0[63] - disto0[nodes[p].pos]);
+      if (s < best_score) { best = p; best_score = s; }
+    }
+  }
+  // write back: DC by the plain formula, AC from the chosen path, zig-zag order
+  int16_t outv[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) outv[i] = 0;
+  outv[0] = static_cast<int16_t>(quantize_coeff(in[0], t.iq[0], t.cpos[0], t.cneg[0]));
+  uint64_t mask = 0;
+  for (int p = best; p > 0; p = nodes[p].prev) {
+    const int n = nodes[p].nbits;
+    const int amp = nodes[p].code;
+    const int val = (amp >> (n - 1)) ? amp : amp - ((1 << n) - 1);
+    outv[nodes[p].pos] = static_cast<int16_t>(val);
+    mask |= 1ull << nodes[p].pos;
+  }
+  {
+    const uint4* s = reinterpret_cast<const uint4*>(outv);
+    uint4* d = reinterpret_cast<uint4*>(blk);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = s[i];
+  }
+  nzmask[g] = mask | (outv[0] != 0 ? 1ull : 0ull);
+}
+
+int cdiv(size_t a, size_t b) { return static_cast<int>((a + b - 1) / b); }
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------
+// launch wrappers
+// -------------------------------------------------------------------------------------------
+static int McuBlocks(int mode) { return mode == kYuv420 ? 6 : (mode == kYuv444 ? 3 : 1); }
+
+void LaunchF1Generic(const ImageDesc& img, int mx0, int my0, int mx1, int my1, bool raw,
+                     const QuantTabs& qt, int16_t* coef, uint64_t* nzmask, cudaStream_t s) {
+  if (mx1 <= mx0 || my1 <= my0) return;
+  const int mb = McuBlocks(img.yuv_mode);
+  const size_t nb = static_cast<size_t>(mx1 - mx0) * (my1 - my0) * mb;
+  if (raw) f1_generic_kernel<true><<<cdiv(nb, 128), 128, 0, s>>>(img, mx0, my0, mx1, my1, mb, qt, coef, nzmask);
+  else     f1_generic_kernel<false><<<cdiv(nb, 128), 128, 0, s>>>(img, mx0, my0, mx1, my1, mb, qt, coef, nzmask);
+}
+
+bool F1FastEligible(const ImageDesc& img) {
+  return img.pix_fmt == kFmtRGB && (reinterpret_cast<uintptr_t>(img.pix) & 15) == 0 && (img.stride & 15) == 0;
+}
+
+template <int kMode, bool kRaw>
+static void LaunchF1FastT(const ImageDesc& img, int mx_full, int my0, int my1, const QuantTabs& qt,
+                          int16_t* coef, uint64_t* nzmask, cudaStream_t s) {
+  static int sm_counts[64] = {0};
+  const size_t smem = kFastWarps * kWarpSmem;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (sm_counts[dev] == 0) {   // once per device and instantiation
+    cudaDeviceGetAttribute(&sm_counts[dev], cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(f1_fast_kernel<kMode, kRaw>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  }
+  const int sm_count = sm_counts[dev];
+  const int per_item = (kMode == kYuv420) ? 16 : 32;
+  const long long items = static_cast<long long>((mx_full + per_item - 1) / per_item) * (my1 - my0);
+  int ctas_per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, f1_fast_kernel<kMode, kRaw>, kFastWarps * 32, smem);
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  long long grid = (items + kFastWarps - 1) / kFastWarps;
+  const long long resident = static_cast<long long>(sm_count) * ctas_per_sm;
+  if (grid > resident) grid = resident;
+  f1_fast_kernel<kMode, kRaw><<<static_cast<int>(grid), kFastWarps * 32, smem, s>>>(img, mx_full, my0, my1, qt, coef, nzmask);
+}
+
+void LaunchF1Fast(const ImageDesc& img, int mx_full, int my0, int my1, bool raw, const QuantTabs& qt,
+                  int16_t* coef, uint64_t* nzmask, cudaStream_t s) {
+  if (mx_full <= 0 || my1 <= my0) return;
+  switch (img.yuv_mode) {
+    case kYuv420:
+      if (raw) LaunchF1FastT<kYuv420, true>(img, mx_full, my0, my1, qt, coef, nzmask, s);
+      else     LaunchF1FastT<kYuv420, false>(img, mx_full, my0, my1, qt, coef, nzmask, s);
+      break;
+    case kYuv444:
+      if (raw) LaunchF1FastT<kYuv444, true>(img, mx_full, my0, my1, qt, coef, nzmask, s);
+      else     LaunchF1FastT<kYuv444, false>(img, mx_full, my0, my1, qt, coef, nzmask, s);
+      break;
+    default:
+      if (raw) LaunchF1FastT<kYuv400, true>(img, mx_full, my0, my1, qt, coef, nzmask, s);
+      else     LaunchF1FastT<kYuv400, false>(img, mx_full, my0, my1, qt, coef, nzmask, s);
+      break;
+  }
+}
+
+void LaunchRequantize(int16_t* coef, uint64_t* nzmask, size_t nb_blocks, int mcu_blocks,
+                      int luma_blocks, const QuantTabs& qt, cudaStream_t s) {
+  requantize_kernel<<<cdiv(nb_blocks, 128), 128, 0, s>>>(coef, nzmask, nb_blocks, mcu_blocks, luma_blocks, qt);
+}
+
+void LaunchHistogram(const int16_t* raw_coef, size_t nb_blocks, int mcu_blocks, int luma_blocks,
+                     int32_t* counts, cudaStream_t s) {
+  static bool init[64] = {false};
+  const size_t smem = 2 * 64 * 128 * sizeof(int32_t);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!init[dev]) {
+    cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    init[dev] = true;
+  }
+  int grid = cdiv(nb_blocks * 8, 256 * 16);
+  if (grid > 148 * 3) grid = 148 * 3;
+  if (grid < 1) grid = 1;
+  histogram_kernel<<<grid, 256, smem, s>>>(raw_coef, nb_blocks, mcu_blocks, luma_blocks, counts);
+}
+
+void LaunchTrellis(int16_t* coef, uint64_t* nzmask, size_t nb_blocks, int mcu_blocks,
+                   int luma_blocks, const QuantTabs& qt, const uint8_t* quant, const CodeTabs* tabs,
+                   cudaStream_t s) {
+  trellis_kernel<<<cdiv(nb_blocks, 64), 64, 0, s>>>(coef, nzmask, nb_blocks, mcu_blocks, luma_blocks, qt, quant, tabs);
+}
+
+void LaunchSymbolStats(const int16_t* zz, const uint64_t* nzmask, size_t nb_blocks, int mcu_blocks,
+                       int luma_blocks, uint32_t* freq, cudaStream_t s) {
+  int grid = cdiv(nb_blocks, kTileBlocks);
+  if (grid > 148 * 8) grid = 148 * 8;
+  symbol_stats_kernel<<<grid, kTileBlocks, 0, s>>>(zz, nzmask, nb_blocks, mcu_blocks, luma_blocks, freq);
+}
+
+void LaunchBlockBits(const int16_t* zz, const uint64_t* nzmask, size_t nb_blocks, int mcu_blocks,
+                     int luma_blocks, const CodeTabs* tabs, uint32_t* block_bits,
+                     uint32_t* tile_sums, cudaStream_t s) {
+  block_bits_kernel<<<cdiv(nb_blocks, kTileBlocks), kTileBlocks, 0, s>>>(zz, nzmask, nb_blocks, mcu_blocks,
+                                                                         luma_blocks, tabs, block_bits, tile_sums);
+}
+
+void LaunchScanTiles(const uint32_t* tile_sums, size_t nb_tiles, unsigned long long* tile_offsets,
+                     StreamInfo* info, cudaStream_t s) {
+  scan_tiles_kernel<<<1, 1024, 0, s>>>(tile_sums, nb_tiles, tile_offsets, info);
+}
+
+void LaunchPack(const int16_t* zz, const uint64_t* nzmask, size_t nb_blocks, int mcu_blocks,
+                int luma_blocks, const CodeTabs* tabs, const uint32_t* block_bits,
+                const unsigned long long* tile_offsets, uint32_t* stream, cudaStream_t s) {
+  pack_kernel<<<cdiv(nb_blocks, kTileBlocks), kTileBlocks, 0, s>>>(zz, nzmask, nb_blocks, mcu_blocks, luma_blocks,
+                                                                   tabs, block_bits, tile_offsets, stream);
+}
+
+void LaunchStuff(uint32_t* stream, size_t max_stream_words, uint32_t* ff_tile_sums,
+                 unsigned long long* ff_tile_offsets, StreamInfo* info, uint8_t* out,
+                 size_t header_len, cudaStream_t s) {
+  size_t tiles = (max_stream_words * 4 + kStuffTileBytes - 1) / kStuffTileBytes;
+  int grid = static_cast<int>(tiles < 148 * 8 ? (tiles ? tiles : 1) : 148 * 8);
+  ff_count_kernel<<<grid, 256, 0, s>>>(stream, info, ff_tile_sums);
+  ff_scan_kernel<<<1, 1024, 0, s>>>(ff_tile_sums, ff_tile_offsets, info, header_len);
+  stuff_kernel<<<grid, 256, 0, s>>>(stream, ff_tile_offsets, info, out + header_len);
+}
+
+}  // namespace sjb

@@ -1,0 +1,460 @@
+// sjpeg_api.cc -- the reference's public entry points (include/sjpeg.h, mirroring
+// /root/reference/src/sjpeg.h and api.cc) implemented on top of the C ABI of the GPU path.
+// Argument checks, ownership (new[] buffers), sink protocol and error returns follow
+// /root/reference/src/api.cc:32-67,145-201; the per-MCU work is in kernels.cu.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/sjpeg.h"
+#include "../../include/sjpeg_b200.h"
+#include "host_codec.h"
+
+namespace {
+
+// One GPU context per host thread: the reference is re-entrant (tests/unit_test.cc:114-131 runs
+// 8 encodes concurrently), so no state is shared between calling threads.
+struct ThreadContext {
+  sjb_context* ctx = nullptr;
+  ~ThreadContext() { sjb_context_destroy(ctx); }
+  sjb_context* get() {
+    if (ctx == nullptr) {
+      const char* dev = getenv("SJPEG_B200_DEVICE");
+      if (sjb_context_create(dev ? atoi(dev) : 0, &ctx) != SJB_OK) ctx = nullptr;
+    }
+    return ctx;
+  }
+};
+thread_local ThreadContext tls_context;
+
+struct DefaultMemory : public sjpeg::MemoryManager {
+  void* Alloc(size_t size) override { return malloc(size); }
+  void Free(void* const ptr) override { free(ptr); }
+} default_memory;
+
+int BytesPerPixel(int fmt) { return fmt == SJB_PIX_RGB ? 3 : 4; }
+
+// api.cc:183-192 + encoders.cc:546-568 + api.cc:145-181, ending in a sink
+bool EncodeToSink(const uint8_t* pix, int width, int height, int stride, int fmt, const sjb_params& params,
+                  sjpeg::ByteSink* sink, sjpeg::MemoryManager* memory) {
+  sink->Reset();                                        // enc.cc:90
+  sjb_context* ctx = tls_context.get();
+  if (ctx == nullptr) return false;
+  if (memory == nullptr) memory = &default_memory;
+  size_t size = 0;
+  int rc = sjb_encode(ctx, pix, 0, width, height, stride, &params, nullptr, 0, 0, &size);
+  if (rc != SJB_ERR_CAPACITY || size == 0) return false;
+  // host staging goes through the caller's memory manager (sjpeg.h:410-415)
+  uint8_t* staging = static_cast<uint8_t*>(memory->Alloc(size));
+  if (staging == nullptr) return false;
+  bool ok = sjb_fetch_output(ctx, staging, 0, size) == SJB_OK;
+  uint8_t* dst = nullptr;
+  ok = ok && sink->Commit(0, size, &dst) && dst != nullptr;
+  if (ok) {
+    memcpy(dst, staging, size);
+    ok = sink->Commit(size, 0, &dst) && sink->Finalize();
+  }
+  memory->Free(staging);
+  if (!ok) sink->Reset();                               // bit_writer.cc:99-105
+  (void)fmt;
+  return ok;
+}
+
+// Encoder::InitFromParam, api.cc:145-181
+bool ParamsFromEncoderParam(const sjpeg::EncoderParam& param, const uint8_t quant[2][64],
+                            const uint8_t min_quant[2][64], bool use_min_quant, int tolerance, int fmt,
+                            sjb_params* out) {
+  memset(out, 0, sizeof(*out));
+  SjpegYUVMode mode = param.yuv_mode;
+  // the riskiness analyser (jpeg_tools.cc:177-236) is not part of this path: AUTO means 4:2:0
+  if (mode == SJPEG_YUV_AUTO) mode = SJPEG_YUV_420;
+  if (mode != SJPEG_YUV_420 && mode != SJPEG_YUV_444 && mode != SJPEG_YUV_400) return false;
+  out->yuv_mode = mode;
+  out->pix_fmt = fmt;
+  for (int i = 0; i < 2; ++i) {
+    sjb::ScaleMatrix(quant[i], 100.f, out->quant[i]);   // enc.cc:106-109
+    if (use_min_quant) sjb::MinMatrixWithTolerance(min_quant[i], tolerance, out->min_quant[i]);
+    else memset(out->min_quant[i], 1, 64);
+  }
+  int method = param.Huffman_compress ? 1 : 0;
+  if (param.adaptive_quantization) method += 3;
+  if (param.use_trellis) method = (method == 4) ? 7 : (method == 6) ? 8 : method;
+  out->method = method;
+  out->q_bias = param.quantization_bias;
+  out->qdelta_max_luma = param.qdelta_max_luma;
+  out->qdelta_max_chroma = param.qdelta_max_chroma;
+  if (out->q_bias < 0 || out->q_bias > 255) return false;
+  // multi-pass search (dichotomy.cc) and metadata chunks (headers.cc:63-180) are outside the path
+  if (param.passes > 1) return false;
+  if (!param.exif.empty() || !param.iccp.empty() || !param.xmp.empty() || !param.app_markers.empty()) return false;
+  return true;
+}
+
+// sinks (bit_writer.h:51-93)
+template <class T>
+class ContainerSink : public sjpeg::ByteSink {
+ public:
+  explicit ContainerSink(T* out) : out_(out), pos_(0) {}
+  bool Commit(size_t used, size_t extra, uint8_t** data) override {
+    pos_ += used;
+    out_->resize(pos_ + extra);
+    if (out_->size() != pos_ + extra) return false;
+    *data = extra ? reinterpret_cast<uint8_t*>(&(*out_)[pos_]) : nullptr;
+    return true;
+  }
+  bool Finalize() override {
+    out_->resize(pos_);
+    return true;
+  }
+  void Reset() override {
+    out_->clear();
+    pos_ = 0;
+  }
+
+ private:
+  T* const out_;
+  size_t pos_;
+};
+
+class NewArraySink : public sjpeg::ByteSink {   // hands over a new[] buffer (api.cc:39,46)
+ public:
+  NewArraySink() : buf_(nullptr), size_(0), cap_(0) {}
+  ~NewArraySink() override { delete[] buf_; }
+  bool Commit(size_t used, size_t extra, uint8_t** data) override {
+    size_ += used;
+    if (size_ + extra > cap_) {
+      uint8_t* nb = new (std::nothrow) uint8_t[size_ + extra];
+      if (nb == nullptr) return false;
+      if (size_) memcpy(nb, buf_, size_);
+      delete[] buf_;
+      buf_ = nb;
+      cap_ = size_ + extra;
+    }
+    *data = buf_ + size_;
+    return true;
+  }
+  bool Finalize() override { return true; }
+  void Reset() override {
+    delete[] buf_;
+    buf_ = nullptr;
+    size_ = cap_ = 0;
+  }
+  size_t Release(uint8_t** out) {
+    *out = buf_;
+    const size_t s = size_;
+    buf_ = nullptr;
+    size_ = cap_ = 0;
+    return s;
+  }
+
+ private:
+  uint8_t* buf_;
+  size_t size_, cap_;
+};
+
+}  // namespace
+
+// friend of EncoderParam: reads its protected matrices (sjpeg.h:262-274)
+namespace sjpeg {
+struct Encoder {
+  static bool Convert(const EncoderParam& p, int fmt, sjb_params* out) {
+    return ParamsFromEncoderParam(p, p.quant_, p.min_quant_, p.use_min_quant_, p.min_quant_tolerance_, fmt, out);
+  }
+};
+}  // namespace sjpeg
+
+// ---------------------------------------------------------------------------------------------
+// plain-C entry points (api.cc:32-67)
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+uint32_t SjpegVersion() { return SJPEG_VERSION; }
+
+size_t SjpegEncode(const uint8_t* rgb, int width, int height, int stride, uint8_t** out_data, float quality,
+                   int method, SjpegYUVMode yuv_mode) {
+  if (rgb == nullptr || out_data == nullptr) return 0;
+  if (width <= 0 || height <= 0 || abs(stride) < 3 * width) return 0;
+  *out_data = nullptr;
+  if (yuv_mode == SJPEG_YUV_AUTO) yuv_mode = SJPEG_YUV_420;   // see ParamsFromEncoderParam
+  if (yuv_mode != SJPEG_YUV_420 && yuv_mode != SJPEG_YUV_444 && yuv_mode != SJPEG_YUV_400) return 0;
+  sjb_params p;
+  sjb_params_default(&p, quality, method, yuv_mode);
+  NewArraySink sink;
+  if (!EncodeToSink(rgb, width, height, stride, SJB_PIX_RGB, p, &sink, nullptr)) return 0;
+  return sink.Release(out_data);
+}
+
+size_t SjpegCompress(const uint8_t* rgb, int width, int height, float quality, uint8_t** out_data) {
+  return SjpegEncode(rgb, width, height, 3 * width, out_data, quality, 4, SJPEG_YUV_AUTO);
+}
+
+void SjpegFreeBuffer(const uint8_t* buffer) { delete[] buffer; }
+
+void SjpegQuantMatrix(float quality, bool for_chroma, uint8_t matrix[64]) {   // jpeg_tools.cc:134-141
+  uint8_t m[2][64];
+  sjb::QualityToMatrices(quality, m);
+  memcpy(matrix, m[for_chroma ? 1 : 0], 64);
+}
+
+float SjpegEstimateQuality(const uint8_t matrix[64], bool for_chroma) {       // jpeg_tools.cc:143-168
+  int best_q = 0;
+  float best = 256.f * 256 * 64 + 1;
+  for (int q = 0; q <= 100; ++q) {
+    uint8_t m[64];
+    SjpegQuantMatrix(static_cast<float>(q), for_chroma, m);
+    float score = 0;
+    for (int i = 0; i < 64 && score <= best; ++i) {
+      const float d = static_cast<float>(m[i]) - matrix[i];
+      score += d * d;
+    }
+    if (score < best) {
+      best = score;
+      best_q = q;
+    }
+  }
+  return static_cast<float>(best_q);
+}
+
+// Walks the marker segments after SOI; returns the offset of the first marker in [lo,hi] or 0.
+static size_t FindMarker(const uint8_t* d, size_t size, int lo, int hi, bool stop_at_sos) {
+  if (d == nullptr || size < 10 || d[0] != 0xff || d[1] != 0xd8) return 0;
+  size_t pos = 2;
+  const size_t end = size - 8;
+  while (pos < end && d[pos] != 0xff) ++pos;
+  while (pos < end) {
+    const int marker = d[pos + 1];
+    if (marker >= lo && marker <= hi) return pos;
+    if (stop_at_sos && marker == 0xda) return 0;
+    pos += 2 + ((d[pos + 2] << 8) | d[pos + 3]);
+  }
+  return 0;
+}
+
+bool SjpegDimensions(const uint8_t* data, size_t size, int* width, int* height, int* is_yuv420) {   // jpeg_tools.cc:52-70
+  const size_t pos = FindMarker(data, size, 0xc0, 0xc1, false);
+  if (pos == 0) return false;
+  const uint8_t* s = data + pos;
+  const size_t left = size - pos;
+  if (left < 11) return false;
+  if (height) *height = (s[5] << 8) | s[6];
+  if (width) *width = (s[7] << 8) | s[8];
+  if (is_yuv420) {
+    const size_t nc = s[9];
+    if (left < 11 + 3 * nc) { *is_yuv420 = (nc == 3); return false; }
+    *is_yuv420 = (nc == 3) && s[11] == 0x22 && s[14] == 0x11 && s[17] == 0x11;
+  }
+  return true;
+}
+
+int SjpegFindQuantizer(const uint8_t* d, size_t size, uint8_t quant[2][64]) {   // jpeg_tools.cc:75-130
+  static const uint8_t zz[64] = SJB_ZIGZAG_INIT;
+  memset(quant, 0, 128);
+  if (d == nullptr || size < 69 || d[0] != 0xff || d[1] != 0xd8) return 0;
+  const size_t end = size - 8;
+  size_t pos = 2;
+  while (pos < end && d[pos] != 0xff) ++pos;
+  int seen = 0;
+  while (pos < end) {
+    const int marker = d[pos + 1];
+    const size_t chunk = 2 + ((d[pos + 2] << 8) | d[pos + 3]);
+    if (pos + chunk > end || marker == 0xda) break;
+    if (marker == 0xdb) {
+      size_t i = 4;
+      while (i + 1 < chunk) {
+        const int pq = d[pos + i] >> 4, tq = d[pos + i] & 15;
+        if (pq > 1 || tq > 3) return 0;
+        const size_t msize = 64 * pq + 65;
+        if (i + msize > chunk) return 0;
+        if (tq < 2) {
+          for (int j = 0; j < 64; ++j) {
+            int v = pq ? ((d[pos + i + 1 + 2 * j] << 8) | d[pos + i + 2 + 2 * j]) : d[pos + i + 1 + j];
+            v = v > 255 ? 255 : v < 1 ? 1 : v;
+            quant[tq][zz[j]] = static_cast<uint8_t>(v);
+          }
+        }
+        seen |= 1 << tq;
+        i += msize;
+      }
+    }
+    pos += chunk;
+  }
+  return __builtin_popcount(seen & 15);
+}
+
+SjpegYUVMode SjpegRiskiness(const uint8_t*, int, int, int, float* risk) {
+  // The chroma-subsampling risk analyser (jpeg_tools.cc:177-236) is not part of this path.
+  if (risk) *risk = 0.f;
+  return SJPEG_YUV_420;
+}
+
+}  // extern "C"
+
+bool SjpegCompress(const uint8_t* rgb, int width, int height, float quality, std::string* output) {
+  if (output == nullptr) return false;
+  sjpeg::EncoderParam param(quality);     // defaults == method 4 + AUTO (api.cc:83-101)
+  return sjpeg::Encode(rgb, width, height, 3 * width, param, output);
+}
+bool SjpegDimensions(const std::string& d, int* w, int* h, int* is420) {
+  return SjpegDimensions(reinterpret_cast<const uint8_t*>(d.data()), d.size(), w, h, is420);
+}
+int SjpegFindQuantizer(const std::string& d, uint8_t quant[2][64]) {
+  return SjpegFindQuantizer(reinterpret_cast<const uint8_t*>(d.data()), d.size(), quant);
+}
+
+// ---------------------------------------------------------------------------------------------
+// C++ API (api.cc:74-307)
+// ---------------------------------------------------------------------------------------------
+namespace sjpeg {
+
+EncoderParam::EncoderParam() : search_hook(nullptr), memory(nullptr) { Init(75.f); }
+EncoderParam::EncoderParam(float quality_factor) : search_hook(nullptr), memory(nullptr) { Init(quality_factor); }
+
+void EncoderParam::Init(float quality_factor) {          // api.cc:83-101
+  Huffman_compress = true;
+  adaptive_quantization = true;
+  use_trellis = false;
+  yuv_mode = SJPEG_YUV_AUTO;
+  quantization_bias = 0x78;
+  qdelta_max_luma = 12;
+  qdelta_max_chroma = 1;
+  adaptive_bias = false;
+  SetLimitQuantization(false);
+  min_quant_tolerance_ = 0;
+  SetQuality(quality_factor);
+  target_mode = TARGET_NONE;
+  target_value = 0;
+  passes = 1;
+  tolerance = 1.;
+  qmin = 0.;
+  qmax = 100.;
+}
+
+void EncoderParam::SetQuality(float quality_factor) { sjb::QualityToMatrices(quality_factor, quant_); }
+
+void EncoderParam::SetQuantization(const uint8_t m[2][64], float reduction) {   // api.cc:109-119
+  if (reduction <= 1.f) reduction = 1.f;
+  if (m == nullptr) return;
+  for (int c = 0; c < 2; ++c) {
+    for (int i = 0; i < 64; ++i) {
+      const int v = static_cast<int>(m[c][i] * 100. / reduction + .5);
+      quant_[c][i] = static_cast<uint8_t>(v > 255 ? 255 : v < 1 ? 1 : v);
+    }
+  }
+}
+
+void EncoderParam::SetLimitQuantization(bool limit_quantization, int min_quant_tolerance) {
+  use_min_quant_ = limit_quantization;
+  if (limit_quantization) SetMinQuantization(quant_, min_quant_tolerance);
+}
+
+void EncoderParam::SetMinQuantization(const uint8_t m[2][64], int min_quant_tolerance) {
+  use_min_quant_ = true;
+  memcpy(min_quant_, m, sizeof(min_quant_));
+  min_quant_tolerance_ = min_quant_tolerance < 0 ? 0 : min_quant_tolerance > 100 ? 100 : min_quant_tolerance;
+}
+
+void EncoderParam::ResetMetadata() {
+  iccp.clear();
+  exif.clear();
+  app_markers.clear();
+  xmp.clear();
+  xmp_split_point = 0u;
+}
+
+static bool EncodePacked(const uint8_t* pix, int width, int height, int stride, int fmt,
+                         const EncoderParam& param, ByteSink* sink) {
+  if (pix == nullptr || sink == nullptr) return false;
+  if (width <= 0 || height <= 0 || abs(stride) < BytesPerPixel(fmt) * width) return false;
+  sjb_params p;
+  if (!Encoder::Convert(param, fmt, &p)) {
+    sink->Reset();
+    return false;
+  }
+  return EncodeToSink(pix, width, height, stride, fmt, p, sink, param.memory);
+}
+
+bool Encode(const uint8_t* rgb, int width, int height, int stride, const EncoderParam& param, ByteSink* sink) {
+  return EncodePacked(rgb, width, height, stride, SJB_PIX_RGB, param, sink);
+}
+
+size_t Encode(const uint8_t* rgb, int width, int height, int stride, const EncoderParam& param,
+              uint8_t** out_data) {
+  if (out_data == nullptr) return 0;
+  NewArraySink sink;
+  if (!Encode(rgb, width, height, stride, param, &sink)) return 0;
+  return sink.Release(out_data);
+}
+
+bool Encode(const uint8_t* rgb, int width, int height, int stride, const EncoderParam& param,
+            std::string* output) {
+  if (output == nullptr) return false;
+  output->clear();
+  ContainerSink<std::string> sink(output);
+  return Encode(rgb, width, height, stride, param, &sink);
+}
+
+bool EncodeBGRA(const uint8_t* bgra, int width, int height, int stride, const EncoderParam& param, ByteSink* sink) {
+  return EncodePacked(bgra, width, height, stride, SJB_PIX_BGRA, param, sink);
+}
+bool EncodeBGRA(const uint8_t* bgra, int width, int height, int stride, const EncoderParam& param,
+                std::string* output) {
+  if (output == nullptr) return false;
+  output->clear();
+  ContainerSink<std::string> sink(output);
+  return EncodeBGRA(bgra, width, height, stride, param, &sink);
+}
+bool EncodeRGBA(const uint8_t* rgba, int width, int height, int stride, const EncoderParam& param, ByteSink* sink) {
+  return EncodePacked(rgba, width, height, stride, SJB_PIX_RGBA, param, sink);
+}
+bool EncodeRGBA(const uint8_t* rgba, int width, int height, int stride, const EncoderParam& param,
+                std::string* output) {
+  if (output == nullptr) return false;
+  output->clear();
+  ContainerSink<std::string> sink(output);
+  return EncodeRGBA(rgba, width, height, stride, param, &sink);
+}
+
+// Other input layouts (encoders.cc:256-541) are outside the accelerated path.
+bool EncodeGray(const uint8_t*, int, int, int, const EncoderParam&, ByteSink*) { return false; }
+bool EncodeGray(const uint8_t*, int, int, int, const EncoderParam&, std::string*) { return false; }
+bool EncodeNV21(const uint8_t*, int, const uint8_t*, int, int, int, const EncoderParam&, ByteSink*) { return false; }
+bool EncodeNV12(const uint8_t*, int, const uint8_t*, int, int, int, const EncoderParam&, ByteSink*) { return false; }
+bool EncodeYUV444(const uint8_t*, int, const uint8_t*, int, const uint8_t*, int, int, int, const EncoderParam&,
+                  ByteSink*) { return false; }
+bool EncodeYUV420(const uint8_t*, int, const uint8_t*, int, const uint8_t*, int, int, int, const EncoderParam&,
+                  ByteSink*) { return false; }
+
+// Search hook (dichotomy.cc:41-75): kept for linkage; the multi-pass search itself is out of scope.
+bool SearchHook::Setup(const EncoderParam& param) {
+  for_size = (param.target_mode == EncoderParam::TARGET_SIZE);
+  target = param.target_value;
+  tolerance = param.tolerance / 100.f;
+  qmin = param.qmin < 0 ? 0 : param.qmin;
+  qmax = param.qmax > 100 ? 100 : (param.qmax < param.qmin ? param.qmin : param.qmax);
+  q = SjpegEstimateQuality(param.GetQuantMatrix(0), false);
+  q = q < qmin ? qmin : q > qmax ? qmax : q;
+  value = 0;
+  pass = 0;
+  return true;
+}
+void SearchHook::NextMatrix(int idx, uint8_t dst[64]) { SjpegQuantMatrix(q, idx != 0, dst); }
+bool SearchHook::Update(float result) {
+  value = result;
+  if (fabsf(value - target) < tolerance * target) return true;
+  if (value > target) qmax = q; else qmin = q;
+  const float last = q;
+  q = (qmin + qmax) / 2.f;
+  return fabsf(q - last) < 0.15f;
+}
+
+std::shared_ptr<ByteSink> MakeByteSink(std::string* output) {
+  return std::shared_ptr<ByteSink>(new (std::nothrow) ContainerSink<std::string>(output));
+}
+template <>
+std::shared_ptr<ByteSink> MakeByteSink(std::vector<uint8_t>* output) {
+  return std::shared_ptr<ByteSink>(new (std::nothrow) ContainerSink<std::vector<uint8_t> >(output));
+}
+
+}  // namespace sjpeg

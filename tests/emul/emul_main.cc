@@ -1,0 +1,213 @@
+// TEST INFRASTRUCTURE: CPU emulation of the kernel pipeline, built from the product's own
+// __host__ __device__ block functions (sjpeg_b200/csrc/block_ops.cuh) and host codec
+// (host_codec.cc) compiled by g++.  It lets the no-GPU test tier check the per-block integer
+// arithmetic, the bit packer / stuffing logic and the host-side table builders against the oracle
+// before anything runs on a B200.  The thread/CTA glue of kernels.cu is NOT covered here -- that is
+// what the -m gpu tests are for.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../sjpeg_b200/csrc/block_ops.cuh"
+#include "../../sjpeg_b200/csrc/host_codec.h"
+
+using namespace sjb;
+
+namespace {
+
+struct Img {
+  const uint8_t* pix; long long stride; int w, h, fmt;
+  void get(int x, int y, int* r, int* g, int* b) const {
+    if (x > w - 1) x = w - 1;
+    if (y > h - 1) y = h - 1;
+    const int ps = fmt == kFmtRGB ? 3 : 4;
+    const uint8_t* p = pix + y * stride + (long long)x * ps;
+    *r = p[fmt == kFmtBGRA ? 2 : 0]; *g = p[1]; *b = p[fmt == kFmtBGRA ? 0 : 2];
+  }
+};
+
+void LumaSamples(const Img& im, int x0, int y0, int (&v)[64]) {
+  for (int y = 0; y < 8; ++y) for (int x = 0; x < 8; ++x) {
+    int r, g, b; im.get(x0 + x, y0 + y, &r, &g, &b); v[8 * y + x] = rgb_to_y(r, g, b);
+  }
+}
+
+// mirrors f1_generic_kernel (kernels.cu) for block k of MCU (mx,my)
+void BlockSamples(const Img& im, int mode, int mx, int my, int k, int (&v)[64]) {
+  if (mode == kYuv420) {
+    const int X = 16 * mx, Y = 16 * my;
+    if (k < 4) {
+      const int sub_w = im.w - X, sub_h = im.h - Y;
+      int src = -1;
+      if (k == 1 && sub_w <= 8) src = 0;
+      if (k >= 2 && sub_h <= 8) src = (sub_w > 8) ? 1 : 0;
+      else if (k == 3 && sub_w <= 8) src = 2;
+      if (src < 0) { LumaSamples(im, X + 8 * (k & 1), Y + 8 * (k >> 1), v); return; }
+      LumaSamples(im, X + 8 * (src & 1), Y + 8 * (src >> 1), v);
+      int sum = 0;
+      for (int i = 0; i < 64; ++i) sum += v[i];
+      for (int i = 0; i < 64; ++i) v[i] = (sum + 32) >> 6;
+    } else {
+      for (int y = 0; y < 8; ++y) for (int x = 0; x < 8; ++x) {
+        int sr = 0, sg = 0, sb = 0;
+        for (int q = 0; q < 4; ++q) {
+          int r, g, b; im.get(X + 2 * x + (q & 1), Y + 2 * y + (q >> 1), &r, &g, &b);
+          sr += r; sg += g; sb += b;
+        }
+        v[8 * y + x] = (k == 4) ? rgb4_to_u(sr, sg, sb) : rgb4_to_v(sr, sg, sb);
+      }
+    }
+  } else {
+    for (int y = 0; y < 8; ++y) for (int x = 0; x < 8; ++x) {
+      int r, g, b; im.get(8 * mx + x, 8 * my + y, &r, &g, &b);
+      v[8 * y + x] = (k == 0) ? rgb_to_y(r, g, b) : (k == 1) ? rgb_to_u(r, g, b) : rgb_to_v(r, g, b);
+    }
+  }
+}
+
+const int kZZ[64] = SJB_ZIGZAG_INIT;
+
+void QuantizeBlock(const int (&v)[64], const QuantTab& t, int16_t* zz, uint64_t* mask) {
+  uint64_t m = 0;
+  for (int i = 0; i < 64; ++i) {
+    const int n = kZZ[i];
+    const int q = quantize_coeff(v[n], t.iq[n], t.cpos[n], t.cneg[n]);
+    zz[i] = (int16_t)q;
+    if (q) m |= 1ull << i;
+  }
+  *mask = m;
+}
+
+int DcPred(const int16_t* zz, size_t g, int k, int mb, int lb) {
+  size_t prev;
+  if (k < lb) { if (k > 0) prev = g - 1; else if (g == 0) return 0; else prev = g - mb + lb - 1; }
+  else { if (g < (size_t)mb) return 0; prev = g - mb; }
+  return zz[prev * 64];
+}
+
+struct Loader { const int16_t* p; int operator()(int i) const { return p[i]; } };
+struct WordOut {
+  std::vector<uint32_t>* w;
+  void or_word(uint64_t i, uint32_t v) { (*w)[i] |= v; }
+  void set_word(uint64_t i, uint32_t v) { (*w)[i] = v; }
+};
+struct Stats {
+  uint32_t* f;
+  void one(int s) { ++f[s]; }
+  void many(int s, int n) { f[s] += n; }
+};
+
+}  // namespace
+
+extern "C" {
+
+// raw (unquantised, natural order) coefficients of the whole picture
+void emul_coeffs(const uint8_t* pix, int w, int h, long long stride, int mode, int fmt, int16_t* out) {
+  FrameGeometry g;
+  if (!MakeGeometry(mode, w, h, &g)) return;
+  Img im = {pix, stride, w, h, fmt};
+  for (int my = 0; my < g.mcus_y; ++my) for (int mx = 0; mx < g.mcus_x; ++mx) for (int k = 0; k < g.mcu_blocks; ++k) {
+    int v[64];
+    BlockSamples(im, mode, mx, my, k, v);
+    fdct64(v);
+    for (int i = 0; i < 64; ++i) *out++ = (int16_t)v[i];
+  }
+}
+
+void emul_default_ac_syms(int chroma, uint8_t* bits, uint8_t* syms, int* n) {
+  HuffSpec s; DefaultHuffSpec(true, chroma, &s);
+  memcpy(bits, s.bits, 16); memcpy(syms, s.syms, s.nb_syms); *n = s.nb_syms;
+}
+
+// full pipeline, methods 0..6 (no trellis).  Returns size; *out malloc()ed.
+size_t emul_encode(const uint8_t* pix, int w, int h, long long stride, int mode, int fmt, int method,
+                   const uint8_t* quant_in /*[2][64]*/, int q_bias, int qdl, int qdc, uint8_t** out) {
+  FrameGeometry g;
+  if (!MakeGeometry(mode, w, h, &g)) return 0;
+  method = method < 0 ? 0 : method > 8 ? 8 : method;
+  if (method >= 7) return 0;
+  const bool adaptive = method >= 3, optimize = method != 0 && method != 3;
+  Img im = {pix, stride, w, h, fmt};
+  uint8_t quant[2][64], minq[2][64];
+  memcpy(quant, quant_in, 128);
+  memset(minq, 1, 128);
+  QuantTabs qt;
+  for (int i = 0; i < 2; ++i) if (!FinalizeQuantizer(quant[i], minq[i], q_bias, &qt.m[i])) return 0;
+  const size_t nb = g.nb_blocks();
+  std::vector<int16_t> raw(nb * 64), zz(nb * 64);
+  std::vector<uint64_t> mask(nb);
+  emul_coeffs(pix, w, h, stride, mode, fmt, raw.data());
+  (void)im;
+  if (adaptive) {
+    std::vector<int32_t> counts(2 * 64 * kHistoStride, 0);
+    for (size_t b = 0; b < nb; ++b) {
+      const int m = ((int)(b % g.mcu_blocks) >= g.luma_blocks) ? 1 : 0;
+      for (int i = 0; i < 64; ++i) {
+        const int a = abs(raw[b * 64 + i]) >> 2;
+        if (a < 128) ++counts[(m * 64 + i) * kHistoStride + a];
+      }
+    }
+    AnalyseHistograms(counts.data(), g.nb_comps, quant, minq, qdl, qdc);
+    for (int i = (g.nb_comps > 1 ? 1 : 0); i >= 0; --i) if (!FinalizeQuantizer(quant[i], minq[i], q_bias, &qt.m[i])) return 0;
+  }
+  for (size_t b = 0; b < nb; ++b) {
+    int v[64];
+    for (int i = 0; i < 64; ++i) v[i] = raw[b * 64 + i];
+    QuantizeBlock(v, qt.m[((int)(b % g.mcu_blocks) >= g.luma_blocks) ? 1 : 0], &zz[b * 64], &mask[b]);
+  }
+  HuffSpec spec[4];
+  for (int i = 0; i < 4; ++i) DefaultHuffSpec(i >= 2, i & 1, &spec[i]);
+  if (optimize) {
+    uint32_t freq[2][272];
+    memset(freq, 0, sizeof(freq));
+    for (size_t b = 0; b < nb; ++b) {
+      const int k = (int)(b % g.mcu_blocks), c = k >= g.luma_blocks;
+      Stats st = {freq[c]};
+      block_symbol_stats(Loader{&zz[b * 64]}, mask[b], zz[b * 64], DcPred(zz.data(), b, k, g.mcu_blocks, g.luma_blocks), st);
+    }
+    for (int c = 0; c < (g.nb_comps == 1 ? 1 : 2); ++c) {
+      OptimalHuffSpec(freq[c] + 256, 12, &spec[c]);
+      OptimalHuffSpec(freq[c], 256, &spec[2 + c]);
+    }
+  }
+  CodeTabs tabs;
+  memset(&tabs, 0, sizeof(tabs));
+  for (int c = 0; c < 2; ++c) { CodesFromSpec(spec[c], tabs.dc[c]); CodesFromSpec(spec[2 + c], tabs.ac[c]); }
+  std::vector<uint8_t> file;
+  AppendHeaders(g, quant, spec, &file);
+  // E1 + scan
+  std::vector<uint64_t> offs(nb + 1, 0);
+  for (size_t b = 0; b < nb; ++b) {
+    const int k = (int)(b % g.mcu_blocks), c = k >= g.luma_blocks;
+    BitCountSink s = {0};
+    code_block(Loader{&zz[b * 64]}, mask[b], zz[b * 64], DcPred(zz.data(), b, k, g.mcu_blocks, g.luma_blocks), tabs.dc[c], tabs.ac[c], s);
+    offs[b + 1] = offs[b] + s.total;
+  }
+  const uint64_t total_bits = offs[nb];
+  std::vector<uint32_t> words(total_bits / 32 + 8, 0);
+  WordOut wo = {&words};
+  for (size_t b = nb; b-- > 0;) {   // reverse order on purpose: packing must not depend on order
+    const int k = (int)(b % g.mcu_blocks), c = k >= g.luma_blocks;
+    BitPackSink<WordOut> s(wo, offs[b]);
+    code_block(Loader{&zz[b * 64]}, mask[b], zz[b * 64], DcPred(zz.data(), b, k, g.mcu_blocks, g.luma_blocks), tabs.dc[c], tabs.ac[c], s);
+    s.finish();
+  }
+  const uint64_t nbytes = (total_bits + 7) >> 3;
+  const unsigned pad = (unsigned)((0 - total_bits) & 7);
+  for (uint64_t i = 0; i < nbytes; ++i) {
+    uint32_t byte = (words[i >> 2] >> (8 * (3 - (i & 3)))) & 0xff;
+    if (i == nbytes - 1 && pad) byte |= (1u << pad) - 1;
+    file.push_back((uint8_t)byte);
+    if (byte == 0xff) file.push_back(0);
+  }
+  file.push_back(0xff); file.push_back(0xd9);
+  *out = (uint8_t*)malloc(file.size());
+  memcpy(*out, file.data(), file.size());
+  return file.size();
+}
+
+void emul_free(uint8_t* p) { free(p); }
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+"""GPU tier: the CUDA path, called through the C ABI (include/sjpeg_b200.h) and through the
+drop-in SjpegEncode() symbol, against the oracle on the same inputs -- bit-exact (integer
+pipeline) -- and against the committed golden md5s of the compiled reference at full size."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_md5.json")))
+MODES = {O.YUV_420: (16, 6), O.YUV_444: (8, 3), O.YUV_400: (8, 1)}
+
+
+def _nb(w, h, mode):
+    mcu, mb = MODES[mode]
+    return ((w + mcu - 1) // mcu) * ((h + mcu - 1) // mcu), mb
+
+
+def _oracle_coeffs(rgb, w, h, stride, mode, fmt=0):
+    nm, mb = _nb(w, h, mode)
+    out = np.zeros((nm * mb, 64), np.int16)
+    O.oracle().sjo_image_to_coeffs(rgb.ctypes.data, w, h, stride, mode, fmt, out.ctypes.data)
+    return out
+
+
+def _oracle_quantised(coeffs, w, h, mode, params):
+    nm, mb = _nb(w, h, mode)
+    out = np.zeros_like(coeffs)
+    q = np.frombuffer(bytes(params.quant), np.uint8).copy()
+    mq = np.frombuffer(bytes(params.min_quant), np.uint8).copy()
+    O.oracle().sjo_quantize_image(coeffs.ctypes.data, nm, mode, q.ctypes.data, mq.ctypes.data,
+                                  params.q_bias, out.ctypes.data)
+    return out
+
+
+def _images(w, h, seed=11):
+    rng = np.random.RandomState(seed)
+    yield "genA", O.make_rgb("A", w, h)
+    yield "genB", O.make_rgb("B", w, h)
+    yield "binary", (rng.randint(0, 2, (h, w, 3)) * 255).astype(np.uint8)
+    yield "noise", rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+
+
+SIZES = [(512, 512), (203, 117), (1, 1), (8, 8), (17, 9), (640, 360), (1920, 1080), (48, 1000), (1000, 16)]
+
+
+@pytest.mark.parametrize("mode", [O.YUV_420, O.YUV_444, O.YUV_400])
+@pytest.mark.parametrize("size", SIZES, ids=lambda s: "%dx%d" % s)
+def test_f1_coefficients_bit_exact(gpu_ctx, size, mode):
+    """fused convert + fDCT (+ quantise) kernel vs oracle stage dumps"""
+    import sjpeg_b200 as S
+    w, h = size
+    for name, rgb in _images(w, h):
+        p = S.default_params(75, 0, mode)
+        want = _oracle_coeffs(rgb, w, h, 3 * w, mode)
+        got, _ = gpu_ctx.coefficients(rgb, w, h, 3 * w, p, quantise=False)
+        assert np.array_equal(got, want), (name, "raw")
+        for q in (75, 97):
+            p = S.default_params(q, 0, mode)
+            wantq = _oracle_quantised(want, w, h, mode, p)
+            gotq, mask = gpu_ctx.coefficients(rgb, w, h, 3 * w, p, quantise=True)
+            assert np.array_equal(gotq, wantq), (name, "quantised", q)
+            nz = (wantq != 0)
+            bits = np.zeros(len(nz), np.uint64)
+            for i in range(1, 64):
+                bits |= nz[:, i].astype(np.uint64) << np.uint64(i)
+            assert np.array_equal(mask & ~np.uint64(1), bits), (name, "mask")
+
+
+@pytest.mark.parametrize("mode", [O.YUV_420, O.YUV_444, O.YUV_400])
+@pytest.mark.parametrize("method", list(range(9)))
+def test_whole_file_bit_exact_small(gpu_ctx, method, mode):
+    import sjpeg_b200 as S
+    for (w, h) in ((203, 117), (1, 1), (16, 16), (17, 9), (512, 512), (7, 33)):
+        for name, rgb in _images(w, h):
+            for q in (0, 50, 75, 93, 100):
+                p = S.default_params(q, method, mode)
+                got = gpu_ctx.encode(rgb, w, h, 3 * w, p)
+                want = O.oracle_encode(rgb, w, h, 3 * w, float(q), method, mode)
+                assert got == want, (w, h, name, q, method, mode, len(got), len(want))
+
+
+def test_strides_and_alignment(gpu_ctx):
+    """padded, unaligned and negative strides (reference tests: unit_test.cc:246-342)"""
+    import sjpeg_b200 as S
+    w, h = 320, 240
+    rgb = O.make_rgb("A", w, h)
+    for mode in (O.YUV_420, O.YUV_444, O.YUV_400):
+        p = S.default_params(75, 0, mode)
+        want = O.oracle_encode(rgb, w, h, 3 * w, 75.0, 0, mode)
+        for pad in (0, 1, 16, 37, 4000):
+            buf = np.full((h, 3 * w + pad), 0x5A, np.uint8)
+            buf[:, :3 * w] = rgb.reshape(h, 3 * w)
+            assert gpu_ctx.encode(buf, w, h, 3 * w + pad, p) == want, (mode, pad)
+        # one byte of misalignment of the base pointer
+        flat = np.zeros(rgb.size + 1, np.uint8)
+        flat[1:] = rgb.ravel()
+        assert gpu_ctx.encode(flat, w, h, 3 * w, p, base=flat.ctypes.data + 1) == want
+        # bottom-up picture
+        base = rgb.ctypes.data + (h - 1) * 3 * w
+        flipped = np.ascontiguousarray(rgb[::-1])
+        assert gpu_ctx.encode(rgb, w, h, -3 * w, p, base=base) == \
+            O.oracle_encode(flipped, w, h, 3 * w, 75.0, 0, mode)
+
+
+def test_rgba_bgra_inputs(gpu_ctx):
+    import sjpeg_b200 as S
+    w, h = 203, 117
+    rgb = O.make_rgb("A", w, h)
+    want = {m: O.oracle_encode(rgb, w, h, 3 * w, 75.0, 4, m) for m in (O.YUV_420, O.YUV_444, O.YUV_400)}
+    rgba = np.dstack([rgb, np.full((h, w, 1), 77, np.uint8)]).copy()
+    bgra = np.ascontiguousarray(rgba[:, :, [2, 1, 0, 3]])
+    for mode in want:
+        p = S.default_params(75, 4, mode)
+        p.pix_fmt = S.PIX_RGBA
+        assert gpu_ctx.encode(rgba, w, h, 4 * w, p) == want[mode]
+        p.pix_fmt = S.PIX_BGRA
+        assert gpu_ctx.encode(bgra, w, h, 4 * w, p) == want[mode]
+
+
+def test_invalid_arguments_are_refused(gpu_ctx):
+    """api.cc:35-36, enc.cc:406-408, unit_test.cc:165-185,393-410"""
+    import sjpeg_b200 as S
+    rgb = O.make_rgb("A", 16, 16)
+    p = S.default_params(75, 0, S.YUV_420)
+    assert gpu_ctx.encode(rgb, 0, 16, 48, p) is None
+    assert gpu_ctx.encode(rgb, 16, 0, 48, p) is None
+    assert gpu_ctx.encode(rgb, 16, 16, 47, p) is None
+    assert gpu_ctx.encode(rgb, 65536, 1, 3 * 65536, p) is None
+    p.yuv_mode = 9
+    assert gpu_ctx.encode(rgb, 16, 16, 48, p) is None
+    assert S.sjpeg_encode(rgb, 16, 16, 47, 75, 0, S.YUV_420) is None
+    assert S.sjpeg_encode(rgb, 16, 16, 48, 75, 0, 9) is None
+    # method is clamped, not refused (unit_test.cc:605-623)
+    a = S.sjpeg_encode(rgb, 16, 16, 48, 75, -1, S.YUV_420)
+    b = S.sjpeg_encode(rgb, 16, 16, 48, 75, 0, S.YUV_420)
+    c = S.sjpeg_encode(rgb, 16, 16, 48, 75, 9, S.YUV_420)
+    d = S.sjpeg_encode(rgb, 16, 16, 48, 75, 8, S.YUV_420)
+    assert a == b and c == d
+
+
+def test_large_dimension_limits(gpu_ctx):
+    """65535 is legal, 65536 is not (unit_test.cc:393-410)"""
+    import sjpeg_b200 as S
+    w, h = 65535, 3
+    rgb = np.zeros((h, w, 3), np.uint8)
+    rgb[:, ::7] = 200
+    p = S.default_params(75, 0, S.YUV_420)
+    assert gpu_ctx.encode(rgb, w, h, 3 * w, p) == O.oracle_encode(rgb, w, h, 3 * w, 75.0, 0, O.YUV_420)
+    rgb2 = np.ascontiguousarray(rgb.transpose(1, 0, 2))
+    assert gpu_ctx.encode(rgb2, h, w, 3 * h, p) == O.oracle_encode(rgb2, h, w, 3 * h, 75.0, 0, O.YUV_420)
+
+
+def test_stage_histogram_and_symbol_stats(gpu_ctx):
+    import sjpeg_b200 as S
+    for (w, h) in ((203, 117), (512, 512)):
+        rgb = O.make_rgb("A", w, h)
+        for mode in (O.YUV_420, O.YUV_444, O.YUV_400):
+            nm, mb = _nb(w, h, mode)
+            p = S.default_params(75, 4, mode)
+            coeffs = _oracle_coeffs(rgb, w, h, 3 * w, mode)
+            want = np.zeros((2, 64, 129), np.int32)
+            O.oracle().sjo_collect_histograms(coeffs.ctypes.data, nm, mode, want.ctypes.data)
+            got = gpu_ctx.histogram(rgb, w, h, 3 * w, p)
+            assert np.array_equal(got[:, :, :128], want[:, :, :128])
+            zz = _oracle_quantised(coeffs, w, h, mode, p)
+            want_ac = np.zeros((2, 256), np.uint32)
+            want_dc = np.zeros((2, 12), np.uint32)
+            O.oracle().sjo_symbol_stats(zz.ctypes.data, nm, mode, want_ac.ctypes.data, want_dc.ctypes.data)
+            ac, dc = gpu_ctx.symbol_stats(rgb, w, h, 3 * w, p)
+            assert np.array_equal(ac, want_ac) and np.array_equal(dc, want_dc)
+
+
+GOLD_GPU = [c for c in GOLD["cases"]]
+
+
+@pytest.mark.parametrize("case", GOLD_GPU, ids=lambda c: "%s_%dx%d_q%d_m%d_y%d" % (
+    c["gen"], c["w"], c["h"], c["quality"], c["method"], c["yuv_mode"]))
+def test_golden_md5_full_size(gpu_ctx, case):
+    """BASELINE.json configs 1-4 at full size: md5 of the compiled reference's own output"""
+    import sjpeg_b200 as S
+    w, h = case["w"], case["h"]
+    rgb = O.make_rgb(case["gen"], w, h, case["seed"])
+    data = S.sjpeg_encode(rgb, w, h, 3 * w, case["quality"], case["method"], case["yuv_mode"])
+    assert data is not None
+    assert len(data) == case["size"]
+    assert O.md5(data) == case["md5"]
+
+
+def test_config5_batch_of_frames(gpu_ctx):
+    """64 x 1080p (clipped bottom MCU row), batch API; digest of digests of the reference"""
+    import sjpeg_b200 as S
+    c5 = GOLD["config5"]
+    w, h, n = c5["w"], c5["h"], c5["frames"]
+    frames = [O.make_rgb("B", w, h, 7654321 + f) for f in range(n)]
+    p = S.default_params(75, 0, S.YUV_420)
+    cap = 1 << 20
+    outs = [np.empty(cap, np.uint8) for _ in range(n)]
+    sizes = gpu_ctx.encode_batch([f.ctypes.data for f in frames], False, w, h, 3 * w, p,
+                                 [o.ctypes.data for o in outs], False, cap)
+    digests = [O.md5(outs[i][:sizes[i]].tobytes()) for i in range(n)]
+    assert digests == c5["frame_md5"]
+    assert sum(sizes) == c5["total_size"]
+    assert O.md5("".join(digests).encode()) == c5["md5_of_md5s"]
+
+
+def test_repeated_encodes_are_stable(gpu_ctx):
+    """self-cleaning bit buffer + cached tables: alternate sizes / methods on one context"""
+    import sjpeg_b200 as S
+    cases = [(512, 512, 0, O.YUV_420), (203, 117, 4, O.YUV_444), (512, 512, 1, O.YUV_420), (64, 64, 7, O.YUV_400)]
+    for _ in range(3):
+        for (w, h, m, mode) in cases:
+            rgb = O.make_rgb("A", w, h)
+            assert gpu_ctx.encode(rgb, w, h, 3 * w, S.default_params(75, m, mode)) == \
+                O.oracle_encode(rgb, w, h, 3 * w, 75.0, m, mode)

@@ -1,0 +1,118 @@
+"""CPU tier: the product's own host code and per-block __host__ __device__ functions
+(sjpeg_b200/csrc/block_ops.cuh, host_codec.cc) compiled by g++ into a CPU emulation of the kernel
+pipeline (tests/emul) and compared with the oracle; plus the C-ABI library's load/exports."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL_DIR = os.path.join(ROOT, "tests", "emul")
+_u8p = C.POINTER(C.c_uint8)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(EMUL_DIR, "libemul.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so,
+                    os.path.join(EMUL_DIR, "emul_main.cc"),
+                    os.path.join(ROOT, "sjpeg_b200", "csrc", "host_codec.cc")], check=True)
+    E = C.CDLL(so)
+    E.emul_encode.restype = C.c_size_t
+    E.emul_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                              C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(_u8p)]
+    E.emul_free.argtypes = [_u8p]
+    E.emul_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p]
+    return E
+
+
+def _emul_encode(E, rgb, w, h, q, m, mode):
+    quant = np.zeros((2, 64), np.uint8)
+    O.oracle().sjo_quality_to_matrices(q, quant.ctypes.data)
+    out = _u8p()
+    n = E.emul_encode(rgb.ctypes.data, w, h, 3 * w, mode, 0, m, quant.ctypes.data, 0x78, 12, 1, C.byref(out))
+    data = C.string_at(out, n)
+    E.emul_free(out)
+    return data
+
+
+def test_block_functions_and_host_codec_match_oracle(emul):
+    rng = np.random.RandomState(3)
+    for (w, h) in ((203, 117), (1, 1), (17, 9), (64, 48), (7, 33), (256, 128)):
+        imgs = [O.make_rgb("A", w, h), O.make_rgb("B", w, h),
+                (rng.randint(0, 2, (h, w, 3)) * 255).astype(np.uint8),
+                rng.randint(0, 256, (h, w, 3)).astype(np.uint8)]
+        for rgb in imgs:
+            for q in (0, 25, 75, 93, 100):
+                for mode in (O.YUV_420, O.YUV_444, O.YUV_400):
+                    for m in (0, 1, 3, 4):
+                        assert _emul_encode(emul, rgb, w, h, float(q), m, mode) == \
+                            O.oracle_encode(rgb, w, h, 3 * w, float(q), m, mode), (w, h, q, mode, m)
+
+
+def test_raw_coefficients_match_oracle(emul):
+    w, h = 203, 117
+    rgb = (np.random.RandomState(5).randint(0, 2, (h, w, 3)) * 255).astype(np.uint8)   # extreme swings
+    for mode, mcu, mb in ((O.YUV_420, 16, 6), (O.YUV_444, 8, 3), (O.YUV_400, 8, 1)):
+        nb = ((w + mcu - 1) // mcu) * ((h + mcu - 1) // mcu) * mb
+        a = np.zeros((nb, 64), np.int16)
+        b = np.zeros((nb, 64), np.int16)
+        emul.emul_coeffs(rgb.ctypes.data, w, h, 3 * w, mode, 0, a.ctypes.data)
+        O.oracle().sjo_image_to_coeffs(rgb.ctypes.data, w, h, 3 * w, mode, 0, b.ctypes.data)
+        assert np.array_equal(a, b)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import sjpeg_b200
+    L = sjpeg_b200.lib()
+    header = open(os.path.join(ROOT, "include", "sjpeg_b200.h")).read()
+    declared = set(re.findall(r"\b(sjb_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared <= set(sjpeg_b200.exported_symbols())
+    assert L.sjb_version() == 0x000101 == L.SjpegVersion()
+    # C entry points of include/sjpeg.h
+    for name in ("SjpegEncode", "SjpegCompress", "SjpegFreeBuffer", "SjpegDimensions", "SjpegFindQuantizer",
+                 "SjpegEstimateQuality", "SjpegQuantMatrix", "SjpegRiskiness"):
+        assert hasattr(L, name), name
+
+
+def test_host_helpers_without_gpu():
+    import sjpeg_b200
+    L = sjpeg_b200.lib()
+    for q in (0, 10, 50, 75, 93, 100):
+        p = sjpeg_b200.default_params(q, 4, sjpeg_b200.YUV_420)
+        ref = np.zeros((2, 64), np.uint8)
+        O.oracle().sjo_quality_to_matrices(float(q), ref.ctypes.data)
+        assert bytes(p.quant[0]) == ref[0].tobytes() and bytes(p.quant[1]) == ref[1].tobytes()
+        m = np.zeros(64, np.uint8)
+        L.SjpegQuantMatrix(float(q), False, m.ctypes.data)
+        assert m.tobytes() == ref[0].tobytes()
+        assert L.SjpegEstimateQuality(m.ctypes.data, False) == pytest.approx(q if q > 0 else 0, abs=1)
+    # parsers on an oracle-made file
+    data = O.oracle_encode(O.make_rgb("A", 33, 21), 33, 21, 99, 75.0, 0, O.YUV_420)
+    w, h, is420 = C.c_int(), C.c_int(), C.c_int()
+    assert L.SjpegDimensions(data, len(data), C.byref(w), C.byref(h), C.byref(is420))
+    assert (w.value, h.value, is420.value) == (33, 21, 1)
+    qm = np.zeros((2, 64), np.uint8)
+    assert L.SjpegFindQuantizer(data, len(data), qm.ctypes.data) == 2
+    ref = np.zeros((2, 64), np.uint8)
+    O.oracle().sjo_quality_to_matrices(75.0, ref.ctypes.data)
+    assert np.array_equal(qm, ref)
+
+
+def test_no_silent_cpu_fallback():
+    """Without a device the compute entry points must fail loudly, never produce bytes."""
+    import sjpeg_b200
+    if sjpeg_b200.lib().sjb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(sjpeg_b200.SjpegB200Error):
+        sjpeg_b200.Context(0)
+    rgb = O.make_rgb("A", 16, 16)
+    assert sjpeg_b200.sjpeg_encode(rgb, 16, 16, 48, 75, 0, sjpeg_b200.YUV_420) is None
