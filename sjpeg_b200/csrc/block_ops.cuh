@@ -22,15 +22,17 @@ namespace sjb {
 enum { kYuv420 = 1, kYuv444 = 3, kYuv400 = 4 };   // numbering of sjpeg.h:54-60
 enum { kFmtRGB = 0, kFmtBGRA = 1, kFmtRGBA = 2 };
 
-// Per-matrix quantiser constants, natural coefficient order.  For a coefficient x:
-//   q = (x * iq + (x < 0 ? cneg : cpos)) >> 20        (arithmetic shift)
-// equals sign(x) * (((|x| + bias) * iquant) >> 16 >> 4) of quantize.cc:116-121, with
-// cpos = bias*iquant and cneg = 2^20 - 1 - cpos; and q != 0 <=> |x| >= qthresh (quantize.cc:144-147),
-// so the reference's threshold test needs no separate compare.
+// Per-matrix quantiser constants.  For a coefficient x, with
+// s = x >> 31 (0 or -1):
+//   q = ((x * iq + (cpos ^ s)) >> 20) - s             (arithmetic shift)
+// equals sign(x) * (((|x| + bias) * iquant) >> 16 >> 4) of quantize.cc:116-121, where
+// cpos = bias * iquant: for x < 0 the addend becomes -cpos - 1 and the "+1" after the shift turns
+// the floor into the ceiling that negating the magnitude quotient needs.  q != 0 <=> |x| >= qthresh
+// (quantize.cc:144-147), so the reference's threshold test needs no separate compare.
+// Entries are stored by ZIG-ZAG position (entry i belongs to natural index zigzag[i]) as
+// {iq, cpos} pairs, so that two consecutive output coefficients share one 16-byte load.
 struct QuantTab {
-  int32_t iq[64];
-  int32_t cpos[64];
-  int32_t cneg[64];
+  int32_t e[64][2];
 };
 struct QuantTabs {
   QuantTab m[2];   // 0 = luma, 1 = chroma
@@ -151,8 +153,9 @@ SJB_HD void fdct64(int (&v)[64]) {
 // ---------------------------------------------------------------------------------------------
 // quantiser (see QuantTab)
 // ---------------------------------------------------------------------------------------------
-SJB_HD int quantize_coeff(int x, int iq, int cpos, int cneg) {
-  return (x * iq + (x < 0 ? cneg : cpos)) >> 20;
+SJB_HD int quantize_coeff(int x, int iq, int cpos) {
+  const int s = x >> 31;
+  return ((x * iq + (cpos ^ s)) >> 20) - s;
 }
 
 // number of bits of v >= 0 (0 for v == 0); sjpegi.h:186-198
@@ -181,14 +184,44 @@ SJB_HD void size_and_bits(int v, int* n, uint32_t* bits) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Block -> Huffman symbols.  zz = 64 quantised values in zig-zag order, nzmask bit i set when
-// zz[i] != 0 (bit 0 ignored), dc_pred = quantised DC of the previous block of the same component.
-// Sink receives (code_bits, length) in stream order; the two uses are bit counting and packing.
-// Follows entropy.cc:161-198 (CodeBlock) with run/levels recomputed on the fly as
+// Block -> Huffman symbols.  The block is 64 quantised int16 in zig-zag order, seen as 32 words
+// (word p = positions 2p, 2p+1, little endian); pairmask bit p is set when word p is non-zero
+// (word 0 also holds the DC).  dc_pred = quantised DC of the previous block of the same
+// component.  Sink receives (code_bits, length) in stream order; the two uses are bit counting
+// and packing.  Follows entropy.cc:161-198 (CodeBlock) with run/levels recomputed on the fly as
 // quantize.cc:288-320 emits them.
 // ---------------------------------------------------------------------------------------------
-template <class Load, class Sink>
-SJB_HD void code_block(Load load_coeff, uint64_t nzmask, int dc, int dc_pred, const uint32_t* dc_codes,
+template <class Sink>
+struct AcEmitter {
+  Sink& sink;
+  const uint32_t* ac_codes;
+  int prev;   // zig-zag position of the previous non-zero coefficient (0 = DC slot)
+  SJB_HD void emit(int pos, int v) {
+    int run = pos - prev - 1;
+    prev = pos;
+    const uint32_t zrl = ac_codes[0xf0];
+    while (run >= 16) {                    // ZRL escapes, entropy.cc:176-179
+      sink.put(zrl >> 16, (int)(zrl & 0xff));
+      run -= 16;
+    }
+    int n;
+    uint32_t bits;
+    size_and_bits(v, &n, &bits);
+    const uint32_t c = ac_codes[(run << 4) | n];
+    sink.put(((c >> 16) << n) | bits, (int)(c & 0xff) + n);
+  }
+};
+
+SJB_HD int find_first_set32(uint32_t m) {   // index of lowest set bit, m != 0
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)m) - 1;
+#else
+  return __builtin_ctz(m);
+#endif
+}
+
+template <class LoadWord, class Sink>
+SJB_HD void code_block(LoadWord load_word, uint32_t pairmask, int dc, int dc_pred, const uint32_t* dc_codes,
                        const uint32_t* ac_codes, Sink& sink) {
   {
     const int diff = dc - dc_pred;
@@ -199,25 +232,17 @@ SJB_HD void code_block(Load load_coeff, uint64_t nzmask, int dc, int dc_pred, co
     // code then n suffix bits; at most 16 + 11 bits
     sink.put(((c >> 16) << n) | bits, (int)(c & 0xff) + n);
   }
-  uint64_t m = nzmask & ~1ull;
-  int prev = 0;   // zig-zag position of the previous non-zero coefficient (0 = DC slot)
+  AcEmitter<Sink> ac = {sink, ac_codes, 0};
+  uint32_t m = pairmask;
   while (m) {
-    const int i = find_first_set64(m);
+    const int p = find_first_set32(m);
     m &= m - 1;
-    int run = i - prev - 1;
-    prev = i;
-    const uint32_t zrl = ac_codes[0xf0];
-    while (run >= 16) {                    // ZRL escapes, entropy.cc:176-179
-      sink.put(zrl >> 16, (int)(zrl & 0xff));
-      run -= 16;
-    }
-    int n;
-    uint32_t bits;
-    size_and_bits(load_coeff(i), &n, &bits);
-    const uint32_t c = ac_codes[(run << 4) | n];
-    sink.put(((c >> 16) << n) | bits, (int)(c & 0xff) + n);
+    const uint32_t w = load_word(p);
+    const int lo = (int16_t)(w & 0xffffu), hi = (int32_t)w >> 16;
+    if (p > 0 && lo != 0) ac.emit(2 * p, lo);
+    if (hi != 0) ac.emit(2 * p + 1, hi);
   }
-  if (prev < 63) {                         // EOB, entropy.cc:195-197
+  if (ac.prev < 63) {                      // EOB, entropy.cc:195-197
     const uint32_t c = ac_codes[0x00];
     sink.put(c >> 16, (int)(c & 0xff));
   }
@@ -230,24 +255,30 @@ struct BitCountSink {
 
 // symbol statistics of a block (entropy.cc:208-227); Add(table_slot) where slot < 256 is an AC
 // symbol and 256 + n a DC size.
-template <class Load, class Add>
-SJB_HD void block_symbol_stats(Load load_coeff, uint64_t nzmask, int dc, int dc_pred, Add& add) {
+template <class LoadWord, class Add>
+SJB_HD void block_symbol_stats(LoadWord load_word, uint32_t pairmask, int dc, int dc_pred, Add& add) {
   {
     const int diff = dc - dc_pred;
     const int m = diff >> 31;
     add.one(256 + bit_length((uint32_t)((diff ^ m) - m)));
   }
-  uint64_t m = nzmask & ~1ull;
+  uint32_t m = pairmask;
   int prev = 0;
   while (m) {
-    const int i = find_first_set64(m);
+    const int p = find_first_set32(m);
     m &= m - 1;
-    const int run = i - prev - 1;
-    prev = i;
-    if (run >> 4) add.many(0xf0, run >> 4);
-    const int v = load_coeff(i);
-    const int s = v >> 31;
-    add.one(((run & 15) << 4) | bit_length((uint32_t)((v ^ s) - s)));
+    const uint32_t w = load_word(p);
+    const int v2[2] = {(int16_t)(w & 0xffffu), (int32_t)w >> 16};
+    for (int e = (p == 0) ? 1 : 0; e < 2; ++e) {
+      const int v = v2[e];
+      if (v == 0) continue;
+      const int pos = 2 * p + e;
+      const int run = pos - prev - 1;
+      prev = pos;
+      if (run >> 4) add.many(0xf0, run >> 4);
+      const int s = v >> 31;
+      add.one(((run & 15) << 4) | bit_length((uint32_t)((v ^ s) - s)));
+    }
   }
   if (prev < 63) add.one(0x00);
 }

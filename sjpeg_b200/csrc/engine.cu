@@ -153,7 +153,7 @@ int MakePlan(sjb_context* ctx, int width, int height, long long stride, const sj
 int ReserveLane(sjb_context* ctx, Lane* L, const Plan& plan) {
   const size_t nb = plan.g.nb_blocks();
   CU(L->coef.Reserve(nb * 64 * sizeof(int16_t)));
-  CU(L->nzmask.Reserve(nb * sizeof(uint64_t)));
+  CU(L->nzmask.Reserve(nb * sizeof(uint32_t)));
   CU(L->block_bits.Reserve(nb * sizeof(uint32_t)));
   CU(L->tile_sums.Reserve(plan.nb_tiles * sizeof(uint32_t)));
   CU(L->tile_offsets.Reserve(plan.nb_tiles * sizeof(unsigned long long)));
@@ -201,7 +201,7 @@ int UploadPicture(sjb_context* ctx, Lane* L, const uint8_t* pix, const Plan& pla
 
 void LaunchF1(Lane* L, const ImageDesc& img, const FrameGeometry& g, bool raw, const QuantTabs& qt) {
   int16_t* coef = L->coef.as<int16_t>();
-  uint64_t* nz = L->nzmask.as<uint64_t>();
+  uint32_t* nz = L->nzmask.as<uint32_t>();
   const int mx_full = g.width / g.mcu_size, my_full = g.height / g.mcu_size;
   int mx_fast = 0, my_fast = 0;
   if (F1FastEligible(img)) {
@@ -253,7 +253,7 @@ int EncodeOnLane(sjb_context* ctx, Lane* L, const uint8_t* d_row0, long long d_s
   }
   const size_t nb = g.nb_blocks();
   int16_t* coef = L->coef.as<int16_t>();
-  uint64_t* nz = L->nzmask.as<uint64_t>();
+  uint32_t* nz = L->nzmask.as<uint32_t>();
 
   if (L->words_dirty) {
     CU(cudaMemsetAsync(L->words.ptr, 0, L->words.bytes, L->stream));
@@ -563,7 +563,7 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
 }
 
 int sjb_stage_coefficients(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
-                           const sjb_params* params, int quantise, int16_t* coef, uint64_t* nzmask) {
+                           const sjb_params* params, int quantise, int16_t* coef, uint32_t* nzmask) {
   if (ctx == nullptr || pix == nullptr || coef == nullptr) return SJB_ERR_ARG;
   ctx->err.clear();
   Plan plan;
@@ -588,7 +588,7 @@ int sjb_stage_coefficients(sjb_context* ctx, const uint8_t* pix, int width, int 
   const size_t nb = plan.g.nb_blocks();
   CU(cudaMemcpyAsync(coef, L->coef.ptr, nb * 64 * sizeof(int16_t), cudaMemcpyDeviceToHost, L->stream));
   if (quantise && nzmask) {
-    CU(cudaMemcpyAsync(nzmask, L->nzmask.ptr, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, L->stream));
+    CU(cudaMemcpyAsync(nzmask, L->nzmask.ptr, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, L->stream));
   }
   CU(cudaStreamSynchronize(L->stream));
   return SJB_OK;
@@ -643,7 +643,7 @@ int sjb_stage_symbol_stats(sjb_context* ctx, const uint8_t* pix, int width, int 
   }
   LaunchF1(L, img, plan.g, false, qt);
   CU(cudaMemsetAsync(L->d_freq(), 0, sizeof(L->host->freq), L->stream));
-  LaunchSymbolStats(L->coef.as<int16_t>(), L->nzmask.as<uint64_t>(), plan.g.nb_blocks(), plan.g.mcu_blocks,
+  LaunchSymbolStats(L->coef.as<int16_t>(), L->nzmask.as<uint32_t>(), plan.g.nb_blocks(), plan.g.mcu_blocks,
                     plan.g.luma_blocks, L->d_freq(), L->stream);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(L->host->freq, L->d_freq(), sizeof(L->host->freq), cudaMemcpyDeviceToHost, L->stream));

@@ -76,7 +76,8 @@ void MinMatrixWithTolerance(const uint8_t in[64], int tolerance, uint8_t out[64]
 
 bool FinalizeQuantizer(uint8_t quant[64], const uint8_t min_quant[64], int q_bias, QuantTab* out) {
   bool ok = true;
-  for (int i = 0; i < 64; ++i) {
+  for (int z = 0; z < 64; ++z) {
+    const int i = kZigzagToNatural[z];       // table entries are stored by zig-zag position
     if (quant[i] < min_quant[i]) quant[i] = min_quant[i];
     const uint32_t q = quant[i];
     // reciprocal in 16-bit fixed point; q == 1 cannot be represented and uses 0xffff with the
@@ -89,9 +90,8 @@ bool FinalizeQuantizer(uint8_t quant[64], const uint8_t min_quant[64], int q_bia
     // the fused form needs: threshold expressible as the reference's uint16 (no wrap) and the
     // products inside int32
     if (thresh < 0 || thresh > 0xffff || cpos + 17000LL * recip >= (1LL << 31)) ok = false;
-    out->iq[i] = static_cast<int32_t>(recip);
-    out->cpos[i] = static_cast<int32_t>(cpos);
-    out->cneg[i] = static_cast<int32_t>((1 << 20) - 1 - cpos);
+    out->e[z][0] = static_cast<int32_t>(recip);
+    out->e[z][1] = static_cast<int32_t>(cpos);
   }
   return ok;
 }

@@ -27,8 +27,8 @@ namespace {
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ uint32_t pack16(int lo, int hi) {
-  return (static_cast<uint32_t>(lo) & 0xffffu) | (static_cast<uint32_t>(hi) << 16);
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) {   // one PRMT
+  return __byte_perm(static_cast<uint32_t>(lo), static_cast<uint32_t>(hi), 0x5410);
 }
 
 // CTA-wide exclusive scan of one uint32 per thread (blockDim.x multiple of 32, <= 1024).
@@ -73,26 +73,43 @@ __device__ __forceinline__ void store_block_natural(const int (&v)[64], int16_t*
   }
 }
 
-// quantise (QuantTab) + zig-zag + non-zero bitmap.  quantize.cc:288-320 without the run/level
-// emission, which E1/E3 redo from the bitmap.
-__device__ __forceinline__ void quantize_store_block(const int (&v)[64], const QuantTab& t,
-                                                     int16_t* dst, uint64_t* nzmask) {
+// quantise (QuantTab) + zig-zag + non-zero pair bitmap (bit p <=> packed word p != 0).
+// quantize.cc:288-320 without the run/level emission, which E1/E3 redo from the bitmap.
+// Tab supplies the constants of output pair p = zig-zag positions 2p, 2p+1.
+struct ParamTab {       // kernel-parameter (constant bank) table, compile-time offsets
+  const QuantTab& t;
+  __device__ __forceinline__ void pair(int p, int& iq0, int& c0, int& iq1, int& c1) const {
+    iq0 = t.e[2 * p][0]; c0 = t.e[2 * p][1]; iq1 = t.e[2 * p + 1][0]; c1 = t.e[2 * p + 1][1];
+  }
+};
+struct SmemTab {        // shared-memory copy, run-time base (lets luma and chroma share code)
+  uint32_t addr;
+  __device__ __forceinline__ void pair(int p, int& iq0, int& c0, int& iq1, int& c1) const {
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(iq0), "=r"(c0), "=r"(iq1), "=r"(c1)
+                 : "r"(addr + 16 * p));
+  }
+};
+
+template <class Tab>
+__device__ __forceinline__ void quantize_store_block(const int (&v)[64], const Tab& tab,
+                                                     int16_t* dst, uint32_t* pairmask) {
   constexpr int zz[64] = SJB_ZIGZAG_INIT;
   uint4* d = reinterpret_cast<uint4*>(dst);
-  uint32_t mlo = 0, mhi = 0;
+  uint32_t mask = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    int q[8];
+    uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = zz[8 * i + j];
-      q[j] = quantize_coeff(v[n], t.iq[n], t.cpos[n], t.cneg[n]);
-      const uint32_t bit = 1u << ((8 * i + j) & 31);
-      if (8 * i + j < 32) mlo |= (q[j] != 0) ? bit : 0u; else mhi |= (q[j] != 0) ? bit : 0u;
+    for (int j = 0; j < 4; ++j) {
+      const int p = 4 * i + j;
+      int iq0, c0, iq1, c1;
+      tab.pair(p, iq0, c0, iq1, c1);
+      w[j] = pack16(quantize_coeff(v[zz[2 * p]], iq0, c0), quantize_coeff(v[zz[2 * p + 1]], iq1, c1));
+      if (w[j] != 0) mask |= 1u << p;
     }
-    d[i] = make_uint4(pack16(q[0], q[1]), pack16(q[2], q[3]), pack16(q[4], q[5]), pack16(q[6], q[7]));
+    d[i] = make_uint4(w[0], w[1], w[2], w[3]);
   }
-  *nzmask = (static_cast<uint64_t>(mhi) << 32) | mlo;
+  *pairmask = mask;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -128,7 +145,7 @@ template <bool kRaw>
 __global__ void __launch_bounds__(128)
 f1_generic_kernel(ImageDesc img, int mx0, int my0, int mx1, int my1, int mcu_blocks,
                   const __grid_constant__ QuantTabs qt, int16_t* __restrict__ coef,
-                  uint64_t* __restrict__ nzmask) {
+                  uint32_t* __restrict__ nzmask) {
   const int rect_w = mx1 - mx0;
   const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long nb = static_cast<long long>(rect_w) * (my1 - my0) * mcu_blocks;
@@ -204,25 +221,25 @@ f1_generic_kernel(ImageDesc img, int mx0, int my0, int mx1, int my1, int mcu_blo
   if (kRaw) {
     store_block_natural(v, coef + g * 64);
   } else {
-    if (chroma) quantize_store_block(v, qt.m[1], coef + g * 64, nzmask + g);
-    else        quantize_store_block(v, qt.m[0], coef + g * 64, nzmask + g);
+    if (chroma) quantize_store_block(v, ParamTab{qt.m[1]}, coef + g * 64, nzmask + g);
+    else        quantize_store_block(v, ParamTab{qt.m[0]}, coef + g * 64, nzmask + g);
   }
 }
 
 // -------------------------------------------------------------------------------------------
-// F1 fast path.  Work unit of a warp = a strip of 8 pixel rows x 256 pixels (32 block columns,
-// 768 bytes per row), staged by 8 bulk-async row copies into one of the warp's two smem slots.
-//   4:2:0 : a tile = two vertically adjacent strips = 16 MCUs; lane = 2*mcu + half; each lane
-//           converts+transforms luma block `half` (top strip) and `2+half` (bottom strip), the
-//           2x2-summed chroma goes through a per-warp smem exchange, then lane half=0 does the U
-//           block and half=1 the V block of its MCU.
-//   4:4:4 : a strip = 32 MCUs, lane = MCU, three passes over the staged pixels (Y, U, V).
+// F1 fast path.  One warp (= one CTA) per tile; every lane owns one 8x8 block at a time, all 64
+// samples in registers.  A strip = 8 pixel rows x 256 pixels (32 block columns, 768 bytes per
+// row) and is staged into shared memory by 8 bulk-async row copies (TMA engine, cp.async.bulk +
+// mbarrier complete_tx).  All copies of a tile are issued up front; the many resident warps per
+// SM (16) hide each other's load latency, and the hardware CTA scheduler balances the SMs.
+//   4:2:0 : tile = two vertically adjacent strips = 16 MCUs; lane = 2*mcu + half; each lane
+//           converts+transforms luma block `half` (top strip) and `2+half` (bottom strip); the
+//           2x2-summed chroma goes through a smem exchange (aliased on the consumed top strip),
+//           then lane half=0 does the U block and half=1 the V block of its MCU.
+//   4:4:4 : tile = one strip = 32 MCUs, lane = MCU, three passes over the staged pixels (Y, U, V).
 //   4:0:0 : as 4:4:4, Y only.
-// Warps are fully independent (own slots, own mbarriers): no CTA-wide barrier in the main loop.
 // -------------------------------------------------------------------------------------------
-enum { kStripRowBytes = 768, kStripBytes = 8 * kStripRowBytes, kUvMcuBytes = 288,
-       kUvBytes = 16 * kUvMcuBytes, kFastWarps = 4,
-       kWarpSmem = 2 * kStripBytes + kUvBytes + 16 };
+enum { kStripRowBytes = 768, kStripBytes = 8 * kStripRowBytes, kUvMcuBytes = 288 };
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -281,9 +298,9 @@ __device__ __forceinline__ void convert_strip_420(uint32_t addr, int (&y)[64], i
   }
 }
 
-// 4:4:4 / 4:0:0 strip: one component of 8x8 pixels.  colors_rgb.cc:809-848
-template <int kComp>
-__device__ __forceinline__ void convert_strip_444(uint32_t addr, int (&s)[64]) {
+// 4:4:4 / 4:0:0 strip: one component of 8x8 pixels, (cr*r + cg*g + cb*b + rnd) >> 16 with the
+// component's coefficients in registers so that Y, U and V share the code.  colors_rgb.cc:809-848
+__device__ __forceinline__ void convert_strip_444(uint32_t addr, int cr, int cg, int cb, int rnd, int (&s)[64]) {
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     uint32_t a[6];
@@ -291,132 +308,115 @@ __device__ __forceinline__ void convert_strip_444(uint32_t addr, int (&s)[64]) {
 #pragma unroll
     for (int x = 0; x < 8; ++x) {
       const int rr = SJB_BYTE(a, 3 * x), gg = SJB_BYTE(a, 3 * x + 1), bb = SJB_BYTE(a, 3 * x + 2);
-      s[8 * r + x] = (kComp == 0) ? rgb_to_y(rr, gg, bb) : (kComp == 1) ? rgb_to_u(rr, gg, bb) : rgb_to_v(rr, gg, bb);
+      s[8 * r + x] = (cr * rr + cg * gg + cb * bb + rnd) >> 16;
     }
   }
 }
 
 template <bool kRaw>
-__device__ __forceinline__ void finish_block(int (&v)[64], const QuantTab& t, int16_t* coef,
-                                             uint64_t* nzmask, size_t g) {
+__device__ __forceinline__ void finish_block(int (&v)[64], uint32_t tab_addr, int16_t* coef,
+                                             uint32_t* nzmask, size_t g) {
   fdct64(v);
   if (kRaw) store_block_natural(v, coef + g * 64);
-  else quantize_store_block(v, t, coef + g * 64, nzmask + g);
+  else quantize_store_block(v, SmemTab{tab_addr}, coef + g * 64, nzmask + g);
 }
 
 template <int kMode, bool kRaw>
-__global__ void __launch_bounds__(kFastWarps * 32)
-f1_fast_kernel(ImageDesc img, int mx_full, int my0, int my1, const __grid_constant__ QuantTabs qt,
-               int16_t* __restrict__ coef, uint64_t* __restrict__ nzmask) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t* wsm = smem_raw + warp * kWarpSmem;
-  const uint32_t slot0 = smem_addr(wsm);
-  const uint32_t uvbuf = slot0 + 2 * kStripBytes;
-  const uint32_t bar0 = uvbuf + kUvBytes;          // two 8-byte mbarriers
-  if (lane == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-
+__global__ void __launch_bounds__(32, 16)
+f1_fast_kernel(ImageDesc img, int mx_full, int my0, const __grid_constant__ QuantTabs qt,
+               int16_t* __restrict__ coef, uint32_t* __restrict__ nzmask) {
   constexpr bool k420 = (kMode == kYuv420);
   constexpr int kMcuBlocks = k420 ? 6 : (kMode == kYuv444 ? 3 : 1);
-  constexpr int kMcusPerItem = k420 ? 16 : 32;          // MCUs per work item along x
-  constexpr int kStripsPerItem = k420 ? 2 : 1;
-  const int chunks_x = (mx_full + kMcusPerItem - 1) / kMcusPerItem;
-  const long long items = static_cast<long long>(chunks_x) * (my1 - my0);
-  const long long gwarp = blockIdx.x * static_cast<long long>(kFastWarps) + warp;
-  const long long nwarps = gridDim.x * static_cast<long long>(kFastWarps);
-  if (gwarp >= items) return;
-  const long long my_items = (items - gwarp + nwarps - 1) / nwarps;
-  const long long strips = my_items * kStripsPerItem;
+  constexpr int kMcusPerTile = k420 ? 16 : 32;          // MCUs per tile along x
+  constexpr int kStrips = k420 ? 2 : 1;
+  __shared__ __align__(128) uint8_t strips[kStrips * kStripBytes];
+  __shared__ __align__(8) unsigned long long bars[kStrips];
+  __shared__ __align__(16) int32_t qtab[2][64][2];      // zig-zag order {iq, cpos}
+  const int lane = threadIdx.x;
+  const uint32_t slot0 = smem_addr(strips);
+  const uint32_t bar0 = smem_addr(bars);
+  const uint32_t tab0 = smem_addr(qtab);
 
-  // issue the bulk copies of strip number h (in this warp's sequence) into slot h&1
-  auto issue = [&](long long h) {
-    const long long item = gwarp + (h / kStripsPerItem) * nwarps;
-    const int cx = static_cast<int>(item % chunks_x), ry = my0 + static_cast<int>(item / chunks_x);
-    const int mcus = min(kMcusPerItem, mx_full - cx * kMcusPerItem);
-    const uint32_t row_bytes = static_cast<uint32_t>(mcus) * (k420 ? 48u : 24u);
-    const int py = (k420 ? 16 * ry + 8 * static_cast<int>(h & 1) : 8 * ry);
-    const uint32_t bar = bar0 + 8 * static_cast<uint32_t>(h & 1);
-    if (lane == 0) mbar_expect_tx(bar, 8 * row_bytes);
-    __syncwarp();
-    if (lane < 8) {
-      const uint8_t* src = img.pix + (py + lane) * img.stride + static_cast<long long>(cx) * kStripRowBytes;
-      bulk_g2s(slot0 + static_cast<uint32_t>(h & 1) * kStripBytes + lane * kStripRowBytes, src, row_bytes, bar);
-    }
-  };
+  const int chunks_x = (mx_full + kMcusPerTile - 1) / kMcusPerTile;
+  const int cx = blockIdx.x % chunks_x, ry = my0 + blockIdx.x / chunks_x;
+  const int mcus = min(kMcusPerTile, mx_full - cx * kMcusPerTile);
+  const uint32_t row_bytes = static_cast<uint32_t>(mcus) * (k420 ? 48u : 24u);
 
-  issue(0);
-  if (strips > 1) issue(1);
-
-  int u[16], v[16];   // 4:2:0 chroma partials of the current strip
-  for (long long h = 0; h < strips; ++h) {
-    const long long item = gwarp + (h / kStripsPerItem) * nwarps;
-    const int cx = static_cast<int>(item % chunks_x), ry = my0 + static_cast<int>(item / chunks_x);
-    const int mcus = min(kMcusPerItem, mx_full - cx * kMcusPerItem);
-    const int slot = static_cast<int>(h & 1);
-    mbar_wait(bar0 + 8 * slot, static_cast<uint32_t>((h >> 1) & 1));
-    const uint32_t src = slot0 + slot * kStripBytes + lane * 24;
-    const size_t mcu0 = static_cast<size_t>(ry) * img.mcus_x + static_cast<size_t>(cx) * kMcusPerItem;
-
-    if (k420) {
-      const int m = lane >> 1, half = lane & 1, bottom = static_cast<int>(h & 1);
-      const bool active = m < mcus;
-      int y[64];
-      convert_strip_420(src, y, u, v);
-      __syncwarp();
-      if (h + 2 < strips) issue(h + 2);     // the slot is consumed: refill it right away
-      // chroma partials -> exchange buffer: rows interleaved U,V (16 bytes each)
-      const uint32_t uvm = uvbuf + m * kUvMcuBytes;
+  if (lane == 0) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const uint32_t a = uvm + (4 * bottom + r) * 32 + half * 8;
-        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(pack16(u[4 * r], u[4 * r + 1])),
-                     "r"(pack16(u[4 * r + 2], u[4 * r + 3])) : "memory");
-        asm volatile("st.shared.v2.u32 [%0+16], {%1,%2};" ::"r"(a), "r"(pack16(v[4 * r], v[4 * r + 1])),
-                     "r"(pack16(v[4 * r + 2], v[4 * r + 3])) : "memory");
-      }
-      if (active) finish_block<kRaw>(y, qt.m[0], coef, nzmask, (mcu0 + m) * 6 + 2 * bottom + half);
-      if (bottom) {
+    for (int i = 0; i < kStrips; ++i) mbar_init(bar0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < kStrips; ++i) mbar_expect_tx(bar0 + 8 * i, 8 * row_bytes);
+  }
+  __syncwarp();
+  if (lane < 8 * kStrips) {
+    // lane -> (strip, row): pixel row = tile origin + lane
+    const long long py = static_cast<long long>(k420 ? 16 : 8) * ry + lane;
+    const uint8_t* src = img.pix + py * img.stride + static_cast<long long>(cx) * kStripRowBytes;
+    bulk_g2s(slot0 + lane * kStripRowBytes, src, row_bytes, bar0 + 8 * (lane >> 3));
+  }
+  if (!kRaw) {
+    // quantiser constants: kernel parameters -> shared memory (256 ints, 8 per lane)
+    const int32_t* q = &qt.m[0].e[0][0];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) (&qtab[0][0][0])[lane + 32 * i] = q[lane + 32 * i];
+  }
+  __syncwarp();
+  const size_t mcu0 = static_cast<size_t>(ry) * img.mcus_x + static_cast<size_t>(cx) * kMcusPerTile;
+  const uint32_t src = slot0 + lane * 24;
+
+  if (k420) {
+    const int m = lane >> 1, half = lane & 1;
+    const bool active = m < mcus;
+    const uint32_t uvm = slot0 + m * kUvMcuBytes;     // exchange buffer aliases the top strip
+    // three blocks per lane through ONE copy of the fDCT/quantise code: top luma, bottom luma,
+    // then the chroma block (U for half 0, V for half 1)
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j) {
+      int x[64];
+      if (j < 2) {
+        int u[16], v[16];
+        mbar_wait(bar0 + 8 * j, 0);
+        convert_strip_420(src + j * kStripBytes, x, u, v);
+        __syncwarp();                                 // top strip fully consumed before reuse
+        // chroma partials: rows interleaved U,V (16 bytes each) inside a 288-byte MCU record
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const uint32_t a = uvm + (4 * j + r) * 32 + half * 8;
+          asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(pack16(u[4 * r], u[4 * r + 1])),
+                       "r"(pack16(u[4 * r + 2], u[4 * r + 3])) : "memory");
+          asm volatile("st.shared.v2.u32 [%0+16], {%1,%2};" ::"r"(a), "r"(pack16(v[4 * r], v[4 * r + 1])),
+                       "r"(pack16(v[4 * r + 2], v[4 * r + 3])) : "memory");
+        }
+      } else {
         __syncwarp();
-        int c[64];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           uint32_t w0, w1, w2, w3;
           asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
                        : "r"(uvm + r * 32 + half * 16));
-          c[8 * r + 0] = static_cast<int16_t>(w0 & 0xffff); c[8 * r + 1] = static_cast<int>(w0) >> 16;
-          c[8 * r + 2] = static_cast<int16_t>(w1 & 0xffff); c[8 * r + 3] = static_cast<int>(w1) >> 16;
-          c[8 * r + 4] = static_cast<int16_t>(w2 & 0xffff); c[8 * r + 5] = static_cast<int>(w2) >> 16;
-          c[8 * r + 6] = static_cast<int16_t>(w3 & 0xffff); c[8 * r + 7] = static_cast<int>(w3) >> 16;
-        }
-        __syncwarp();   // exchange buffer free for the next tile
-        if (active) finish_block<kRaw>(c, qt.m[1], coef, nzmask, (mcu0 + m) * 6 + 4 + half);
-      }
-    } else {
-      const bool active = lane < mcus;
-      {
-        int s[64];
-        convert_strip_444<0>(src, s);
-        if (active) finish_block<kRaw>(s, qt.m[0], coef, nzmask, (mcu0 + lane) * kMcuBlocks);
-      }
-      if (kMode == kYuv444) {
-        {
-          int s[64];
-          convert_strip_444<1>(src, s);
-          if (active) finish_block<kRaw>(s, qt.m[1], coef, nzmask, (mcu0 + lane) * 3 + 1);
-        }
-        {
-          int s[64];
-          convert_strip_444<2>(src, s);
-          if (active) finish_block<kRaw>(s, qt.m[1], coef, nzmask, (mcu0 + lane) * 3 + 2);
+          x[8 * r + 0] = static_cast<int16_t>(w0 & 0xffff); x[8 * r + 1] = static_cast<int>(w0) >> 16;
+          x[8 * r + 2] = static_cast<int16_t>(w1 & 0xffff); x[8 * r + 3] = static_cast<int>(w1) >> 16;
+          x[8 * r + 4] = static_cast<int16_t>(w2 & 0xffff); x[8 * r + 5] = static_cast<int>(w2) >> 16;
+          x[8 * r + 6] = static_cast<int16_t>(w3 & 0xffff); x[8 * r + 7] = static_cast<int>(w3) >> 16;
         }
       }
-      __syncwarp();
-      if (h + 2 < strips) issue(h + 2);
+      const size_t g = (mcu0 + m) * 6 + ((j < 2) ? 2 * j : 4) + half;
+      if (active) finish_block<kRaw>(x, tab0 + ((j < 2) ? 0u : 512u), coef, nzmask, g);
+    }
+  } else {
+    const bool active = lane < mcus;
+    mbar_wait(bar0, 0);
+    int cr = 19595, cg = 38469, cb = 7471, rnd = 32768 - (128 << 16);
+#pragma unroll 1
+    for (int c = 0; c < kMcuBlocks; ++c) {
+      int x[64];
+      convert_strip_444(src, cr, cg, cb, rnd, x);
+      if (active) finish_block<kRaw>(x, tab0 + (c ? 512u : 0u), coef, nzmask, (mcu0 + lane) * kMcuBlocks + c);
+      // next component: U then V (colors_rgb.cc:809-819)
+      if (c == 0) { cr = -11059; cg = -21709; cb = 32768; } else { cr = 32768; cg = -27439; cb = -5329; }
+      rnd = 32768;
     }
   }
 }
@@ -437,14 +437,14 @@ __device__ __forceinline__ void load_block_natural(const int16_t* src, int (&v)[
 }
 
 __global__ void __launch_bounds__(128)
-requantize_kernel(int16_t* __restrict__ coef, uint64_t* __restrict__ nzmask, size_t nb_blocks,
+requantize_kernel(int16_t* __restrict__ coef, uint32_t* __restrict__ nzmask, size_t nb_blocks,
                   int mcu_blocks, int luma_blocks, const __grid_constant__ QuantTabs qt) {
   const size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (g >= nb_blocks) return;
   int v[64];
   load_block_natural(coef + g * 64, v);
-  if (static_cast<int>(g % mcu_blocks) >= luma_blocks) quantize_store_block(v, qt.m[1], coef + g * 64, nzmask + g);
-  else quantize_store_block(v, qt.m[0], coef + g * 64, nzmask + g);
+  if (static_cast<int>(g % mcu_blocks) >= luma_blocks) quantize_store_block(v, ParamTab{qt.m[1]}, coef + g * 64, nzmask + g);
+  else quantize_store_block(v, ParamTab{qt.m[0]}, coef + g * 64, nzmask + g);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -504,9 +504,9 @@ __device__ __forceinline__ int dc_predictor(const int16_t* zz, size_t g, int k, 
   return zz[prev * 64];
 }
 
-struct CoefLoader {
-  const int16_t* p;
-  __device__ __forceinline__ int operator()(int i) const { return p[i]; }
+struct WordLoader {    // word p of a block = zig-zag positions 2p, 2p+1
+  const uint32_t* p;
+  __device__ __forceinline__ uint32_t operator()(int i) const { return p[i]; }
 };
 
 __device__ __forceinline__ void load_code_tables(const CodeTabs* tabs, CodeTabs* sh) {
@@ -518,7 +518,7 @@ __device__ __forceinline__ void load_code_tables(const CodeTabs* tabs, CodeTabs*
 
 // E1 (entropy.cc:161-198 as a length count)
 __global__ void __launch_bounds__(kTileBlocks)
-block_bits_kernel(const int16_t* __restrict__ zz, const uint64_t* __restrict__ nzmask, size_t nb_blocks,
+block_bits_kernel(const int16_t* __restrict__ zz, const uint32_t* __restrict__ nzmask, size_t nb_blocks,
                   int mcu_blocks, int luma_blocks, const CodeTabs* __restrict__ tabs,
                   uint32_t* __restrict__ block_bits, uint32_t* __restrict__ tile_sums) {
   __shared__ CodeTabs sh;
@@ -531,7 +531,7 @@ block_bits_kernel(const int16_t* __restrict__ zz, const uint64_t* __restrict__ n
     const int c = (k >= luma_blocks) ? 1 : 0;
     const int16_t* b = zz + g * 64;
     BitCountSink sink = {0};
-    code_block(CoefLoader{b}, nzmask[g], b[0], dc_predictor(zz, g, k, mcu_blocks, luma_blocks),
+    code_block(WordLoader{reinterpret_cast<const uint32_t*>(b)}, nzmask[g], b[0], dc_predictor(zz, g, k, mcu_blocks, luma_blocks),
                sh.dc[c], sh.ac[c], sink);
     bits = sink.total;
     block_bits[g] = bits;
@@ -549,7 +549,7 @@ struct SmemStats {
 };
 
 __global__ void __launch_bounds__(kTileBlocks)
-symbol_stats_kernel(const int16_t* __restrict__ zz, const uint64_t* __restrict__ nzmask, size_t nb_blocks,
+symbol_stats_kernel(const int16_t* __restrict__ zz, const uint32_t* __restrict__ nzmask, size_t nb_blocks,
                     int mcu_blocks, int luma_blocks, uint32_t* __restrict__ freq) {
   __shared__ uint32_t f[2][272];
   for (int i = threadIdx.x; i < 2 * 272; i += blockDim.x) (&f[0][0])[i] = 0;
@@ -560,7 +560,7 @@ symbol_stats_kernel(const int16_t* __restrict__ zz, const uint64_t* __restrict__
     const int c = (k >= luma_blocks) ? 1 : 0;
     const int16_t* b = zz + g * 64;
     SmemStats add = {f[c]};
-    block_symbol_stats(CoefLoader{b}, nzmask[g], b[0], dc_predictor(zz, g, k, mcu_blocks, luma_blocks), add);
+    block_symbol_stats(WordLoader{reinterpret_cast<const uint32_t*>(b)}, nzmask[g], b[0], dc_predictor(zz, g, k, mcu_blocks, luma_blocks), add);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * 272; i += blockDim.x) {
@@ -594,7 +594,7 @@ struct StreamOut {
 };
 
 __global__ void __launch_bounds__(kTileBlocks)
-pack_kernel(const int16_t* __restrict__ zz, const uint64_t* __restrict__ nzmask, size_t nb_blocks,
+pack_kernel(const int16_t* __restrict__ zz, const uint32_t* __restrict__ nzmask, size_t nb_blocks,
             int mcu_blocks, int luma_blocks, const CodeTabs* __restrict__ tabs,
             const uint32_t* __restrict__ block_bits, const unsigned long long* __restrict__ tile_offsets,
             uint32_t* __restrict__ stream) {
@@ -611,7 +611,7 @@ pack_kernel(const int16_t* __restrict__ zz, const uint64_t* __restrict__ nzmask,
   const int16_t* b = zz + g * 64;
   StreamOut out = {stream};
   BitPackSink<StreamOut> sink(out, tile_offsets[blockIdx.x] + ex);
-  code_block(CoefLoader{b}, nzmask[g], b[0], dc_predictor(zz, g, k, mcu_blocks, luma_blocks),
+  code_block(WordLoader{reinterpret_cast<const uint32_t*>(b)}, nzmask[g], b[0], dc_predictor(zz, g, k, mcu_blocks, luma_blocks),
              sh.dc[c], sh.ac[c], sink);
   sink.finish();
 }
@@ -736,7 +736,7 @@ struct TrellisNode {
 };
 
 __global__ void __launch_bounds__(64)
-trellis_kernel(int16_t* __restrict__ coef, uint64_t* __restrict__ nzmask, size_t nb_blocks,
+trellis_kernel(int16_t* __restrict__ coef, uint32_t* __restrict__ nzmask, size_t nb_blocks,
                int mcu_blocks, int luma_blocks, const __grid_constant__ QuantTabs qt,
                const uint8_t* __restrict__ quant, const CodeTabs* __restrict__ tabs) {
   __shared__ uint8_t ac_len[2][256];
@@ -773,7 +773,7 @@ trellis_kernel(int16_t* __restrict__ coef, uint64_t* __restrict__ nzmask, size_t
     const int sign = x >> 31;
     const int V = (x ^ sign) - sign;
     disto0[i] = static_cast<uint32_t>(V * V) + disto0[i - 1];
-    int v = (V * t.iq[j] + t.cpos[j]) >> 20;
+    int v = (V * t.e[i][0] + t.e[i][1]) >> 20;   // V >= 0
     if (v == 0) continue;
     int nbits = bit_length(static_cast<uint32_t>(v));
     for (int k = 0; k < 2; ++k) {
@@ -820,14 +820,14 @@ trellis_kernel(int16_t* __restrict__ coef, uint64_t* __restrict__ nzmask, size_t
   int16_t outv[64];
 #pragma unroll
   for (int i = 0; i < 64; ++i) outv[i] = 0;
-  outv[0] = static_cast<int16_t>(quantize_coeff(in[0], t.iq[0], t.cpos[0], t.cneg[0]));
-  uint64_t mask = 0;
+  outv[0] = static_cast<int16_t>(quantize_coeff(in[0], t.e[0][0], t.e[0][1]));
+  uint32_t mask = (outv[0] != 0) ? 1u : 0u;
   for (int p = best; p > 0; p = nodes[p].prev) {
     const int n = nodes[p].nbits;
     const int amp = nodes[p].code;
     const int val = (amp >> (n - 1)) ? amp : amp - ((1 << n) - 1);
     outv[nodes[p].pos] = static_cast<int16_t>(val);
-    mask |= 1ull << nodes[p].pos;
+    mask |= 1u << (nodes[p].pos >> 1);
   }
   {
     const uint4* s = reinterpret_cast<const uint4*>(outv);
@@ -835,7 +835,7 @@ trellis_kernel(int16_t* __restrict__ coef, uint64_t* __restrict__ nzmask, size_t
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = s[i];
   }
-  nzmask[g] = mask | (outv[0] != 0 ? 1ull : 0ull);
+  nzmask[g] = mask;
 }
 
 int cdiv(size_t a, size_t b) { return static_cast<int>((a + b - 1) / b); }
@@ -848,7 +848,7 @@ int cdiv(size_t a, size_t b) { return static_cast<int>((a + b - 1) / b); }
 static int McuBlocks(int mode) { return mode == kYuv420 ? 6 : (mode == kYuv444 ? 3 : 1); }
 
 void LaunchF1Generic(const ImageDesc& img, int mx0, int my0, int mx1, int my1, bool raw,
-                     const QuantTabs& qt, int16_t* coef, uint64_t* nzmask, cudaStream_t s) {
+                     const QuantTabs& qt, int16_t* coef, uint32_t* nzmask, cudaStream_t s) {
   if (mx1 <= mx0 || my1 <= my0) return;
   const int mb = McuBlocks(img.yuv_mode);
   const size_t nb = static_cast<size_t>(mx1 - mx0) * (my1 - my0) * mb;
@@ -862,30 +862,14 @@ bool F1FastEligible(const ImageDesc& img) {
 
 template <int kMode, bool kRaw>
 static void LaunchF1FastT(const ImageDesc& img, int mx_full, int my0, int my1, const QuantTabs& qt,
-                          int16_t* coef, uint64_t* nzmask, cudaStream_t s) {
-  static int sm_counts[64] = {0};
-  const size_t smem = kFastWarps * kWarpSmem;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  dev &= 63;
-  if (sm_counts[dev] == 0) {   // once per device and instantiation
-    cudaDeviceGetAttribute(&sm_counts[dev], cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(f1_fast_kernel<kMode, kRaw>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  }
-  const int sm_count = sm_counts[dev];
-  const int per_item = (kMode == kYuv420) ? 16 : 32;
-  const long long items = static_cast<long long>((mx_full + per_item - 1) / per_item) * (my1 - my0);
-  int ctas_per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, f1_fast_kernel<kMode, kRaw>, kFastWarps * 32, smem);
-  if (ctas_per_sm < 1) ctas_per_sm = 1;
-  long long grid = (items + kFastWarps - 1) / kFastWarps;
-  const long long resident = static_cast<long long>(sm_count) * ctas_per_sm;
-  if (grid > resident) grid = resident;
-  f1_fast_kernel<kMode, kRaw><<<static_cast<int>(grid), kFastWarps * 32, smem, s>>>(img, mx_full, my0, my1, qt, coef, nzmask);
+                          int16_t* coef, uint32_t* nzmask, cudaStream_t s) {
+  const int per_tile = (kMode == kYuv420) ? 16 : 32;
+  const long long tiles = static_cast<long long>((mx_full + per_tile - 1) / per_tile) * (my1 - my0);
+  f1_fast_kernel<kMode, kRaw><<<static_cast<unsigned>(tiles), 32, 0, s>>>(img, mx_full, my0, qt, coef, nzmask);
 }
 
 void LaunchF1Fast(const ImageDesc& img, int mx_full, int my0, int my1, bool raw, const QuantTabs& qt,
-                  int16_t* coef, uint64_t* nzmask, cudaStream_t s) {
+                  int16_t* coef, uint32_t* nzmask, cudaStream_t s) {
   if (mx_full <= 0 || my1 <= my0) return;
   switch (img.yuv_mode) {
     case kYuv420:
@@ -903,7 +887,7 @@ void LaunchF1Fast(const ImageDesc& img, int mx_full, int my0, int my1, bool raw,
   }
 }
 
-void LaunchRequantize(int16_t* coef, uint64_t* nzmask, size_t nb_blocks, int mcu_blocks,
+void LaunchRequantize(int16_t* coef, uint32_t* nzmask, size_t nb_blocks, int mcu_blocks,
                       int luma_blocks, const QuantTabs& qt, cudaStream_t s) {
   requantize_kernel<<<cdiv(nb_blocks, 128), 128, 0, s>>>(coef, nzmask, nb_blocks, mcu_blocks, luma_blocks, qt);
 }
@@ -925,20 +909,20 @@ void LaunchHistogram(const int16_t* raw_coef, size_t nb_blocks, int mcu_blocks, 
   histogram_kernel<<<grid, 256, smem, s>>>(raw_coef, nb_blocks, mcu_blocks, luma_blocks, counts);
 }
 
-void LaunchTrellis(int16_t* coef, uint64_t* nzmask, size_t nb_blocks, int mcu_blocks,
+void LaunchTrellis(int16_t* coef, uint32_t* nzmask, size_t nb_blocks, int mcu_blocks,
                    int luma_blocks, const QuantTabs& qt, const uint8_t* quant, const CodeTabs* tabs,
                    cudaStream_t s) {
   trellis_kernel<<<cdiv(nb_blocks, 64), 64, 0, s>>>(coef, nzmask, nb_blocks, mcu_blocks, luma_blocks, qt, quant, tabs);
 }
 
-void LaunchSymbolStats(const int16_t* zz, const uint64_t* nzmask, size_t nb_blocks, int mcu_blocks,
+void LaunchSymbolStats(const int16_t* zz, const uint32_t* nzmask, size_t nb_blocks, int mcu_blocks,
                        int luma_blocks, uint32_t* freq, cudaStream_t s) {
   int grid = cdiv(nb_blocks, kTileBlocks);
   if (grid > 148 * 8) grid = 148 * 8;
   symbol_stats_kernel<<<grid, kTileBlocks, 0, s>>>(zz, nzmask, nb_blocks, mcu_blocks, luma_blocks, freq);
 }
 
-void LaunchBlockBits(const int16_t* zz, const uint64_t* nzmask, size_t nb_blocks, int mcu_blocks,
+void LaunchBlockBits(const int16_t* zz, const uint32_t* nzmask, size_t nb_blocks, int mcu_blocks,
                      int luma_blocks, const CodeTabs* tabs, uint32_t* block_bits,
                      uint32_t* tile_sums, cudaStream_t s) {
   block_bits_kernel<<<cdiv(nb_blocks, kTileBlocks), kTileBlocks, 0, s>>>(zz, nzmask, nb_blocks, mcu_blocks,
@@ -950,7 +934,7 @@ void LaunchScanTiles(const uint32_t* tile_sums, size_t nb_tiles, unsigned long l
   scan_tiles_kernel<<<1, 1024, 0, s>>>(tile_sums, nb_tiles, tile_offsets, info);
 }
 
-void LaunchPack(const int16_t* zz, const uint64_t* nzmask, size_t nb_blocks, int mcu_blocks,
+void LaunchPack(const int16_t* zz, const uint32_t* nzmask, size_t nb_blocks, int mcu_blocks,
                 int luma_blocks, const CodeTabs* tabs, const uint32_t* block_bits,
                 const unsigned long long* tile_offsets, uint32_t* stream, cudaStream_t s) {
   pack_kernel<<<cdiv(nb_blocks, kTileBlocks), kTileBlocks, 0, s>>>(zz, nzmask, nb_blocks, mcu_blocks, luma_blocks,

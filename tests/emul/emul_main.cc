@@ -69,13 +69,13 @@ void BlockSamples(const Img& im, int mode, int mx, int my, int k, int (&v)[64]) 
 
 const int kZZ[64] = SJB_ZIGZAG_INIT;
 
-void QuantizeBlock(const int (&v)[64], const QuantTab& t, int16_t* zz, uint64_t* mask) {
-  uint64_t m = 0;
+void QuantizeBlock(const int (&v)[64], const QuantTab& t, int16_t* zz, uint32_t* mask) {
+  uint32_t m = 0;
   for (int i = 0; i < 64; ++i) {
     const int n = kZZ[i];
-    const int q = quantize_coeff(v[n], t.iq[n], t.cpos[n], t.cneg[n]);
+    const int q = quantize_coeff(v[n], t.e[i][0], t.e[i][1]);
     zz[i] = (int16_t)q;
-    if (q) m |= 1ull << i;
+    if (q) m |= 1u << (i >> 1);
   }
   *mask = m;
 }
@@ -87,7 +87,7 @@ int DcPred(const int16_t* zz, size_t g, int k, int mb, int lb) {
   return zz[prev * 64];
 }
 
-struct Loader { const int16_t* p; int operator()(int i) const { return p[i]; } };
+struct Loader { const int16_t* p; uint32_t operator()(int i) const { return (uint16_t)p[2 * i] | ((uint32_t)(uint16_t)p[2 * i + 1] << 16); } };
 struct WordOut {
   std::vector<uint32_t>* w;
   void or_word(uint64_t i, uint32_t v) { (*w)[i] |= v; }
@@ -137,7 +137,7 @@ size_t emul_encode(const uint8_t* pix, int w, int h, long long stride, int mode,
   for (int i = 0; i < 2; ++i) if (!FinalizeQuantizer(quant[i], minq[i], q_bias, &qt.m[i])) return 0;
   const size_t nb = g.nb_blocks();
   std::vector<int16_t> raw(nb * 64), zz(nb * 64);
-  std::vector<uint64_t> mask(nb);
+  std::vector<uint32_t> mask(nb);
   emul_coeffs(pix, w, h, stride, mode, fmt, raw.data());
   (void)im;
   if (adaptive) {

@@ -65,11 +65,11 @@ def test_f1_coefficients_bit_exact(gpu_ctx, size, mode):
             wantq = _oracle_quantised(want, w, h, mode, p)
             gotq, mask = gpu_ctx.coefficients(rgb, w, h, 3 * w, p, quantise=True)
             assert np.array_equal(gotq, wantq), (name, "quantised", q)
-            nz = (wantq != 0)
-            bits = np.zeros(len(nz), np.uint64)
-            for i in range(1, 64):
-                bits |= nz[:, i].astype(np.uint64) << np.uint64(i)
-            assert np.array_equal(mask & ~np.uint64(1), bits), (name, "mask")
+            pair_nz = (wantq.view(np.uint32) != 0)      # word p = zig-zag positions 2p, 2p+1
+            bits = np.zeros(len(pair_nz), np.uint32)
+            for i in range(32):
+                bits |= pair_nz[:, i].astype(np.uint32) << np.uint32(i)
+            assert np.array_equal(mask, bits), (name, "pair mask")
 
 
 @pytest.mark.parametrize("mode", [O.YUV_420, O.YUV_444, O.YUV_400])
