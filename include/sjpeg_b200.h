@@ -87,7 +87,8 @@ int sjb_fetch_output(sjb_context* ctx, uint8_t* out, int out_on_device, size_t o
 /*
  * Batch of independent pictures with identical geometry and settings (config 5 of BASELINE.json:
  * frames are the unit of sharding).  pix[i] / out[i] as above; sizes[i] receives each size.
- * Work of different frames is overlapped on the context's streams.
+ * Pictures are processed in groups (one kernel launch covers a whole group) and the groups are
+ * overlapped on the context's streams.
  */
 int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix_on_device, int width,
                      int height, long long stride, const sjb_params* params, uint8_t* const* out,
@@ -125,10 +126,12 @@ int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int
                      float* f1_ms, size_t* jpeg_bytes, unsigned long long* launches);
 
 /* Times ONLY the fused F1 kernel (convert + fDCT + quantise): launches it back to back over the
- * n device pictures, 'iters' rounds, on one stream; ms_per_launch = CUDA-event time / (n*iters).
- * n pictures larger than L2 in total keep the input cold. */
+ * n device pictures in groups of *frames_per_launch pictures (the group size the encoder itself
+ * uses for this geometry), 'iters' rounds, on one stream; ms_per_launch = CUDA-event time /
+ * number of launches.  n pictures larger than L2 in total keep the input cold. */
 int sjb_bench_f1(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int width, int height,
-                 long long stride, const sjb_params* params, int iters, float* ms_per_launch);
+                 long long stride, const sjb_params* params, int iters, float* ms_per_launch,
+                 int* frames_per_launch);
 
 #ifdef __cplusplus
 }

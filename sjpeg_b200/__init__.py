@@ -62,7 +62,7 @@ _SIGNATURES = {
                                    C.c_longlong, C.POINTER(Params), C.c_int, C.POINTER(C.c_float),
                                    C.POINTER(C.c_float), C.POINTER(C.c_size_t), C.POINTER(C.c_ulonglong)]),
     "sjb_bench_f1": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_longlong,
-                               C.POINTER(Params), C.c_int, C.POINTER(C.c_float)]),
+                               C.POINTER(Params), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     # drop-in C entry points (include/sjpeg.h)
     "SjpegVersion": (C.c_uint32, []),
     "SjpegEncode": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(_u8p), C.c_float, C.c_int, C.c_int]),
@@ -215,10 +215,11 @@ class Context:
     def bench_f1(self, dev_ptrs, width, height, stride, params, iters):
         n = len(dev_ptrs)
         a = (C.c_void_p * n)(*dev_ptrs)
-        ms = C.c_float(0)
-        rc = lib().sjb_bench_f1(self._ctx, n, a, width, height, stride, C.byref(params), iters, C.byref(ms))
+        ms, fpl = C.c_float(0), C.c_int(0)
+        rc = lib().sjb_bench_f1(self._ctx, n, a, width, height, stride, C.byref(params), iters, C.byref(ms),
+                                C.byref(fpl))
         _check(self._ctx, rc, "sjb_bench_f1")
-        return ms.value
+        return ms.value, fpl.value
 
 
 def sjpeg_encode(rgb, width, height, stride, quality, method, yuv_mode, base=None):

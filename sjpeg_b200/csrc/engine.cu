@@ -2,6 +2,11 @@
 // scratch, and the kernel-launch sequence that replaces the reference's per-MCU driver loops
 // (Encoder::Encode enc.cc:391-448, SinglePassScan :276-307, SinglePassScanOptimized :323-386,
 // CollectHistograms histogram.cc:317-339).  No CPU fallback: every error is reported.
+//
+// Unit of work = a GROUP of up to kMaxGroup pictures with identical geometry and settings,
+// processed by one launch of each kernel (kernels.cuh).  A context owns up to kMaxLanes lanes
+// (stream + scratch for one group); groups of a batch rotate over the lanes so that the copies
+// and kernels of different groups overlap.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -21,12 +26,13 @@ using namespace sjb;
 namespace {
 
 enum { kMaxLanes = 4, kHeaderReserve = 2048, kWorstBitsPerBlock = 1696 };
+const size_t kGroupCoefBudget = 64u << 20;   // keep a group's coefficients inside the 126 MB L2
 
 struct DeviceBuffer {
   void* ptr = nullptr;
   size_t bytes = 0;
-  // grow-only; contents are not preserved
-  cudaError_t Reserve(size_t need, bool zero = false) {
+  // grow-only; contents are not preserved.  *grew reports a reallocation.
+  cudaError_t Reserve(size_t need, bool zero = false, bool* grew = nullptr) {
     if (need <= bytes) return cudaSuccess;
     if (ptr) cudaFree(ptr);
     ptr = nullptr;
@@ -35,6 +41,7 @@ struct DeviceBuffer {
     cudaError_t e = cudaMalloc(&ptr, need);
     if (e != cudaSuccess) return e;
     bytes = need;
+    if (grew) *grew = true;
     if (zero) e = cudaMemset(ptr, 0, need);
     return e;
   }
@@ -46,34 +53,43 @@ struct DeviceBuffer {
   template <class T> T* as() const { return static_cast<T*>(ptr); }
 };
 
-struct HostScratch {     // pinned, for small async up/downloads
-  CodeTabs tabs;
-  StreamInfo info;
-  int32_t hist[2 * 64 * kHistoStride];
-  uint32_t freq[2 * 272];
-  uint8_t quant[2][64];
-  uint8_t header[kHeaderReserve];
+struct HostScratch {     // pinned, for small async up/downloads; one slot per picture of a group
+  CodeTabs tabs[kMaxGroup];
+  QuantTabs qtabs[kMaxGroup];
+  StreamInfo info[kMaxGroup];
+  int32_t hist[kMaxGroup][2 * 64 * kHistoStride];
+  uint32_t freq[kMaxGroup][2 * 272];
+  uint8_t quant[kMaxGroup][2][64];
+  uint8_t header[kMaxGroup][kHeaderReserve];
 };
 
-// one independent pipeline: a stream plus all the scratch one picture needs
+// device mirror of the small per-picture records
+struct SmallLayout {
+  StreamInfo info[kMaxGroup];
+  CodeTabs tabs[kMaxGroup];
+  QuantTabs qtabs[kMaxGroup];
+  int32_t hist[kMaxGroup][2 * 64 * kHistoStride];
+  uint32_t freq[kMaxGroup][2 * 272];
+  uint8_t quant[kMaxGroup][2][64];
+};
+
+// one independent pipeline: a stream plus all the scratch one group needs
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  DeviceBuffer pix, coef, nzmask, block_bits, tile_sums, tile_offsets, words, ff_sums, ff_offsets, out,
-      small;   // small: StreamInfo | CodeTabs | hist | freq | quant
+  DeviceBuffer pix, coef, nzmask, words, out, state, small;
   HostScratch* host = nullptr;
+  GroupBuffers gb = {};
+  int group_capacity = 0;        // pictures the buffers are laid out for
+  size_t pix_pitch = 0;
   bool words_dirty = false;
-  bool tabs_valid = false;      // d_tabs() mirrors host->tabs
-  size_t last_size = 0;         // size of the JPEG left in 'out' by the last sjb_encode
-  size_t header_len = 0;        // bytes of host->header mirrored at the start of 'out' (0 = none)
+  int tabs_valid = 0;            // number of leading device tabs[] slots that mirror host->tabs
+  int header_valid = 0;          // same for the header bytes at the start of each out slot
+  unsigned header_len[kMaxGroup] = {0};
+  size_t last_size = 0;          // size of the JPEG left in out slot 0 by the last sjb_encode
   float ms_f1 = 0, ms_entropy = 0, ms_total = 0;
   unsigned long long launches = 0;
-
-  StreamInfo* d_info() const { return small.as<StreamInfo>(); }
-  CodeTabs* d_tabs() const { return reinterpret_cast<CodeTabs*>(small.as<uint8_t>() + 256); }
-  int32_t* d_hist() const { return reinterpret_cast<int32_t*>(small.as<uint8_t>() + 256 + 4096); }
-  uint32_t* d_freq() const { return reinterpret_cast<uint32_t*>(small.as<uint8_t>() + 256 + 4096 + 68 * 1024); }
-  uint8_t* d_quant() const { return small.as<uint8_t>() + 256 + 4096 + 68 * 1024 + 4096; }
+  SmallLayout* d_small() const { return small.as<SmallLayout>(); }
 };
 
 }  // namespace
@@ -95,21 +111,25 @@ namespace {
       return (e_ == cudaErrorMemoryAllocation) ? SJB_ERR_NOMEM : SJB_ERR_CUDA;     \
     }                                                                              \
   } while (0)
+#define RC(expr)                   \
+  do {                             \
+    const int rc_ = (expr);        \
+    if (rc_ != SJB_OK) return rc_; \
+  } while (0)
 
 int InitLane(sjb_context* ctx, Lane* L) {
   if (L->stream) return SJB_OK;
   CU(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
   for (auto& e : L->ev) CU(cudaEventCreate(&e));
   CU(cudaMallocHost(reinterpret_cast<void**>(&L->host), sizeof(HostScratch)));
-  CU(L->small.Reserve(256 + 4096 + 68 * 1024 + 4096 + 256, true));
+  memset(L->host, 0, sizeof(HostScratch));
+  CU(L->small.Reserve(sizeof(SmallLayout), true));
   return SJB_OK;
 }
 
 void DestroyLane(Lane* L) {
   if (L->stream) cudaStreamSynchronize(L->stream);
-  for (DeviceBuffer* b : {&L->pix, &L->coef, &L->nzmask, &L->block_bits, &L->tile_sums, &L->tile_offsets,
-                          &L->words, &L->ff_sums, &L->ff_offsets, &L->out, &L->small})
-    b->Release();
+  for (DeviceBuffer* b : {&L->pix, &L->coef, &L->nzmask, &L->words, &L->out, &L->state, &L->small}) b->Release();
   for (auto& e : L->ev) if (e) cudaEventDestroy(e);
   if (L->host) cudaFreeHost(L->host);
   if (L->stream) cudaStreamDestroy(L->stream);
@@ -121,12 +141,13 @@ struct Plan {
   sjb_params p;
   int pstep;
   bool adaptive, optimize, trellis;
-  size_t stream_words;      // worst case, multiple of 4
-  size_t out_capacity;      // worst case device output
+  size_t stream_words;      // worst case per picture, multiple of 4
+  size_t out_capacity;      // worst case per picture
   size_t nb_tiles, ff_tiles;
+  int group;                // pictures per launch
 };
 
-int MakePlan(sjb_context* ctx, int width, int height, long long stride, const sjb_params* params, Plan* plan) {
+int MakePlan(int width, int height, long long stride, const sjb_params* params, Plan* plan) {
   if (params == nullptr) return SJB_ERR_ARG;
   plan->p = *params;
   sjb_params& p = plan->p;
@@ -143,238 +164,305 @@ int MakePlan(sjb_context* ctx, int width, int height, long long stride, const sj
   if (p.q_bias < 0 || p.q_bias > 255) return SJB_ERR_ARG;
   const size_t nb = plan->g.nb_blocks();
   plan->stream_words = ((nb * kWorstBitsPerBlock / 32 + 64) + 3) & ~static_cast<size_t>(3);
-  plan->out_capacity = kHeaderReserve + 2 * plan->stream_words * 4 + 16;
+  plan->out_capacity = (kHeaderReserve + 2 * plan->stream_words * 4 + 16 + 255) & ~static_cast<size_t>(255);
   plan->nb_tiles = (nb + kTileBlocks - 1) / kTileBlocks;
   plan->ff_tiles = (plan->stream_words * 4 + kStuffTileBytes - 1) / kStuffTileBytes;
-  (void)ctx;
+  const size_t coef_bytes = nb * 128;
+  plan->group = static_cast<int>(std::min<size_t>(kMaxGroup, std::max<size_t>(1, kGroupCoefBudget / coef_bytes)));
   return SJB_OK;
 }
 
-int ReserveLane(sjb_context* ctx, Lane* L, const Plan& plan) {
+// (Re)lays out the lane's buffers for `frames` pictures of this plan.
+int ReserveLane(sjb_context* ctx, Lane* L, const Plan& plan, int frames) {
   const size_t nb = plan.g.nb_blocks();
-  CU(L->coef.Reserve(nb * 64 * sizeof(int16_t)));
-  CU(L->nzmask.Reserve(nb * sizeof(uint32_t)));
-  CU(L->block_bits.Reserve(nb * sizeof(uint32_t)));
-  CU(L->tile_sums.Reserve(plan.nb_tiles * sizeof(uint32_t)));
-  CU(L->tile_offsets.Reserve(plan.nb_tiles * sizeof(unsigned long long)));
-  if (plan.stream_words * 4 + 64 > L->words.bytes) {
-    CU(L->words.Reserve(plan.stream_words * 4 + 64, true));   // zeroed once, then self-cleaning
-    L->words_dirty = false;
-  }
-  CU(L->ff_sums.Reserve(plan.ff_tiles * sizeof(uint32_t)));
-  CU(L->ff_offsets.Reserve(plan.ff_tiles * sizeof(unsigned long long)));
-  CU(L->out.Reserve(plan.out_capacity));
+  frames = std::max(frames, 1);
+  const size_t f = static_cast<size_t>(frames);
+  bool out_grew = false, words_grew = false;
+  CU(L->coef.Reserve(f * nb * 64 * sizeof(int16_t)));
+  CU(L->nzmask.Reserve(f * nb * sizeof(uint32_t)));
+  CU(L->words.Reserve(f * plan.stream_words * 4 + 64, true, &words_grew));   // zeroed once, then self-cleaning
+  CU(L->out.Reserve(f * plan.out_capacity, false, &out_grew));
+  CU(L->state.Reserve(f * (plan.nb_tiles + plan.ff_tiles) * sizeof(unsigned long long)));
+  GroupBuffers& gb = L->gb;
+  const bool relayout = out_grew || gb.out_pitch != plan.out_capacity || gb.words_pitch != plan.stream_words ||
+                        L->group_capacity != frames;
+  gb.coef = L->coef.as<int16_t>();
+  gb.coef_pitch = nb * 64;
+  gb.nzmask = L->nzmask.as<uint32_t>();
+  gb.mask_pitch = nb;
+  gb.words = L->words.as<uint32_t>();
+  gb.words_pitch = plan.stream_words;
+  gb.out = L->out.as<uint8_t>();
+  gb.out_pitch = plan.out_capacity;
+  gb.bit_state = L->state.as<unsigned long long>();
+  gb.bit_state_pitch = plan.nb_tiles;
+  gb.ff_state = gb.bit_state + f * plan.nb_tiles;
+  gb.ff_state_pitch = plan.ff_tiles;
+  SmallLayout* s = L->d_small();
+  gb.info = s->info;
+  gb.tabs = s->tabs;
+  gb.qtabs = s->qtabs;
+  gb.hist = &s->hist[0][0];
+  gb.freq = &s->freq[0][0];
+  gb.quant = &s->quant[0][0][0];
+  if (relayout) L->header_valid = 0;   // out slots moved: headers must be sent again
+  L->group_capacity = frames;
   return SJB_OK;
 }
 
-// Copies a host picture to the lane's pixel buffer; returns the device address of row 0.
-int UploadPicture(sjb_context* ctx, Lane* L, const uint8_t* pix, const Plan& plan, long long stride,
+size_t PixSlotBytes(const Plan& plan, long long stride) {
+  const size_t row_bytes = static_cast<size_t>(plan.pstep) * plan.g.width;
+  const size_t astride = static_cast<size_t>(stride < 0 ? -stride : stride);
+  const size_t h = plan.g.height;
+  const size_t need =
+      (astride <= 2 * row_bytes + 64) ? astride * (h - 1) + row_bytes : ((row_bytes + 15) & ~size_t(15)) * h;
+  return (need + 64 + 255) & ~static_cast<size_t>(255);
+}
+
+int ReservePix(sjb_context* ctx, Lane* L, const Plan& plan, long long stride, int frames) {
+  L->pix_pitch = PixSlotBytes(plan, stride);
+  CU(L->pix.Reserve(L->pix_pitch * frames));
+  return SJB_OK;
+}
+
+// Copies one host picture into slot `slot` of the lane's pixel buffer; returns the device
+// address of its row 0.
+int UploadPicture(sjb_context* ctx, Lane* L, const uint8_t* pix, const Plan& plan, long long stride, int slot,
                   const uint8_t** d_row0, long long* d_stride) {
   const size_t row_bytes = static_cast<size_t>(plan.pstep) * plan.g.width;
   const long long astride = stride < 0 ? -stride : stride;
   const int h = plan.g.height;
+  uint8_t* base = L->pix.as<uint8_t>() + slot * L->pix_pitch;
+  const uint8_t* lowest = (stride < 0) ? pix + stride * (h - 1) : pix;
   if (static_cast<size_t>(astride) <= 2 * row_bytes + 64) {
     // one contiguous span, stride kept (sign included)
     const size_t span = static_cast<size_t>(astride) * (h - 1) + row_bytes;
-    const uint8_t* lowest = (stride < 0) ? pix + stride * (h - 1) : pix;
-    CU(L->pix.Reserve(span + 64));
-    CU(cudaMemcpyAsync(L->pix.ptr, lowest, span, cudaMemcpyHostToDevice, L->stream));
-    *d_row0 = L->pix.as<uint8_t>() + ((stride < 0) ? static_cast<size_t>(astride) * (h - 1) : 0);
+    CU(cudaMemcpyAsync(base, lowest, span, cudaMemcpyHostToDevice, L->stream));
+    *d_row0 = base + ((stride < 0) ? static_cast<size_t>(astride) * (h - 1) : 0);
     *d_stride = stride;
   } else {
     // sparse rows: gather into a tight pitch
     const size_t pitch = (row_bytes + 15) & ~static_cast<size_t>(15);
-    CU(L->pix.Reserve(pitch * h + 64));
-    if (stride > 0) {
-      CU(cudaMemcpy2DAsync(L->pix.ptr, pitch, pix, static_cast<size_t>(stride), row_bytes, h,
-                           cudaMemcpyHostToDevice, L->stream));
-    } else {
-      // bottom-up source: copy from the lowest address, rows come out reversed -> negative pitch
-      CU(cudaMemcpy2DAsync(L->pix.ptr, pitch, pix + stride * (h - 1), static_cast<size_t>(astride), row_bytes, h,
-                           cudaMemcpyHostToDevice, L->stream));
-    }
-    *d_row0 = L->pix.as<uint8_t>() + ((stride < 0) ? pitch * (h - 1) : 0);
+    CU(cudaMemcpy2DAsync(base, pitch, lowest, static_cast<size_t>(astride), row_bytes, h, cudaMemcpyHostToDevice,
+                         L->stream));
+    *d_row0 = base + ((stride < 0) ? pitch * (h - 1) : 0);
     *d_stride = (stride < 0) ? -static_cast<long long>(pitch) : static_cast<long long>(pitch);
   }
   return SJB_OK;
 }
 
-void LaunchF1(Lane* L, const ImageDesc& img, const FrameGeometry& g, bool raw, const QuantTabs& qt) {
-  int16_t* coef = L->coef.as<int16_t>();
-  uint32_t* nz = L->nzmask.as<uint32_t>();
+void FillFrameSet(const Plan& plan, long long stride, FrameSet* fs) {
+  memset(fs, 0, sizeof(*fs));
+  const FrameGeometry& g = plan.g;
+  fs->stride = stride;
+  fs->width = g.width;
+  fs->height = g.height;
+  fs->yuv_mode = g.yuv_mode;
+  fs->pix_fmt = plan.p.pix_fmt;
+  fs->mcus_x = g.mcus_x;
+  fs->mcus_y = g.mcus_y;
+  fs->mcu_blocks = g.mcu_blocks;
+  fs->luma_blocks = g.luma_blocks;
+  fs->blocks_per_frame = static_cast<unsigned>(g.nb_blocks());
+}
+
+void LaunchF1(Lane* L, const FrameSet& fs, const FrameGeometry& g, bool raw, const QuantTabs& qt) {
   const int mx_full = g.width / g.mcu_size, my_full = g.height / g.mcu_size;
   int mx_fast = 0, my_fast = 0;
-  if (F1FastEligible(img)) {
+  if (F1FastEligible(fs)) {
     mx_fast = (g.yuv_mode == kYuv420) ? mx_full : (mx_full & ~1);
     my_fast = my_full;
     if (mx_fast == 0) my_fast = 0;
     if (my_fast == 0) mx_fast = 0;
   }
   if (mx_fast > 0) {
-    LaunchF1Fast(img, mx_fast, 0, my_fast, raw, qt, coef, nz, L->stream);
+    LaunchF1Fast(fs, mx_fast, 0, my_fast, raw, qt, L->gb, L->stream);
     ++L->launches;
   }
   if (mx_fast < g.mcus_x && my_fast > 0) {        // columns right of the fast region
-    LaunchF1Generic(img, mx_fast, 0, g.mcus_x, my_fast, raw, qt, coef, nz, L->stream);
+    LaunchF1Generic(fs, mx_fast, 0, g.mcus_x, my_fast, raw, qt, L->gb, L->stream);
     ++L->launches;
   }
   if (my_fast < g.mcus_y) {                        // rows below it
-    LaunchF1Generic(img, 0, my_fast, g.mcus_x, g.mcus_y, raw, qt, coef, nz, L->stream);
+    LaunchF1Generic(fs, 0, my_fast, g.mcus_x, g.mcus_y, raw, qt, L->gb, L->stream);
     ++L->launches;
   }
 }
 
-// Device pipeline for one picture already in device memory.  On return the JPEG is in L->out
-// (header included) and L->host->info.out_size holds its size (after the stream is synchronised,
-// which this function does only when it has to look at intermediate results).
-int EncodeOnLane(sjb_context* ctx, Lane* L, const uint8_t* d_row0, long long d_stride, const Plan& plan,
-                 bool timed) {
-  const FrameGeometry& g = plan.g;
-  HostScratch* H = L->host;
-  ImageDesc img;
-  img.pix = d_row0;
-  img.stride = d_stride;
-  img.width = g.width;
-  img.height = g.height;
-  img.yuv_mode = g.yuv_mode;
-  img.pix_fmt = plan.p.pix_fmt;
-  img.mcus_x = g.mcus_x;
-  img.mcus_y = g.mcus_y;
-
-  uint8_t quant[2][64], min_quant[2][64];
-  memcpy(quant, plan.p.quant, sizeof(quant));
-  memcpy(min_quant, plan.p.min_quant, sizeof(min_quant));
-  QuantTabs qt;
+bool MakeQuantTabs(const Plan& plan, uint8_t quant[2][64], uint8_t min_quant[2][64], QuantTabs* qt) {
+  memcpy(quant, plan.p.quant, 128);
+  memcpy(min_quant, plan.p.min_quant, 128);
   for (int i = 0; i < 2; ++i) {
-    if (!FinalizeQuantizer(quant[i], min_quant[i], plan.p.q_bias, &qt.m[i])) {
-      ctx->err = "quantiser entry outside the range of the fused quantise form";
-      return SJB_ERR_ARG;
-    }
+    if (!FinalizeQuantizer(quant[i], min_quant[i], plan.p.q_bias, &qt->m[i])) return false;
   }
-  const size_t nb = g.nb_blocks();
-  int16_t* coef = L->coef.as<int16_t>();
-  uint32_t* nz = L->nzmask.as<uint32_t>();
+  return true;
+}
 
+// Device pipeline for one group whose pixels are already in device memory (fs.pix[]).  On return
+// the JPEGs are (asynchronously) in the lane's out slots, header included, and host->info[] will
+// hold their sizes once the stream has drained.
+int EncodeGroup(sjb_context* ctx, Lane* L, const FrameSet& fs, const Plan& plan, bool timed) {
+  const FrameGeometry& g = plan.g;
+  const int n = fs.frames;
+  HostScratch* H = L->host;
+  SmallLayout* D = L->d_small();
+  const GroupBuffers& gb = L->gb;
+
+  uint8_t quant0[2][64], min_quant[2][64];
+  QuantTabs qt;
+  if (!MakeQuantTabs(plan, quant0, min_quant, &qt)) {
+    ctx->err = "quantiser entry outside the range of the fused quantise form";
+    return SJB_ERR_ARG;
+  }
   if (L->words_dirty) {
     CU(cudaMemsetAsync(L->words.ptr, 0, L->words.bytes, L->stream));
     L->words_dirty = false;
   }
   if (timed) CU(cudaEventRecord(L->ev[0], L->stream));
 
-  HuffSpec spec[4];   // dc0 dc1 ac0 ac1
-  for (int i = 0; i < 4; ++i) DefaultHuffSpec(i >= 2, i & 1, &spec[i]);
-  CodeTabs tabs;
-  memset(&tabs, 0, sizeof(tabs));
+  // default Huffman tables (entropy.cc:31-86)
+  HuffSpec def_spec[4];   // dc0 dc1 ac0 ac1
+  for (int i = 0; i < 4; ++i) DefaultHuffSpec(i >= 2, i & 1, &def_spec[i]);
+  CodeTabs def_tabs;
+  memset(&def_tabs, 0, sizeof(def_tabs));
   for (int c = 0; c < 2; ++c) {
-    CodesFromSpec(spec[c], tabs.dc[c]);
-    CodesFromSpec(spec[2 + c], tabs.ac[c]);
+    CodesFromSpec(def_spec[c], def_tabs.dc[c]);
+    CodesFromSpec(def_spec[2 + c], def_tabs.ac[c]);
   }
-  // Pinned staging (tables, header) is only rewritten when its content changes, and then only
+  // Pinned staging (tables, headers) is only rewritten when its content changes, and then only
   // after the stream has drained: an earlier async copy may still be reading it.
+  std::vector<CodeTabs> tabs(n, def_tabs);
   auto upload_tabs = [&]() -> int {
-    if (L->tabs_valid && memcmp(&H->tabs, &tabs, sizeof(tabs)) == 0) return SJB_OK;
+    bool same = L->tabs_valid >= n;
+    for (int f = 0; same && f < n; ++f) same = memcmp(&H->tabs[f], &tabs[f], sizeof(CodeTabs)) == 0;
+    if (same) return SJB_OK;
     CU(cudaStreamSynchronize(L->stream));
-    H->tabs = tabs;
-    CU(cudaMemcpyAsync(L->d_tabs(), &H->tabs, sizeof(CodeTabs), cudaMemcpyHostToDevice, L->stream));
-    L->tabs_valid = true;
+    for (int f = 0; f < n; ++f) H->tabs[f] = tabs[f];
+    CU(cudaMemcpyAsync(D->tabs, H->tabs, n * sizeof(CodeTabs), cudaMemcpyHostToDevice, L->stream));
+    L->tabs_valid = n;
     return SJB_OK;
   };
 
+  std::vector<uint8_t> quant(static_cast<size_t>(n) * 128);
+  for (int f = 0; f < n; ++f) memcpy(&quant[f * 128], quant0, 128);
+
   if (plan.adaptive) {
     // enc.cc:425-429 : histogram pass over unquantised coefficients, matrices re-derived on host
-    LaunchF1(L, img, g, /*raw=*/true, qt);
-    CU(cudaMemsetAsync(L->d_hist(), 0, sizeof(H->hist), L->stream));
-    LaunchHistogram(coef, nb, g.mcu_blocks, g.luma_blocks, L->d_hist(), L->stream);
+    LaunchF1(L, fs, g, /*raw=*/true, qt);
+    CU(cudaMemsetAsync(D->hist, 0, n * sizeof(D->hist[0]), L->stream));
+    LaunchHistogram(fs, gb, L->stream);
     L->launches += 1;
-    CU(cudaMemcpyAsync(H->hist, L->d_hist(), sizeof(H->hist), cudaMemcpyDeviceToHost, L->stream));
+    CU(cudaMemcpyAsync(H->hist, D->hist, n * sizeof(D->hist[0]), cudaMemcpyDeviceToHost, L->stream));
     if (timed) CU(cudaEventRecord(L->ev[1], L->stream));
     CU(cudaStreamSynchronize(L->stream));
-    AnalyseHistograms(H->hist, g.nb_comps, quant, min_quant, plan.p.qdelta_max_luma, plan.p.qdelta_max_chroma);
-    for (int i = (g.nb_comps > 1 ? 1 : 0); i >= 0; --i) {
-      if (!FinalizeQuantizer(quant[i], min_quant[i], plan.p.q_bias, &qt.m[i])) return SJB_ERR_ARG;
+    for (int f = 0; f < n; ++f) {
+      uint8_t q[2][64];
+      memcpy(q, quant0, 128);
+      AnalyseHistograms(H->hist[f], g.nb_comps, q, min_quant, plan.p.qdelta_max_luma, plan.p.qdelta_max_chroma);
+      QuantTabs qf = qt;
+      for (int i = (g.nb_comps > 1 ? 1 : 0); i >= 0; --i) {
+        if (!FinalizeQuantizer(q[i], min_quant[i], plan.p.q_bias, &qf.m[i])) return SJB_ERR_ARG;
+      }
+      H->qtabs[f] = qf;
+      memcpy(H->quant[f], q, 128);
+      memcpy(&quant[f * 128], q, 128);
     }
+    CU(cudaMemcpyAsync(D->qtabs, H->qtabs, n * sizeof(QuantTabs), cudaMemcpyHostToDevice, L->stream));
     if (plan.trellis) {
       // rate model = default AC tables (enc.cc:334)
-      memcpy(H->quant, quant, sizeof(quant));
-      CU(cudaMemcpyAsync(L->d_quant(), H->quant, sizeof(quant), cudaMemcpyHostToDevice, L->stream));
-      { const int rc = upload_tabs(); if (rc != SJB_OK) return rc; }
-      LaunchTrellis(coef, nz, nb, g.mcu_blocks, g.luma_blocks, qt, L->d_quant(), L->d_tabs(), L->stream);
+      CU(cudaMemcpyAsync(D->quant, H->quant, n * 128, cudaMemcpyHostToDevice, L->stream));
+      RC(upload_tabs());
+      LaunchTrellis(fs, gb, L->stream);
     } else {
-      LaunchRequantize(coef, nz, nb, g.mcu_blocks, g.luma_blocks, qt, L->stream);
+      LaunchRequantize(fs, gb, L->stream);
     }
     L->launches += 1;
   } else {
-    LaunchF1(L, img, g, /*raw=*/false, qt);
+    LaunchF1(L, fs, g, /*raw=*/false, qt);
     if (timed) CU(cudaEventRecord(L->ev[1], L->stream));
   }
 
+  std::vector<HuffSpec> spec(static_cast<size_t>(n) * 4);
+  for (int f = 0; f < n; ++f) for (int i = 0; i < 4; ++i) spec[f * 4 + i] = def_spec[i];
   if (plan.optimize) {
     // enc.cc:344-374 : symbol statistics -> optimal tables
-    CU(cudaMemsetAsync(L->d_freq(), 0, sizeof(H->freq), L->stream));
-    LaunchSymbolStats(coef, nz, nb, g.mcu_blocks, g.luma_blocks, L->d_freq(), L->stream);
+    CU(cudaMemsetAsync(D->freq, 0, n * sizeof(D->freq[0]), L->stream));
+    LaunchSymbolStats(fs, gb, L->stream);
     L->launches += 1;
-    CU(cudaMemcpyAsync(H->freq, L->d_freq(), sizeof(H->freq), cudaMemcpyDeviceToHost, L->stream));
+    CU(cudaMemcpyAsync(H->freq, D->freq, n * sizeof(D->freq[0]), cudaMemcpyDeviceToHost, L->stream));
     CU(cudaStreamSynchronize(L->stream));
     const int nb_tables = (g.nb_comps == 1) ? 1 : 2;
-    for (int c = 0; c < nb_tables; ++c) {
-      OptimalHuffSpec(H->freq + 272 * c + 256, 12, &spec[c]);
-      OptimalHuffSpec(H->freq + 272 * c, 256, &spec[2 + c]);
-      CodesFromSpec(spec[c], tabs.dc[c]);
-      CodesFromSpec(spec[2 + c], tabs.ac[c]);
+    for (int f = 0; f < n; ++f) {
+      for (int c = 0; c < nb_tables; ++c) {
+        OptimalHuffSpec(H->freq[f] + 272 * c + 256, 12, &spec[f * 4 + c]);
+        OptimalHuffSpec(H->freq[f] + 272 * c, 256, &spec[f * 4 + 2 + c]);
+        CodesFromSpec(spec[f * 4 + c], tabs[f].dc[c]);
+        CodesFromSpec(spec[f * 4 + 2 + c], tabs[f].ac[c]);
+      }
     }
   }
-  { const int rc = upload_tabs(); if (rc != SJB_OK) return rc; }
+  RC(upload_tabs());
 
-  std::vector<uint8_t> header;
-  header.reserve(1024);
-  AppendHeaders(g, quant, spec, &header);
-  if (header.size() > kHeaderReserve) return SJB_ERR_ARG;
-  if (L->header_len != header.size() || memcmp(H->header, header.data(), header.size()) != 0) {
-    CU(cudaStreamSynchronize(L->stream));
-    memcpy(H->header, header.data(), header.size());
-    L->header_len = header.size();
+  // headers (host) -> start of each out slot
+  {
+    std::vector<std::vector<uint8_t> > headers(n);
+    bool same = L->header_valid >= n;
+    for (int f = 0; f < n; ++f) {
+      headers[f].reserve(1024);
+      AppendHeaders(g, reinterpret_cast<const uint8_t(*)[64]>(&quant[f * 128]), &spec[f * 4], &headers[f]);
+      if (headers[f].size() > kHeaderReserve) return SJB_ERR_ARG;
+      same = same && L->header_len[f] == headers[f].size() &&
+             memcmp(H->header[f], headers[f].data(), headers[f].size()) == 0;
+    }
+    if (!same) {
+      CU(cudaStreamSynchronize(L->stream));
+      for (int f = 0; f < n; ++f) {
+        memcpy(H->header[f], headers[f].data(), headers[f].size());
+        L->header_len[f] = static_cast<unsigned>(headers[f].size());
+        CU(cudaMemcpyAsync(gb.out + f * gb.out_pitch, H->header[f], headers[f].size(), cudaMemcpyHostToDevice,
+                           L->stream));
+      }
+      L->header_valid = n;
+    }
   }
-  // the header is re-sent every time: 'out' may have been reallocated or overwritten
-  CU(cudaMemcpyAsync(L->out.ptr, H->header, header.size(), cudaMemcpyHostToDevice, L->stream));
 
   L->words_dirty = true;
-  LaunchBlockBits(coef, nz, nb, g.mcu_blocks, g.luma_blocks, L->d_tabs(), L->block_bits.as<uint32_t>(),
-                  L->tile_sums.as<uint32_t>(), L->stream);
-  LaunchScanTiles(L->tile_sums.as<uint32_t>(), plan.nb_tiles, L->tile_offsets.as<unsigned long long>(),
-                  L->d_info(), L->stream);
-  LaunchPack(coef, nz, nb, g.mcu_blocks, g.luma_blocks, L->d_tabs(), L->block_bits.as<uint32_t>(),
-             L->tile_offsets.as<unsigned long long>(), L->words.as<uint32_t>(), L->stream);
-  LaunchStuff(L->words.as<uint32_t>(), plan.stream_words, L->ff_sums.as<uint32_t>(),
-              L->ff_offsets.as<unsigned long long>(), L->d_info(), L->out.as<uint8_t>(), header.size(),
-              L->stream);
-  L->launches += 6;
+  CU(cudaMemsetAsync(L->state.ptr, 0, L->state.bytes, L->stream));   // look-back descriptors
+  LaunchEntropyPack(fs, gb, L->stream);
+  LaunchStuff(fs, gb, L->header_len, L->stream);
+  L->launches += 2;
   CU(cudaGetLastError());
   L->words_dirty = false;   // the stuffing kernel zeroes every word it consumed
   if (timed) CU(cudaEventRecord(L->ev[2], L->stream));
-  CU(cudaMemcpyAsync(&H->info, L->d_info(), sizeof(StreamInfo), cudaMemcpyDeviceToHost, L->stream));
+  CU(cudaMemcpyAsync(H->info, D->info, n * sizeof(StreamInfo), cudaMemcpyDeviceToHost, L->stream));
   return SJB_OK;
 }
 
-int FinishTimings(sjb_context* ctx, Lane* L, bool adaptive) {
+int FinishTimings(sjb_context* ctx, Lane* L) {
   CU(cudaEventSynchronize(L->ev[2]));
   CU(cudaEventElapsedTime(&L->ms_total, L->ev[0], L->ev[2]));
-  if (!adaptive) {
-    CU(cudaEventElapsedTime(&L->ms_f1, L->ev[0], L->ev[1]));
-    CU(cudaEventElapsedTime(&L->ms_entropy, L->ev[1], L->ev[2]));
-  } else {
-    CU(cudaEventElapsedTime(&L->ms_f1, L->ev[0], L->ev[1]));
-    L->ms_entropy = L->ms_total - L->ms_f1;
-  }
+  CU(cudaEventElapsedTime(&L->ms_f1, L->ev[0], L->ev[1]));
+  L->ms_entropy = L->ms_total - L->ms_f1;
   return SJB_OK;
 }
 
-int IsDevicePointer(const void* p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
+// single host/device picture on lane 0, result left in out slot 0
+int EncodeSingle(sjb_context* ctx, const uint8_t* pix, int pix_on_device, long long stride, const Plan& plan,
+                 bool timed) {
+  Lane* L = &ctx->lanes[0];
+  RC(ReserveLane(ctx, L, plan, 1));
+  FrameSet fs;
+  FillFrameSet(plan, stride, &fs);
+  fs.frames = 1;
+  fs.pix[0] = pix;
+  if (!pix_on_device) {
+    RC(ReservePix(ctx, L, plan, stride, 1));
+    RC(UploadPicture(ctx, L, pix, plan, stride, 0, &fs.pix[0], &fs.stride));
   }
-  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+  L->launches = 0;
+  const int rc = EncodeGroup(ctx, L, fs, plan, timed);
+  if (rc != SJB_OK) L->words_dirty = true;
+  return rc;
 }
 
 }  // namespace
@@ -467,27 +555,13 @@ int sjb_encode(sjb_context* ctx, const uint8_t* pix, int pix_on_device, int widt
   ctx->lanes[0].last_size = 0;
   ctx->err.clear();
   Plan plan;
-  int rc = MakePlan(ctx, width, height, stride, params, &plan);
-  if (rc != SJB_OK) return rc;
+  RC(MakePlan(width, height, stride, params, &plan));
   CU(cudaSetDevice(ctx->device));
   Lane* L = &ctx->lanes[0];
-  rc = ReserveLane(ctx, L, plan);
-  if (rc != SJB_OK) return rc;
-  const uint8_t* d_row0 = pix;
-  long long d_stride = stride;
-  if (!pix_on_device) {
-    rc = UploadPicture(ctx, L, pix, plan, stride, &d_row0, &d_stride);
-    if (rc != SJB_OK) return rc;
-  }
-  L->launches = 0;
-  rc = EncodeOnLane(ctx, L, d_row0, d_stride, plan, /*timed=*/true);
-  if (rc != SJB_OK) {
-    L->words_dirty = true;
-    return rc;
-  }
+  RC(EncodeSingle(ctx, pix, pix_on_device, stride, plan, /*timed=*/true));
   CU(cudaStreamSynchronize(L->stream));
-  FinishTimings(ctx, L, plan.adaptive);
-  const size_t size = static_cast<size_t>(L->host->info.out_size);
+  FinishTimings(ctx, L);
+  const size_t size = static_cast<size_t>(L->host->info[0].out_size);
   *out_size = size;
   L->last_size = size;
   if (out == nullptr || size > out_capacity) return SJB_ERR_CAPACITY;
@@ -515,76 +589,99 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
                      int out_on_device, size_t out_capacity, size_t* sizes) {
   if (ctx == nullptr || pix == nullptr || out == nullptr || sizes == nullptr || n < 0) return SJB_ERR_ARG;
   ctx->err.clear();
+  ctx->lanes[0].last_size = 0;
   Plan plan;
-  int rc = MakePlan(ctx, width, height, stride, params, &plan);
-  if (rc != SJB_OK) return rc;
+  RC(MakePlan(width, height, stride, params, &plan));
+  for (int i = 0; i < n; ++i) if (pix[i] == nullptr) return SJB_ERR_ARG;
+  if (n == 0) return SJB_OK;
   CU(cudaSetDevice(ctx->device));
-  const int nl = std::min<int>(kMaxLanes, std::max(1, n));
+  const int B = std::max(1, std::min(plan.group, n));
+  const int groups = (n + B - 1) / B;
+  const int nl = std::min<int>(kMaxLanes, std::max(1, groups));
   for (int l = 0; l < nl; ++l) {
-    if ((rc = InitLane(ctx, &ctx->lanes[l])) != SJB_OK) return rc;
-    if ((rc = ReserveLane(ctx, &ctx->lanes[l], plan)) != SJB_OK) return rc;
+    RC(InitLane(ctx, &ctx->lanes[l]));
+    RC(ReserveLane(ctx, &ctx->lanes[l], plan, B));
+    if (!pix_on_device) RC(ReservePix(ctx, &ctx->lanes[l], plan, stride, B));
   }
-  // software pipeline over the lanes: frame i runs on lane i % nl; a lane is drained (size read,
+  // software pipeline over the lanes: group k runs on lane k % nl; a lane is drained (sizes read,
   // bytes copied out) right before it is reused.
-  auto drain = [&](int i) -> int {
-    Lane* L = &ctx->lanes[i % nl];
+  auto drain = [&](int k) -> int {
+    Lane* L = &ctx->lanes[k % nl];
     CU(cudaStreamSynchronize(L->stream));
-    const size_t size = static_cast<size_t>(L->host->info.out_size);
-    sizes[i] = size;
-    if (out[i] == nullptr || size > out_capacity) return SJB_ERR_CAPACITY;
-    CU(cudaMemcpyAsync(out[i], L->out.ptr, size, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
-                       L->stream));
-    return SJB_OK;
+    int rc = SJB_OK;
+    for (int f = 0; f < B && k * B + f < n; ++f) {
+      const int i = k * B + f;
+      const size_t size = static_cast<size_t>(L->host->info[f].out_size);
+      sizes[i] = size;
+      if (out[i] == nullptr || size > out_capacity) {
+        rc = SJB_ERR_CAPACITY;
+        continue;
+      }
+      CU(cudaMemcpyAsync(out[i], L->gb.out + f * L->gb.out_pitch, size,
+                         out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, L->stream));
+    }
+    return rc;
   };
   int first_err = SJB_OK;
-  for (int i = 0; i < n; ++i) {
-    Lane* L = &ctx->lanes[i % nl];
-    if (i >= nl) {
-      rc = drain(i - nl);
+  for (int k = 0; k < groups; ++k) {
+    Lane* L = &ctx->lanes[k % nl];
+    if (k >= nl) {
+      const int rc = drain(k - nl);
       if (rc != SJB_OK && first_err == SJB_OK) first_err = rc;
     }
-    if (pix[i] == nullptr) return SJB_ERR_ARG;
-    const uint8_t* d_row0 = pix[i];
-    long long d_stride = stride;
-    if (!pix_on_device) {
-      if ((rc = UploadPicture(ctx, L, pix[i], plan, stride, &d_row0, &d_stride)) != SJB_OK) return rc;
+    FrameSet fs;
+    FillFrameSet(plan, stride, &fs);
+    fs.frames = std::min(B, n - k * B);
+    for (int f = 0; f < fs.frames; ++f) {
+      fs.pix[f] = pix[k * B + f];
+      if (!pix_on_device) {
+        long long ds = stride;
+        RC(UploadPicture(ctx, L, pix[k * B + f], plan, stride, f, &fs.pix[f], &ds));
+        fs.stride = ds;
+      }
     }
-    if ((rc = EncodeOnLane(ctx, L, d_row0, d_stride, plan, false)) != SJB_OK) {
+    const int rc = EncodeGroup(ctx, L, fs, plan, false);
+    if (rc != SJB_OK) {
       L->words_dirty = true;
       return rc;
     }
   }
-  for (int i = std::max(0, n - nl); i < n; ++i) {
-    rc = drain(i);
+  for (int k = std::max(0, groups - nl); k < groups; ++k) {
+    const int rc = drain(k);
     if (rc != SJB_OK && first_err == SJB_OK) first_err = rc;
   }
   for (int l = 0; l < nl; ++l) CU(cudaStreamSynchronize(ctx->lanes[l].stream));
   return first_err;
 }
 
+// ---- stage-level entry points ----------------------------------------------------------------
+static int StageF1(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
+                   const sjb_params* params, bool raw, Plan* plan, FrameSet* fs) {
+  ctx->err.clear();
+  ctx->lanes[0].last_size = 0;
+  RC(MakePlan(width, height, stride, params, plan));
+  CU(cudaSetDevice(ctx->device));
+  Lane* L = &ctx->lanes[0];
+  RC(ReserveLane(ctx, L, *plan, 1));
+  RC(ReservePix(ctx, L, *plan, stride, 1));
+  FillFrameSet(*plan, stride, fs);
+  fs->frames = 1;
+  RC(UploadPicture(ctx, L, pix, *plan, stride, 0, &fs->pix[0], &fs->stride));
+  uint8_t quant[2][64], min_quant[2][64];
+  QuantTabs qt;
+  if (!MakeQuantTabs(*plan, quant, min_quant, &qt)) return SJB_ERR_ARG;
+  LaunchF1(L, *fs, plan->g, raw, qt);
+  CU(cudaGetLastError());
+  return SJB_OK;
+}
+
 int sjb_stage_coefficients(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
                            const sjb_params* params, int quantise, int16_t* coef, uint32_t* nzmask) {
   if (ctx == nullptr || pix == nullptr || coef == nullptr) return SJB_ERR_ARG;
-  ctx->err.clear();
   Plan plan;
-  int rc = MakePlan(ctx, width, height, stride, params, &plan);
-  if (rc != SJB_OK) return rc;
-  CU(cudaSetDevice(ctx->device));
+  FrameSet fs;
+  RC(StageF1(ctx, pix, width, height, stride, params, quantise == 0, &plan, &fs));
   Lane* L = &ctx->lanes[0];
-  if ((rc = ReserveLane(ctx, L, plan)) != SJB_OK) return rc;
-  const uint8_t* d_row0;
-  long long d_stride;
-  if ((rc = UploadPicture(ctx, L, pix, plan, stride, &d_row0, &d_stride)) != SJB_OK) return rc;
-  ImageDesc img = {d_row0, d_stride, width, height, plan.g.yuv_mode, plan.p.pix_fmt, plan.g.mcus_x, plan.g.mcus_y};
-  uint8_t quant[2][64], min_quant[2][64];
-  memcpy(quant, plan.p.quant, sizeof(quant));
-  memcpy(min_quant, plan.p.min_quant, sizeof(min_quant));
-  QuantTabs qt;
-  for (int i = 0; i < 2; ++i) {
-    if (!FinalizeQuantizer(quant[i], min_quant[i], plan.p.q_bias, &qt.m[i])) return SJB_ERR_ARG;
-  }
-  LaunchF1(L, img, plan.g, quantise == 0, qt);
-  CU(cudaGetLastError());
   const size_t nb = plan.g.nb_blocks();
   CU(cudaMemcpyAsync(coef, L->coef.ptr, nb * 64 * sizeof(int16_t), cudaMemcpyDeviceToHost, L->stream));
   if (quantise && nzmask) {
@@ -597,25 +694,15 @@ int sjb_stage_coefficients(sjb_context* ctx, const uint8_t* pix, int width, int 
 int sjb_stage_histogram(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
                         const sjb_params* params, int32_t* counts) {
   if (ctx == nullptr || pix == nullptr || counts == nullptr) return SJB_ERR_ARG;
-  ctx->err.clear();
   Plan plan;
-  int rc = MakePlan(ctx, width, height, stride, params, &plan);
-  if (rc != SJB_OK) return rc;
-  CU(cudaSetDevice(ctx->device));
+  FrameSet fs;
+  RC(StageF1(ctx, pix, width, height, stride, params, true, &plan, &fs));
   Lane* L = &ctx->lanes[0];
-  if ((rc = ReserveLane(ctx, L, plan)) != SJB_OK) return rc;
-  const uint8_t* d_row0;
-  long long d_stride;
-  if ((rc = UploadPicture(ctx, L, pix, plan, stride, &d_row0, &d_stride)) != SJB_OK) return rc;
-  ImageDesc img = {d_row0, d_stride, width, height, plan.g.yuv_mode, plan.p.pix_fmt, plan.g.mcus_x, plan.g.mcus_y};
-  QuantTabs qt;
-  memset(&qt, 0, sizeof(qt));
-  LaunchF1(L, img, plan.g, true, qt);
-  CU(cudaMemsetAsync(L->d_hist(), 0, sizeof(L->host->hist), L->stream));
-  LaunchHistogram(L->coef.as<int16_t>(), plan.g.nb_blocks(), plan.g.mcu_blocks, plan.g.luma_blocks, L->d_hist(),
-                  L->stream);
+  SmallLayout* D = L->d_small();
+  CU(cudaMemsetAsync(D->hist, 0, sizeof(D->hist[0]), L->stream));
+  LaunchHistogram(fs, L->gb, L->stream);
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(counts, L->d_hist(), sizeof(L->host->hist), cudaMemcpyDeviceToHost, L->stream));
+  CU(cudaMemcpyAsync(counts, D->hist, sizeof(D->hist[0]), cudaMemcpyDeviceToHost, L->stream));
   CU(cudaStreamSynchronize(L->stream));
   return SJB_OK;
 }
@@ -623,34 +710,19 @@ int sjb_stage_histogram(sjb_context* ctx, const uint8_t* pix, int width, int hei
 int sjb_stage_symbol_stats(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
                            const sjb_params* params, uint32_t* freq_ac, uint32_t* freq_dc) {
   if (ctx == nullptr || pix == nullptr || freq_ac == nullptr || freq_dc == nullptr) return SJB_ERR_ARG;
-  ctx->err.clear();
   Plan plan;
-  int rc = MakePlan(ctx, width, height, stride, params, &plan);
-  if (rc != SJB_OK) return rc;
-  CU(cudaSetDevice(ctx->device));
+  FrameSet fs;
+  RC(StageF1(ctx, pix, width, height, stride, params, false, &plan, &fs));
   Lane* L = &ctx->lanes[0];
-  if ((rc = ReserveLane(ctx, L, plan)) != SJB_OK) return rc;
-  const uint8_t* d_row0;
-  long long d_stride;
-  if ((rc = UploadPicture(ctx, L, pix, plan, stride, &d_row0, &d_stride)) != SJB_OK) return rc;
-  ImageDesc img = {d_row0, d_stride, width, height, plan.g.yuv_mode, plan.p.pix_fmt, plan.g.mcus_x, plan.g.mcus_y};
-  uint8_t quant[2][64], min_quant[2][64];
-  memcpy(quant, plan.p.quant, sizeof(quant));
-  memcpy(min_quant, plan.p.min_quant, sizeof(min_quant));
-  QuantTabs qt;
-  for (int i = 0; i < 2; ++i) {
-    if (!FinalizeQuantizer(quant[i], min_quant[i], plan.p.q_bias, &qt.m[i])) return SJB_ERR_ARG;
-  }
-  LaunchF1(L, img, plan.g, false, qt);
-  CU(cudaMemsetAsync(L->d_freq(), 0, sizeof(L->host->freq), L->stream));
-  LaunchSymbolStats(L->coef.as<int16_t>(), L->nzmask.as<uint32_t>(), plan.g.nb_blocks(), plan.g.mcu_blocks,
-                    plan.g.luma_blocks, L->d_freq(), L->stream);
+  SmallLayout* D = L->d_small();
+  CU(cudaMemsetAsync(D->freq, 0, sizeof(D->freq[0]), L->stream));
+  LaunchSymbolStats(fs, L->gb, L->stream);
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(L->host->freq, L->d_freq(), sizeof(L->host->freq), cudaMemcpyDeviceToHost, L->stream));
+  CU(cudaMemcpyAsync(L->host->freq[0], D->freq, sizeof(D->freq[0]), cudaMemcpyDeviceToHost, L->stream));
   CU(cudaStreamSynchronize(L->stream));
   for (int c = 0; c < 2; ++c) {
-    memcpy(freq_ac + 256 * c, L->host->freq + 272 * c, 256 * sizeof(uint32_t));
-    memcpy(freq_dc + 12 * c, L->host->freq + 272 * c + 256, 12 * sizeof(uint32_t));
+    memcpy(freq_ac + 256 * c, L->host->freq[0] + 272 * c, 256 * sizeof(uint32_t));
+    memcpy(freq_dc + 12 * c, L->host->freq[0] + 272 * c + 256, 12 * sizeof(uint32_t));
   }
   return SJB_OK;
 }
@@ -668,14 +740,16 @@ int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int
                      float* f1_ms, size_t* jpeg_bytes, unsigned long long* launches) {
   if (ctx == nullptr || dev_pix == nullptr || n <= 0 || iters <= 0 || total_ms == nullptr) return SJB_ERR_ARG;
   ctx->err.clear();
+  ctx->lanes[0].last_size = 0;
   Plan plan;
-  int rc = MakePlan(ctx, width, height, stride, params, &plan);
-  if (rc != SJB_OK) return rc;
+  RC(MakePlan(width, height, stride, params, &plan));
   CU(cudaSetDevice(ctx->device));
-  const int nl = std::min<int>(kMaxLanes, n);
+  const int B = std::max(1, std::min(plan.group, n));
+  const int groups = (n + B - 1) / B;
+  const int nl = std::min<int>(kMaxLanes, groups);
   for (int l = 0; l < nl; ++l) {
-    if ((rc = InitLane(ctx, &ctx->lanes[l])) != SJB_OK) return rc;
-    if ((rc = ReserveLane(ctx, &ctx->lanes[l], plan)) != SJB_OK) return rc;
+    RC(InitLane(ctx, &ctx->lanes[l]));
+    RC(ReserveLane(ctx, &ctx->lanes[l], plan, B));
     ctx->lanes[l].launches = 0;
   }
   CU(cudaDeviceSynchronize());
@@ -685,16 +759,14 @@ int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int
   Lane* L0 = &ctx->lanes[0];
   CU(cudaEventRecord(t0, L0->stream));
   for (int l = 1; l < nl; ++l) CU(cudaStreamWaitEvent(ctx->lanes[l].stream, t0, 0));
-  double f1_sum = 0;
-  int f1_n = 0;
   for (int it = 0; it < iters; ++it) {
-    for (int i = 0; i < n; ++i) {
-      Lane* L = &ctx->lanes[i % nl];
-      const bool timed = (i % nl == 0) && !plan.adaptive;
-      if ((rc = EncodeOnLane(ctx, L, dev_pix[i], stride, plan, timed)) != SJB_OK) return rc;
-      if (timed && it == iters - 1 && i + nl >= n) {
-        // sample the fused kernel's time on lane 0 once per run (events add no sync)
-      }
+    for (int k = 0; k < groups; ++k) {
+      Lane* L = &ctx->lanes[k % nl];
+      FrameSet fs;
+      FillFrameSet(plan, stride, &fs);
+      fs.frames = std::min(B, n - k * B);
+      for (int f = 0; f < fs.frames; ++f) fs.pix[f] = dev_pix[k * B + f];
+      RC(EncodeGroup(ctx, L, fs, plan, /*timed=*/k % nl == 0));
     }
   }
   for (int l = 1; l < nl; ++l) {
@@ -704,15 +776,11 @@ int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int
   CU(cudaEventRecord(t1, L0->stream));
   CU(cudaEventSynchronize(t1));
   CU(cudaEventElapsedTime(total_ms, t0, t1));
-  if (!plan.adaptive) {
+  if (f1_ms) {
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, L0->ev[0], L0->ev[1]) == cudaSuccess) {
-      f1_sum += ms;
-      ++f1_n;
-    }
+    *f1_ms = (cudaEventElapsedTime(&ms, L0->ev[0], L0->ev[1]) == cudaSuccess) ? ms : 0.f;
   }
-  if (f1_ms) *f1_ms = f1_n ? static_cast<float>(f1_sum / f1_n) : 0.f;
-  if (jpeg_bytes) *jpeg_bytes = static_cast<size_t>(L0->host->info.out_size);
+  if (jpeg_bytes) *jpeg_bytes = static_cast<size_t>(L0->host->info[0].out_size);
   if (launches) {
     *launches = 0;
     for (int l = 0; l < nl; ++l) *launches += ctx->lanes[l].launches;
@@ -723,28 +791,31 @@ int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int
 }
 
 int sjb_bench_f1(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int width, int height,
-                 long long stride, const sjb_params* params, int iters, float* ms_per_launch) {
+                 long long stride, const sjb_params* params, int iters, float* ms_per_launch,
+                 int* frames_per_launch) {
   if (ctx == nullptr || dev_pix == nullptr || n <= 0 || iters <= 0 || ms_per_launch == nullptr) return SJB_ERR_ARG;
   ctx->err.clear();
+  ctx->lanes[0].last_size = 0;
   Plan plan;
-  int rc = MakePlan(ctx, width, height, stride, params, &plan);
-  if (rc != SJB_OK) return rc;
+  RC(MakePlan(width, height, stride, params, &plan));
   CU(cudaSetDevice(ctx->device));
   Lane* L = &ctx->lanes[0];
-  if ((rc = ReserveLane(ctx, L, plan)) != SJB_OK) return rc;
+  const int B = std::max(1, std::min(plan.group, n));
+  const int groups = n / B;             // whole groups only, so that every launch is identical
+  if (groups < 1) return SJB_ERR_ARG;
+  RC(ReserveLane(ctx, L, plan, B));
   uint8_t quant[2][64], min_quant[2][64];
-  memcpy(quant, plan.p.quant, sizeof(quant));
-  memcpy(min_quant, plan.p.min_quant, sizeof(min_quant));
   QuantTabs qt;
-  for (int i = 0; i < 2; ++i) {
-    if (!FinalizeQuantizer(quant[i], min_quant[i], plan.p.q_bias, &qt.m[i])) return SJB_ERR_ARG;
-  }
+  if (!MakeQuantTabs(plan, quant, min_quant, &qt)) return SJB_ERR_ARG;
   CU(cudaStreamSynchronize(L->stream));
   CU(cudaEventRecord(L->ev[0], L->stream));
   for (int it = 0; it < iters; ++it) {
-    for (int i = 0; i < n; ++i) {
-      ImageDesc img = {dev_pix[i], stride, width, height, plan.g.yuv_mode, plan.p.pix_fmt, plan.g.mcus_x, plan.g.mcus_y};
-      LaunchF1(L, img, plan.g, false, qt);
+    for (int k = 0; k < groups; ++k) {
+      FrameSet fs;
+      FillFrameSet(plan, stride, &fs);
+      fs.frames = B;
+      for (int f = 0; f < B; ++f) fs.pix[f] = dev_pix[k * B + f];
+      LaunchF1(L, fs, plan.g, false, qt);
     }
   }
   CU(cudaEventRecord(L->ev[1], L->stream));
@@ -752,7 +823,8 @@ int sjb_bench_f1(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int wid
   CU(cudaGetLastError());
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, L->ev[0], L->ev[1]));
-  *ms_per_launch = ms / (static_cast<float>(n) * iters);
+  *ms_per_launch = ms / (static_cast<float>(groups) * iters);
+  if (frames_per_launch) *frames_per_launch = B;
   return SJB_OK;
 }
 

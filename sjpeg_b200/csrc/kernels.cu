@@ -2,16 +2,18 @@
 //
 //   F1  colour convert + 4:2:0 downsample + integer fDCT + quantise, one 8x8 block per thread,
 //       everything in registers (fully unrolled; the zig-zag reorder is a compile-time register
-//       permutation).  Fast path: per-warp double-buffered strips of 8 pixel rows x 768 bytes
-//       staged into shared memory with bulk-async copies (TMA engine, cp.async.bulk + mbarrier).
+//       permutation).  Fast path: one warp per tile, strips of 8 pixel rows x 768 bytes staged
+//       into shared memory with bulk-async copies (TMA engine, cp.async.bulk + mbarrier).
 //       Generic path: clamped byte loads, handles edges / odd strides / BGRA / RGBA.
 //   Q1  re-quantise stored raw coefficients (adaptive quantisation, methods >= 3)
 //   H1  coefficient histogram (methods >= 3), shared-memory privatised
 //   T1  trellis quantiser (methods 7, 8), one block per thread
 //   S1  Huffman symbol statistics (optimised tables)
-//   E1  bits per block + tile sums, E2 scan of tile sums, E3 bit packing at scanned offsets
-//   E4  0xFF byte stuffing: count / scan / scatter, padding and EOI
-//
+//   E   entropy stage in one pass: bits per block -> CTA scan -> decoupled look-back over tiles
+//       -> bit packing at the resulting offsets (replaces the serial bit writer)
+//   S   0xFF byte stuffing in one pass: count -> CTA scan -> decoupled look-back -> scatter,
+//       padding and EOI
+// Every kernel takes a group of pictures (gridDim.y); see kernels.cuh.
 // Reference behaviour each stage reproduces is cited in block_ops.cuh and at each kernel.
 #include "kernels.cuh"
 
@@ -143,35 +145,38 @@ __device__ __forceinline__ void luma_samples(const PixelReader& px, int x0, int 
 
 template <bool kRaw>
 __global__ void __launch_bounds__(128)
-f1_generic_kernel(ImageDesc img, int mx0, int my0, int mx1, int my1, int mcu_blocks,
-                  const __grid_constant__ QuantTabs qt, int16_t* __restrict__ coef,
-                  uint32_t* __restrict__ nzmask) {
+f1_generic_kernel(const __grid_constant__ FrameSet fs, int mx0, int my0, int mx1, int my1,
+                  const __grid_constant__ QuantTabs qt, GroupBuffers gb) {
   const int rect_w = mx1 - mx0;
+  const int mcu_blocks = fs.mcu_blocks;
   const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long nb = static_cast<long long>(rect_w) * (my1 - my0) * mcu_blocks;
   if (t >= nb) return;
+  const int frame = blockIdx.y;
   const int k = static_cast<int>(t % mcu_blocks);
   const long long m = t / mcu_blocks;
   const int mx = mx0 + static_cast<int>(m % rect_w), my = my0 + static_cast<int>(m / rect_w);
-  const size_t g = (static_cast<size_t>(my) * img.mcus_x + mx) * mcu_blocks + k;
+  const size_t g = (static_cast<size_t>(my) * fs.mcus_x + mx) * mcu_blocks + k;
+  int16_t* coef = gb.coef + frame * gb.coef_pitch;
+  uint32_t* nzmask = gb.nzmask + frame * gb.mask_pitch;
 
   PixelReader px;
-  px.base = img.pix;
-  px.stride = img.stride;
-  px.w1 = img.width - 1;
-  px.h1 = img.height - 1;
-  px.pstep = (img.pix_fmt == kFmtRGB) ? 3 : 4;
-  px.ro = (img.pix_fmt == kFmtBGRA) ? 2 : 0;
-  px.bo = (img.pix_fmt == kFmtBGRA) ? 0 : 2;
+  px.base = fs.pix[frame];
+  px.stride = fs.stride;
+  px.w1 = fs.width - 1;
+  px.h1 = fs.height - 1;
+  px.pstep = (fs.pix_fmt == kFmtRGB) ? 3 : 4;
+  px.ro = (fs.pix_fmt == kFmtBGRA) ? 2 : 0;
+  px.bo = (fs.pix_fmt == kFmtBGRA) ? 0 : 2;
 
   int v[64];
   int chroma = 0;
-  if (img.yuv_mode == kYuv420) {
+  if (fs.yuv_mode == kYuv420) {
     const int X = 16 * mx, Y = 16 * my;
     if (k < 4) {
       // AverageExtraLuma (encoders.cc:107-125): luma blocks wholly outside the picture are
       // flattened to the rounded mean of a neighbour block's samples.
-      const int sub_w = img.width - X, sub_h = img.height - Y;
+      const int sub_w = fs.width - X, sub_h = fs.height - Y;
       int src = -1;
       if (k == 1 && sub_w <= 8) src = 0;
       if (k >= 2 && sub_h <= 8) src = (sub_w > 8) ? 1 : 0;
@@ -323,8 +328,8 @@ __device__ __forceinline__ void finish_block(int (&v)[64], uint32_t tab_addr, in
 
 template <int kMode, bool kRaw>
 __global__ void __launch_bounds__(32, 16)
-f1_fast_kernel(ImageDesc img, int mx_full, int my0, const __grid_constant__ QuantTabs qt,
-               int16_t* __restrict__ coef, uint32_t* __restrict__ nzmask) {
+f1_fast_kernel(const __grid_constant__ FrameSet fs, int mx_full, int my0,
+               const __grid_constant__ QuantTabs qt, GroupBuffers gb) {
   constexpr bool k420 = (kMode == kYuv420);
   constexpr int kMcuBlocks = k420 ? 6 : (kMode == kYuv444 ? 3 : 1);
   constexpr int kMcusPerTile = k420 ? 16 : 32;          // MCUs per tile along x
@@ -333,9 +338,12 @@ f1_fast_kernel(ImageDesc img, int mx_full, int my0, const __grid_constant__ Quan
   __shared__ __align__(8) unsigned long long bars[kStrips];
   __shared__ __align__(16) int32_t qtab[2][64][2];      // zig-zag order {iq, cpos}
   const int lane = threadIdx.x;
+  const int frame = blockIdx.y;
   const uint32_t slot0 = smem_addr(strips);
   const uint32_t bar0 = smem_addr(bars);
   const uint32_t tab0 = smem_addr(qtab);
+  int16_t* coef = gb.coef + frame * gb.coef_pitch;
+  uint32_t* nzmask = gb.nzmask + frame * gb.mask_pitch;
 
   const int chunks_x = (mx_full + kMcusPerTile - 1) / kMcusPerTile;
   const int cx = blockIdx.x % chunks_x, ry = my0 + blockIdx.x / chunks_x;
@@ -353,7 +361,7 @@ f1_fast_kernel(ImageDesc img, int mx_full, int my0, const __grid_constant__ Quan
   if (lane < 8 * kStrips) {
     // lane -> (strip, row): pixel row = tile origin + lane
     const long long py = static_cast<long long>(k420 ? 16 : 8) * ry + lane;
-    const uint8_t* src = img.pix + py * img.stride + static_cast<long long>(cx) * kStripRowBytes;
+    const uint8_t* src = fs.pix[frame] + py * fs.stride + static_cast<long long>(cx) * kStripRowBytes;
     bulk_g2s(slot0 + lane * kStripRowBytes, src, row_bytes, bar0 + 8 * (lane >> 3));
   }
   if (!kRaw) {
@@ -363,7 +371,7 @@ f1_fast_kernel(ImageDesc img, int mx_full, int my0, const __grid_constant__ Quan
     for (int i = 0; i < 8; ++i) (&qtab[0][0][0])[lane + 32 * i] = q[lane + 32 * i];
   }
   __syncwarp();
-  const size_t mcu0 = static_cast<size_t>(ry) * img.mcus_x + static_cast<size_t>(cx) * kMcusPerTile;
+  const size_t mcu0 = static_cast<size_t>(ry) * fs.mcus_x + static_cast<size_t>(cx) * kMcusPerTile;
   const uint32_t src = slot0 + lane * 24;
 
   if (k420) {
@@ -422,7 +430,7 @@ f1_fast_kernel(ImageDesc img, int mx_full, int my0, const __grid_constant__ Quan
 }
 
 // -------------------------------------------------------------------------------------------
-// Q1: quantise stored raw coefficients in place
+// Q1: quantise stored raw coefficients in place (per-picture tables from global memory)
 // -------------------------------------------------------------------------------------------
 __device__ __forceinline__ void load_block_natural(const int16_t* src, int (&v)[64]) {
   const uint4* s = reinterpret_cast<const uint4*>(src);
@@ -437,27 +445,35 @@ __device__ __forceinline__ void load_block_natural(const int16_t* src, int (&v)[
 }
 
 __global__ void __launch_bounds__(128)
-requantize_kernel(int16_t* __restrict__ coef, uint32_t* __restrict__ nzmask, size_t nb_blocks,
-                  int mcu_blocks, int luma_blocks, const __grid_constant__ QuantTabs qt) {
+requantize_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
+  __shared__ __align__(16) int32_t qtab[2][64][2];
+  const int frame = blockIdx.y;
+  {
+    const int32_t* q = &gb.qtabs[frame].m[0].e[0][0];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) (&qtab[0][0][0])[i] = q[i];
+  }
+  __syncthreads();
   const size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (g >= nb_blocks) return;
+  if (g >= fs.blocks_per_frame) return;
+  int16_t* blk = gb.coef + frame * gb.coef_pitch + g * 64;
   int v[64];
-  load_block_natural(coef + g * 64, v);
-  if (static_cast<int>(g % mcu_blocks) >= luma_blocks) quantize_store_block(v, ParamTab{qt.m[1]}, coef + g * 64, nzmask + g);
-  else quantize_store_block(v, ParamTab{qt.m[0]}, coef + g * 64, nzmask + g);
+  load_block_natural(blk, v);
+  const uint32_t tab = smem_addr(qtab) + ((static_cast<int>(g % fs.mcu_blocks) >= fs.luma_blocks) ? 512u : 0u);
+  quantize_store_block(v, SmemTab{tab}, blk, gb.nzmask + frame * gb.mask_pitch + g);
 }
 
 // -------------------------------------------------------------------------------------------
-// H1: histogram of |coef| >> 2 (histogram.cc:99-108).  Per-CTA privatised copy of the 64x128
-// bins of ONE matrix at a time would need two passes; instead each CTA keeps both matrices'
-// bins for the positions it is working on: 64 KB of shared memory, flushed with atomicAdd.
+// H1: histogram of |coef| >> 2 (histogram.cc:99-108).  Each CTA keeps a private copy of the
+// 2 x 64 x 128 bins in 64 KB of shared memory and flushes the used ones with atomicAdd.
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-histogram_kernel(const int16_t* __restrict__ raw, size_t nb_blocks, int mcu_blocks, int luma_blocks,
-                 int32_t* __restrict__ counts) {
+histogram_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   extern __shared__ int32_t hist[];   // [2][64][128]
   for (int i = threadIdx.x; i < 2 * 64 * 128; i += blockDim.x) hist[i] = 0;
   __syncthreads();
+  const int frame = blockIdx.y;
+  const int16_t* raw = gb.coef + frame * gb.coef_pitch;
+  const size_t nb_blocks = fs.blocks_per_frame;
   // 8 lanes per block, each lane owns 8 consecutive natural positions (one 16-byte load):
   // coalesced, and the 8 lanes of a block hit different rows of the table.
   const size_t lanes_total = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -465,7 +481,7 @@ histogram_kernel(const int16_t* __restrict__ raw, size_t nb_blocks, int mcu_bloc
        t += lanes_total) {
     const size_t g = t >> 3;
     const int part = static_cast<int>(t & 7);
-    const int m = (static_cast<int>(g % mcu_blocks) >= luma_blocks) ? 1 : 0;
+    const int m = (static_cast<int>(g % fs.mcu_blocks) >= fs.luma_blocks) ? 1 : 0;
     const uint4 w = reinterpret_cast<const uint4*>(raw + g * 64)[part];
     const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
@@ -476,6 +492,7 @@ histogram_kernel(const int16_t* __restrict__ raw, size_t nb_blocks, int mcu_bloc
     }
   }
   __syncthreads();
+  int32_t* counts = gb.hist + static_cast<size_t>(frame) * 2 * 64 * 129;
   for (int i = threadIdx.x; i < 2 * 64 * 128; i += blockDim.x) {
     const int c = hist[i];
     if (c) atomicAdd(&counts[(i >> 7) * 129 + (i & 127)], c);
@@ -485,10 +502,6 @@ histogram_kernel(const int16_t* __restrict__ raw, size_t nb_blocks, int mcu_bloc
 // -------------------------------------------------------------------------------------------
 // Entropy stage helpers
 // -------------------------------------------------------------------------------------------
-struct ScanGeom {
-  int mcu_blocks, luma_blocks;
-};
-
 // quantised DC of the previous block of the same component in scan order (enc.cc:286-305:
 // MCU raster order, blocks interleaved; predictors reset once per image, entropy.cc:155-159)
 __device__ __forceinline__ int dc_predictor(const int16_t* zz, size_t g, int k, int mcu_blocks, int luma_blocks) {
@@ -516,29 +529,101 @@ __device__ __forceinline__ void load_code_tables(const CodeTabs* tabs, CodeTabs*
   __syncthreads();
 }
 
-// E1 (entropy.cc:161-198 as a length count)
+// Decoupled look-back (single-pass chained scan).  One 64-bit descriptor per tile:
+// [63:62] state (0 = not ready, 1 = tile aggregate, 2 = inclusive prefix), [61:0] value; the
+// value travels in the same word as the flag, so no fence is needed.  Executed by one full warp;
+// returns the exclusive prefix of `tile` in every lane and publishes the inclusive one.
+// Tiles are dispatched in blockIdx order, so a predecessor is always running or finished.
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long warp_lookback(unsigned long long* state, long long tile,
+                                                            unsigned long long aggregate) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long kValue = (1ull << 62) - 1;
+  if (tile == 0) {
+    if (lane == 0) st_volatile_u64(&state[0], (2ull << 62) | aggregate);
+    return 0;
+  }
+  if (lane == 0) st_volatile_u64(&state[tile], (1ull << 62) | aggregate);
+  unsigned long long prefix = 0;
+  long long base = tile - 1;
+  while (true) {
+    const long long j = base - lane;
+    const unsigned long long v = (j >= 0) ? ld_volatile_u64(&state[j]) : (2ull << 62);   // virtual 0 before tile 0
+    const unsigned flag = static_cast<unsigned>(v >> 62);
+    const unsigned not_ready = __ballot_sync(0xffffffffu, flag == 0);
+    const unsigned has_prefix = __ballot_sync(0xffffffffu, flag == 2);
+    const int first = has_prefix ? (__ffs(has_prefix) - 1) : 31;     // last lane that contributes
+    const unsigned need = (first == 31) ? 0xffffffffu : ((2u << first) - 1u);
+    if (not_ready & need) continue;                                  // spin: re-read the window
+    unsigned long long val = (lane <= first) ? (v & kValue) : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+    prefix += val;
+    if (has_prefix) break;
+    base -= 32;
+  }
+  if (lane == 0) st_volatile_u64(&state[tile], (2ull << 62) | (prefix + aggregate));
+  return prefix;
+}
+
+// -------------------------------------------------------------------------------------------
+// E: entropy-code lengths + prefix + bit packing, one 8x8 block per thread, 256 blocks per CTA
+// (entropy.cc:161-198 CodeBlock; bit_writer.h:201-209 PutBits without the serial accumulator)
+// -------------------------------------------------------------------------------------------
+struct StreamOut {
+  uint32_t* words;
+  __device__ __forceinline__ void or_word(uint64_t i, uint32_t v) { if (v) atomicOr(&words[i], v); }
+  __device__ __forceinline__ void set_word(uint64_t i, uint32_t v) { words[i] = v; }
+};
+
 __global__ void __launch_bounds__(kTileBlocks)
-block_bits_kernel(const int16_t* __restrict__ zz, const uint32_t* __restrict__ nzmask, size_t nb_blocks,
-                  int mcu_blocks, int luma_blocks, const CodeTabs* __restrict__ tabs,
-                  uint32_t* __restrict__ block_bits, uint32_t* __restrict__ tile_sums) {
+entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   __shared__ CodeTabs sh;
   __shared__ uint32_t scratch[33];
-  load_code_tables(tabs, &sh);
+  __shared__ unsigned long long tile_prefix;
+  const int frame = blockIdx.y;
+  load_code_tables(gb.tabs + frame, &sh);
+  const int16_t* zz = gb.coef + frame * gb.coef_pitch;
+  const uint32_t* nzmask = gb.nzmask + frame * gb.mask_pitch;
+  const size_t nb_blocks = fs.blocks_per_frame;
   const size_t g = blockIdx.x * static_cast<size_t>(kTileBlocks) + threadIdx.x;
+  const bool valid = g < nb_blocks;
+  int k = 0, c = 0, dc = 0, pred = 0;
+  uint32_t mask = 0;
+  const int16_t* b = zz + (valid ? g : 0) * 64;
   uint32_t bits = 0;
-  if (g < nb_blocks) {
-    const int k = static_cast<int>(g % mcu_blocks);
-    const int c = (k >= luma_blocks) ? 1 : 0;
-    const int16_t* b = zz + g * 64;
+  if (valid) {
+    k = static_cast<int>(g % fs.mcu_blocks);
+    c = (k >= fs.luma_blocks) ? 1 : 0;
+    mask = nzmask[g];
+    dc = b[0];
+    pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks);
     BitCountSink sink = {0};
-    code_block(WordLoader{reinterpret_cast<const uint32_t*>(b)}, nzmask[g], b[0], dc_predictor(zz, g, k, mcu_blocks, luma_blocks),
-               sh.dc[c], sh.ac[c], sink);
+    code_block(WordLoader{reinterpret_cast<const uint32_t*>(b)}, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
     bits = sink.total;
-    block_bits[g] = bits;
   }
   uint32_t total;
-  cta_exclusive_scan(bits, scratch, &total);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+  const uint32_t ex = cta_exclusive_scan(bits, scratch, &total);
+  if (threadIdx.x < 32) {
+    const unsigned long long p = warp_lookback(gb.bit_state + frame * gb.bit_state_pitch, blockIdx.x, total);
+    if (threadIdx.x == 0) {
+      tile_prefix = p;
+      if (blockIdx.x == gridDim.x - 1) gb.info[frame].total_bits = p + total;
+    }
+  }
+  __syncthreads();
+  if (!valid) return;
+  StreamOut out = {gb.words + frame * gb.words_pitch};
+  BitPackSink<StreamOut> sink(out, tile_prefix + ex);
+  code_block(WordLoader{reinterpret_cast<const uint32_t*>(b)}, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
+  sink.finish();
 }
 
 // S1 (entropy.cc:208-227)
@@ -549,78 +634,37 @@ struct SmemStats {
 };
 
 __global__ void __launch_bounds__(kTileBlocks)
-symbol_stats_kernel(const int16_t* __restrict__ zz, const uint32_t* __restrict__ nzmask, size_t nb_blocks,
-                    int mcu_blocks, int luma_blocks, uint32_t* __restrict__ freq) {
+symbol_stats_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   __shared__ uint32_t f[2][272];
   for (int i = threadIdx.x; i < 2 * 272; i += blockDim.x) (&f[0][0])[i] = 0;
   __syncthreads();
+  const int frame = blockIdx.y;
+  const int16_t* zz = gb.coef + frame * gb.coef_pitch;
+  const uint32_t* nzmask = gb.nzmask + frame * gb.mask_pitch;
+  const size_t nb_blocks = fs.blocks_per_frame;
   const size_t stride = static_cast<size_t>(gridDim.x) * kTileBlocks;
   for (size_t g = blockIdx.x * static_cast<size_t>(kTileBlocks) + threadIdx.x; g < nb_blocks; g += stride) {
-    const int k = static_cast<int>(g % mcu_blocks);
-    const int c = (k >= luma_blocks) ? 1 : 0;
+    const int k = static_cast<int>(g % fs.mcu_blocks);
+    const int c = (k >= fs.luma_blocks) ? 1 : 0;
     const int16_t* b = zz + g * 64;
     SmemStats add = {f[c]};
-    block_symbol_stats(WordLoader{reinterpret_cast<const uint32_t*>(b)}, nzmask[g], b[0], dc_predictor(zz, g, k, mcu_blocks, luma_blocks), add);
+    block_symbol_stats(WordLoader{reinterpret_cast<const uint32_t*>(b)}, nzmask[g], b[0],
+                       dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks), add);
   }
   __syncthreads();
+  uint32_t* freq = gb.freq + static_cast<size_t>(frame) * 2 * 272;
   for (int i = threadIdx.x; i < 2 * 272; i += blockDim.x) {
     const uint32_t c = (&f[0][0])[i];
     if (c) atomicAdd(&freq[i], c);
   }
 }
 
-// E2: one CTA scans all tile sums (tiles are few: nb_blocks / 256)
-__global__ void __launch_bounds__(1024)
-scan_tiles_kernel(const uint32_t* __restrict__ tile_sums, size_t nb_tiles,
-                  unsigned long long* __restrict__ tile_offsets, StreamInfo* __restrict__ info) {
-  __shared__ uint32_t scratch[33];
-  unsigned long long base = 0;
-  for (size_t i0 = 0; i0 < nb_tiles; i0 += blockDim.x) {
-    const size_t i = i0 + threadIdx.x;
-    const uint32_t v = (i < nb_tiles) ? tile_sums[i] : 0;
-    uint32_t total;
-    const uint32_t ex = cta_exclusive_scan(v, scratch, &total);
-    if (i < nb_tiles) tile_offsets[i] = base + ex;
-    base += total;
-  }
-  if (threadIdx.x == 0) info->total_bits = base;
-}
-
-// E3: pack (bit_writer.h:201-209 without the serial accumulator)
-struct StreamOut {
-  uint32_t* words;
-  __device__ __forceinline__ void or_word(uint64_t i, uint32_t v) { if (v) atomicOr(&words[i], v); }
-  __device__ __forceinline__ void set_word(uint64_t i, uint32_t v) { words[i] = v; }
-};
-
-__global__ void __launch_bounds__(kTileBlocks)
-pack_kernel(const int16_t* __restrict__ zz, const uint32_t* __restrict__ nzmask, size_t nb_blocks,
-            int mcu_blocks, int luma_blocks, const CodeTabs* __restrict__ tabs,
-            const uint32_t* __restrict__ block_bits, const unsigned long long* __restrict__ tile_offsets,
-            uint32_t* __restrict__ stream) {
-  __shared__ CodeTabs sh;
-  __shared__ uint32_t scratch[33];
-  load_code_tables(tabs, &sh);
-  const size_t g = blockIdx.x * static_cast<size_t>(kTileBlocks) + threadIdx.x;
-  const uint32_t bits = (g < nb_blocks) ? block_bits[g] : 0;
-  uint32_t total;
-  const uint32_t ex = cta_exclusive_scan(bits, scratch, &total);
-  if (g >= nb_blocks) return;
-  const int k = static_cast<int>(g % mcu_blocks);
-  const int c = (k >= luma_blocks) ? 1 : 0;
-  const int16_t* b = zz + g * 64;
-  StreamOut out = {stream};
-  BitPackSink<StreamOut> sink(out, tile_offsets[blockIdx.x] + ex);
-  code_block(WordLoader{reinterpret_cast<const uint32_t*>(b)}, nzmask[g], b[0], dc_predictor(zz, g, k, mcu_blocks, luma_blocks),
-             sh.dc[c], sh.ac[c], sink);
-  sink.finish();
-}
-
 // -------------------------------------------------------------------------------------------
-// E4: byte stuffing (bit_writer.h:172-196, bit_writer.cc:107-116, headers.cc:262-268).
+// S: byte stuffing (bit_writer.h:172-196, bit_writer.cc:107-116, headers.cc:262-268).
 // The word stream holds ceil(total_bits/8) bytes, MSB-first inside each word; the last byte is
 // padded with 1-bits.  Every 0xFF byte is followed by 0x00.  Tile = 4096 stream bytes per CTA
-// iteration, 16 bytes per thread.
+// iteration, 16 bytes per thread; persistent CTAs stride over the tiles (all CTAs are resident,
+// so the look-back chain always makes progress).
 // -------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 load_stream16(const uint32_t* stream, unsigned long long byte0,
                                                unsigned long long nbytes, unsigned long long total_bits) {
@@ -637,75 +681,50 @@ __device__ __forceinline__ uint4 load_stream16(const uint32_t* stream, unsigned 
   return w;
 }
 __device__ __forceinline__ int count_ff(uint32_t w) {
-  // a byte is 0xFF iff all its bits are set
+  // a byte is 0xFF iff all its bits are set; bytes past the end of the stream are zero
   uint32_t t = w & (w >> 4);
   t &= t >> 2;
   t &= t >> 1;
   return __popc(t & 0x01010101u);
 }
-__device__ __forceinline__ int valid_bytes(unsigned long long byte0, unsigned long long nbytes) {
-  return (byte0 >= nbytes) ? 0 : static_cast<int>(min(16ull, nbytes - byte0));
-}
-__device__ __forceinline__ int count_ff16(uint4 w, int valid) {
-  // bytes past 'valid' are zero in the stream (never written), so they never count
-  (void)valid;
-  return count_ff(w.x) + count_ff(w.y) + count_ff(w.z) + count_ff(w.w);
-}
+
+struct HeaderLens {
+  unsigned v[kMaxGroup];
+};
 
 __global__ void __launch_bounds__(256)
-ff_count_kernel(const uint32_t* __restrict__ stream, const StreamInfo* __restrict__ info,
-                uint32_t* __restrict__ ff_tile_sums) {
+stuff_kernel(GroupBuffers gb, const __grid_constant__ HeaderLens hl) {
   __shared__ uint32_t scratch[33];
-  const unsigned long long total_bits = info->total_bits;
+  __shared__ unsigned long long tile_prefix;
+  const int frame = blockIdx.y;
+  uint32_t* stream = gb.words + frame * gb.words_pitch;
+  unsigned long long* state = gb.ff_state + frame * gb.ff_state_pitch;
+  const unsigned long long total_bits = gb.info[frame].total_bits;
   const unsigned long long nbytes = (total_bits + 7) >> 3;
   const unsigned long long tiles = (nbytes + kStuffTileBytes - 1) / kStuffTileBytes;
+  uint8_t* out = gb.out + frame * gb.out_pitch + hl.v[frame];
   for (unsigned long long t = blockIdx.x; t < tiles; t += gridDim.x) {
     const unsigned long long byte0 = t * kStuffTileBytes + threadIdx.x * 16ull;
+    const int valid = (byte0 >= nbytes) ? 0 : static_cast<int>(min(16ull, nbytes - byte0));
     const uint4 w = load_stream16(stream, byte0, nbytes, total_bits);
+    const uint32_t ff = static_cast<uint32_t>(count_ff(w.x) + count_ff(w.y) + count_ff(w.z) + count_ff(w.w));
     uint32_t total;
-    cta_exclusive_scan(static_cast<uint32_t>(count_ff16(w, valid_bytes(byte0, nbytes))), scratch, &total);
-    if (threadIdx.x == 0) ff_tile_sums[t] = total;
-  }
-}
-
-__global__ void __launch_bounds__(1024)
-ff_scan_kernel(const uint32_t* __restrict__ ff_tile_sums, unsigned long long* __restrict__ ff_tile_offsets,
-               StreamInfo* __restrict__ info, unsigned long long header_len) {
-  __shared__ uint32_t scratch[33];
-  const unsigned long long nbytes = (info->total_bits + 7) >> 3;
-  const unsigned long long tiles = (nbytes + kStuffTileBytes - 1) / kStuffTileBytes;
-  unsigned long long base = 0;
-  for (unsigned long long i0 = 0; i0 < tiles; i0 += blockDim.x) {
-    const unsigned long long i = i0 + threadIdx.x;
-    const uint32_t v = (i < tiles) ? ff_tile_sums[i] : 0;
-    uint32_t total;
-    const uint32_t ex = cta_exclusive_scan(v, scratch, &total);
-    if (i < tiles) ff_tile_offsets[i] = base + ex;
-    base += total;
-  }
-  if (threadIdx.x == 0) {
-    info->stuffed_bytes = base;
-    info->out_size = header_len + nbytes + base + 2;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-stuff_kernel(uint32_t* __restrict__ stream, const unsigned long long* __restrict__ ff_tile_offsets,
-             const StreamInfo* __restrict__ info, uint8_t* __restrict__ out) {
-  __shared__ uint32_t scratch[33];
-  const unsigned long long total_bits = info->total_bits;
-  const unsigned long long nbytes = (total_bits + 7) >> 3;
-  const unsigned long long tiles = (nbytes + kStuffTileBytes - 1) / kStuffTileBytes;
-  for (unsigned long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-    const unsigned long long byte0 = t * kStuffTileBytes + threadIdx.x * 16ull;
-    const int valid = valid_bytes(byte0, nbytes);
-    const uint4 w = load_stream16(stream, byte0, nbytes, total_bits);
-    uint32_t total;
-    const uint32_t ex = cta_exclusive_scan(static_cast<uint32_t>(count_ff16(w, valid)), scratch, &total);
+    const uint32_t ex = cta_exclusive_scan(ff, scratch, &total);
+    if (threadIdx.x < 32) {
+      const unsigned long long p = warp_lookback(state, static_cast<long long>(t), total);
+      if (threadIdx.x == 0) {
+        tile_prefix = p;
+        if (t == tiles - 1) {
+          gb.info[frame].stuffed_bytes = p + total;
+          gb.info[frame].out_size = hl.v[frame] + nbytes + p + total + 2;
+        }
+      }
+    }
+    __syncthreads();
     if (valid > 0) {
       // self-cleaning: the stream buffer must be all zero for the next encode's atomicOr
       *reinterpret_cast<uint4*>(stream + (byte0 >> 2)) = make_uint4(0, 0, 0, 0);
-      uint8_t* dst = out + byte0 + ff_tile_offsets[t] + ex;
+      uint8_t* dst = out + byte0 + tile_prefix + ex;
       const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -720,6 +739,7 @@ stuff_kernel(uint32_t* __restrict__ stream, const unsigned long long* __restrict
         dst[1] = 0xd9;
       }
     }
+    __syncthreads();   // tile_prefix reused next iteration
   }
 }
 
@@ -736,21 +756,26 @@ struct TrellisNode {
 };
 
 __global__ void __launch_bounds__(64)
-trellis_kernel(int16_t* __restrict__ coef, uint32_t* __restrict__ nzmask, size_t nb_blocks,
-               int mcu_blocks, int luma_blocks, const __grid_constant__ QuantTabs qt,
-               const uint8_t* __restrict__ quant, const CodeTabs* __restrict__ tabs) {
+trellis_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   __shared__ uint8_t ac_len[2][256];
   __shared__ uint8_t qm[2][64];
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) ac_len[i >> 8][i & 255] = static_cast<uint8_t>(tabs->ac[i >> 8][i & 255] & 0xff);
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) qm[i >> 6][i & 63] = quant[i];
+  __shared__ int32_t qtab[2][64][2];
+  const int frame = blockIdx.y;
+  {
+    const CodeTabs* tabs = gb.tabs + frame;
+    const uint8_t* quant = gb.quant + frame * 128;
+    const int32_t* q = &gb.qtabs[frame].m[0].e[0][0];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) ac_len[i >> 8][i & 255] = static_cast<uint8_t>(tabs->ac[i >> 8][i & 255] & 0xff);
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) qm[i >> 6][i & 63] = quant[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) (&qtab[0][0][0])[i] = q[i];
+  }
   __syncthreads();
   const size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (g >= nb_blocks) return;
-  const int c = (static_cast<int>(g % mcu_blocks) >= luma_blocks) ? 1 : 0;
-  const QuantTab& t = qt.m[c];
+  if (g >= fs.blocks_per_frame) return;
+  const int c = (static_cast<int>(g % fs.mcu_blocks) >= fs.luma_blocks) ? 1 : 0;
   const uint8_t* len = ac_len[c];
   constexpr int zz[64] = SJB_ZIGZAG_INIT;
-  int16_t* blk = coef + g * 64;
+  int16_t* blk = gb.coef + frame * gb.coef_pitch + g * 64;
 
   TrellisNode nodes[1 + 2 * 63];
   uint32_t disto0[64];
@@ -773,7 +798,7 @@ trellis_kernel(int16_t* __restrict__ coef, uint32_t* __restrict__ nzmask, size_t
     const int sign = x >> 31;
     const int V = (x ^ sign) - sign;
     disto0[i] = static_cast<uint32_t>(V * V) + disto0[i - 1];
-    int v = (V * t.e[i][0] + t.e[i][1]) >> 20;   // V >= 0
+    int v = (V * qtab[c][i][0] + qtab[c][i][1]) >> 20;   // V >= 0
     if (v == 0) continue;
     int nbits = bit_length(static_cast<uint32_t>(v));
     for (int k = 0; k < 2; ++k) {
@@ -820,7 +845,7 @@ trellis_kernel(int16_t* __restrict__ coef, uint32_t* __restrict__ nzmask, size_t
   int16_t outv[64];
 #pragma unroll
   for (int i = 0; i < 64; ++i) outv[i] = 0;
-  outv[0] = static_cast<int16_t>(quantize_coeff(in[0], t.e[0][0], t.e[0][1]));
+  outv[0] = static_cast<int16_t>(quantize_coeff(in[0], qtab[c][0][0], qtab[c][0][1]));
   uint32_t mask = (outv[0] != 0) ? 1u : 0u;
   for (int p = best; p > 0; p = nodes[p].prev) {
     const int n = nodes[p].nbits;
@@ -835,65 +860,66 @@ trellis_kernel(int16_t* __restrict__ coef, uint32_t* __restrict__ nzmask, size_t
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = s[i];
   }
-  nzmask[g] = mask;
+  gb.nzmask[frame * gb.mask_pitch + g] = mask;
 }
 
-int cdiv(size_t a, size_t b) { return static_cast<int>((a + b - 1) / b); }
+unsigned cdiv(size_t a, size_t b) { return static_cast<unsigned>((a + b - 1) / b); }
 
 }  // namespace
 
 // -------------------------------------------------------------------------------------------
 // launch wrappers
 // -------------------------------------------------------------------------------------------
-static int McuBlocks(int mode) { return mode == kYuv420 ? 6 : (mode == kYuv444 ? 3 : 1); }
-
-void LaunchF1Generic(const ImageDesc& img, int mx0, int my0, int mx1, int my1, bool raw,
-                     const QuantTabs& qt, int16_t* coef, uint32_t* nzmask, cudaStream_t s) {
+void LaunchF1Generic(const FrameSet& fs, int mx0, int my0, int mx1, int my1, bool raw,
+                     const QuantTabs& qt, const GroupBuffers& gb, cudaStream_t s) {
   if (mx1 <= mx0 || my1 <= my0) return;
-  const int mb = McuBlocks(img.yuv_mode);
-  const size_t nb = static_cast<size_t>(mx1 - mx0) * (my1 - my0) * mb;
-  if (raw) f1_generic_kernel<true><<<cdiv(nb, 128), 128, 0, s>>>(img, mx0, my0, mx1, my1, mb, qt, coef, nzmask);
-  else     f1_generic_kernel<false><<<cdiv(nb, 128), 128, 0, s>>>(img, mx0, my0, mx1, my1, mb, qt, coef, nzmask);
+  const size_t nb = static_cast<size_t>(mx1 - mx0) * (my1 - my0) * fs.mcu_blocks;
+  const dim3 grid(cdiv(nb, 128), fs.frames);
+  if (raw) f1_generic_kernel<true><<<grid, 128, 0, s>>>(fs, mx0, my0, mx1, my1, qt, gb);
+  else     f1_generic_kernel<false><<<grid, 128, 0, s>>>(fs, mx0, my0, mx1, my1, qt, gb);
 }
 
-bool F1FastEligible(const ImageDesc& img) {
-  return img.pix_fmt == kFmtRGB && (reinterpret_cast<uintptr_t>(img.pix) & 15) == 0 && (img.stride & 15) == 0;
+bool F1FastEligible(const FrameSet& fs) {
+  if (fs.pix_fmt != kFmtRGB || (fs.stride & 15) != 0) return false;
+  for (int f = 0; f < fs.frames; ++f) {
+    if ((reinterpret_cast<uintptr_t>(fs.pix[f]) & 15) != 0) return false;
+  }
+  return true;
 }
 
 template <int kMode, bool kRaw>
-static void LaunchF1FastT(const ImageDesc& img, int mx_full, int my0, int my1, const QuantTabs& qt,
-                          int16_t* coef, uint32_t* nzmask, cudaStream_t s) {
+static void LaunchF1FastT(const FrameSet& fs, int mx_full, int my0, int my1, const QuantTabs& qt,
+                          const GroupBuffers& gb, cudaStream_t s) {
   const int per_tile = (kMode == kYuv420) ? 16 : 32;
   const long long tiles = static_cast<long long>((mx_full + per_tile - 1) / per_tile) * (my1 - my0);
-  f1_fast_kernel<kMode, kRaw><<<static_cast<unsigned>(tiles), 32, 0, s>>>(img, mx_full, my0, qt, coef, nzmask);
+  const dim3 grid(static_cast<unsigned>(tiles), fs.frames);
+  f1_fast_kernel<kMode, kRaw><<<grid, 32, 0, s>>>(fs, mx_full, my0, qt, gb);
 }
 
-void LaunchF1Fast(const ImageDesc& img, int mx_full, int my0, int my1, bool raw, const QuantTabs& qt,
-                  int16_t* coef, uint32_t* nzmask, cudaStream_t s) {
+void LaunchF1Fast(const FrameSet& fs, int mx_full, int my0, int my1, bool raw, const QuantTabs& qt,
+                  const GroupBuffers& gb, cudaStream_t s) {
   if (mx_full <= 0 || my1 <= my0) return;
-  switch (img.yuv_mode) {
+  switch (fs.yuv_mode) {
     case kYuv420:
-      if (raw) LaunchF1FastT<kYuv420, true>(img, mx_full, my0, my1, qt, coef, nzmask, s);
-      else     LaunchF1FastT<kYuv420, false>(img, mx_full, my0, my1, qt, coef, nzmask, s);
+      if (raw) LaunchF1FastT<kYuv420, true>(fs, mx_full, my0, my1, qt, gb, s);
+      else     LaunchF1FastT<kYuv420, false>(fs, mx_full, my0, my1, qt, gb, s);
       break;
     case kYuv444:
-      if (raw) LaunchF1FastT<kYuv444, true>(img, mx_full, my0, my1, qt, coef, nzmask, s);
-      else     LaunchF1FastT<kYuv444, false>(img, mx_full, my0, my1, qt, coef, nzmask, s);
+      if (raw) LaunchF1FastT<kYuv444, true>(fs, mx_full, my0, my1, qt, gb, s);
+      else     LaunchF1FastT<kYuv444, false>(fs, mx_full, my0, my1, qt, gb, s);
       break;
     default:
-      if (raw) LaunchF1FastT<kYuv400, true>(img, mx_full, my0, my1, qt, coef, nzmask, s);
-      else     LaunchF1FastT<kYuv400, false>(img, mx_full, my0, my1, qt, coef, nzmask, s);
+      if (raw) LaunchF1FastT<kYuv400, true>(fs, mx_full, my0, my1, qt, gb, s);
+      else     LaunchF1FastT<kYuv400, false>(fs, mx_full, my0, my1, qt, gb, s);
       break;
   }
 }
 
-void LaunchRequantize(int16_t* coef, uint32_t* nzmask, size_t nb_blocks, int mcu_blocks,
-                      int luma_blocks, const QuantTabs& qt, cudaStream_t s) {
-  requantize_kernel<<<cdiv(nb_blocks, 128), 128, 0, s>>>(coef, nzmask, nb_blocks, mcu_blocks, luma_blocks, qt);
+void LaunchRequantize(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {
+  requantize_kernel<<<dim3(cdiv(fs.blocks_per_frame, 128), fs.frames), 128, 0, s>>>(fs, gb);
 }
 
-void LaunchHistogram(const int16_t* raw_coef, size_t nb_blocks, int mcu_blocks, int luma_blocks,
-                     int32_t* counts, cudaStream_t s) {
+void LaunchHistogram(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {
   static bool init[64] = {false};
   const size_t smem = 2 * 64 * 128 * sizeof(int32_t);
   int dev = 0;
@@ -903,52 +929,37 @@ void LaunchHistogram(const int16_t* raw_coef, size_t nb_blocks, int mcu_blocks, 
     cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     init[dev] = true;
   }
-  int grid = cdiv(nb_blocks * 8, 256 * 16);
-  if (grid > 148 * 3) grid = 148 * 3;
+  unsigned grid = cdiv(static_cast<size_t>(fs.blocks_per_frame) * 8, 256 * 16);
+  const unsigned cap = 148 * 3 / (fs.frames > 0 ? fs.frames : 1) + 1;
+  if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  histogram_kernel<<<grid, 256, smem, s>>>(raw_coef, nb_blocks, mcu_blocks, luma_blocks, counts);
+  histogram_kernel<<<dim3(grid, fs.frames), 256, smem, s>>>(fs, gb);
 }
 
-void LaunchTrellis(int16_t* coef, uint32_t* nzmask, size_t nb_blocks, int mcu_blocks,
-                   int luma_blocks, const QuantTabs& qt, const uint8_t* quant, const CodeTabs* tabs,
-                   cudaStream_t s) {
-  trellis_kernel<<<cdiv(nb_blocks, 64), 64, 0, s>>>(coef, nzmask, nb_blocks, mcu_blocks, luma_blocks, qt, quant, tabs);
+void LaunchTrellis(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {
+  trellis_kernel<<<dim3(cdiv(fs.blocks_per_frame, 64), fs.frames), 64, 0, s>>>(fs, gb);
 }
 
-void LaunchSymbolStats(const int16_t* zz, const uint32_t* nzmask, size_t nb_blocks, int mcu_blocks,
-                       int luma_blocks, uint32_t* freq, cudaStream_t s) {
-  int grid = cdiv(nb_blocks, kTileBlocks);
-  if (grid > 148 * 8) grid = 148 * 8;
-  symbol_stats_kernel<<<grid, kTileBlocks, 0, s>>>(zz, nzmask, nb_blocks, mcu_blocks, luma_blocks, freq);
+void LaunchSymbolStats(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {
+  unsigned grid = cdiv(fs.blocks_per_frame, kTileBlocks);
+  const unsigned cap = 148 * 8 / (fs.frames > 0 ? fs.frames : 1) + 1;
+  if (grid > cap) grid = cap;
+  symbol_stats_kernel<<<dim3(grid, fs.frames), kTileBlocks, 0, s>>>(fs, gb);
 }
 
-void LaunchBlockBits(const int16_t* zz, const uint32_t* nzmask, size_t nb_blocks, int mcu_blocks,
-                     int luma_blocks, const CodeTabs* tabs, uint32_t* block_bits,
-                     uint32_t* tile_sums, cudaStream_t s) {
-  block_bits_kernel<<<cdiv(nb_blocks, kTileBlocks), kTileBlocks, 0, s>>>(zz, nzmask, nb_blocks, mcu_blocks,
-                                                                         luma_blocks, tabs, block_bits, tile_sums);
+void LaunchEntropyPack(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {
+  entropy_pack_kernel<<<dim3(cdiv(fs.blocks_per_frame, kTileBlocks), fs.frames), kTileBlocks, 0, s>>>(fs, gb);
 }
 
-void LaunchScanTiles(const uint32_t* tile_sums, size_t nb_tiles, unsigned long long* tile_offsets,
-                     StreamInfo* info, cudaStream_t s) {
-  scan_tiles_kernel<<<1, 1024, 0, s>>>(tile_sums, nb_tiles, tile_offsets, info);
-}
-
-void LaunchPack(const int16_t* zz, const uint32_t* nzmask, size_t nb_blocks, int mcu_blocks,
-                int luma_blocks, const CodeTabs* tabs, const uint32_t* block_bits,
-                const unsigned long long* tile_offsets, uint32_t* stream, cudaStream_t s) {
-  pack_kernel<<<cdiv(nb_blocks, kTileBlocks), kTileBlocks, 0, s>>>(zz, nzmask, nb_blocks, mcu_blocks, luma_blocks,
-                                                                   tabs, block_bits, tile_offsets, stream);
-}
-
-void LaunchStuff(uint32_t* stream, size_t max_stream_words, uint32_t* ff_tile_sums,
-                 unsigned long long* ff_tile_offsets, StreamInfo* info, uint8_t* out,
-                 size_t header_len, cudaStream_t s) {
-  size_t tiles = (max_stream_words * 4 + kStuffTileBytes - 1) / kStuffTileBytes;
-  int grid = static_cast<int>(tiles < 148 * 8 ? (tiles ? tiles : 1) : 148 * 8);
-  ff_count_kernel<<<grid, 256, 0, s>>>(stream, info, ff_tile_sums);
-  ff_scan_kernel<<<1, 1024, 0, s>>>(ff_tile_sums, ff_tile_offsets, info, header_len);
-  stuff_kernel<<<grid, 256, 0, s>>>(stream, ff_tile_offsets, info, out + header_len);
+void LaunchStuff(const FrameSet& fs, const GroupBuffers& gb, const unsigned* header_len, cudaStream_t s) {
+  HeaderLens hl;
+  for (int f = 0; f < kMaxGroup; ++f) hl.v[f] = (f < fs.frames) ? header_len[f] : 0;
+  // persistent CTAs: all of them must be resident for the look-back to make progress
+  const size_t max_tiles = (gb.words_pitch * 4 + kStuffTileBytes - 1) / kStuffTileBytes;
+  unsigned grid = 148 * 4 / (fs.frames > 0 ? fs.frames : 1);
+  if (grid < 1) grid = 1;
+  if (grid > max_tiles) grid = static_cast<unsigned>(max_tiles);
+  stuff_kernel<<<dim3(grid, fs.frames), 256, 0, s>>>(gb, hl);
 }
 
 }  // namespace sjb

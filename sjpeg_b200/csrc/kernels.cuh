@@ -1,5 +1,9 @@
 // kernels.cuh -- launch wrappers of the sm_100a kernels (kernels.cu).  Host code (engine.cu)
 // sees only these plain functions; every pointer is a device pointer unless stated.
+//
+// All kernels work on a GROUP of up to kMaxGroup pictures of identical geometry in one launch
+// (gridDim.y = picture): a single 4K picture is only ~2000 warp-tiles, too few to balance 592
+// warp schedulers, and per-picture launches of the small entropy kernels are latency bound.
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -9,19 +13,23 @@
 
 namespace sjb {
 
-enum { kTileBlocks = 256 };        // 8x8 blocks per CTA in the entropy kernels (scan tile)
-enum { kStuffTileBytes = 4096 };   // stream bytes per CTA tile in the stuffing kernels
+enum { kMaxGroup = 8 };
+enum { kTileBlocks = 256 };        // 8x8 blocks per CTA in the entropy kernel (look-back tile)
+enum { kStuffTileBytes = 4096 };   // stream bytes per CTA iteration in the stuffing kernel
 
-struct ImageDesc {
-  const uint8_t* pix;   // row 0 of the image (device)
-  long long stride;     // bytes between rows, may be negative
+struct FrameSet {
+  const uint8_t* pix[kMaxGroup];   // row 0 of each picture
+  int frames;
+  long long stride;                // bytes between rows, may be negative
   int width, height;
-  int yuv_mode;         // kYuv420 / kYuv444 / kYuv400
-  int pix_fmt;          // kFmtRGB / kFmtBGRA / kFmtRGBA
+  int yuv_mode;                    // kYuv420 / kYuv444 / kYuv400
+  int pix_fmt;                     // kFmtRGB / kFmtBGRA / kFmtRGBA
   int mcus_x, mcus_y;
+  int mcu_blocks, luma_blocks;
+  unsigned blocks_per_frame;
 };
 
-// Device-side scalars of one encode (one cache line).
+// Device-side scalars of one picture (one 32-byte record).
 struct StreamInfo {
   unsigned long long total_bits;    // entropy-coded bits before padding
   unsigned long long stuffed_bytes; // number of 0xFF bytes that got a 0x00 appended
@@ -29,49 +37,52 @@ struct StreamInfo {
   unsigned long long pad;
 };
 
-// F1: colour convert + fDCT (+ quantise) for the MCU rectangle [mx0,mx1) x [my0,my1).
+// Per-lane device arrays, picture-major with fixed pitches (in elements of the pointed type).
+struct GroupBuffers {
+  int16_t* coef;            size_t coef_pitch;    // [frames][blocks*64]
+  uint32_t* nzmask;         size_t mask_pitch;    // [frames][blocks]
+  uint32_t* words;          size_t words_pitch;   // [frames][worst-case stream words], zero between encodes
+  uint8_t* out;             size_t out_pitch;     // [frames][worst-case file bytes]
+  unsigned long long* bit_state; size_t bit_state_pitch;   // look-back descriptors of the entropy kernel
+  unsigned long long* ff_state;  size_t ff_state_pitch;    // look-back descriptors of the stuffing kernel
+  StreamInfo* info;         // [frames]
+  CodeTabs* tabs;           // [frames]
+  QuantTabs* qtabs;         // [frames]  (adaptive methods: per-picture matrices)
+  int32_t* hist;            // [frames][2][64][129]
+  uint32_t* freq;           // [frames][2][272]
+  uint8_t* quant;           // [frames][2][64]
+};
+
+// F1: colour convert + fDCT (+ quantise) for the MCU rectangle [mx0,mx1) x [my0,my1) of every
+// picture of the set.
 //   raw = true : coef receives the unquantised x16 coefficients, natural order
 //   raw = false: coef receives quantised values in zig-zag order, nzmask the non-zero PAIR bitmaps
 //                (bit p set <=> zig-zag positions 2p, 2p+1 are not both zero; bit 0 includes the DC)
 // generic path: any stride / alignment / pixel format, edge replication (encoders.cc:157-253)
-void LaunchF1Generic(const ImageDesc& img, int mx0, int my0, int mx1, int my1, bool raw,
-                     const QuantTabs& qt, int16_t* coef, uint32_t* nzmask, cudaStream_t s);
-// fast path: 4:2:0 / 4:4:4 / 4:0:0, RGB24, full MCUs only, rows 16-byte aligned (stride % 16 == 0,
-// base % 16 == 0); rows [my0,my1) x all columns [0, mx_full).  Bulk-async (TMA) staged tiles.
-bool F1FastEligible(const ImageDesc& img);
-void LaunchF1Fast(const ImageDesc& img, int mx_full, int my0, int my1, bool raw, const QuantTabs& qt,
-                  int16_t* coef, uint32_t* nzmask, cudaStream_t s);
+void LaunchF1Generic(const FrameSet& fs, int mx0, int my0, int mx1, int my1, bool raw,
+                     const QuantTabs& qt, const GroupBuffers& gb, cudaStream_t s);
+// fast path: RGB24, full MCUs only, rows 16-byte aligned (stride % 16 == 0, every base % 16 == 0);
+// MCU rows [my0,my1) x columns [0, mx_full).  Bulk-async (TMA engine) staged strips.
+bool F1FastEligible(const FrameSet& fs);
+void LaunchF1Fast(const FrameSet& fs, int mx_full, int my0, int my1, bool raw, const QuantTabs& qt,
+                  const GroupBuffers& gb, cudaStream_t s);
 
-// Q1: quantise stored raw coefficients in place (natural int16 -> zig-zag int16) + nzmask
-void LaunchRequantize(int16_t* coef, uint32_t* nzmask, size_t nb_blocks, int mcu_blocks,
-                      int luma_blocks, const QuantTabs& qt, cudaStream_t s);
-// H1: histogram of |coef| >> 2 per matrix and position: counts[2][64][129] (int32, pre-zeroed)
-void LaunchHistogram(const int16_t* raw_coef, size_t nb_blocks, int mcu_blocks, int luma_blocks,
-                     int32_t* counts, cudaStream_t s);
-// T1: trellis quantisation of raw coefficients in place (quantize.cc:388-457) + nzmask.
-// quant = the two 8-bit matrices (device, natural order); rate from ac code lengths in tabs.
-void LaunchTrellis(int16_t* coef, uint32_t* nzmask, size_t nb_blocks, int mcu_blocks,
-                   int luma_blocks, const QuantTabs& qt, const uint8_t* quant, const CodeTabs* tabs,
-                   cudaStream_t s);
+// Q1: quantise stored raw coefficients in place (natural -> zig-zag) + bitmap; tables gb.qtabs[frame]
+void LaunchRequantize(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s);
+// H1: histogram of |coef| >> 2 per matrix and position into gb.hist[frame] (pre-zeroed)
+void LaunchHistogram(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s);
+// T1: trellis quantisation of raw coefficients in place (quantize.cc:388-457) + bitmap; tables
+// gb.qtabs[frame], matrices gb.quant[frame], rate from the AC code lengths in gb.tabs[frame]
+void LaunchTrellis(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s);
+// S1: symbol statistics into gb.freq[frame] (slot < 256 AC symbol, 256+n DC size), pre-zeroed
+void LaunchSymbolStats(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s);
 
-// S1: symbol statistics: freq[2][272] (slot < 256 AC symbol, 256+n DC size), pre-zeroed
-void LaunchSymbolStats(const int16_t* zz, const uint32_t* nzmask, size_t nb_blocks, int mcu_blocks,
-                       int luma_blocks, uint32_t* freq, cudaStream_t s);
-// E1: bits per block + per-tile sums
-void LaunchBlockBits(const int16_t* zz, const uint32_t* nzmask, size_t nb_blocks, int mcu_blocks,
-                     int luma_blocks, const CodeTabs* tabs, uint32_t* block_bits,
-                     uint32_t* tile_sums, cudaStream_t s);
-// E2: exclusive scan of the tile sums (u32 -> u64) and the grand total into info->total_bits
-void LaunchScanTiles(const uint32_t* tile_sums, size_t nb_tiles, unsigned long long* tile_offsets,
-                     StreamInfo* info, cudaStream_t s);
-// E3: pack the code words at their bit offsets into the (zeroed) word stream
-void LaunchPack(const int16_t* zz, const uint32_t* nzmask, size_t nb_blocks, int mcu_blocks,
-                int luma_blocks, const CodeTabs* tabs, const uint32_t* block_bits,
-                const unsigned long long* tile_offsets, uint32_t* stream, cudaStream_t s);
-// E4: 0xFF stuffing.  Count per tile, scan, then scatter to out + header_len, append padding and
-// EOI, zero the consumed stream words, write info->out_size.
-void LaunchStuff(uint32_t* stream, size_t max_stream_words, uint32_t* ff_tile_sums,
-                 unsigned long long* ff_tile_offsets, StreamInfo* info, uint8_t* out,
-                 size_t header_len, cudaStream_t s);
+// E: bits per block, decoupled look-back prefix over 256-block tiles, bit packing into gb.words;
+// the last tile of each picture writes info.total_bits.  gb.bit_state must be zero on entry.
+void LaunchEntropyPack(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s);
+// S: 0xFF stuffing with a decoupled look-back over 4 KB stream tiles: scatter to out + header_len,
+// padding, EOI, info.out_size; zeroes the consumed stream words.  gb.ff_state zero on entry.
+void LaunchStuff(const FrameSet& fs, const GroupBuffers& gb, const unsigned* header_len /* host, [frames] */,
+                 cudaStream_t s);
 
 }  // namespace sjb

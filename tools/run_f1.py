@@ -31,9 +31,10 @@ def clocks():
 if what == "f1":
     for _ in range(3):
         ctx.bench_f1(ptrs, w, h, 3 * w, p, 40)      # warm-up: clocks ramp, I-cache, TLB
-    ms = min(ctx.bench_f1(ptrs, w, h, 3 * w, p, iters) for _ in range(5))
-    print("clocks:", clocks())
-    print("f1 ms/launch %.5f  -> %.1f GB/s algorithmic" % (ms, (3 * w * h * 2) / ms / 1e6))
+    ms, fpl = min(ctx.bench_f1(ptrs, w, h, 3 * w, p, iters) for _ in range(5))
+    print("clocks:", clocks(), "frames/launch", fpl)
+    ms /= fpl
+    print("f1 ms/frame %.5f  -> %.1f GB/s algorithmic" % (ms, (3 * w * h * 2) / ms / 1e6))
 else:
     for _ in range(3):
         ctx.bench_device(ptrs, w, h, 3 * w, p, 10)
