@@ -93,7 +93,7 @@ def cpu_reference_throughput(frames, seconds_budget=12.0):
     t0 = time.perf_counter()
     enc(frames[0], W, H, 3 * W, QUALITY, METHOD, O.YUV_420)
     probe = time.perf_counter() - t0
-    rounds = max(1, min(8, int(seconds_budget / max(probe * 1.5, 1e-3))))
+    rounds = max(1, min(2000, int(seconds_budget / max(probe * 1.3, 1e-3))))
     done = [0] * nthreads
 
     def work(t):
@@ -125,7 +125,7 @@ def run_reference(args):
     vals = []
     total_dt = 0.0
     for _ in range(args.steps):
-        v, kind, cores, sample, dt, n = cpu_reference_throughput(frames, seconds_budget=60.0 / max(args.steps, 1))
+        v, kind, cores, sample, dt, n = cpu_reference_throughput(frames, seconds_budget=min(15.0, 90.0 / max(args.steps, 1)))
         vals.append(v)
         total_dt += dt
     value = sum(vals) / len(vals)
@@ -241,7 +241,7 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N == 1 only) --------------------------------------------------
     cpu = None
     if world == 1:
-        v, kind, cores, sample, _, _ = cpu_reference_throughput(frames[:4])
+        v, kind, cores, sample, _, _ = cpu_reference_throughput(frames[:4], seconds_budget=12.0)
         cpu = {"value": round(v, 2), "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample}
 
     line = {

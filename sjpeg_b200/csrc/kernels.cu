@@ -583,11 +583,39 @@ struct StreamOut {
   __device__ __forceinline__ void set_word(uint64_t i, uint32_t v) { words[i] = v; }
 };
 
+// Per-thread sink of pass 1: counts the bits and, as long as they fit, keeps the packed words of
+// the block (bit 0 of the block = MSB of word 0) in a private shared-memory slot.
+enum { kLocalWords = 16 };            // 512 bits per block kept; longer blocks are re-walked
+struct LocalSink {
+  uint32_t* w;                        // slot of kLocalWords words
+  uint64_t acc;
+  int n, nw;
+  uint32_t total;
+  __device__ __forceinline__ void put(uint32_t bits, int len) {
+    total += static_cast<uint32_t>(len);
+    acc |= static_cast<uint64_t>(bits) << (64 - n - len);
+    n += len;
+    if (n >= 32) {
+      if (nw < kLocalWords) w[nw] = static_cast<uint32_t>(acc >> 32);
+      ++nw;
+      acc <<= 32;
+      n -= 32;
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    if (n > 0) {
+      if (nw < kLocalWords) w[nw] = static_cast<uint32_t>(acc >> 32);
+      ++nw;
+    }
+  }
+};
+
 __global__ void __launch_bounds__(kTileBlocks)
 entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   __shared__ CodeTabs sh;
   __shared__ uint32_t scratch[33];
   __shared__ unsigned long long tile_prefix;
+  __shared__ uint32_t local[kTileBlocks][kLocalWords + 1];   // odd stride: conflict-free
   const int frame = blockIdx.y;
   load_code_tables(gb.tabs + frame, &sh);
   const int16_t* zz = gb.coef + frame * gb.coef_pitch;
@@ -599,15 +627,19 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   uint32_t mask = 0;
   const int16_t* b = zz + (valid ? g : 0) * 64;
   uint32_t bits = 0;
+  int nw = 0;
+  uint32_t* mine = local[threadIdx.x];
   if (valid) {
     k = static_cast<int>(g % fs.mcu_blocks);
     c = (k >= fs.luma_blocks) ? 1 : 0;
     mask = nzmask[g];
     dc = b[0];
     pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks);
-    BitCountSink sink = {0};
+    LocalSink sink = {mine, 0, 0, 0, 0};
     code_block(WordLoader{reinterpret_cast<const uint32_t*>(b)}, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
+    sink.finish();
     bits = sink.total;
+    nw = sink.nw;
   }
   uint32_t total;
   const uint32_t ex = cta_exclusive_scan(bits, scratch, &total);
@@ -620,10 +652,28 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   }
   __syncthreads();
   if (!valid) return;
-  StreamOut out = {gb.words + frame * gb.words_pitch};
-  BitPackSink<StreamOut> sink(out, tile_prefix + ex);
-  code_block(WordLoader{reinterpret_cast<const uint32_t*>(b)}, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
-  sink.finish();
+  uint32_t* stream = gb.words + frame * gb.words_pitch;
+  const unsigned long long offset = tile_prefix + ex;
+  if (nw <= kLocalWords) {
+    // copy the kept words to their place in the stream, shifted by the bit offset; the first and
+    // the last stream word may be shared with the neighbouring blocks (OR), the others are owned
+    const unsigned long long w0 = offset >> 5, wl = (offset + bits - 1) >> 5;
+    const int s = static_cast<int>(offset & 31);
+    uint32_t prev = 0;
+    for (unsigned long long j = w0; j <= wl; ++j) {
+      const int kk = static_cast<int>(j - w0);
+      const uint32_t cur = (kk < nw) ? mine[kk] : 0u;
+      const uint32_t v = __funnelshift_r(cur, prev, s);     // (prev << (32-s)) | (cur >> s)
+      prev = cur;
+      if (j == w0 || j == wl) { if (v) atomicOr(&stream[j], v); }
+      else stream[j] = v;
+    }
+  } else {
+    StreamOut out = {stream};
+    BitPackSink<StreamOut> sink(out, offset);
+    code_block(WordLoader{reinterpret_cast<const uint32_t*>(b)}, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
+    sink.finish();
+  }
 }
 
 // S1 (entropy.cc:208-227)
