@@ -26,7 +26,16 @@ using namespace sjb;
 namespace {
 
 enum { kMaxLanes = 4, kHeaderReserve = 2048, kWorstBitsPerBlock = 1696 };
-const size_t kGroupCoefBudget = 64u << 20;   // keep a group's coefficients inside the 126 MB L2
+// A group's coefficients should stay inside the 126 MB L2 between F1 and the entropy kernel.
+// SJB_GROUP_BUDGET_MB overrides the default (for experiments).
+size_t GroupCoefBudget() {
+  static const size_t v = [] {
+    const char* e = getenv("SJB_GROUP_BUDGET_MB");
+    const long mb = e ? atol(e) : 100;
+    return static_cast<size_t>(mb > 0 ? mb : 100) << 20;
+  }();
+  return v;
+}
 
 struct DeviceBuffer {
   void* ptr = nullptr;
@@ -168,7 +177,7 @@ int MakePlan(int width, int height, long long stride, const sjb_params* params, 
   plan->nb_tiles = (nb + kTileBlocks - 1) / kTileBlocks;
   plan->ff_tiles = (plan->stream_words * 4 + kStuffTileBytes - 1) / kStuffTileBytes;
   const size_t coef_bytes = nb * 128;
-  plan->group = static_cast<int>(std::min<size_t>(kMaxGroup, std::max<size_t>(1, kGroupCoefBudget / coef_bytes)));
+  plan->group = static_cast<int>(std::min<size_t>(kMaxGroup, std::max<size_t>(1, GroupCoefBudget() / coef_bytes)));
   return SJB_OK;
 }
 
