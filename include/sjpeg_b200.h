@@ -94,6 +94,36 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
                      int height, long long stride, const sjb_params* params, uint8_t* const* out,
                      int out_on_device, size_t out_capacity, size_t* sizes);
 
+/*
+ * Row stripes: a picture split into horizontal stripes of whole MCU rows, one stripe per GPU
+ * (BASELINE.json config 5; the reference has no restart markers, headers.cc:242-258, so the
+ * stripes of one picture form a single bit string and need two tiny exchanges between ranks).
+ * A session holds this rank's stripe of each of n pictures.  Method 0 (default tables) only.
+ *   1. transform: colour convert + fDCT + quantise; last_dc[n][3] = quantised DC of the last
+ *      Y / U / V block of every stripe                         -> exchange with the next rank
+ *   2. code:      entropy-code with dc_pred[n][3] = last_dc of the previous rank's stripe (zeros
+ *      on the first rank, entropy.cc:155-159); bits[n] = bit count  -> all-gather, prefix sum
+ *   3. finish:    byte-align to the global bit offset, 0xFF-stuff (bit_writer.h:172-196) the bytes
+ *      owned entirely by this stripe into out[i]; the byte shared with the previous stripe
+ *      (head_byte, present iff offset % 8 != 0) and with the next one (tail_byte, tail_bits of it
+ *      ours) are returned for the gatherer to OR together and stuff.  The last rank pads with
+ *      1-bits and appends EOI (headers.cc:262-268).  sjb_picture_header gives the bytes before
+ *      the scan.
+ */
+typedef struct sjb_stripes sjb_stripes;
+int sjb_stripes_create(sjb_context* ctx, int n, int width, int stripe_height, const sjb_params* params,
+                       sjb_stripes** out);
+void sjb_stripes_destroy(sjb_stripes* s);
+int sjb_stripes_transform(sjb_stripes* s, const uint8_t* const* pix, int pix_on_device, long long stride,
+                          int* last_dc);
+int sjb_stripes_code(sjb_stripes* s, const int* dc_pred, unsigned long long* bits);
+int sjb_stripes_finish(sjb_stripes* s, const unsigned long long* bit_offsets, int is_first, int is_last,
+                       uint8_t* const* out, size_t out_capacity, size_t* sizes, unsigned char* head_byte,
+                       unsigned char* tail_byte, unsigned char* tail_bits);
+/* SOI..SOS bytes of a method-0 picture (headers.cc:48-61,182-258); host only */
+int sjb_picture_header(const sjb_params* params, int width, int height, uint8_t* out, size_t out_capacity,
+                       size_t* out_size);
+
 /* Pinned host memory helpers (for callers that want async copies at PCIe speed). */
 void* sjb_host_alloc(size_t bytes);
 void sjb_host_free(void* p);

@@ -641,7 +641,7 @@ int sjo_build_optimal_table(const uint32_t* freq, int size, uint8_t out_bits[16]
 /* ------------------------------------------------------------------------------------------
  * Bit writer (bit_writer.h:172-209, bit_writer.cc:107-116): MSB first, 0xFF -> 0xFF 0x00
  * ---------------------------------------------------------------------------------------- */
-typedef struct { uint8_t* buf; size_t pos, cap; uint64_t acc; int nb; int ok; } BW;
+typedef struct { uint8_t* buf; size_t pos, cap; uint64_t acc; int nb; int ok; int raw; uint64_t nbits; } BW;
 
 static void bw_need(BW* w, size_t extra) {
   if (w->pos + extra <= w->cap) return;
@@ -659,11 +659,12 @@ static void bw_flush_bits(BW* w) {
   while (w->nb >= 8) {
     const int b = (int)(w->acc >> 56);
     bw_byte(w, b);
-    if (b == 0xff) bw_byte(w, 0x00);
+    if (b == 0xff && !w->raw) bw_byte(w, 0x00);
     w->acc <<= 8; w->nb -= 8;
   }
 }
 static void bw_put(BW* w, uint32_t bits, int nb) {
+  w->nbits += (uint64_t)nb;
   if (w->nb + nb > 56) bw_flush_bits(w);
   w->nb += nb;
   w->acc |= (uint64_t)bits << (64 - w->nb);
@@ -1096,6 +1097,64 @@ size_t sjo_sjpeg_encode(const uint8_t* rgb, int w, int h, int stride, float qual
 }
 
 void sjo_free(uint8_t* p) { free(p); }
+
+/* A horizontal stripe of whole MCU rows coded on its own (multi-GPU row striping):
+ * the same per-block pipeline as sjo_encode() for method 0 (default Huffman tables), but the DC
+ * predictors start from dc_pred[] (entropy.cc:133-136 carried across the stripe boundary) and the
+ * result is the RAW entropy-coded bit string: no 0xFF stuffing, no padding, no markers.
+ * *bits_out (malloc) holds ceil(nbits/8) bytes, MSB first, last byte zero-filled. */
+size_t sjo_encode_stripe(const uint8_t* pix, int w, int hs, int stride, const sjo_params* p,
+                         const int dc_pred[3], int dc_last[3], uint8_t** bits_out, uint64_t* nbits) {
+  if (pix == NULL || p == NULL || bits_out == NULL || nbits == NULL) return 0;
+  *bits_out = NULL;
+  *nbits = 0;
+  Enc* e = (Enc*)calloc(1, sizeof(Enc));
+  if (e == NULL) return 0;
+  if (!init_geom(p->yuv_mode, &e->g)) { free(e); return 0; }
+  e->W = w; e->H = hs; e->yuv_mode = p->yuv_mode;
+  e->mb_w = (w + e->g.block_w - 1) / e->g.block_w;
+  e->mb_h = (hs + e->g.block_h - 1) / e->g.block_h;
+  e->bw.ok = 1;
+  e->bw.raw = 1;
+  for (int i = 0; i < 2; ++i) {
+    memcpy(e->quants[i].quant, p->quant[i], 64);
+    memcpy(e->quants[i].min_quant, p->min_quant[i], 64);
+    finalize(&e->quants[i], p->q_bias);
+    std_table(0, i, &e->huff[i]);
+    std_table(1, i, &e->huff[2 + i]);
+  }
+  init_codes(e, 0);
+  for (int c = 0; c < 3; ++c) e->DCs[c] = dc_pred ? dc_pred[c] : 0;
+  const size_t nb_mcus = (size_t)e->mb_w * e->mb_h;
+  int16_t* coeffs = (int16_t*)malloc(nb_mcus * e->g.mcu_blocks * 64 * sizeof(int16_t));
+  size_t result = 0;
+  if (coeffs == NULL) goto end;
+  sjo_image_to_coeffs(pix, w, hs, stride, p->yuv_mode, p->pix_fmt, coeffs);
+  {
+    RunLevel rl[64];
+    DCTCoeffs info;
+    const int16_t* in = coeffs;
+    for (size_t m = 0; m < nb_mcus; ++m) {
+      for (int c = 0; c < e->g.nb_comps; ++c) {
+        for (int i = 0; i < e->g.nb_blocks[c]; ++i, in += 64) {
+          const int dc = quantize_block(in, c, &e->quants[e->g.quant_idx[c]], &info, rl);
+          info.dc_code = dc_diff_code(dc, &e->DCs[c]);
+          code_block(e, &info, rl);
+        }
+      }
+    }
+  }
+  *nbits = e->bw.nbits;
+  bw_flush_bits(&e->bw);
+  if (e->bw.nb > 0) bw_byte(&e->bw, (int)(e->bw.acc >> 56));   /* zero-filled tail */
+  if (dc_last) for (int c = 0; c < 3; ++c) dc_last[c] = e->DCs[c];
+  if (e->bw.ok) { *bits_out = e->bw.buf; result = e->bw.pos; e->bw.buf = NULL; }
+end:
+  free(e->bw.buf);
+  free(coeffs);
+  free(e);
+  return result;
+}
 
 /* ------------------------------------------------------------------------------------------
  * Synthetic inputs.  LCG of tests/unit_test.cc:73-79.

@@ -99,6 +99,11 @@ size_t sjo_sjpeg_encode(const uint8_t* rgb, int w, int h, int stride, float qual
                         int yuv_mode, uint8_t** out);
 void sjo_free(uint8_t* p);
 
+/* Row stripe coded on its own (method 0): raw entropy-coded bits, DC predictors in/out.
+ * Used as the CPU stand-in stage by the multi-rank (gloo) tests of the stripe exchange. */
+size_t sjo_encode_stripe(const uint8_t* pix, int w, int hs, int stride, const sjo_params* p,
+                         const int dc_pred[3], int dc_last[3], uint8_t** bits_out, uint64_t* nbits);
+
 /* Deterministic synthetic inputs of SURVEY.md 8(d): gen 'A' = tests/unit_test.cc:73-94 MakeRGB,
  * gen 'B' = photo-like ramp + noise.  Packed RGB, stride 3*w. */
 void sjo_make_rgb(char gen, int w, int h, uint32_t seed, uint8_t* out);

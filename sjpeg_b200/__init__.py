@@ -63,6 +63,14 @@ _SIGNATURES = {
                                    C.POINTER(C.c_float), C.POINTER(C.c_size_t), C.POINTER(C.c_ulonglong)]),
     "sjb_bench_f1": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_longlong,
                                C.POINTER(Params), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "sjb_stripes_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]),
+    "sjb_stripes_destroy": (None, [C.c_void_p]),
+    "sjb_stripes_transform": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_longlong, C.c_void_p]),
+    "sjb_stripes_code": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sjb_stripes_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_size_t,
+                                     C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sjb_picture_header": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                     C.POINTER(C.c_size_t)]),
     # drop-in C entry points (include/sjpeg.h)
     "SjpegVersion": (C.c_uint32, []),
     "SjpegEncode": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(_u8p), C.c_float, C.c_int, C.c_int]),

@@ -214,6 +214,7 @@ int ReserveLane(sjb_context* ctx, Lane* L, const Plan& plan, int frames) {
   gb.hist = &s->hist[0][0];
   gb.freq = &s->freq[0][0];
   gb.quant = &s->quant[0][0][0];
+  gb.dc_init = nullptr;
   if (relayout) L->header_valid = 0;   // out slots moved: headers must be sent again
   L->group_capacity = frames;
   return SJB_OK;
@@ -438,7 +439,15 @@ int EncodeGroup(sjb_context* ctx, Lane* L, const FrameSet& fs, const Plan& plan,
   L->words_dirty = true;
   CU(cudaMemsetAsync(L->state.ptr, 0, L->state.bytes, L->stream));   // look-back descriptors
   LaunchEntropyPack(fs, gb, L->stream);
-  LaunchStuff(fs, gb, L->header_len, L->stream);
+  {
+    StuffArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    for (int f = 0; f < n; ++f) {
+      sa.header_len[f] = L->header_len[f];
+      sa.flags[f] = kStuffFirst | kStuffLast;
+    }
+    LaunchStuff(fs, gb, sa, L->stream);
+  }
   L->launches += 2;
   CU(cudaGetLastError());
   L->words_dirty = false;   // the stuffing kernel zeroes every word it consumed
@@ -834,6 +843,231 @@ int sjb_bench_f1(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int wid
   CU(cudaEventElapsedTime(&ms, L->ev[0], L->ev[1]));
   *ms_per_launch = ms / (static_cast<float>(groups) * iters);
   if (frames_per_launch) *frames_per_launch = B;
+  return SJB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row stripes of pictures split across GPUs (BASELINE.json config 5).  A session
+// holds n stripes (one per picture, same geometry) between the three phases; the caller (one
+// process per GPU, sjpeg_b200/distributed.py) exchanges the DC predictors and the bit offsets
+// between the phases.  Default Huffman tables only (method 0).
+// ---------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct sjb_stripes {
+  sjb_context* ctx = nullptr;
+  Plan plan;
+  int n = 0;
+  long long stride = 0;
+  std::vector<Lane*> sets;          // one buffer set per group of <= kMaxGroup stripes
+  std::vector<FrameSet> fsets;
+  DeviceBuffer dc;                  // [n][3] last DCs out, then [n][3] predictors in
+  bool transformed = false, coded = false;
+};
+
+extern "C" {
+
+int sjb_stripes_create(sjb_context* ctx, int n, int width, int stripe_height, const sjb_params* params,
+                       sjb_stripes** out) {
+  if (ctx == nullptr || out == nullptr || n <= 0) return SJB_ERR_ARG;
+  *out = nullptr;
+  ctx->err.clear();
+  sjb_stripes* s = new (std::nothrow) sjb_stripes();
+  if (s == nullptr) return SJB_ERR_NOMEM;
+  s->ctx = ctx;
+  s->n = n;
+  const int pstep = (params && params->pix_fmt != SJB_PIX_RGB) ? 4 : 3;
+  int rc = MakePlan(width, stripe_height, static_cast<long long>(pstep) * width, params, &s->plan);
+  if (rc == SJB_OK && s->plan.p.method != 0) rc = SJB_ERR_ARG;     // stripes: default tables only
+  if (rc != SJB_OK) {
+    delete s;
+    return rc;
+  }
+  *out = s;
+  return SJB_OK;
+}
+
+void sjb_stripes_destroy(sjb_stripes* s) {
+  if (s == nullptr) return;
+  cudaSetDevice(s->ctx->device);
+  for (Lane* L : s->sets) {
+    DestroyLane(L);
+    delete L;
+  }
+  s->dc.Release();
+  delete s;
+}
+
+int sjb_stripes_transform(sjb_stripes* s, const uint8_t* const* pix, int pix_on_device, long long stride,
+                          int* last_dc) {
+  if (s == nullptr || pix == nullptr || last_dc == nullptr) return SJB_ERR_ARG;
+  sjb_context* ctx = s->ctx;
+  ctx->err.clear();
+  Plan plan;
+  RC(MakePlan(s->plan.g.width, s->plan.g.height, stride, &s->plan.p, &plan));   // validates the stride
+  s->plan = plan;
+  s->stride = stride;
+  CU(cudaSetDevice(ctx->device));
+  const int groups = (s->n + kMaxGroup - 1) / kMaxGroup;
+  while (static_cast<int>(s->sets.size()) < groups) {
+    Lane* L = new (std::nothrow) Lane();
+    if (L == nullptr) return SJB_ERR_NOMEM;
+    s->sets.push_back(L);
+    RC(InitLane(ctx, L));
+  }
+  CU(s->dc.Reserve(static_cast<size_t>(s->n) * 6 * sizeof(int)));
+  s->fsets.assign(groups, FrameSet());
+  uint8_t quant[2][64], min_quant[2][64];
+  QuantTabs qt;
+  if (!MakeQuantTabs(plan, quant, min_quant, &qt)) return SJB_ERR_ARG;
+  std::vector<int> host_dc(static_cast<size_t>(s->n) * 3);
+  for (int k = 0; k < groups; ++k) {
+    Lane* L = s->sets[k];
+    const int frames = std::min<int>(kMaxGroup, s->n - k * kMaxGroup);
+    RC(ReserveLane(ctx, L, plan, frames));
+    FrameSet& fs = s->fsets[k];
+    FillFrameSet(plan, stride, &fs);
+    fs.frames = frames;
+    if (!pix_on_device) RC(ReservePix(ctx, L, plan, stride, frames));
+    for (int f = 0; f < frames; ++f) {
+      const uint8_t* p = pix[k * kMaxGroup + f];
+      if (p == nullptr) return SJB_ERR_ARG;
+      fs.pix[f] = p;
+      if (!pix_on_device) {
+        long long ds = stride;
+        RC(UploadPicture(ctx, L, p, plan, stride, f, &fs.pix[f], &ds));
+        fs.stride = ds;
+      }
+    }
+    LaunchF1(L, fs, plan.g, /*raw=*/false, qt);
+    LaunchLastDc(fs, L->gb, s->dc.as<int>() + k * kMaxGroup * 3, L->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&host_dc[static_cast<size_t>(k) * kMaxGroup * 3], s->dc.as<int>() + k * kMaxGroup * 3,
+                       frames * 3 * sizeof(int), cudaMemcpyDeviceToHost, L->stream));
+  }
+  for (int k = 0; k < groups; ++k) CU(cudaStreamSynchronize(s->sets[k]->stream));
+  memcpy(last_dc, host_dc.data(), host_dc.size() * sizeof(int));
+  s->transformed = true;
+  s->coded = false;
+  return SJB_OK;
+}
+
+int sjb_stripes_code(sjb_stripes* s, const int* dc_pred, unsigned long long* bits) {
+  if (s == nullptr || dc_pred == nullptr || bits == nullptr || !s->transformed) return SJB_ERR_ARG;
+  sjb_context* ctx = s->ctx;
+  ctx->err.clear();
+  CU(cudaSetDevice(ctx->device));
+  const int groups = static_cast<int>(s->fsets.size());
+  int* d_pred = s->dc.as<int>() + static_cast<size_t>(s->n) * 3;
+  // default Huffman tables for every stripe
+  HuffSpec spec[4];
+  CodeTabs tabs;
+  memset(&tabs, 0, sizeof(tabs));
+  for (int i = 0; i < 4; ++i) DefaultHuffSpec(i >= 2, i & 1, &spec[i]);
+  for (int c = 0; c < 2; ++c) {
+    CodesFromSpec(spec[c], tabs.dc[c]);
+    CodesFromSpec(spec[2 + c], tabs.ac[c]);
+  }
+  for (int k = 0; k < groups; ++k) {
+    Lane* L = s->sets[k];
+    const FrameSet& fs = s->fsets[k];
+    CU(cudaStreamSynchronize(L->stream));
+    for (int f = 0; f < fs.frames; ++f) L->host->tabs[f] = tabs;
+    CU(cudaMemcpyAsync(L->d_small()->tabs, L->host->tabs, fs.frames * sizeof(CodeTabs), cudaMemcpyHostToDevice,
+                       L->stream));
+    L->tabs_valid = 0;
+    CU(cudaMemcpyAsync(d_pred + k * kMaxGroup * 3, dc_pred + k * kMaxGroup * 3, fs.frames * 3 * sizeof(int),
+                       cudaMemcpyHostToDevice, L->stream));
+    if (L->words_dirty) {
+      CU(cudaMemsetAsync(L->words.ptr, 0, L->words.bytes, L->stream));
+      L->words_dirty = false;
+    }
+    CU(cudaMemsetAsync(L->state.ptr, 0, L->state.bytes, L->stream));
+    GroupBuffers gb = L->gb;
+    gb.dc_init = d_pred + k * kMaxGroup * 3;
+    L->words_dirty = true;
+    LaunchEntropyPack(fs, gb, L->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(L->host->info, L->d_small()->info, fs.frames * sizeof(StreamInfo), cudaMemcpyDeviceToHost,
+                       L->stream));
+  }
+  for (int k = 0; k < groups; ++k) {
+    Lane* L = s->sets[k];
+    CU(cudaStreamSynchronize(L->stream));
+    for (int f = 0; f < s->fsets[k].frames; ++f) bits[k * kMaxGroup + f] = L->host->info[f].total_bits;
+  }
+  s->coded = true;
+  return SJB_OK;
+}
+
+int sjb_stripes_finish(sjb_stripes* s, const unsigned long long* bit_offsets, int is_first, int is_last,
+                       uint8_t* const* out, size_t out_capacity, size_t* sizes, unsigned char* head_byte,
+                       unsigned char* tail_byte, unsigned char* tail_bits) {
+  if (s == nullptr || bit_offsets == nullptr || out == nullptr || sizes == nullptr || head_byte == nullptr ||
+      tail_byte == nullptr || tail_bits == nullptr || !s->coded)
+    return SJB_ERR_ARG;
+  sjb_context* ctx = s->ctx;
+  ctx->err.clear();
+  CU(cudaSetDevice(ctx->device));
+  const int groups = static_cast<int>(s->fsets.size());
+  for (int k = 0; k < groups; ++k) {
+    Lane* L = s->sets[k];
+    const FrameSet& fs = s->fsets[k];
+    StuffArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    for (int f = 0; f < fs.frames; ++f) {
+      sa.header_len[f] = 0;
+      sa.shift[f] = static_cast<unsigned>(bit_offsets[k * kMaxGroup + f] & 7);
+      sa.flags[f] = (is_first ? kStuffFirst : 0) | (is_last ? kStuffLast : 0) | kStuffKeepWords;
+    }
+    LaunchStuff(fs, L->gb, sa, L->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(L->host->info, L->d_small()->info, fs.frames * sizeof(StreamInfo), cudaMemcpyDeviceToHost,
+                       L->stream));
+    L->header_valid = 0;      // the out slots now start with scan bytes
+    L->words_dirty = true;    // shifted reads cannot self-clean: rezero before the next use
+  }
+  int rc = SJB_OK;
+  for (int k = 0; k < groups; ++k) {
+    Lane* L = s->sets[k];
+    CU(cudaStreamSynchronize(L->stream));
+    for (int f = 0; f < s->fsets[k].frames; ++f) {
+      const int i = k * kMaxGroup + f;
+      const StreamInfo& info = L->host->info[f];
+      sizes[i] = static_cast<size_t>(info.out_size);
+      head_byte[i] = info.head_byte;
+      tail_byte[i] = info.tail_byte;
+      tail_bits[i] = info.tail_bits;
+      if (out[i] == nullptr || sizes[i] > out_capacity) {
+        rc = SJB_ERR_CAPACITY;
+        continue;
+      }
+      CU(cudaMemcpyAsync(out[i], L->gb.out + f * L->gb.out_pitch, sizes[i], cudaMemcpyDeviceToHost, L->stream));
+    }
+  }
+  for (int k = 0; k < groups; ++k) CU(cudaStreamSynchronize(s->sets[k]->stream));
+  s->coded = false;
+  s->transformed = false;
+  return rc;
+}
+
+int sjb_picture_header(const sjb_params* params, int width, int height, uint8_t* out, size_t out_capacity,
+                       size_t* out_size) {
+  if (params == nullptr || out_size == nullptr) return SJB_ERR_ARG;
+  Plan plan;
+  const int pstep = (params->pix_fmt != SJB_PIX_RGB) ? 4 : 3;
+  RC(MakePlan(width, height, static_cast<long long>(pstep) * width, params, &plan));
+  if (plan.p.method != 0) return SJB_ERR_ARG;   // optimised tables / adapted matrices are data dependent
+  uint8_t quant[2][64], min_quant[2][64];
+  QuantTabs qt;
+  if (!MakeQuantTabs(plan, quant, min_quant, &qt)) return SJB_ERR_ARG;
+  HuffSpec spec[4];
+  for (int i = 0; i < 4; ++i) DefaultHuffSpec(i >= 2, i & 1, &spec[i]);
+  std::vector<uint8_t> h;
+  AppendHeaders(plan.g, quant, spec, &h);
+  *out_size = h.size();
+  if (out == nullptr || h.size() > out_capacity) return SJB_ERR_CAPACITY;
+  memcpy(out, h.data(), h.size());
   return SJB_OK;
 }
 

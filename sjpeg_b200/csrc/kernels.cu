@@ -504,14 +504,15 @@ histogram_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
 // -------------------------------------------------------------------------------------------
 // quantised DC of the previous block of the same component in scan order (enc.cc:286-305:
 // MCU raster order, blocks interleaved; predictors reset once per image, entropy.cc:155-159)
-__device__ __forceinline__ int dc_predictor(const int16_t* zz, size_t g, int k, int mcu_blocks, int luma_blocks) {
+__device__ __forceinline__ int dc_predictor(const int16_t* zz, size_t g, int k, int mcu_blocks, int luma_blocks,
+                                            const int* init) {
   size_t prev;
   if (k < luma_blocks) {
     if (k > 0) prev = g - 1;
-    else if (g == 0) return 0;
+    else if (g == 0) return init ? init[0] : 0;
     else prev = g - mcu_blocks + luma_blocks - 1;
   } else {
-    if (g < static_cast<size_t>(mcu_blocks)) return 0;
+    if (g < static_cast<size_t>(mcu_blocks)) return init ? init[1 + k - luma_blocks] : 0;
     prev = g - mcu_blocks;
   }
   return zz[prev * 64];
@@ -634,7 +635,7 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
     c = (k >= fs.luma_blocks) ? 1 : 0;
     mask = nzmask[g];
     dc = b[0];
-    pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks);
+    pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, gb.dc_init ? gb.dc_init + 3 * frame : nullptr);
     LocalSink sink = {mine, 0, 0, 0, 0};
     code_block(WordLoader{reinterpret_cast<const uint32_t*>(b)}, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
     sink.finish();
@@ -647,7 +648,12 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
     const unsigned long long p = warp_lookback(gb.bit_state + frame * gb.bit_state_pitch, blockIdx.x, total);
     if (threadIdx.x == 0) {
       tile_prefix = p;
-      if (blockIdx.x == gridDim.x - 1) gb.info[frame].total_bits = p + total;
+      if (blockIdx.x == gridDim.x - 1) {
+        gb.info[frame].total_bits = p + total;
+        gb.info[frame].head_byte = 0;      // stripe hand-over fields, set again by the stuffing kernel
+        gb.info[frame].tail_byte = 0;
+        gb.info[frame].tail_bits = 0;
+      }
     }
   }
   __syncthreads();
@@ -699,7 +705,8 @@ symbol_stats_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
     const int16_t* b = zz + g * 64;
     SmemStats add = {f[c]};
     block_symbol_stats(WordLoader{reinterpret_cast<const uint32_t*>(b)}, nzmask[g], b[0],
-                       dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks), add);
+                       dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks,
+                                    gb.dc_init ? gb.dc_init + 3 * frame : nullptr), add);
   }
   __syncthreads();
   uint32_t* freq = gb.freq + static_cast<size_t>(frame) * 2 * 272;
@@ -716,48 +723,71 @@ symbol_stats_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
 // iteration, 16 bytes per thread; persistent CTAs stride over the tiles (all CTAs are resident,
 // so the look-back chain always makes progress).
 // -------------------------------------------------------------------------------------------
+// 16 bytes of the byte-aligned stream R = (shift zero bits) ++ packed bits, starting at byte0
+// (multiple of 16).  end_bits = shift + total_bits; bytes at or past ceil(end_bits/8) read as 0.
 __device__ __forceinline__ uint4 load_stream16(const uint32_t* stream, unsigned long long byte0,
-                                               unsigned long long nbytes, unsigned long long total_bits) {
+                                               unsigned long long end_bits, unsigned shift) {
   uint4 w = make_uint4(0, 0, 0, 0);
-  if (byte0 < nbytes) {
-    w = *reinterpret_cast<const uint4*>(stream + (byte0 >> 2));
-    const unsigned pad = static_cast<unsigned>((0 - total_bits) & 7);
-    if (pad && nbytes - byte0 <= 16) {             // the padded byte is in here
-      const unsigned last = static_cast<unsigned>(nbytes - 1 - byte0);
-      const uint32_t m = ((1u << pad) - 1u) << (8 * (3 - (last & 3)));
-      if ((last >> 2) == 0) w.x |= m; else if ((last >> 2) == 1) w.y |= m; else if ((last >> 2) == 2) w.z |= m; else w.w |= m;
+  if (byte0 * 8 < end_bits) {
+    const unsigned long long j = byte0 >> 2;
+    w = *reinterpret_cast<const uint4*>(stream + j);
+    if (shift) {
+      const uint32_t before = (j > 0) ? stream[j - 1] : 0u;
+      const uint32_t x = w.x, y = w.y, z = w.z;
+      w.x = __funnelshift_r(x, before, shift);
+      w.y = __funnelshift_r(y, x, shift);
+      w.z = __funnelshift_r(z, y, shift);
+      w.w = __funnelshift_r(w.w, z, shift);
     }
   }
   return w;
 }
 __device__ __forceinline__ int count_ff(uint32_t w) {
-  // a byte is 0xFF iff all its bits are set; bytes past the end of the stream are zero
+  // a byte is 0xFF iff all its bits are set
   uint32_t t = w & (w >> 4);
   t &= t >> 2;
   t &= t >> 1;
   return __popc(t & 0x01010101u);
 }
-
-struct HeaderLens {
-  unsigned v[kMaxGroup];
-};
+__device__ __forceinline__ uint32_t stream_byte(const uint4& w, int i) {   // byte i (0..15) in stream order
+  const uint32_t v = (i < 4) ? w.x : (i < 8) ? w.y : (i < 12) ? w.z : w.w;
+  return (v >> (8 * (3 - (i & 3)))) & 0xffu;
+}
 
 __global__ void __launch_bounds__(256)
-stuff_kernel(GroupBuffers gb, const __grid_constant__ HeaderLens hl) {
+stuff_kernel(GroupBuffers gb, const __grid_constant__ StuffArgs args) {
   __shared__ uint32_t scratch[33];
   __shared__ unsigned long long tile_prefix;
   const int frame = blockIdx.y;
   uint32_t* stream = gb.words + frame * gb.words_pitch;
   unsigned long long* state = gb.ff_state + frame * gb.ff_state_pitch;
-  const unsigned long long total_bits = gb.info[frame].total_bits;
-  const unsigned long long nbytes = (total_bits + 7) >> 3;
-  const unsigned long long tiles = (nbytes + kStuffTileBytes - 1) / kStuffTileBytes;
-  uint8_t* out = gb.out + frame * gb.out_pitch + hl.v[frame];
+  const unsigned shift = args.shift[frame], flags = args.flags[frame];
+  const bool last = (flags & kStuffLast) != 0;
+  const unsigned long long end_bits = gb.info[frame].total_bits + shift;
+  // bytes [b0, b1) of R are emitted here; with kStuffLast the final partial byte is padded with
+  // 1-bits (bit_writer.cc:107-116) and emitted too
+  const unsigned long long b0 = (shift != 0 && !(flags & kStuffFirst)) ? 1 : 0;
+  const unsigned long long b1 = last ? (end_bits + 7) >> 3 : end_bits >> 3;
+  const unsigned pad = last ? static_cast<unsigned>((0 - end_bits) & 7) : 0;
+  const unsigned long long tiles = (((end_bits + 7) >> 3) + kStuffTileBytes - 1) / kStuffTileBytes;
+  uint8_t* out = gb.out + frame * gb.out_pitch + args.header_len[frame];
   for (unsigned long long t = blockIdx.x; t < tiles; t += gridDim.x) {
     const unsigned long long byte0 = t * kStuffTileBytes + threadIdx.x * 16ull;
-    const int valid = (byte0 >= nbytes) ? 0 : static_cast<int>(min(16ull, nbytes - byte0));
-    const uint4 w = load_stream16(stream, byte0, nbytes, total_bits);
-    const uint32_t ff = static_cast<uint32_t>(count_ff(w.x) + count_ff(w.y) + count_ff(w.z) + count_ff(w.w));
+    uint4 w = load_stream16(stream, byte0, end_bits, shift);
+    if (pad && byte0 < b1 && b1 - byte0 <= 16) {             // the padded byte is in here
+      const unsigned i = static_cast<unsigned>(b1 - 1 - byte0);
+      const uint32_t m = ((1u << pad) - 1u) << (8 * (3 - (i & 3)));
+      if ((i >> 2) == 0) w.x |= m; else if ((i >> 2) == 1) w.y |= m; else if ((i >> 2) == 2) w.z |= m; else w.w |= m;
+    }
+    // bytes of this thread that are emitted: [lo, hi) relative to byte0
+    const int lo = (byte0 < b0) ? static_cast<int>(min(16ull, b0 - byte0)) : 0;
+    const int hi = (byte0 >= b1) ? 0 : static_cast<int>(min(16ull, b1 - byte0));
+    uint32_t ff = 0;
+    if (lo == 0 && hi == 16) {
+      ff = static_cast<uint32_t>(count_ff(w.x) + count_ff(w.y) + count_ff(w.z) + count_ff(w.w));
+    } else {
+      for (int i = lo; i < hi; ++i) ff += (stream_byte(w, i) == 0xffu) ? 1u : 0u;
+    }
     uint32_t total;
     const uint32_t ex = cta_exclusive_scan(ff, scratch, &total);
     if (threadIdx.x < 32) {
@@ -766,25 +796,33 @@ stuff_kernel(GroupBuffers gb, const __grid_constant__ HeaderLens hl) {
         tile_prefix = p;
         if (t == tiles - 1) {
           gb.info[frame].stuffed_bytes = p + total;
-          gb.info[frame].out_size = hl.v[frame] + nbytes + p + total + 2;
+          gb.info[frame].out_size = args.header_len[frame] + (b1 - b0) + p + total + (last ? 2 : 0);
         }
       }
     }
     __syncthreads();
-    if (valid > 0) {
+    // shared bytes of a stripe: reported, not emitted
+    if (b0 == 1 && byte0 == 0) gb.info[frame].head_byte = static_cast<unsigned char>(stream_byte(w, 0));
+    if (!last && byte0 <= b1 && b1 < byte0 + 16) {
+      gb.info[frame].tail_bits = static_cast<unsigned char>(end_bits & 7);
+      gb.info[frame].tail_byte = static_cast<unsigned char>((end_bits & 7) ? stream_byte(w, static_cast<int>(b1 - byte0)) : 0u);
+    }
+    if (byte0 * 8 < end_bits && !(flags & kStuffKeepWords)) {
       // self-cleaning: the stream buffer must be all zero for the next encode's atomicOr
+      // (only without a shift: shifted reads look one word back into the neighbour's words)
       *reinterpret_cast<uint4*>(stream + (byte0 >> 2)) = make_uint4(0, 0, 0, 0);
-      uint8_t* dst = out + byte0 + tile_prefix + ex;
-      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+    }
+    if (hi > lo) {
+      uint8_t* dst = out + (byte0 + lo - b0) + tile_prefix + ex;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        if (i < valid) {
-          const uint32_t b = (ww[i >> 2] >> (8 * (3 - (i & 3)))) & 0xffu;
+        if (i >= lo && i < hi) {
+          const uint32_t b = stream_byte(w, i);
           *dst++ = static_cast<uint8_t>(b);
           if (b == 0xffu) *dst++ = 0;
         }
       }
-      if (byte0 + valid == nbytes) {   // EOI
+      if (last && byte0 + hi == b1) {   // EOI (headers.cc:262-268)
         dst[0] = 0xff;
         dst[1] = 0xd9;
       }
@@ -913,6 +951,21 @@ trellis_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   gb.nzmask[frame * gb.mask_pitch + g] = mask;
 }
 
+// quantised DC of the last block of each component (what the next stripe predicts from)
+__global__ void last_dc_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, int* out /*[frames][3]*/) {
+  const int t = threadIdx.x;
+  if (t >= fs.frames * 3) return;
+  const int frame = t / 3, comp = t % 3;
+  const int nb_comps = (fs.mcu_blocks == 1) ? 1 : 3;
+  int v = 0;
+  if (comp < nb_comps) {
+    const size_t last_mcu = static_cast<size_t>(fs.blocks_per_frame) - fs.mcu_blocks;
+    const size_t g = last_mcu + ((comp == 0) ? fs.luma_blocks - 1 : fs.luma_blocks + comp - 1);
+    v = gb.coef[frame * gb.coef_pitch + g * 64];
+  }
+  out[t] = v;
+}
+
 unsigned cdiv(size_t a, size_t b) { return static_cast<unsigned>((a + b - 1) / b); }
 
 }  // namespace
@@ -1001,15 +1054,17 @@ void LaunchEntropyPack(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t 
   entropy_pack_kernel<<<dim3(cdiv(fs.blocks_per_frame, kTileBlocks), fs.frames), kTileBlocks, 0, s>>>(fs, gb);
 }
 
-void LaunchStuff(const FrameSet& fs, const GroupBuffers& gb, const unsigned* header_len, cudaStream_t s) {
-  HeaderLens hl;
-  for (int f = 0; f < kMaxGroup; ++f) hl.v[f] = (f < fs.frames) ? header_len[f] : 0;
+void LaunchLastDc(const FrameSet& fs, const GroupBuffers& gb, int* out, cudaStream_t s) {
+  last_dc_kernel<<<1, 32, 0, s>>>(fs, gb, out);
+}
+
+void LaunchStuff(const FrameSet& fs, const GroupBuffers& gb, const StuffArgs& args, cudaStream_t s) {
   // persistent CTAs: all of them must be resident for the look-back to make progress
   const size_t max_tiles = (gb.words_pitch * 4 + kStuffTileBytes - 1) / kStuffTileBytes;
   unsigned grid = 148 * 4 / (fs.frames > 0 ? fs.frames : 1);
   if (grid < 1) grid = 1;
   if (grid > max_tiles) grid = static_cast<unsigned>(max_tiles);
-  stuff_kernel<<<dim3(grid, fs.frames), 256, 0, s>>>(gb, hl);
+  stuff_kernel<<<dim3(grid, fs.frames), 256, 0, s>>>(gb, args);
 }
 
 }  // namespace sjb

@@ -33,8 +33,11 @@ struct FrameSet {
 struct StreamInfo {
   unsigned long long total_bits;    // entropy-coded bits before padding
   unsigned long long stuffed_bytes; // number of 0xFF bytes that got a 0x00 appended
-  unsigned long long out_size;      // header + scan + EOI
-  unsigned long long pad;
+  unsigned long long out_size;      // header + scan (+ EOI) bytes written
+  unsigned char head_byte;          // stripe mode: first, shared byte (low 8-shift bits are ours)
+  unsigned char tail_byte;          // stripe mode: last, shared byte (top tail_bits bits are ours)
+  unsigned char tail_bits;          // 0 = no shared tail byte
+  unsigned char pad[5];
 };
 
 // Per-lane device arrays, picture-major with fixed pitches (in elements of the pointed type).
@@ -51,6 +54,19 @@ struct GroupBuffers {
   int32_t* hist;            // [frames][2][64][129]
   uint32_t* freq;           // [frames][2][272]
   uint8_t* quant;           // [frames][2][64]
+  const int* dc_init;       // [frames][3] DC predictors at the first MCU (Y,U,V); null = zeros
+};
+
+// Per-picture arguments of the stuffing kernel.  A whole picture uses shift 0 and
+// kStuffFirst|kStuffLast.  A row stripe of a picture split across GPUs starts at
+// global bit offset O: shift = O % 8 re-aligns its bits to the global byte grid; the byte it
+// shares with the previous stripe (head) and the one it shares with the next (tail) are not
+// emitted but reported in StreamInfo for the gatherer to merge.
+enum { kStuffFirst = 1, kStuffLast = 2, kStuffKeepWords = 4 };
+struct StuffArgs {
+  unsigned header_len[kMaxGroup];
+  unsigned shift[kMaxGroup];
+  unsigned flags[kMaxGroup];
 };
 
 // F1: colour convert + fDCT (+ quantise) for the MCU rectangle [mx0,mx1) x [my0,my1) of every
@@ -82,7 +98,8 @@ void LaunchSymbolStats(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t 
 void LaunchEntropyPack(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s);
 // S: 0xFF stuffing with a decoupled look-back over 4 KB stream tiles: scatter to out + header_len,
 // padding, EOI, info.out_size; zeroes the consumed stream words.  gb.ff_state zero on entry.
-void LaunchStuff(const FrameSet& fs, const GroupBuffers& gb, const unsigned* header_len /* host, [frames] */,
-                 cudaStream_t s);
+void LaunchStuff(const FrameSet& fs, const GroupBuffers& gb, const StuffArgs& args, cudaStream_t s);
+// quantised DC of the last Y / U / V block of every picture -> out[frames][3] (stripe hand-over)
+void LaunchLastDc(const FrameSet& fs, const GroupBuffers& gb, int* out, cudaStream_t s);
 
 }  // namespace sjb

@@ -218,3 +218,43 @@ def test_repeated_encodes_are_stable(gpu_ctx):
             rgb = O.make_rgb("A", w, h)
             assert gpu_ctx.encode(rgb, w, h, 3 * w, S.default_params(75, m, mode)) == \
                 O.oracle_encode(rgb, w, h, 3 * w, 75.0, m, mode)
+
+
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_row_stripes_on_one_gpu(gpu_ctx, parts):
+    """BASELINE.json config 5, intra-picture striping: the three-phase stripe API (sjb_stripes_*)
+    driven for every 'rank' in turn on one GPU, exchange done by hand, assembled with the product's
+    own merge rule -- must equal the whole-picture encode.  (The collectives themselves are covered
+    by tests/test_distributed_cpu.py over gloo and tools/bench_config5.py over NCCL.)"""
+    import sjpeg_b200 as S
+    from sjpeg_b200 import distributed as D
+    for (w, h, mode, q) in ((1920, 1080, S.YUV_420, 75), (203, 117, S.YUV_444, 90), (320, 200, S.YUV_400, 50),
+                            (640, 360, S.YUV_420, 100)):
+        n = 3
+        frames = [O.make_rgb("A" if i % 2 == 0 else "B", w, h, 100 + i) for i in range(n)]
+        params = S.default_params(q, 0, mode)
+        plan = D.stripe_plan(h, mode, parts)
+        holders = [r for r in range(parts) if plan[r][1] > plan[r][0]]
+        backends = {r: D.GpuStripeBackend(gpu_ctx, params) for r in holders}
+        last = {}
+        for r in holders:
+            y0, y1 = plan[r]
+            last[r] = backends[r].transform([np.ascontiguousarray(f[y0:y1]) for f in frames], w, y1 - y0, 3 * w)
+        bits, prev = {}, None
+        for r in holders:
+            bits[r] = backends[r].code(np.zeros((n, 3), np.int32) if prev is None else last[prev])
+            prev = r
+        offs = np.zeros(n, np.uint64)
+        meta, blobs = {}, {}
+        for r in holders:
+            partsb, head, tail, tb = backends[r].finish(offs, r == holders[0], r == holders[-1], 4 << 20)
+            meta[r] = [(len(partsb[i]), head[i], tail[i], tb[i]) for i in range(n)]
+            blobs[r] = b"".join(partsb)
+            offs = offs + bits[r]
+        got = D.assemble_striped(backends[holders[0]].header(w, h), holders, meta, blobs)
+        for b in backends.values():
+            b.close()
+        for i in range(n):
+            assert got[i] == O.oracle_encode(frames[i], w, h, 3 * w, float(q), 0, mode), (w, h, mode, parts, i)
+        # the context must still encode whole pictures correctly afterwards
+        assert gpu_ctx.encode(frames[0], w, h, 3 * w, params) == O.oracle_encode(frames[0], w, h, 3 * w, float(q), 0, mode)
