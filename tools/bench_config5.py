@@ -34,6 +34,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29512")
     torch.cuda.set_device(local)
     dist.init_process_group("nccl" if world > 1 else "gloo", rank=rank, world_size=world,
                             **({"device_id": torch.device("cuda", local)} if world > 1 else {}))
