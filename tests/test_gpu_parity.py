@@ -258,3 +258,20 @@ def test_row_stripes_on_one_gpu(gpu_ctx, parts):
             assert got[i] == O.oracle_encode(frames[i], w, h, 3 * w, float(q), 0, mode), (w, h, mode, parts, i)
         # the context must still encode whole pictures correctly afterwards
         assert gpu_ctx.encode(frames[0], w, h, 3 * w, params) == O.oracle_encode(frames[0], w, h, 3 * w, float(q), 0, mode)
+
+
+# the reference's own API tests that lie inside this round's scope
+REFERENCE_TESTS_IN_SCOPE = ["InvalidArguments", "SinkFailure", "CompressionMethod", "Compress", "Dimensions",
+                            "QuantMatrix", "LargeDimensions"]
+
+
+def test_reference_unit_tests_against_the_product_library(gpu_ctx):
+    """tests/unit_test.cc of the reference, compiled UNMODIFIED against include/sjpeg.h and linked
+    with libsjpeg_b200.so (oracle/Makefile target `conformance`; the binary travels in oracle/_ref)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "unit_test_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/unit_test_b200 not built (reference sources absent at build time)")
+    res = subprocess.run([exe] + REFERENCE_TESTS_IN_SCOPE, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+    assert "%d test(s)" % len(REFERENCE_TESTS_IN_SCOPE) in res.stdout and " 0 failure(s)" in res.stdout, res.stdout
