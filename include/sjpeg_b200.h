@@ -132,11 +132,11 @@ void sjb_host_free(void* p);
 
 /* F1 only: colour convert + fDCT (+ quantise).  coef (host, int16[nb_blocks*64]):
  *   quantise = 0: unquantised x16 coefficients, natural order
- *   quantise = 1: quantised values in zig-zag order; nzmask (host, uint32[nb_blocks], may be NULL)
- *                 receives the kernels' side output: bit p set <=> positions 2p, 2p+1 not both 0
+ *   quantise = 1: quantised values in zig-zag order; nzmask (host, uint8[nb_blocks], may be NULL)
+ *                 receives the kernels' side output: bit c set <=> positions 8c..8c+7 not all 0
  * Blocks are in scan order: MCU raster, Y.. U V inside an MCU (enc.cc:286-305). */
 int sjb_stage_coefficients(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
-                           const sjb_params* params, int quantise, int16_t* coef, uint32_t* nzmask);
+                           const sjb_params* params, int quantise, int16_t* coef, uint8_t* nzmask);
 /* histogram.cc:99-108 over the whole picture: counts = int32[2][64][129] (host) */
 int sjb_stage_histogram(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
                         const sjb_params* params, int32_t* counts);

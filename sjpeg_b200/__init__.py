@@ -182,7 +182,7 @@ class Context:
     def coefficients(self, pix, width, height, stride, params, quantise, base=None):
         nb = self._nblocks(width, height, params.yuv_mode)
         coef = np.empty((nb, 64), dtype=np.int16)
-        mask = np.zeros(nb, dtype=np.uint32)
+        mask = np.zeros(nb, dtype=np.uint8)
         ptr = base if base is not None else pix.ctypes.data
         rc = lib().sjb_stage_coefficients(self._ctx, ptr, width, height, stride, C.byref(params),
                                           int(quantise), coef.ctypes.data, mask.ctypes.data)

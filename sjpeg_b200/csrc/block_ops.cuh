@@ -184,10 +184,11 @@ SJB_HD void size_and_bits(int v, int* n, uint32_t* bits) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Block -> Huffman symbols.  The block is 64 quantised int16 in zig-zag order, seen as 32 words
-// (word p = positions 2p, 2p+1, little endian); pairmask bit p is set when word p is non-zero
-// (word 0 also holds the DC).  dc_pred = quantised DC of the previous block of the same
-// component.  Sink receives (code_bits, length) in stream order; the two uses are bit counting
+// Block -> Huffman symbols.  The block is 64 quantised int16 in zig-zag order, seen as 8 chunks
+// of 16 bytes (chunk c = positions 8c..8c+7 = four little-endian words of two values each);
+// chunkmask bit c is set when chunk c holds a non-zero value (chunk 0 also holds the DC), so a
+// coder only loads the chunks that matter.  dc_pred = quantised DC of the previous block of the
+// same component.  Sink receives (code_bits, length) in stream order; the two uses are bit counting
 // and packing.  Follows entropy.cc:161-198 (CodeBlock) with run/levels recomputed on the fly as
 // quantize.cc:288-320 emits them.
 // ---------------------------------------------------------------------------------------------
@@ -220,8 +221,12 @@ SJB_HD int find_first_set32(uint32_t m) {   // index of lowest set bit, m != 0
 #endif
 }
 
-template <class LoadWord, class Sink>
-SJB_HD void code_block(LoadWord load_word, uint32_t pairmask, int dc, int dc_pred, const uint32_t* dc_codes,
+struct Words4 {
+  uint32_t w[4];
+};
+
+template <class LoadChunk, class Sink>
+SJB_HD void code_block(LoadChunk load_chunk, uint32_t chunkmask, int dc, int dc_pred, const uint32_t* dc_codes,
                        const uint32_t* ac_codes, Sink& sink) {
   {
     const int diff = dc - dc_pred;
@@ -233,14 +238,22 @@ SJB_HD void code_block(LoadWord load_word, uint32_t pairmask, int dc, int dc_pre
     sink.put(((c >> 16) << n) | bits, (int)(c & 0xff) + n);
   }
   AcEmitter<Sink> ac = {sink, ac_codes, 0};
-  uint32_t m = pairmask;
+  uint32_t m = chunkmask;
   while (m) {
-    const int p = find_first_set32(m);
+    const int c = find_first_set32(m);
     m &= m - 1;
-    const uint32_t w = load_word(p);
-    const int lo = (int16_t)(w & 0xffffu), hi = (int32_t)w >> 16;
-    if (p > 0 && lo != 0) ac.emit(2 * p, lo);
-    if (hi != 0) ac.emit(2 * p + 1, hi);
+    const Words4 q = load_chunk(c);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t w = q.w[j];
+      if (w == 0) continue;
+      const int p = 4 * c + j;
+      const int lo = (int16_t)(w & 0xffffu), hi = (int32_t)w >> 16;
+      if (p > 0 && lo != 0) ac.emit(2 * p, lo);
+      if (hi != 0) ac.emit(2 * p + 1, hi);
+    }
   }
   if (ac.prev < 63) {                      // EOB, entropy.cc:195-197
     const uint32_t c = ac_codes[0x00];
@@ -255,29 +268,33 @@ struct BitCountSink {
 
 // symbol statistics of a block (entropy.cc:208-227); Add(table_slot) where slot < 256 is an AC
 // symbol and 256 + n a DC size.
-template <class LoadWord, class Add>
-SJB_HD void block_symbol_stats(LoadWord load_word, uint32_t pairmask, int dc, int dc_pred, Add& add) {
+template <class LoadChunk, class Add>
+SJB_HD void block_symbol_stats(LoadChunk load_chunk, uint32_t chunkmask, int dc, int dc_pred, Add& add) {
   {
     const int diff = dc - dc_pred;
     const int m = diff >> 31;
     add.one(256 + bit_length((uint32_t)((diff ^ m) - m)));
   }
-  uint32_t m = pairmask;
+  uint32_t m = chunkmask;
   int prev = 0;
   while (m) {
-    const int p = find_first_set32(m);
+    const int c = find_first_set32(m);
     m &= m - 1;
-    const uint32_t w = load_word(p);
-    const int v2[2] = {(int16_t)(w & 0xffffu), (int32_t)w >> 16};
-    for (int e = (p == 0) ? 1 : 0; e < 2; ++e) {
-      const int v = v2[e];
-      if (v == 0) continue;
-      const int pos = 2 * p + e;
-      const int run = pos - prev - 1;
-      prev = pos;
-      if (run >> 4) add.many(0xf0, run >> 4);
-      const int s = v >> 31;
-      add.one(((run & 15) << 4) | bit_length((uint32_t)((v ^ s) - s)));
+    const Words4 q = load_chunk(c);
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t w = q.w[j];
+      const int p = 4 * c + j;
+      const int v2[2] = {(int16_t)(w & 0xffffu), (int32_t)w >> 16};
+      for (int e = (p == 0) ? 1 : 0; e < 2; ++e) {
+        const int v = v2[e];
+        if (v == 0) continue;
+        const int pos = 2 * p + e;
+        const int run = pos - prev - 1;
+        prev = pos;
+        if (run >> 4) add.many(0xf0, run >> 4);
+        const int s = v >> 31;
+        add.one(((run & 15) << 4) | bit_length((uint32_t)((v ^ s) - s)));
+      }
     }
   }
   if (prev < 63) add.one(0x00);

@@ -188,7 +188,7 @@ int ReserveLane(sjb_context* ctx, Lane* L, const Plan& plan, int frames) {
   const size_t f = static_cast<size_t>(frames);
   bool out_grew = false, words_grew = false;
   CU(L->coef.Reserve(f * nb * 64 * sizeof(int16_t)));
-  CU(L->nzmask.Reserve(f * nb * sizeof(uint32_t)));
+  CU(L->nzmask.Reserve(f * nb * sizeof(uint8_t) + 64));
   CU(L->words.Reserve(f * plan.stream_words * 4 + 64, true, &words_grew));   // zeroed once, then self-cleaning
   CU(L->out.Reserve(f * plan.out_capacity, false, &out_grew));
   CU(L->state.Reserve(f * (plan.nb_tiles + plan.ff_tiles) * sizeof(unsigned long long)));
@@ -197,7 +197,7 @@ int ReserveLane(sjb_context* ctx, Lane* L, const Plan& plan, int frames) {
                         L->group_capacity != frames;
   gb.coef = L->coef.as<int16_t>();
   gb.coef_pitch = nb * 64;
-  gb.nzmask = L->nzmask.as<uint32_t>();
+  gb.nzmask = L->nzmask.as<uint8_t>();
   gb.mask_pitch = nb;
   gb.words = L->words.as<uint32_t>();
   gb.words_pitch = plan.stream_words;
@@ -694,7 +694,7 @@ static int StageF1(sjb_context* ctx, const uint8_t* pix, int width, int height, 
 }
 
 int sjb_stage_coefficients(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
-                           const sjb_params* params, int quantise, int16_t* coef, uint32_t* nzmask) {
+                           const sjb_params* params, int quantise, int16_t* coef, uint8_t* nzmask) {
   if (ctx == nullptr || pix == nullptr || coef == nullptr) return SJB_ERR_ARG;
   Plan plan;
   FrameSet fs;
@@ -703,7 +703,7 @@ int sjb_stage_coefficients(sjb_context* ctx, const uint8_t* pix, int width, int 
   const size_t nb = plan.g.nb_blocks();
   CU(cudaMemcpyAsync(coef, L->coef.ptr, nb * 64 * sizeof(int16_t), cudaMemcpyDeviceToHost, L->stream));
   if (quantise && nzmask) {
-    CU(cudaMemcpyAsync(nzmask, L->nzmask.ptr, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, L->stream));
+    CU(cudaMemcpyAsync(nzmask, L->nzmask.ptr, nb * sizeof(uint8_t), cudaMemcpyDeviceToHost, L->stream));
   }
   CU(cudaStreamSynchronize(L->stream));
   return SJB_OK;

@@ -75,7 +75,7 @@ __device__ __forceinline__ void store_block_natural(const int (&v)[64], int16_t*
   }
 }
 
-// quantise (QuantTab) + zig-zag + non-zero pair bitmap (bit p <=> packed word p != 0).
+// quantise (QuantTab) + zig-zag + non-zero chunk bitmap (bit c <=> the 16-byte chunk c != 0).
 // quantize.cc:288-320 without the run/level emission, which E1/E3 redo from the bitmap.
 // Tab supplies the constants of output pair p = zig-zag positions 2p, 2p+1.
 struct ParamTab {       // kernel-parameter (constant bank) table, compile-time offsets
@@ -94,7 +94,7 @@ struct SmemTab {        // shared-memory copy, run-time base (lets luma and chro
 
 template <class Tab>
 __device__ __forceinline__ void quantize_store_block(const int (&v)[64], const Tab& tab,
-                                                     int16_t* dst, uint32_t* pairmask) {
+                                                     int16_t* dst, uint8_t* chunkmask) {
   constexpr int zz[64] = SJB_ZIGZAG_INIT;
   uint4* d = reinterpret_cast<uint4*>(dst);
   uint32_t mask = 0;
@@ -107,11 +107,11 @@ __device__ __forceinline__ void quantize_store_block(const int (&v)[64], const T
       int iq0, c0, iq1, c1;
       tab.pair(p, iq0, c0, iq1, c1);
       w[j] = pack16(quantize_coeff(v[zz[2 * p]], iq0, c0), quantize_coeff(v[zz[2 * p + 1]], iq1, c1));
-      if (w[j] != 0) mask |= 1u << p;
     }
+    if ((w[0] | w[1] | w[2] | w[3]) != 0) mask |= 1u << i;
     d[i] = make_uint4(w[0], w[1], w[2], w[3]);
   }
-  *pairmask = mask;
+  *chunkmask = static_cast<uint8_t>(mask);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -158,7 +158,7 @@ f1_generic_kernel(const __grid_constant__ FrameSet fs, int mx0, int my0, int mx1
   const int mx = mx0 + static_cast<int>(m % rect_w), my = my0 + static_cast<int>(m / rect_w);
   const size_t g = (static_cast<size_t>(my) * fs.mcus_x + mx) * mcu_blocks + k;
   int16_t* coef = gb.coef + frame * gb.coef_pitch;
-  uint32_t* nzmask = gb.nzmask + frame * gb.mask_pitch;
+  uint8_t* nzmask = gb.nzmask + frame * gb.mask_pitch;
 
   PixelReader px;
   px.base = fs.pix[frame];
@@ -320,7 +320,7 @@ __device__ __forceinline__ void convert_strip_444(uint32_t addr, int cr, int cg,
 
 template <bool kRaw>
 __device__ __forceinline__ void finish_block(int (&v)[64], uint32_t tab_addr, int16_t* coef,
-                                             uint32_t* nzmask, size_t g) {
+                                             uint8_t* nzmask, size_t g) {
   fdct64(v);
   if (kRaw) store_block_natural(v, coef + g * 64);
   else quantize_store_block(v, SmemTab{tab_addr}, coef + g * 64, nzmask + g);
@@ -343,7 +343,7 @@ f1_fast_kernel(const __grid_constant__ FrameSet fs, int mx_full, int my0,
   const uint32_t bar0 = smem_addr(bars);
   const uint32_t tab0 = smem_addr(qtab);
   int16_t* coef = gb.coef + frame * gb.coef_pitch;
-  uint32_t* nzmask = gb.nzmask + frame * gb.mask_pitch;
+  uint8_t* nzmask = gb.nzmask + frame * gb.mask_pitch;
 
   const int chunks_x = (mx_full + kMcusPerTile - 1) / kMcusPerTile;
   const int cx = blockIdx.x % chunks_x, ry = my0 + blockIdx.x / chunks_x;
@@ -518,9 +518,14 @@ __device__ __forceinline__ int dc_predictor(const int16_t* zz, size_t g, int k, 
   return zz[prev * 64];
 }
 
-struct WordLoader {    // word p of a block = zig-zag positions 2p, 2p+1
-  const uint32_t* p;
-  __device__ __forceinline__ uint32_t operator()(int i) const { return p[i]; }
+struct ChunkLoader {   // chunk c of a block = zig-zag positions 8c..8c+7, one 16-byte load
+  const int16_t* p;
+  __device__ __forceinline__ Words4 operator()(int c) const {
+    const uint4 q = reinterpret_cast<const uint4*>(p)[c];
+    Words4 r;
+    r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
+    return r;
+  }
 };
 
 __device__ __forceinline__ void load_code_tables(const CodeTabs* tabs, CodeTabs* sh) {
@@ -620,7 +625,7 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   const int frame = blockIdx.y;
   load_code_tables(gb.tabs + frame, &sh);
   const int16_t* zz = gb.coef + frame * gb.coef_pitch;
-  const uint32_t* nzmask = gb.nzmask + frame * gb.mask_pitch;
+  const uint8_t* nzmask = gb.nzmask + frame * gb.mask_pitch;
   const size_t nb_blocks = fs.blocks_per_frame;
   const size_t g = blockIdx.x * static_cast<size_t>(kTileBlocks) + threadIdx.x;
   const bool valid = g < nb_blocks;
@@ -637,7 +642,7 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
     dc = b[0];
     pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, gb.dc_init ? gb.dc_init + 3 * frame : nullptr);
     LocalSink sink = {mine, 0, 0, 0, 0};
-    code_block(WordLoader{reinterpret_cast<const uint32_t*>(b)}, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
+    code_block(ChunkLoader{b}, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
     sink.finish();
     bits = sink.total;
     nw = sink.nw;
@@ -677,7 +682,7 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   } else {
     StreamOut out = {stream};
     BitPackSink<StreamOut> sink(out, offset);
-    code_block(WordLoader{reinterpret_cast<const uint32_t*>(b)}, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
+    code_block(ChunkLoader{b}, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
     sink.finish();
   }
 }
@@ -696,7 +701,7 @@ symbol_stats_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   __syncthreads();
   const int frame = blockIdx.y;
   const int16_t* zz = gb.coef + frame * gb.coef_pitch;
-  const uint32_t* nzmask = gb.nzmask + frame * gb.mask_pitch;
+  const uint8_t* nzmask = gb.nzmask + frame * gb.mask_pitch;
   const size_t nb_blocks = fs.blocks_per_frame;
   const size_t stride = static_cast<size_t>(gridDim.x) * kTileBlocks;
   for (size_t g = blockIdx.x * static_cast<size_t>(kTileBlocks) + threadIdx.x; g < nb_blocks; g += stride) {
@@ -704,7 +709,7 @@ symbol_stats_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
     const int c = (k >= fs.luma_blocks) ? 1 : 0;
     const int16_t* b = zz + g * 64;
     SmemStats add = {f[c]};
-    block_symbol_stats(WordLoader{reinterpret_cast<const uint32_t*>(b)}, nzmask[g], b[0],
+    block_symbol_stats(ChunkLoader{b}, nzmask[g], b[0],
                        dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks,
                                     gb.dc_init ? gb.dc_init + 3 * frame : nullptr), add);
   }
@@ -934,13 +939,13 @@ trellis_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
 #pragma unroll
   for (int i = 0; i < 64; ++i) outv[i] = 0;
   outv[0] = static_cast<int16_t>(quantize_coeff(in[0], qtab[c][0][0], qtab[c][0][1]));
-  uint32_t mask = (outv[0] != 0) ? 1u : 0u;
+  uint32_t mask = (outv[0] != 0) ? 1u : 0u;   // chunk bitmap
   for (int p = best; p > 0; p = nodes[p].prev) {
     const int n = nodes[p].nbits;
     const int amp = nodes[p].code;
     const int val = (amp >> (n - 1)) ? amp : amp - ((1 << n) - 1);
     outv[nodes[p].pos] = static_cast<int16_t>(val);
-    mask |= 1u << (nodes[p].pos >> 1);
+    mask |= 1u << (nodes[p].pos >> 3);
   }
   {
     const uint4* s = reinterpret_cast<const uint4*>(outv);
@@ -948,7 +953,7 @@ trellis_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = s[i];
   }
-  gb.nzmask[frame * gb.mask_pitch + g] = mask;
+  gb.nzmask[frame * gb.mask_pitch + g] = static_cast<uint8_t>(mask);
 }
 
 // quantised DC of the last block of each component (what the next stripe predicts from)

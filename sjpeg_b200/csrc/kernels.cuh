@@ -43,7 +43,7 @@ struct StreamInfo {
 // Per-lane device arrays, picture-major with fixed pitches (in elements of the pointed type).
 struct GroupBuffers {
   int16_t* coef;            size_t coef_pitch;    // [frames][blocks*64]
-  uint32_t* nzmask;         size_t mask_pitch;    // [frames][blocks]
+  uint8_t* nzmask;          size_t mask_pitch;    // [frames][blocks] chunk bitmaps
   uint32_t* words;          size_t words_pitch;   // [frames][worst-case stream words], zero between encodes
   uint8_t* out;             size_t out_pitch;     // [frames][worst-case file bytes]
   unsigned long long* bit_state; size_t bit_state_pitch;   // look-back descriptors of the entropy kernel
@@ -72,8 +72,8 @@ struct StuffArgs {
 // F1: colour convert + fDCT (+ quantise) for the MCU rectangle [mx0,mx1) x [my0,my1) of every
 // picture of the set.
 //   raw = true : coef receives the unquantised x16 coefficients, natural order
-//   raw = false: coef receives quantised values in zig-zag order, nzmask the non-zero PAIR bitmaps
-//                (bit p set <=> zig-zag positions 2p, 2p+1 are not both zero; bit 0 includes the DC)
+//   raw = false: coef receives quantised values in zig-zag order, nzmask the non-zero CHUNK bitmaps
+//                (bit c set <=> zig-zag positions 8c..8c+7 are not all zero; bit 0 includes the DC)
 // generic path: any stride / alignment / pixel format, edge replication (encoders.cc:157-253)
 void LaunchF1Generic(const FrameSet& fs, int mx0, int my0, int mx1, int my1, bool raw,
                      const QuantTabs& qt, const GroupBuffers& gb, cudaStream_t s);

@@ -75,7 +75,7 @@ void QuantizeBlock(const int (&v)[64], const QuantTab& t, int16_t* zz, uint32_t*
     const int n = kZZ[i];
     const int q = quantize_coeff(v[n], t.e[i][0], t.e[i][1]);
     zz[i] = (int16_t)q;
-    if (q) m |= 1u << (i >> 1);
+    if (q) m |= 1u << (i >> 3);
   }
   *mask = m;
 }
@@ -87,7 +87,14 @@ int DcPred(const int16_t* zz, size_t g, int k, int mb, int lb) {
   return zz[prev * 64];
 }
 
-struct Loader { const int16_t* p; uint32_t operator()(int i) const { return (uint16_t)p[2 * i] | ((uint32_t)(uint16_t)p[2 * i + 1] << 16); } };
+struct Loader {
+  const int16_t* p;
+  Words4 operator()(int c) const {
+    Words4 r;
+    for (int j = 0; j < 4; ++j) r.w[j] = (uint16_t)p[8 * c + 2 * j] | ((uint32_t)(uint16_t)p[8 * c + 2 * j + 1] << 16);
+    return r;
+  }
+};
 struct WordOut {
   std::vector<uint32_t>* w;
   void or_word(uint64_t i, uint32_t v) { (*w)[i] |= v; }

@@ -65,11 +65,11 @@ def test_f1_coefficients_bit_exact(gpu_ctx, size, mode):
             wantq = _oracle_quantised(want, w, h, mode, p)
             gotq, mask = gpu_ctx.coefficients(rgb, w, h, 3 * w, p, quantise=True)
             assert np.array_equal(gotq, wantq), (name, "quantised", q)
-            pair_nz = (wantq.view(np.uint32) != 0)      # word p = zig-zag positions 2p, 2p+1
-            bits = np.zeros(len(pair_nz), np.uint32)
-            for i in range(32):
-                bits |= pair_nz[:, i].astype(np.uint32) << np.uint32(i)
-            assert np.array_equal(mask, bits), (name, "pair mask")
+            chunk_nz = (wantq.reshape(-1, 8, 8) != 0).any(axis=2)      # chunk c = zig-zag 8c..8c+7
+            bits = np.zeros(len(chunk_nz), np.uint8)
+            for i in range(8):
+                bits |= chunk_nz[:, i].astype(np.uint8) << np.uint8(i)
+            assert np.array_equal(mask, bits), (name, "chunk bitmap")
 
 
 @pytest.mark.parametrize("mode", [O.YUV_420, O.YUV_444, O.YUV_400])
