@@ -269,7 +269,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 
 // bytes of one 24-byte block row held in six 32-bit words
-#define SJB_BYTE(w, i) (((w)[(i) >> 2] >> (8 * ((i) & 3))) & 0xffu)
+// one PRMT per byte: result = source byte (i & 3), upper three bytes zero
+#define SJB_BYTE(w, i) __byte_perm((w)[(i) >> 2], 0u, 0x4440u | ((i) & 3))
 
 __device__ __forceinline__ void load_row24(uint32_t addr, uint32_t (&w)[6]) {
   // three 64-bit shared loads; lane stride is 24 bytes => conflict-free per half-warp
