@@ -244,7 +244,12 @@ f1_generic_kernel(const __grid_constant__ FrameSet fs, int mx0, int my0, int mx1
 //   4:4:4 : tile = one strip = 32 MCUs, lane = MCU, three passes over the staged pixels (Y, U, V).
 //   4:0:0 : as 4:4:4, Y only.
 // -------------------------------------------------------------------------------------------
-enum { kStripRowBytes = 768, kStripBytes = 8 * kStripRowBytes, kUvMcuBytes = 288 };
+enum { kUvMcuBytes = 288 };
+// pixel layouts of the fast path: bytes per pixel and the byte offsets of R and B
+template <int kFmt> struct PixLayout;
+template <> struct PixLayout<kFmtRGB>  { enum { kStep = 3, kR = 0, kB = 2 }; };
+template <> struct PixLayout<kFmtRGBA> { enum { kStep = 4, kR = 0, kB = 2 }; };
+template <> struct PixLayout<kFmtBGRA> { enum { kStep = 4, kR = 2, kB = 0 }; };
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -268,32 +273,42 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// bytes of one 24-byte block row held in six 32-bit words
-// one PRMT per byte: result = source byte (i & 3), upper three bytes zero
+// one block row (8 pixels = 24 or 32 bytes) held in 32-bit words; one PRMT per byte:
+// result = source byte (i & 3), upper three bytes zero
 #define SJB_BYTE(w, i) __byte_perm((w)[(i) >> 2], 0u, 0x4440u | ((i) & 3))
 
-__device__ __forceinline__ void load_row24(uint32_t addr, uint32_t (&w)[6]) {
-  // three 64-bit shared loads; lane stride is 24 bytes => conflict-free per half-warp
-  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(addr));
-  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+8];" : "=r"(w[2]), "=r"(w[3]) : "r"(addr));
-  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+16];" : "=r"(w[4]), "=r"(w[5]) : "r"(addr));
+template <int kStep>
+__device__ __forceinline__ void load_block_row(uint32_t addr, uint32_t (&w)[2 * kStep]) {
+  if (kStep == 3) {
+    // three 64-bit shared loads; lane stride is 24 bytes => conflict-free per half-warp
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(addr));
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+8];" : "=r"(w[2]), "=r"(w[3]) : "r"(addr));
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+16];" : "=r"(w[4]), "=r"(w[5]) : "r"(addr));
+  } else {
+    // two 128-bit shared loads; lane stride 32 bytes (2-way conflict, the LSU has headroom)
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(addr));
+  }
 }
 
 // 4:2:0 strip: 8x8 pixels -> 64 luma samples + 4x4 U and V (2x2 sums).  colors_rgb.cc:850-879
-__device__ __forceinline__ void convert_strip_420(uint32_t addr, int (&y)[64], int (&u)[16], int (&v)[16]) {
+template <int kFmt>
+__device__ __forceinline__ void convert_strip_420(uint32_t addr, uint32_t row_stride, int (&y)[64], int (&u)[16],
+                                                  int (&v)[16]) {
+  typedef PixLayout<kFmt> P;
 #pragma unroll
   for (int rp = 0; rp < 4; ++rp) {
-    uint32_t a[6], b[6];
-    load_row24(addr + (2 * rp) * kStripRowBytes, a);
-    load_row24(addr + (2 * rp + 1) * kStripRowBytes, b);
+    uint32_t a[2 * P::kStep], b[2 * P::kStep];
+    load_block_row<P::kStep>(addr + (2 * rp) * row_stride, a);
+    load_block_row<P::kStep>(addr + (2 * rp + 1) * row_stride, b);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       int sr = 0, sg = 0, sb = 0;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int x = 2 * q + e;
-        const int r0 = SJB_BYTE(a, 3 * x), g0 = SJB_BYTE(a, 3 * x + 1), b0 = SJB_BYTE(a, 3 * x + 2);
-        const int r1 = SJB_BYTE(b, 3 * x), g1 = SJB_BYTE(b, 3 * x + 1), b1 = SJB_BYTE(b, 3 * x + 2);
+        const int r0 = SJB_BYTE(a, P::kStep * x + P::kR), g0 = SJB_BYTE(a, P::kStep * x + 1), b0 = SJB_BYTE(a, P::kStep * x + P::kB);
+        const int r1 = SJB_BYTE(b, P::kStep * x + P::kR), g1 = SJB_BYTE(b, P::kStep * x + 1), b1 = SJB_BYTE(b, P::kStep * x + P::kB);
         y[16 * rp + x] = rgb_to_y(r0, g0, b0);
         y[16 * rp + 8 + x] = rgb_to_y(r1, g1, b1);
         sr += r0 + r1; sg += g0 + g1; sb += b0 + b1;
@@ -306,14 +321,17 @@ __device__ __forceinline__ void convert_strip_420(uint32_t addr, int (&y)[64], i
 
 // 4:4:4 / 4:0:0 strip: one component of 8x8 pixels, (cr*r + cg*g + cb*b + rnd) >> 16 with the
 // component's coefficients in registers so that Y, U and V share the code.  colors_rgb.cc:809-848
-__device__ __forceinline__ void convert_strip_444(uint32_t addr, int cr, int cg, int cb, int rnd, int (&s)[64]) {
+template <int kFmt>
+__device__ __forceinline__ void convert_strip_444(uint32_t addr, uint32_t row_stride, int cr, int cg, int cb, int rnd,
+                                                  int (&s)[64]) {
+  typedef PixLayout<kFmt> P;
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    uint32_t a[6];
-    load_row24(addr + r * kStripRowBytes, a);
+    uint32_t a[2 * P::kStep];
+    load_block_row<P::kStep>(addr + r * row_stride, a);
 #pragma unroll
     for (int x = 0; x < 8; ++x) {
-      const int rr = SJB_BYTE(a, 3 * x), gg = SJB_BYTE(a, 3 * x + 1), bb = SJB_BYTE(a, 3 * x + 2);
+      const int rr = SJB_BYTE(a, P::kStep * x + P::kR), gg = SJB_BYTE(a, P::kStep * x + 1), bb = SJB_BYTE(a, P::kStep * x + P::kB);
       s[8 * r + x] = (cr * rr + cg * gg + cb * bb + rnd) >> 16;
     }
   }
@@ -327,11 +345,14 @@ __device__ __forceinline__ void finish_block(int (&v)[64], uint32_t tab_addr, in
   else quantize_store_block(v, SmemTab{tab_addr}, coef + g * 64, nzmask + g);
 }
 
-template <int kMode, bool kRaw>
-__global__ void __launch_bounds__(32, 16)
+template <int kMode, bool kRaw, int kFmt>
+__global__ void __launch_bounds__(32, (kFmt == kFmtRGB) ? 16 : 12)
 f1_fast_kernel(const __grid_constant__ FrameSet fs, int mx_full, int my0,
                const __grid_constant__ QuantTabs qt, GroupBuffers gb) {
   constexpr bool k420 = (kMode == kYuv420);
+  constexpr int kStep = PixLayout<kFmt>::kStep;
+  constexpr int kStripRowBytes = 32 * 8 * kStep;        // 32 block columns
+  constexpr int kStripBytes = 8 * kStripRowBytes;
   constexpr int kMcuBlocks = k420 ? 6 : (kMode == kYuv444 ? 3 : 1);
   constexpr int kMcusPerTile = k420 ? 16 : 32;          // MCUs per tile along x
   constexpr int kStrips = k420 ? 2 : 1;
@@ -349,7 +370,7 @@ f1_fast_kernel(const __grid_constant__ FrameSet fs, int mx_full, int my0,
   const int chunks_x = (mx_full + kMcusPerTile - 1) / kMcusPerTile;
   const int cx = blockIdx.x % chunks_x, ry = my0 + blockIdx.x / chunks_x;
   const int mcus = min(kMcusPerTile, mx_full - cx * kMcusPerTile);
-  const uint32_t row_bytes = static_cast<uint32_t>(mcus) * (k420 ? 48u : 24u);
+  const uint32_t row_bytes = static_cast<uint32_t>(mcus) * (k420 ? 16u : 8u) * kStep;
 
   if (lane == 0) {
 #pragma unroll
@@ -373,7 +394,7 @@ f1_fast_kernel(const __grid_constant__ FrameSet fs, int mx_full, int my0,
   }
   __syncwarp();
   const size_t mcu0 = static_cast<size_t>(ry) * fs.mcus_x + static_cast<size_t>(cx) * kMcusPerTile;
-  const uint32_t src = slot0 + lane * 24;
+  const uint32_t src = slot0 + lane * (8 * kStep);
 
   if (k420) {
     const int m = lane >> 1, half = lane & 1;
@@ -387,7 +408,7 @@ f1_fast_kernel(const __grid_constant__ FrameSet fs, int mx_full, int my0,
       if (j < 2) {
         int u[16], v[16];
         mbar_wait(bar0 + 8 * j, 0);
-        convert_strip_420(src + j * kStripBytes, x, u, v);
+        convert_strip_420<kFmt>(src + j * kStripBytes, kStripRowBytes, x, u, v);
         __syncwarp();                                 // top strip fully consumed before reuse
         // chroma partials: rows interleaved U,V (16 bytes each) inside a 288-byte MCU record
 #pragma unroll
@@ -421,7 +442,7 @@ f1_fast_kernel(const __grid_constant__ FrameSet fs, int mx_full, int my0,
 #pragma unroll 1
     for (int c = 0; c < kMcuBlocks; ++c) {
       int x[64];
-      convert_strip_444(src, cr, cg, cb, rnd, x);
+      convert_strip_444<kFmt>(src, kStripRowBytes, cr, cg, cb, rnd, x);
       if (active) finish_block<kRaw>(x, tab0 + (c ? 512u : 0u), coef, nzmask, (mcu0 + lane) * kMcuBlocks + c);
       // next component: U then V (colors_rgb.cc:809-819)
       if (c == 0) { cr = -11059; cg = -21709; cb = 32768; } else { cr = 32768; cg = -27439; cb = -5329; }
@@ -989,20 +1010,28 @@ void LaunchF1Generic(const FrameSet& fs, int mx0, int my0, int mx1, int my1, boo
 }
 
 bool F1FastEligible(const FrameSet& fs) {
-  if (fs.pix_fmt != kFmtRGB || (fs.stride & 15) != 0) return false;
+  if ((fs.stride & 15) != 0) return false;
   for (int f = 0; f < fs.frames; ++f) {
     if ((reinterpret_cast<uintptr_t>(fs.pix[f]) & 15) != 0) return false;
   }
   return true;
 }
 
-template <int kMode, bool kRaw>
+template <int kMode, bool kRaw, int kFmt>
 static void LaunchF1FastT(const FrameSet& fs, int mx_full, int my0, int my1, const QuantTabs& qt,
                           const GroupBuffers& gb, cudaStream_t s) {
   const int per_tile = (kMode == kYuv420) ? 16 : 32;
   const long long tiles = static_cast<long long>((mx_full + per_tile - 1) / per_tile) * (my1 - my0);
   const dim3 grid(static_cast<unsigned>(tiles), fs.frames);
-  f1_fast_kernel<kMode, kRaw><<<grid, 32, 0, s>>>(fs, mx_full, my0, qt, gb);
+  f1_fast_kernel<kMode, kRaw, kFmt><<<grid, 32, 0, s>>>(fs, mx_full, my0, qt, gb);
+}
+
+template <int kMode, bool kRaw>
+static void LaunchF1FastF(const FrameSet& fs, int mx_full, int my0, int my1, const QuantTabs& qt,
+                          const GroupBuffers& gb, cudaStream_t s) {
+  if (fs.pix_fmt == kFmtRGB) LaunchF1FastT<kMode, kRaw, kFmtRGB>(fs, mx_full, my0, my1, qt, gb, s);
+  else if (fs.pix_fmt == kFmtRGBA) LaunchF1FastT<kMode, kRaw, kFmtRGBA>(fs, mx_full, my0, my1, qt, gb, s);
+  else LaunchF1FastT<kMode, kRaw, kFmtBGRA>(fs, mx_full, my0, my1, qt, gb, s);
 }
 
 void LaunchF1Fast(const FrameSet& fs, int mx_full, int my0, int my1, bool raw, const QuantTabs& qt,
@@ -1010,16 +1039,16 @@ void LaunchF1Fast(const FrameSet& fs, int mx_full, int my0, int my1, bool raw, c
   if (mx_full <= 0 || my1 <= my0) return;
   switch (fs.yuv_mode) {
     case kYuv420:
-      if (raw) LaunchF1FastT<kYuv420, true>(fs, mx_full, my0, my1, qt, gb, s);
-      else     LaunchF1FastT<kYuv420, false>(fs, mx_full, my0, my1, qt, gb, s);
+      if (raw) LaunchF1FastF<kYuv420, true>(fs, mx_full, my0, my1, qt, gb, s);
+      else     LaunchF1FastF<kYuv420, false>(fs, mx_full, my0, my1, qt, gb, s);
       break;
     case kYuv444:
-      if (raw) LaunchF1FastT<kYuv444, true>(fs, mx_full, my0, my1, qt, gb, s);
-      else     LaunchF1FastT<kYuv444, false>(fs, mx_full, my0, my1, qt, gb, s);
+      if (raw) LaunchF1FastF<kYuv444, true>(fs, mx_full, my0, my1, qt, gb, s);
+      else     LaunchF1FastF<kYuv444, false>(fs, mx_full, my0, my1, qt, gb, s);
       break;
     default:
-      if (raw) LaunchF1FastT<kYuv400, true>(fs, mx_full, my0, my1, qt, gb, s);
-      else     LaunchF1FastT<kYuv400, false>(fs, mx_full, my0, my1, qt, gb, s);
+      if (raw) LaunchF1FastF<kYuv400, true>(fs, mx_full, my0, my1, qt, gb, s);
+      else     LaunchF1FastF<kYuv400, false>(fs, mx_full, my0, my1, qt, gb, s);
       break;
   }
 }

@@ -108,9 +108,11 @@ def test_strides_and_alignment(gpu_ctx):
             O.oracle_encode(flipped, w, h, 3 * w, 75.0, 0, mode)
 
 
-def test_rgba_bgra_inputs(gpu_ctx):
+@pytest.mark.parametrize("size", [(203, 117), (640, 360), (1024, 96)], ids=lambda s: "%dx%d" % s)
+def test_rgba_bgra_inputs(gpu_ctx, size):
+    """4-byte pixels: generic path (odd strides) and the bulk-copy fast path (16-byte aligned rows)"""
     import sjpeg_b200 as S
-    w, h = 203, 117
+    w, h = size
     rgb = O.make_rgb("A", w, h)
     want = {m: O.oracle_encode(rgb, w, h, 3 * w, 75.0, 4, m) for m in (O.YUV_420, O.YUV_444, O.YUV_400)}
     rgba = np.dstack([rgb, np.full((h, w, 1), 77, np.uint8)]).copy()
