@@ -79,6 +79,21 @@ int sjb_encode(sjb_context* ctx, const uint8_t* pix, int pix_on_device, int widt
                long long stride, const sjb_params* params, uint8_t* out, int out_on_device,
                size_t out_capacity, size_t* out_size);
 
+/*
+ * Planar / semi-planar YUV input: what EncodeYUV420 / EncodeYUV444 / EncodeGray / EncodeNV12 /
+ * EncodeNV21 do (/root/reference/src/encoders.cc:256-507, sjpeg.h:313-349).  params->yuv_mode selects the layout:
+ *   SJB_YUV_420 : y is width x height, u and v are (width+1)/2 x (height+1)/2; uv_step = 1 for
+ *                 separate planes, 2 for one interleaved plane (NV12: u = uv, v = uv + 1; NV21:
+ *                 v = vu, u = vu + 1; both strides = the plane's stride)
+ *   SJB_YUV_444 : three width x height planes        SJB_YUV_400 : y only (u, v ignored)
+ * No colour conversion: samples are pixel - 128; clipped MCUs replicate each plane's last row and
+ * column.  Other arguments as sjb_encode (out == NULL returns the size with SJB_ERR_CAPACITY).
+ */
+int sjb_encode_planar(sjb_context* ctx, const uint8_t* y, long long y_stride, const uint8_t* u,
+                      long long u_stride, const uint8_t* v, long long v_stride, int uv_step, int on_device,
+                      int width, int height, const sjb_params* params, uint8_t* out, int out_on_device,
+                      size_t out_capacity, size_t* out_size);
+
 /* Copies the JPEG produced by the most recent sjb_encode() of this context (it stays resident in
  * device memory until the next encode).  Lets a caller learn the size first -- sjb_encode with
  * out == NULL returns SJB_ERR_CAPACITY and the size -- and then fetch into an exact allocation. */

@@ -3,6 +3,8 @@
 // can drive parameters the plain-C SjpegEncode() does not expose (custom matrices, bias, deltas,
 // trellis flag).  Compiled only where /root/reference exists; lives in oracle/_ref/.
 #include <cstring>
+#include <memory>
+#include <string>
 #include "sjpeg.h"
 
 extern "C" size_t ref_encode_param(const uint8_t* rgb, int w, int h, int stride, int yuv_mode,
@@ -23,4 +25,29 @@ extern "C" size_t ref_encode_param(const uint8_t* rgb, int w, int h, int stride,
   if (qd_luma >= 0) p.qdelta_max_luma = qd_luma;
   if (qd_chroma >= 0) p.qdelta_max_chroma = qd_chroma;
   return sjpeg::Encode(rgb, w, h, stride, p, out);
+}
+
+// planar / semi-planar entry points of the reference (sjpeg.h:313-349) behind one C door.
+// kind: 0 = EncodeYUV420, 1 = EncodeYUV444, 2 = EncodeNV12, 3 = EncodeNV21, 4 = EncodeGray
+extern "C" size_t ref_encode_planar(int kind, const uint8_t* y, int y_stride, const uint8_t* u, int u_stride,
+                                    const uint8_t* v, int v_stride, int w, int h, float quality, int huffman,
+                                    int adaptive, int trellis, uint8_t** out) {
+  sjpeg::EncoderParam p(quality);
+  p.Huffman_compress = huffman != 0;
+  p.adaptive_quantization = adaptive != 0;
+  p.use_trellis = trellis != 0;
+  std::string s;
+  std::shared_ptr<sjpeg::ByteSink> sink = sjpeg::MakeByteSink(&s);
+  bool ok = false;
+  switch (kind) {
+    case 0: ok = sjpeg::EncodeYUV420(y, y_stride, u, u_stride, v, v_stride, w, h, p, sink.get()); break;
+    case 1: ok = sjpeg::EncodeYUV444(y, y_stride, u, u_stride, v, v_stride, w, h, p, sink.get()); break;
+    case 2: ok = sjpeg::EncodeNV12(y, y_stride, u, u_stride, w, h, p, sink.get()); break;
+    case 3: ok = sjpeg::EncodeNV21(y, y_stride, u, u_stride, w, h, p, sink.get()); break;
+    case 4: ok = sjpeg::EncodeGray(y, w, h, y_stride, p, sink.get()); break;
+  }
+  if (!ok || s.empty()) return 0;
+  *out = new uint8_t[s.size()];
+  memcpy(*out, s.data(), s.size());
+  return s.size();
 }

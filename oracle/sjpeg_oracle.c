@@ -290,6 +290,41 @@ static void get_samples(const uint8_t* pix, int W, int H, int stride, const Geom
   }
 }
 
+/* Planar / semi-planar sources (encoders.cc:256-507): samples are pixel - 128
+ * (colors_rgb.cc:1234-1260 Convert8To16b[Clipped]), clipped MCUs replicate the last valid
+ * row/column of each plane (GetReplicatedYSamples encoders.cc:138-143, Replicate8b with x_step 2
+ * for NV12/NV21 :307-314).  uv_step = 1 for planar chroma, 2 for interleaved. */
+typedef struct {
+  const uint8_t* y; const uint8_t* u; const uint8_t* v;
+  int ys, us, vs, uv_step;
+} Planes;
+
+static void plane_block(const uint8_t* p, int stride, int xstep, int pw, int ph, int x0, int y0, int16_t* out) {
+  for (int y = 0; y < 8; ++y) {
+    const int sy = (y0 + y < ph) ? y0 + y : ph - 1;
+    for (int x = 0; x < 8; ++x) {
+      const int sx = (x0 + x < pw) ? x0 + x : pw - 1;
+      out[8 * y + x] = (int16_t)(p[(ptrdiff_t)sy * stride + sx * xstep] - 128);
+    }
+  }
+}
+
+static void get_samples_planar(const Planes* P, int W, int H, const Geom* g, int mb_x, int mb_y, int16_t* out) {
+  if (g->mcu_blocks == 6) {
+    const int clipped = (mb_x == W / 16) || (mb_y == H / 16);
+    for (int k = 0; k < 4; ++k) plane_block(P->y, P->ys, 1, W, H, 16 * mb_x + 8 * (k & 1), 16 * mb_y + 8 * (k >> 1), out + 64 * k);
+    if (clipped) average_extra_luma(W - mb_x * 16, H - mb_y * 16, out);
+    plane_block(P->u, P->us, P->uv_step, (W + 1) >> 1, (H + 1) >> 1, 8 * mb_x, 8 * mb_y, out + 4 * 64);
+    plane_block(P->v, P->vs, P->uv_step, (W + 1) >> 1, (H + 1) >> 1, 8 * mb_x, 8 * mb_y, out + 5 * 64);
+  } else {
+    plane_block(P->y, P->ys, 1, W, H, 8 * mb_x, 8 * mb_y, out);
+    if (g->mcu_blocks == 3) {
+      plane_block(P->u, P->us, 1, W, H, 8 * mb_x, 8 * mb_y, out + 64);
+      plane_block(P->v, P->vs, 1, W, H, 8 * mb_x, 8 * mb_y, out + 128);
+    }
+  }
+}
+
 /* ------------------------------------------------------------------------------------------
  * Integer fDCT (fdct.cc:28-43, 67-144, 150-209, 596-609).  Output = 16 x JPEG-normalised DCT.
  * ---------------------------------------------------------------------------------------- */
@@ -382,18 +417,23 @@ void sjo_fdct(int16_t* c, int nb) {   /* fdct.cc:596-609 */
   }
 }
 
-static void image_to_blocks(const uint8_t* pix, int w, int h, int stride, int yuv_mode, int fmt,
-                            int do_dct, int16_t* out) {
+static void image_to_blocks_ex(const uint8_t* pix, const Planes* planes, int w, int h, int stride, int yuv_mode,
+                               int fmt, int do_dct, int16_t* out) {
   Geom g;
   if (!init_geom(yuv_mode, &g)) return;
   const int mb_w = (w + g.block_w - 1) / g.block_w, mb_h = (h + g.block_h - 1) / g.block_h;
   for (int mb_y = 0; mb_y < mb_h; ++mb_y) {     /* enc.cc:257-271 raster order */
     for (int mb_x = 0; mb_x < mb_w; ++mb_x) {
-      get_samples(pix, w, h, stride, &g, fmt, mb_x, mb_y, out);
+      if (planes) get_samples_planar(planes, w, h, &g, mb_x, mb_y, out);
+      else get_samples(pix, w, h, stride, &g, fmt, mb_x, mb_y, out);
       if (do_dct) sjo_fdct(out, g.mcu_blocks);
       out += 64 * g.mcu_blocks;
     }
   }
+}
+static void image_to_blocks(const uint8_t* pix, int w, int h, int stride, int yuv_mode, int fmt,
+                            int do_dct, int16_t* out) {
+  image_to_blocks_ex(pix, NULL, w, h, stride, yuv_mode, fmt, do_dct, out);
 }
 void sjo_image_to_coeffs(const uint8_t* pix, int w, int h, int stride, int yuv_mode, int fmt,
                          int16_t* out) {
@@ -994,11 +1034,36 @@ void sjo_default_params(sjo_params* p, float quality, int method, int yuv_mode) 
   p->qdelta_max_chroma = 1;
 }
 
+static size_t encode_impl(const uint8_t* pix, const Planes* planes, int w, int h, int stride, const sjo_params* p,
+                          uint8_t** out);
+
 size_t sjo_encode(const uint8_t* pix, int w, int h, int stride, const sjo_params* p,
                   uint8_t** out) {
   if (pix == NULL || out == NULL || p == NULL) return 0;
   const int pstep = (p->pix_fmt == SJO_RGB) ? 3 : 4;
   if (w <= 0 || h <= 0 || abs(stride) < pstep * w) return 0;     /* api.cc:35-36 */
+  return encode_impl(pix, NULL, w, h, stride, p, out);
+}
+
+/* Planar / semi-planar input (sjpeg.h:313-349; argument checks of encoders.cc:346-358,421-440,
+ * 492-507, api.cc:283-292).  yuv_mode selects the layout: 420 (u,v planes of ((w+1)/2, (h+1)/2);
+ * uv_step 2 = one interleaved plane, u and v pointing at its first U and V byte), 444, or 400
+ * (y only). */
+size_t sjo_encode_planar(const uint8_t* y, int y_stride, const uint8_t* u, int u_stride, const uint8_t* v,
+                         int v_stride, int uv_step, int w, int h, const sjo_params* p, uint8_t** out) {
+  if (y == NULL || out == NULL || p == NULL) return 0;
+  if (w <= 0 || h <= 0 || abs(y_stride) < w) return 0;
+  if (p->yuv_mode != SJO_YUV_400) {
+    if (u == NULL || v == NULL) return 0;
+    const int cw = (p->yuv_mode == SJO_YUV_420) ? uv_step * ((w + 1) / 2) : w;
+    if (abs(u_stride) < cw || abs(v_stride) < cw) return 0;
+  }
+  Planes P = { y, u, v, y_stride, u_stride, v_stride, (p->yuv_mode == SJO_YUV_420) ? uv_step : 1 };
+  return encode_impl(NULL, &P, w, h, 0, p, out);
+}
+
+static size_t encode_impl(const uint8_t* pix, const Planes* planes, int w, int h, int stride, const sjo_params* p,
+                          uint8_t** out) {
   *out = NULL;
   if (w > 65535 || h > 65535) return 0;                          /* enc.cc:406-408 */
   Enc* e = (Enc*)calloc(1, sizeof(Enc));
@@ -1029,7 +1094,7 @@ size_t sjo_encode(const uint8_t* pix, int w, int h, int stride, const sjo_params
   size_t result = 0;
   if (coeffs == NULL || infos == NULL || rls == NULL) goto end;
 
-  sjo_image_to_coeffs(pix, w, h, stride, p->yuv_mode, p->pix_fmt, coeffs);
+  image_to_blocks_ex(pix, planes, w, h, stride, p->yuv_mode, p->pix_fmt, 1, coeffs);
 
   write_app0(e);
   if (adaptive) {                                                /* enc.cc:425-429 */

@@ -11,7 +11,7 @@
  * PARITY PIN: the reference's own tests hold no golden vectors for this path;
  * the restatement is pinned instead against the UNMODIFIED reference compiled here
  * (oracle/_ref/libsjpeg_ref.so, built by oracle/Makefile) -- byte equality of whole JPEG
- * files over the matrix in tests/test_oracle_vs_ref.py -- and against the md5 table the
+ * files over the matrix in tests/test_oracle.py -- and against the md5 table the
  * compiled reference produced (tests/golden/ref_md5.json, made by tests/golden/make_golden.py).
  *
  * Every function cites the reference file:line it follows.
@@ -97,6 +97,11 @@ size_t sjo_encode(const uint8_t* pix, int w, int h, int stride, const sjo_params
 /* SjpegEncode() equivalent for RGB input (api.cc:32-49), yuv_mode in {420,444,400} */
 size_t sjo_sjpeg_encode(const uint8_t* rgb, int w, int h, int stride, float quality, int method,
                         int yuv_mode, uint8_t** out);
+/* Planar (EncodeYUV420 / EncodeYUV444 / EncodeGray) and semi-planar (EncodeNV12 / EncodeNV21)
+ * input, encoders.cc:256-507.  p->yuv_mode selects 420 / 444 / 400; uv_step = 2 for NV12/NV21
+ * (u, v point at the first U and V byte of the interleaved plane). */
+size_t sjo_encode_planar(const uint8_t* y, int y_stride, const uint8_t* u, int u_stride, const uint8_t* v,
+                         int v_stride, int uv_step, int w, int h, const sjo_params* p, uint8_t** out);
 void sjo_free(uint8_t* p);
 
 /* Row stripe coded on its own (method 0): raw entropy-coded bits, DC predictors in/out.

@@ -46,6 +46,9 @@ _SIGNATURES = {
     "sjb_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong,
                              C.POINTER(Params), C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_size_t)]),
     "sjb_fetch_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
+    "sjb_encode_planar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p,
+                                    C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Params), C.c_void_p,
+                                    C.c_int, C.c_size_t, C.POINTER(C.c_size_t)]),
     "sjb_encode_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,
                                    C.c_longlong, C.POINTER(Params), C.POINTER(C.c_void_p), C.c_int,
                                    C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -153,6 +156,19 @@ class Context:
             return None
         if rc != ERR_CAPACITY:
             _check(self._ctx, rc if rc != OK else ERR_CUDA, "sjb_encode")
+        out = np.empty(size.value, dtype=np.uint8)
+        _check(self._ctx, lib().sjb_fetch_output(self._ctx, out.ctypes.data, 0, out.nbytes), "sjb_fetch_output")
+        return out.tobytes()
+
+    def encode_planar(self, y, y_stride, u, u_stride, v, v_stride, uv_step, width, height, params):
+        """y/u/v: addresses (ints) of the first sample of each plane, or None."""
+        size = C.c_size_t(0)
+        rc = lib().sjb_encode_planar(self._ctx, y, y_stride, u, u_stride, v, v_stride, uv_step, 0, width, height,
+                                     C.byref(params), None, 0, 0, C.byref(size))
+        if rc == ERR_ARG:
+            return None
+        if rc != ERR_CAPACITY:
+            _check(self._ctx, rc if rc != OK else ERR_CUDA, "sjb_encode_planar")
         out = np.empty(size.value, dtype=np.uint8)
         _check(self._ctx, lib().sjb_fetch_output(self._ctx, out.ctypes.data, 0, out.nbytes), "sjb_fetch_output")
         return out.tobytes()

@@ -483,6 +483,19 @@ int EncodeSingle(sjb_context* ctx, const uint8_t* pix, int pix_on_device, long l
   return rc;
 }
 
+// copies a host plane (rows of row_bytes, any stride sign) to dst; returns the device row 0
+int UploadPlane(sjb_context* ctx, Lane* L, uint8_t* dst, const uint8_t* src, long long stride, size_t row_bytes,
+                int rows, const uint8_t** d_row0, long long* d_stride) {
+  const size_t pitch = (row_bytes + 15) & ~static_cast<size_t>(15);
+  const long long astride = stride < 0 ? -stride : stride;
+  const uint8_t* lowest = (stride < 0) ? src + stride * (rows - 1) : src;
+  CU(cudaMemcpy2DAsync(dst, pitch, lowest, static_cast<size_t>(astride), row_bytes, rows, cudaMemcpyHostToDevice,
+                       L->stream));
+  *d_row0 = dst + ((stride < 0) ? pitch * (rows - 1) : 0);
+  *d_stride = (stride < 0) ? -static_cast<long long>(pitch) : static_cast<long long>(pitch);
+  return SJB_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -670,6 +683,85 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
   }
   for (int l = 0; l < nl; ++l) CU(cudaStreamSynchronize(ctx->lanes[l].stream));
   return first_err;
+}
+
+int sjb_encode_planar(sjb_context* ctx, const uint8_t* y, long long y_stride, const uint8_t* u,
+                      long long u_stride, const uint8_t* v, long long v_stride, int uv_step, int on_device,
+                      int width, int height, const sjb_params* params, uint8_t* out, int out_on_device,
+                      size_t out_capacity, size_t* out_size) {
+  if (ctx == nullptr || y == nullptr || out_size == nullptr || params == nullptr) return SJB_ERR_ARG;
+  *out_size = 0;
+  ctx->lanes[0].last_size = 0;
+  ctx->err.clear();
+  const int mode = params->yuv_mode;
+  if (mode != SJB_YUV_420 && mode != SJB_YUV_444 && mode != SJB_YUV_400) return SJB_ERR_ARG;
+  if (width <= 0 || height <= 0) return SJB_ERR_ARG;
+  if (uv_step != 1 && !(uv_step == 2 && mode == SJB_YUV_420)) return SJB_ERR_ARG;
+  const int cw = (mode == SJB_YUV_420) ? (width + 1) / 2 : width, ch = (mode == SJB_YUV_420) ? (height + 1) / 2 : height;
+  auto absll = [](long long a) { return a < 0 ? -a : a; };
+  if (absll(y_stride) < width) return SJB_ERR_ARG;                       // encoders.cc:349,428,499
+  if (mode != SJB_YUV_400) {
+    if (u == nullptr || v == nullptr) return SJB_ERR_ARG;
+    if (absll(u_stride) < static_cast<long long>(uv_step) * cw || absll(v_stride) < static_cast<long long>(uv_step) * cw)
+      return SJB_ERR_ARG;
+  }
+  sjb_params p = *params;
+  p.pix_fmt = SJB_PIX_RGB;
+  Plan plan;
+  RC(MakePlan(width, height, 3LL * width, &p, &plan));   // geometry / method; the stride is not used
+  CU(cudaSetDevice(ctx->device));
+  Lane* L = &ctx->lanes[0];
+  RC(ReserveLane(ctx, L, plan, 1));
+  FrameSet fs;
+  FillFrameSet(plan, y_stride, &fs);
+  fs.frames = 1;
+  fs.planar = 1;
+  fs.uv_step = (mode == SJB_YUV_420) ? uv_step : 1;
+  fs.pix[0] = y;
+  fs.pix_u[0] = u;
+  fs.pix_v[0] = v;
+  fs.stride_u = u_stride;
+  fs.stride_v = v_stride;
+  if (!on_device) {
+    const size_t ypitch = (static_cast<size_t>(width) + 15) & ~size_t(15);
+    const size_t crow = static_cast<size_t>(fs.uv_step) * cw;
+    const size_t cpitch = (crow + 15) & ~size_t(15);
+    const size_t ybytes = ypitch * height, cbytes = cpitch * ch;
+    CU(L->pix.Reserve(ybytes + 2 * cbytes + 256));
+    uint8_t* base = L->pix.as<uint8_t>();
+    RC(UploadPlane(ctx, L, base, y, y_stride, width, height, &fs.pix[0], &fs.stride));
+    if (mode != SJB_YUV_400) {
+      if (uv_step == 2) {
+        // one interleaved plane: copy it once, from whichever of u / v comes first in memory
+        const uint8_t* first = (u < v) ? u : v;
+        const uint8_t* d0;
+        long long ds;
+        RC(UploadPlane(ctx, L, base + ybytes, first, u_stride, crow, ch, &d0, &ds));
+        fs.pix_u[0] = d0 + (u - first);
+        fs.pix_v[0] = d0 + (v - first);
+        fs.stride_u = fs.stride_v = ds;
+      } else {
+        RC(UploadPlane(ctx, L, base + ybytes, u, u_stride, crow, ch, &fs.pix_u[0], &fs.stride_u));
+        RC(UploadPlane(ctx, L, base + ybytes + cbytes, v, v_stride, crow, ch, &fs.pix_v[0], &fs.stride_v));
+      }
+    }
+  }
+  L->launches = 0;
+  const int rc = EncodeGroup(ctx, L, fs, plan, /*timed=*/true);
+  if (rc != SJB_OK) {
+    L->words_dirty = true;
+    return rc;
+  }
+  CU(cudaStreamSynchronize(L->stream));
+  FinishTimings(ctx, L);
+  const size_t size = static_cast<size_t>(L->host->info[0].out_size);
+  *out_size = size;
+  L->last_size = size;
+  if (out == nullptr || size > out_capacity) return SJB_ERR_CAPACITY;
+  CU(cudaMemcpyAsync(out, L->out.ptr, size, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                     L->stream));
+  CU(cudaStreamSynchronize(L->stream));
+  return SJB_OK;
 }
 
 // ---- stage-level entry points ----------------------------------------------------------------

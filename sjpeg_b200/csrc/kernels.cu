@@ -143,6 +143,18 @@ __device__ __forceinline__ void luma_samples(const PixelReader& px, int x0, int 
   }
 }
 
+// planar sources: sample = pixel - 128, last valid row / column replicated
+// (Convert8To16b[Clipped] colors_rgb.cc:1234-1260, GetReplicatedYSamples encoders.cc:138-143)
+__device__ __forceinline__ void plane_samples(const uint8_t* p, long long stride, int xstep, int pw1, int ph1,
+                                              int x0, int y0, int (&v)[64]) {
+#pragma unroll
+  for (int y = 0; y < 8; ++y) {
+    const uint8_t* row = p + min(y0 + y, ph1) * stride;
+#pragma unroll
+    for (int x = 0; x < 8; ++x) v[8 * y + x] = static_cast<int>(row[min(x0 + x, pw1) * xstep]) - 128;
+  }
+}
+
 template <bool kRaw>
 __global__ void __launch_bounds__(128)
 f1_generic_kernel(const __grid_constant__ FrameSet fs, int mx0, int my0, int mx1, int my1,
@@ -181,10 +193,10 @@ f1_generic_kernel(const __grid_constant__ FrameSet fs, int mx0, int my0, int mx1
       if (k == 1 && sub_w <= 8) src = 0;
       if (k >= 2 && sub_h <= 8) src = (sub_w > 8) ? 1 : 0;
       else if (k == 3 && sub_w <= 8) src = 2;
-      if (src < 0) {
-        luma_samples(px, X + 8 * (k & 1), Y + 8 * (k >> 1), v);
-      } else {
-        luma_samples(px, X + 8 * (src & 1), Y + 8 * (src >> 1), v);
+      const int kk = (src < 0) ? k : src;
+      if (fs.planar) plane_samples(px.base, px.stride, 1, px.w1, px.h1, X + 8 * (kk & 1), Y + 8 * (kk >> 1), v);
+      else luma_samples(px, X + 8 * (kk & 1), Y + 8 * (kk >> 1), v);
+      if (src >= 0) {
         int sum = 0;
 #pragma unroll
         for (int i = 0; i < 64; ++i) sum += v[i];
@@ -192,6 +204,10 @@ f1_generic_kernel(const __grid_constant__ FrameSet fs, int mx0, int my0, int mx1
 #pragma unroll
         for (int i = 0; i < 64; ++i) v[i] = dc;
       }
+    } else if (fs.planar) {
+      chroma = 1;
+      plane_samples(k == 4 ? fs.pix_u[frame] : fs.pix_v[frame], k == 4 ? fs.stride_u : fs.stride_v, fs.uv_step,
+                    ((fs.width + 1) >> 1) - 1, ((fs.height + 1) >> 1) - 1, 8 * mx, 8 * my, v);
     } else {
       chroma = 1;
 #pragma unroll
@@ -209,6 +225,11 @@ f1_generic_kernel(const __grid_constant__ FrameSet fs, int mx0, int my0, int mx1
         }
       }
     }
+  } else if (fs.planar) {
+    chroma = (k > 0);
+    const uint8_t* base = (k == 0) ? px.base : (k == 1) ? fs.pix_u[frame] : fs.pix_v[frame];
+    const long long st = (k == 0) ? px.stride : (k == 1) ? fs.stride_u : fs.stride_v;
+    plane_samples(base, st, 1, px.w1, px.h1, 8 * mx, 8 * my, v);
   } else {
     const int X = 8 * mx, Y = 8 * my;
     chroma = (k > 0);
@@ -1010,7 +1031,7 @@ void LaunchF1Generic(const FrameSet& fs, int mx0, int my0, int mx1, int my1, boo
 }
 
 bool F1FastEligible(const FrameSet& fs) {
-  if ((fs.stride & 15) != 0) return false;
+  if (fs.planar || (fs.stride & 15) != 0) return false;
   for (int f = 0; f < fs.frames; ++f) {
     if ((reinterpret_cast<uintptr_t>(fs.pix[f]) & 15) != 0) return false;
   }

@@ -18,7 +18,12 @@ enum { kTileBlocks = 256 };        // 8x8 blocks per CTA in the entropy kernel (
 enum { kStuffTileBytes = 4096 };   // stream bytes per CTA iteration in the stuffing kernel
 
 struct FrameSet {
-  const uint8_t* pix[kMaxGroup];   // row 0 of each picture
+  const uint8_t* pix[kMaxGroup];   // row 0 of each picture (packed RGB/RGBA/BGRA, or the Y plane)
+  const uint8_t* pix_u[kMaxGroup]; // planar input: row 0 of the U and V planes (for NV12/NV21: the
+  const uint8_t* pix_v[kMaxGroup]; //   first U and V byte of the interleaved plane)
+  long long stride_u, stride_v;
+  int planar;                      // 0 = packed pixels, 1 = planar / semi-planar YUV (encoders.cc:256-507)
+  int uv_step;                     // bytes between chroma samples: 1 planar, 2 interleaved
   int frames;
   long long stride;                // bytes between rows, may be negative
   int width, height;

@@ -416,15 +416,77 @@ bool EncodeRGBA(const uint8_t* rgba, int width, int height, int stride, const En
   return EncodeRGBA(rgba, width, height, stride, param, &sink);
 }
 
-// Other input layouts (encoders.cc:256-541) are outside the accelerated path.
-bool EncodeGray(const uint8_t*, int, int, int, const EncoderParam&, ByteSink*) { return false; }
-bool EncodeGray(const uint8_t*, int, int, int, const EncoderParam&, std::string*) { return false; }
-bool EncodeNV21(const uint8_t*, int, const uint8_t*, int, int, int, const EncoderParam&, ByteSink*) { return false; }
-bool EncodeNV12(const uint8_t*, int, const uint8_t*, int, int, int, const EncoderParam&, ByteSink*) { return false; }
-bool EncodeYUV444(const uint8_t*, int, const uint8_t*, int, const uint8_t*, int, int, int, const EncoderParam&,
-                  ByteSink*) { return false; }
-bool EncodeYUV420(const uint8_t*, int, const uint8_t*, int, const uint8_t*, int, int, int, const EncoderParam&,
-                  ByteSink*) { return false; }
+// Planar / semi-planar inputs (encoders.cc:256-507): the colour space is implied by the entry
+// point, param.yuv_mode is not consulted.
+static bool EncodePlanar(const uint8_t* y, int ys, const uint8_t* u, int us, const uint8_t* v, int vs, int uv_step,
+                         int mode, int width, int height, const EncoderParam& param, ByteSink* sink) {
+  if (sink == nullptr) return false;
+  EncoderParam fixed = param;
+  fixed.yuv_mode = static_cast<SjpegYUVMode>(mode);
+  sjb_params p;
+  if (!Encoder::Convert(fixed, SJB_PIX_RGB, &p)) {
+    sink->Reset();
+    return false;
+  }
+  sink->Reset();
+  sjb_context* ctx = tls_context.get();
+  if (ctx == nullptr) return false;
+  sjpeg::MemoryManager* memory = param.memory ? param.memory : &default_memory;
+  size_t size = 0;
+  const int rc = sjb_encode_planar(ctx, y, ys, u, us, v, vs, uv_step, 0, width, height, &p, nullptr, 0, 0, &size);
+  if (rc != SJB_ERR_CAPACITY || size == 0) return false;
+  uint8_t* staging = static_cast<uint8_t*>(memory->Alloc(size));
+  if (staging == nullptr) return false;
+  bool ok = sjb_fetch_output(ctx, staging, 0, size) == SJB_OK;
+  uint8_t* dst = nullptr;
+  ok = ok && sink->Commit(0, size, &dst) && dst != nullptr;
+  if (ok) {
+    memcpy(dst, staging, size);
+    ok = sink->Commit(size, 0, &dst) && sink->Finalize();
+  }
+  memory->Free(staging);
+  if (!ok) sink->Reset();
+  return ok;
+}
+
+bool EncodeGray(const uint8_t* gray, int width, int height, int stride, const EncoderParam& param, ByteSink* sink) {
+  if (gray == nullptr || sink == nullptr) return false;                    // api.cc:283-292
+  if (width <= 0 || height <= 0 || abs(stride) < width) return false;
+  return EncodePlanar(gray, stride, nullptr, 0, nullptr, 0, 1, SJPEG_YUV_400, width, height, param, sink);
+}
+bool EncodeGray(const uint8_t* gray, int width, int height, int stride, const EncoderParam& param,
+                std::string* output) {
+  if (output == nullptr) return false;
+  output->clear();
+  ContainerSink<std::string> sink(output);
+  return EncodeGray(gray, width, height, stride, param, &sink);
+}
+bool EncodeNV21(const uint8_t* y, int y_stride, const uint8_t* vu, int vu_stride, int width, int height,
+                const EncoderParam& param, ByteSink* output) {                 // encoders.cc:346-380
+  if (y == nullptr || vu == nullptr || output == nullptr) return false;
+  if (width <= 0 || height <= 0 || abs(y_stride) < width || abs(vu_stride) < 2 * ((width + 1) / 2)) return false;
+  return EncodePlanar(y, y_stride, vu + 1, vu_stride, vu, vu_stride, 2, SJPEG_YUV_420, width, height, param, output);
+}
+bool EncodeNV12(const uint8_t* y, int y_stride, const uint8_t* uv, int uv_stride, int width, int height,
+                const EncoderParam& param, ByteSink* output) {
+  if (y == nullptr || uv == nullptr || output == nullptr) return false;
+  if (width <= 0 || height <= 0 || abs(y_stride) < width || abs(uv_stride) < 2 * ((width + 1) / 2)) return false;
+  return EncodePlanar(y, y_stride, uv, uv_stride, uv + 1, uv_stride, 2, SJPEG_YUV_420, width, height, param, output);
+}
+bool EncodeYUV444(const uint8_t* Y, int Y_stride, const uint8_t* U, int U_stride, const uint8_t* V, int V_stride,
+                  int width, int height, const EncoderParam& param, ByteSink* output) {   // encoders.cc:421-440
+  if (Y == nullptr || U == nullptr || V == nullptr || output == nullptr) return false;
+  if (width <= 0 || height <= 0) return false;
+  if (abs(Y_stride) < width || abs(U_stride) < width || abs(V_stride) < width) return false;
+  return EncodePlanar(Y, Y_stride, U, U_stride, V, V_stride, 1, SJPEG_YUV_444, width, height, param, output);
+}
+bool EncodeYUV420(const uint8_t* Y, int Y_stride, const uint8_t* U, int U_stride, const uint8_t* V, int V_stride,
+                  int width, int height, const EncoderParam& param, ByteSink* output) {   // encoders.cc:492-507
+  if (Y == nullptr || U == nullptr || V == nullptr || output == nullptr) return false;
+  if (width <= 0 || height <= 0) return false;
+  if (abs(Y_stride) < width || abs(U_stride) < (width + 1) / 2 || abs(V_stride) < (width + 1) / 2) return false;
+  return EncodePlanar(Y, Y_stride, U, U_stride, V, V_stride, 1, SJPEG_YUV_420, width, height, param, output);
+}
 
 // Search hook (dichotomy.cc:41-75): kept for linkage; the multi-pass search itself is out of scope.
 bool SearchHook::Setup(const EncoderParam& param) {

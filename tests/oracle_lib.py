@@ -58,6 +58,9 @@ def oracle():
         L.sjo_build_optimal_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.sjo_quality_to_matrices.argtypes = [C.c_float, C.c_void_p]
         L.sjo_geometry.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int)] * 5
+        L.sjo_encode_planar.restype = C.c_size_t
+        L.sjo_encode_planar.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.POINTER(SjoParams), C.POINTER(_u8p)]
         _oracle = L
     return _oracle
 
@@ -77,6 +80,9 @@ def ref():
         L.SjpegEncode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(_u8p), C.c_float,
                                   C.c_int, C.c_int]
         L.SjpegFreeBuffer.argtypes = [_u8p]
+        L.ref_encode_planar.restype = C.c_size_t
+        L.ref_encode_planar.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                        C.c_int, C.c_int, C.c_float] + [C.c_int] * 3 + [C.POINTER(_u8p)]
         L.ref_encode_param.restype = C.c_size_t
         L.ref_encode_param.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                        C.c_float] + [C.c_int] * 6 + [C.POINTER(_u8p)]
@@ -130,3 +136,62 @@ def ref_encode(rgb, w, h, stride, quality, method, yuv_mode, base=None):
 
 def md5(data):
     return hashlib.md5(data).hexdigest().upper()
+
+
+# planar kinds of oracle/ref_shim.cc::ref_encode_planar
+KIND_YUV420, KIND_YUV444, KIND_NV12, KIND_NV21, KIND_GRAY = 0, 1, 2, 3, 4
+KIND_MODE = {KIND_YUV420: YUV_420, KIND_YUV444: YUV_444, KIND_NV12: YUV_420, KIND_NV21: YUV_420, KIND_GRAY: YUV_400}
+
+
+def make_planes(kind, w, h, seed=5, pad=(5, 3, 7)):
+    """Random planes with padded strides for a planar kind.  Returns dict(y, u, v: arrays or None)."""
+    rng = np.random.RandomState(seed)
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    Y = rng.randint(0, 256, (h, w + pad[0])).astype(np.uint8)
+    if kind == KIND_GRAY:
+        return {"y": Y, "u": None, "v": None}
+    if kind == KIND_YUV420:
+        return {"y": Y, "u": rng.randint(0, 256, (ch, cw + pad[1])).astype(np.uint8),
+                "v": rng.randint(0, 256, (ch, cw + pad[2])).astype(np.uint8)}
+    if kind == KIND_YUV444:
+        return {"y": Y, "u": rng.randint(0, 256, (h, w + pad[1])).astype(np.uint8),
+                "v": rng.randint(0, 256, (h, w + pad[2])).astype(np.uint8)}
+    return {"y": Y, "u": rng.randint(0, 256, (ch, 2 * cw + pad[1])).astype(np.uint8), "v": None}   # interleaved
+
+
+def planar_args(kind, planes):
+    """(y, ys, u, us, v, vs, uv_step) as addresses / strides for sjo_encode_planar and sjb_encode_planar."""
+    y, u, v = planes["y"], planes["u"], planes["v"]
+    if kind == KIND_GRAY:
+        return y.ctypes.data, y.strides[0], None, 0, None, 0, 1
+    if kind in (KIND_NV12, KIND_NV21):
+        base = u.ctypes.data
+        up, vp = (base, base + 1) if kind == KIND_NV12 else (base + 1, base)
+        return y.ctypes.data, y.strides[0], up, u.strides[0], vp, u.strides[0], 2
+    return y.ctypes.data, y.strides[0], u.ctypes.data, u.strides[0], v.ctypes.data, v.strides[0], 1
+
+
+def oracle_encode_planar(kind, planes, w, h, quality, method):
+    p = SjoParams()
+    oracle().sjo_default_params(C.byref(p), float(quality), method, KIND_MODE[kind])
+    out = _u8p()
+    n = oracle().sjo_encode_planar(*planar_args(kind, planes), w, h, C.byref(p), C.byref(out))
+    if n == 0:
+        return None
+    data = C.string_at(out, n)
+    oracle().sjo_free(out)
+    return data
+
+
+def ref_encode_planar(kind, planes, w, h, quality, huffman, adaptive, trellis):
+    y, u, v = planes["y"], planes["u"], planes["v"]
+    out = _u8p()
+    n = ref().ref_encode_planar(kind, y.ctypes.data, y.strides[0], u.ctypes.data if u is not None else None,
+                                u.strides[0] if u is not None else 0, v.ctypes.data if v is not None else None,
+                                v.strides[0] if v is not None else 0, w, h, float(quality), huffman, adaptive, trellis,
+                                C.byref(out))
+    if n == 0:
+        return None
+    data = C.string_at(out, n)
+    ref().SjpegFreeBuffer(out)
+    return data

@@ -264,7 +264,8 @@ def test_row_stripes_on_one_gpu(gpu_ctx, parts):
 
 # the reference's own API tests that lie inside this round's scope
 REFERENCE_TESTS_IN_SCOPE = ["InvalidArguments", "SinkFailure", "CompressionMethod", "Compress", "Dimensions",
-                            "QuantMatrix", "LargeDimensions"]
+                            "QuantMatrix", "LargeDimensions", "EncodeYUV420Strides", "EncodeYUV444Strides",
+                            "EncodeNV", "NegativeStrides"]
 
 
 def test_reference_unit_tests_against_the_product_library(gpu_ctx):
@@ -277,3 +278,15 @@ def test_reference_unit_tests_against_the_product_library(gpu_ctx):
     res = subprocess.run([exe] + REFERENCE_TESTS_IN_SCOPE, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
     assert "%d test(s)" % len(REFERENCE_TESTS_IN_SCOPE) in res.stdout and " 0 failure(s)" in res.stdout, res.stdout
+
+
+@pytest.mark.parametrize("kind", [O.KIND_YUV420, O.KIND_YUV444, O.KIND_NV12, O.KIND_NV21, O.KIND_GRAY])
+def test_planar_and_semiplanar_inputs(gpu_ctx, kind):
+    """sjb_encode_planar (EncodeYUV420 / YUV444 / NV12 / NV21 / Gray, encoders.cc:256-507) vs oracle"""
+    import sjpeg_b200 as S
+    for (w, h) in ((17, 13), (64, 48), (203, 117), (1, 1), (640, 360)):
+        for q, method in ((80, 4), (30, 0), (97, 7), (75, 1)):
+            planes = O.make_planes(kind, w, h, seed=w + q + kind)
+            p = S.default_params(q, method, O.KIND_MODE[kind])
+            got = gpu_ctx.encode_planar(*O.planar_args(kind, planes), w, h, p)
+            assert got == O.oracle_encode_planar(kind, planes, w, h, q, method), (kind, w, h, q, method)

@@ -82,3 +82,17 @@ def test_oracle_refuses_invalid_arguments():
     assert O.oracle_encode(rgb, 16, 16, 48, 75.0, 0, 7) is None          # unknown mode
     assert O.oracle_encode(rgb, 16, 16, 48, 75.0, -3, O.YUV_420) == O.oracle_encode(rgb, 16, 16, 48, 75.0, 0, O.YUV_420)
     assert O.oracle_encode(rgb, 16, 16, 48, 75.0, 11, O.YUV_420) == O.oracle_encode(rgb, 16, 16, 48, 75.0, 8, O.YUV_420)
+
+
+@pytest.mark.skipif(O.ref() is None, reason="oracle/_ref not built")
+def test_oracle_planar_inputs_equal_compiled_reference():
+    """EncodeYUV420 / YUV444 / NV12 / NV21 / Gray (encoders.cc:256-507), padded strides, clipped MCUs"""
+    flags = {0: (0, 0, 0), 1: (1, 0, 0), 3: (0, 1, 0), 4: (1, 1, 0), 7: (1, 1, 1)}
+    for (w, h) in ((17, 13), (64, 48), (203, 117), (1, 1), (16, 16), (33, 40)):
+        for q in (30, 80, 97):
+            for method, fl in flags.items():
+                for kind in range(5):
+                    planes = O.make_planes(kind, w, h, seed=w + q + kind)
+                    a = O.oracle_encode_planar(kind, planes, w, h, q, method)
+                    b = O.ref_encode_planar(kind, planes, w, h, q, *fl)
+                    assert a is not None and a == b, (w, h, q, method, kind)
