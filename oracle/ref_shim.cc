@@ -51,3 +51,18 @@ extern "C" size_t ref_encode_planar(int kind, const uint8_t* y, int y_stride, co
   memcpy(*out, s.data(), s.size());
   return s.size();
 }
+
+// metadata (sjpeg.h:238-259): the four payloads as (pointer, length) pairs
+extern "C" size_t ref_encode_meta(const uint8_t* rgb, int w, int h, int stride, int yuv_mode, float quality,
+                                  const char* exif, size_t exif_len, const char* iccp, size_t iccp_len,
+                                  const char* xmp, size_t xmp_len, const char* app, size_t app_len, int xmp_split,
+                                  uint8_t** out) {
+  sjpeg::EncoderParam p(quality);
+  p.yuv_mode = static_cast<SjpegYUVMode>(yuv_mode);
+  if (exif_len) p.exif.assign(exif, exif_len);
+  if (iccp_len) p.iccp.assign(iccp, iccp_len);
+  if (xmp_len) p.xmp.assign(xmp, xmp_len);
+  if (app_len) p.app_markers.assign(app, app_len);
+  p.xmp_split_point = static_cast<uint16_t>(xmp_split);
+  return sjpeg::Encode(rgb, w, h, stride, p, out);
+}

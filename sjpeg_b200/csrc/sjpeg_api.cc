@@ -6,7 +6,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
+#include <string>
 
 #include "../../include/sjpeg.h"
 #include "../../include/sjpeg_b200.h"
@@ -37,8 +39,10 @@ struct DefaultMemory : public sjpeg::MemoryManager {
 int BytesPerPixel(int fmt) { return fmt == SJB_PIX_RGB ? 3 : 4; }
 
 // api.cc:183-192 + encoders.cc:546-568 + api.cc:145-181, ending in a sink
+bool CommitWithMetadata(const uint8_t* jpeg, size_t size, const std::string& meta, sjpeg::ByteSink* sink);
+
 bool EncodeToSink(const uint8_t* pix, int width, int height, int stride, int fmt, const sjb_params& params,
-                  sjpeg::ByteSink* sink, sjpeg::MemoryManager* memory) {
+                  sjpeg::ByteSink* sink, sjpeg::MemoryManager* memory, const std::string& meta = std::string()) {
   sink->Reset();                                        // enc.cc:90
   sjb_context* ctx = tls_context.get();
   if (ctx == nullptr) return false;
@@ -50,12 +54,7 @@ bool EncodeToSink(const uint8_t* pix, int width, int height, int stride, int fmt
   uint8_t* staging = static_cast<uint8_t*>(memory->Alloc(size));
   if (staging == nullptr) return false;
   bool ok = sjb_fetch_output(ctx, staging, 0, size) == SJB_OK;
-  uint8_t* dst = nullptr;
-  ok = ok && sink->Commit(0, size, &dst) && dst != nullptr;
-  if (ok) {
-    memcpy(dst, staging, size);
-    ok = sink->Commit(size, 0, &dst) && sink->Finalize();
-  }
+  ok = ok && CommitWithMetadata(staging, size, meta, sink);
   memory->Free(staging);
   if (!ok) sink->Reset();                               // bit_writer.cc:99-105
   (void)fmt;
@@ -86,10 +85,164 @@ bool ParamsFromEncoderParam(const sjpeg::EncoderParam& param, const uint8_t quan
   out->qdelta_max_luma = param.qdelta_max_luma;
   out->qdelta_max_chroma = param.qdelta_max_chroma;
   if (out->q_bias < 0 || out->q_bias > 255) return false;
-  // multi-pass search (dichotomy.cc) and metadata chunks (headers.cc:63-180) are outside the path
+  // the multi-pass size / PSNR search (dichotomy.cc) is outside the path
   if (param.passes > 1) return false;
-  if (!param.exif.empty() || !param.iccp.empty() || !param.xmp.empty() || !param.app_markers.empty()) return false;
   return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Metadata segments (headers.cc:63-180): host-side bytes inserted between APP0 and DQT.
+// ---------------------------------------------------------------------------------------------
+// RFC 1321 MD5, upper-case hex digest (the GUID of extended XMP, headers.cc:127-129)
+std::string Md5HexUpper(const std::string& data) {
+  static const int kShift[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 5, 9, 14, 20, 5, 9,
+                                 14, 20, 5, 9, 14, 20, 5, 9, 14, 20, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23,
+                                 4, 11, 16, 23, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
+  uint32_t K[64];
+  for (int i = 0; i < 64; ++i) K[i] = static_cast<uint32_t>(floor(fabs(sin(i + 1.0)) * 4294967296.0));
+  uint32_t h[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
+  std::string msg = data;
+  const uint64_t bit_len = static_cast<uint64_t>(data.size()) * 8;
+  msg.push_back(static_cast<char>(0x80));
+  while (msg.size() % 64 != 56) msg.push_back(0);
+  for (int i = 0; i < 8; ++i) msg.push_back(static_cast<char>((bit_len >> (8 * i)) & 0xff));
+  for (size_t off = 0; off < msg.size(); off += 64) {
+    uint32_t w[16];
+    for (int i = 0; i < 16; ++i) {
+      const uint8_t* b = reinterpret_cast<const uint8_t*>(&msg[off + 4 * i]);
+      w[i] = b[0] | (b[1] << 8) | (b[2] << 16) | (static_cast<uint32_t>(b[3]) << 24);
+    }
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3];
+    for (int i = 0; i < 64; ++i) {
+      uint32_t f;
+      int g;
+      if (i < 16) { f = (b & c) | (~b & d); g = i; }
+      else if (i < 32) { f = (d & b) | (~d & c); g = (5 * i + 1) & 15; }
+      else if (i < 48) { f = b ^ c ^ d; g = (3 * i + 5) & 15; }
+      else { f = c ^ (b | ~d); g = (7 * i) & 15; }
+      const uint32_t t = a + f + K[i] + w[g];
+      a = d; d = c; c = b;
+      b += (t << kShift[i]) | (t >> (32 - kShift[i]));
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d;
+  }
+  static const char kHex[] = "0123456789ABCDEF";
+  std::string out;
+  for (int i = 0; i < 4; ++i) {
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t byte = (h[i] >> (8 * j)) & 0xff;
+      out.push_back(kHex[byte >> 4]);
+      out.push_back(kHex[byte & 15]);
+    }
+  }
+  return out;
+}
+
+void Put16(std::string* o, size_t v) {
+  o->push_back(static_cast<char>((v >> 8) & 0xff));
+  o->push_back(static_cast<char>(v & 0xff));
+}
+void Put32(std::string* o, size_t v) {
+  Put16(o, (v >> 16) & 0xffff);
+  Put16(o, v & 0xffff);
+}
+
+bool AppendXmp(const std::string& data, std::string* o);
+
+// headers.cc:115-160
+bool AppendXmpExtended(const std::string& data, size_t split_point, std::string* o) {
+  const size_t kMainSize = 65503;
+  if (data.size() < kMainSize) return true;
+  if (data.size() > (1u << 31)) return false;
+  size_t split = (split_point == 0) ? kMainSize : split_point;
+  split = std::min(split, data.size());
+  const size_t note = data.find("xmpNote:HasExtendedXMP=\"");
+  if (note == std::string::npos) return false;
+  if (note + 24 + 32 + 1 > split) return false;
+  if (data[note + 24 + 32] != '"') return false;
+  std::string main_data(data, 0, split), ext(data, split);
+  main_data.replace(note + 24, 32, Md5HexUpper(ext));
+  const std::string guid = main_data.substr(note + 24, 32);
+  if (!AppendXmp(main_data, o)) return false;
+  static const char kExt[] = "http://ns.adobe.com/xmp/extension/";
+  const size_t kBuf = 65458, kHeader = sizeof(kExt) + 40;
+  const size_t chunks = ext.size() / kBuf + 1;
+  size_t pos = 0;
+  for (size_t c = 0; c < chunks; ++c) {
+    const size_t n = std::min(kBuf, ext.size() - pos);
+    Put16(o, 0xffe1);
+    Put16(o, 2 + kHeader + n);
+    o->append(kExt, sizeof(kExt));
+    o->append(guid);
+    Put32(o, ext.size());
+    Put32(o, pos);
+    o->append(ext, pos, n);
+    pos += n;
+  }
+  return true;
+}
+
+thread_local size_t tls_xmp_split = 0;
+
+// headers.cc:162-180
+bool AppendXmp(const std::string& data, std::string* o) {
+  if (data.empty()) return true;
+  static const char kXmp[] = "http://ns.adobe.com/xap/1.0/";
+  const size_t size = 2 + data.size() + sizeof(kXmp);
+  if (size <= 0xffff) {
+    Put16(o, 0xffe1);
+    Put16(o, size);
+    o->append(kXmp, sizeof(kXmp));
+    o->append(data);
+    return true;
+  }
+  return AppendXmpExtended(data, tls_xmp_split, o);
+}
+
+// enc.cc:415-421: app markers as is, then EXIF, ICC, XMP
+bool BuildMetadata(const sjpeg::EncoderParam& p, std::string* o) {
+  o->clear();
+  o->append(p.app_markers);
+  if (!p.exif.empty()) {                                   // headers.cc:72-85
+    const size_t size = p.exif.size() + 6 + 2;
+    if (size > 0xffff) return false;
+    Put16(o, 0xffe1);
+    Put16(o, size);
+    o->append("Exif\0\0", 6);
+    o->append(p.exif);
+  }
+  if (!p.iccp.empty()) {                                   // headers.cc:87-113
+    const size_t kMaxChunk = 0xffff - 12 - 4;
+    const size_t chunks = (p.iccp.size() + kMaxChunk - 1) / kMaxChunk;
+    if (chunks >= 256) return false;
+    size_t pos = 0;
+    for (size_t seq = 1; pos < p.iccp.size(); ++seq) {
+      const size_t n = std::min(kMaxChunk, p.iccp.size() - pos);
+      Put16(o, 0xffe2);
+      Put16(o, n + 12 + 4);
+      o->append("ICC_PROFILE\0", 12);
+      o->push_back(static_cast<char>(seq & 0xff));
+      o->push_back(static_cast<char>(chunks & 0xff));
+      o->append(p.iccp, pos, n);
+      pos += n;
+    }
+  }
+  tls_xmp_split = p.xmp_split_point;
+  return AppendXmp(p.xmp, o);
+}
+
+// Hands a finished file (SOI+APP0 first, 20 bytes: headers.cc:48-61) to the sink, with the metadata
+// segments inserted right after APP0.
+bool CommitWithMetadata(const uint8_t* jpeg, size_t size, const std::string& meta, sjpeg::ByteSink* sink) {
+  const size_t kApp0 = 20;
+  if (size < kApp0) return false;
+  uint8_t* dst = nullptr;
+  const size_t total = size + meta.size();
+  if (!sink->Commit(0, total, &dst) || dst == nullptr) return false;
+  memcpy(dst, jpeg, kApp0);
+  if (!meta.empty()) memcpy(dst + kApp0, meta.data(), meta.size());
+  memcpy(dst + kApp0 + meta.size(), jpeg + kApp0, size - kApp0);
+  return sink->Commit(total, 0, &dst) && sink->Finalize();
 }
 
 // sinks (bit_writer.h:51-93)
@@ -368,11 +521,12 @@ static bool EncodePacked(const uint8_t* pix, int width, int height, int stride, 
   if (pix == nullptr || sink == nullptr) return false;
   if (width <= 0 || height <= 0 || abs(stride) < BytesPerPixel(fmt) * width) return false;
   sjb_params p;
-  if (!Encoder::Convert(param, fmt, &p)) {
+  std::string meta;
+  if (!Encoder::Convert(param, fmt, &p) || !BuildMetadata(param, &meta)) {
     sink->Reset();
     return false;
   }
-  return EncodeToSink(pix, width, height, stride, fmt, p, sink, param.memory);
+  return EncodeToSink(pix, width, height, stride, fmt, p, sink, param.memory, meta);
 }
 
 bool Encode(const uint8_t* rgb, int width, int height, int stride, const EncoderParam& param, ByteSink* sink) {
@@ -424,7 +578,8 @@ static bool EncodePlanar(const uint8_t* y, int ys, const uint8_t* u, int us, con
   EncoderParam fixed = param;
   fixed.yuv_mode = static_cast<SjpegYUVMode>(mode);
   sjb_params p;
-  if (!Encoder::Convert(fixed, SJB_PIX_RGB, &p)) {
+  std::string meta;
+  if (!Encoder::Convert(fixed, SJB_PIX_RGB, &p) || !BuildMetadata(param, &meta)) {
     sink->Reset();
     return false;
   }
@@ -438,12 +593,7 @@ static bool EncodePlanar(const uint8_t* y, int ys, const uint8_t* u, int us, con
   uint8_t* staging = static_cast<uint8_t*>(memory->Alloc(size));
   if (staging == nullptr) return false;
   bool ok = sjb_fetch_output(ctx, staging, 0, size) == SJB_OK;
-  uint8_t* dst = nullptr;
-  ok = ok && sink->Commit(0, size, &dst) && dst != nullptr;
-  if (ok) {
-    memcpy(dst, staging, size);
-    ok = sink->Commit(size, 0, &dst) && sink->Finalize();
-  }
+  ok = ok && CommitWithMetadata(staging, size, meta, sink);
   memory->Free(staging);
   if (!ok) sink->Reset();
   return ok;

@@ -290,3 +290,77 @@ def test_planar_and_semiplanar_inputs(gpu_ctx, kind):
             p = S.default_params(q, method, O.KIND_MODE[kind])
             got = gpu_ctx.encode_planar(*O.planar_args(kind, planes), w, h, p)
             assert got == O.oracle_encode_planar(kind, planes, w, h, q, method), (kind, w, h, q, method)
+
+
+def _api_shims():
+    """oracle/ref_shim.cc only uses the PUBLIC sjpeg.h API, so the same source compiled against
+    include/sjpeg.h + libsjpeg_b200.so gives a C door onto the product's C++ facade."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "tests", "emul", "libapi_shim.so")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", os.path.join(root, "include"), "-o", so,
+                    os.path.join(root, "oracle", "ref_shim.cc"), "-L", os.path.join(root, "sjpeg_b200"),
+                    "-lsjpeg_b200", "-Wl,-rpath," + os.path.join(root, "sjpeg_b200")], check=True)
+    prod = C.CDLL(so)
+    ref = O.ref()
+    for L in (prod, ref):
+        L.ref_encode_meta.restype = C.c_size_t
+        L.ref_encode_meta.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float] + \
+            [C.c_char_p, C.c_size_t] * 4 + [C.c_int, C.POINTER(C.POINTER(C.c_uint8))]
+        L.ref_encode_param.restype = C.c_size_t
+        L.ref_encode_param.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float] + \
+            [C.c_int] * 6 + [C.POINTER(C.POINTER(C.c_uint8))]
+    return prod, ref
+
+
+def _call_meta(L, free, rgb, w, h, mode, q, exif=b"", iccp=b"", xmp=b"", app=b"", split=0):
+    out = C.POINTER(C.c_uint8)()
+    n = L.ref_encode_meta(rgb.ctypes.data, w, h, 3 * w, mode, q, exif, len(exif), iccp, len(iccp), xmp, len(xmp),
+                          app, len(app), split, C.byref(out))
+    if n == 0:
+        return None
+    data = C.string_at(out, n)
+    free(out)
+    return data
+
+
+@pytest.mark.skipif(O.ref() is None, reason="oracle/_ref not shipped")
+def test_cpp_facade_params_and_metadata_equal_reference(gpu_ctx):
+    """sjpeg::Encode with an EncoderParam through the product's C++ facade vs the compiled
+    reference: custom matrices / bias / deltas / trellis flag (api.cc:145-181) and the metadata
+    segments EXIF, ICC (multi-chunk), XMP, extended XMP with its MD5 GUID, raw app markers
+    (headers.cc:63-180)."""
+    import sjpeg_b200 as S
+    prod, ref = _api_shims()
+    w, h = 203, 117
+    rgb = O.make_rgb("A", w, h)
+    rng = np.random.RandomState(9)
+    # --- EncoderParam fields ---
+    quant = rng.randint(1, 120, (2, 64)).astype(np.uint8)
+    for mode in (O.YUV_420, O.YUV_444, O.YUV_400):
+        for (hf, ad, tr, bias, dl, dc) in ((1, 1, 0, -1, -1, -1), (0, 0, 0, 0x60, -1, -1), (1, 1, 1, 0x78, 6, 3),
+                                           (0, 1, 0, 0x90, 12, 12), (1, 0, 1, -1, -1, -1)):
+            outs = []
+            for L, free in ((prod, S.lib().SjpegFreeBuffer), (ref, ref.SjpegFreeBuffer)):
+                out = C.POINTER(C.c_uint8)()
+                n = L.ref_encode_param(rgb.ctypes.data, w, h, 3 * w, mode, quant.ctypes.data, 85.0, hf, ad, tr, bias,
+                                       dl, dc, C.byref(out))
+                outs.append(C.string_at(out, n) if n else None)
+                if n:
+                    free(out)
+            assert outs[0] is not None and outs[0] == outs[1], (mode, hf, ad, tr, bias, dl, dc)
+    # --- metadata ---
+    note = b'<x:xmpmeta xmpNote:HasExtendedXMP="' + b"0" * 32 + b'" >'
+    big_xmp = note + bytes(rng.randint(32, 127, 150000).astype(np.uint8))
+    cases = [dict(exif=b"II*\x00" + bytes(rng.randint(0, 256, 300).astype(np.uint8))),
+             dict(iccp=bytes(rng.randint(0, 256, 150000).astype(np.uint8))),
+             dict(xmp=b"<x:xmpmeta>small</x:xmpmeta>"),
+             dict(xmp=big_xmp), dict(xmp=big_xmp, split=40000),
+             dict(app=b"\xff\xe5\x00\x06ABCD"),
+             dict(exif=b"E" * 10, iccp=b"I" * 70000, xmp=b"X" * 100, app=b"\xff\xe7\x00\x04zz"),
+             dict(exif=b"E" * 70000),                     # too large: both must refuse
+             dict(xmp=b"Y" * 70000)]                      # extended without the note: both must refuse
+    for kw in cases:
+        a = _call_meta(prod, S.lib().SjpegFreeBuffer, rgb, w, h, O.YUV_420, 75.0, **kw)
+        b = _call_meta(ref, ref.SjpegFreeBuffer, rgb, w, h, O.YUV_420, 75.0, **kw)
+        assert a == b, {k: (len(v) if isinstance(v, bytes) else v) for k, v in kw.items()}
