@@ -94,6 +94,31 @@ int sjb_encode_planar(sjb_context* ctx, const uint8_t* y, long long y_stride, co
                       int width, int height, const sjb_params* params, uint8_t* out, int out_on_device,
                       size_t out_capacity, size_t* out_size);
 
+/*
+ * Multi-pass search for a target size or PSNR = Encoder::LoopScan (/root/reference/src/dichotomy.cc:113-205,
+ * used when EncoderParam::passes > 1, api.cc:169-176).  The unquantised coefficients (and, for the
+ * adaptive methods, their histogram) stay in device memory; every pass re-quantises them with the
+ * matrices the callbacks propose and measures the size (symbol statistics / exact bit count incl.
+ * stuffing, dichotomy.cc:210-298) or the PSNR (quantize.cc:547-559, dichotomy.cc:302-323).
+ * The callbacks are SearchHook's virtuals (sjpeg.h:355-372).  Arm a search with
+ * sjb_context_set_search(); it applies to the NEXT sjb_encode / sjb_encode_planar call on the
+ * context and is then cleared.
+ */
+typedef struct sjb_search {
+  int passes;                 /* 2..20 */
+  int for_size;               /* 1: target is a size in bytes, 0: a PSNR in dB */
+  float target;
+  size_t header_extra_bytes;  /* metadata part of Encoder::HeaderSize(), dichotomy.cc:212-229 */
+  void* user;
+  void (*begin_pass)(void* user, int pass);
+  void (*next_matrix)(void* user, int idx, uint8_t dst[64]);   /* SearchHook::NextMatrix */
+  int (*update)(void* user, float result);                     /* SearchHook::Update: non-zero = done */
+  /* filled on return: index of the pass whose matrices were kept, and its measured value */
+  int best_pass;
+  float best_result;
+} sjb_search;
+int sjb_context_set_search(sjb_context* ctx, sjb_search* search /* NULL disarms */);
+
 /* Copies the JPEG produced by the most recent sjb_encode() of this context (it stays resident in
  * device memory until the next encode).  Lets a caller learn the size first -- sjb_encode with
  * out == NULL returns SJB_ERR_CAPACITY and the size -- and then fetch into an exact allocation. */

@@ -66,3 +66,24 @@ extern "C" size_t ref_encode_meta(const uint8_t* rgb, int w, int h, int stride, 
   p.xmp_split_point = static_cast<uint16_t>(xmp_split);
   return sjpeg::Encode(rgb, w, h, stride, p, out);
 }
+
+// target size / PSNR search (sjpeg.h:214-226, dichotomy.cc)
+extern "C" size_t ref_encode_search(const uint8_t* rgb, int w, int h, int stride, int yuv_mode, float quality,
+                                    int target_mode, float target_value, int passes, float tolerance, int huffman,
+                                    int adaptive, int trellis, float* final_q, float* final_value, uint8_t** out) {
+  sjpeg::EncoderParam p(quality);
+  p.yuv_mode = static_cast<SjpegYUVMode>(yuv_mode);
+  p.Huffman_compress = huffman != 0;
+  p.adaptive_quantization = adaptive != 0;
+  p.use_trellis = trellis != 0;
+  p.target_mode = static_cast<sjpeg::EncoderParam::TargetMode>(target_mode);
+  p.target_value = target_value;
+  p.passes = passes;
+  p.tolerance = tolerance;
+  sjpeg::SearchHook hook;
+  p.search_hook = &hook;
+  const size_t n = sjpeg::Encode(rgb, w, h, stride, p, out);
+  if (final_q) *final_q = hook.q;
+  if (final_value) *final_value = hook.value;
+  return n;
+}

@@ -8,6 +8,7 @@
 // (stream + scratch for one group); groups of a batch rotate over the lanes so that the copies
 // and kernels of different groups overlap.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -86,7 +87,7 @@ struct SmallLayout {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  DeviceBuffer pix, coef, nzmask, words, out, state, small;
+  DeviceBuffer pix, coef, nzmask, words, out, state, small, raw;
   HostScratch* host = nullptr;
   GroupBuffers gb = {};
   int group_capacity = 0;        // pictures the buffers are laid out for
@@ -108,6 +109,7 @@ struct sjb_context {
   int sm_count = 0;
   Lane lanes[kMaxLanes];
   std::string err;
+  sjb_search* search = nullptr;   // armed by sjb_context_set_search for the next single encode
 };
 
 namespace {
@@ -138,7 +140,7 @@ int InitLane(sjb_context* ctx, Lane* L) {
 
 void DestroyLane(Lane* L) {
   if (L->stream) cudaStreamSynchronize(L->stream);
-  for (DeviceBuffer* b : {&L->pix, &L->coef, &L->nzmask, &L->words, &L->out, &L->state, &L->small}) b->Release();
+  for (DeviceBuffer* b : {&L->pix, &L->coef, &L->nzmask, &L->words, &L->out, &L->state, &L->small, &L->raw}) b->Release();
   for (auto& e : L->ev) if (e) cudaEventDestroy(e);
   if (L->host) cudaFreeHost(L->host);
   if (L->stream) cudaStreamDestroy(L->stream);
@@ -382,9 +384,9 @@ int EncodeGroup(sjb_context* ctx, Lane* L, const FrameSet& fs, const Plan& plan,
       // rate model = default AC tables (enc.cc:334)
       CU(cudaMemcpyAsync(D->quant, H->quant, n * 128, cudaMemcpyHostToDevice, L->stream));
       RC(upload_tabs());
-      LaunchTrellis(fs, gb, L->stream);
+      LaunchTrellis(fs, gb, nullptr, L->stream);
     } else {
-      LaunchRequantize(fs, gb, L->stream);
+      LaunchRequantize(fs, gb, nullptr, L->stream);
     }
     L->launches += 1;
   } else {
@@ -456,6 +458,226 @@ int EncodeGroup(sjb_context* ctx, Lane* L, const FrameSet& fs, const Plan& plan,
   return SJB_OK;
 }
 
+// Encoder::LoopScan (dichotomy.cc:113-205) for one picture on lane L.
+int EncodeSearch(sjb_context* ctx, Lane* L, const FrameSet& fs, const Plan& plan, sjb_search* S) {
+  const FrameGeometry& g = plan.g;
+  HostScratch* H = L->host;
+  SmallLayout* D = L->d_small();
+  GroupBuffers gb = L->gb;
+  const size_t nb = g.nb_blocks();
+  const int nb_tables = (g.nb_comps == 1) ? 1 : 2;
+  const int passes = std::min(20, std::max(1, S->passes));
+
+  uint8_t quant[2][64], min_quant[2][64];
+  QuantTabs qt;
+  if (!MakeQuantTabs(plan, quant, min_quant, &qt)) return SJB_ERR_ARG;
+  if (L->words_dirty) {
+    CU(cudaMemsetAsync(L->words.ptr, 0, L->words.bytes, L->stream));
+    L->words_dirty = false;
+  }
+  CU(cudaEventRecord(L->ev[0], L->stream));
+  // unquantised coefficients -> raw buffer (kept for all passes)
+  CU(L->raw.Reserve(nb * 64 * sizeof(int16_t)));
+  {
+    GroupBuffers graw = gb;
+    graw.coef = L->raw.as<int16_t>();
+    Lane tmp_view;   // LaunchF1 only reads gb / stream / launches
+    tmp_view.gb = graw;
+    tmp_view.stream = L->stream;
+    LaunchF1(&tmp_view, fs, g, /*raw=*/true, qt);
+    L->launches += tmp_view.launches;
+    tmp_view.stream = nullptr;
+    if (plan.adaptive) {                                           // dichotomy.cc:117-121
+      CU(cudaMemsetAsync(D->hist, 0, sizeof(D->hist[0]), L->stream));
+      LaunchHistogram(fs, graw, L->stream);
+      CU(cudaMemcpyAsync(H->hist, D->hist, sizeof(D->hist[0]), cudaMemcpyDeviceToHost, L->stream));
+    }
+  }
+  CU(cudaEventRecord(L->ev[1], L->stream));
+  CU(cudaStreamSynchronize(L->stream));
+  const int16_t* raw = L->raw.as<int16_t>();
+
+  // current Huffman tables: default until statistics are compiled (entropy.cc:84-86)
+  HuffSpec spec[4];
+  for (int i = 0; i < 4; ++i) DefaultHuffSpec(i >= 2, i & 1, &spec[i]);
+  CodeTabs tabs;
+  memset(&tabs, 0, sizeof(tabs));
+  auto rebuild_codes = [&]() {
+    for (int c = 0; c < nb_tables; ++c) {
+      CodesFromSpec(spec[c], tabs.dc[c]);
+      CodesFromSpec(spec[2 + c], tabs.ac[c]);
+    }
+  };
+  for (int c = 0; c < 2; ++c) {
+    CodesFromSpec(spec[c], tabs.dc[c]);
+    CodesFromSpec(spec[2 + c], tabs.ac[c]);
+  }
+  auto upload_tabs = [&]() -> int {
+    CU(cudaStreamSynchronize(L->stream));
+    H->tabs[0] = tabs;
+    CU(cudaMemcpyAsync(D->tabs, H->tabs, sizeof(CodeTabs), cudaMemcpyHostToDevice, L->stream));
+    L->tabs_valid = 0;
+    return SJB_OK;
+  };
+  auto upload_quant = [&]() -> int {
+    CU(cudaStreamSynchronize(L->stream));
+    H->qtabs[0] = qt;
+    memcpy(H->quant[0], quant, 128);
+    CU(cudaMemcpyAsync(D->qtabs, H->qtabs, sizeof(QuantTabs), cudaMemcpyHostToDevice, L->stream));
+    CU(cudaMemcpyAsync(D->quant, H->quant, 128, cudaMemcpyHostToDevice, L->stream));
+    return SJB_OK;
+  };
+  // StoreRunLevels (dichotomy.cc:80-111): quantise raw -> gb.coef with the current matrices (the
+  // trellis prices with the AC codes in force), gather symbol statistics when optimising
+  auto store_run_levels = [&]() -> int {
+    RC(upload_quant());
+    if (plan.trellis) {
+      RC(upload_tabs());
+      LaunchTrellis(fs, gb, raw, L->stream);
+    } else {
+      LaunchRequantize(fs, gb, raw, L->stream);
+    }
+    ++L->launches;
+    if (plan.optimize) {
+      CU(cudaMemsetAsync(D->freq, 0, sizeof(D->freq[0]), L->stream));
+      LaunchSymbolStats(fs, gb, L->stream);
+      ++L->launches;
+      CU(cudaMemcpyAsync(H->freq, D->freq, sizeof(D->freq[0]), cudaMemcpyDeviceToHost, L->stream));
+      CU(cudaStreamSynchronize(L->stream));
+    }
+    CU(cudaGetLastError());
+    return SJB_OK;
+  };
+  auto compile_stats = [&]() {                                     // entropy.cc:432-444
+    for (int c = 0; c < nb_tables; ++c) {
+      OptimalHuffSpec(H->freq[0] + 272 * c + 256, 12, &spec[c]);
+      OptimalHuffSpec(H->freq[0] + 272 * c, 256, &spec[2 + c]);
+    }
+  };
+  auto header_bits = [&]() -> size_t {                             // dichotomy.cc:210-243
+    size_t size = 20 + S->header_extra_bytes;
+    size += nb_tables * 65 + 2 + 2;
+    size += 8 + 3 * g.nb_comps + 2;
+    size += 6 + 2 * g.nb_comps + 2;
+    size += 2;
+    for (int c = 0; c < nb_tables; ++c) {
+      size += 2 + 3 + 16 + spec[c].nb_syms;
+      size += 2 + 3 + 16 + spec[2 + c].nb_syms;
+    }
+    return size * 8;
+  };
+
+  uint8_t opt_quants[2][64];
+  memcpy(opt_quants, quant, 128);
+  float best = 0.f, best_result = 0.f;
+  int best_pass = 0;
+  bool last_is_best = false;
+  for (int p = 0; p < passes; ++p) {
+    if (S->begin_pass) S->begin_pass(S->user, p);
+    for (int c = 0; c < 2; ++c) {
+      S->next_matrix(S->user, c, quant[c]);
+      if (!FinalizeQuantizer(quant[c], min_quant[c], plan.p.q_bias, &qt.m[c])) return SJB_ERR_ARG;
+    }
+    if (plan.adaptive) {
+      AnalyseHistograms(H->hist[0], g.nb_comps, quant, min_quant, plan.p.qdelta_max_luma, plan.p.qdelta_max_chroma);
+      for (int c = (g.nb_comps > 1 ? 1 : 0); c >= 0; --c) {
+        if (!FinalizeQuantizer(quant[c], min_quant[c], plan.p.q_bias, &qt.m[c])) return SJB_ERR_ARG;
+      }
+    }
+    float result;
+    if (S->for_size) {
+      RC(store_run_levels());
+      size_t size;
+      if (plan.optimize) {
+        compile_stats();                                           // dichotomy.cc:150-153
+        rebuild_codes();                                           // ComputeSize: InitCodes(false)
+        size = header_bits();
+        for (int q = 0; q < nb_tables; ++q) {                      // EntropySize, entropy.cc:230-245
+          const uint32_t* f = H->freq[0] + 272 * q;
+          for (int len = 0; len < 12; ++len) if (f[256 + len]) size += static_cast<size_t>(f[256 + len]) * ((tabs.dc[q][len] & 0xff) + len);
+          for (int sym = 0; sym < 256; ++sym) if (f[sym]) size += static_cast<size_t>(f[sym]) * ((tabs.ac[q][sym] & 0xff) + (sym & 0x0f));
+        }
+      } else {
+        // exact bit count incl. the 0x00 after every complete 0xFF byte (BitCounter, bit_writer.h:292-365)
+        rebuild_codes();
+        size = header_bits();
+        RC(upload_tabs());
+        CU(cudaMemsetAsync(L->state.ptr, 0, L->state.bytes, L->stream));
+        LaunchEntropyPack(fs, gb, L->stream);
+        StuffArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.header_len[0] = kHeaderReserve;          // scratch area of the out slot
+        sa.flags[0] = kStuffFirst | kStuffKeepWords;
+        LaunchStuff(fs, gb, sa, L->stream);
+        L->launches += 2;
+        CU(cudaMemcpyAsync(H->info, D->info, sizeof(StreamInfo), cudaMemcpyDeviceToHost, L->stream));
+        CU(cudaMemsetAsync(L->words.ptr, 0, L->words.bytes, L->stream));
+        CU(cudaStreamSynchronize(L->stream));
+        CU(cudaGetLastError());
+        L->header_valid = 0;
+        size += static_cast<size_t>(H->info[0].total_bits) + 8 * static_cast<size_t>(H->info[0].stuffed_bytes);
+      }
+      result = size / 8.f;
+    } else {
+      RC(upload_quant());
+      unsigned long long* d_err = reinterpret_cast<unsigned long long*>(&D->info[1]);   // spare record
+      CU(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), L->stream));
+      LaunchQuantError(fs, gb, raw, d_err - 0, L->stream);
+      ++L->launches;
+      CU(cudaMemcpyAsync(&H->info[1], &D->info[1], sizeof(StreamInfo), cudaMemcpyDeviceToHost, L->stream));
+      CU(cudaStreamSynchronize(L->stream));
+      CU(cudaGetLastError());
+      const unsigned long long err = H->info[1].total_bits;
+      const unsigned long long size = 64ull * nb;
+      result = (err > 0 && size > 0) ? static_cast<float>(4.3429448f * log(size / (err / 255. / 255.))) : 99.f;
+    }
+    last_is_best = (p == 0 || fabs(result - S->target) < best);
+    if (last_is_best) {
+      memcpy(opt_quants, quant, 128);
+      best = static_cast<float>(fabs(result - S->target));
+      best_pass = p;
+      best_result = result;
+    }
+    if (S->update(S->user, result)) break;
+  }
+  S->best_pass = best_pass;
+  S->best_result = best_result;
+
+  // transfer back the kept matrices and finish (dichotomy.cc:176-203)
+  memcpy(quant, opt_quants, 128);
+  for (int c = 0; c < 2; ++c) {
+    if (!FinalizeQuantizer(quant[c], min_quant[c], plan.p.q_bias, &qt.m[c])) return SJB_ERR_ARG;
+  }
+  if (!S->for_size || !last_is_best) {
+    RC(store_run_levels());
+    if (plan.optimize) compile_stats();
+  }
+  rebuild_codes();
+  RC(upload_tabs());
+  std::vector<uint8_t> header;
+  AppendHeaders(g, quant, spec, &header);
+  if (header.size() > kHeaderReserve) return SJB_ERR_ARG;
+  CU(cudaStreamSynchronize(L->stream));
+  memcpy(H->header[0], header.data(), header.size());
+  L->header_len[0] = static_cast<unsigned>(header.size());
+  L->header_valid = 0;
+  CU(cudaMemcpyAsync(gb.out, H->header[0], header.size(), cudaMemcpyHostToDevice, L->stream));
+  L->words_dirty = true;
+  CU(cudaMemsetAsync(L->state.ptr, 0, L->state.bytes, L->stream));
+  LaunchEntropyPack(fs, gb, L->stream);
+  StuffArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.header_len[0] = L->header_len[0];
+  sa.flags[0] = kStuffFirst | kStuffLast;
+  LaunchStuff(fs, gb, sa, L->stream);
+  L->launches += 2;
+  CU(cudaGetLastError());
+  L->words_dirty = false;
+  CU(cudaEventRecord(L->ev[2], L->stream));
+  CU(cudaMemcpyAsync(H->info, D->info, sizeof(StreamInfo), cudaMemcpyDeviceToHost, L->stream));
+  return SJB_OK;
+}
+
 int FinishTimings(sjb_context* ctx, Lane* L) {
   CU(cudaEventSynchronize(L->ev[2]));
   CU(cudaEventElapsedTime(&L->ms_total, L->ev[0], L->ev[2]));
@@ -478,7 +700,9 @@ int EncodeSingle(sjb_context* ctx, const uint8_t* pix, int pix_on_device, long l
     RC(UploadPicture(ctx, L, pix, plan, stride, 0, &fs.pix[0], &fs.stride));
   }
   L->launches = 0;
-  const int rc = EncodeGroup(ctx, L, fs, plan, timed);
+  sjb_search* search = ctx->search;
+  ctx->search = nullptr;
+  const int rc = search ? EncodeSearch(ctx, L, fs, plan, search) : EncodeGroup(ctx, L, fs, plan, timed);
   if (rc != SJB_OK) L->words_dirty = true;
   return rc;
 }
@@ -747,7 +971,9 @@ int sjb_encode_planar(sjb_context* ctx, const uint8_t* y, long long y_stride, co
     }
   }
   L->launches = 0;
-  const int rc = EncodeGroup(ctx, L, fs, plan, /*timed=*/true);
+  sjb_search* search = ctx->search;
+  ctx->search = nullptr;
+  const int rc = search ? EncodeSearch(ctx, L, fs, plan, search) : EncodeGroup(ctx, L, fs, plan, /*timed=*/true);
   if (rc != SJB_OK) {
     L->words_dirty = true;
     return rc;
@@ -761,6 +987,13 @@ int sjb_encode_planar(sjb_context* ctx, const uint8_t* y, long long y_stride, co
   CU(cudaMemcpyAsync(out, L->out.ptr, size, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                      L->stream));
   CU(cudaStreamSynchronize(L->stream));
+  return SJB_OK;
+}
+
+int sjb_context_set_search(sjb_context* ctx, sjb_search* search) {
+  if (ctx == nullptr) return SJB_ERR_ARG;
+  if (search && (search->next_matrix == nullptr || search->update == nullptr || search->passes < 1)) return SJB_ERR_ARG;
+  ctx->search = search;
   return SJB_OK;
 }
 

@@ -488,7 +488,7 @@ __device__ __forceinline__ void load_block_natural(const int16_t* src, int (&v)[
 }
 
 __global__ void __launch_bounds__(128)
-requantize_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
+requantize_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, const int16_t* __restrict__ raw_src) {
   __shared__ __align__(16) int32_t qtab[2][64][2];
   const int frame = blockIdx.y;
   {
@@ -500,9 +500,57 @@ requantize_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   if (g >= fs.blocks_per_frame) return;
   int16_t* blk = gb.coef + frame * gb.coef_pitch + g * 64;
   int v[64];
-  load_block_natural(blk, v);
+  load_block_natural(raw_src ? raw_src + frame * gb.coef_pitch + g * 64 : blk, v);
   const uint32_t tab = smem_addr(qtab) + ((static_cast<int>(g % fs.mcu_blocks) >= fs.luma_blocks) ? 512u : 0u);
   quantize_store_block(v, SmemTab{tab}, blk, gb.nzmask + frame * gb.mask_pitch + g);
+}
+
+// -------------------------------------------------------------------------------------------
+// Quantisation error of stored raw coefficients for the PSNR search (quantize.cc:547-559,
+// dichotomy.cc:309-323): sum over all coefficients of ((|c| >> 4) - Q * quantise(|c|))^2 with the
+// matrices gb.quant[frame] / tables gb.qtabs[frame]; one 64-bit sum per picture.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+quant_error_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, const int16_t* __restrict__ raw,
+                   unsigned long long* __restrict__ err_out) {
+  __shared__ int32_t qtab[2][64][2];     // zig-zag order {iq, cpos}
+  __shared__ uint8_t qm[2][64];          // natural order
+  __shared__ unsigned long long warp_sums[8];
+  const int frame = blockIdx.y;
+  {
+    const int32_t* q = &gb.qtabs[frame].m[0].e[0][0];
+    const uint8_t* quant = gb.quant + frame * 128;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) (&qtab[0][0][0])[i] = q[i];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) qm[i >> 6][i & 63] = quant[i];
+  }
+  __syncthreads();
+  constexpr int zz[64] = SJB_ZIGZAG_INIT;
+  unsigned long long sum = 0;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; g < fs.blocks_per_frame; g += stride) {
+    const int c = (static_cast<int>(g % fs.mcu_blocks) >= fs.luma_blocks) ? 1 : 0;
+    int v[64];
+    load_block_natural(raw + frame * gb.coef_pitch + g * 64, v);
+    uint32_t e = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      const int j = zz[i];
+      const int a = abs(v[j]);
+      const uint32_t q = static_cast<uint32_t>(qm[c][j]) * static_cast<uint32_t>((a * qtab[c][i][0] + qtab[c][i][1]) >> 20);
+      const uint32_t d = static_cast<uint32_t>(a >> 4) - q;
+      e += d * d;
+    }
+    sum += e;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w) t += warp_sums[w];
+    atomicAdd(&err_out[frame], t);
+  }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -892,7 +940,7 @@ struct TrellisNode {
 };
 
 __global__ void __launch_bounds__(64)
-trellis_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
+trellis_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, const int16_t* __restrict__ raw_src) {
   __shared__ uint8_t ac_len[2][256];
   __shared__ uint8_t qm[2][64];
   __shared__ int32_t qtab[2][64][2];
@@ -917,7 +965,7 @@ trellis_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   uint32_t disto0[64];
   int16_t in[64];
   {
-    const uint4* s = reinterpret_cast<const uint4*>(blk);
+    const uint4* s = reinterpret_cast<const uint4*>(raw_src ? raw_src + frame * gb.coef_pitch + g * 64 : blk);
     uint4* d = reinterpret_cast<uint4*>(in);
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = s[i];
@@ -1074,8 +1122,15 @@ void LaunchF1Fast(const FrameSet& fs, int mx_full, int my0, int my1, bool raw, c
   }
 }
 
-void LaunchRequantize(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {
-  requantize_kernel<<<dim3(cdiv(fs.blocks_per_frame, 128), fs.frames), 128, 0, s>>>(fs, gb);
+void LaunchRequantize(const FrameSet& fs, const GroupBuffers& gb, const int16_t* raw_src, cudaStream_t s) {
+  requantize_kernel<<<dim3(cdiv(fs.blocks_per_frame, 128), fs.frames), 128, 0, s>>>(fs, gb, raw_src);
+}
+
+void LaunchQuantError(const FrameSet& fs, const GroupBuffers& gb, const int16_t* raw, unsigned long long* err,
+                      cudaStream_t s) {
+  unsigned grid = cdiv(fs.blocks_per_frame, 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  quant_error_kernel<<<dim3(grid, fs.frames), 256, 0, s>>>(fs, gb, raw, err);
 }
 
 void LaunchHistogram(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {
@@ -1095,8 +1150,8 @@ void LaunchHistogram(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s)
   histogram_kernel<<<dim3(grid, fs.frames), 256, smem, s>>>(fs, gb);
 }
 
-void LaunchTrellis(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {
-  trellis_kernel<<<dim3(cdiv(fs.blocks_per_frame, 64), fs.frames), 64, 0, s>>>(fs, gb);
+void LaunchTrellis(const FrameSet& fs, const GroupBuffers& gb, const int16_t* raw_src, cudaStream_t s) {
+  trellis_kernel<<<dim3(cdiv(fs.blocks_per_frame, 64), fs.frames), 64, 0, s>>>(fs, gb, raw_src);
 }
 
 void LaunchSymbolStats(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {

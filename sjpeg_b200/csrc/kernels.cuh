@@ -89,12 +89,17 @@ void LaunchF1Fast(const FrameSet& fs, int mx_full, int my0, int my1, bool raw, c
                   const GroupBuffers& gb, cudaStream_t s);
 
 // Q1: quantise stored raw coefficients in place (natural -> zig-zag) + bitmap; tables gb.qtabs[frame]
-void LaunchRequantize(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s);
+// raw_src = null: in place (gb.coef holds the raw values); else raw values are read from raw_src
+// (same pitch as gb.coef) and the result goes to gb.coef, leaving the raw copy intact (search).
+void LaunchRequantize(const FrameSet& fs, const GroupBuffers& gb, const int16_t* raw_src, cudaStream_t s);
+// PSNR search: err[frame] += sum of squared quantisation errors of the raw coefficients
+void LaunchQuantError(const FrameSet& fs, const GroupBuffers& gb, const int16_t* raw, unsigned long long* err,
+                      cudaStream_t s);
 // H1: histogram of |coef| >> 2 per matrix and position into gb.hist[frame] (pre-zeroed)
 void LaunchHistogram(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s);
 // T1: trellis quantisation of raw coefficients in place (quantize.cc:388-457) + bitmap; tables
 // gb.qtabs[frame], matrices gb.quant[frame], rate from the AC code lengths in gb.tabs[frame]
-void LaunchTrellis(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s);
+void LaunchTrellis(const FrameSet& fs, const GroupBuffers& gb, const int16_t* raw_src, cudaStream_t s);
 // S1: symbol statistics into gb.freq[frame] (slot < 256 AC symbol, 256+n DC size), pre-zeroed
 void LaunchSymbolStats(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s);
 

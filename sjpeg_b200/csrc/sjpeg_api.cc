@@ -41,26 +41,14 @@ int BytesPerPixel(int fmt) { return fmt == SJB_PIX_RGB ? 3 : 4; }
 // api.cc:183-192 + encoders.cc:546-568 + api.cc:145-181, ending in a sink
 bool CommitWithMetadata(const uint8_t* jpeg, size_t size, const std::string& meta, sjpeg::ByteSink* sink);
 
-bool EncodeToSink(const uint8_t* pix, int width, int height, int stride, int fmt, const sjb_params& params,
-                  sjpeg::ByteSink* sink, sjpeg::MemoryManager* memory, const std::string& meta = std::string()) {
-  sink->Reset();                                        // enc.cc:90
-  sjb_context* ctx = tls_context.get();
-  if (ctx == nullptr) return false;
-  if (memory == nullptr) memory = &default_memory;
-  size_t size = 0;
-  int rc = sjb_encode(ctx, pix, 0, width, height, stride, &params, nullptr, 0, 0, &size);
-  if (rc != SJB_ERR_CAPACITY || size == 0) return false;
-  // host staging goes through the caller's memory manager (sjpeg.h:410-415)
-  uint8_t* staging = static_cast<uint8_t*>(memory->Alloc(size));
-  if (staging == nullptr) return false;
-  bool ok = sjb_fetch_output(ctx, staging, 0, size) == SJB_OK;
-  ok = ok && CommitWithMetadata(staging, size, meta, sink);
-  memory->Free(staging);
-  if (!ok) sink->Reset();                               // bit_writer.cc:99-105
-  (void)fmt;
-  return ok;
-}
+struct SearchState;
+bool ArmSearch(sjb_context* ctx, const sjpeg::EncoderParam& param, sjpeg::SearchHook* fallback, SearchState* st,
+               sjb_search* search);
+void FinishSearch(const sjpeg::EncoderParam& param, SearchState* st, const sjb_search& search, bool ok);
 
+bool EncodeToSink(const uint8_t* pix, int width, int height, int stride, int fmt, const sjb_params& params,
+                  sjpeg::ByteSink* sink, sjpeg::MemoryManager* memory, const std::string& meta = std::string(),
+                  const sjpeg::EncoderParam* full = nullptr);
 // Encoder::InitFromParam, api.cc:145-181
 bool ParamsFromEncoderParam(const sjpeg::EncoderParam& param, const uint8_t quant[2][64],
                             const uint8_t min_quant[2][64], bool use_min_quant, int tolerance, int fmt,
@@ -85,8 +73,6 @@ bool ParamsFromEncoderParam(const sjpeg::EncoderParam& param, const uint8_t quan
   out->qdelta_max_luma = param.qdelta_max_luma;
   out->qdelta_max_chroma = param.qdelta_max_chroma;
   if (out->q_bias < 0 || out->q_bias > 255) return false;
-  // the multi-pass size / PSNR search (dichotomy.cc) is outside the path
-  if (param.passes > 1) return false;
   return true;
 }
 
@@ -243,6 +229,88 @@ bool CommitWithMetadata(const uint8_t* jpeg, size_t size, const std::string& met
   if (!meta.empty()) memcpy(dst + kApp0, meta.data(), meta.size());
   memcpy(dst + kApp0 + meta.size(), jpeg + kApp0, size - kApp0);
   return sink->Commit(total, 0, &dst) && sink->Finalize();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-pass search glue (api.cc:169-176, dichotomy.cc:113-205): SearchHook <-> sjb_search
+// ---------------------------------------------------------------------------------------------
+struct SearchState {
+  sjpeg::SearchHook* hook;
+  float q_of_pass[32];
+};
+void SearchBeginPass(void* user, int pass) {
+  SearchState* st = static_cast<SearchState*>(user);
+  st->hook->pass = pass;
+  st->q_of_pass[pass & 31] = st->hook->q;
+}
+void SearchNextMatrix(void* user, int idx, uint8_t dst[64]) { static_cast<SearchState*>(user)->hook->NextMatrix(idx, dst); }
+int SearchUpdate(void* user, float result) { return static_cast<SearchState*>(user)->hook->Update(result) ? 1 : 0; }
+
+// metadata part of Encoder::HeaderSize() (dichotomy.cc:212-229): an estimate, reproduced as is
+size_t MetadataSizeEstimate(const sjpeg::EncoderParam& p) {
+  size_t size = p.app_markers.size();
+  if (!p.exif.empty()) size += 8 + p.exif.size();
+  if (!p.iccp.empty()) {
+    const size_t chunk_max = 0xffff - 12 - 4;
+    size += ((p.iccp.size() - 1) / chunk_max + 1) * (12 + 4 + 2) + p.iccp.size();
+  }
+  if (!p.xmp.empty()) {
+    size += 2 + 2 + 29 + p.xmp.size();
+    if (p.xmp.size() > 65533) size += (p.xmp.size() / 65458 + 1) * 40;
+  }
+  return size;
+}
+
+// Arms the context's search when param.passes > 1.  Returns false if the hook refuses.
+bool ArmSearch(sjb_context* ctx, const sjpeg::EncoderParam& param, sjpeg::SearchHook* fallback, SearchState* st,
+               sjb_search* search) {
+  const int passes = param.passes < 1 ? 1 : param.passes > 20 ? 20 : param.passes;
+  if (passes <= 1) return true;
+  st->hook = param.search_hook ? param.search_hook : fallback;
+  if (!st->hook->Setup(param)) return false;
+  memset(search, 0, sizeof(*search));
+  search->passes = passes;
+  search->for_size = st->hook->for_size ? 1 : 0;
+  search->target = st->hook->target;
+  search->header_extra_bytes = MetadataSizeEstimate(param);
+  search->user = st;
+  search->begin_pass = SearchBeginPass;
+  search->next_matrix = SearchNextMatrix;
+  search->update = SearchUpdate;
+  return sjb_context_set_search(ctx, search) == SJB_OK;
+}
+void FinishSearch(const sjpeg::EncoderParam& param, SearchState* st, const sjb_search& search, bool ok) {
+  const int passes = param.passes < 1 ? 1 : param.passes > 20 ? 20 : param.passes;
+  if (passes <= 1 || !ok) return;
+  st->hook->q = st->q_of_pass[search.best_pass & 31];      // dichotomy.cc:183-185
+  st->hook->value = search.best_result;
+}
+
+bool EncodeToSink(const uint8_t* pix, int width, int height, int stride, int fmt, const sjb_params& params,
+                  sjpeg::ByteSink* sink, sjpeg::MemoryManager* memory, const std::string& meta,
+                  const sjpeg::EncoderParam* full) {
+  sink->Reset();                                        // enc.cc:90
+  sjb_context* ctx = tls_context.get();
+  if (ctx == nullptr) return false;
+  if (memory == nullptr) memory = &default_memory;
+  SearchState st;
+  sjb_search search;
+  sjpeg::SearchHook default_hook;
+  if (full != nullptr && !ArmSearch(ctx, *full, &default_hook, &st, &search)) return false;
+  size_t size = 0;
+  const int rc = sjb_encode(ctx, pix, 0, width, height, stride, &params, nullptr, 0, 0, &size);
+  sjb_context_set_search(ctx, nullptr);
+  if (rc != SJB_ERR_CAPACITY || size == 0) return false;
+  if (full != nullptr) FinishSearch(*full, &st, search, true);
+  // host staging goes through the caller's memory manager (sjpeg.h:410-415)
+  uint8_t* staging = static_cast<uint8_t*>(memory->Alloc(size));
+  if (staging == nullptr) return false;
+  bool ok = sjb_fetch_output(ctx, staging, 0, size) == SJB_OK;
+  ok = ok && CommitWithMetadata(staging, size, meta, sink);
+  memory->Free(staging);
+  if (!ok) sink->Reset();                               // bit_writer.cc:99-105
+  (void)fmt;
+  return ok;
 }
 
 // sinks (bit_writer.h:51-93)
@@ -526,7 +594,7 @@ static bool EncodePacked(const uint8_t* pix, int width, int height, int stride, 
     sink->Reset();
     return false;
   }
-  return EncodeToSink(pix, width, height, stride, fmt, p, sink, param.memory, meta);
+  return EncodeToSink(pix, width, height, stride, fmt, p, sink, param.memory, meta, &param);
 }
 
 bool Encode(const uint8_t* rgb, int width, int height, int stride, const EncoderParam& param, ByteSink* sink) {
@@ -587,9 +655,15 @@ static bool EncodePlanar(const uint8_t* y, int ys, const uint8_t* u, int us, con
   sjb_context* ctx = tls_context.get();
   if (ctx == nullptr) return false;
   sjpeg::MemoryManager* memory = param.memory ? param.memory : &default_memory;
+  SearchState st;
+  sjb_search search;
+  sjpeg::SearchHook default_hook;
+  if (!ArmSearch(ctx, param, &default_hook, &st, &search)) return false;
   size_t size = 0;
   const int rc = sjb_encode_planar(ctx, y, ys, u, us, v, vs, uv_step, 0, width, height, &p, nullptr, 0, 0, &size);
+  sjb_context_set_search(ctx, nullptr);
   if (rc != SJB_ERR_CAPACITY || size == 0) return false;
+  FinishSearch(param, &st, search, true);
   uint8_t* staging = static_cast<uint8_t*>(memory->Alloc(size));
   if (staging == nullptr) return false;
   bool ok = sjb_fetch_output(ctx, staging, 0, size) == SJB_OK;
@@ -642,7 +716,7 @@ bool EncodeYUV420(const uint8_t* Y, int Y_stride, const uint8_t* U, int U_stride
 bool SearchHook::Setup(const EncoderParam& param) {
   for_size = (param.target_mode == EncoderParam::TARGET_SIZE);
   target = param.target_value;
-  tolerance = param.tolerance / 100.f;
+  tolerance = static_cast<float>(param.tolerance / 100.);
   qmin = param.qmin < 0 ? 0 : param.qmin;
   qmax = param.qmax > 100 ? 100 : (param.qmax < param.qmin ? param.qmin : param.qmax);
   q = SjpegEstimateQuality(param.GetQuantMatrix(0), false);
@@ -657,7 +731,7 @@ bool SearchHook::Update(float result) {
   if (fabsf(value - target) < tolerance * target) return true;
   if (value > target) qmax = q; else qmin = q;
   const float last = q;
-  q = (qmin + qmax) / 2.f;
+  q = static_cast<float>((qmin + qmax) / 2.);
   return fabsf(q - last) < 0.15f;
 }
 

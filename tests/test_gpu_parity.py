@@ -265,7 +265,7 @@ def test_row_stripes_on_one_gpu(gpu_ctx, parts):
 # the reference's own API tests that lie inside this round's scope
 REFERENCE_TESTS_IN_SCOPE = ["InvalidArguments", "SinkFailure", "CompressionMethod", "Compress", "Dimensions",
                             "QuantMatrix", "LargeDimensions", "EncodeYUV420Strides", "EncodeYUV444Strides",
-                            "EncodeNV", "NegativeStrides"]
+                            "EncodeNV", "NegativeStrides", "TargetSize", "AllocationFailure"]
 
 
 def test_reference_unit_tests_against_the_product_library(gpu_ctx):
@@ -364,3 +364,35 @@ def test_cpp_facade_params_and_metadata_equal_reference(gpu_ctx):
         a = _call_meta(prod, S.lib().SjpegFreeBuffer, rgb, w, h, O.YUV_420, 75.0, **kw)
         b = _call_meta(ref, ref.SjpegFreeBuffer, rgb, w, h, O.YUV_420, 75.0, **kw)
         assert a == b, {k: (len(v) if isinstance(v, bytes) else v) for k, v in kw.items()}
+
+
+@pytest.mark.skipif(O.ref() is None, reason="oracle/_ref not shipped")
+def test_target_size_and_psnr_search_equal_reference(gpu_ctx):
+    """EncoderParam::passes > 1 (Encoder::LoopScan, dichotomy.cc:113-205): same bytes, same final q
+    and measured value as the compiled reference, for size and PSNR targets."""
+    import sjpeg_b200 as S
+    prod, ref = _api_shims()
+    for L in (prod, ref):
+        L.ref_encode_search.restype = C.c_size_t
+        L.ref_encode_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float,
+                                        C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                        C.POINTER(C.c_float), C.POINTER(C.POINTER(C.c_uint8))]
+    w, h = 203, 117
+    for gen in ("A", "B"):
+        rgb = O.make_rgb(gen, w, h)
+        for mode in (O.YUV_420, O.YUV_444, O.YUV_400):
+            for (tmode, tval, passes, tol) in ((1, 6000.0, 8, 1.0), (1, 2500.0, 12, 0.5), (2, 36.0, 6, 1.0),
+                                               (2, 42.0, 10, 0.2), (0, 0.0, 3, 1.0)):
+                for (hf, ad, tr) in ((1, 1, 0), (0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 1)):
+                    res = []
+                    for L, free in ((prod, S.lib().SjpegFreeBuffer), (ref, ref.SjpegFreeBuffer)):
+                        out = C.POINTER(C.c_uint8)()
+                        q, v = C.c_float(-1), C.c_float(-1)
+                        n = L.ref_encode_search(rgb.ctypes.data, w, h, 3 * w, mode, 70.0, tmode, tval, passes, tol, hf,
+                                                ad, tr, C.byref(q), C.byref(v), C.byref(out))
+                        res.append((C.string_at(out, n) if n else None, q.value, v.value))
+                        if n:
+                            free(out)
+                    assert res[0][0] is not None and res[0][0] == res[1][0], (gen, mode, tmode, tval, passes, hf, ad, tr,
+                                                                              len(res[0][0] or b""), len(res[1][0] or b""))
+                    assert res[0][1:] == res[1][1:], (gen, mode, tmode, tval, res[0][1:], res[1][1:])
