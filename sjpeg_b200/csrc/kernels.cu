@@ -618,12 +618,33 @@ struct ChunkLoader {   // chunk c of a block = zig-zag positions 8c..8c+7, one 1
     return r;
   }
 };
+// Same, with the first two chunks (one 32-byte sector: where the low frequencies live) fetched
+// eagerly together with the bitmap and the predictor, so that a typical block needs a single
+// round trip to memory instead of a dependent chain.
+struct PrefetchedChunkLoader {
+  const int16_t* p;
+  uint4 c0, c1;
+  __device__ __forceinline__ Words4 operator()(int c) const {
+    const uint4 q = (c == 0) ? c0 : (c == 1) ? c1 : reinterpret_cast<const uint4*>(p)[c];
+    Words4 r;
+    r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
+    return r;
+  }
+};
 
 __device__ __forceinline__ void load_code_tables(const CodeTabs* tabs, CodeTabs* sh) {
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(tabs);
-  uint32_t* dst = reinterpret_cast<uint32_t*>(sh);
-  for (int i = threadIdx.x; i < static_cast<int>(sizeof(CodeTabs) / 4); i += blockDim.x) dst[i] = src[i];
+  // 2176 bytes = 136 x 16 bytes: one vector copy per thread
+  static_assert(sizeof(CodeTabs) % 16 == 0, "CodeTabs must be a multiple of 16 bytes");
+  const uint4* src = reinterpret_cast<const uint4*>(tabs);
+  uint4* dst = reinterpret_cast<uint4*>(sh);
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(CodeTabs) / 16); i += blockDim.x) dst[i] = src[i];
   __syncthreads();
+}
+
+// block index inside its MCU without a run-time division (mcu_blocks is 6, 3 or 1)
+__device__ __forceinline__ int block_in_mcu(size_t g, int mcu_blocks) {
+  const unsigned gg = static_cast<unsigned>(g);
+  return (mcu_blocks == 6) ? static_cast<int>(gg % 6u) : (mcu_blocks == 3) ? static_cast<int>(gg % 3u) : 0;
 }
 
 // Decoupled look-back (single-pass chained scan).  One 64-bit descriptor per tile:
@@ -709,7 +730,7 @@ struct LocalSink {
 
 __global__ void __launch_bounds__(kTileBlocks)
 entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
-  __shared__ CodeTabs sh;
+  __shared__ __align__(16) CodeTabs sh;
   __shared__ uint32_t scratch[33];
   __shared__ unsigned long long tile_prefix;
   __shared__ uint32_t local[kTileBlocks][kLocalWords + 1];   // odd stride: conflict-free
@@ -727,13 +748,14 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   int nw = 0;
   uint32_t* mine = local[threadIdx.x];
   if (valid) {
-    k = static_cast<int>(g % fs.mcu_blocks);
+    k = block_in_mcu(g, fs.mcu_blocks);
     c = (k >= fs.luma_blocks) ? 1 : 0;
     mask = nzmask[g];
-    dc = b[0];
+    const PrefetchedChunkLoader loader = {b, reinterpret_cast<const uint4*>(b)[0], reinterpret_cast<const uint4*>(b)[1]};
     pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, gb.dc_init ? gb.dc_init + 3 * frame : nullptr);
+    dc = static_cast<int16_t>(loader.c0.x & 0xffffu);
     LocalSink sink = {mine, 0, 0, 0, 0};
-    code_block(ChunkLoader{b}, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
+    code_block(loader, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
     sink.finish();
     bits = sink.total;
     nw = sink.nw;
@@ -759,16 +781,16 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   if (nw <= kLocalWords) {
     // copy the kept words to their place in the stream, shifted by the bit offset; the first and
     // the last stream word may be shared with the neighbouring blocks (OR), the others are owned
-    const unsigned long long w0 = offset >> 5, wl = (offset + bits - 1) >> 5;
     const int s = static_cast<int>(offset & 31);
+    uint32_t* dst = stream + (offset >> 5);
+    const int last = static_cast<int>((s + bits - 1) >> 5);   // index of the last stream word touched
     uint32_t prev = 0;
-    for (unsigned long long j = w0; j <= wl; ++j) {
-      const int kk = static_cast<int>(j - w0);
+    for (int kk = 0; kk <= last; ++kk) {
       const uint32_t cur = (kk < nw) ? mine[kk] : 0u;
       const uint32_t v = __funnelshift_r(cur, prev, s);     // (prev << (32-s)) | (cur >> s)
       prev = cur;
-      if (j == w0 || j == wl) { if (v) atomicOr(&stream[j], v); }
-      else stream[j] = v;
+      if (kk == 0 || kk == last) { if (v) atomicOr(&dst[kk], v); }
+      else dst[kk] = v;
     }
   } else {
     StreamOut out = {stream};
