@@ -1013,6 +1013,8 @@ static int StageF1(sjb_context* ctx, const uint8_t* pix, int width, int height, 
   uint8_t quant[2][64], min_quant[2][64];
   QuantTabs qt;
   if (!MakeQuantTabs(*plan, quant, min_quant, &qt)) return SJB_ERR_ARG;
+  // the fast kernel skips all-zero chunks: give the dump a defined background
+  CU(cudaMemsetAsync(L->coef.ptr, 0, plan->g.nb_blocks() * 64 * sizeof(int16_t), L->stream));
   LaunchF1(L, *fs, plan->g, raw, qt);
   CU(cudaGetLastError());
   return SJB_OK;

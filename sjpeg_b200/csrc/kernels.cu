@@ -92,24 +92,32 @@ struct SmemTab {        // shared-memory copy, run-time base (lets luma and chro
   }
 };
 
-template <class Tab>
+template <bool kSparse = false, class Tab>
 __device__ __forceinline__ void quantize_store_block(const int (&v)[64], const Tab& tab,
                                                      int16_t* dst, uint8_t* chunkmask) {
   constexpr int zz[64] = SJB_ZIGZAG_INIT;
   uint4* d = reinterpret_cast<uint4*>(dst);
   uint32_t mask = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    uint32_t w[4];
+  for (int s = 0; s < 4; ++s) {          // one 32-byte sector = two 16-byte chunks
+    uint32_t w[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int p = 4 * i + j;
+    for (int j = 0; j < 8; ++j) {
+      const int p = 8 * s + j;
       int iq0, c0, iq1, c1;
       tab.pair(p, iq0, c0, iq1, c1);
       w[j] = pack16(quantize_coeff(v[zz[2 * p]], iq0, c0), quantize_coeff(v[zz[2 * p + 1]], iq1, c1));
     }
-    if ((w[0] | w[1] | w[2] | w[3]) != 0) mask |= 1u << i;
-    d[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    const bool nz0 = (w[0] | w[1] | w[2] | w[3]) != 0, nz1 = (w[4] | w[5] | w[6] | w[7]) != 0;
+    if (nz0) mask |= 1u << (2 * s);
+    if (nz1) mask |= 1u << (2 * s + 1);
+    // Sector 0 carries the DC and is always stored.  An all-zero sector is never read back (the
+    // bitmap gates every load of the entropy stage), so the fast path does not write it; whole
+    // sectors are written so that L2 never has to fill a partial one from DRAM.
+    if (!kSparse || s == 0 || nz0 || nz1) {
+      d[2 * s] = make_uint4(w[0], w[1], w[2], w[3]);
+      d[2 * s + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
   }
   *chunkmask = static_cast<uint8_t>(mask);
 }
@@ -289,9 +297,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "WAIT_DONE:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+// The pixels are read exactly once: mark them evict-first in L2 so that the streaming input does
+// not push out the coefficients the entropy kernel is about to read back.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+  unsigned long long policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
 
 // one block row (8 pixels = 24 or 32 bytes) held in 32-bit words; one PRMT per byte:
@@ -363,7 +375,7 @@ __device__ __forceinline__ void finish_block(int (&v)[64], uint32_t tab_addr, in
                                              uint8_t* nzmask, size_t g) {
   fdct64(v);
   if (kRaw) store_block_natural(v, coef + g * 64);
-  else quantize_store_block(v, SmemTab{tab_addr}, coef + g * 64, nzmask + g);
+  else quantize_store_block<true>(v, SmemTab{tab_addr}, coef + g * 64, nzmask + g);
 }
 
 template <int kMode, bool kRaw, int kFmt>
