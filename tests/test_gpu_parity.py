@@ -396,3 +396,34 @@ def test_target_size_and_psnr_search_equal_reference(gpu_ctx):
                     assert res[0][0] is not None and res[0][0] == res[1][0], (gen, mode, tmode, tval, passes, hf, ad, tr,
                                                                               len(res[0][0] or b""), len(res[1][0] or b""))
                     assert res[0][1:] == res[1][1:], (gen, mode, tmode, tval, res[0][1:], res[1][1:])
+
+
+def test_concurrent_host_threads(gpu_ctx):
+    """The library is re-entrant like the reference (unit_test.cc:114-131): 8 host threads call the
+    drop-in SjpegEncode() at the same time (one lazily created GPU context per thread)."""
+    import threading
+    import sjpeg_b200 as S
+    cases = [(512, 512, 0, O.YUV_420), (203, 117, 4, O.YUV_444), (640, 360, 7, O.YUV_420), (320, 200, 1, O.YUV_400)]
+    want = {}
+    imgs = {}
+    for (w, h, m, mode) in cases:
+        imgs[(w, h)] = O.make_rgb("A", w, h)
+        want[(w, h, m, mode)] = O.oracle_encode(imgs[(w, h)], w, h, 3 * w, 75.0, m, mode)
+    errors = []
+
+    def work(t):
+        try:
+            for rep in range(6):
+                w, h, m, mode = cases[(t + rep) % len(cases)]
+                got = S.sjpeg_encode(imgs[(w, h)], w, h, 3 * w, 75, m, mode)
+                if got != want[(w, h, m, mode)]:
+                    errors.append((t, rep, w, h, m, mode))
+        except Exception as e:
+            errors.append((t, repr(e)))
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errors, errors
