@@ -46,16 +46,35 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock and throttle reasons sampled every 20 ms during the timed regions (NVML in
+    process; nvidia-smi every 200 ms as a fallback)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
         self.reasons = set()
+        self.sm_max = None
         self.stop = threading.Event()
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        self.sm_max = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        names = {N.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 N.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 N.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 N.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop.is_set():
+            self.samples.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+            r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+            self.stop.wait(0.02)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -65,7 +84,8 @@ class ClockSampler(threading.Thread):
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True,
                                      timeout=5).stdout.strip().split(",")
-                self.samples.append((float(out[0]), float(out[1])))
+                self.samples.append(float(out[0]))
+                self.sm_max = float(out[1])
                 for n, v in zip(names, out[2:]):
                     if v.strip().lower() == "active":
                         self.reasons.add(n)
@@ -73,11 +93,17 @@ class ClockSampler(threading.Thread):
                 pass
             self.stop.wait(0.2)
 
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons)}
-        sm = sorted(s[0] for s in self.samples)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons),
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
                 "samples": len(sm)}
 
 
