@@ -46,6 +46,7 @@ _SIGNATURES = {
     "sjb_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong,
                              C.POINTER(Params), C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_size_t)]),
     "sjb_fetch_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
+    "sjb_context_set_search": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sjb_encode_planar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p,
                                     C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Params), C.c_void_p,
                                     C.c_int, C.c_size_t, C.POINTER(C.c_size_t)]),
