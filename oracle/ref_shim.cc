@@ -87,3 +87,19 @@ extern "C" size_t ref_encode_search(const uint8_t* rgb, int w, int h, int stride
   if (final_value) *final_value = hook.value;
   return n;
 }
+
+// sharp RGB->YUV420 pre-pass and the riskiness score table: internal symbols of the reference
+// (declared in /root/reference/src/sjpegi.h:89,118), reached here so that tests can compare planes
+// and feed the reference's own generated table (score_7.cc) to the code under test.
+namespace sjpeg {
+extern const uint8_t kSharpnessScore[];
+void ApplySharpYUVConversion(const uint8_t* const rgb, int W, int H, int stride, uint8_t* y_plane,
+                             uint8_t* u_plane, uint8_t* v_plane);
+}
+extern "C" void ref_sharp_yuv(const uint8_t* rgb, int w, int h, int stride, uint8_t* y, uint8_t* u, uint8_t* v) {
+  sjpeg::ApplySharpYUVConversion(rgb, w, h, stride, y, u, v);
+}
+extern "C" const uint8_t* ref_score_table(size_t* size) {
+  if (size) *size = 343u * 343u;
+  return sjpeg::kSharpnessScore;
+}

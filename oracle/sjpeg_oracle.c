@@ -1042,6 +1042,20 @@ size_t sjo_encode(const uint8_t* pix, int w, int h, int stride, const sjo_params
   if (pix == NULL || out == NULL || p == NULL) return 0;
   const int pstep = (p->pix_fmt == SJO_RGB) ? 3 : 4;
   if (w <= 0 || h <= 0 || abs(stride) < pstep * w) return 0;     /* api.cc:35-36 */
+  if (p->yuv_mode == SJO_YUV_SHARP) {                            /* EncoderSharp420, encoders.cc:512-541 */
+    if (p->pix_fmt != SJO_RGB) return 0;
+    const int cw = (w + 1) / 2, ch = (h + 1) / 2;
+    uint8_t* yuv = (uint8_t*)malloc((size_t)w * h + 2 * (size_t)cw * ch);
+    if (yuv == NULL) return 0;
+    sjo_params q = *p;
+    q.yuv_mode = SJO_YUV_420;
+    size_t n = 0;
+    if (sjo_sharp_yuv(pix, w, h, stride, yuv, yuv + (size_t)w * h, yuv + (size_t)w * h + (size_t)cw * ch)) {
+      n = sjo_encode_planar(yuv, w, yuv + (size_t)w * h, cw, yuv + (size_t)w * h + (size_t)cw * ch, cw, 1, w, h, &q, out);
+    }
+    free(yuv);
+    return n;
+  }
   return encode_impl(pix, NULL, w, h, stride, p, out);
 }
 

@@ -32,7 +32,7 @@ enum { SJO_YUV_AUTO = 0, SJO_YUV_420 = 1, SJO_YUV_SHARP = 2, SJO_YUV_444 = 3, SJ
 enum { SJO_RGB = 0, SJO_BGRA = 1, SJO_RGBA = 2 };
 
 typedef struct {
-  int yuv_mode;            /* 420 / 444 / 400 only */
+  int yuv_mode;            /* 420 / 444 / 400, or SHARP (RGB input only) */
   int method;              /* 0..8, clamped like enc.cc:121-129 */
   int pix_fmt;             /* SJO_RGB / SJO_BGRA / SJO_RGBA */
   uint8_t quant[2][64];    /* natural order, luma then chroma */
@@ -103,6 +103,15 @@ size_t sjo_sjpeg_encode(const uint8_t* rgb, int w, int h, int stride, float qual
 size_t sjo_encode_planar(const uint8_t* y, int y_stride, const uint8_t* u, int u_stride, const uint8_t* v,
                          int v_stride, int uv_step, int w, int h, const sjo_params* p, uint8_t** out);
 void sjo_free(uint8_t* p);
+
+/* "Sharp" RGB -> YUV 4:2:0 conversion (yuv_convert.cc:671-695, oracle/sjpeg_oracle_sharp.c): y is
+ * W x H, u and v are ((W+1)/2) x ((H+1)/2), tightly packed.  sjo_encode()/sjo_sjpeg_encode() with
+ * yuv_mode SJO_YUV_SHARP run it and then the planar 4:2:0 encoder, as EncoderSharp420 does
+ * (encoders.cc:512-541).  Returns 0 on allocation failure. */
+int sjo_sharp_yuv(const uint8_t* rgb, int W, int H, int stride, uint8_t* y, uint8_t* u, uint8_t* v);
+/* SjpegRiskiness (jpeg_tools.cc:177-236).  table = the reference's 343 x 343 score table
+ * (score_7.cc; generated data, not restated -- tests pass the compiled reference's copy). */
+int sjo_riskiness(const uint8_t* rgb, int width, int height, int stride, const uint8_t* table, float* risk);
 
 /* Row stripe coded on its own (method 0): raw entropy-coded bits, DC predictors in/out.
  * Used as the CPU stand-in stage by the multi-rank (gloo) tests of the stripe exchange. */

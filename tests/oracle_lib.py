@@ -10,7 +10,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
-YUV_420, YUV_444, YUV_400 = 1, 3, 4
+YUV_AUTO, YUV_420, YUV_SHARP, YUV_444, YUV_400 = 0, 1, 2, 3, 4
 
 _u8p = C.POINTER(C.c_uint8)
 
@@ -61,6 +61,10 @@ def oracle():
         L.sjo_encode_planar.restype = C.c_size_t
         L.sjo_encode_planar.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.POINTER(SjoParams), C.POINTER(_u8p)]
+        L.sjo_sharp_yuv.restype = C.c_int
+        L.sjo_sharp_yuv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sjo_riskiness.restype = C.c_int
+        L.sjo_riskiness.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_float)]
         _oracle = L
     return _oracle
 
@@ -86,6 +90,12 @@ def ref():
         L.ref_encode_param.restype = C.c_size_t
         L.ref_encode_param.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                        C.c_float] + [C.c_int] * 6 + [C.POINTER(_u8p)]
+        L.ref_sharp_yuv.restype = None
+        L.ref_sharp_yuv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_score_table.restype = C.c_void_p
+        L.ref_score_table.argtypes = [C.POINTER(C.c_size_t)]
+        L.SjpegRiskiness.restype = C.c_int
+        L.SjpegRiskiness.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
         _ref = L
     return _ref
 
@@ -195,3 +205,43 @@ def ref_encode_planar(kind, planes, w, h, quality, huffman, adaptive, trellis):
     data = C.string_at(out, n)
     ref().SjpegFreeBuffer(out)
     return data
+
+
+# ---- sharp YUV pre-pass and riskiness ----------------------------------------------------------
+def _sharp(fn, rgb, w, h, stride, base=None):
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    y = np.zeros((h, w), np.uint8)
+    u = np.zeros((ch, cw), np.uint8)
+    v = np.zeros((ch, cw), np.uint8)
+    fn(base if base is not None else rgb.ctypes.data, w, h, stride, y.ctypes.data, u.ctypes.data, v.ctypes.data)
+    return y, u, v
+
+
+def oracle_sharp_yuv(rgb, w, h, stride, base=None):
+    return _sharp(oracle().sjo_sharp_yuv, rgb, w, h, stride, base)
+
+
+def ref_sharp_yuv(rgb, w, h, stride, base=None):
+    return _sharp(ref().ref_sharp_yuv, rgb, w, h, stride, base)
+
+
+def score_table():
+    """The reference's generated 343 x 343 riskiness table, read out of the compiled reference
+    (None when oracle/_ref did not travel)."""
+    if ref() is None:
+        return None
+    n = C.c_size_t()
+    p = ref().ref_score_table(C.byref(n))
+    return np.frombuffer(C.string_at(p, n.value), np.uint8).copy()
+
+
+def oracle_riskiness(rgb, w, h, stride, table):
+    risk = C.c_float()
+    mode = oracle().sjo_riskiness(rgb.ctypes.data, w, h, stride, table.ctypes.data, C.byref(risk))
+    return mode, risk.value
+
+
+def ref_riskiness(rgb, w, h, stride):
+    risk = C.c_float()
+    mode = ref().SjpegRiskiness(rgb.ctypes.data, w, h, stride, C.byref(risk))
+    return mode, risk.value
