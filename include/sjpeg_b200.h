@@ -31,8 +31,12 @@ enum {
   SJB_ERR_CAPACITY = -4   /* caller's output buffer too small (out_size still reports the need) */
 };
 
-/* values of SjpegYUVMode, /root/reference/src/sjpeg.h:54-60 (AUTO and SHARP are not on this path) */
-enum { SJB_YUV_420 = 1, SJB_YUV_444 = 3, SJB_YUV_400 = 4 };
+/* values of SjpegYUVMode, /root/reference/src/sjpeg.h:54-60.  SHARP and AUTO are accepted by
+ * sjb_encode() for packed RGB input only (as in the reference, api.cc:208,235): SHARP runs the
+ * iterative sharp RGB->YUV 4:2:0 conversion on the device and then the planar encoder
+ * (EncoderSharp420, encoders.cc:512-541); AUTO runs the riskiness analyser first and needs the
+ * score table (sjb_set_score_table). */
+enum { SJB_YUV_AUTO = 0, SJB_YUV_420 = 1, SJB_YUV_SHARP = 2, SJB_YUV_444 = 3, SJB_YUV_400 = 4 };
 /* PixelFormat of /root/reference/src/sjpegi.h (kRGBInput, kBGRAInput, kRGBAInput) */
 enum { SJB_PIX_RGB = 0, SJB_PIX_BGRA = 1, SJB_PIX_RGBA = 2 };
 
@@ -93,6 +97,29 @@ int sjb_encode_planar(sjb_context* ctx, const uint8_t* y, long long y_stride, co
                       long long u_stride, const uint8_t* v, long long v_stride, int uv_step, int on_device,
                       int width, int height, const sjb_params* params, uint8_t* out, int out_on_device,
                       size_t out_capacity, size_t* out_size);
+
+/*
+ * Sharp RGB -> YUV 4:2:0 conversion on its own = sjpeg::ApplySharpYUVConversion
+ * (/root/reference/src/yuv_convert.cc:671-695, sjpegi.h:118): packed RGB in, three tightly packed
+ * planes out (y: width x height; u, v: (width+1)/2 x (height+1)/2).  Stage-level entry point of
+ * the SJB_YUV_SHARP path (parity tests, callers that want the planes).
+ */
+int sjb_sharp_yuv(sjb_context* ctx, const uint8_t* rgb, int rgb_on_device, int width, int height,
+                  long long stride, uint8_t* y, uint8_t* u, uint8_t* v, int out_on_device);
+
+/*
+ * Riskiness analyser = SjpegRiskiness (/root/reference/src/sjpeg.h:139-150, jpeg_tools.cc:177-236):
+ * recommends 4:2:0 / sharp 4:2:0 / 4:4:4 / 4:0:0 for a packed RGB picture and reports the 0..100
+ * risk score.  The analyser looks pixel triples up in the reference's GENERATED 343 x 343 score
+ * table (/root/reference/src/score_7.cc, sjpeg::kSharpnessScore); that table is a data asset of
+ * the reference and is not reproduced here -- the host binding passes it once per process
+ * (INTEGRATION.md), or SJPEG_B200_SCORE_TABLE names a file holding its 117649 bytes.
+ * Without a table sjb_riskiness and SJB_YUV_AUTO return SJB_ERR_ARG.
+ */
+int sjb_set_score_table(const uint8_t* table, size_t size /* 343*343 */);   /* NULL clears */
+int sjb_has_score_table(void);
+int sjb_riskiness(sjb_context* ctx, const uint8_t* rgb, int rgb_on_device, int width, int height,
+                  long long stride, int* yuv_mode, float* risk);
 
 /*
  * Multi-pass search for a target size or PSNR = Encoder::LoopScan (/root/reference/src/dichotomy.cc:113-205,

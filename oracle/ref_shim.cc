@@ -88,6 +88,7 @@ extern "C" size_t ref_encode_search(const uint8_t* rgb, int w, int h, int stride
   return n;
 }
 
+#ifdef SJPEG_REF_INTERNALS   // only when linked with the reference's own objects (oracle/Makefile)
 // sharp RGB->YUV420 pre-pass and the riskiness score table: internal symbols of the reference
 // (declared in /root/reference/src/sjpegi.h:89,118), reached here so that tests can compare planes
 // and feed the reference's own generated table (score_7.cc) to the code under test.
@@ -103,3 +104,4 @@ extern "C" const uint8_t* ref_score_table(size_t* size) {
   if (size) *size = 343u * 343u;
   return sjpeg::kSharpnessScore;
 }
+#endif  // SJPEG_REF_INTERNALS

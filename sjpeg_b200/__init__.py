@@ -47,6 +47,12 @@ _SIGNATURES = {
                              C.POINTER(Params), C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_size_t)]),
     "sjb_fetch_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
     "sjb_context_set_search": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sjb_sharp_yuv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_int]),
+    "sjb_set_score_table": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "sjb_has_score_table": (C.c_int, []),
+    "sjb_riskiness": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong,
+                                C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     "sjb_encode_planar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p,
                                     C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Params), C.c_void_p,
                                     C.c_int, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -221,6 +227,26 @@ class Context:
         _check(self._ctx, rc, "sjb_stage_symbol_stats")
         return ac, dc
 
+    def sharp_yuv(self, rgb, width, height, stride, base=None):
+        """sjpeg::ApplySharpYUVConversion on the device: returns the (y, u, v) planes."""
+        cw, ch = (width + 1) // 2, (height + 1) // 2
+        y = np.zeros((height, width), np.uint8)
+        u = np.zeros((ch, cw), np.uint8)
+        v = np.zeros((ch, cw), np.uint8)
+        ptr = base if base is not None else rgb.ctypes.data
+        rc = lib().sjb_sharp_yuv(self._ctx, ptr, 0, width, height, stride, y.ctypes.data, u.ctypes.data,
+                                 v.ctypes.data, 0)
+        _check(self._ctx, rc, "sjb_sharp_yuv")
+        return y, u, v
+
+    def riskiness(self, rgb, width, height, stride, base=None):
+        """SjpegRiskiness on the device: (recommended yuv mode, risk).  Needs set_score_table()."""
+        mode, risk = C.c_int(0), C.c_float(0)
+        ptr = base if base is not None else rgb.ctypes.data
+        rc = lib().sjb_riskiness(self._ctx, ptr, 0, width, height, stride, C.byref(mode), C.byref(risk))
+        _check(self._ctx, rc, "sjb_riskiness")
+        return mode.value, risk.value
+
     def last_timings(self):
         ms = (C.c_float * 3)()
         lib().sjb_last_timings(self._ctx, C.byref(ms))
@@ -245,6 +271,18 @@ class Context:
                                 C.byref(fpl))
         _check(self._ctx, rc, "sjb_bench_f1")
         return ms.value, fpl.value
+
+
+def set_score_table(table):
+    """Hands the reference's generated 343 x 343 riskiness table (sjpeg::kSharpnessScore) to the
+    library, process-wide; None clears it."""
+    if table is None:
+        return lib().sjb_set_score_table(None, 0)
+    t = np.ascontiguousarray(table, dtype=np.uint8)
+    rc = lib().sjb_set_score_table(t.ctypes.data, t.size)
+    if rc != OK:
+        raise SjpegB200Error("sjb_set_score_table: rc=%d" % rc)
+    return rc
 
 
 def sjpeg_encode(rgb, width, height, stride, quality, method, yuv_mode, base=None):

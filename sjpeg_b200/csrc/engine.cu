@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -21,6 +22,7 @@
 #include "../../include/sjpeg_b200.h"
 #include "host_codec.h"
 #include "kernels.cuh"
+#include "sharp.cuh"
 
 using namespace sjb;
 
@@ -110,6 +112,10 @@ struct sjb_context {
   Lane lanes[kMaxLanes];
   std::string err;
   sjb_search* search = nullptr;   // armed by sjb_context_set_search for the next single encode
+  // whole-picture passes in front of the block pipeline (sharp.cu)
+  DeviceBuffer sharp_scratch, sharp_planes, sharp_tabs, risk_table, risk_sums;
+  unsigned long long* risk_host = nullptr;   // pinned, 3 sums
+  int risk_table_version = 0;                // version of the process-wide table held in risk_table
 };
 
 namespace {
@@ -699,7 +705,6 @@ int EncodeSingle(sjb_context* ctx, const uint8_t* pix, int pix_on_device, long l
     RC(ReservePix(ctx, L, plan, stride, 1));
     RC(UploadPicture(ctx, L, pix, plan, stride, 0, &fs.pix[0], &fs.stride));
   }
-  L->launches = 0;
   sjb_search* search = ctx->search;
   ctx->search = nullptr;
   const int rc = search ? EncodeSearch(ctx, L, fs, plan, search) : EncodeGroup(ctx, L, fs, plan, timed);
@@ -764,6 +769,10 @@ void sjb_context_destroy(sjb_context* ctx) {
   if (ctx == nullptr) return;
   cudaSetDevice(ctx->device);
   for (auto& L : ctx->lanes) DestroyLane(&L);
+  for (DeviceBuffer* b : {&ctx->sharp_scratch, &ctx->sharp_planes, &ctx->sharp_tabs, &ctx->risk_table, &ctx->risk_sums}) {
+    b->Release();
+  }
+  if (ctx->risk_host) cudaFreeHost(ctx->risk_host);
   delete ctx;
 }
 
@@ -802,6 +811,12 @@ void sjb_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 
+namespace {
+int EncodeAutoOrSharp(sjb_context* ctx, const uint8_t* pix, int pix_on_device, int width, int height,
+                      long long stride, const sjb_params* params);
+int FinishSingle(sjb_context* ctx, uint8_t* out, int out_on_device, size_t out_capacity, size_t* out_size);
+}  // namespace
+
 int sjb_encode(sjb_context* ctx, const uint8_t* pix, int pix_on_device, int width, int height,
                long long stride, const sjb_params* params, uint8_t* out, int out_on_device,
                size_t out_capacity, size_t* out_size) {
@@ -809,21 +824,16 @@ int sjb_encode(sjb_context* ctx, const uint8_t* pix, int pix_on_device, int widt
   *out_size = 0;
   ctx->lanes[0].last_size = 0;
   ctx->err.clear();
-  Plan plan;
-  RC(MakePlan(width, height, stride, params, &plan));
-  CU(cudaSetDevice(ctx->device));
-  Lane* L = &ctx->lanes[0];
-  RC(EncodeSingle(ctx, pix, pix_on_device, stride, plan, /*timed=*/true));
-  CU(cudaStreamSynchronize(L->stream));
-  FinishTimings(ctx, L);
-  const size_t size = static_cast<size_t>(L->host->info[0].out_size);
-  *out_size = size;
-  L->last_size = size;
-  if (out == nullptr || size > out_capacity) return SJB_ERR_CAPACITY;
-  CU(cudaMemcpyAsync(out, L->out.ptr, size, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
-                     L->stream));
-  CU(cudaStreamSynchronize(L->stream));
-  return SJB_OK;
+  if (params != nullptr && (params->yuv_mode == SJB_YUV_AUTO || params->yuv_mode == SJB_YUV_SHARP)) {
+    RC(EncodeAutoOrSharp(ctx, pix, pix_on_device, width, height, stride, params));
+  } else {
+    Plan plan;
+    RC(MakePlan(width, height, stride, params, &plan));
+    CU(cudaSetDevice(ctx->device));
+    ctx->lanes[0].launches = 0;
+    RC(EncodeSingle(ctx, pix, pix_on_device, stride, plan, /*timed=*/true));
+  }
+  return FinishSingle(ctx, out, out_on_device, out_capacity, out_size);
 }
 
 int sjb_fetch_output(sjb_context* ctx, uint8_t* out, int out_on_device, size_t out_capacity) {
@@ -909,14 +919,14 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
   return first_err;
 }
 
-int sjb_encode_planar(sjb_context* ctx, const uint8_t* y, long long y_stride, const uint8_t* u,
-                      long long u_stride, const uint8_t* v, long long v_stride, int uv_step, int on_device,
-                      int width, int height, const sjb_params* params, uint8_t* out, int out_on_device,
-                      size_t out_capacity, size_t* out_size) {
-  if (ctx == nullptr || y == nullptr || out_size == nullptr || params == nullptr) return SJB_ERR_ARG;
-  *out_size = 0;
-  ctx->lanes[0].last_size = 0;
-  ctx->err.clear();
+}  // extern "C"
+
+namespace {
+
+// planar input up to the end of the kernel sequence (no wait, nothing copied out)
+int EncodePlanarOnLane(sjb_context* ctx, const uint8_t* y, long long y_stride, const uint8_t* u, long long u_stride,
+                       const uint8_t* v, long long v_stride, int uv_step, int on_device, int width, int height,
+                       const sjb_params* params) {
   const int mode = params->yuv_mode;
   if (mode != SJB_YUV_420 && mode != SJB_YUV_444 && mode != SJB_YUV_400) return SJB_ERR_ARG;
   if (width <= 0 || height <= 0) return SJB_ERR_ARG;
@@ -970,14 +980,16 @@ int sjb_encode_planar(sjb_context* ctx, const uint8_t* y, long long y_stride, co
       }
     }
   }
-  L->launches = 0;
   sjb_search* search = ctx->search;
   ctx->search = nullptr;
   const int rc = search ? EncodeSearch(ctx, L, fs, plan, search) : EncodeGroup(ctx, L, fs, plan, /*timed=*/true);
-  if (rc != SJB_OK) {
-    L->words_dirty = true;
-    return rc;
-  }
+  if (rc != SJB_OK) L->words_dirty = true;
+  return rc;
+}
+
+// waits for lane 0, reports the size and copies the JPEG out (shared tail of the single-picture calls)
+int FinishSingle(sjb_context* ctx, uint8_t* out, int out_on_device, size_t out_capacity, size_t* out_size) {
+  Lane* L = &ctx->lanes[0];
   CU(cudaStreamSynchronize(L->stream));
   FinishTimings(ctx, L);
   const size_t size = static_cast<size_t>(L->host->info[0].out_size);
@@ -986,6 +998,210 @@ int sjb_encode_planar(sjb_context* ctx, const uint8_t* y, long long y_stride, co
   if (out == nullptr || size > out_capacity) return SJB_ERR_CAPACITY;
   CU(cudaMemcpyAsync(out, L->out.ptr, size, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                      L->stream));
+  CU(cudaStreamSynchronize(L->stream));
+  return SJB_OK;
+}
+
+// ---- whole-picture passes in front of the block pipeline (sharp.cu) -----------------------------
+std::mutex g_table_mutex;
+std::vector<uint8_t> g_score_table;      // process-wide copy of the caller's 343 x 343 table
+int g_score_table_version = 0;           // bumped on every change; 0 = never set
+bool g_score_table_env_checked = false;
+
+// SJPEG_B200_SCORE_TABLE=<file with the 117649 table bytes> is honoured once, if no table was set
+void LoadScoreTableFromEnvLocked() {
+  if (g_score_table_env_checked) return;
+  g_score_table_env_checked = true;
+  const char* path = getenv("SJPEG_B200_SCORE_TABLE");
+  if (path == nullptr || !g_score_table.empty()) return;
+  FILE* f = fopen(path, "rb");
+  if (f == nullptr) return;
+  std::vector<uint8_t> t(kRiskTableBytes);
+  if (fread(t.data(), 1, t.size(), f) == t.size()) {
+    g_score_table.swap(t);
+    ++g_score_table_version;
+  }
+  fclose(f);
+}
+
+int EnsureSharpTabs(sjb_context* ctx, const uint32_t** g2l, const uint32_t** l2g) {
+  if (ctx->sharp_tabs.ptr == nullptr) {
+    uint32_t host[1024 + 34];
+    MakeSharpGammaTables(host, host + 1024);
+    CU(ctx->sharp_tabs.Reserve(sizeof(host)));
+    CU(cudaMemcpy(ctx->sharp_tabs.ptr, host, sizeof(host), cudaMemcpyHostToDevice));
+  }
+  *g2l = ctx->sharp_tabs.as<uint32_t>();
+  *l2g = *g2l + 1024;
+  return SJB_OK;
+}
+
+int EnsureScoreTable(sjb_context* ctx) {
+  std::lock_guard<std::mutex> lock(g_table_mutex);
+  LoadScoreTableFromEnvLocked();
+  if (g_score_table.empty()) {
+    ctx->err = "no riskiness score table: call sjb_set_score_table() or set SJPEG_B200_SCORE_TABLE";
+    return SJB_ERR_ARG;
+  }
+  if (ctx->risk_table_version != g_score_table_version) {
+    CU(ctx->risk_table.Reserve(kRiskTableBytes));
+    CU(cudaMemcpy(ctx->risk_table.ptr, g_score_table.data(), kRiskTableBytes, cudaMemcpyHostToDevice));
+    ctx->risk_table_version = g_score_table_version;
+  }
+  if (ctx->risk_host == nullptr) {
+    CU(cudaMallocHost(reinterpret_cast<void**>(&ctx->risk_host), 3 * sizeof(unsigned long long)));
+    CU(ctx->risk_sums.Reserve(256));
+  }
+  return SJB_OK;
+}
+
+// device address of a packed RGB picture: as given, or uploaded into lane 0's pixel buffer
+int ResidentRgb(sjb_context* ctx, const uint8_t* rgb, int on_device, int width, int height, long long stride,
+                const uint8_t** d_rgb, long long* d_stride) {
+  if (rgb == nullptr || width <= 0 || height <= 0) return SJB_ERR_ARG;
+  const long long astride = stride < 0 ? -stride : stride;
+  if (astride < 3LL * width) return SJB_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  Lane* L = &ctx->lanes[0];
+  *d_rgb = rgb;
+  *d_stride = stride;
+  if (!on_device) {
+    sjb_params p;
+    sjb_params_default(&p, 75.f, 0, SJB_YUV_420);
+    Plan plan;
+    RC(MakePlan(width, height, stride, &p, &plan));
+    RC(ReservePix(ctx, L, plan, stride, 1));
+    RC(UploadPicture(ctx, L, rgb, plan, stride, 0, d_rgb, d_stride));
+  }
+  return SJB_OK;
+}
+
+// riskiness of a device-resident picture (jpeg_tools.cc:177-236); waits for the three sums
+int RiskinessOnDevice(sjb_context* ctx, const uint8_t* d_rgb, long long d_stride, int width, int height, int* mode,
+                      float* risk) {
+  RC(EnsureScoreTable(ctx));
+  Lane* L = &ctx->lanes[0];
+  unsigned long long* d_sums = ctx->risk_sums.as<unsigned long long>();
+  CU(LaunchRiskiness(d_rgb, d_stride, width, height, ctx->risk_table.as<uint8_t>(), d_sums, ctx->sm_count, L->stream));
+  L->launches += 1;
+  CU(cudaMemcpyAsync(ctx->risk_host, d_sums, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, L->stream));
+  CU(cudaStreamSynchronize(L->stream));
+  *mode = RiskinessDecision(ctx->risk_host[0], ctx->risk_host[1], ctx->risk_host[2], width, height, risk);
+  return SJB_OK;
+}
+
+// sharp conversion of a device-resident picture into the context's plane buffer (stream-ordered)
+int SharpOnDevice(sjb_context* ctx, const uint8_t* d_rgb, long long d_stride, int width, int height, uint8_t** y,
+                  uint8_t** u, uint8_t** v) {
+  const uint32_t *g2l, *l2g;
+  RC(EnsureSharpTabs(ctx, &g2l, &l2g));
+  Lane* L = &ctx->lanes[0];
+  const size_t cw = (static_cast<size_t>(width) + 1) / 2, ch = (static_cast<size_t>(height) + 1) / 2;
+  const size_t ybytes = (static_cast<size_t>(width) * height + 255) & ~size_t(255);
+  const size_t cbytes = (cw * ch + 255) & ~size_t(255);
+  CU(ctx->sharp_planes.Reserve(ybytes + 2 * cbytes));
+  SharpLayout lay;
+  if (width > 4 && height > 4) CU(ctx->sharp_scratch.Reserve(SharpScratchBytes(width, height, &lay)));
+  *y = ctx->sharp_planes.as<uint8_t>();
+  *u = *y + ybytes;
+  *v = *u + cbytes;
+  int launches = 0;
+  CU(LaunchSharpYuv(d_rgb, d_stride, width, height, ctx->sharp_scratch.as<uint8_t>(), g2l, l2g, *y, *u, *v, L->stream,
+                    &launches));
+  L->launches += launches;
+  return SJB_OK;
+}
+
+// SJB_YUV_AUTO / SJB_YUV_SHARP for packed RGB (EncoderFactory, encoders.cc:546-568): the pixels are
+// uploaded once; AUTO asks the analyser, SHARP converts on the device and feeds the planar encoder.
+int EncodeAutoOrSharp(sjb_context* ctx, const uint8_t* pix, int pix_on_device, int width, int height,
+                      long long stride, const sjb_params* params) {
+  if (params->pix_fmt != SJB_PIX_RGB) return SJB_ERR_ARG;   // api.cc:208,235: callers convert to RGB first
+  if (width > 65535 || height > 65535) return SJB_ERR_ARG;
+  Lane* L = &ctx->lanes[0];
+  const uint8_t* d_rgb;
+  long long d_stride;
+  RC(ResidentRgb(ctx, pix, pix_on_device, width, height, stride, &d_rgb, &d_stride));
+  L->launches = 0;
+  sjb_params p = *params;
+  if (p.yuv_mode == SJB_YUV_AUTO) {
+    float risk;
+    RC(RiskinessOnDevice(ctx, d_rgb, d_stride, width, height, &p.yuv_mode, &risk));
+  }
+  if (p.yuv_mode != SJB_YUV_SHARP) {
+    Plan plan;
+    RC(MakePlan(width, height, d_stride, &p, &plan));
+    return EncodeSingle(ctx, d_rgb, /*pix_on_device=*/1, d_stride, plan, /*timed=*/true);
+  }
+  uint8_t *y, *u, *v;
+  RC(SharpOnDevice(ctx, d_rgb, d_stride, width, height, &y, &u, &v));
+  p.yuv_mode = SJB_YUV_420;
+  const long long cw = (width + 1) / 2;
+  return EncodePlanarOnLane(ctx, y, width, u, cw, v, cw, 1, /*on_device=*/1, width, height, &p);
+}
+
+}  // namespace
+
+extern "C" {
+
+int sjb_encode_planar(sjb_context* ctx, const uint8_t* y, long long y_stride, const uint8_t* u,
+                      long long u_stride, const uint8_t* v, long long v_stride, int uv_step, int on_device,
+                      int width, int height, const sjb_params* params, uint8_t* out, int out_on_device,
+                      size_t out_capacity, size_t* out_size) {
+  if (ctx == nullptr || y == nullptr || out_size == nullptr || params == nullptr) return SJB_ERR_ARG;
+  *out_size = 0;
+  ctx->lanes[0].last_size = 0;
+  ctx->err.clear();
+  ctx->lanes[0].launches = 0;
+  RC(EncodePlanarOnLane(ctx, y, y_stride, u, u_stride, v, v_stride, uv_step, on_device, width, height, params));
+  return FinishSingle(ctx, out, out_on_device, out_capacity, out_size);
+}
+
+int sjb_set_score_table(const uint8_t* table, size_t size) {
+  std::lock_guard<std::mutex> lock(g_table_mutex);
+  if (table == nullptr) {
+    g_score_table.clear();
+    ++g_score_table_version;
+    g_score_table_env_checked = true;   // an explicit clear is not undone by the environment
+    return SJB_OK;
+  }
+  if (size != static_cast<size_t>(kRiskTableBytes)) return SJB_ERR_ARG;
+  g_score_table.assign(table, table + size);
+  ++g_score_table_version;
+  return SJB_OK;
+}
+
+int sjb_has_score_table(void) {
+  std::lock_guard<std::mutex> lock(g_table_mutex);
+  LoadScoreTableFromEnvLocked();
+  return g_score_table.empty() ? 0 : 1;
+}
+
+int sjb_riskiness(sjb_context* ctx, const uint8_t* rgb, int rgb_on_device, int width, int height, long long stride,
+                  int* yuv_mode, float* risk) {
+  if (ctx == nullptr || yuv_mode == nullptr) return SJB_ERR_ARG;
+  ctx->err.clear();
+  const uint8_t* d_rgb;
+  long long d_stride;
+  RC(ResidentRgb(ctx, rgb, rgb_on_device, width, height, stride, &d_rgb, &d_stride));
+  return RiskinessOnDevice(ctx, d_rgb, d_stride, width, height, yuv_mode, risk);
+}
+
+int sjb_sharp_yuv(sjb_context* ctx, const uint8_t* rgb, int rgb_on_device, int width, int height, long long stride,
+                  uint8_t* y, uint8_t* u, uint8_t* v, int out_on_device) {
+  if (ctx == nullptr || y == nullptr || u == nullptr || v == nullptr) return SJB_ERR_ARG;
+  ctx->err.clear();
+  const uint8_t* d_rgb;
+  long long d_stride;
+  RC(ResidentRgb(ctx, rgb, rgb_on_device, width, height, stride, &d_rgb, &d_stride));
+  uint8_t *dy, *du, *dv;
+  RC(SharpOnDevice(ctx, d_rgb, d_stride, width, height, &dy, &du, &dv));
+  Lane* L = &ctx->lanes[0];
+  const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  const size_t cw = (static_cast<size_t>(width) + 1) / 2, ch = (static_cast<size_t>(height) + 1) / 2;
+  CU(cudaMemcpyAsync(y, dy, static_cast<size_t>(width) * height, kind, L->stream));
+  CU(cudaMemcpyAsync(u, du, cw * ch, kind, L->stream));
+  CU(cudaMemcpyAsync(v, dv, cw * ch, kind, L->stream));
   CU(cudaStreamSynchronize(L->stream));
   return SJB_OK;
 }

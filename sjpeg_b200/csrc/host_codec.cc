@@ -348,4 +348,45 @@ void AppendHeaders(const FrameGeometry& g, const uint8_t quant[2][64], const Huf
   put(0); put(63); put(0);
 }
 
+// ---------------------------------------------------------------------------------------------
+// sharp-YUV gamma tables and the riskiness decision
+// ---------------------------------------------------------------------------------------------
+void MakeSharpGammaTables(uint32_t g2l[1024], uint32_t l2g[34]) {   // yuv_convert.cc:102-151
+  const double a = 0.099, thresh = 0.018, gamma = 1. / 0.45;
+  const int max_y = 1023, lin_bits = 14, nodes = 32;
+  for (int v = 0; v <= max_y; ++v) {
+    const double g = (1. / max_y) * v;
+    double value;
+    if (g <= thresh * 4.5) {
+      value = g / 4.5;
+    } else {
+      const double a_rec = 1. / (1. + a);
+      value = pow(a_rec * (g + a), gamma);
+    }
+    g2l[v] = static_cast<uint32_t>(value * static_cast<double>(1 << lin_bits) + .5);
+  }
+  for (int v = 0; v <= nodes; ++v) {
+    const double g = (1. / nodes) * v;
+    double value;
+    if (g <= thresh) value = 4.5 * g;
+    else value = (1. + a) * pow(g, 1. / gamma) - a;
+    l2g[v] = static_cast<uint32_t>(max_y * value) + (1 << lin_bits >> 1);
+  }
+  l2g[nodes + 1] = l2g[nodes];
+}
+
+int RiskinessDecision(unsigned long long score_sum, unsigned long long score_num, unsigned long long gray_num,
+                      int width, int height, float* risk) {   // jpeg_tools.cc:212-235
+  const double count = static_cast<double>(score_num);
+  double gray_count = static_cast<double>(gray_num);
+  double total_score = (count > 0) ? static_cast<double>(static_cast<long long>(score_sum)) / count : 0.;
+  const double num_samples = (width - 1.) * (height - 1.);
+  if (num_samples > 0.) gray_count /= num_samples;
+  const double frac = 100. * count / (static_cast<double>(width) * height);
+  if (frac < 1.) total_score = 0.;
+  total_score = (total_score > 25.) ? 100. : total_score * 100. / 25.;
+  if (risk != nullptr) *risk = static_cast<float>(total_score);
+  return (gray_count > 0.995) ? 4 : (total_score < 40.0) ? 1 : (total_score < 70.0) ? 2 : 3;
+}
+
 }  // namespace sjb

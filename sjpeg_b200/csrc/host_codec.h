@@ -53,4 +53,14 @@ bool MakeGeometry(int yuv_mode, int width, int height, FrameGeometry* g);   // e
 void AppendHeaders(const FrameGeometry& g, const uint8_t quant[2][64], const HuffSpec spec[4],
                    std::vector<uint8_t>* out);
 
+// Gamma tables of the sharp RGB->YUV conversion (yuv_convert.cc:102-151): g2l[1024] gamma ->
+// linear with 14 fractional bits, l2g[34] interpolation nodes of the inverse.  Double-precision
+// pow() on the host, exactly as the reference builds them at first use.
+void MakeSharpGammaTables(uint32_t g2l[1024], uint32_t l2g[34]);
+
+// Final decision of the riskiness analyser (jpeg_tools.cc:212-235) from the three sums the device
+// pass produces.  Returns the SjpegYUVMode value (420 = 1, SHARP = 2, 444 = 3, 400 = 4).
+int RiskinessDecision(unsigned long long score_sum, unsigned long long score_num, unsigned long long gray_num,
+                      int width, int height, float* risk);
+
 }  // namespace sjb

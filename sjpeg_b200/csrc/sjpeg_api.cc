@@ -55,9 +55,13 @@ bool ParamsFromEncoderParam(const sjpeg::EncoderParam& param, const uint8_t quan
                             sjb_params* out) {
   memset(out, 0, sizeof(*out));
   SjpegYUVMode mode = param.yuv_mode;
-  // the riskiness analyser (jpeg_tools.cc:177-236) is not part of this path: AUTO means 4:2:0
-  if (mode == SJPEG_YUV_AUTO) mode = SJPEG_YUV_420;
-  if (mode != SJPEG_YUV_420 && mode != SJPEG_YUV_444 && mode != SJPEG_YUV_400) return false;
+  // The riskiness analyser (jpeg_tools.cc:177-236) runs on the device but needs the reference's
+  // generated score table (sjb_set_score_table / SJPEG_B200_SCORE_TABLE); without it AUTO means 4:2:0.
+  if (mode == SJPEG_YUV_AUTO && !sjb_has_score_table()) mode = SJPEG_YUV_420;
+  if (mode != SJPEG_YUV_AUTO && mode != SJPEG_YUV_420 && mode != SJPEG_YUV_SHARP && mode != SJPEG_YUV_444 &&
+      mode != SJPEG_YUV_400) {
+    return false;
+  }
   out->yuv_mode = mode;
   out->pix_fmt = fmt;
   for (int i = 0; i < 2; ++i) {
@@ -398,8 +402,11 @@ size_t SjpegEncode(const uint8_t* rgb, int width, int height, int stride, uint8_
   if (rgb == nullptr || out_data == nullptr) return 0;
   if (width <= 0 || height <= 0 || abs(stride) < 3 * width) return 0;
   *out_data = nullptr;
-  if (yuv_mode == SJPEG_YUV_AUTO) yuv_mode = SJPEG_YUV_420;   // see ParamsFromEncoderParam
-  if (yuv_mode != SJPEG_YUV_420 && yuv_mode != SJPEG_YUV_444 && yuv_mode != SJPEG_YUV_400) return 0;
+  if (yuv_mode == SJPEG_YUV_AUTO && !sjb_has_score_table()) yuv_mode = SJPEG_YUV_420;   // see ParamsFromEncoderParam
+  if (yuv_mode != SJPEG_YUV_AUTO && yuv_mode != SJPEG_YUV_420 && yuv_mode != SJPEG_YUV_SHARP &&
+      yuv_mode != SJPEG_YUV_444 && yuv_mode != SJPEG_YUV_400) {
+    return 0;
+  }
   sjb_params p;
   sjb_params_default(&p, quality, method, yuv_mode);
   NewArraySink sink;
@@ -504,10 +511,17 @@ int SjpegFindQuantizer(const uint8_t* d, size_t size, uint8_t quant[2][64]) {   
   return __builtin_popcount(seen & 15);
 }
 
-SjpegYUVMode SjpegRiskiness(const uint8_t*, int, int, int, float* risk) {
-  // The chroma-subsampling risk analyser (jpeg_tools.cc:177-236) is not part of this path.
+SjpegYUVMode SjpegRiskiness(const uint8_t* rgb, int width, int height, int stride, float* risk) {
+  // jpeg_tools.cc:177-236 on the device.  The generated score table comes from the host binding
+  // (sjb_set_score_table) or SJPEG_B200_SCORE_TABLE; without it the answer is 4:2:0 / risk 0.
   if (risk) *risk = 0.f;
-  return SJPEG_YUV_420;
+  if (rgb == nullptr || width <= 0 || height <= 0 || !sjb_has_score_table()) return SJPEG_YUV_420;
+  sjb_context* ctx = tls_context.get();
+  int mode = SJPEG_YUV_420;
+  float r = 0.f;
+  if (ctx == nullptr || sjb_riskiness(ctx, rgb, 0, width, height, stride, &mode, &r) != SJB_OK) return SJPEG_YUV_420;
+  if (risk) *risk = r;
+  return static_cast<SjpegYUVMode>(mode);
 }
 
 }  // extern "C"
@@ -593,6 +607,25 @@ static bool EncodePacked(const uint8_t* pix, int width, int height, int stride, 
   if (!Encoder::Convert(param, fmt, &p) || !BuildMetadata(param, &meta)) {
     sink->Reset();
     return false;
+  }
+  if (fmt != SJB_PIX_RGB && (p.yuv_mode == SJPEG_YUV_AUTO || p.yuv_mode == SJPEG_YUV_SHARP)) {
+    // api.cc:208-224,235-251: these two modes work on a scratch RGB copy of 4-byte pixels
+    const size_t rgb_stride = 3 * static_cast<size_t>(width);
+    std::unique_ptr<uint8_t[]> rgb(new (std::nothrow) uint8_t[rgb_stride * height]);
+    if (rgb == nullptr) return false;
+    const int ro = (fmt == SJB_PIX_BGRA) ? 2 : 0, bo = 2 - ro;
+    for (int y = 0; y < height; ++y) {
+      const uint8_t* s = pix + static_cast<ptrdiff_t>(y) * stride;
+      uint8_t* d = rgb.get() + y * rgb_stride;
+      for (int x = 0; x < width; ++x, s += 4, d += 3) {
+        d[0] = s[ro];
+        d[1] = s[1];
+        d[2] = s[bo];
+      }
+    }
+    p.pix_fmt = SJB_PIX_RGB;
+    return EncodeToSink(rgb.get(), width, height, static_cast<int>(rgb_stride), SJB_PIX_RGB, p, sink, param.memory,
+                        meta, &param);
   }
   return EncodeToSink(pix, width, height, stride, fmt, p, sink, param.memory, meta, &param);
 }

@@ -12,6 +12,7 @@
 
 #include "../../sjpeg_b200/csrc/block_ops.cuh"
 #include "../../sjpeg_b200/csrc/host_codec.h"
+#include "../../sjpeg_b200/csrc/sharp_ops.cuh"
 
 using namespace sjb;
 
@@ -216,5 +217,101 @@ size_t emul_encode(const uint8_t* pix, int w, int h, long long stride, int mode,
 }
 
 void emul_free(uint8_t* p) { free(p); }
+
+// Sharp RGB->YUV 4:2:0 as sharp.cu lays it out: import into state 0, four refinement iterations
+// each writing its OWN copy of the state (the kernels run them as a pipeline), the exit rule
+// applied afterwards to pick the copy to keep.  Pictures with a side <= 4 take the plain path.
+struct PlainLd {
+  int y(const uint16_t* p) const { return *p; }
+  int uv(const int16_t* p) const { return *p; }
+};
+void emul_sharp_yuv(const uint8_t* rgb, int width, int height, long long stride, uint8_t* yo, uint8_t* uo,
+                    uint8_t* vo) {
+  const int out_uv_w = (width + 1) >> 1;
+  if (width <= 4 || height <= 4) {
+    const int uv_h = (height + 1) >> 1;
+    for (int r = 0; r < uv_h; ++r) {
+      for (int i = 0; i < out_uv_w; ++i) {
+        int sum[3] = {0, 0, 0};
+        for (int dy = 0; dy < 2; ++dy) {
+          const int y = (2 * r + dy < height) ? 2 * r + dy : height - 1;
+          for (int dx = 0; dx < 2; ++dx) {
+            const int x = (2 * i + dx < width) ? 2 * i + dx : width - 1;
+            const uint8_t* px = rgb + y * stride + 3 * x;
+            for (int k = 0; k < 3; ++k) sum[k] += px[k];
+            if (2 * r + dy < height && 2 * i + dx < width) yo[(size_t)y * width + x] = (uint8_t)sharp_small_y(px[0], px[1], px[2]);
+          }
+        }
+        uo[(size_t)r * out_uv_w + i] = (uint8_t)sharp_final_u(sum[0], sum[1], sum[2]);
+        vo[(size_t)r * out_uv_w + i] = (uint8_t)sharp_final_v(sum[0], sum[1], sum[2]);
+      }
+    }
+    return;
+  }
+  uint32_t g2l[1024], l2g[34];
+  MakeSharpGammaTables(g2l, l2g);
+  const SharpTabs t = {g2l, l2g};
+  const int w = (width + 1) & ~1, h = (height + 1) & ~1, uv_w = w >> 1, uv_h = h >> 1;
+  const size_t yp = (size_t)w * h, up = (size_t)uv_w * 3 * uv_h;
+  std::vector<uint16_t> ys((kSharpIterations + 1) * yp), ty(yp);
+  std::vector<int16_t> uvs((kSharpIterations + 1) * up), tuv(up);
+  for (int r = 0; r < uv_h; ++r) {
+    for (int i = 0; i < uv_w; ++i) {
+      sharp_import_cell(t, rgb, stride, width, height, w, uv_w, r, i, ys.data(), ty.data(), uvs.data(), tuv.data());
+    }
+  }
+  unsigned long long diff[kSharpIterations] = {0, 0, 0, 0};
+  const PlainLd ld;
+  for (int it = 0; it < kSharpIterations; ++it) {
+    const uint16_t* y_prev = ys.data() + it * yp;
+    uint16_t* y_mine = ys.data() + (it + 1) * yp;
+    const int16_t* uv_prev = uvs.data() + it * up;
+    int16_t* uv_mine = uvs.data() + (it + 1) * up;
+    for (int r = 0; r < uv_h; ++r) {
+      const size_t row = (size_t)r * 3 * uv_w, y_row = (size_t)(2 * r) * w;
+      const int16_t* above = (r > 0) ? uv_mine + row - 3 * uv_w : uv_prev;
+      const int16_t* below = uv_prev + ((r < uv_h - 1) ? row + 3 * uv_w : row);
+      for (int i = 0; i < uv_w; ++i) {
+        diff[it] += sharp_refine_cell(t, ld, w, uv_w, i, y_prev + y_row, y_mine + y_row, above, false, uv_prev + row,
+                                      below, uv_mine + row, ty.data() + y_row, tuv.data() + row);
+      }
+    }
+  }
+  const int keep = sharp_final_iteration(diff, w, h) + 1;
+  const uint16_t* yk = ys.data() + keep * yp;
+  const int16_t* uvk = uvs.data() + keep * up;
+  for (int j = 0; j < height; ++j) {
+    const int16_t* uv = uvk + (size_t)(j >> 1) * 3 * uv_w;
+    for (int i = 0; i < width; ++i) {
+      const int W = yk[(size_t)j * w + i];
+      yo[(size_t)j * width + i] = (uint8_t)sharp_final_y(uv[i >> 1] + W, uv[uv_w + (i >> 1)] + W, uv[2 * uv_w + (i >> 1)] + W);
+    }
+  }
+  for (int r = 0; r < uv_h; ++r) {
+    const int16_t* uv = uvk + (size_t)r * 3 * uv_w;
+    for (int i = 0; i < uv_w; ++i) {
+      uo[(size_t)r * out_uv_w + i] = (uint8_t)sharp_final_u(uv[i], uv[uv_w + i], uv[2 * uv_w + i]);
+      vo[(size_t)r * out_uv_w + i] = (uint8_t)sharp_final_v(uv[i], uv[uv_w + i], uv[2 * uv_w + i]);
+    }
+  }
+}
+
+// riskiness sums + decision from the product's index function and host decision
+int emul_riskiness(const uint8_t* rgb, int width, int height, long long stride, const uint8_t* table, float* risk) {
+  unsigned long long sum = 0, num = 0, gray = 0;
+  for (int j = 0; j + 1 < height; ++j) {
+    const uint8_t* a = rgb + j * stride;
+    const uint8_t* b = a + stride;
+    for (int x = 0; x + 1 < width; ++x) {
+      const int i0 = risk_index(a[3 * x], a[3 * x + 1], a[3 * x + 2]);
+      const int i1 = risk_index(a[3 * x + 3], a[3 * x + 4], a[3 * x + 5]);
+      const int i2 = risk_index(b[3 * x], b[3 * x + 1], b[3 * x + 2]);
+      const int score = table[i0 + kRiskLevels3 * i1] + table[i0 + kRiskLevels3 * i2] + table[i1 + kRiskLevels3 * i2];
+      if (score > kRiskNoise) { sum += score; num += 1; }
+      gray += (i0 >= kRiskGrayMin && i0 < kRiskGrayMin + 7) ? 1 : 0;
+    }
+  }
+  return RiskinessDecision(sum, num, gray, width, height, risk);
+}
 
 }  // extern "C"

@@ -20,7 +20,12 @@ CASES = [
     ("B", 1920, 1080, 75, 0, 1),
     ("A", 203, 117, 75, 0, 1), ("A", 203, 117, 90, 4, 3), ("A", 203, 117, 50, 7, 4),
     ("B", 1000, 700, 85, 2, 1), ("A", 1000, 700, 30, 5, 3), ("B", 1000, 700, 95, 8, 4),
+    # SJPEG_YUV_SHARP (yuv_mode 2): iterative sharp RGB->YUV420 pre-pass, then the planar encoder
+    ("A", 203, 117, 75, 0, 2), ("A", 1000, 700, 85, 1, 2), ("B", 1001, 701, 60, 4, 2),
+    ("A", 3840, 2160, 75, 0, 2), ("B", 3840, 2160, 75, 4, 2),
 ]
+# SjpegRiskiness (mode, risk) of the reference on the same generators
+RISK_CASES = [("A", 512, 512), ("B", 512, 512), ("A", 3840, 2160), ("B", 3840, 2160), ("A", 203, 117), ("B", 1001, 701)]
 
 
 def main():
@@ -43,9 +48,15 @@ def main():
         total += len(data)
     c5 = {"frames": 64, "w": 1920, "h": 1080, "total_size": total,
           "md5_of_md5s": O.md5("".join(digests).encode()), "frame_md5": digests}
+    risk = []
+    for gen, w, h in RISK_CASES:
+        rgb = O.make_rgb(gen, w, h)
+        mode, value = O.ref_riskiness(rgb, w, h, 3 * w)
+        risk.append({"gen": gen, "w": w, "h": h, "seed": 7654321, "mode": mode, "risk": value})
+        print(risk[-1])
     with open(os.path.join(os.path.dirname(__file__), "ref_md5.json"), "w") as fp:
         json.dump({"generator": "tests/golden/make_golden.py", "reference_commit": "6b8cd89",
-                   "cases": out, "config5": c5}, fp, indent=1)
+                   "cases": out, "config5": c5, "riskiness": risk}, fp, indent=1)
 
 
 if __name__ == "__main__":

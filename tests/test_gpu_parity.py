@@ -262,10 +262,12 @@ def test_row_stripes_on_one_gpu(gpu_ctx, parts):
         assert gpu_ctx.encode(frames[0], w, h, 3 * w, params) == O.oracle_encode(frames[0], w, h, 3 * w, float(q), 0, mode)
 
 
-# the reference's own API tests that lie inside this round's scope
+# the reference's own API tests: all 17.  Riskiness / YUV_AUTO need the
+# reference's generated score table, handed over through SJPEG_B200_SCORE_TABLE.
 REFERENCE_TESTS_IN_SCOPE = ["InvalidArguments", "SinkFailure", "CompressionMethod", "Compress", "Dimensions",
                             "QuantMatrix", "LargeDimensions", "EncodeYUV420Strides", "EncodeYUV444Strides",
-                            "EncodeNV", "NegativeStrides", "TargetSize", "AllocationFailure"]
+                            "EncodeNV", "NegativeStrides", "TargetSize", "AllocationFailure", "Threads",
+                            "EncodeParams", "MemoryManager", "Riskiness"]
 
 
 def test_reference_unit_tests_against_the_product_library(gpu_ctx):
@@ -275,7 +277,13 @@ def test_reference_unit_tests_against_the_product_library(gpu_ctx):
     exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "unit_test_b200")
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/unit_test_b200 not built (reference sources absent at build time)")
-    res = subprocess.run([exe] + REFERENCE_TESTS_IN_SCOPE, capture_output=True, text=True, timeout=600)
+    table = O.score_table()
+    if table is None:
+        pytest.skip("oracle/_ref not shipped: no score table for the Riskiness test")
+    table_path = os.path.join(os.path.dirname(exe), "score_table.bin")
+    table.tofile(table_path)
+    env = dict(os.environ, SJPEG_B200_SCORE_TABLE=table_path)
+    res = subprocess.run([exe] + REFERENCE_TESTS_IN_SCOPE, capture_output=True, text=True, timeout=900, env=env)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
     assert "%d test(s)" % len(REFERENCE_TESTS_IN_SCOPE) in res.stdout and " 0 failure(s)" in res.stdout, res.stdout
 
@@ -290,6 +298,97 @@ def test_planar_and_semiplanar_inputs(gpu_ctx, kind):
             p = S.default_params(q, method, O.KIND_MODE[kind])
             got = gpu_ctx.encode_planar(*O.planar_args(kind, planes), w, h, p)
             assert got == O.oracle_encode_planar(kind, planes, w, h, q, method), (kind, w, h, q, method)
+
+
+SHARP_SIZES = [(1, 1), (3, 7), (4, 4), (5, 5), (5, 4), (4, 9), (6, 5), (7, 7), (16, 16), (17, 33), (64, 48), (203, 117),
+               (256, 255), (640, 481), (1030, 64), (2050, 37), (4100, 21)]
+
+
+def _sharp_images(w, h, seed=5):
+    rng = np.random.RandomState(seed + w + h)
+    yield from _images(w, h, seed)
+    sat = np.zeros((h, w, 3), np.uint8)      # saturated stripes: the case the iteration exists for
+    sat[:, ::2, 0] = 255
+    sat[::2, :, 2] = 255
+    yield "saturated", sat
+    yield "gray", np.repeat(rng.randint(0, 256, (h, w, 1)), 3, axis=2).astype(np.uint8)
+
+
+@pytest.mark.parametrize("size", SHARP_SIZES, ids=lambda s: "%dx%d" % s)
+def test_sharp_yuv_planes_bit_exact(gpu_ctx, size):
+    """sjb_sharp_yuv (import -> pipelined refinement clusters -> finish; ApplySharpYUVConversion,
+    yuv_convert.cc:671-695) vs the oracle, plane by plane; widths above 512 / 1024 / 2048 chroma
+    columns exercise clusters of 2, 4 and 8 CTAs."""
+    w, h = size
+    for name, rgb in _sharp_images(w, h):
+        got = gpu_ctx.sharp_yuv(rgb, w, h, 3 * w)
+        for plane, g, want in zip("yuv", got, O.oracle_sharp_yuv(rgb, w, h, 3 * w)):
+            assert np.array_equal(g, want), (name, w, h, plane)
+    # padded and negative strides
+    pad = np.zeros((h, 3 * w + 7), np.uint8)
+    rgb = O.make_rgb("A", w, h)
+    pad[:, :3 * w] = rgb.reshape(h, 3 * w)
+    want = O.oracle_sharp_yuv(rgb, w, h, 3 * w)
+    for g, wv in zip(gpu_ctx.sharp_yuv(pad, w, h, pad.strides[0]), want):
+        assert np.array_equal(g, wv)
+    flipped = np.ascontiguousarray(pad[::-1])
+    base = flipped.ctypes.data + (h - 1) * flipped.strides[0]
+    for g, wv in zip(gpu_ctx.sharp_yuv(flipped, w, h, -flipped.strides[0], base=base), want):
+        assert np.array_equal(g, wv)
+
+
+@pytest.mark.parametrize("method", [0, 1, 4, 7])
+def test_sharp_mode_whole_file(gpu_ctx, method):
+    """SJPEG_YUV_SHARP through sjb_encode and the drop-in SjpegEncode() (EncoderSharp420,
+    encoders.cc:512-541) vs the oracle; RGBA / BGRA go through the facade's RGB copy (api.cc:208-251)."""
+    import sjpeg_b200 as S
+    for (w, h) in ((3, 3), (17, 9), (203, 117), (640, 360)):
+        for name, rgb in _sharp_images(w, h):
+            want = O.oracle_encode(rgb, w, h, 3 * w, 75.0, method, O.YUV_SHARP)
+            assert gpu_ctx.encode(rgb, w, h, 3 * w, S.default_params(75, method, S.YUV_SHARP)) == want, (name, w, h)
+            assert S.sjpeg_encode(rgb, w, h, 3 * w, 75, method, S.YUV_SHARP) == want, (name, w, h)
+    p = S.default_params(75, method, S.YUV_SHARP)
+    p.pix_fmt = S.PIX_RGBA
+    rgba = np.zeros((9, 17, 4), np.uint8)
+    assert gpu_ctx.encode(rgba, 17, 9, 68, p) is None      # C ABI: sharp takes packed RGB only
+
+
+def test_riskiness_and_auto_mode(gpu_ctx):
+    """sjb_riskiness / SjpegRiskiness / SJPEG_YUV_AUTO (jpeg_tools.cc:177-236, encoders.cc:549-551)
+    with the reference's own score table vs the oracle and the committed reference values."""
+    import sjpeg_b200 as S
+    table = O.score_table()
+    if table is None:
+        pytest.skip("oracle/_ref not shipped: no score table")
+    S.set_score_table(None)
+    rgb = O.make_rgb("A", 64, 48)
+    assert S.lib().sjb_has_score_table() == 0
+    with pytest.raises(S.SjpegB200Error):
+        gpu_ctx.riskiness(rgb, 64, 48, 192)                  # loud without the table
+    # the drop-in facade's documented policy without a table: AUTO = 4:2:0
+    assert S.sjpeg_encode(rgb, 64, 48, 192, 75, 0, S.YUV_AUTO) == O.oracle_encode(rgb, 64, 48, 192, 75.0, 0, O.YUV_420)
+    S.set_score_table(table)
+    try:
+        seen = set()
+        for (w, h) in ((1, 1), (2, 2), (9, 2), (2, 9), (64, 48), (203, 117), (641, 359), (1920, 1080)):
+            for name, img in _sharp_images(w, h):
+                want = O.oracle_riskiness(img, w, h, 3 * w, table)
+                assert gpu_ctx.riskiness(img, w, h, 3 * w) == want, (name, w, h)
+                risk = C.c_float()
+                mode = S.lib().SjpegRiskiness(img.ctypes.data, w, h, 3 * w, C.byref(risk))
+                assert (mode, risk.value) == want, (name, w, h)
+                seen.add(want[0])
+                if w <= 641:
+                    for method in (0, 4):
+                        got = S.sjpeg_encode(img, w, h, 3 * w, 75, method, S.YUV_AUTO)
+                        assert got == O.oracle_encode(img, w, h, 3 * w, 75.0, method, want[0]), (name, w, h, method)
+        assert seen == {O.YUV_420, O.YUV_SHARP, O.YUV_444, O.YUV_400}, seen
+        for case in GOLD.get("riskiness", []):
+            img = O.make_rgb(case["gen"], case["w"], case["h"], case["seed"])
+            mode, risk = gpu_ctx.riskiness(img, case["w"], case["h"], 3 * case["w"])
+            assert mode == case["mode"] and risk == pytest.approx(case["risk"], abs=0, rel=0), case
+    finally:
+        S.set_score_table(None)
 
 
 def _api_shims():

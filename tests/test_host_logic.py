@@ -28,6 +28,9 @@ def emul():
                               C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(_u8p)]
     E.emul_free.argtypes = [_u8p]
     E.emul_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p]
+    E.emul_sharp_yuv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
+    E.emul_riskiness.restype = C.c_int
+    E.emul_riskiness.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.POINTER(C.c_float)]
     return E
 
 
@@ -81,6 +84,29 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in ("SjpegEncode", "SjpegCompress", "SjpegFreeBuffer", "SjpegDimensions", "SjpegFindQuantizer",
                  "SjpegEstimateQuality", "SjpegQuantMatrix", "SjpegRiskiness"):
         assert hasattr(L, name), name
+
+
+def test_sharp_yuv_and_riskiness_cell_functions_match_oracle(emul):
+    """sharp_ops.cuh (the per-cell code of sharp.cu) run on the CPU in the kernels' own data layout
+    -- one state copy per iteration, exit rule applied afterwards -- equals the oracle's in-place loop."""
+    rng = np.random.RandomState(3)
+    table = O.score_table()
+    if table is None:   # the compiled reference did not travel: any table exercises the same code
+        table = rng.randint(0, 40, 343 * 343).astype(np.uint8)
+    for (w, h) in ((1, 1), (4, 9), (5, 5), (6, 5), (7, 8), (16, 16), (33, 21), (130, 67)):
+        sat = np.zeros((h, w, 3), np.uint8)
+        sat[:, ::2, 0] = 255
+        sat[::2, :, 2] = 255
+        for img in (O.make_rgb("A", w, h), O.make_rgb("B", w, h), rng.randint(0, 256, (h, w, 3)).astype(np.uint8),
+                    (rng.randint(0, 2, (h, w, 3)) * 255).astype(np.uint8), sat):
+            cw, ch = (w + 1) // 2, (h + 1) // 2
+            y, u, v = np.zeros((h, w), np.uint8), np.zeros((ch, cw), np.uint8), np.zeros((ch, cw), np.uint8)
+            emul.emul_sharp_yuv(img.ctypes.data, w, h, 3 * w, y.ctypes.data, u.ctypes.data, v.ctypes.data)
+            for got, want in zip((y, u, v), O.oracle_sharp_yuv(img, w, h, 3 * w)):
+                assert np.array_equal(got, want), (w, h)
+            risk = C.c_float()
+            mode = emul.emul_riskiness(img.ctypes.data, w, h, 3 * w, table.ctypes.data, C.byref(risk))
+            assert (mode, risk.value) == O.oracle_riskiness(img, w, h, 3 * w, table), (w, h)
 
 
 def test_host_helpers_without_gpu():

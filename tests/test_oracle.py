@@ -96,3 +96,25 @@ def test_oracle_planar_inputs_equal_compiled_reference():
                     a = O.oracle_encode_planar(kind, planes, w, h, q, method)
                     b = O.ref_encode_planar(kind, planes, w, h, q, *fl)
                     assert a is not None and a == b, (w, h, q, method, kind)
+
+
+@pytest.mark.skipif(O.ref() is None, reason="oracle/_ref not built")
+def test_sharp_yuv_and_riskiness_match_reference():
+    """Pins oracle/sjpeg_oracle_sharp.c: planes of sjpeg::ApplySharpYUVConversion, (mode, risk) of
+    SjpegRiskiness, and whole SJPEG_YUV_SHARP files of the compiled unmodified reference."""
+    rng = np.random.RandomState(1)
+    table = O.score_table()
+    for (w, h) in ((1, 1), (3, 7), (4, 4), (5, 5), (5, 4), (4, 9), (6, 5), (7, 7), (16, 16), (17, 33), (64, 48),
+                   (203, 117), (256, 255)):
+        sat = np.zeros((h, w, 3), np.uint8)
+        sat[:, ::2, 0] = 255
+        sat[::2, :, 2] = 255
+        gray = np.repeat(rng.randint(0, 256, (h, w, 1)), 3, axis=2).astype(np.uint8)
+        for img in (O.make_rgb("A", w, h), O.make_rgb("B", w, h), rng.randint(0, 256, (h, w, 3)).astype(np.uint8),
+                    (rng.randint(0, 2, (h, w, 3)) * 255).astype(np.uint8), sat, gray):
+            for a, b in zip(O.oracle_sharp_yuv(img, w, h, 3 * w), O.ref_sharp_yuv(img, w, h, 3 * w)):
+                assert np.array_equal(a, b), (w, h)
+            assert O.oracle_riskiness(img, w, h, 3 * w, table) == O.ref_riskiness(img, w, h, 3 * w), (w, h)
+            for m in (0, 4):
+                assert O.oracle_encode(img, w, h, 3 * w, 75.0, m, O.YUV_SHARP) == \
+                    O.ref_encode(img, w, h, 3 * w, 75.0, m, O.YUV_SHARP), (w, h, m)
