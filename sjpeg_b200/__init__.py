@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsjpeg_b200.so")
+# SJPEG_B200_LIB selects another build of the same library (kernel A/B experiments)
+LIB_PATH = os.environ.get("SJPEG_B200_LIB") or os.path.join(_HERE, "libsjpeg_b200.so")
 
 YUV_AUTO, YUV_420, YUV_SHARP, YUV_444, YUV_400 = 0, 1, 2, 3, 4
 PIX_RGB, PIX_BGRA, PIX_RGBA = 0, 1, 2

@@ -192,27 +192,6 @@ SJB_HD void size_and_bits(int v, int* n, uint32_t* bits) {
 // and packing.  Follows entropy.cc:161-198 (CodeBlock) with run/levels recomputed on the fly as
 // quantize.cc:288-320 emits them.
 // ---------------------------------------------------------------------------------------------
-template <class Sink>
-struct AcEmitter {
-  Sink& sink;
-  const uint32_t* ac_codes;
-  int prev;   // zig-zag position of the previous non-zero coefficient (0 = DC slot)
-  SJB_HD void emit(int pos, int v) {
-    int run = pos - prev - 1;
-    prev = pos;
-    const uint32_t zrl = ac_codes[0xf0];
-    while (run >= 16) {                    // ZRL escapes, entropy.cc:176-179
-      sink.put(zrl >> 16, (int)(zrl & 0xff));
-      run -= 16;
-    }
-    int n;
-    uint32_t bits;
-    size_and_bits(v, &n, &bits);
-    const uint32_t c = ac_codes[(run << 4) | n];
-    sink.put(((c >> 16) << n) | bits, (int)(c & 0xff) + n);
-  }
-};
-
 SJB_HD int find_first_set32(uint32_t m) {   // index of lowest set bit, m != 0
 #if defined(__CUDA_ARCH__)
   return __ffs((int)m) - 1;
@@ -225,8 +204,28 @@ struct Words4 {
   uint32_t w[4];
 };
 
-template <class LoadChunk, class Sink>
-SJB_HD void code_block(LoadChunk load_chunk, uint32_t chunkmask, int dc, int dc_pred, const uint32_t* dc_codes,
+// 8 flag bits of a chunk: bit k <=> value k of the chunk (zig-zag position 8c + k) is non-zero
+SJB_HD uint32_t chunk_nonzero_bits(const Words4& q) {
+  uint32_t m = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t w = q.w[j];
+    const uint32_t lo = (w & 0xffffu) ? 1u : 0u, hi = (w >> 16) ? 2u : 0u;
+    m |= (lo | hi) << (2 * j);
+  }
+  return m;
+}
+
+// The walk has two phases so that the lanes of a warp stay converged: first the 64-bit map of
+// non-zero positions is assembled from the chunks the bitmap names (a short loop, usually one or
+// two chunks), then ONE loop iteration per non-zero coefficient emits its run/size symbol -- the
+// trip count of a warp is the largest number of non-zeros among its 32 blocks, not the number of
+// (chunk, slot) pairs any of them touches.  Loader: operator()(chunk) -> Words4, value(pos) -> the
+// quantised value at zig-zag position pos.
+template <class Loader, class Sink>
+SJB_HD void code_block(Loader load, uint32_t chunkmask, int dc, int dc_pred, const uint32_t* dc_codes,
                        const uint32_t* ac_codes, Sink& sink) {
   {
     const int diff = dc - dc_pred;
@@ -237,25 +236,31 @@ SJB_HD void code_block(LoadChunk load_chunk, uint32_t chunkmask, int dc, int dc_
     // code then n suffix bits; at most 16 + 11 bits
     sink.put(((c >> 16) << n) | bits, (int)(c & 0xff) + n);
   }
-  AcEmitter<Sink> ac = {sink, ac_codes, 0};
-  uint32_t m = chunkmask;
-  while (m) {
+  uint64_t nz = 0;
+  for (uint32_t m = chunkmask; m; m &= m - 1) {
     const int c = find_first_set32(m);
-    m &= m - 1;
-    const Words4 q = load_chunk(c);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t w = q.w[j];
-      if (w == 0) continue;
-      const int p = 4 * c + j;
-      const int lo = (int16_t)(w & 0xffffu), hi = (int32_t)w >> 16;
-      if (p > 0 && lo != 0) ac.emit(2 * p, lo);
-      if (hi != 0) ac.emit(2 * p + 1, hi);
-    }
+    nz |= (uint64_t)chunk_nonzero_bits(load(c)) << (8 * c);
   }
-  if (ac.prev < 63) {                      // EOB, entropy.cc:195-197
+  nz &= ~(uint64_t)1;                      // position 0 is the DC
+  const uint32_t zrl = ac_codes[0xf0];
+  int prev = 0;                            // zig-zag position of the previous non-zero (0 = DC slot)
+  while (nz) {
+    const int pos = find_first_set64(nz);
+    nz &= nz - 1;
+    const int v = load.value(pos);
+    int run = pos - prev - 1;
+    prev = pos;
+    while (run >= 16) {                    // ZRL escapes, entropy.cc:176-179
+      sink.put(zrl >> 16, (int)(zrl & 0xff));
+      run -= 16;
+    }
+    int n;
+    uint32_t bits;
+    size_and_bits(v, &n, &bits);
+    const uint32_t c = ac_codes[(run << 4) | n];
+    sink.put(((c >> 16) << n) | bits, (int)(c & 0xff) + n);
+  }
+  if (prev < 63) {                         // EOB, entropy.cc:195-197
     const uint32_t c = ac_codes[0x00];
     sink.put(c >> 16, (int)(c & 0xff));
   }

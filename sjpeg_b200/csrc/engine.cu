@@ -1341,6 +1341,7 @@ int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int
     float ms = 0;
     *f1_ms = (cudaEventElapsedTime(&ms, L0->ev[0], L0->ev[1]) == cudaSuccess) ? ms : 0.f;
   }
+  FinishTimings(ctx, L0);   // F1 / entropy split of the last group timed on lane 0 (sjb_last_timings)
   if (jpeg_bytes) *jpeg_bytes = static_cast<size_t>(L0->host->info[0].out_size);
   if (launches) {
     *launches = 0;

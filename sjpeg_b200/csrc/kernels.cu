@@ -629,6 +629,7 @@ struct ChunkLoader {   // chunk c of a block = zig-zag positions 8c..8c+7, one 1
     r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
     return r;
   }
+  __device__ __forceinline__ int value(int pos) const { return p[pos]; }
 };
 // Same, with the first two chunks (one 32-byte sector: where the low frequencies live) fetched
 // eagerly together with the bitmap and the predictor, so that a typical block needs a single
@@ -642,6 +643,8 @@ struct PrefetchedChunkLoader {
     r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
     return r;
   }
+  // the 128-byte line of the block is in L1 by now (its first sector was fetched up front)
+  __device__ __forceinline__ int value(int pos) const { return p[pos]; }
 };
 
 __device__ __forceinline__ void load_code_tables(const CodeTabs* tabs, CodeTabs* sh) {
@@ -672,6 +675,18 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// One warp inspects kLookWindow predecessors per round trip to L2, kLookPerLane per lane (lane l
+// owns the predecessors at distance l*kLookPerLane + 1 .., nearest first).  Measured on B200 (4K,
+// 4 pictures per launch): windows of 128 and 256 are SLOWER than 32 (entropy+stuffing 81 / 110 us
+// against 60 us) -- the polling traffic of the wider windows costs more than the shorter walk
+// saves -- so one descriptor per lane is the default.
+#ifndef SJB_LOOK_PER_LANE
+#define SJB_LOOK_PER_LANE 1
+#endif
+#ifndef SJB_E_MINBLOCKS
+#define SJB_E_MINBLOCKS 6
+#endif
+enum { kLookPerLane = SJB_LOOK_PER_LANE, kLookWindow = 32 * kLookPerLane };
 __device__ __forceinline__ unsigned long long warp_lookback(unsigned long long* state, long long tile,
                                                             unsigned long long aggregate) {
   const int lane = threadIdx.x & 31;
@@ -684,20 +699,35 @@ __device__ __forceinline__ unsigned long long warp_lookback(unsigned long long* 
   unsigned long long prefix = 0;
   long long base = tile - 1;
   while (true) {
-    const long long j = base - lane;
-    const unsigned long long v = (j >= 0) ? ld_volatile_u64(&state[j]) : (2ull << 62);   // virtual 0 before tile 0
-    const unsigned flag = static_cast<unsigned>(v >> 62);
-    const unsigned not_ready = __ballot_sync(0xffffffffu, flag == 0);
-    const unsigned has_prefix = __ballot_sync(0xffffffffu, flag == 2);
-    const int first = has_prefix ? (__ffs(has_prefix) - 1) : 31;     // last lane that contributes
+    unsigned long long v[kLookPerLane];
+#pragma unroll
+    for (int e = 0; e < kLookPerLane; ++e) {
+      const long long j = base - (lane * kLookPerLane + e);
+      v[e] = (j >= 0) ? ld_volatile_u64(&state[j]) : (2ull << 62);   // virtual 0 before tile 0
+    }
+    // within the lane, nearest first: sum up to and including the first inclusive prefix
+    unsigned long long sum = 0;
+    bool ready = true, closed = false;      // closed: an inclusive prefix ends the walk here
+#pragma unroll
+    for (int e = 0; e < kLookPerLane; ++e) {
+      const unsigned flag = static_cast<unsigned>(v[e] >> 62);
+      if (!closed) {
+        ready = ready && (flag != 0);
+        sum += v[e] & kValue;
+        closed = (flag == 2);
+      }
+    }
+    const unsigned closed_lanes = __ballot_sync(0xffffffffu, closed);
+    const int first = closed_lanes ? (__ffs(closed_lanes) - 1) : 31;     // last lane that contributes
     const unsigned need = (first == 31) ? 0xffffffffu : ((2u << first) - 1u);
-    if (not_ready & need) continue;                                  // spin: re-read the window
-    unsigned long long val = (lane <= first) ? (v & kValue) : 0ull;
+    const unsigned not_ready = __ballot_sync(0xffffffffu, !ready);
+    if (not_ready & need) continue;                                      // spin: re-read the window
+    unsigned long long val = (lane <= first) ? sum : 0ull;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
     prefix += val;
-    if (has_prefix) break;
-    base -= 32;
+    if (closed_lanes) break;
+    base -= kLookWindow;
   }
   if (lane == 0) st_volatile_u64(&state[tile], (2ull << 62) | (prefix + aggregate));
   return prefix;
@@ -740,7 +770,7 @@ struct LocalSink {
   }
 };
 
-__global__ void __launch_bounds__(kTileBlocks)
+__global__ void __launch_bounds__(kTileBlocks, SJB_E_MINBLOCKS)
 entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   __shared__ __align__(16) CodeTabs sh;
   __shared__ uint32_t scratch[33];

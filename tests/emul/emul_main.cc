@@ -95,6 +95,7 @@ struct Loader {
     for (int j = 0; j < 4; ++j) r.w[j] = (uint16_t)p[8 * c + 2 * j] | ((uint32_t)(uint16_t)p[8 * c + 2 * j + 1] << 16);
     return r;
   }
+  int value(int pos) const { return p[pos]; }
 };
 struct WordOut {
   std::vector<uint32_t>* w;

@@ -42,3 +42,5 @@ else:
     print("clocks:", clocks())
     print("device pipeline: %.4f ms/frame, %.1f Mpix/s, jpeg %d B, launches %d" % (
         total / (n * iters), n * iters * w * h / total / 1e3, nbytes, launches))
+    t = ctx.last_timings()
+    print("last group on lane 0 (ms): F1 stage %.4f, entropy+stuffing %.4f, total %.4f" % (t[0], t[1], t[2]))
