@@ -182,7 +182,7 @@ int MakePlan(int width, int height, long long stride, const sjb_params* params, 
   const size_t nb = plan->g.nb_blocks();
   plan->stream_words = ((nb * kWorstBitsPerBlock / 32 + 64) + 3) & ~static_cast<size_t>(3);
   plan->out_capacity = (kHeaderReserve + 2 * plan->stream_words * 4 + 16 + 255) & ~static_cast<size_t>(255);
-  plan->nb_tiles = (nb + kTileBlocks - 1) / kTileBlocks;
+  plan->nb_tiles = (nb + kTileBlocks - 1) / kTileBlocks + 1;   // + the tile counter of the entropy kernel
   plan->ff_tiles = (plan->stream_words * 4 + kStuffTileBytes - 1) / kStuffTileBytes;
   const size_t coef_bytes = nb * 128;
   plan->group = static_cast<int>(std::min<size_t>(kMaxGroup, std::max<size_t>(1, GroupCoefBudget() / coef_bytes)));

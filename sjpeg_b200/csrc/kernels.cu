@@ -669,11 +669,11 @@ __device__ __forceinline__ int block_in_mcu(size_t g, int mcu_blocks) {
 // Tiles are dispatched in blockIdx order, so a predecessor is always running or finished.
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // One warp inspects kLookWindow predecessors per round trip to L2, kLookPerLane per lane (lane l
 // owns the predecessors at distance l*kLookPerLane + 1 .., nearest first).  Measured on B200 (4K,
@@ -770,75 +770,191 @@ struct LocalSink {
   }
 };
 
-__global__ void __launch_bounds__(kTileBlocks, SJB_E_MINBLOCKS)
+// Persistent, warp-specialised form.  A CTA = 8 worker warps (one 8x8 block per thread, 256 blocks
+// per tile) + 1 look-back warp, and claims tiles from a per-picture counter (so a tile is only ever
+// owned by a running CTA and the look-back chain cannot starve).  Profiling the one-tile-per-CTA
+// form showed 48 % of every CTA's life spent by all warps at the barrier behind the look-back,
+// waiting for the slowest of the ~32 preceding tiles to publish its bit count.  Here the workers
+// do not wait: after walking tile i they hand (tile id, bit total) to the look-back warp and go on
+// to walk tile i+1 into the other half of the double-buffered slots; only then do they pick up
+// the prefix of tile i -- long since resolved -- and copy its words to the stream.
+enum { kEWorkers = kTileBlocks, kEThreads = kTileBlocks + 32 };
+enum { kBarWorkers = 1, kBarFull = 2 /* +buffer */, kBarReady = 4 /* +buffer */ };
+// barrier ids are immediates (a register id makes ptxas reserve all 16 hardware barriers per CTA,
+// which caps the SM at 4 CTAs)
+template <int kId>
+__device__ __forceinline__ void bar_sync_id(int count) {
+  asm volatile("bar.sync %0, %1;" ::"n"(kId), "r"(count) : "memory");
+}
+template <int kId>
+__device__ __forceinline__ void bar_arrive_id(int count) {
+  asm volatile("bar.arrive %0, %1;" ::"n"(kId), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_sync(int id, int count) {
+  switch (id) {
+    case 1: bar_sync_id<1>(count); break;
+    case 2: bar_sync_id<2>(count); break;
+    case 3: bar_sync_id<3>(count); break;
+    case 4: bar_sync_id<4>(count); break;
+    default: bar_sync_id<5>(count); break;
+  }
+}
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+  switch (id) {
+    case 2: bar_arrive_id<2>(count); break;
+    case 3: bar_arrive_id<3>(count); break;
+    case 4: bar_arrive_id<4>(count); break;
+    default: bar_arrive_id<5>(count); break;
+  }
+}
+// cta_exclusive_scan for the worker warps only (named barrier instead of __syncthreads)
+__device__ __forceinline__ uint32_t workers_exclusive_scan(uint32_t v, uint32_t* scratch, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int nwarps = kEWorkers / 32;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) scratch[warp] = incl;
+  bar_sync(kBarWorkers, kEWorkers);
+  if (warp == 0) {
+    const uint32_t w = (lane < nwarps) ? scratch[lane] : 0;
+    uint32_t wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += t;
+    }
+    scratch[lane] = wi - w;
+    if (lane == 31) scratch[32] = wi;
+  }
+  bar_sync(kBarWorkers, kEWorkers);
+  const uint32_t res = scratch[warp] + incl - v;
+  *total = scratch[32];
+  bar_sync(kBarWorkers, kEWorkers);   // scratch reusable afterwards
+  return res;
+}
+
+__global__ void __launch_bounds__(kEThreads, 5)
 entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   __shared__ __align__(16) CodeTabs sh;
   __shared__ uint32_t scratch[33];
-  __shared__ unsigned long long tile_prefix;
-  __shared__ uint32_t local[kTileBlocks][kLocalWords + 1];   // odd stride: conflict-free
+  __shared__ long long tile_id[2];
+  __shared__ uint32_t tile_total[2];
+  __shared__ unsigned long long tile_prefix[2];
+  __shared__ uint32_t local[2][kTileBlocks][kLocalWords + 1];   // odd stride: conflict-free; word 16 = ex | bits << 20
   const int frame = blockIdx.y;
   load_code_tables(gb.tabs + frame, &sh);
   const int16_t* zz = gb.coef + frame * gb.coef_pitch;
   const uint8_t* nzmask = gb.nzmask + frame * gb.mask_pitch;
   const size_t nb_blocks = fs.blocks_per_frame;
-  const size_t g = blockIdx.x * static_cast<size_t>(kTileBlocks) + threadIdx.x;
-  const bool valid = g < nb_blocks;
-  int k = 0, c = 0, dc = 0, pred = 0;
-  uint32_t mask = 0;
-  const int16_t* b = zz + (valid ? g : 0) * 64;
-  uint32_t bits = 0;
-  int nw = 0;
-  uint32_t* mine = local[threadIdx.x];
-  if (valid) {
-    k = block_in_mcu(g, fs.mcu_blocks);
-    c = (k >= fs.luma_blocks) ? 1 : 0;
-    mask = nzmask[g];
-    const PrefetchedChunkLoader loader = {b, reinterpret_cast<const uint4*>(b)[0], reinterpret_cast<const uint4*>(b)[1]};
-    pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, gb.dc_init ? gb.dc_init + 3 * frame : nullptr);
-    dc = static_cast<int16_t>(loader.c0.x & 0xffffu);
-    LocalSink sink = {mine, 0, 0, 0, 0};
-    code_block(loader, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
-    sink.finish();
-    bits = sink.total;
-    nw = sink.nw;
+  const long long ntiles = static_cast<long long>((nb_blocks + kTileBlocks - 1) / kTileBlocks);
+  unsigned long long* state = gb.bit_state + frame * gb.bit_state_pitch;
+  unsigned long long* counter = state + (gb.bit_state_pitch - 1);   // last slot: next tile to claim
+  const int* dc_init = gb.dc_init ? gb.dc_init + 3 * frame : nullptr;
+
+  if (threadIdx.x >= kEWorkers) {
+    // ---- look-back warp ----
+    for (int i = 0;; ++i) {
+      const int b = i & 1;
+      bar_sync(kBarFull + b, kEThreads);            // the workers walked their i-th tile
+      const long long t = tile_id[b];
+      if (t < 0) break;
+      const uint32_t total = tile_total[b];
+      const unsigned long long p = warp_lookback(state, t, total);
+      if ((threadIdx.x & 31) == 0) {
+        tile_prefix[b] = p;
+        if (t == ntiles - 1) {
+          gb.info[frame].total_bits = p + total;
+          gb.info[frame].head_byte = 0;      // stripe hand-over fields, set again by the stuffing kernel
+          gb.info[frame].tail_byte = 0;
+          gb.info[frame].tail_bits = 0;
+        }
+      }
+      __threadfence_block();
+      __syncwarp();
+      bar_arrive(kBarReady + b, kEThreads);
+    }
+    return;
   }
-  uint32_t total;
-  const uint32_t ex = cta_exclusive_scan(bits, scratch, &total);
-  if (threadIdx.x < 32) {
-    const unsigned long long p = warp_lookback(gb.bit_state + frame * gb.bit_state_pitch, blockIdx.x, total);
+
+  // ---- worker warps ----
+  uint32_t* stream = gb.words + frame * gb.words_pitch;
+  long long t_prev = -1;
+  for (int i = 0;; ++i) {
+    const int b = i & 1;
     if (threadIdx.x == 0) {
-      tile_prefix = p;
-      if (blockIdx.x == gridDim.x - 1) {
-        gb.info[frame].total_bits = p + total;
-        gb.info[frame].head_byte = 0;      // stripe hand-over fields, set again by the stuffing kernel
-        gb.info[frame].tail_byte = 0;
-        gb.info[frame].tail_bits = 0;
+      const unsigned long long claimed = atomicAdd(counter, 1ull);
+      tile_id[b] = (claimed < static_cast<unsigned long long>(ntiles)) ? static_cast<long long>(claimed) : -1;
+    }
+    bar_sync(kBarWorkers, kEWorkers);
+    const long long t = tile_id[b];
+    if (t >= 0) {
+      const size_t g = static_cast<size_t>(t) * kTileBlocks + threadIdx.x;
+      uint32_t* mine = local[b][threadIdx.x];
+      uint32_t bits = 0;
+      if (g < nb_blocks) {
+        const int k = block_in_mcu(g, fs.mcu_blocks);
+        const int c = (k >= fs.luma_blocks) ? 1 : 0;
+        const int16_t* blk = zz + g * 64;
+        const uint32_t mask = nzmask[g];
+        const PrefetchedChunkLoader loader = {blk, reinterpret_cast<const uint4*>(blk)[0], reinterpret_cast<const uint4*>(blk)[1]};
+        const int pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, dc_init);
+        const int dc = static_cast<int16_t>(loader.c0.x & 0xffffu);
+        LocalSink sink = {mine, 0, 0, 0, 0};
+        code_block(loader, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
+        sink.finish();
+        bits = sink.total;
+      }
+      uint32_t total;
+      const uint32_t ex = workers_exclusive_scan(bits, scratch, &total);
+      mine[kLocalWords] = ex | (bits << 20);        // ex < 256 * 1696 < 2^20, bits < 2^11
+      if (threadIdx.x == 0) tile_total[b] = total;
+    }
+    __threadfence_block();
+    bar_arrive(kBarFull + b, kEThreads);            // t < 0 tells the look-back warp to stop
+    if (t_prev >= 0) {
+      // ---- copy tile i-1 to the stream at its now known bit offset ----
+      const int pb = b ^ 1;
+      bar_sync(kBarReady + pb, kEThreads);
+      const size_t g = static_cast<size_t>(t_prev) * kTileBlocks + threadIdx.x;
+      if (g < nb_blocks) {
+        const uint32_t* mine = local[pb][threadIdx.x];
+        const uint32_t packed = mine[kLocalWords];
+        const uint32_t bits = packed >> 20;
+        const unsigned long long offset = tile_prefix[pb] + (packed & 0xfffffu);
+        const int nw = static_cast<int>((bits + 31) >> 5);
+        if (nw <= kLocalWords) {
+          // shifted copy; the first and the last stream word may be shared with the neighbouring
+          // blocks (OR), the others are owned
+          const int s = static_cast<int>(offset & 31);
+          uint32_t* dst = stream + (offset >> 5);
+          const int last = static_cast<int>((s + bits - 1) >> 5);   // index of the last stream word touched
+          uint32_t prev = 0;
+          for (int kk = 0; kk <= last; ++kk) {
+            const uint32_t cur = (kk < nw) ? mine[kk] : 0u;
+            const uint32_t v = __funnelshift_r(cur, prev, s);     // (prev << (32-s)) | (cur >> s)
+            prev = cur;
+            if (kk == 0 || kk == last) { if (v) atomicOr(&dst[kk], v); }
+            else dst[kk] = v;
+          }
+        } else {
+          // more than 512 bits: walk the block again, straight into the stream
+          const int k = block_in_mcu(g, fs.mcu_blocks);
+          const int c = (k >= fs.luma_blocks) ? 1 : 0;
+          const int16_t* blk = zz + g * 64;
+          StreamOut out = {stream};
+          BitPackSink<StreamOut> sink(out, offset);
+          code_block(ChunkLoader{blk}, nzmask[g], blk[0], dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, dc_init),
+                     sh.dc[c], sh.ac[c], sink);
+          sink.finish();
+        }
       }
     }
-  }
-  __syncthreads();
-  if (!valid) return;
-  uint32_t* stream = gb.words + frame * gb.words_pitch;
-  const unsigned long long offset = tile_prefix + ex;
-  if (nw <= kLocalWords) {
-    // copy the kept words to their place in the stream, shifted by the bit offset; the first and
-    // the last stream word may be shared with the neighbouring blocks (OR), the others are owned
-    const int s = static_cast<int>(offset & 31);
-    uint32_t* dst = stream + (offset >> 5);
-    const int last = static_cast<int>((s + bits - 1) >> 5);   // index of the last stream word touched
-    uint32_t prev = 0;
-    for (int kk = 0; kk <= last; ++kk) {
-      const uint32_t cur = (kk < nw) ? mine[kk] : 0u;
-      const uint32_t v = __funnelshift_r(cur, prev, s);     // (prev << (32-s)) | (cur >> s)
-      prev = cur;
-      if (kk == 0 || kk == last) { if (v) atomicOr(&dst[kk], v); }
-      else dst[kk] = v;
-    }
-  } else {
-    StreamOut out = {stream};
-    BitPackSink<StreamOut> sink(out, offset);
-    code_block(ChunkLoader{b}, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
-    sink.finish();
+    if (t < 0) break;
+    t_prev = t;
   }
 }
 
@@ -1226,7 +1342,12 @@ void LaunchSymbolStats(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t 
 }
 
 void LaunchEntropyPack(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {
-  entropy_pack_kernel<<<dim3(cdiv(fs.blocks_per_frame, kTileBlocks), fs.frames), kTileBlocks, 0, s>>>(fs, gb);
+  // persistent CTAs claiming tiles from a counter: about 5 CTAs per SM over all pictures of the group
+  const unsigned tiles = cdiv(fs.blocks_per_frame, kTileBlocks);
+  unsigned grid = 148 * 5 / (fs.frames > 0 ? fs.frames : 1);
+  if (grid < 1) grid = 1;
+  if (grid > tiles) grid = tiles;
+  entropy_pack_kernel<<<dim3(grid, fs.frames), kEThreads, 0, s>>>(fs, gb);
 }
 
 void LaunchLastDc(const FrameSet& fs, const GroupBuffers& gb, int* out, cudaStream_t s) {
