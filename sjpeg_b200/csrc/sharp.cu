@@ -98,30 +98,46 @@ sharp_refine_kernel(const __grid_constant__ SharpJob job) {
   unsigned seen = 0;                 // rows the previous iteration is known to have finished
   unsigned long long diff = 0;
 
-  for (int r = 0; r < uv_h; ++r) {
-    if (upstream != nullptr) {
-      const unsigned need = static_cast<unsigned>(min(r + 2, uv_h));
-      if (seen < need) {             // uniform across the CTA
-        if (threadIdx.x == 0) {
-          unsigned v;
-          do { v = ld_acquire(upstream); } while (v < need);
-          seen_shared = v;
-        }
-        __syncthreads();
-        seen = seen_shared;
-        __syncthreads();
-      }
+  // Row r of this iteration reads rows r, r+1 of the previous state.  The first cell of every
+  // thread is fetched one row ahead (everything but the row above, which is the critical path),
+  // so the wait on the upstream iteration covers row r+2.
+  auto wait_upstream = [&](int rows_needed) {
+    if (upstream == nullptr) return;
+    const unsigned need = static_cast<unsigned>(min(rows_needed, uv_h));
+    if (seen >= need) return;          // uniform across the CTA
+    if (threadIdx.x == 0) {
+      unsigned v;
+      do { v = ld_acquire(upstream); } while (v < need);
+      seen_shared = v;
     }
-    const size_t uv_row = static_cast<size_t>(r) * 3 * uv_w;
-    const int16_t* above = (r > 0) ? uv_mine + uv_row - 3 * uv_w : uv_prev;
+    __syncthreads();
+    seen = seen_shared;
+    __syncthreads();
+  };
+  auto load_row_cell = [&](int r, int i, SharpCellIn* in) {
+    const size_t uv_row = static_cast<size_t>(r) * 3 * uv_w, y_row = static_cast<size_t>(2 * r) * w;
     const int16_t* below = uv_prev + ((r < uv_h - 1) ? uv_row + 3 * uv_w : uv_row);
-    const size_t y_row = static_cast<size_t>(2 * r) * w;
-    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-      diff += sharp_refine_cell(t, ld, w, uv_w, i, y_prev + y_row, y_mine + y_row, above, /*above_is_own=*/false,
-                                uv_prev + uv_row, below, uv_mine + uv_row, job.target_y + y_row,
-                                job.target_uv + uv_row);
+    sharp_load_cell(ld, w, uv_w, i, y_prev + y_row, uv_prev + uv_row, below, job.target_y + y_row,
+                    job.target_uv + uv_row, in);
+  };
+  const int first = lo + static_cast<int>(threadIdx.x);
+  SharpCellIn ahead;
+  wait_upstream(2);
+  if (first < hi) load_row_cell(0, first, &ahead);
+  for (int r = 0; r < uv_h; ++r) {
+    const size_t uv_row = static_cast<size_t>(r) * 3 * uv_w, y_row = static_cast<size_t>(2 * r) * w;
+    const int16_t* above = (r > 0) ? uv_mine + uv_row - 3 * uv_w : uv_prev;
+    SharpCellIn in = ahead;
+    wait_upstream(r + 3);
+    for (int i = first; i < hi; i += blockDim.x) {
+      SharpCellAbove up;
+      sharp_load_above(ld, uv_w, i, above, &up);
+      if (i != first) load_row_cell(r, i, &in);
+      else if (r + 1 < uv_h) load_row_cell(r + 1, first, &ahead);     // in flight during the compute below
+      diff += sharp_refine_cell(t, w, uv_w, i, in, up, y_mine + y_row, uv_mine + uv_row);
     }
-    __threadfence();                 // this row is visible device-wide before anybody is told
+    // The row barrier releases this row to the other CTAs of the cluster; the release store of
+    // rank 0 then extends it (cumulatively) to the next iteration's cluster.
     row_barrier(nctas);
     if (rank == 0 && threadIdx.x == 0) st_release(job.progress + it, static_cast<unsigned>(r + 1));
   }

@@ -119,58 +119,79 @@ SJB_HD void sharp_import_cell(const SharpTabs& t, const uint8_t* rgb, long long 
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// One refinement step of chroma column i in chroma row r (the body of the iteration loop,
-// :636-653).  Rows are passed as pointers to their first element:
-//   y_in / y_out    luma state rows 2r (and 2r+1 at +w) of the previous / this iteration
-//   uv_above        chroma row r-1 of THIS iteration (r == 0: row 0 of the previous state)
-//   uv_cur, uv_below  chroma rows r and min(r+1, uv_h-1) of the previous state
-//   uv_out          chroma row r of this iteration
-// Returns the sum of |luma correction| of the four pixels (SharpUpdateY's return, :174-184).
-// Ld loads one sample of the previous iteration's state (a different CTA wrote it).
-// ---------------------------------------------------------------------------------------------
-template <class Ld>
-SJB_HD uint32_t sharp_refine_cell(const SharpTabs& t, const Ld& ld, int w, int uv_w, int i, const uint16_t* y_in,
-                                  uint16_t* y_out, const int16_t* uv_above, bool above_is_own, const int16_t* uv_cur,
-                                  const int16_t* uv_below, int16_t* uv_out, const uint16_t* target_y,
-                                  const int16_t* target_uv) {
-  const int im = (i > 0) ? i - 1 : 0, ip = (i < uv_w - 1) ? i + 1 : i;
+// Inputs of one cell, split by when they become available: everything that comes from the
+// previous iteration's state or from the targets can be fetched one row ahead; only `above`
+// (row r-1 of the iteration in progress) has to wait for the row barrier.
+struct SharpCellIn {
   int y_old[2][2];
+  int cur[3][3], below[3][3];     // [channel][i-1, i, i+1] (edge columns clamped)
+  int target_y[2][2], target_uv[3];
+};
+struct SharpCellAbove {
+  int v[3][3];
+};
+
+template <class Ld>
+SJB_HD void sharp_load_cell(const Ld& ld, int w, int uv_w, int i, const uint16_t* y_in, const int16_t* uv_cur,
+                            const int16_t* uv_below, const uint16_t* target_y, const int16_t* target_uv,
+                            SharpCellIn* in) {
+  const int im = (i > 0) ? i - 1 : 0, ip = (i < uv_w - 1) ? i + 1 : i;
   for (int dy = 0; dy < 2; ++dy) {
-    for (int dx = 0; dx < 2; ++dx) y_old[dy][dx] = ld.y(y_in + dy * w + 2 * i + dx);
+    for (int dx = 0; dx < 2; ++dx) {
+      in->y_old[dy][dx] = ld.y(y_in + dy * w + 2 * i + dx);
+      in->target_y[dy][dx] = ld.y(target_y + dy * w + 2 * i + dx);
+    }
   }
-  SharpCell c;
-  int cur0[3];
   for (int k = 0; k < 3; ++k) {
     const int16_t* A = uv_cur + k * uv_w;
-    const int16_t* P = uv_above + k * uv_w;
     const int16_t* N = uv_below + k * uv_w;
-    const int a_m = ld.uv(A + im), a_0 = ld.uv(A + i), a_p = ld.uv(A + ip);
-    const int n_m = ld.uv(N + im), n_0 = ld.uv(N + i), n_p = ld.uv(N + ip);
-    int p_m, p_0, p_p;
-    if (above_is_own) { p_m = P[im]; p_0 = P[i]; p_p = P[ip]; }
-    else { p_m = ld.uv(P + im); p_0 = ld.uv(P + i); p_p = ld.uv(P + ip); }
-    cur0[k] = a_0;
+    in->cur[k][0] = ld.uv(A + im); in->cur[k][1] = ld.uv(A + i); in->cur[k][2] = ld.uv(A + ip);
+    in->below[k][0] = ld.uv(N + im); in->below[k][1] = ld.uv(N + i); in->below[k][2] = ld.uv(N + ip);
+    in->target_uv[k] = ld.uv(target_uv + k * uv_w + i);
+  }
+}
+template <class Ld>
+SJB_HD void sharp_load_above(const Ld& ld, int uv_w, int i, const int16_t* uv_above, SharpCellAbove* a) {
+  const int im = (i > 0) ? i - 1 : 0, ip = (i < uv_w - 1) ? i + 1 : i;
+  for (int k = 0; k < 3; ++k) {
+    const int16_t* P = uv_above + k * uv_w;
+    a->v[k][0] = ld.uv(P + im); a->v[k][1] = ld.uv(P + i); a->v[k][2] = ld.uv(P + ip);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One refinement step of chroma column i in chroma row r (the body of the iteration loop,
+// :636-653): interpolate the 2x2 cell from the chroma rows above / here / below, convert it back
+// to W and chroma, and move the state by the distance to the targets.  y_out / uv_out = rows 2r
+// (and 2r+1 at +w) and r of THIS iteration's state.  Returns the sum of |luma correction| of the
+// four pixels (SharpUpdateY's return, :174-184).
+// ---------------------------------------------------------------------------------------------
+SJB_HD uint32_t sharp_refine_cell(const SharpTabs& t, int w, int uv_w, int i, const SharpCellIn& in,
+                                  const SharpCellAbove& above, uint16_t* y_out, int16_t* uv_out) {
+  SharpCell c;
+  for (int k = 0; k < 3; ++k) {
     int e, o;
-    sharp_upsample_pair(i, uv_w, a_m, a_0, a_p, p_m, p_0, p_p, &e, &o);
-    c.px[0][0][k] = sharp_clip_y(y_old[0][0] + e);
-    c.px[0][1][k] = sharp_clip_y(y_old[0][1] + o);
-    sharp_upsample_pair(i, uv_w, a_m, a_0, a_p, n_m, n_0, n_p, &e, &o);
-    c.px[1][0][k] = sharp_clip_y(y_old[1][0] + e);
-    c.px[1][1][k] = sharp_clip_y(y_old[1][1] + o);
+    sharp_upsample_pair(i, uv_w, in.cur[k][0], in.cur[k][1], in.cur[k][2], above.v[k][0], above.v[k][1], above.v[k][2],
+                        &e, &o);
+    c.px[0][0][k] = sharp_clip_y(in.y_old[0][0] + e);
+    c.px[0][1][k] = sharp_clip_y(in.y_old[0][1] + o);
+    sharp_upsample_pair(i, uv_w, in.cur[k][0], in.cur[k][1], in.cur[k][2], in.below[k][0], in.below[k][1],
+                        in.below[k][2], &e, &o);
+    c.px[1][0][k] = sharp_clip_y(in.y_old[1][0] + e);
+    c.px[1][1][k] = sharp_clip_y(in.y_old[1][1] + o);
   }
   int wy[2][2], uv[3];
   sharp_cell_targets(t, c, wy, uv);
   uint32_t diff = 0;
   for (int dy = 0; dy < 2; ++dy) {
     for (int dx = 0; dx < 2; ++dx) {
-      const int d = static_cast<int>(target_y[dy * w + 2 * i + dx]) - wy[dy][dx];
-      y_out[dy * w + 2 * i + dx] = static_cast<uint16_t>(sharp_clip_y(y_old[dy][dx] + d));
+      const int d = in.target_y[dy][dx] - wy[dy][dx];
+      y_out[dy * w + 2 * i + dx] = static_cast<uint16_t>(sharp_clip_y(in.y_old[dy][dx] + d));
       diff += static_cast<uint32_t>(d < 0 ? -d : d);
     }
   }
   for (int k = 0; k < 3; ++k) {   // SharpUpdateRGB :186-192 (int16 wrap-around kept)
-    uv_out[k * uv_w + i] = static_cast<int16_t>(cur0[k] + (static_cast<int>(target_uv[k * uv_w + i]) - uv[k]));
+    uv_out[k * uv_w + i] = static_cast<int16_t>(in.cur[k][1] + (in.target_uv[k] - uv[k]));
   }
   return diff;
 }

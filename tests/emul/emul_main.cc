@@ -273,8 +273,11 @@ void emul_sharp_yuv(const uint8_t* rgb, int width, int height, long long stride,
       const int16_t* above = (r > 0) ? uv_mine + row - 3 * uv_w : uv_prev;
       const int16_t* below = uv_prev + ((r < uv_h - 1) ? row + 3 * uv_w : row);
       for (int i = 0; i < uv_w; ++i) {
-        diff[it] += sharp_refine_cell(t, ld, w, uv_w, i, y_prev + y_row, y_mine + y_row, above, false, uv_prev + row,
-                                      below, uv_mine + row, ty.data() + y_row, tuv.data() + row);
+        SharpCellIn in;
+        SharpCellAbove up;
+        sharp_load_cell(ld, w, uv_w, i, y_prev + y_row, uv_prev + row, below, ty.data() + y_row, tuv.data() + row, &in);
+        sharp_load_above(ld, uv_w, i, above, &up);
+        diff[it] += sharp_refine_cell(t, w, uv_w, i, in, up, y_mine + y_row, uv_mine + row);
       }
     }
   }

@@ -301,7 +301,7 @@ def test_planar_and_semiplanar_inputs(gpu_ctx, kind):
 
 
 SHARP_SIZES = [(1, 1), (3, 7), (4, 4), (5, 5), (5, 4), (4, 9), (6, 5), (7, 7), (16, 16), (17, 33), (64, 48), (203, 117),
-               (256, 255), (640, 481), (1030, 64), (2050, 37), (4100, 21)]
+               (256, 255), (640, 481), (1030, 64), (2050, 37), (4100, 21), (8300, 9)]
 
 
 def _sharp_images(w, h, seed=5):
@@ -318,7 +318,7 @@ def _sharp_images(w, h, seed=5):
 def test_sharp_yuv_planes_bit_exact(gpu_ctx, size):
     """sjb_sharp_yuv (import -> pipelined refinement clusters -> finish; ApplySharpYUVConversion,
     yuv_convert.cc:671-695) vs the oracle, plane by plane; widths above 512 / 1024 / 2048 chroma
-    columns exercise clusters of 2, 4 and 8 CTAs."""
+    columns exercise clusters of 2, 4 and 8 CTAs, 8300 px more than one cell per thread."""
     w, h = size
     for name, rgb in _sharp_images(w, h):
         got = gpu_ctx.sharp_yuv(rgb, w, h, 3 * w)
