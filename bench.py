@@ -107,6 +107,39 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this rank to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host memory
+    is allocated, so that the staging buffers of the e2e leg are node-local (on a two-socket 8-GPU
+    box remote buffers cost host-to-device bandwidth).  SJPEG_B200_NUMA=0 disables it.  Returns a
+    short description for the JSON line."""
+    if os.environ.get("SJPEG_B200_NUMA", "1") == "0":
+        return "off"
+    try:
+        import pynvml as N
+        N.nvmlInit()
+        bus = N.nvmlDeviceGetPciInfo(N.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as fp:
+            node = int(fp.read().strip())
+        if node < 0:
+            return "node unknown"
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fp:
+            cpus = set()
+            for part in fp.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "node %d: no allowed cpus" % node
+        os.sched_setaffinity(0, cpus)
+        return "node %d, %d cpus" % (node, len(cpus))
+    except Exception as e:   # containers often hide sysfs; the bench works without it
+        return "unavailable (%s)" % type(e).__name__
+
+
 def cpu_reference_throughput(frames, seconds_budget=12.0):
     """Frame-parallel encode on all host cores with the reference's own code (oracle/_ref) or,
     if that library did not travel, the oracle port.  Returns (Mpix/s, kind, cores, sample)."""
@@ -177,6 +210,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the encode path has no CPU fallback")
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -267,6 +302,7 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N == 1 only) --------------------------------------------------
     cpu = None
     if world == 1:
+        os.sched_setaffinity(0, all_cpus)      # the CPU arm gets every host core again
         v, kind, cores, sample, _, _ = cpu_reference_throughput(frames[:4], seconds_budget=12.0)
         cpu = {"value": round(v, 2), "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample}
 
@@ -277,7 +313,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": n, "bytes_in_per_step_per_gpu": n * 3 * W * H,
                    "l2_policy": "inputs larger than L2 (16 distinct frames = 398 MB per rank)",
-                   "jpeg_bytes_frame0": int(jpeg_bytes), "bit_exact_vs_oracle": True, "parallelism": "frames sharded across ranks, no collective"},
+                   "jpeg_bytes_frame0": int(jpeg_bytes), "bit_exact_vs_oracle": True, "parallelism": "frames sharded across ranks, no collective",
+                   "numa_binding_rank0": numa},
         "e2e": {"value": round(e2e_value, 1), "unit": "Mpix/s", "h2d_bytes_per_step": n * 3 * W * H,
                 "d2h_bytes_per_step": int(sum(sizes)), "api": "sjb_encode_batch, pinned host input, host output"},
         "gpu_launches": int(launches),

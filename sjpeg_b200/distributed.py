@@ -60,6 +60,7 @@ class GpuStripeBackend:
         self.ctx, self.params = ctx, params
         self._s = C.c_void_p()
         self._n = 0
+        self._shape = None      # (n, width, stripe_height) of the open session
 
     def header(self, width, height):
         buf = (C.c_uint8 * 2048)()
@@ -72,10 +73,15 @@ class GpuStripeBackend:
     def transform(self, stripes, width, stripe_height, stride):
         """stripes: list of contiguous uint8 arrays (this rank's rows of each picture)."""
         n = len(stripes)
-        self.close()
-        rc = lib().sjb_stripes_create(self.ctx._ctx, n, width, stripe_height, C.byref(self.params), C.byref(self._s))
-        if rc != OK:
-            raise SjpegB200Error("sjb_stripes_create rc=%d" % rc)
+        if self._shape != (n, width, stripe_height):
+            # a session owns device buffers: keep it across calls of the same geometry (creating
+            # one costs several cudaMalloc / cudaFree, each a device-wide synchronisation)
+            self.close()
+            rc = lib().sjb_stripes_create(self.ctx._ctx, n, width, stripe_height, C.byref(self.params),
+                                          C.byref(self._s))
+            if rc != OK:
+                raise SjpegB200Error("sjb_stripes_create rc=%d" % rc)
+            self._shape = (n, width, stripe_height)
         self._n = n
         ptrs = (C.c_void_p * n)(*[s.ctypes.data for s in stripes])
         last = np.zeros((n, 3), np.int32)
@@ -111,6 +117,7 @@ class GpuStripeBackend:
         if self._s:
             lib().sjb_stripes_destroy(self._s)
             self._s = C.c_void_p()
+            self._shape = None
 
 
 # ------------------------------------------------------------------------------------------------
