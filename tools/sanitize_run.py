@@ -17,5 +17,20 @@ sizes = ctx.encode_batch([f.ctypes.data for f in frames], False, 320, 240, 960, 
                          [o.ctypes.data for o in outs], False, 1 << 18)
 for f, o, s in zip(frames, outs, sizes):
     ok &= o[:s].tobytes() == O.oracle_encode(f, 320, 240, 960, 75.0, 0, S.YUV_420)
+# whole-picture passes: sharp conversion (cluster of 2 CTAs at 1100 px), AUTO with the score table
+for (w, h) in ((66, 34), (1100, 20)):
+    rgb = O.make_rgb("A", w, h)
+    ok &= ctx.encode(rgb, w, h, 3 * w, S.default_params(75, 0, S.YUV_SHARP)) == \
+        O.oracle_encode(rgb, w, h, 3 * w, 75.0, 0, O.YUV_SHARP)
+table = O.score_table()
+if table is not None:
+    S.set_score_table(table)
+    rgb = O.make_rgb("A", 203, 117)
+    ok &= ctx.riskiness(rgb, 203, 117, 609) == O.oracle_riskiness(rgb, 203, 117, 609, table)
+# a picture with several entropy tiles per persistent CTA and blocks longer than the 512-bit slots
+rng = np.random.RandomState(2)
+noise = rng.randint(0, 256, (160, 1024, 3)).astype(np.uint8)
+ok &= ctx.encode(noise, 1024, 160, 3072, S.default_params(98, 0, S.YUV_444)) == \
+    O.oracle_encode(noise, 1024, 160, 3072, 98.0, 0, O.YUV_444)
 print("sanitize workload parity:", ok)
 ctx.close()
