@@ -212,7 +212,7 @@ int sjb_stage_symbol_stats(sjb_context* ctx, const uint8_t* pix, int width, int 
                            const sjb_params* params, uint32_t* freq_ac, uint32_t* freq_dc);
 
 /* Time (ms, CUDA events on the context's stream) of the kernels of the last sjb_encode call:
- * [0] F1 (all launches), [1] entropy stage (E1..E4), [2] whole device pipeline. */
+ * [0] F1 (all launches), [1] entropy stage (memset + E + S), [2] whole device pipeline. */
 int sjb_last_timings(const sjb_context* ctx, float ms[3]);
 
 /* Device-resident benchmark loop: encodes the n device pictures round-robin 'iters' times with

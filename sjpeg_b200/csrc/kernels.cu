@@ -9,8 +9,10 @@
 //   H1  coefficient histogram (methods >= 3), shared-memory privatised
 //   T1  trellis quantiser (methods 7, 8), one block per thread
 //   S1  Huffman symbol statistics (optimised tables)
-//   E   entropy stage in one pass: bits per block -> CTA scan -> decoupled look-back over tiles
-//       -> bit packing at the resulting offsets (replaces the serial bit writer)
+//   E   entropy stage in one pass, persistent and warp-specialised: worker warps walk the blocks
+//       of a tile (bits + packed words per block) -> scan -> a dedicated warp runs the decoupled
+//       look-back over the tiles of the picture while the workers walk the next tile -> bit
+//       packing at the resulting offsets (replaces the serial bit writer)
 //   S   0xFF byte stuffing in one pass: count -> CTA scan -> decoupled look-back -> scatter,
 //       padding and EOI
 // Every kernel takes a group of pictures (gridDim.y); see kernels.cuh.
@@ -76,7 +78,7 @@ __device__ __forceinline__ void store_block_natural(const int (&v)[64], int16_t*
 }
 
 // quantise (QuantTab) + zig-zag + non-zero chunk bitmap (bit c <=> the 16-byte chunk c != 0).
-// quantize.cc:288-320 without the run/level emission, which E1/E3 redo from the bitmap.
+// quantize.cc:288-320 without the run/level emission, which the entropy kernel redoes from the bitmap.
 // Tab supplies the constants of output pair p = zig-zag positions 2p, 2p+1.
 struct ParamTab {       // kernel-parameter (constant bank) table, compile-time offsets
   const QuantTab& t;

@@ -745,7 +745,7 @@ bool EncodeYUV420(const uint8_t* Y, int Y_stride, const uint8_t* U, int U_stride
   return EncodePlanar(Y, Y_stride, U, U_stride, V, V_stride, 1, SJPEG_YUV_420, width, height, param, output);
 }
 
-// Search hook (dichotomy.cc:41-75): kept for linkage; the multi-pass search itself is out of scope.
+// Search hook (dichotomy.cc:41-75): the default dichotomy the multi-pass search (engine.cu::EncodeSearch) calls back into.
 bool SearchHook::Setup(const EncoderParam& param) {
   for_size = (param.target_mode == EncoderParam::TARGET_SIZE);
   target = param.target_value;
