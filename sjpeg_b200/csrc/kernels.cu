@@ -747,7 +747,10 @@ struct StreamOut {
 
 // Per-thread sink of pass 1: counts the bits and, as long as they fit, keeps the packed words of
 // the block (bit 0 of the block = MSB of word 0) in a private shared-memory slot.
-enum { kLocalWords = 16 };            // 512 bits per block kept; longer blocks are re-walked
+#ifndef SJB_LOCAL_WORDS
+#define SJB_LOCAL_WORDS 16
+#endif
+enum { kLocalWords = SJB_LOCAL_WORDS };   // 32-bit words per block kept (512 bits); longer blocks are re-walked
 struct LocalSink {
   uint32_t* w;                        // slot of kLocalWords words
   uint64_t acc;
@@ -780,7 +783,7 @@ struct LocalSink {
 // do not wait: after walking tile i they hand (tile id, bit total) to the look-back warp and go on
 // to walk tile i+1 into the other half of the double-buffered slots; only then do they pick up
 // the prefix of tile i -- long since resolved -- and copy its words to the stream.
-enum { kEWorkers = kTileBlocks, kEThreads = kTileBlocks + 32 };
+enum { kEWorkers = kTileBlocks, kEThreads = kTileBlocks + 32, kECtasPerSm = (kTileBlocks >= 512) ? 3 : (kTileBlocks >= 256) ? 5 : 10 };
 enum { kBarWorkers = 1, kBarFull = 2 /* +buffer */, kBarReady = 4 /* +buffer */ };
 // barrier ids are immediates (a register id makes ptxas reserve all 16 hardware barriers per CTA,
 // which caps the SM at 4 CTAs)
@@ -839,7 +842,7 @@ __device__ __forceinline__ uint32_t workers_exclusive_scan(uint32_t v, uint32_t*
   return res;
 }
 
-__global__ void __launch_bounds__(kEThreads, 5)
+__global__ void __launch_bounds__(kEThreads, kECtasPerSm)
 entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   __shared__ __align__(16) CodeTabs sh;
   __shared__ uint32_t scratch[33];
@@ -1346,7 +1349,7 @@ void LaunchSymbolStats(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t 
 void LaunchEntropyPack(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {
   // persistent CTAs claiming tiles from a counter: about 5 CTAs per SM over all pictures of the group
   const unsigned tiles = cdiv(fs.blocks_per_frame, kTileBlocks);
-  unsigned grid = 148 * 5 / (fs.frames > 0 ? fs.frames : 1);
+  unsigned grid = 148 * kECtasPerSm / (fs.frames > 0 ? fs.frames : 1);
   if (grid < 1) grid = 1;
   if (grid > tiles) grid = tiles;
   entropy_pack_kernel<<<dim3(grid, fs.frames), kEThreads, 0, s>>>(fs, gb);
