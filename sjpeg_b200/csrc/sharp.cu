@@ -20,6 +20,7 @@
 #include "sharp.cuh"
 
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 namespace sjb {
 namespace {
@@ -146,6 +147,133 @@ sharp_refine_kernel(const __grid_constant__ SharpJob job) {
   if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = diff;
   __syncthreads();
   if (threadIdx.x == 0) {
+    unsigned long long s = 0;
+    for (int k = 0; k < static_cast<int>(blockDim.x >> 5); ++k) s += warp_sums[k];
+    atomicAdd(job.diff + it, s);
+  }
+}
+
+// Fast form for pictures up to 8192 pixels wide (one cell per thread).  Two things are taken off
+// the per-row critical path of the kernel above:
+//  * the row above travels through shared memory -- every thread leaves its new chroma in a
+//    double-buffered row in its CTA's shared memory and the two edge threads also drop theirs
+//    into the neighbouring CTAs' halo slots over distributed shared memory -- so the next row
+//    starts from a shared-memory read instead of an L2 round trip;
+//  * the global stores of a row (needed by the NEXT iteration's cluster and by the finish kernel,
+//    not by this one) are issued one row late, so the release at the row barrier finds them
+//    drained instead of waiting for them.  The progress counter accordingly lags one row.
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local, unsigned target_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+               : "=r"(r) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(local))), "r"(target_rank));
+  return r;
+}
+__device__ __forceinline__ void dsmem_store_s16(uint32_t addr, int v) {
+  asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<short>(v)) : "memory");
+}
+
+__global__ void __launch_bounds__(kSharpRefineThreads)
+sharp_refine_fast_kernel(const __grid_constant__ SharpJob job) {
+  __shared__ uint32_t g2l[kSharpMaxY + 1];
+  __shared__ uint32_t l2g[kSharpGammaTab + 2];
+  __shared__ unsigned long long warp_sums[kSharpRefineThreads / 32];
+  __shared__ unsigned seen_shared;
+  __shared__ int16_t rowbuf[2][3][kSharpRefineThreads + 2];   // [row parity][channel][halo | cells | halo]
+  load_tabs(job, g2l, l2g);
+  const SharpTabs t = {g2l, l2g};
+  const LdCg ld;
+  const int it = blockIdx.y, tid = threadIdx.x;
+  const unsigned nctas = cluster_size(), rank = cluster_rank();
+  const int w = job.w, uv_w = job.uv_w, uv_h = job.uv_h;
+  const int per = (uv_w + static_cast<int>(nctas) - 1) / static_cast<int>(nctas);   // <= blockDim.x
+  const int lo = static_cast<int>(rank) * per, hi = min(uv_w, lo + per);
+  const int i = lo + tid;
+  const bool valid = i < hi;
+  const bool feeds_left = valid && tid == 0 && rank > 0;                        // my cell is the left CTA's right halo
+  const bool feeds_right = valid && i == hi - 1 && rank + 1 < nctas && hi < uv_w;   // ... the right CTA's left halo
+  const size_t y_plane = static_cast<size_t>(w) * job.h, uv_plane = static_cast<size_t>(uv_w) * 3 * uv_h;
+  const uint16_t* y_prev = job.y_state + it * y_plane;
+  uint16_t* y_mine = job.y_state + (it + 1) * y_plane;
+  const int16_t* uv_prev = job.uv_state + it * uv_plane;
+  int16_t* uv_mine = job.uv_state + (it + 1) * uv_plane;
+  const unsigned* upstream = (it > 0) ? job.progress + (it - 1) : nullptr;
+  unsigned seen = 0;
+  unsigned long long diff = 0;
+
+  auto wait_upstream = [&](int rows_needed) {
+    if (upstream == nullptr) return;
+    const unsigned need = static_cast<unsigned>(min(rows_needed, uv_h));
+    if (seen >= need) return;          // uniform across the CTA
+    if (tid == 0) {
+      unsigned v;
+      do { v = ld_acquire(upstream); } while (v < need);
+      seen_shared = v;
+    }
+    __syncthreads();
+    seen = seen_shared;
+    __syncthreads();
+  };
+  auto load_row_cell = [&](int r, SharpCellIn* in) {
+    const size_t uv_row = static_cast<size_t>(r) * 3 * uv_w, y_row = static_cast<size_t>(2 * r) * w;
+    const int16_t* below = uv_prev + ((r < uv_h - 1) ? uv_row + 3 * uv_w : uv_row);
+    sharp_load_cell(ld, w, uv_w, i, y_prev + y_row, uv_prev + uv_row, below, job.target_y + y_row,
+                    job.target_uv + uv_row, in);
+  };
+  SharpCellIn ahead;
+  SharpCellOut pending;
+  row_barrier(nctas);                  // every CTA of the cluster is running before anyone writes into its halo
+  wait_upstream(2);
+  if (valid) load_row_cell(0, &ahead);
+  for (int r = 0; r < uv_h; ++r) {
+    const SharpCellIn in = ahead;
+    if (valid && r > 0) {              // last row's results: out to global memory, one row late
+      sharp_store_cell(w, uv_w, i, pending, y_mine + static_cast<size_t>(2 * (r - 1)) * w,
+                       uv_mine + static_cast<size_t>(r - 1) * 3 * uv_w);
+    }
+    wait_upstream(r + 3);
+    if (valid) {
+      SharpCellAbove up;
+      if (r == 0) {
+        sharp_load_above(ld, uv_w, i, uv_prev, &up);
+      } else {
+        const int16_t(*prev_row)[kSharpRefineThreads + 2] = rowbuf[(r - 1) & 1];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          up.v[k][1] = prev_row[k][tid + 1];
+          up.v[k][0] = (i > 0) ? prev_row[k][tid] : up.v[k][1];
+          up.v[k][2] = (i < uv_w - 1) ? prev_row[k][tid + 2] : up.v[k][1];
+        }
+      }
+      if (r + 1 < uv_h) load_row_cell(r + 1, &ahead);      // in flight during the compute below
+      sharp_refine_compute(t, uv_w, i, in, up, &pending);
+      diff += pending.diff;
+      int16_t(*row)[kSharpRefineThreads + 2] = rowbuf[r & 1];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) row[k][tid + 1] = static_cast<int16_t>(pending.uv_new[k]);
+      if (feeds_left) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dsmem_store_s16(dsmem_addr(&row[k][per + 1], rank - 1), pending.uv_new[k]);
+      }
+      if (feeds_right) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dsmem_store_s16(dsmem_addr(&row[k][0], rank + 1), pending.uv_new[k]);
+      }
+    }
+    row_barrier(nctas);
+    // rows < r are in global memory and released (cumulatively) by the barrier just passed
+    if (rank == 0 && tid == 0 && r > 0) st_release(job.progress + it, static_cast<unsigned>(r));
+  }
+  if (valid) {
+    sharp_store_cell(w, uv_w, i, pending, y_mine + static_cast<size_t>(2 * (uv_h - 1)) * w,
+                     uv_mine + static_cast<size_t>(uv_h - 1) * 3 * uv_w);
+  }
+  row_barrier(nctas);                  // also: nobody leaves while a neighbour may still write its halo
+  if (rank == 0 && tid == 0) st_release(job.progress + it, static_cast<unsigned>(uv_h));
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, d);
+  if ((tid & 31) == 0) warp_sums[tid >> 5] = diff;
+  __syncthreads();
+  if (tid == 0) {
     unsigned long long s = 0;
     for (int k = 0; k < static_cast<int>(blockDim.x >> 5); ++k) s += warp_sums[k];
     atomicAdd(job.diff + it, s);
@@ -310,7 +438,9 @@ cudaError_t LaunchSharpYuv(const uint8_t* rgb, long long stride, int width, int 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, sharp_refine_kernel, job);
+  // one cell per thread (pictures up to 8 x 512 x 2 = 8192 pixels wide): shared-memory row exchange
+  const bool fast = job.uv_w <= nctas * kSharpRefineThreads && getenv("SJB_SHARP_GENERIC") == nullptr;
+  e = fast ? cudaLaunchKernelEx(&cfg, sharp_refine_fast_kernel, job) : cudaLaunchKernelEx(&cfg, sharp_refine_kernel, job);
   if (e != cudaSuccess) return e;
   sharp_finish_kernel<<<cells, 256, 0, s>>>(job);
   if (launches) *launches += 3;

@@ -166,8 +166,13 @@ SJB_HD void sharp_load_above(const Ld& ld, int uv_w, int i, const int16_t* uv_ab
 // (and 2r+1 at +w) and r of THIS iteration's state.  Returns the sum of |luma correction| of the
 // four pixels (SharpUpdateY's return, :174-184).
 // ---------------------------------------------------------------------------------------------
-SJB_HD uint32_t sharp_refine_cell(const SharpTabs& t, int w, int uv_w, int i, const SharpCellIn& in,
-                                  const SharpCellAbove& above, uint16_t* y_out, int16_t* uv_out) {
+struct SharpCellOut {
+  int y_new[2][2];   // refined luma of the four pixels
+  int uv_new[3];     // refined chroma of the cell
+  uint32_t diff;     // sum of |luma correction|
+};
+SJB_HD void sharp_refine_compute(const SharpTabs& t, int uv_w, int i, const SharpCellIn& in,
+                                 const SharpCellAbove& above, SharpCellOut* out) {
   SharpCell c;
   for (int k = 0; k < 3; ++k) {
     int e, o;
@@ -182,18 +187,30 @@ SJB_HD uint32_t sharp_refine_cell(const SharpTabs& t, int w, int uv_w, int i, co
   }
   int wy[2][2], uv[3];
   sharp_cell_targets(t, c, wy, uv);
-  uint32_t diff = 0;
+  out->diff = 0;
   for (int dy = 0; dy < 2; ++dy) {
     for (int dx = 0; dx < 2; ++dx) {
       const int d = in.target_y[dy][dx] - wy[dy][dx];
-      y_out[dy * w + 2 * i + dx] = static_cast<uint16_t>(sharp_clip_y(in.y_old[dy][dx] + d));
-      diff += static_cast<uint32_t>(d < 0 ? -d : d);
+      out->y_new[dy][dx] = sharp_clip_y(in.y_old[dy][dx] + d);
+      out->diff += static_cast<uint32_t>(d < 0 ? -d : d);
     }
   }
   for (int k = 0; k < 3; ++k) {   // SharpUpdateRGB :186-192 (int16 wrap-around kept)
-    uv_out[k * uv_w + i] = static_cast<int16_t>(in.cur[k][1] + (in.target_uv[k] - uv[k]));
+    out->uv_new[k] = static_cast<int16_t>(in.cur[k][1] + (in.target_uv[k] - uv[k]));
   }
-  return diff;
+}
+SJB_HD void sharp_store_cell(int w, int uv_w, int i, const SharpCellOut& out, uint16_t* y_out, int16_t* uv_out) {
+  for (int dy = 0; dy < 2; ++dy) {
+    for (int dx = 0; dx < 2; ++dx) y_out[dy * w + 2 * i + dx] = static_cast<uint16_t>(out.y_new[dy][dx]);
+  }
+  for (int k = 0; k < 3; ++k) uv_out[k * uv_w + i] = static_cast<int16_t>(out.uv_new[k]);
+}
+SJB_HD uint32_t sharp_refine_cell(const SharpTabs& t, int w, int uv_w, int i, const SharpCellIn& in,
+                                  const SharpCellAbove& above, uint16_t* y_out, int16_t* uv_out) {
+  SharpCellOut out;
+  sharp_refine_compute(t, uv_w, i, in, above, &out);
+  sharp_store_cell(w, uv_w, i, out, y_out, uv_out);
+  return out.diff;
 }
 
 // Which iteration's state is the result: the loop of :628-660 always runs iterations 0 and 1 and
