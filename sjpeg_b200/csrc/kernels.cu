@@ -783,6 +783,9 @@ struct LocalSink {
 // do not wait: after walking tile i they hand (tile id, bit total) to the look-back warp and go on
 // to walk tile i+1 into the other half of the double-buffered slots; only then do they pick up
 // the prefix of tile i -- long since resolved -- and copy its words to the stream.
+#ifndef SJB_E_PREFETCH
+#define SJB_E_PREFETCH 1
+#endif
 enum { kEWorkers = kTileBlocks, kEThreads = kTileBlocks + 32, kECtasPerSm = (kTileBlocks >= 512) ? 3 : (kTileBlocks >= 256) ? 5 : 10 };
 enum { kBarWorkers = 1, kBarFull = 2 /* +buffer */, kBarReady = 4 /* +buffer */ };
 // barrier ids are immediates (a register id makes ptxas reserve all 16 hardware barriers per CTA,
@@ -846,7 +849,7 @@ __global__ void __launch_bounds__(kEThreads, kECtasPerSm)
 entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   __shared__ __align__(16) CodeTabs sh;
   __shared__ uint32_t scratch[33];
-  __shared__ long long tile_id[2];
+  __shared__ long long tile_id[2], next_id[2];
   __shared__ uint32_t tile_total[2];
   __shared__ unsigned long long tile_prefix[2];
   __shared__ uint32_t local[2][kTileBlocks][kLocalWords + 1];   // odd stride: conflict-free; word 16 = ex | bits << 20
@@ -887,15 +890,18 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
 
   // ---- worker warps ----
   uint32_t* stream = gb.words + frame * gb.words_pitch;
+  auto claim_tile = [&]() -> long long {
+    const unsigned long long claimed = atomicAdd(counter, 1ull);
+    return (claimed < static_cast<unsigned long long>(ntiles)) ? static_cast<long long>(claimed) : -1;
+  };
+  if (threadIdx.x == 0) next_id[1] = claim_tile();
+  bar_sync(kBarWorkers, kEWorkers);
+  long long t = next_id[1];
   long long t_prev = -1;
   for (int i = 0;; ++i) {
     const int b = i & 1;
-    if (threadIdx.x == 0) {
-      const unsigned long long claimed = atomicAdd(counter, 1ull);
-      tile_id[b] = (claimed < static_cast<unsigned long long>(ntiles)) ? static_cast<long long>(claimed) : -1;
-    }
-    bar_sync(kBarWorkers, kEWorkers);
-    const long long t = tile_id[b];
+    if (threadIdx.x == 0) tile_id[b] = t;           // for the look-back warp, published by the Full barrier
+    long long t_next = -1;
     if (t >= 0) {
       const size_t g = static_cast<size_t>(t) * kTileBlocks + threadIdx.x;
       uint32_t* mine = local[b][threadIdx.x];
@@ -913,10 +919,23 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
         sink.finish();
         bits = sink.total;
       }
+      if (threadIdx.x == 0) next_id[b] = claim_tile();   // broadcast by the barriers of the scan
       uint32_t total;
       const uint32_t ex = workers_exclusive_scan(bits, scratch, &total);
       mine[kLocalWords] = ex | (bits << 20);        // ex < 256 * 1696 < 2^20, bits < 2^11
       if (threadIdx.x == 0) tile_total[b] = total;
+      t_next = next_id[b];
+#if SJB_E_PREFETCH
+      if (t_next >= 0) {
+        // the next tile's first sector and bitmap byte start their way to L1 now and arrive while
+        // this tile's prefix is resolved and the previous tile is written out
+        const size_t gn = static_cast<size_t>(t_next) * kTileBlocks + threadIdx.x;
+        if (gn < nb_blocks) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(zz + gn * 64));
+          if ((threadIdx.x & 31) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(nzmask + gn));
+        }
+      }
+#endif
     }
     __threadfence_block();
     bar_arrive(kBarFull + b, kEThreads);            // t < 0 tells the look-back warp to stop
@@ -960,6 +979,7 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
     }
     if (t < 0) break;
     t_prev = t;
+    t = t_next;
   }
 }
 
