@@ -1055,7 +1055,7 @@ __device__ __forceinline__ uint32_t stream_byte(const uint4& w, int i) {   // by
   return (v >> (8 * (3 - (i & 3)))) & 0xffu;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kStuffThreads)
 stuff_kernel(GroupBuffers gb, const __grid_constant__ StuffArgs args) {
   __shared__ uint32_t scratch[33];
   __shared__ unsigned long long tile_prefix;
@@ -1382,10 +1382,10 @@ void LaunchLastDc(const FrameSet& fs, const GroupBuffers& gb, int* out, cudaStre
 void LaunchStuff(const FrameSet& fs, const GroupBuffers& gb, const StuffArgs& args, cudaStream_t s) {
   // persistent CTAs: all of them must be resident for the look-back to make progress
   const size_t max_tiles = (gb.words_pitch * 4 + kStuffTileBytes - 1) / kStuffTileBytes;
-  unsigned grid = 148 * 4 / (fs.frames > 0 ? fs.frames : 1);
+  unsigned grid = 148 * (1024 / kStuffThreads) / (fs.frames > 0 ? fs.frames : 1);
   if (grid < 1) grid = 1;
   if (grid > max_tiles) grid = static_cast<unsigned>(max_tiles);
-  stuff_kernel<<<dim3(grid, fs.frames), 256, 0, s>>>(gb, args);
+  stuff_kernel<<<dim3(grid, fs.frames), kStuffThreads, 0, s>>>(gb, args);
 }
 
 }  // namespace sjb

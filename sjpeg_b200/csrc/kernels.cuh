@@ -21,7 +21,10 @@ enum { kMaxGroup = 8 };
 // stuffing per 4 pictures: 128 -> 71 us (twice the tiles in the look-back chain), 256 -> 56 us, 512 with 256-bit
 // slots -> 54 us but 30 % slower on busy pictures (more blocks overflow the slots); 256 is the default.
 enum { kTileBlocks = SJB_TILE_BLOCKS };
-enum { kStuffTileBytes = 4096 };   // stream bytes per CTA iteration in the stuffing kernel
+#ifndef SJB_STUFF_THREADS
+#define SJB_STUFF_THREADS 256
+#endif
+enum { kStuffThreads = SJB_STUFF_THREADS, kStuffTileBytes = 16 * kStuffThreads };   // stream bytes per CTA iteration of the stuffing kernel
 
 struct FrameSet {
   const uint8_t* pix[kMaxGroup];   // row 0 of each picture (packed RGB/RGBA/BGRA, or the Y plane)
