@@ -21,6 +21,7 @@
 
 #include "../../include/sjpeg_b200.h"
 #include "host_codec.h"
+#include "host_stager.h"
 #include "kernels.cuh"
 #include "sharp.cuh"
 
@@ -116,6 +117,8 @@ struct sjb_context {
   DeviceBuffer sharp_scratch, sharp_planes, sharp_tabs, risk_table, risk_sums;
   unsigned long long* risk_host = nullptr;   // pinned, 3 sums
   int risk_table_version = 0;                // version of the process-wide table held in risk_table
+  HostStager stager;                         // threaded upload of pageable pictures (host_stager.h)
+  bool many_uploads = false;                 // set by the batch / stripe entry points: uploads come back to back
 };
 
 namespace {
@@ -228,6 +231,21 @@ int ReserveLane(sjb_context* ctx, Lane* L, const Plan& plan, int frames) {
   return SJB_OK;
 }
 
+struct ManyUploads {     // scope guard for sjb_context::many_uploads
+  sjb_context* ctx;
+  bool before;
+  ManyUploads(sjb_context* c, bool on) : ctx(c), before(c->many_uploads) { c->many_uploads = on; }
+  ~ManyUploads() { ctx->many_uploads = before; }
+};
+
+bool StagerEnabled() {
+  static const bool on = [] {
+    const char* e = getenv("SJPEG_B200_STAGER");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
+}
+
 size_t PixSlotBytes(const Plan& plan, long long stride) {
   const size_t row_bytes = static_cast<size_t>(plan.pstep) * plan.g.width;
   const size_t astride = static_cast<size_t>(stride < 0 ? -stride : stride);
@@ -255,7 +273,24 @@ int UploadPicture(sjb_context* ctx, Lane* L, const uint8_t* pix, const Plan& pla
   if (static_cast<size_t>(astride) <= 2 * row_bytes + 64) {
     // one contiguous span, stride kept (sign included)
     const size_t span = static_cast<size_t>(astride) * (h - 1) + row_bytes;
-    CU(cudaMemcpyAsync(base, lowest, span, cudaMemcpyHostToDevice, L->stream));
+    bool staged = false;
+    // Waking the helper threads costs ~0.1 ms: worth it from 4K pictures up for a lone call, from
+    // 4 MB up when the uploads of a batch follow each other (measured: 1080p alone 0.45 ms through
+    // the driver vs 0.54 ms staged; 64 x 1080p in a batch 3.0 vs 6.6 Gpix/s; 8K alone 9.0 vs 3.6 ms).
+    const size_t min_bytes = ctx->many_uploads ? HostStager::kMinBytes : 4 * HostStager::kMinBytes;
+    if (span >= min_bytes && StagerEnabled()) {
+      // malloc()ed memory (the normal case behind SjpegEncode): copy out through the pinned ring
+      // with helper threads instead of the driver's single-threaded pageable path
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, lowest) == cudaSuccess && attr.type == cudaMemoryTypeUnregistered) {
+        const cudaError_t e = ctx->stager.Upload(base, lowest, span, L->stream);
+        if (e == cudaSuccess) staged = true;
+        else if (e != cudaErrorNotSupported) CU(e);
+      } else {
+        cudaGetLastError();
+      }
+    }
+    if (!staged) CU(cudaMemcpyAsync(base, lowest, span, cudaMemcpyHostToDevice, L->stream));
     *d_row0 = base + ((stride < 0) ? static_cast<size_t>(astride) * (h - 1) : 0);
     *d_stride = stride;
   } else {
@@ -860,6 +895,7 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
   for (int i = 0; i < n; ++i) if (pix[i] == nullptr) return SJB_ERR_ARG;
   if (n == 0) return SJB_OK;
   CU(cudaSetDevice(ctx->device));
+  const ManyUploads back_to_back(ctx, n > 1);
   const int B = std::max(1, std::min(plan.group, n));
   const int groups = (n + B - 1) / B;
   const int nl = std::min<int>(kMaxLanes, std::max(1, groups));
@@ -1452,6 +1488,7 @@ int sjb_stripes_transform(sjb_stripes* s, const uint8_t* const* pix, int pix_on_
   s->plan = plan;
   s->stride = stride;
   CU(cudaSetDevice(ctx->device));
+  const ManyUploads back_to_back(ctx, s->n > 1);
   const int groups = (s->n + kMaxGroup - 1) / kMaxGroup;
   while (static_cast<int>(s->sets.size()) < groups) {
     Lane* L = new (std::nothrow) Lane();

@@ -1,0 +1,71 @@
+// host_stager.h -- host-to-device upload of PAGEABLE memory through a pinned ring, with the
+// host-side copy spread over a few helper threads.
+//
+// Why: the drop-in entry points (SjpegEncode, sjpeg::Encode; /root/reference/src/sjpeg.h:104,280)
+// receive whatever buffer the caller has, normally malloc()ed.  cudaMemcpyAsync from pageable
+// memory is staged by the driver on the calling thread at about 19 GB/s on the B200 boxes (24.9 MB
+// of 4K RGB: 1.3 ms), while the device pipeline for that picture takes 0.06 ms, so the copy IS
+// the call.  Here the picture is cut into chunks; the caller and kHelpers helper threads copy
+// each chunk into pinned memory together -- in 128 KB pieces claimed from a shared cursor, so the
+// caller never waits for a helper that is still waking up -- and the DMA of chunk c overlaps the
+// host copy of chunk c+1.  Pinned / registered / managed sources never come here (engine.cu checks the
+// pointer's type first).
+//
+// One stager per context; a context is used by one thread at a time (include/sjpeg_b200.h), so
+// Upload() is never entered concurrently.  The helpers spin only while an upload is running and
+// sleep on a condition variable otherwise.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
+namespace sjb {
+
+class HostStager {
+ public:
+  enum { kHelpers = 3, kSlots = 4 };
+  static constexpr size_t kChunk = 2u << 20;       // bytes per pinned slot
+  static constexpr size_t kPiece = 128u << 10;     // unit of work claimed by a thread
+  static constexpr size_t kMinBytes = 4u << 20;    // below this the driver's own path is as good
+
+  HostStager() = default;
+  ~HostStager();
+  HostStager(const HostStager&) = delete;
+  HostStager& operator=(const HostStager&) = delete;
+
+  // Asynchronous on `stream` like cudaMemcpyAsync, except that the SOURCE may be reused as soon
+  // as the call returns (it has been copied out).  Returns cudaErrorNotSupported when the stager
+  // could not be set up (no threads / no pinned memory): the caller falls back to cudaMemcpyAsync.
+  cudaError_t Upload(void* dst_device, const void* src_host, size_t bytes, cudaStream_t stream);
+
+ private:
+  bool Start();
+  void HelperLoop(int id);
+  void CopyChunk(uint8_t* dst, const uint8_t* src, size_t bytes);
+
+  bool started_ = false, failed_ = false;
+  uint8_t* pinned_ = nullptr;                       // kSlots * kChunk
+  cudaEvent_t slot_free_[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  std::thread helpers_[kHelpers];
+
+  // sleeping / waking
+  std::mutex mutex_;
+  std::condition_variable wake_;
+  bool active_ = false, quit_ = false;
+  // One chunk job at a time; cursor_ packs (ticket, pieces, next piece), see host_stager.cc.
+  std::atomic<unsigned long long> cursor_{0};
+  std::atomic<unsigned> pieces_done_{0};
+  std::atomic<bool> spinning_{false};
+  unsigned ticket_ = 0;
+  void Work();
+  uint8_t* job_dst_ = nullptr;
+  const uint8_t* job_src_ = nullptr;
+  size_t job_bytes_ = 0;
+};
+
+}  // namespace sjb

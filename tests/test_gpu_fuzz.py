@@ -81,3 +81,31 @@ def test_random_configurations_bit_exact(gpu_ctx):
                                      pad=pad, lead=lead, flip=flip)
     finally:
         S.set_score_table(None)
+
+
+def test_pageable_upload_through_the_stager(gpu_ctx):
+    """Pictures of 4 MB and more in ordinary (pageable) numpy memory go through the threaded pinned
+    ring of csrc/host_stager.cc; sizes that are not multiples of the 128 KB pieces / 2 MB chunks,
+    back-to-back calls that reuse ring slots while their DMA is still in flight, and a bottom-up
+    picture.  Bytes must equal the oracle's every time."""
+    import sjpeg_b200 as S
+    rng = np.random.RandomState(77)
+    p = S.default_params(75, 0, S.YUV_420)
+    cases = [(1366, 1025), (1920, 1080), (2731, 1537), (3840, 2160), (4099, 2309)]
+    for rep in range(3):
+        for (w, h) in cases:
+            rgb = rng.randint(0, 256, (h, w, 3)).astype(np.uint8) if rep == 0 else O.make_rgb("B", w, h, 100 + rep)
+            assert rgb.nbytes >= 4 << 20
+            want = O.oracle_encode(rgb, w, h, 3 * w, 75.0, 0, O.YUV_420)
+            assert gpu_ctx.encode(rgb, w, h, 3 * w, p) == want, (rep, w, h)
+            if rep == 2:
+                flipped = np.ascontiguousarray(rgb[::-1])
+                base = flipped.ctypes.data + (h - 1) * 3 * w
+                assert gpu_ctx.encode(flipped, w, h, -3 * w, p, base=base) == want, ("flip", w, h)
+    # batch API: 24 pageable 1080p frames back to back over the lanes
+    frames = [O.make_rgb("B", 1920, 1080, 500 + f) for f in range(24)]
+    outs = [np.empty(1 << 20, np.uint8) for _ in frames]
+    sizes = gpu_ctx.encode_batch([f.ctypes.data for f in frames], False, 1920, 1080, 5760, p,
+                                 [o.ctypes.data for o in outs], False, 1 << 20)
+    for f, o, n in zip(frames, outs, sizes):
+        assert o[:n].tobytes() == O.oracle_encode(f, 1920, 1080, 5760, 75.0, 0, O.YUV_420)
