@@ -664,6 +664,29 @@ __device__ __forceinline__ int block_in_mcu(size_t g, int mcu_blocks) {
   return (mcu_blocks == 6) ? static_cast<int>(gg % 6u) : (mcu_blocks == 3) ? static_cast<int>(gg % 3u) : 0;
 }
 
+// Position inside a tile of `count` consecutive blocks starting at global block `first` of the
+// block that worker `i` walks: the tile's luma blocks in order, then its chroma blocks.  Blocks
+// are stored MCU by MCU, `lb` luma blocks then `mb - lb` chroma blocks (6/4 for 4:2:0, 3/1 for
+// 4:4:4; 4:0:0 has no chroma and keeps the identity).
+__device__ __forceinline__ uint32_t walk_order(uint32_t first, uint32_t count, uint32_t i, int mcu_blocks) {
+  if (mcu_blocks == 1) return i;
+  uint32_t g;
+  if (mcu_blocks == 6) {
+    const uint32_t l0 = (first / 6u) * 4u + min(first % 6u, 4u);                     // luma blocks before the tile
+    const uint32_t end = first + count;
+    const uint32_t nl = (end / 6u) * 4u + min(end % 6u, 4u) - l0;                    // luma blocks in the tile
+    if (i < nl) { const uint32_t k = l0 + i; g = (k / 4u) * 6u + (k % 4u); }
+    else { const uint32_t k = (first - l0) + (i - nl); g = (k / 2u) * 6u + 4u + (k % 2u); }
+  } else {
+    const uint32_t l0 = (first / 3u) + min(first % 3u, 1u);
+    const uint32_t end = first + count;
+    const uint32_t nl = (end / 3u) + min(end % 3u, 1u) - l0;
+    if (i < nl) { g = (l0 + i) * 3u; }
+    else { const uint32_t k = (first - l0) + (i - nl); g = (k / 2u) * 3u + 1u + (k % 2u); }
+  }
+  return g - first;
+}
+
 // Decoupled look-back (single-pass chained scan).  One 64-bit descriptor per tile:
 // [63:62] state (0 = not ready, 1 = tile aggregate, 2 = inclusive prefix), [61:0] value; the
 // value travels in the same word as the flag, so no fence is needed.  Executed by one full warp;
@@ -788,6 +811,7 @@ struct LocalSink {
 #endif
 enum { kEWorkers = kTileBlocks, kEThreads = kTileBlocks + 32, kECtasPerSm = (kTileBlocks >= 512) ? 3 : (kTileBlocks >= 256) ? 5 : 10 };
 enum { kBarWorkers = 1, kBarFull = 2 /* +buffer */, kBarReady = 4 /* +buffer */ };
+enum { kBusyTileBits = 32 * kTileBlocks };   // above 32 bits per block on average a tile counts as busy
 // barrier ids are immediates (a register id makes ptxas reserve all 16 hardware barriers per CTA,
 // which caps the SM at 4 CTAs)
 template <int kId>
@@ -898,15 +922,32 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   bar_sync(kBarWorkers, kEWorkers);
   long long t = next_id[1];
   long long t_prev = -1;
+  uint32_t prev_total = 0;
   for (int i = 0;; ++i) {
     const int b = i & 1;
     if (threadIdx.x == 0) tile_id[b] = t;           // for the look-back warp, published by the Full barrier
     long long t_next = -1;
+    // Busy tiles are walked luma blocks first (below); sparse ones keep thread i on block i, which
+    // needs neither the index arithmetic nor the two extra barriers.  The previous tile's bit count
+    // decides (neighbouring tiles look alike); it is the same in every worker.
+    const bool regroup = prev_total > kBusyTileBits;
+    // slot j of this buffer is about to be refilled by whichever thread walks block j, which is not
+    // the thread that has just copied tile i-2 out of it: everybody must be done with that copy
+    if (regroup && i >= 2) bar_sync(kBarWorkers, kEWorkers);
     if (t >= 0) {
-      const size_t g = static_cast<size_t>(t) * kTileBlocks + threadIdx.x;
-      uint32_t* mine = local[b][threadIdx.x];
-      uint32_t bits = 0;
-      if (g < nb_blocks) {
+      // Which block of the tile this thread walks: luma blocks first, chroma blocks after them,
+      // so that the 32 walks of a warp have similar lengths (luma blocks carry several times the
+      // non-zeros of chroma blocks; interleaved as they are stored, a warp ran at 39 % lane
+      // efficiency on busy pictures).  Slots stay indexed by block, and the scan and the copy to
+      // the stream below run in block order with the identity mapping.
+      const uint32_t first = static_cast<uint32_t>(t) * kTileBlocks;
+      const uint32_t count = min(static_cast<uint32_t>(kTileBlocks), static_cast<uint32_t>(nb_blocks) - first);
+      if (threadIdx.x >= count) {
+        local[b][threadIdx.x][kLocalWords] = 0;
+      } else {
+        const uint32_t j = regroup ? walk_order(first, count, threadIdx.x, fs.mcu_blocks) : threadIdx.x;
+        const size_t g = static_cast<size_t>(first) + j;
+        uint32_t* mine = local[b][j];
         const int k = block_in_mcu(g, fs.mcu_blocks);
         const int c = (k >= fs.luma_blocks) ? 1 : 0;
         const int16_t* blk = zz + g * 64;
@@ -917,13 +958,17 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
         LocalSink sink = {mine, 0, 0, 0, 0};
         code_block(loader, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
         sink.finish();
-        bits = sink.total;
+        mine[kLocalWords] = sink.total;
       }
-      if (threadIdx.x == 0) next_id[b] = claim_tile();   // broadcast by the barriers of the scan
+      if (threadIdx.x == 0) next_id[b] = claim_tile();   // broadcast by the barriers below
+      if (regroup) bar_sync(kBarWorkers, kEWorkers);     // every slot of the tile is filled
+      uint32_t* mine = local[b][threadIdx.x];            // from here on: thread i <-> block i of the tile
+      const uint32_t bits = mine[kLocalWords];
       uint32_t total;
       const uint32_t ex = workers_exclusive_scan(bits, scratch, &total);
       mine[kLocalWords] = ex | (bits << 20);        // ex < 256 * 1696 < 2^20, bits < 2^11
       if (threadIdx.x == 0) tile_total[b] = total;
+      prev_total = total;
       t_next = next_id[b];
 #if SJB_E_PREFETCH
       if (t_next >= 0) {
