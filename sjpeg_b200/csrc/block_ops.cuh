@@ -218,11 +218,11 @@ SJB_HD uint32_t chunk_nonzero_bits(const Words4& q) {
   return m;
 }
 
-// The walk has two phases so that the lanes of a warp stay converged: first the 64-bit map of
-// non-zero positions is assembled from the chunks the bitmap names (a short loop, usually one or
-// two chunks), then ONE loop iteration per non-zero coefficient emits its run/size symbol -- the
-// trip count of a warp is the largest number of non-zeros among its 32 blocks, not the number of
-// (chunk, slot) pairs any of them touches.  Loader: operator()(chunk) -> Words4, value(pos) -> the
+// The walk has two phases so that the lanes of a warp stay converged: first the map of non-zero
+// positions (two 32-bit words) is assembled from the chunks the bitmap names (a short loop,
+// usually one or two chunks), then ONE loop iteration per non-zero coefficient emits its run/size
+// symbol -- the trip count of a warp is the largest number of non-zeros among its 32 blocks (per
+// half of the block), not the number of (chunk, slot) pairs any of them touches.  Loader: operator()(chunk) -> Words4, value(pos) -> the
 // quantised value at zig-zag position pos.
 template <class Loader, class Sink>
 SJB_HD void code_block(Loader load, uint32_t chunkmask, int dc, int dc_pred, const uint32_t* dc_codes,
@@ -236,29 +236,35 @@ SJB_HD void code_block(Loader load, uint32_t chunkmask, int dc, int dc_pred, con
     // code then n suffix bits; at most 16 + 11 bits
     sink.put(((c >> 16) << n) | bits, (int)(c & 0xff) + n);
   }
-  uint64_t nz = 0;
+  // positions 0..31 and 32..63 as two 32-bit maps: cheaper to scan than one 64-bit word
+  uint32_t nz_lo = 0, nz_hi = 0;
   for (uint32_t m = chunkmask; m; m &= m - 1) {
     const int c = find_first_set32(m);
-    nz |= (uint64_t)chunk_nonzero_bits(load(c)) << (8 * c);
+    const uint32_t b8 = chunk_nonzero_bits(load(c)) << (8 * (c & 3));
+    if (c < 4) nz_lo |= b8; else nz_hi |= b8;
   }
-  nz &= ~(uint64_t)1;                      // position 0 is the DC
+  nz_lo &= ~1u;                            // position 0 is the DC
   const uint32_t zrl = ac_codes[0xf0];
   int prev = 0;                            // zig-zag position of the previous non-zero (0 = DC slot)
-  while (nz) {
-    const int pos = find_first_set64(nz);
-    nz &= nz - 1;
-    const int v = load.value(pos);
-    int run = pos - prev - 1;
-    prev = pos;
-    while (run >= 16) {                    // ZRL escapes, entropy.cc:176-179
-      sink.put(zrl >> 16, (int)(zrl & 0xff));
-      run -= 16;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int half = 0; half < 2; ++half) {
+    for (uint32_t m = half ? nz_hi : nz_lo; m; m &= m - 1) {
+      const int pos = 32 * half + find_first_set32(m);
+      const int v = load.value(pos);
+      int run = pos - prev - 1;
+      prev = pos;
+      while (run >= 16) {                  // ZRL escapes, entropy.cc:176-179
+        sink.put(zrl >> 16, (int)(zrl & 0xff));
+        run -= 16;
+      }
+      int n;
+      uint32_t bits;
+      size_and_bits(v, &n, &bits);
+      const uint32_t c = ac_codes[(run << 4) | n];
+      sink.put(((c >> 16) << n) | bits, (int)(c & 0xff) + n);
     }
-    int n;
-    uint32_t bits;
-    size_and_bits(v, &n, &bits);
-    const uint32_t c = ac_codes[(run << 4) | n];
-    sink.put(((c >> 16) << n) | bits, (int)(c & 0xff) + n);
   }
   if (prev < 63) {                         // EOB, entropy.cc:195-197
     const uint32_t c = ac_codes[0x00];

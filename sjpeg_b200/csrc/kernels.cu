@@ -635,18 +635,36 @@ struct ChunkLoader {   // chunk c of a block = zig-zag positions 8c..8c+7, one 1
 };
 // Same, with the first two chunks (one 32-byte sector: where the low frequencies live) fetched
 // eagerly together with the bitmap and the predictor, so that a typical block needs a single
-// round trip to memory instead of a dependent chain.
+// round trip to memory instead of a dependent chain.  The block's address is held as an opaque
+// 64-bit register and dereferenced with explicit ld.global: left to itself, ptxas (capped at 40
+// registers here) rematerialises the whole address chain -- frame pitch, tile, block -- for every
+// coefficient fetched in the walk.
 struct PrefetchedChunkLoader {
-  const int16_t* p;
+  unsigned long long addr;    // global address of the block's 64 coefficients
   uint4 c0, c1;
+  __device__ __forceinline__ explicit PrefetchedChunkLoader(const int16_t* p) {
+    addr = static_cast<unsigned long long>(__cvta_generic_to_global(p));
+    asm volatile("" : "+l"(addr));
+    c0 = chunk(0);
+    c1 = chunk(1);
+  }
+  __device__ __forceinline__ uint4 chunk(int c) const {
+    uint4 q;
+    asm("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(addr + 16ull * c));
+    return q;
+  }
   __device__ __forceinline__ Words4 operator()(int c) const {
-    const uint4 q = (c == 0) ? c0 : (c == 1) ? c1 : reinterpret_cast<const uint4*>(p)[c];
+    const uint4 q = (c == 0) ? c0 : (c == 1) ? c1 : chunk(c);
     Words4 r;
     r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
     return r;
   }
   // the 128-byte line of the block is in L1 by now (its first sector was fetched up front)
-  __device__ __forceinline__ int value(int pos) const { return p[pos]; }
+  __device__ __forceinline__ int value(int pos) const {
+    short v;
+    asm("ld.global.s16 %0, [%1];" : "=h"(v) : "l"(addr + 2ull * pos));
+    return v;
+  }
 };
 
 __device__ __forceinline__ void load_code_tables(const CodeTabs* tabs, CodeTabs* sh) {
@@ -952,7 +970,7 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
         const int c = (k >= fs.luma_blocks) ? 1 : 0;
         const int16_t* blk = zz + g * 64;
         const uint32_t mask = nzmask[g];
-        const PrefetchedChunkLoader loader = {blk, reinterpret_cast<const uint4*>(blk)[0], reinterpret_cast<const uint4*>(blk)[1]};
+        const PrefetchedChunkLoader loader(blk);
         const int pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, dc_init);
         const int dc = static_cast<int16_t>(loader.c0.x & 0xffffu);
         LocalSink sink = {mine, 0, 0, 0, 0};
