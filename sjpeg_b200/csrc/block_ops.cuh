@@ -250,9 +250,19 @@ SJB_HD void code_block(Loader load, uint32_t chunkmask, int dc, int dc_pred, con
 #pragma unroll
 #endif
   for (int half = 0; half < 2; ++half) {
-    for (uint32_t m = half ? nz_hi : nz_lo; m; m &= m - 1) {
-      const int pos = 32 * half + find_first_set32(m);
-      const int v = load.value(pos);
+    uint32_t m = half ? nz_hi : nz_lo;
+    if (m == 0) continue;
+    // software pipeline: the value of the NEXT non-zero is requested before this one is coded
+    int next_pos = 32 * half + find_first_set32(m);
+    int next_v = load.value(next_pos);
+    while (m) {
+      const int pos = next_pos;
+      const int v = next_v;
+      m &= m - 1;
+      if (m) {
+        next_pos = 32 * half + find_first_set32(m);
+        next_v = load.value(next_pos);
+      }
       int run = pos - prev - 1;
       prev = pos;
       while (run >= 16) {                  // ZRL escapes, entropy.cc:176-179
