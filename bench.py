@@ -280,6 +280,26 @@ def run_ours(args):
     if bytes(out0) != want:
         raise SystemExit("bench.py: batch output differs from the oracle")
 
+    # what the host->device link itself delivers on this box (bare pinned copy of one step's input),
+    # so that the reader can see how far e2e is from the PCIe ceiling
+    link_gbs = None
+    try:
+        nbytes = n * 3 * W * H
+        hbuf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        dbuf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        best = None
+        for _ in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dbuf.copy_(hbuf, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        link_gbs = round(nbytes / best / 1e9, 2)
+        del hbuf, dbuf
+    except Exception:
+        pass
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -316,7 +336,9 @@ def run_ours(args):
                    "jpeg_bytes_frame0": int(jpeg_bytes), "bit_exact_vs_oracle": True, "parallelism": "frames sharded across ranks, no collective",
                    "numa_binding_rank0": numa},
         "e2e": {"value": round(e2e_value, 1), "unit": "Mpix/s", "h2d_bytes_per_step": n * 3 * W * H,
-                "d2h_bytes_per_step": int(sum(sizes)), "api": "sjb_encode_batch, pinned host input, host output"},
+                "d2h_bytes_per_step": int(sum(sizes)), "api": "sjb_encode_batch, pinned host input, host output",
+                "h2d_gbs_achieved": round(n * 3 * W * H * args.steps * world / float(t.item()) / 1e9 / world, 2),
+                "h2d_gbs_bare_copy": link_gbs},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "f1_fast_kernel<420> (convert+fDCT+quantise)",
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
