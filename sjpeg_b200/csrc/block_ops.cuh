@@ -353,4 +353,29 @@ struct BitPackSink {
   }
 };
 
+SJB_HD uint32_t sjb_minu(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+// Position inside a tile of `count` consecutive blocks starting at global block `first` of the
+// block that worker `i` walks: the tile's luma blocks in order, then its chroma blocks.  Blocks
+// are stored MCU by MCU, `lb` luma blocks then `mb - lb` chroma blocks (6/4 for 4:2:0, 3/1 for
+// 4:4:4; 4:0:0 has no chroma and keeps the identity).
+SJB_HD uint32_t walk_order(uint32_t first, uint32_t count, uint32_t i, int mcu_blocks) {
+  if (mcu_blocks == 1) return i;
+  uint32_t g;
+  if (mcu_blocks == 6) {
+    const uint32_t l0 = (first / 6u) * 4u + sjb_minu(first % 6u, 4u);                     // luma blocks before the tile
+    const uint32_t end = first + count;
+    const uint32_t nl = (end / 6u) * 4u + sjb_minu(end % 6u, 4u) - l0;                    // luma blocks in the tile
+    if (i < nl) { const uint32_t k = l0 + i; g = (k / 4u) * 6u + (k % 4u); }
+    else { const uint32_t k = (first - l0) + (i - nl); g = (k / 2u) * 6u + 4u + (k % 2u); }
+  } else {
+    const uint32_t l0 = (first / 3u) + sjb_minu(first % 3u, 1u);
+    const uint32_t end = first + count;
+    const uint32_t nl = (end / 3u) + sjb_minu(end % 3u, 1u) - l0;
+    if (i < nl) { g = (l0 + i) * 3u; }
+    else { const uint32_t k = (first - l0) + (i - nl); g = (k / 2u) * 3u + 1u + (k % 2u); }
+  }
+  return g - first;
+}
+
 }  // namespace sjb

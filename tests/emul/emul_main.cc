@@ -219,6 +219,11 @@ size_t emul_encode(const uint8_t* pix, int w, int h, long long stride, int mode,
 
 void emul_free(uint8_t* p) { free(p); }
 
+// the entropy kernel's walk order of busy tiles (block_ops.cuh::walk_order)
+unsigned emul_walk_order(unsigned first, unsigned count, unsigned i, int mcu_blocks) {
+  return walk_order(first, count, i, mcu_blocks);
+}
+
 // Sharp RGB->YUV 4:2:0 as sharp.cu lays it out: import into state 0, four refinement iterations
 // each writing its OWN copy of the state (the kernels run them as a pipeline), the exit rule
 // applied afterwards to pick the copy to keep.  Pictures with a side <= 4 take the plain path.

@@ -109,6 +109,23 @@ def test_sharp_yuv_and_riskiness_cell_functions_match_oracle(emul):
             assert (mode, risk.value) == O.oracle_riskiness(img, w, h, 3 * w, table), (w, h)
 
 
+def test_entropy_walk_order_is_a_luma_first_permutation(emul):
+    """block_ops.cuh::walk_order (which block of a tile each worker of the entropy kernel walks when
+    the tile is busy): a bijection on the tile that lists the luma blocks first, for every phase of
+    the tile start inside an MCU and for short last tiles."""
+    emul.emul_walk_order.restype = C.c_uint
+    emul.emul_walk_order.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_int]
+    for mb, lb in ((6, 4), (3, 1), (1, 1)):
+        for first in list(range(0, 256 * 7, 256)) + [256 * 12345, 4294966784]:
+            for count in (256, 255, 100, 7, 2, 1):
+                js = [emul.emul_walk_order(first, count, i, mb) for i in range(count)]
+                assert sorted(js) == list(range(count)), (mb, first, count)
+                chroma = [((first + j) % mb) >= lb for j in js]
+                assert chroma == sorted(chroma), (mb, first, count)
+                if mb == 1:
+                    assert js == list(range(count))
+
+
 def test_host_helpers_without_gpu():
     import sjpeg_b200
     L = sjpeg_b200.lib()
