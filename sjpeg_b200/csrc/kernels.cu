@@ -703,9 +703,6 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned 
 #ifndef SJB_LOOK_PER_LANE
 #define SJB_LOOK_PER_LANE 1
 #endif
-#ifndef SJB_E_MINBLOCKS
-#define SJB_E_MINBLOCKS 6
-#endif
 enum { kLookPerLane = SJB_LOOK_PER_LANE, kLookWindow = 32 * kLookPerLane };
 __device__ __forceinline__ unsigned long long warp_lookback(unsigned long long* state, long long tile,
                                                             unsigned long long aggregate) {
