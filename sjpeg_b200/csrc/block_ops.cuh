@@ -353,6 +353,99 @@ struct BitPackSink {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Trellis quantiser of one block (quantize.cc:325-457): rate-distortion
+// dynamic programme over the non-zero zig-zag positions, two candidate levels per position,
+// uint32 scores that wrap exactly like the reference's score_t.
+//   in      raw x16 coefficients, natural order      qm     8-bit matrix, natural order
+//   qtab    {iq, cpos} by zig-zag position           ac_len code lengths of the DEFAULT AC table
+//   out     quantised values, zig-zag order (all 64 written); returns the chunk bitmap
+// Working storage is passed in (local memory on the device): structure-of-arrays nodes, 10 bytes
+// each -- score | packed {pos:6, nbits:4, prev:7, rank:7, run:6} | amplitude code.
+// ---------------------------------------------------------------------------------------------
+struct TrellisScratch {
+  uint32_t score[1 + 2 * 63];
+  uint32_t meta[1 + 2 * 63];
+  uint16_t code[1 + 2 * 63];
+  uint32_t disto0[64];
+};
+SJB_HD uint32_t trellis_meta(int pos, int nbits, int prev, int rank, int run) {
+  return (uint32_t)pos | ((uint32_t)nbits << 6) | ((uint32_t)prev << 10) | ((uint32_t)rank << 17) | ((uint32_t)run << 24);
+}
+SJB_HD uint32_t trellis_block(const int16_t* in, const uint8_t* qm, const int32_t (*qtab)[2], const uint8_t* ac_len,
+                              int16_t* out, TrellisScratch& S) {
+  const int zz[64] = SJB_ZIGZAG_INIT;
+  S.score[0] = 0;
+  S.meta[0] = 0;                 // the sink: position 0, rank 0
+  S.code[0] = 0;
+  S.disto0[0] = 0;
+  int cur = 1;
+  for (int i = 1; i < 64; ++i) {
+    const int j = zz[i];
+    const uint32_t q = (uint32_t)qm[j] << 4;
+    const uint32_t lambda = q * q / 32u;
+    const int x = in[j];
+    const int sign = x >> 31;
+    const int V = (x ^ sign) - sign;
+    S.disto0[i] = (uint32_t)(V * V) + S.disto0[i - 1];
+    int v = (V * qtab[i][0] + qtab[i][1]) >> 20;   // V >= 0
+    if (v == 0) continue;
+    int nbits = bit_length((uint32_t)v);
+    for (int k = 0; k < 2; ++k) {
+      const int err = V - v * (int)q;
+      const uint32_t base = (uint32_t)(err * err) + S.disto0[i - 1];
+      // SearchBestPrev, quantize.cc:350-383: walk back from the newest kept node to the sink
+      uint32_t best_score = 0xffffffffu;
+      int best_prev = -1, best_rank = 0, best_run = 0;
+      for (int p = cur - 1; p >= 0; --p) {
+        const uint32_t pm = S.meta[p];
+        const int ppos = (int)(pm & 63u);
+        const int run = i - 1 - ppos;
+        if (run < 0) continue;                       // the other candidate of this same position
+        uint32_t bits = (uint32_t)nbits + (uint32_t)(run >> 4) * ac_len[0xf0];
+        const uint32_t d = base - S.disto0[ppos];
+        if (d + lambda * bits >= best_score) break;   // exact early-out of the reference
+        bits += ac_len[((run & 15) << 4) | nbits];
+        const uint32_t score = d + lambda * bits + S.score[p];
+        if (score < best_score) {
+          best_score = score;
+          best_prev = p;
+          best_rank = (int)((pm >> 17) & 127u) + 1;
+          best_run = run;
+        }
+      }
+      if (best_prev >= 0) {                           // a candidate without predecessor is dropped
+        S.score[cur] = best_score;
+        S.meta[cur] = trellis_meta(i, nbits, best_prev, best_rank, best_run);
+        S.code[cur] = (uint16_t)((v ^ sign) & ((1 << nbits) - 1));
+        ++cur;
+      }
+      --nbits;
+      if (nbits <= 0) break;
+      v = (1 << nbits) - 1;
+    }
+  }
+  int best = 0;
+  if (cur != 1) {
+    uint32_t best_score = 0xffffffffu;
+    for (int p = cur - 1; p >= 0; --p) {         // the sink takes part (quantize.cc:430: all-zero block)
+      const uint32_t s = S.score[p] + (S.disto0[63] - S.disto0[S.meta[p] & 63u]);
+      if (s < best_score) { best = p; best_score = s; }
+    }
+  }
+  for (int i = 0; i < 64; ++i) out[i] = 0;
+  out[0] = (int16_t)quantize_coeff(in[0], qtab[0][0], qtab[0][1]);      // DC: plain quantiser
+  uint32_t mask = (out[0] != 0) ? 1u : 0u;
+  for (int p = best; p > 0; p = (int)((S.meta[p] >> 10) & 127u)) {
+    const uint32_t pm = S.meta[p];
+    const int pos = (int)(pm & 63u), n = (int)((pm >> 6) & 15u);
+    const int amp = S.code[p];
+    out[pos] = (int16_t)((amp >> (n - 1)) ? amp : amp - ((1 << n) - 1));
+    mask |= 1u << (pos >> 3);
+  }
+  return mask;
+}
+
 SJB_HD uint32_t sjb_minu(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 // Position inside a tile of `count` consecutive blocks starting at global block `first` of the

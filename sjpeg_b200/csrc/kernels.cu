@@ -1170,17 +1170,9 @@ stuff_kernel(GroupBuffers gb, const __grid_constant__ StuffArgs args) {
 }
 
 // -------------------------------------------------------------------------------------------
-// T1: trellis quantisation, one block per thread (quantize.cc:325-457).  Node arrays live in
-// local memory; scores are uint32 and wrap exactly like the reference's score_t.
+// T1: trellis quantisation, one block per thread (quantize.cc:325-457); the dynamic programme is
+// block_ops.cuh::trellis_block (shared with the CPU emulation), its node arrays in local memory.
 // -------------------------------------------------------------------------------------------
-struct TrellisNode {
-  uint32_t score, disto;
-  int16_t prev;       // index of best predecessor
-  uint8_t pos, nbits;
-  uint16_t code;
-  uint8_t rank, run;
-};
-
 __global__ void __launch_bounds__(64)
 trellis_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, const int16_t* __restrict__ raw_src) {
   __shared__ uint8_t ac_len[2][256];
@@ -1199,87 +1191,17 @@ trellis_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, const int16
   const size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (g >= fs.blocks_per_frame) return;
   const int c = (static_cast<int>(g % fs.mcu_blocks) >= fs.luma_blocks) ? 1 : 0;
-  const uint8_t* len = ac_len[c];
-  constexpr int zz[64] = SJB_ZIGZAG_INIT;
   int16_t* blk = gb.coef + frame * gb.coef_pitch + g * 64;
-
-  TrellisNode nodes[1 + 2 * 63];
-  uint32_t disto0[64];
-  int16_t in[64];
+  __align__(16) int16_t in[64];
+  __align__(16) int16_t outv[64];
   {
     const uint4* s = reinterpret_cast<const uint4*>(raw_src ? raw_src + frame * gb.coef_pitch + g * 64 : blk);
     uint4* d = reinterpret_cast<uint4*>(in);
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = s[i];
   }
-  nodes[0].score = 0; nodes[0].disto = 0; nodes[0].prev = -1; nodes[0].pos = 0; nodes[0].nbits = 0;
-  nodes[0].code = 0; nodes[0].rank = 0; nodes[0].run = 0;
-  int cur = 1;
-  disto0[0] = 0;
-  for (int i = 1; i < 64; ++i) {
-    const int j = zz[i];
-    const uint32_t q = static_cast<uint32_t>(qm[c][j]) << 4;
-    const uint32_t lambda = q * q / 32u;
-    const int x = in[j];
-    const int sign = x >> 31;
-    const int V = (x ^ sign) - sign;
-    disto0[i] = static_cast<uint32_t>(V * V) + disto0[i - 1];
-    int v = (V * qtab[c][i][0] + qtab[c][i][1]) >> 20;   // V >= 0
-    if (v == 0) continue;
-    int nbits = bit_length(static_cast<uint32_t>(v));
-    for (int k = 0; k < 2; ++k) {
-      const int err = V - v * static_cast<int>(q);
-      TrellisNode n;
-      n.code = static_cast<uint16_t>((v ^ sign) & ((1 << nbits) - 1));
-      n.pos = static_cast<uint8_t>(i);
-      n.nbits = static_cast<uint8_t>(nbits);
-      n.score = 0xffffffffu;
-      n.prev = -1; n.rank = 0; n.run = 0;
-      // SearchBestPrev, quantize.cc:350-383
-      const uint32_t base = static_cast<uint32_t>(err * err) + disto0[i - 1];
-      n.disto = static_cast<uint32_t>(err * err);
-      bool found = false;
-      for (int p = cur - 1; p >= 0; --p) {
-        const int run = i - 1 - nodes[p].pos;
-        if (run < 0) continue;
-        uint32_t bits = static_cast<uint32_t>(nbits) + static_cast<uint32_t>(run >> 4) * len[0xf0];
-        const uint32_t d = base - disto0[nodes[p].pos];
-        if (d + lambda * bits >= n.score) break;
-        bits += len[((run & 15) << 4) | nbits];
-        const uint32_t score = d + lambda * bits + nodes[p].score;
-        if (score < n.score) {
-          n.score = score; n.disto = d; n.prev = static_cast<int16_t>(p);
-          n.rank = static_cast<uint8_t>(nodes[p].rank + 1); n.run = static_cast<uint8_t>(run);
-          found = true;
-        }
-      }
-      if (found) nodes[cur++] = n;
-      --nbits;
-      if (nbits <= 0) break;
-      v = (1 << nbits) - 1;
-    }
-  }
-  int best = 0;
-  if (cur != 1) {
-    uint32_t best_score = 0xffffffffu;
-    for (int p = cur - 1; p >= 0; --p) {
-      const uint32_t s = nodes[p].score + (disto0[63] - disto0[nodes[p].pos]);
-      if (s < best_score) { best = p; best_score = s; }
-    }
-  }
-  // write back: DC by the plain formula, AC from the chosen path, zig-zag order
-  int16_t outv[64];
-#pragma unroll
-  for (int i = 0; i < 64; ++i) outv[i] = 0;
-  outv[0] = static_cast<int16_t>(quantize_coeff(in[0], qtab[c][0][0], qtab[c][0][1]));
-  uint32_t mask = (outv[0] != 0) ? 1u : 0u;   // chunk bitmap
-  for (int p = best; p > 0; p = nodes[p].prev) {
-    const int n = nodes[p].nbits;
-    const int amp = nodes[p].code;
-    const int val = (amp >> (n - 1)) ? amp : amp - ((1 << n) - 1);
-    outv[nodes[p].pos] = static_cast<int16_t>(val);
-    mask |= 1u << (nodes[p].pos >> 3);
-  }
+  TrellisScratch scratch;     // local memory: 1.5 KB per thread
+  const uint32_t mask = trellis_block(in, qm[c], qtab[c], ac_len[c], outv, scratch);
   {
     const uint4* s = reinterpret_cast<const uint4*>(outv);
     uint4* d = reinterpret_cast<uint4*>(blk);

@@ -130,14 +130,13 @@ void emul_default_ac_syms(int chroma, uint8_t* bits, uint8_t* syms, int* n) {
   memcpy(bits, s.bits, 16); memcpy(syms, s.syms, s.nb_syms); *n = s.nb_syms;
 }
 
-// full pipeline, methods 0..6 (no trellis).  Returns size; *out malloc()ed.
+// full pipeline, methods 0..8.  Returns size; *out malloc()ed.
 size_t emul_encode(const uint8_t* pix, int w, int h, long long stride, int mode, int fmt, int method,
                    const uint8_t* quant_in /*[2][64]*/, int q_bias, int qdl, int qdc, uint8_t** out) {
   FrameGeometry g;
   if (!MakeGeometry(mode, w, h, &g)) return 0;
   method = method < 0 ? 0 : method > 8 ? 8 : method;
-  if (method >= 7) return 0;
-  const bool adaptive = method >= 3, optimize = method != 0 && method != 3;
+  const bool adaptive = method >= 3, optimize = method != 0 && method != 3, trellis = method >= 7;
   Img im = {pix, stride, w, h, fmt};
   uint8_t quant[2][64], minq[2][64];
   memcpy(quant, quant_in, 128);
@@ -161,10 +160,26 @@ size_t emul_encode(const uint8_t* pix, int w, int h, long long stride, int mode,
     AnalyseHistograms(counts.data(), g.nb_comps, quant, minq, qdl, qdc);
     for (int i = (g.nb_comps > 1 ? 1 : 0); i >= 0; --i) if (!FinalizeQuantizer(quant[i], minq[i], q_bias, &qt.m[i])) return 0;
   }
+  // rate model of the trellis = code lengths of the DEFAULT AC tables (enc.cc:334)
+  uint8_t default_len[2][256];
+  for (int c = 0; c < 2; ++c) {
+    HuffSpec hs;
+    DefaultHuffSpec(true, c, &hs);
+    uint32_t codes[256];
+    memset(codes, 0, sizeof(codes));
+    CodesFromSpec(hs, codes);
+    for (int i = 0; i < 256; ++i) default_len[c][i] = (uint8_t)(codes[i] & 0xff);
+  }
   for (size_t b = 0; b < nb; ++b) {
+    const int c = ((int)(b % g.mcu_blocks) >= g.luma_blocks) ? 1 : 0;
+    if (trellis) {
+      TrellisScratch scratch;
+      mask[b] = trellis_block(&raw[b * 64], quant[c], qt.m[c].e, default_len[c], &zz[b * 64], scratch);
+      continue;
+    }
     int v[64];
     for (int i = 0; i < 64; ++i) v[i] = raw[b * 64 + i];
-    QuantizeBlock(v, qt.m[((int)(b % g.mcu_blocks) >= g.luma_blocks) ? 1 : 0], &zz[b * 64], &mask[b]);
+    QuantizeBlock(v, qt.m[c], &zz[b * 64], &mask[b]);
   }
   HuffSpec spec[4];
   for (int i = 0; i < 4; ++i) DefaultHuffSpec(i >= 2, i & 1, &spec[i]);

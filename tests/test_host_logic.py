@@ -53,7 +53,7 @@ def test_block_functions_and_host_codec_match_oracle(emul):
         for rgb in imgs:
             for q in (0, 25, 75, 93, 100):
                 for mode in (O.YUV_420, O.YUV_444, O.YUV_400):
-                    for m in (0, 1, 3, 4):
+                    for m in (0, 1, 3, 4, 7, 8):
                         assert _emul_encode(emul, rgb, w, h, float(q), m, mode) == \
                             O.oracle_encode(rgb, w, h, 3 * w, float(q), m, mode), (w, h, q, mode, m)
 
