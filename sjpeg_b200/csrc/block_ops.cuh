@@ -9,6 +9,7 @@
 //   DC diff / run-level /root/reference/src/entropy.cc:133-198
 //   bit accumulator     /root/reference/src/bit_writer.h:172-209
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -49,6 +50,28 @@ struct CodeTabs {
   { 0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, \
     20, 13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,  \
     58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 }
+
+// ---------------------------------------------------------------------------------------------
+// Coefficient storage in HBM: sector-interleaved.  A block is 64 int16 = four 32-byte sectors
+// (sector s = positions 16s..16s+15, zig-zag order once quantised).  Four consecutive blocks form
+// a group of four 128-byte lines, and line s of the group holds sector s of each of its blocks:
+//   int16 offset of (block g, position p) = (g / 4) * 256 + (p / 16) * 64 + (g % 4) * 16 + p % 16
+// Photographic pictures quantise to non-zeros in sector 0 only (99.97 % of the blocks of the 4K
+// benchmark picture), and with one 128-byte line per block every such block cost the entropy
+// stage a whole line of DRAM / L2 / L1 for 32 useful bytes (ncu: 128 bytes of DRAM reads per
+// block).  Interleaved, the lines that hold the sector-0s are dense and the others are never
+// touched.  Kernels address a block through coef_block_base() and step kCoefSectorStride int16
+// from one sector to the next; a picture's array is padded to a multiple of four blocks.
+// ---------------------------------------------------------------------------------------------
+enum { kCoefSectorStride = 64 };   // int16 units between two sectors of the same block
+SJB_HD size_t coef_block_base(size_t g) {   // block indices fit 32 bits (<= 3 * 8192 * 8192 blocks)
+  const uint32_t b = static_cast<uint32_t>(g);
+  return (static_cast<size_t>(b >> 2) << 8) | ((b & 3u) << 4);
+}
+SJB_HD int coef_pos_offset(int pos) { return pos + (pos >> 4) * 48; }   // = (pos / 16) * 64 + pos % 16
+// index, in 16-byte units from the block base, of chunk c (positions 8c..8c+7)
+SJB_HD int coef_chunk_index(int c) { return ((c >> 1) << 3) + (c & 1); }
+SJB_HD size_t coef_padded_blocks(size_t nb) { return (nb + 3) & ~static_cast<size_t>(3); }
 
 // ---------------------------------------------------------------------------------------------
 // colour conversion.  16-bit fixed point BT.601, colors_rgb.cc:17-32.

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -201,7 +202,8 @@ int ReserveLane(sjb_context* ctx, Lane* L, const Plan& plan, int frames) {
   frames = std::max(frames, 1);
   const size_t f = static_cast<size_t>(frames);
   bool out_grew = false, words_grew = false;
-  CU(L->coef.Reserve(f * nb * 64 * sizeof(int16_t)));
+  const size_t coef_pitch = coef_padded_blocks(nb) * 64;   // sector-interleaved: whole groups of 4 blocks
+  CU(L->coef.Reserve(f * coef_pitch * sizeof(int16_t)));
   CU(L->nzmask.Reserve(f * nb * sizeof(uint8_t) + 64));
   CU(L->words.Reserve(f * plan.stream_words * 4 + 64, true, &words_grew));   // zeroed once, then self-cleaning
   CU(L->out.Reserve(f * plan.out_capacity, false, &out_grew));
@@ -210,7 +212,7 @@ int ReserveLane(sjb_context* ctx, Lane* L, const Plan& plan, int frames) {
   const bool relayout = out_grew || gb.out_pitch != plan.out_capacity || gb.words_pitch != plan.stream_words ||
                         L->group_capacity != frames;
   gb.coef = L->coef.as<int16_t>();
-  gb.coef_pitch = nb * 64;
+  gb.coef_pitch = coef_pitch;
   gb.nzmask = L->nzmask.as<uint8_t>();
   gb.mask_pitch = nb;
   gb.words = L->words.as<uint32_t>();
@@ -521,7 +523,7 @@ int EncodeSearch(sjb_context* ctx, Lane* L, const FrameSet& fs, const Plan& plan
   }
   CU(cudaEventRecord(L->ev[0], L->stream));
   // unquantised coefficients -> raw buffer (kept for all passes)
-  CU(L->raw.Reserve(nb * 64 * sizeof(int16_t)));
+  CU(L->raw.Reserve(coef_padded_blocks(nb) * 64 * sizeof(int16_t)));
   {
     GroupBuffers graw = gb;
     graw.coef = L->raw.as<int16_t>();
@@ -1278,7 +1280,7 @@ static int StageF1(sjb_context* ctx, const uint8_t* pix, int width, int height, 
   QuantTabs qt;
   if (!MakeQuantTabs(*plan, quant, min_quant, &qt)) return SJB_ERR_ARG;
   // the fast kernel skips all-zero chunks: give the dump a defined background
-  CU(cudaMemsetAsync(L->coef.ptr, 0, plan->g.nb_blocks() * 64 * sizeof(int16_t), L->stream));
+  CU(cudaMemsetAsync(L->coef.ptr, 0, coef_padded_blocks(plan->g.nb_blocks()) * 64 * sizeof(int16_t), L->stream));
   LaunchF1(L, *fs, plan->g, raw, qt);
   CU(cudaGetLastError());
   return SJB_OK;
@@ -1292,11 +1294,19 @@ int sjb_stage_coefficients(sjb_context* ctx, const uint8_t* pix, int width, int 
   RC(StageF1(ctx, pix, width, height, stride, params, quantise == 0, &plan, &fs));
   Lane* L = &ctx->lanes[0];
   const size_t nb = plan.g.nb_blocks();
-  CU(cudaMemcpyAsync(coef, L->coef.ptr, nb * 64 * sizeof(int16_t), cudaMemcpyDeviceToHost, L->stream));
+  // the device array is sector-interleaved (block_ops.cuh); the caller gets plain [nblocks][64]
+  const size_t stored_count = coef_padded_blocks(nb) * 64;
+  std::unique_ptr<int16_t[]> stored(new (std::nothrow) int16_t[stored_count]);
+  if (!stored) return SJB_ERR_NOMEM;
+  CU(cudaMemcpyAsync(stored.get(), L->coef.ptr, stored_count * sizeof(int16_t), cudaMemcpyDeviceToHost, L->stream));
   if (quantise && nzmask) {
     CU(cudaMemcpyAsync(nzmask, L->nzmask.ptr, nb * sizeof(uint8_t), cudaMemcpyDeviceToHost, L->stream));
   }
   CU(cudaStreamSynchronize(L->stream));
+  for (size_t g = 0; g < nb; ++g) {
+    const int16_t* src = stored.get() + coef_block_base(g);
+    for (int s = 0; s < 4; ++s) memcpy(coef + g * 64 + 16 * s, src + s * kCoefSectorStride, 16 * sizeof(int16_t));
+  }
   return SJB_OK;
 }
 
@@ -1364,9 +1374,16 @@ int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int
     ctx->lanes[l].launches = 0;
   }
   CU(cudaDeviceSynchronize());
-  cudaEvent_t t0, t1;
-  CU(cudaEventCreate(&t0));
-  CU(cudaEventCreate(&t1));
+  struct EventPair {      // destroyed on every return path
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() {
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+    }
+  } span;
+  CU(cudaEventCreate(&span.a));
+  CU(cudaEventCreate(&span.b));
+  const cudaEvent_t t0 = span.a, t1 = span.b;
   Lane* L0 = &ctx->lanes[0];
   CU(cudaEventRecord(t0, L0->stream));
   for (int l = 1; l < nl; ++l) CU(cudaStreamWaitEvent(ctx->lanes[l].stream, t0, 0));
@@ -1397,8 +1414,6 @@ int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int
     *launches = 0;
     for (int l = 0; l < nl; ++l) *launches += ctx->lanes[l].launches;
   }
-  cudaEventDestroy(t0);
-  cudaEventDestroy(t1);
   return SJB_OK;
 }
 

@@ -20,6 +20,7 @@
 #include "kernels.cuh"
 
 #include <cuda_runtime.h>
+#include <atomic>
 
 namespace sjb {
 
@@ -66,14 +67,15 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* scr
 }
 
 // -------------------------------------------------------------------------------------------
-// block output: 64 int32 registers -> 128 bytes
+// block output: 64 int32 registers -> 128 bytes, four sectors kCoefSectorStride apart
+// (sector-interleaved layout, block_ops.cuh); dst = base of the block (coef_block_base)
 // -------------------------------------------------------------------------------------------
 __device__ __forceinline__ void store_block_natural(const int (&v)[64], int16_t* dst) {
   uint4* d = reinterpret_cast<uint4*>(dst);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    d[i] = make_uint4(pack16(v[8 * i], v[8 * i + 1]), pack16(v[8 * i + 2], v[8 * i + 3]),
-                      pack16(v[8 * i + 4], v[8 * i + 5]), pack16(v[8 * i + 6], v[8 * i + 7]));
+    d[coef_chunk_index(i)] = make_uint4(pack16(v[8 * i], v[8 * i + 1]), pack16(v[8 * i + 2], v[8 * i + 3]),
+                                        pack16(v[8 * i + 4], v[8 * i + 5]), pack16(v[8 * i + 6], v[8 * i + 7]));
   }
 }
 
@@ -117,8 +119,8 @@ __device__ __forceinline__ void quantize_store_block(const int (&v)[64], const T
     // bitmap gates every load of the entropy stage), so the fast path does not write it; whole
     // sectors are written so that L2 never has to fill a partial one from DRAM.
     if (!kSparse || s == 0 || nz0 || nz1) {
-      d[2 * s] = make_uint4(w[0], w[1], w[2], w[3]);
-      d[2 * s + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+      d[coef_chunk_index(2 * s)] = make_uint4(w[0], w[1], w[2], w[3]);
+      d[coef_chunk_index(2 * s + 1)] = make_uint4(w[4], w[5], w[6], w[7]);
     }
   }
   *chunkmask = static_cast<uint8_t>(mask);
@@ -255,10 +257,10 @@ f1_generic_kernel(const __grid_constant__ FrameSet fs, int mx0, int my0, int mx1
   }
   fdct64(v);
   if (kRaw) {
-    store_block_natural(v, coef + g * 64);
+    store_block_natural(v, coef + coef_block_base(g));
   } else {
-    if (chroma) quantize_store_block(v, ParamTab{qt.m[1]}, coef + g * 64, nzmask + g);
-    else        quantize_store_block(v, ParamTab{qt.m[0]}, coef + g * 64, nzmask + g);
+    if (chroma) quantize_store_block(v, ParamTab{qt.m[1]}, coef + coef_block_base(g), nzmask + g);
+    else        quantize_store_block(v, ParamTab{qt.m[0]}, coef + coef_block_base(g), nzmask + g);
   }
 }
 
@@ -374,10 +376,10 @@ __device__ __forceinline__ void convert_strip_444(uint32_t addr, uint32_t row_st
 
 template <bool kRaw>
 __device__ __forceinline__ void finish_block(int (&v)[64], uint32_t tab_addr, int16_t* coef,
-                                             uint8_t* nzmask, size_t g) {
+                                             uint8_t* nzmask, uint32_t g) {
   fdct64(v);
-  if (kRaw) store_block_natural(v, coef + g * 64);
-  else quantize_store_block<true>(v, SmemTab{tab_addr}, coef + g * 64, nzmask + g);
+  if (kRaw) store_block_natural(v, coef + coef_block_base(g));
+  else quantize_store_block<true>(v, SmemTab{tab_addr}, coef + coef_block_base(g), nzmask + g);
 }
 
 template <int kMode, bool kRaw, int kFmt>
@@ -428,7 +430,8 @@ f1_fast_kernel(const __grid_constant__ FrameSet fs, int mx_full, int my0,
     for (int i = 0; i < 8; ++i) (&qtab[0][0][0])[lane + 32 * i] = q[lane + 32 * i];
   }
   __syncwarp();
-  const size_t mcu0 = static_cast<size_t>(ry) * fs.mcus_x + static_cast<size_t>(cx) * kMcusPerTile;
+  // block indices fit 32 bits (at most 3 * 8192 * 8192 blocks per picture)
+  const uint32_t mcu0 = static_cast<uint32_t>(ry) * fs.mcus_x + static_cast<uint32_t>(cx) * kMcusPerTile;
   const uint32_t src = slot0 + lane * (8 * kStep);
 
   if (k420) {
@@ -467,7 +470,7 @@ f1_fast_kernel(const __grid_constant__ FrameSet fs, int mx_full, int my0,
           x[8 * r + 6] = static_cast<int16_t>(w3 & 0xffff); x[8 * r + 7] = static_cast<int>(w3) >> 16;
         }
       }
-      const size_t g = (mcu0 + m) * 6 + ((j < 2) ? 2 * j : 4) + half;
+      const uint32_t g = (mcu0 + m) * 6u + ((j < 2) ? 2 * j : 4) + half;
       if (active) finish_block<kRaw>(x, tab0 + ((j < 2) ? 0u : 512u), coef, nzmask, g);
     }
   } else {
@@ -493,7 +496,7 @@ __device__ __forceinline__ void load_block_natural(const int16_t* src, int (&v)[
   const uint4* s = reinterpret_cast<const uint4*>(src);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const uint4 w = s[i];
+    const uint4 w = s[coef_chunk_index(i)];
     v[8 * i + 0] = static_cast<int16_t>(w.x & 0xffff); v[8 * i + 1] = static_cast<int>(w.x) >> 16;
     v[8 * i + 2] = static_cast<int16_t>(w.y & 0xffff); v[8 * i + 3] = static_cast<int>(w.y) >> 16;
     v[8 * i + 4] = static_cast<int16_t>(w.z & 0xffff); v[8 * i + 5] = static_cast<int>(w.z) >> 16;
@@ -512,9 +515,9 @@ requantize_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, const in
   __syncthreads();
   const size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (g >= fs.blocks_per_frame) return;
-  int16_t* blk = gb.coef + frame * gb.coef_pitch + g * 64;
+  int16_t* blk = gb.coef + frame * gb.coef_pitch + coef_block_base(g);
   int v[64];
-  load_block_natural(raw_src ? raw_src + frame * gb.coef_pitch + g * 64 : blk, v);
+  load_block_natural(raw_src ? raw_src + frame * gb.coef_pitch + coef_block_base(g) : blk, v);
   const uint32_t tab = smem_addr(qtab) + ((static_cast<int>(g % fs.mcu_blocks) >= fs.luma_blocks) ? 512u : 0u);
   quantize_store_block(v, SmemTab{tab}, blk, gb.nzmask + frame * gb.mask_pitch + g);
 }
@@ -544,7 +547,7 @@ quant_error_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, const i
   for (size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; g < fs.blocks_per_frame; g += stride) {
     const int c = (static_cast<int>(g % fs.mcu_blocks) >= fs.luma_blocks) ? 1 : 0;
     int v[64];
-    load_block_natural(raw + frame * gb.coef_pitch + g * 64, v);
+    load_block_natural(raw + frame * gb.coef_pitch + coef_block_base(g), v);
     uint32_t e = 0;
 #pragma unroll
     for (int i = 0; i < 64; ++i) {
@@ -587,7 +590,7 @@ histogram_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
     const size_t g = t >> 3;
     const int part = static_cast<int>(t & 7);
     const int m = (static_cast<int>(g % fs.mcu_blocks) >= fs.luma_blocks) ? 1 : 0;
-    const uint4 w = reinterpret_cast<const uint4*>(raw + g * 64)[part];
+    const uint4 w = reinterpret_cast<const uint4*>(raw + coef_block_base(g))[coef_chunk_index(part)];
     const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -620,18 +623,18 @@ __device__ __forceinline__ int dc_predictor(const int16_t* zz, size_t g, int k, 
     if (g < static_cast<size_t>(mcu_blocks)) return init ? init[1 + k - luma_blocks] : 0;
     prev = g - mcu_blocks;
   }
-  return zz[prev * 64];
+  return zz[coef_block_base(prev)];
 }
 
 struct ChunkLoader {   // chunk c of a block = zig-zag positions 8c..8c+7, one 16-byte load
-  const int16_t* p;
+  const int16_t* p;    // base of the block (coef_block_base)
   __device__ __forceinline__ Words4 operator()(int c) const {
-    const uint4 q = reinterpret_cast<const uint4*>(p)[c];
+    const uint4 q = reinterpret_cast<const uint4*>(p)[coef_chunk_index(c)];
     Words4 r;
     r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
     return r;
   }
-  __device__ __forceinline__ int value(int pos) const { return p[pos]; }
+  __device__ __forceinline__ int value(int pos) const { return p[coef_pos_offset(pos)]; }
 };
 // Same, with the first two chunks (one 32-byte sector: where the low frequencies live) fetched
 // eagerly together with the bitmap and the predictor, so that a typical block needs a single
@@ -640,7 +643,7 @@ struct ChunkLoader {   // chunk c of a block = zig-zag positions 8c..8c+7, one 1
 // registers here) rematerialises the whole address chain -- frame pitch, tile, block -- for every
 // coefficient fetched in the walk.
 struct PrefetchedChunkLoader {
-  unsigned long long addr;    // global address of the block's 64 coefficients
+  unsigned long long addr;    // global address of the block's sector 0 (coef_block_base)
   uint4 c0, c1;
   __device__ __forceinline__ explicit PrefetchedChunkLoader(const int16_t* p) {
     addr = static_cast<unsigned long long>(__cvta_generic_to_global(p));
@@ -650,7 +653,7 @@ struct PrefetchedChunkLoader {
   }
   __device__ __forceinline__ uint4 chunk(int c) const {
     uint4 q;
-    asm("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(addr + 16ull * c));
+    asm("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(addr + 16ull * coef_chunk_index(c)));
     return q;
   }
   __device__ __forceinline__ Words4 operator()(int c) const {
@@ -659,10 +662,10 @@ struct PrefetchedChunkLoader {
     r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
     return r;
   }
-  // the 128-byte line of the block is in L1 by now (its first sector was fetched up front)
+  // sector 0 of the block is in L1 by now (fetched up front); the later sectors sit in other lines
   __device__ __forceinline__ int value(int pos) const {
     short v;
-    asm("ld.global.s16 %0, [%1];" : "=h"(v) : "l"(addr + 2ull * pos));
+    asm("ld.global.s16 %0, [%1];" : "=h"(v) : "l"(addr + 2ull * coef_pos_offset(pos)));
     return v;
   }
 };
@@ -942,7 +945,7 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
         uint32_t* mine = local[b][j];
         const int k = block_in_mcu(g, fs.mcu_blocks);
         const int c = (k >= fs.luma_blocks) ? 1 : 0;
-        const int16_t* blk = zz + g * 64;
+        const int16_t* blk = zz + coef_block_base(g);
         const uint32_t mask = nzmask[g];
         const PrefetchedChunkLoader loader(blk);
         const int pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, dc_init);
@@ -968,7 +971,8 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
         // this tile's prefix is resolved and the previous tile is written out
         const size_t gn = static_cast<size_t>(t_next) * kTileBlocks + threadIdx.x;
         if (gn < nb_blocks) {
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(zz + gn * 64));
+          // (four consecutive blocks share the line that holds their first sectors)
+          if ((threadIdx.x & 3) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(zz + coef_block_base(gn)));
           if ((threadIdx.x & 31) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(nzmask + gn));
         }
       }
@@ -1005,7 +1009,7 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
           // more than 512 bits: walk the block again, straight into the stream
           const int k = block_in_mcu(g, fs.mcu_blocks);
           const int c = (k >= fs.luma_blocks) ? 1 : 0;
-          const int16_t* blk = zz + g * 64;
+          const int16_t* blk = zz + coef_block_base(g);
           StreamOut out = {stream};
           BitPackSink<StreamOut> sink(out, offset);
           code_block(ChunkLoader{blk}, nzmask[g], blk[0], dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, dc_init),
@@ -1040,7 +1044,7 @@ symbol_stats_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   for (size_t g = blockIdx.x * static_cast<size_t>(kTileBlocks) + threadIdx.x; g < nb_blocks; g += stride) {
     const int k = static_cast<int>(g % fs.mcu_blocks);
     const int c = (k >= fs.luma_blocks) ? 1 : 0;
-    const int16_t* b = zz + g * 64;
+    const int16_t* b = zz + coef_block_base(g);
     SmemStats add = {f[c]};
     block_symbol_stats(ChunkLoader{b}, nzmask[g], b[0],
                        dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks,
@@ -1191,14 +1195,14 @@ trellis_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, const int16
   const size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (g >= fs.blocks_per_frame) return;
   const int c = (static_cast<int>(g % fs.mcu_blocks) >= fs.luma_blocks) ? 1 : 0;
-  int16_t* blk = gb.coef + frame * gb.coef_pitch + g * 64;
+  int16_t* blk = gb.coef + frame * gb.coef_pitch + coef_block_base(g);
   __align__(16) int16_t in[64];
   __align__(16) int16_t outv[64];
   {
-    const uint4* s = reinterpret_cast<const uint4*>(raw_src ? raw_src + frame * gb.coef_pitch + g * 64 : blk);
+    const uint4* s = reinterpret_cast<const uint4*>(raw_src ? raw_src + frame * gb.coef_pitch + coef_block_base(g) : blk);
     uint4* d = reinterpret_cast<uint4*>(in);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = s[i];
+    for (int i = 0; i < 8; ++i) d[i] = s[coef_chunk_index(i)];
   }
   TrellisScratch scratch;     // local memory: 1.5 KB per thread
   const uint32_t mask = trellis_block(in, qm[c], qtab[c], ac_len[c], outv, scratch);
@@ -1206,7 +1210,7 @@ trellis_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, const int16
     const uint4* s = reinterpret_cast<const uint4*>(outv);
     uint4* d = reinterpret_cast<uint4*>(blk);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = s[i];
+    for (int i = 0; i < 8; ++i) d[coef_chunk_index(i)] = s[i];
   }
   gb.nzmask[frame * gb.mask_pitch + g] = static_cast<uint8_t>(mask);
 }
@@ -1221,7 +1225,7 @@ __global__ void last_dc_kernel(const __grid_constant__ FrameSet fs, GroupBuffers
   if (comp < nb_comps) {
     const size_t last_mcu = static_cast<size_t>(fs.blocks_per_frame) - fs.mcu_blocks;
     const size_t g = last_mcu + ((comp == 0) ? fs.luma_blocks - 1 : fs.luma_blocks + comp - 1);
-    v = gb.coef[frame * gb.coef_pitch + g * 64];
+    v = gb.coef[frame * gb.coef_pitch + coef_block_base(g)];
   }
   out[t] = v;
 }
@@ -1298,14 +1302,15 @@ void LaunchQuantError(const FrameSet& fs, const GroupBuffers& gb, const int16_t*
 }
 
 void LaunchHistogram(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {
-  static bool init[64] = {false};
+  // the attribute is per device; concurrent host threads may get here together (any of them may set it)
+  static std::atomic<bool> init[64];
   const size_t smem = 2 * 64 * 128 * sizeof(int32_t);
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
-  if (!init[dev]) {
+  if (!init[dev].load(std::memory_order_acquire)) {
     cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    init[dev] = true;
+    init[dev].store(true, std::memory_order_release);
   }
   unsigned grid = cdiv(static_cast<size_t>(fs.blocks_per_frame) * 8, 256 * 16);
   const unsigned cap = 148 * 3 / (fs.frames > 0 ? fs.frames : 1) + 1;

@@ -56,7 +56,7 @@ struct StreamInfo {
 
 // Per-lane device arrays, picture-major with fixed pitches (in elements of the pointed type).
 struct GroupBuffers {
-  int16_t* coef;            size_t coef_pitch;    // [frames][blocks*64]
+  int16_t* coef;            size_t coef_pitch;    // [frames][padded blocks*64], sector-interleaved (block_ops.cuh)
   uint8_t* nzmask;          size_t mask_pitch;    // [frames][blocks] chunk bitmaps
   uint32_t* words;          size_t words_pitch;   // [frames][worst-case stream words], zero between encodes
   uint8_t* out;             size_t out_pitch;     // [frames][worst-case file bytes]

@@ -239,6 +239,12 @@ unsigned emul_walk_order(unsigned first, unsigned count, unsigned i, int mcu_blo
   return walk_order(first, count, i, mcu_blocks);
 }
 
+// the sector-interleaved coefficient layout of the device arrays (block_ops.cuh): int16 offset of
+// (block g, position pos) by the two routes the kernels use, and the padded block count
+unsigned long long emul_coef_offset(unsigned long long g, int pos) { return coef_block_base(g) + coef_pos_offset(pos); }
+unsigned long long emul_coef_chunk_offset(unsigned long long g, int c) { return coef_block_base(g) + 8ull * coef_chunk_index(c); }
+unsigned long long emul_coef_padded_blocks(unsigned long long nb) { return coef_padded_blocks(nb); }
+
 // Sharp RGB->YUV 4:2:0 as sharp.cu lays it out: import into state 0, four refinement iterations
 // each writing its OWN copy of the state (the kernels run them as a pipeline), the exit rule
 // applied afterwards to pick the copy to keep.  Pictures with a side <= 4 take the plain path.

@@ -126,6 +126,33 @@ def test_entropy_walk_order_is_a_luma_first_permutation(emul):
                     assert js == list(range(count))
 
 
+def test_coefficient_layout_is_a_sector_interleaved_bijection(emul):
+    """block_ops.cuh coef_block_base / coef_pos_offset / coef_chunk_index: every (block, position)
+    owns one int16 of the padded array, chunks are 16-byte aligned runs of 8 positions, and the
+    first sectors of four consecutive blocks share one 128-byte line."""
+    for f in (emul.emul_coef_offset, emul.emul_coef_chunk_offset, emul.emul_coef_padded_blocks):
+        f.restype = C.c_ulonglong
+    emul.emul_coef_offset.argtypes = [C.c_ulonglong, C.c_int]
+    emul.emul_coef_chunk_offset.argtypes = [C.c_ulonglong, C.c_int]
+    emul.emul_coef_padded_blocks.argtypes = [C.c_ulonglong]
+    for nb in (1, 2, 3, 4, 5, 6, 7, 8, 9, 48, 49, 50, 51):
+        padded = emul.emul_coef_padded_blocks(nb)
+        assert padded % 4 == 0 and nb <= padded < nb + 4
+        offs = [emul.emul_coef_offset(g, p) for g in range(nb) for p in range(64)]
+        assert len(set(offs)) == len(offs) and max(offs) < padded * 64
+    for g in (0, 1, 2, 3, 4, 7, 194399, 201326591):
+        for c in range(8):
+            base = emul.emul_coef_chunk_offset(g, c)
+            assert base % 8 == 0
+            assert [emul.emul_coef_offset(g, 8 * c + k) for k in range(8)] == list(range(base, base + 8))
+        # sector s of blocks 4j..4j+3 = one 128-byte line (64 int16)
+        for s in range(4):
+            line = {emul.emul_coef_offset(4 * (g // 4) + b, 16 * s + k) // 64 for b in range(4) for k in range(16)}
+            assert len(line) == 1
+    # block index arithmetic is 32-bit: the largest picture (65535 x 65535, 4:4:4) still fits
+    assert emul.emul_coef_offset(3 * 8192 * 8192 - 1, 63) == (3 * 8192 * 8192) * 64 - 1
+
+
 def test_host_helpers_without_gpu():
     import sjpeg_b200
     L = sjpeg_b200.lib()
