@@ -1340,7 +1340,7 @@ void LaunchEntropyPack(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t 
 }
 
 void LaunchLastDc(const FrameSet& fs, const GroupBuffers& gb, int* out, cudaStream_t s) {
-  last_dc_kernel<<<1, 32, 0, s>>>(fs, gb, out);
+  last_dc_kernel<<<1, (3 * kMaxGroup + 31) / 32 * 32, 0, s>>>(fs, gb, out);
 }
 
 void LaunchStuff(const FrameSet& fs, const GroupBuffers& gb, const StuffArgs& args, cudaStream_t s) {

@@ -13,7 +13,10 @@
 
 namespace sjb {
 
-enum { kMaxGroup = 8 };
+#ifndef SJB_MAX_GROUP
+#define SJB_MAX_GROUP 8
+#endif
+enum { kMaxGroup = SJB_MAX_GROUP };
 #ifndef SJB_TILE_BLOCKS
 #define SJB_TILE_BLOCKS 256
 #endif
