@@ -135,6 +135,12 @@ namespace {
       return (e_ == cudaErrorMemoryAllocation) ? SJB_ERR_NOMEM : SJB_ERR_CUDA;     \
     }                                                                              \
   } while (0)
+// The C ABI promises that no exception leaves the library (include/sjpeg_b200.h): the entry points
+// are function-try-blocks; the only exceptions the host code can meet are failed allocations of
+// its small std::vector / std::string temporaries.
+#define SJB_NOTHROW_END                                   \
+  catch (const std::bad_alloc&) { return SJB_ERR_NOMEM; } \
+  catch (...) { return SJB_ERR_CUDA; }
 #define RC(expr)                   \
   do {                             \
     const int rc_ = (expr);        \
@@ -783,7 +789,7 @@ int sjb_device_count(void) {
   return n;
 }
 
-int sjb_context_create(int device, sjb_context** out) {
+int sjb_context_create(int device, sjb_context** out) try {
   if (out == nullptr) return SJB_ERR_ARG;
   *out = nullptr;
   if (device < 0 || device >= sjb_device_count()) return SJB_ERR_CUDA;
@@ -803,7 +809,7 @@ int sjb_context_create(int device, sjb_context** out) {
   }
   *out = ctx;
   return SJB_OK;
-}
+} SJB_NOTHROW_END
 
 void sjb_context_destroy(sjb_context* ctx) {
   if (ctx == nullptr) return;
@@ -859,7 +865,7 @@ int FinishSingle(sjb_context* ctx, uint8_t* out, int out_on_device, size_t out_c
 
 int sjb_encode(sjb_context* ctx, const uint8_t* pix, int pix_on_device, int width, int height,
                long long stride, const sjb_params* params, uint8_t* out, int out_on_device,
-               size_t out_capacity, size_t* out_size) {
+               size_t out_capacity, size_t* out_size) try {
   if (ctx == nullptr || pix == nullptr || out_size == nullptr) return SJB_ERR_ARG;
   *out_size = 0;
   ctx->lanes[0].last_size = 0;
@@ -874,9 +880,9 @@ int sjb_encode(sjb_context* ctx, const uint8_t* pix, int pix_on_device, int widt
     RC(EncodeSingle(ctx, pix, pix_on_device, stride, plan, /*timed=*/true));
   }
   return FinishSingle(ctx, out, out_on_device, out_capacity, out_size);
-}
+} SJB_NOTHROW_END
 
-int sjb_fetch_output(sjb_context* ctx, uint8_t* out, int out_on_device, size_t out_capacity) {
+int sjb_fetch_output(sjb_context* ctx, uint8_t* out, int out_on_device, size_t out_capacity) try {
   if (ctx == nullptr || out == nullptr) return SJB_ERR_ARG;
   Lane* L = &ctx->lanes[0];
   const size_t size = L->last_size;
@@ -887,11 +893,11 @@ int sjb_fetch_output(sjb_context* ctx, uint8_t* out, int out_on_device, size_t o
                      L->stream));
   CU(cudaStreamSynchronize(L->stream));
   return SJB_OK;
-}
+} SJB_NOTHROW_END
 
 int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix_on_device, int width,
                      int height, long long stride, const sjb_params* params, uint8_t* const* out,
-                     int out_on_device, size_t out_capacity, size_t* sizes) {
+                     int out_on_device, size_t out_capacity, size_t* sizes) try {
   if (ctx == nullptr || pix == nullptr || out == nullptr || sizes == nullptr || n < 0) return SJB_ERR_ARG;
   ctx->err.clear();
   ctx->lanes[0].last_size = 0;
@@ -967,7 +973,7 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
   }
   for (int l = 0; l < nl; ++l) CU(cudaStreamSynchronize(ctx->lanes[l].stream));
   return first_err;
-}
+} SJB_NOTHROW_END
 
 }  // extern "C"
 
@@ -1197,7 +1203,7 @@ extern "C" {
 int sjb_encode_planar(sjb_context* ctx, const uint8_t* y, long long y_stride, const uint8_t* u,
                       long long u_stride, const uint8_t* v, long long v_stride, int uv_step, int on_device,
                       int width, int height, const sjb_params* params, uint8_t* out, int out_on_device,
-                      size_t out_capacity, size_t* out_size) {
+                      size_t out_capacity, size_t* out_size) try {
   if (ctx == nullptr || y == nullptr || out_size == nullptr || params == nullptr) return SJB_ERR_ARG;
   *out_size = 0;
   ctx->lanes[0].last_size = 0;
@@ -1205,9 +1211,9 @@ int sjb_encode_planar(sjb_context* ctx, const uint8_t* y, long long y_stride, co
   ctx->lanes[0].launches = 0;
   RC(EncodePlanarOnLane(ctx, y, y_stride, u, u_stride, v, v_stride, uv_step, on_device, width, height, params));
   return FinishSingle(ctx, out, out_on_device, out_capacity, out_size);
-}
+} SJB_NOTHROW_END
 
-int sjb_set_score_table(const uint8_t* table, size_t size) {
+int sjb_set_score_table(const uint8_t* table, size_t size) try {
   std::lock_guard<std::mutex> lock(g_table_mutex);
   if (table == nullptr) {
     g_score_table.clear();
@@ -1219,26 +1225,26 @@ int sjb_set_score_table(const uint8_t* table, size_t size) {
   g_score_table.assign(table, table + size);
   ++g_score_table_version;
   return SJB_OK;
-}
+} SJB_NOTHROW_END
 
-int sjb_has_score_table(void) {
+int sjb_has_score_table(void) try {
   std::lock_guard<std::mutex> lock(g_table_mutex);
   LoadScoreTableFromEnvLocked();
   return g_score_table.empty() ? 0 : 1;
-}
+} SJB_NOTHROW_END
 
 int sjb_riskiness(sjb_context* ctx, const uint8_t* rgb, int rgb_on_device, int width, int height, long long stride,
-                  int* yuv_mode, float* risk) {
+                  int* yuv_mode, float* risk) try {
   if (ctx == nullptr || yuv_mode == nullptr) return SJB_ERR_ARG;
   ctx->err.clear();
   const uint8_t* d_rgb;
   long long d_stride;
   RC(ResidentRgb(ctx, rgb, rgb_on_device, width, height, stride, &d_rgb, &d_stride));
   return RiskinessOnDevice(ctx, d_rgb, d_stride, width, height, yuv_mode, risk);
-}
+} SJB_NOTHROW_END
 
 int sjb_sharp_yuv(sjb_context* ctx, const uint8_t* rgb, int rgb_on_device, int width, int height, long long stride,
-                  uint8_t* y, uint8_t* u, uint8_t* v, int out_on_device) {
+                  uint8_t* y, uint8_t* u, uint8_t* v, int out_on_device) try {
   if (ctx == nullptr || y == nullptr || u == nullptr || v == nullptr) return SJB_ERR_ARG;
   ctx->err.clear();
   const uint8_t* d_rgb;
@@ -1254,14 +1260,14 @@ int sjb_sharp_yuv(sjb_context* ctx, const uint8_t* rgb, int rgb_on_device, int w
   CU(cudaMemcpyAsync(v, dv, cw * ch, kind, L->stream));
   CU(cudaStreamSynchronize(L->stream));
   return SJB_OK;
-}
+} SJB_NOTHROW_END
 
-int sjb_context_set_search(sjb_context* ctx, sjb_search* search) {
+int sjb_context_set_search(sjb_context* ctx, sjb_search* search) try {
   if (ctx == nullptr) return SJB_ERR_ARG;
   if (search && (search->next_matrix == nullptr || search->update == nullptr || search->passes < 1)) return SJB_ERR_ARG;
   ctx->search = search;
   return SJB_OK;
-}
+} SJB_NOTHROW_END
 
 // ---- stage-level entry points ----------------------------------------------------------------
 static int StageF1(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
@@ -1287,7 +1293,7 @@ static int StageF1(sjb_context* ctx, const uint8_t* pix, int width, int height, 
 }
 
 int sjb_stage_coefficients(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
-                           const sjb_params* params, int quantise, int16_t* coef, uint8_t* nzmask) {
+                           const sjb_params* params, int quantise, int16_t* coef, uint8_t* nzmask) try {
   if (ctx == nullptr || pix == nullptr || coef == nullptr) return SJB_ERR_ARG;
   Plan plan;
   FrameSet fs;
@@ -1308,10 +1314,10 @@ int sjb_stage_coefficients(sjb_context* ctx, const uint8_t* pix, int width, int 
     for (int s = 0; s < 4; ++s) memcpy(coef + g * 64 + 16 * s, src + s * kCoefSectorStride, 16 * sizeof(int16_t));
   }
   return SJB_OK;
-}
+} SJB_NOTHROW_END
 
 int sjb_stage_histogram(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
-                        const sjb_params* params, int32_t* counts) {
+                        const sjb_params* params, int32_t* counts) try {
   if (ctx == nullptr || pix == nullptr || counts == nullptr) return SJB_ERR_ARG;
   Plan plan;
   FrameSet fs;
@@ -1324,10 +1330,10 @@ int sjb_stage_histogram(sjb_context* ctx, const uint8_t* pix, int width, int hei
   CU(cudaMemcpyAsync(counts, D->hist, sizeof(D->hist[0]), cudaMemcpyDeviceToHost, L->stream));
   CU(cudaStreamSynchronize(L->stream));
   return SJB_OK;
-}
+} SJB_NOTHROW_END
 
 int sjb_stage_symbol_stats(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
-                           const sjb_params* params, uint32_t* freq_ac, uint32_t* freq_dc) {
+                           const sjb_params* params, uint32_t* freq_ac, uint32_t* freq_dc) try {
   if (ctx == nullptr || pix == nullptr || freq_ac == nullptr || freq_dc == nullptr) return SJB_ERR_ARG;
   Plan plan;
   FrameSet fs;
@@ -1344,7 +1350,7 @@ int sjb_stage_symbol_stats(sjb_context* ctx, const uint8_t* pix, int width, int 
     memcpy(freq_dc + 12 * c, L->host->freq[0] + 272 * c + 256, 12 * sizeof(uint32_t));
   }
   return SJB_OK;
-}
+} SJB_NOTHROW_END
 
 int sjb_last_timings(const sjb_context* ctx, float ms[3]) {
   if (ctx == nullptr || ms == nullptr) return SJB_ERR_ARG;
@@ -1356,7 +1362,7 @@ int sjb_last_timings(const sjb_context* ctx, float ms[3]) {
 
 int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int width, int height,
                      long long stride, const sjb_params* params, int iters, float* total_ms,
-                     float* f1_ms, size_t* jpeg_bytes, unsigned long long* launches) {
+                     float* f1_ms, size_t* jpeg_bytes, unsigned long long* launches) try {
   if (ctx == nullptr || dev_pix == nullptr || n <= 0 || iters <= 0 || total_ms == nullptr) return SJB_ERR_ARG;
   ctx->err.clear();
   ctx->lanes[0].last_size = 0;
@@ -1415,11 +1421,11 @@ int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int
     for (int l = 0; l < nl; ++l) *launches += ctx->lanes[l].launches;
   }
   return SJB_OK;
-}
+} SJB_NOTHROW_END
 
 int sjb_bench_f1(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int width, int height,
                  long long stride, const sjb_params* params, int iters, float* ms_per_launch,
-                 int* frames_per_launch) {
+                 int* frames_per_launch) try {
   if (ctx == nullptr || dev_pix == nullptr || n <= 0 || iters <= 0 || ms_per_launch == nullptr) return SJB_ERR_ARG;
   ctx->err.clear();
   ctx->lanes[0].last_size = 0;
@@ -1453,7 +1459,7 @@ int sjb_bench_f1(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int wid
   *ms_per_launch = ms / (static_cast<float>(groups) * iters);
   if (frames_per_launch) *frames_per_launch = B;
   return SJB_OK;
-}
+} SJB_NOTHROW_END
 
 // ---------------------------------------------------------------------------------------------
 // Row stripes of pictures split across GPUs (BASELINE.json config 5).  A session
@@ -1477,7 +1483,7 @@ struct sjb_stripes {
 extern "C" {
 
 int sjb_stripes_create(sjb_context* ctx, int n, int width, int stripe_height, const sjb_params* params,
-                       sjb_stripes** out) {
+                       sjb_stripes** out) try {
   if (ctx == nullptr || out == nullptr || n <= 0) return SJB_ERR_ARG;
   *out = nullptr;
   ctx->err.clear();
@@ -1494,7 +1500,7 @@ int sjb_stripes_create(sjb_context* ctx, int n, int width, int stripe_height, co
   }
   *out = s;
   return SJB_OK;
-}
+} SJB_NOTHROW_END
 
 void sjb_stripes_destroy(sjb_stripes* s) {
   if (s == nullptr) return;
@@ -1508,7 +1514,7 @@ void sjb_stripes_destroy(sjb_stripes* s) {
 }
 
 int sjb_stripes_transform(sjb_stripes* s, const uint8_t* const* pix, int pix_on_device, long long stride,
-                          int* last_dc) {
+                          int* last_dc) try {
   if (s == nullptr || pix == nullptr || last_dc == nullptr) return SJB_ERR_ARG;
   sjb_context* ctx = s->ctx;
   ctx->err.clear();
@@ -1560,9 +1566,9 @@ int sjb_stripes_transform(sjb_stripes* s, const uint8_t* const* pix, int pix_on_
   s->transformed = true;
   s->coded = false;
   return SJB_OK;
-}
+} SJB_NOTHROW_END
 
-int sjb_stripes_code(sjb_stripes* s, const int* dc_pred, unsigned long long* bits) {
+int sjb_stripes_code(sjb_stripes* s, const int* dc_pred, unsigned long long* bits) try {
   if (s == nullptr || dc_pred == nullptr || bits == nullptr || !s->transformed) return SJB_ERR_ARG;
   sjb_context* ctx = s->ctx;
   ctx->err.clear();
@@ -1608,11 +1614,11 @@ int sjb_stripes_code(sjb_stripes* s, const int* dc_pred, unsigned long long* bit
   }
   s->coded = true;
   return SJB_OK;
-}
+} SJB_NOTHROW_END
 
 int sjb_stripes_finish(sjb_stripes* s, const unsigned long long* bit_offsets, int is_first, int is_last,
                        uint8_t* const* out, size_t out_capacity, size_t* sizes, unsigned char* head_byte,
-                       unsigned char* tail_byte, unsigned char* tail_bits) {
+                       unsigned char* tail_byte, unsigned char* tail_bits) try {
   if (s == nullptr || bit_offsets == nullptr || out == nullptr || sizes == nullptr || head_byte == nullptr ||
       tail_byte == nullptr || tail_bits == nullptr || !s->coded)
     return SJB_ERR_ARG;
@@ -1659,10 +1665,10 @@ int sjb_stripes_finish(sjb_stripes* s, const unsigned long long* bit_offsets, in
   s->coded = false;
   s->transformed = false;
   return rc;
-}
+} SJB_NOTHROW_END
 
 int sjb_picture_header(const sjb_params* params, int width, int height, uint8_t* out, size_t out_capacity,
-                       size_t* out_size) {
+                       size_t* out_size) try {
   if (params == nullptr || out_size == nullptr) return SJB_ERR_ARG;
   Plan plan;
   const int pstep = (params->pix_fmt != SJB_PIX_RGB) ? 4 : 3;
@@ -1679,6 +1685,6 @@ int sjb_picture_header(const sjb_params* params, int width, int height, uint8_t*
   if (out == nullptr || h.size() > out_capacity) return SJB_ERR_CAPACITY;
   memcpy(out, h.data(), h.size());
   return SJB_OK;
-}
+} SJB_NOTHROW_END
 
 }  // extern "C"
