@@ -153,6 +153,27 @@ def test_coefficient_layout_is_a_sector_interleaved_bijection(emul):
     assert emul.emul_coef_offset(3 * 8192 * 8192 - 1, 63) == (3 * 8192 * 8192) * 64 - 1
 
 
+def test_hot_kernels_keep_their_resource_budget():
+    """ptxas report of the build (csrc/kernels.ptxas.log, written by the Makefile): the residency the
+    design counts on -- 16 CTAs per SM of the 4:2:0 F1 kernel (128 registers, no spill), 5 CTAs of
+    the entropy kernel (40 registers, no spill, below 45 KB of shared memory) -- is a build-time
+    property; a source change that breaks it shows up here, not as a slower bench line."""
+    log = os.path.join(ROOT, "sjpeg_b200", "csrc", "kernels.ptxas.log")
+    if not os.path.exists(log):
+        pytest.skip("no ptxas log (library not built by the Makefile here)")
+    text = open(log).read()
+    entries = {}
+    for m in re.finditer(r"Compiling entry function '(\S+)' for 'sm_100a'\n.*\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores,"
+                         r" (\d+) bytes spill loads\n.*Used (\d+) registers(?:.*?(\d+) bytes smem)?", text):
+        entries[m.group(1)] = dict(stack=int(m.group(2)), spill=int(m.group(3)) + int(m.group(4)), regs=int(m.group(5)),
+                                   smem=int(m.group(6) or 0))
+    f1 = [v for k, v in entries.items() if "f1_fast_kernelILi1ELb0ELi0E" in k]
+    ent = [v for k, v in entries.items() if "entropy_pack_kernel" in k]
+    assert len(f1) == 1 and len(ent) == 1, sorted(entries)
+    assert f1[0]["regs"] <= 128 and f1[0]["spill"] == 0 and 16 * (f1[0]["smem"] + 1024) <= 228 * 1024, f1
+    assert ent[0]["regs"] <= 40 and ent[0]["spill"] == 0 and 5 * (ent[0]["smem"] + 1024) <= 228 * 1024, ent
+
+
 def test_host_helpers_without_gpu():
     import sjpeg_b200
     L = sjpeg_b200.lib()
