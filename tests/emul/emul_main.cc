@@ -234,6 +234,16 @@ size_t emul_encode(const uint8_t* pix, int w, int h, long long stride, int mode,
 
 void emul_free(uint8_t* p) { free(p); }
 
+// host_codec.cc::AnalyseHistograms on its own (the product's restatement of histogram.cc:126-315)
+void emul_analyse_histo(const int32_t* counts, int nb_comps, uint8_t* quant /*[2][64]*/, const uint8_t* min_quant,
+                        int qdl, int qdc) {
+  uint8_t q[2][64], mq[2][64];
+  memcpy(q, quant, 128);
+  memcpy(mq, min_quant, 128);
+  AnalyseHistograms(counts, nb_comps, q, mq, qdl, qdc);
+  memcpy(quant, q, 128);
+}
+
 // the entropy kernel's walk order of busy tiles (block_ops.cuh::walk_order)
 unsigned emul_walk_order(unsigned first, unsigned count, unsigned i, int mcu_blocks) {
   return walk_order(first, count, i, mcu_blocks);

@@ -5,6 +5,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -29,6 +30,7 @@ def emul():
     E.emul_free.argtypes = [_u8p]
     E.emul_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p]
     E.emul_sharp_yuv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
+    E.emul_analyse_histo.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     E.emul_riskiness.restype = C.c_int
     E.emul_riskiness.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.POINTER(C.c_float)]
     return E
@@ -151,6 +153,66 @@ def test_coefficient_layout_is_a_sector_interleaved_bijection(emul):
             assert len(line) == 1
     # block index arithmetic is 32-bit: the largest picture (65535 x 65535, 4:4:4) still fits
     assert emul.emul_coef_offset(3 * 8192 * 8192 - 1, 63) == (3 * 8192 * 8192) * 64 - 1
+
+
+def test_histogram_analysis_baseline_isa_path():
+    """The same comparison in a fresh process with SJPEG_B200_NO_AVX2=1, so that the non-AVX2 build of the
+    inner sums (what a CPU without AVX2 would run) is exercised as well."""
+    env = dict(os.environ, SJPEG_B200_NO_AVX2="1", PYTHONPATH=os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", os.path.join(ROOT, "tests", "test_host_logic.py"),
+                        "-k", "equals_oracle_on_hard_histograms"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_histogram_analysis_equals_oracle_on_hard_histograms(emul):
+    """host_codec.cc::AnalyseHistograms (int64 sums over squeezed bins, one branch-free term) against the
+    oracle's line-by-line restatement of histogram.cc:126-315, on histograms chosen to hit what the
+    whole-file tests rarely do: counts large enough for the 32-bit products to wrap, single-bin and
+    full-width rows, tiny and saturated matrices, restricted minima, every delta limit."""
+    rng = np.random.default_rng(20261017)
+    lib = O.oracle()
+    cases = 0
+    for trial in range(160):
+        counts = np.zeros((2, 64, 129), np.int64)
+        kind = trial % 8
+        for m in range(2):
+            for pos in range(64):
+                width = int(rng.integers(1, 129))
+                if kind == 0:      # geometric, photographic
+                    row = (rng.integers(1, 200000) * np.exp(-rng.uniform(0.02, 0.6) * np.arange(width))).astype(np.int64)
+                elif kind == 1:    # flat and huge: products wrap
+                    row = rng.integers(0, 40_000_000, width)
+                elif kind == 2:    # single bin
+                    row = np.zeros(width, np.int64); row[-1] = rng.integers(1, 1 << 30)
+                elif kind == 3:    # sparse spikes
+                    row = np.where(rng.random(width) < 0.1, rng.integers(1, 5_000_000, width), 0)
+                elif kind == 4:    # nearly empty (density rule)
+                    row = np.where(rng.random(width) < 0.02, 1, 0)
+                elif kind == 5:    # bimodal
+                    row = rng.integers(0, 3000, width) + np.where(np.arange(width) > width // 2, 50000, 0)
+                elif kind == 6:    # small counts
+                    row = rng.integers(0, 4, width)
+                else:              # everything at once
+                    row = rng.integers(0, 1 << int(rng.integers(1, 31)), width)
+                counts[m, pos, :width] = row
+        c32 = np.ascontiguousarray(counts.astype(np.int32))
+        for quant_kind in range(3):
+            if quant_kind == 0:
+                quant = rng.integers(1, 256, (2, 64)).astype(np.uint8)
+            elif quant_kind == 1:
+                quant = rng.integers(1, 14, (2, 64)).astype(np.uint8)
+            else:
+                quant = rng.integers(240, 256, (2, 64)).astype(np.uint8)
+            minq = np.minimum(quant, rng.integers(1, 256, (2, 64))).astype(np.uint8) if trial % 3 else np.ones((2, 64), np.uint8)
+            for (qdl, qdc) in ((12, 1), (0, 0), (5, 12), (12, 12), (1, 0)):
+                for comps in (3, 1):
+                    a = np.ascontiguousarray(quant.copy()); b = np.ascontiguousarray(quant.copy())
+                    emul.emul_analyse_histo(c32.ctypes.data, comps, a.ctypes.data, minq.ctypes.data, qdl, qdc)
+                    lib.sjo_analyse_histo(C.c_void_p(c32.ctypes.data), comps, C.c_void_p(b.ctypes.data),
+                                          C.c_void_p(minq.ctypes.data), qdl, qdc)
+                    assert a.tobytes() == b.tobytes(), (trial, quant_kind, qdl, qdc, comps)
+                    cases += 1
+    assert cases == 160 * 3 * 5 * 2
 
 
 def test_hot_kernels_keep_their_resource_budget():
