@@ -20,9 +20,12 @@ _u8p = C.POINTER(C.c_uint8)
 @pytest.fixture(scope="module")
 def emul():
     so = os.path.join(EMUL_DIR, "libemul.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so,
-                    os.path.join(EMUL_DIR, "emul_main.cc"),
-                    os.path.join(ROOT, "sjpeg_b200", "csrc", "host_codec.cc")], check=True)
+    if not (os.environ.get("SJB_EMUL_REUSE") == "1" and os.path.exists(so)):   # a child run reuses the parent's build
+        tmp = so + ".%d.tmp" % os.getpid()
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", tmp,
+                        os.path.join(EMUL_DIR, "emul_main.cc"),
+                        os.path.join(ROOT, "sjpeg_b200", "csrc", "host_codec.cc")], check=True)
+        os.replace(tmp, so)      # atomic: a process that has the old file mapped keeps it
     E = C.CDLL(so)
     E.emul_encode.restype = C.c_size_t
     E.emul_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int,
@@ -155,10 +158,10 @@ def test_coefficient_layout_is_a_sector_interleaved_bijection(emul):
     assert emul.emul_coef_offset(3 * 8192 * 8192 - 1, 63) == (3 * 8192 * 8192) * 64 - 1
 
 
-def test_histogram_analysis_baseline_isa_path():
+def test_histogram_analysis_baseline_isa_path(emul):
     """The same comparison in a fresh process with SJPEG_B200_NO_AVX2=1, so that the non-AVX2 build of the
     inner sums (what a CPU without AVX2 would run) is exercised as well."""
-    env = dict(os.environ, SJPEG_B200_NO_AVX2="1", PYTHONPATH=os.path.join(ROOT, "tests"))
+    env = dict(os.environ, SJPEG_B200_NO_AVX2="1", SJB_EMUL_REUSE="1", PYTHONPATH=os.path.join(ROOT, "tests"))
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", os.path.join(ROOT, "tests", "test_host_logic.py"),
                         "-k", "equals_oracle_on_hard_histograms"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
