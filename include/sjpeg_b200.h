@@ -222,6 +222,12 @@ int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int
                      long long stride, const sjb_params* params, int iters, float* total_ms,
                      float* f1_ms, size_t* jpeg_bytes, unsigned long long* launches);
 
+/* Host copy of the JPEG that the LAST round of the most recent sjb_bench_device call left in HBM
+ * for picture `index` (so that the bytes of the timed path itself can be checked).  SJB_ERR_ARG
+ * when a later group of that call has reused the picture's buffers (more groups per round than
+ * lanes): bench fewer pictures per call to verify them all. */
+int sjb_bench_output(sjb_context* ctx, int index, uint8_t* out, size_t out_capacity, size_t* out_size);
+
 /* Times ONLY the fused F1 kernel (convert + fDCT + quantise): launches it back to back over the
  * n device pictures in groups of *frames_per_launch pictures (the group size the encoder itself
  * uses for this geometry), 'iters' rounds, on one stream; ms_per_launch = CUDA-event time /

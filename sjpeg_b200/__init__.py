@@ -72,6 +72,7 @@ _SIGNATURES = {
     "sjb_bench_device": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                    C.c_longlong, C.POINTER(Params), C.c_int, C.POINTER(C.c_float),
                                    C.POINTER(C.c_float), C.POINTER(C.c_size_t), C.POINTER(C.c_ulonglong)]),
+    "sjb_bench_output": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "sjb_bench_f1": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_longlong,
                                C.POINTER(Params), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "sjb_stripes_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]),
@@ -263,6 +264,13 @@ class Context:
         _check(self._ctx, rc, "sjb_bench_device")
         return total.value, f1.value, nbytes.value, launches.value
 
+    def bench_output(self, index, cap=64 << 20):
+        """bytes of picture `index` as the last round of bench_device left them in HBM"""
+        size = C.c_size_t(0)
+        out = np.empty(cap, np.uint8)
+        rc = lib().sjb_bench_output(self._ctx, index, out.ctypes.data, cap, C.byref(size))
+        _check(self._ctx, rc, "sjb_bench_output")
+        return out[:size.value].tobytes()
 
     def bench_f1(self, dev_ptrs, width, height, stride, params, iters):
         n = len(dev_ptrs)

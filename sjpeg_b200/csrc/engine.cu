@@ -121,6 +121,11 @@ struct sjb_context {
   DeviceBuffer sharp_scratch, sharp_planes, sharp_tabs, risk_table, risk_sums;
   unsigned long long* risk_host = nullptr;   // pinned, 3 sums
   int risk_table_version = 0;                // version of the process-wide table held in risk_table
+  // where sjb_bench_device left each picture of its last round: {lane, slot, turn}; a picture can be
+  // fetched (sjb_bench_output) while no later group has reused its lane
+  struct BenchSlot { int lane, slot, turn; };
+  std::vector<BenchSlot> bench_slots;
+  int bench_last_turn[4] = {-1, -1, -1, -1};
   HostStager stager;                         // threaded upload of pageable pictures (host_stager.h)
   bool many_uploads = false;                 // set by the batch / stripe entry points: uploads come back to back
 };
@@ -196,7 +201,7 @@ int MakePlan(int width, int height, long long stride, const sjb_params* params, 
   plan->stream_words = ((nb * kWorstBitsPerBlock / 32 + 64) + 3) & ~static_cast<size_t>(3);
   plan->out_capacity = (kHeaderReserve + 2 * plan->stream_words * 4 + 16 + 255) & ~static_cast<size_t>(255);
   plan->nb_tiles = (nb + kTileBlocks - 1) / kTileBlocks + 1;   // + the tile counter of the entropy kernel
-  plan->ff_tiles = (plan->stream_words * 4 + kStuffTileBytes - 1) / kStuffTileBytes;
+  plan->ff_tiles = (plan->stream_words * 4 + kStuffTileBytes - 1) / kStuffTileBytes + 1;   // + the tile counter
   const size_t coef_bytes = nb * 128;
   plan->group = static_cast<int>(std::min<size_t>(kMaxGroup, std::max<size_t>(1, GroupCoefBudget() / coef_bytes)));
   return SJB_OK;
@@ -944,34 +949,50 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
     return rc;
   };
   int first_err = SJB_OK;
+  for (int i = 0; i < n; ++i) sizes[i] = 0;
+  // A failure in the middle of the pipeline must not leave copies in flight that read the caller's
+  // (pinned) inputs or write the caller's outputs after we return: every lane is drained first.
+  auto abort_batch = [&](int rc) -> int {
+    for (int l = 0; l < nl; ++l) {
+      if (ctx->lanes[l].stream) cudaStreamSynchronize(ctx->lanes[l].stream);
+      ctx->lanes[l].words_dirty = true;
+    }
+    cudaGetLastError();
+    return rc;
+  };
   for (int k = 0; k < groups; ++k) {
     Lane* L = &ctx->lanes[k % nl];
     if (k >= nl) {
       const int rc = drain(k - nl);
+      if (rc == SJB_ERR_CUDA || rc == SJB_ERR_NOMEM) return abort_batch(rc);
       if (rc != SJB_OK && first_err == SJB_OK) first_err = rc;
     }
     FrameSet fs;
     FillFrameSet(plan, stride, &fs);
     fs.frames = std::min(B, n - k * B);
-    for (int f = 0; f < fs.frames; ++f) {
+    int rc = SJB_OK;
+    for (int f = 0; f < fs.frames && rc == SJB_OK; ++f) {
       fs.pix[f] = pix[k * B + f];
       if (!pix_on_device) {
         long long ds = stride;
-        RC(UploadPicture(ctx, L, pix[k * B + f], plan, stride, f, &fs.pix[f], &ds));
+        rc = UploadPicture(ctx, L, pix[k * B + f], plan, stride, f, &fs.pix[f], &ds);
         fs.stride = ds;
       }
     }
-    const int rc = EncodeGroup(ctx, L, fs, plan, false);
-    if (rc != SJB_OK) {
-      L->words_dirty = true;
-      return rc;
-    }
+    if (rc == SJB_OK) rc = EncodeGroup(ctx, L, fs, plan, false);
+    if (rc != SJB_OK) return abort_batch(rc);
   }
   for (int k = std::max(0, groups - nl); k < groups; ++k) {
     const int rc = drain(k);
+    if (rc == SJB_ERR_CUDA || rc == SJB_ERR_NOMEM) return abort_batch(rc);
     if (rc != SJB_OK && first_err == SJB_OK) first_err = rc;
   }
-  for (int l = 0; l < nl; ++l) CU(cudaStreamSynchronize(ctx->lanes[l].stream));
+  for (int l = 0; l < nl; ++l) {
+    if (cudaStreamSynchronize(ctx->lanes[l].stream) != cudaSuccess) {
+      ctx->err = "cudaStreamSynchronize failed at the end of the batch";
+      return abort_batch(SJB_ERR_CUDA);
+    }
+  }
   return first_err;
 } SJB_NOTHROW_END
 
@@ -1393,13 +1414,18 @@ int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int
   Lane* L0 = &ctx->lanes[0];
   CU(cudaEventRecord(t0, L0->stream));
   for (int l = 1; l < nl; ++l) CU(cudaStreamWaitEvent(ctx->lanes[l].stream, t0, 0));
+  ctx->bench_slots.assign(n, sjb_context::BenchSlot{-1, -1, -1});
   for (int it = 0, turn = 0; it < iters; ++it) {
     for (int k = 0; k < groups; ++k, ++turn) {
       Lane* L = &ctx->lanes[turn % nl];
       FrameSet fs;
       FillFrameSet(plan, stride, &fs);
       fs.frames = std::min(B, n - k * B);
-      for (int f = 0; f < fs.frames; ++f) fs.pix[f] = dev_pix[k * B + f];
+      for (int f = 0; f < fs.frames; ++f) {
+        fs.pix[f] = dev_pix[k * B + f];
+        ctx->bench_slots[k * B + f] = sjb_context::BenchSlot{turn % nl, f, turn};
+      }
+      ctx->bench_last_turn[turn % nl] = turn;
       RC(EncodeGroup(ctx, L, fs, plan, /*timed=*/turn % nl == 0));
     }
   }
@@ -1420,6 +1446,22 @@ int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int
     *launches = 0;
     for (int l = 0; l < nl; ++l) *launches += ctx->lanes[l].launches;
   }
+  return SJB_OK;
+} SJB_NOTHROW_END
+
+int sjb_bench_output(sjb_context* ctx, int index, uint8_t* out, size_t out_capacity, size_t* out_size) try {
+  if (ctx == nullptr || out_size == nullptr || index < 0 || index >= static_cast<int>(ctx->bench_slots.size()))
+    return SJB_ERR_ARG;
+  const sjb_context::BenchSlot b = ctx->bench_slots[index];
+  if (b.lane < 0 || ctx->bench_last_turn[b.lane] != b.turn) return SJB_ERR_ARG;   // overwritten by a later group
+  CU(cudaSetDevice(ctx->device));
+  Lane* L = &ctx->lanes[b.lane];
+  CU(cudaStreamSynchronize(L->stream));
+  const size_t size = static_cast<size_t>(L->host->info[b.slot].out_size);
+  *out_size = size;
+  if (out == nullptr || size > out_capacity) return SJB_ERR_CAPACITY;
+  CU(cudaMemcpyAsync(out, L->gb.out + b.slot * L->gb.out_pitch, size, cudaMemcpyDeviceToHost, L->stream));
+  CU(cudaStreamSynchronize(L->stream));
   return SJB_OK;
 } SJB_NOTHROW_END
 
@@ -1626,6 +1668,19 @@ int sjb_stripes_finish(sjb_stripes* s, const unsigned long long* bit_offsets, in
   ctx->err.clear();
   CU(cudaSetDevice(ctx->device));
   const int groups = static_cast<int>(s->fsets.size());
+  // A stripe that is neither the first nor the last and whose bits all fall inside the byte it
+  // shares with its predecessor (offset % 8 + bits < 8: only a flat 4:0:0 stripe of one block can
+  // be that short) owns no byte boundary at all; the (head, tail) hand-over cannot express three
+  // stripes meeting in one byte, so such a partition is refused instead of mis-assembled.
+  for (int k = 0; k < groups; ++k) {
+    for (int f = 0; f < s->fsets[k].frames; ++f) {
+      const unsigned long long off = bit_offsets[k * kMaxGroup + f] & 7;
+      if (!is_first && off != 0 && off + s->sets[k]->host->info[f].total_bits < 8) {
+        ctx->err = "row stripe shorter than the byte it shares with its neighbours: use fewer stripes";
+        return SJB_ERR_ARG;
+      }
+    }
+  }
   for (int k = 0; k < groups; ++k) {
     Lane* L = s->sets[k];
     const FrameSet& fs = s->fsets[k];

@@ -1062,8 +1062,7 @@ symbol_stats_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
 // S: byte stuffing (bit_writer.h:172-196, bit_writer.cc:107-116, headers.cc:262-268).
 // The word stream holds ceil(total_bits/8) bytes, MSB-first inside each word; the last byte is
 // padded with 1-bits.  Every 0xFF byte is followed by 0x00.  Tile = 4096 stream bytes per CTA
-// iteration, 16 bytes per thread; persistent CTAs stride over the tiles (all CTAs are resident,
-// so the look-back chain always makes progress).
+// iteration, 16 bytes per thread; persistent CTAs claim the tiles of a picture from a counter.
 // -------------------------------------------------------------------------------------------
 // 16 bytes of the byte-aligned stream R = (shift zero bits) ++ packed bits, starting at byte0
 // (multiple of 16).  end_bits = shift + total_bits; bytes at or past ceil(end_bits/8) read as 0.
@@ -1100,9 +1099,14 @@ __global__ void __launch_bounds__(kStuffThreads)
 stuff_kernel(GroupBuffers gb, const __grid_constant__ StuffArgs args) {
   __shared__ uint32_t scratch[33];
   __shared__ unsigned long long tile_prefix;
+  __shared__ unsigned long long claimed[2];
   const int frame = blockIdx.y;
   uint32_t* stream = gb.words + frame * gb.words_pitch;
   unsigned long long* state = gb.ff_state + frame * gb.ff_state_pitch;
+  // Tiles are claimed from a per-picture counter (last slot of the picture's descriptor row), as
+  // in the entropy kernel: a tile is only ever owned by a running CTA, so the look-back chain makes
+  // progress whatever the grid size and whatever else occupies the SMs.
+  unsigned long long* counter = state + (gb.ff_state_pitch - 1);
   const unsigned shift = args.shift[frame], flags = args.flags[frame];
   const bool last = (flags & kStuffLast) != 0;
   const unsigned long long end_bits = gb.info[frame].total_bits + shift;
@@ -1113,7 +1117,13 @@ stuff_kernel(GroupBuffers gb, const __grid_constant__ StuffArgs args) {
   const unsigned pad = last ? static_cast<unsigned>((0 - end_bits) & 7) : 0;
   const unsigned long long tiles = (((end_bits + 7) >> 3) + kStuffTileBytes - 1) / kStuffTileBytes;
   uint8_t* out = gb.out + frame * gb.out_pitch + args.header_len[frame];
-  for (unsigned long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+  if (threadIdx.x == 0) claimed[0] = atomicAdd(counter, 1ull);
+  __syncthreads();
+  for (int it = 0;; ++it) {
+    const unsigned long long t = claimed[it & 1];
+    if (t >= tiles) break;
+    // the next claim travels while this tile is processed (read after the barriers below)
+    if (threadIdx.x == 0) claimed[(it + 1) & 1] = atomicAdd(counter, 1ull);
     const unsigned long long byte0 = t * kStuffTileBytes + threadIdx.x * 16ull;
     uint4 w = load_stream16(stream, byte0, end_bits, shift);
     if (pad && byte0 < b1 && b1 - byte0 <= 16) {             // the padded byte is in here
@@ -1169,7 +1179,7 @@ stuff_kernel(GroupBuffers gb, const __grid_constant__ StuffArgs args) {
         dst[1] = 0xd9;
       }
     }
-    __syncthreads();   // tile_prefix reused next iteration
+    __syncthreads();   // tile_prefix and the claim slots are reused next iteration
   }
 }
 
@@ -1231,6 +1241,21 @@ __global__ void last_dc_kernel(const __grid_constant__ FrameSet fs, GroupBuffers
 }
 
 unsigned cdiv(size_t a, size_t b) { return static_cast<unsigned>((a + b - 1) / b); }
+
+// SMs of the current device (grids of the persistent kernels are sized from it), cached per device;
+// concurrent host threads may race to fill a slot with the same value.
+unsigned SmCount() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return static_cast<unsigned>(n);
+}
 
 }  // namespace
 
@@ -1297,7 +1322,7 @@ void LaunchRequantize(const FrameSet& fs, const GroupBuffers& gb, const int16_t*
 void LaunchQuantError(const FrameSet& fs, const GroupBuffers& gb, const int16_t* raw, unsigned long long* err,
                       cudaStream_t s) {
   unsigned grid = cdiv(fs.blocks_per_frame, 256);
-  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid > SmCount() * 8) grid = SmCount() * 8;
   quant_error_kernel<<<dim3(grid, fs.frames), 256, 0, s>>>(fs, gb, raw, err);
 }
 
@@ -1313,7 +1338,7 @@ void LaunchHistogram(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s)
     init[dev].store(true, std::memory_order_release);
   }
   unsigned grid = cdiv(static_cast<size_t>(fs.blocks_per_frame) * 8, 256 * 16);
-  const unsigned cap = 148 * 3 / (fs.frames > 0 ? fs.frames : 1) + 1;
+  const unsigned cap = SmCount() * 3 / (fs.frames > 0 ? fs.frames : 1) + 1;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   histogram_kernel<<<dim3(grid, fs.frames), 256, smem, s>>>(fs, gb);
@@ -1325,7 +1350,7 @@ void LaunchTrellis(const FrameSet& fs, const GroupBuffers& gb, const int16_t* ra
 
 void LaunchSymbolStats(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {
   unsigned grid = cdiv(fs.blocks_per_frame, kTileBlocks);
-  const unsigned cap = 148 * 8 / (fs.frames > 0 ? fs.frames : 1) + 1;
+  const unsigned cap = SmCount() * 8 / (fs.frames > 0 ? fs.frames : 1) + 1;
   if (grid > cap) grid = cap;
   symbol_stats_kernel<<<dim3(grid, fs.frames), kTileBlocks, 0, s>>>(fs, gb);
 }
@@ -1333,7 +1358,7 @@ void LaunchSymbolStats(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t 
 void LaunchEntropyPack(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {
   // persistent CTAs claiming tiles from a counter: about 5 CTAs per SM over all pictures of the group
   const unsigned tiles = cdiv(fs.blocks_per_frame, kTileBlocks);
-  unsigned grid = 148 * kECtasPerSm / (fs.frames > 0 ? fs.frames : 1);
+  unsigned grid = SmCount() * kECtasPerSm / (fs.frames > 0 ? fs.frames : 1);
   if (grid < 1) grid = 1;
   if (grid > tiles) grid = tiles;
   entropy_pack_kernel<<<dim3(grid, fs.frames), kEThreads, 0, s>>>(fs, gb);
@@ -1344,9 +1369,10 @@ void LaunchLastDc(const FrameSet& fs, const GroupBuffers& gb, int* out, cudaStre
 }
 
 void LaunchStuff(const FrameSet& fs, const GroupBuffers& gb, const StuffArgs& args, cudaStream_t s) {
-  // persistent CTAs: all of them must be resident for the look-back to make progress
+  // persistent CTAs claiming tiles from a counter (no co-residency requirement): about one SM-full
+  // of threads per SM over all pictures of the group
   const size_t max_tiles = (gb.words_pitch * 4 + kStuffTileBytes - 1) / kStuffTileBytes;
-  unsigned grid = 148 * (1024 / kStuffThreads) / (fs.frames > 0 ? fs.frames : 1);
+  unsigned grid = SmCount() * (1024 / kStuffThreads) / (fs.frames > 0 ? fs.frames : 1);
   if (grid < 1) grid = 1;
   if (grid > max_tiles) grid = static_cast<unsigned>(max_tiles);
   stuff_kernel<<<dim3(grid, fs.frames), kStuffThreads, 0, s>>>(gb, args);

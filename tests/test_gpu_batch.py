@@ -1,0 +1,155 @@
+"""GPU tier, groups of pictures per launch: the paths bench.py times (device-resident input and
+output, 8 pictures per launch, several lanes) and the batch API with per-picture quantiser tables,
+Huffman tables and headers inside one launch (methods >= 1), on sparse, busy and mixed content.
+Every output is compared byte for byte with the oracle."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+_want_cache = {}
+
+
+def _want(key, rgb, w, h, q, method, mode):
+    k = (key, w, h, q, method, mode)
+    if k not in _want_cache:
+        _want_cache[k] = O.oracle_encode(rgb, w, h, 3 * w, float(q), method, mode)
+    return _want_cache[k]
+
+
+def _frame(kind, w, h, seed):
+    if kind in ("A", "B"):
+        return O.make_rgb(kind, w, h, seed)
+    rng = np.random.RandomState(seed)
+    if kind == "noise":
+        return rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    if kind == "flat":
+        return np.full((h, w, 3), seed & 255, np.uint8)
+    raise ValueError(kind)
+
+
+def _content(name, n, w, h):
+    """list of (key, frame): n pictures of one kind, or kinds mixed inside every group"""
+    kinds = {"A": ["A"], "B": ["B"], "noise": ["noise"], "mixed": ["A", "noise", "B", "flat", "B", "A"]}[name]
+    out = []
+    for i in range(n):
+        kind = kinds[i % len(kinds)]
+        seed = 1000 + i * 17 + len(name)
+        out.append(((kind, seed), _frame(kind, w, h, seed)))
+    return out
+
+
+def _encode_batch_device(ctx, frames, w, h, params, cap):
+    """device-resident pixels in, device-resident JPEGs out (pix_on_device = out_on_device = 1)"""
+    import torch
+    dev = [torch.from_numpy(f.reshape(-1)).cuda() for f in frames]
+    outs = [torch.zeros(cap, dtype=torch.uint8, device="cuda") for _ in frames]
+    torch.cuda.synchronize()
+    sizes = ctx.encode_batch([t.data_ptr() for t in dev], True, w, h, 3 * w, params,
+                             [t.data_ptr() for t in outs], True, cap)
+    torch.cuda.synchronize()
+    return [outs[i][:sizes[i]].cpu().numpy().tobytes() for i in range(len(frames))]
+
+
+def _encode_batch_host(ctx, frames, w, h, params, cap):
+    outs = [np.empty(cap, np.uint8) for _ in frames]
+    sizes = ctx.encode_batch([f.ctypes.data for f in frames], False, w, h, 3 * w, params,
+                             [o.ctypes.data for o in outs], False, cap)
+    return [outs[i][:sizes[i]].tobytes() for i in range(len(frames))]
+
+
+@pytest.mark.parametrize("shape", [(3840, 2160, 16), (1920, 1080, 17)], ids=["16x4K", "17x1080p"])
+def test_device_resident_batches(gpu_ctx, shape):
+    """the configuration of the headline number: groups of 8 device-resident pictures per launch,
+    JPEGs left in device memory; 17 pictures leave a ragged last group of one"""
+    import sjpeg_b200 as S
+    w, h, n = shape
+    frames = [O.make_rgb("B", w, h, 7654321 + f) for f in range(n)]
+    p = S.default_params(75, 0, S.YUV_420)
+    got = _encode_batch_device(gpu_ctx, frames, w, h, p, 4 << 20)
+    for i, f in enumerate(frames):
+        assert got[i] == O.oracle_encode(f, w, h, 3 * w, 75.0, 0, O.YUV_420), (w, h, i)
+
+
+def test_bench_device_outputs(gpu_ctx):
+    """sjb_bench_device is what bench.py times: its outputs (sjb_bench_output) after several rounds
+    over rotating lanes equal the oracle's, for a sparse and a busy picture set, methods 0 and 4"""
+    import torch
+    import sjpeg_b200 as S
+    w, h, n = 1920, 1080, 16
+    for kind, method in (("B", 0), ("A", 0), ("A", 4), ("noise", 1)):
+        frames = [_frame(kind, w, h, 4242 + f) for f in range(n)]
+        dev = [torch.from_numpy(f.reshape(-1)).cuda() for f in frames]
+        p = S.default_params(75, method, S.YUV_420)
+        for iters in (1, 3):
+            gpu_ctx.bench_device([t.data_ptr() for t in dev], w, h, 3 * w, p, iters)
+            for i, f in enumerate(frames):
+                assert gpu_ctx.bench_output(i) == _want((kind, 4242 + i), f, w, h, 75, method, O.YUV_420), \
+                    (kind, method, iters, i)
+
+
+@pytest.mark.parametrize("content", ["A", "B", "noise", "mixed"])
+@pytest.mark.parametrize("mode", [O.YUV_420, O.YUV_444, O.YUV_400])
+@pytest.mark.parametrize("method", [1, 4, 6, 7])
+def test_batch_matrix_methods_modes_content(gpu_ctx, method, mode, content):
+    """per-picture matrices / Huffman tables / headers inside one launch (gridDim.y > 1), host and
+    device-resident groups, group sizes with a ragged tail, several lanes in flight"""
+    import sjpeg_b200 as S
+    w, h = (331, 203) if content != "noise" else (200, 120)
+    p = S.default_params(75, method, mode)
+    for n in (3, 8, 9, 33):
+        items = _content(content, n, w, h)
+        frames = [f for _, f in items]
+        want = [_want(k, f, w, h, 75, method, mode) for k, f in items]
+        got = _encode_batch_device(gpu_ctx, frames, w, h, p, 1 << 20)
+        assert got == want, (method, mode, content, n, "device", [i for i in range(n) if got[i] != want[i]])
+        if n in (3, 9):
+            got = _encode_batch_host(gpu_ctx, frames, w, h, p, 1 << 20)
+            assert got == want, (method, mode, content, n, "host", [i for i in range(n) if got[i] != want[i]])
+
+
+@pytest.mark.parametrize("method", [0, 4, 7])
+def test_busy_batches_multi_iteration_stuffing(gpu_ctx, method):
+    """noise and gen-A 1080p pictures: streams of several hundred KB to MBs per picture, so the
+    persistent stuffing CTAs run several tiles each while other lanes hold SM slots; blocks longer
+    than the 512-bit slots of the entropy kernel; 9 pictures = groups of 8 + 1 (device) or 2 (host)"""
+    import sjpeg_b200 as S
+    w, h, n = 1920, 1080, 9
+    kinds = ["noise", "A", "noise", "B", "A", "noise", "noise", "A", "noise"]
+    frames = [_frame(k, w, h, 900 + i) for i, k in enumerate(kinds)]
+    p = S.default_params(90 if method == 0 else 75, method, S.YUV_420)
+    q = 90 if method == 0 else 75
+    want = [_want((kinds[i], 900 + i), f, w, h, q, method, O.YUV_420) for i, f in enumerate(frames)]
+    got = _encode_batch_device(gpu_ctx, frames, w, h, p, 16 << 20)
+    assert got == want, [i for i in range(n) if got[i] != want[i]]
+    got = _encode_batch_host(gpu_ctx, frames, w, h, p, 16 << 20)
+    assert got == want, [i for i in range(n) if got[i] != want[i]]
+
+
+@pytest.mark.parametrize("method", [0, 7])
+def test_8k_busy_batch(gpu_ctx, method):
+    """three 8K gen-A pictures (groups of 2 at this size): ~1 700 stuffing tiles per picture"""
+    import sjpeg_b200 as S
+    w, h, n = 7680, 4320, 3
+    frames = [O.make_rgb("A", w, h, 31 + f) for f in range(n)]
+    p = S.default_params(75, method, S.YUV_420)
+    got = _encode_batch_device(gpu_ctx, frames, w, h, p, 48 << 20)
+    for i, f in enumerate(frames):
+        assert got[i] == O.oracle_encode(f, w, h, 3 * w, 75.0, method, O.YUV_420), (method, i)
+
+
+def test_batch_error_leaves_no_copies_in_flight(gpu_ctx):
+    """a too-small output capacity is reported (sizes still filled) and the context stays usable"""
+    import sjpeg_b200 as S
+    w, h, n = 640, 360, 5
+    frames = [O.make_rgb("A", w, h, 5 + f) for f in range(n)]
+    p = S.default_params(75, 0, S.YUV_420)
+    outs = [np.empty(64, np.uint8) for _ in frames]
+    with pytest.raises(S.SjpegB200Error):
+        gpu_ctx.encode_batch([f.ctypes.data for f in frames], False, w, h, 3 * w, p,
+                             [o.ctypes.data for o in outs], False, 64)
+    got = _encode_batch_host(gpu_ctx, frames, w, h, p, 1 << 20)
+    for i, f in enumerate(frames):
+        assert got[i] == O.oracle_encode(f, w, h, 3 * w, 75.0, 0, O.YUV_420)
