@@ -469,6 +469,233 @@ SJB_HD uint32_t trellis_block(const int16_t* in, const uint8_t* qm, const int32_
   return mask;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Trellis quantiser, second form: the same dynamic programme laid out for a GPU thread whose
+// working storage is a 1 KB private column of SHARED memory (no local memory, no data-dependent
+// register indexing).  What changes against trellis_block() is bookkeeping only:
+//   * nodes are addressed by (zig-zag position, candidate) instead of a compacted list: at most
+//     two candidates exist per position (quantize.cc:386), so node id = 2 * pos + k; which nodes
+//     were kept is two 64-bit masks in registers.  The reference walks its list from the newest
+//     kept node down to the sink (quantize.cc:357): that is descending position, candidate 1
+//     before candidate 0, the sink (position 0) last -- the order the masks are scanned in.
+//   * a first, branch-free pass over the 63 AC positions leaves the prefix sums of V^2 (disto0)
+//     and the map of positions that quantise to non-zero; the second pass visits only those.
+//   * the two candidates of a position see exactly the same predecessors (the first candidate is
+//     skipped by the second: run < 0, quantize.cc:362), so both walks share one loop and one set
+//     of loads; each keeps its own running best and its own early-out (quantize.cc:367).
+//   * a node stores its score and its predecessor only; level and sign are re-derived from the
+//     coefficient when the best path is read back.
+// Scores are uint32 and wrap as the reference's score_t does.
+// Mem: private storage.  Tab: per-matrix constants by ZIG-ZAG position.
+//   Mem: coef_ld(w) / coef_st(w, v)        32 words: the block, two int16 per word
+//        disto_ld(i) / disto_st(i, v)      64 words
+//        score_ld(pos, &s0, &s1) / score_st(pos, k, v)
+//        prev_ld(node) / prev_st(node, v)  128 bytes
+//        out_zero() / out_st(pos, v) / out_ld(w)   32 words (may alias disto)
+//   Tab: qt(i, &iq, &cpos), q16(i) = matrix entry << 4, len(sym) = AC code length
+// raw: the 64 unquantised x16 coefficients in natural order, two per word (low half first).
+// Result: quantised block in zig-zag order in Mem::out (two per word); returns the chunk bitmap.
+// ---------------------------------------------------------------------------------------------
+SJB_HD int sjb_half(uint32_t w, int hi) { return hi ? ((int32_t)w >> 16) : ((int32_t)(w << 16) >> 16); }
+SJB_HD int find_last_set64(uint64_t m) {   // index of highest set bit, m != 0
+#if defined(__CUDA_ARCH__)
+  return 63 - __clzll((long long)m);
+#else
+  return 63 - __builtin_clzll(m);
+#endif
+}
+
+template <class Mem, class Tab>
+SJB_HD uint32_t trellis_block_v2(const uint32_t (&raw)[32], Mem& M, const Tab& T) {
+#if defined(__CUDA_ARCH__)
+  constexpr int zz[64] = SJB_ZIGZAG_INIT;
+#else
+  const int zz[64] = SJB_ZIGZAG_INIT;
+#endif
+  // ---- pass 1: prefix sums of V^2, map of non-zero positions, block re-stored in zig-zag order ----
+  uint64_t nz = 0;
+  {
+    uint32_t acc = 0;
+    M.disto_st(0, 0u);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 1; i < 64; ++i) {
+      const int x = sjb_half(raw[zz[i] >> 1], zz[i] & 1);
+      const int sg = x >> 31;
+      const int V = (x ^ sg) - sg;
+      acc += (uint32_t)(V * V);
+      M.disto_st(i, acc);
+      int iq, cpos;
+      T.qt(i, iq, cpos);
+      if (V * iq + cpos >= (1 << 20)) nz |= 1ull << i;
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int w = 0; w < 32; ++w) {
+      const uint32_t lo = (uint32_t)sjb_half(raw[zz[2 * w] >> 1], zz[2 * w] & 1) & 0xffffu;
+      const uint32_t hi = (uint32_t)sjb_half(raw[zz[2 * w + 1] >> 1], zz[2 * w + 1] & 1);
+      M.coef_st(w, lo | (hi << 16));
+    }
+  }
+  // ---- pass 2: the dynamic programme over the non-zero positions ----
+  uint64_t kept0 = 1, kept1 = 0;          // bit pos <=> node (pos, k) exists; (0, 0) is the sink
+  M.score_st(0, 0, 0u);
+  const uint32_t zrl_len = T.len(0xf0);
+  for (uint64_t rest = nz; rest; rest &= rest - 1) {
+    const int i = find_first_set64(rest);
+    const int x = sjb_half(M.coef_ld(i >> 1), i & 1);
+    const int sg = x >> 31;
+    const int V = (x ^ sg) - sg;
+    int iq, cpos;
+    T.qt(i, iq, cpos);
+    const int q = T.q16(i);
+    const uint32_t lambda = (uint32_t)(q * q) / 32u;
+    const int vA = (V * iq + cpos) >> 20;                    // >= 1
+    const int nbA = bit_length((uint32_t)vA);
+    const uint32_t dprev = M.disto_ld(i - 1);
+    const int eA = V - vA * q;
+    const uint32_t baseA = (uint32_t)(eA * eA) + dprev;
+    const bool hasB = nbA > 1;                               // second candidate: (1 << (nbits-1)) - 1
+    const int nbB = nbA - 1;
+    const int eB = V - ((1 << nbB) - 1) * q;
+    const uint32_t baseB = (uint32_t)(eB * eB) + dprev;
+    uint32_t bestA = 0xffffffffu, bestB = 0xffffffffu;
+    int bpA = -1, bpB = -1;
+    bool actA = true, actB = hasB;
+    // Predecessors: the kept nodes at positions below i, newest first; the sink (bit 0) is always
+    // among them.  The loop is software-pipelined: the loads of the NEXT predecessor (prefix sum,
+    // both scores, both code lengths) are issued before the current one is evaluated, which takes
+    // the shared-memory latency off the dependent chain of compares (few warps are resident, so
+    // that chain is what bounds the kernel).  A load past the end re-reads the sink: harmless.
+    uint64_t m = (kept0 | kept1) & ((1ull << i) - 1ull);
+    int pp = find_last_set64(m);
+    m ^= 1ull << pp;
+    uint32_t d0 = M.disto_ld(pp), s0, s1;
+    M.score_ld(pp, s0, s1);
+    uint32_t lenA = T.len((((i - 1 - pp) & 15) << 4) | nbA), lenB = T.len((((i - 1 - pp) & 15) << 4) | nbB);
+    bool more = true;
+    while (more && (actA || actB)) {
+      more = m != 0;
+      const int np = more ? find_last_set64(m) : 0;
+      m &= ~(1ull << np);
+      const uint32_t nd0 = M.disto_ld(np);
+      uint32_t ns0, ns1;
+      M.score_ld(np, ns0, ns1);
+      const uint32_t nlenA = T.len((((i - 1 - np) & 15) << 4) | nbA), nlenB = T.len((((i - 1 - np) & 15) << 4) | nbB);
+      const bool h1 = (kept1 >> pp) & 1, h0 = (kept0 >> pp) & 1;
+      const uint32_t zr = (uint32_t)((i - 1 - pp) >> 4) * zrl_len;
+      if (actA) {
+        const uint32_t thr = baseA - d0 + lambda * ((uint32_t)nbA + zr);
+        const uint32_t full = thr + lambda * lenA;
+        if (h1) {
+          if (thr >= bestA) actA = false;
+          else { const uint32_t sc = full + s1; if (sc < bestA) { bestA = sc; bpA = 2 * pp + 1; } }
+        }
+        if (h0 && actA) {
+          if (thr >= bestA) actA = false;
+          else { const uint32_t sc = full + s0; if (sc < bestA) { bestA = sc; bpA = 2 * pp; } }
+        }
+      }
+      if (actB) {
+        const uint32_t thr = baseB - d0 + lambda * ((uint32_t)nbB + zr);
+        const uint32_t full = thr + lambda * lenB;
+        if (h1) {
+          if (thr >= bestB) actB = false;
+          else { const uint32_t sc = full + s1; if (sc < bestB) { bestB = sc; bpB = 2 * pp + 1; } }
+        }
+        if (h0 && actB) {
+          if (thr >= bestB) actB = false;
+          else { const uint32_t sc = full + s0; if (sc < bestB) { bestB = sc; bpB = 2 * pp; } }
+        }
+      }
+      pp = np; d0 = nd0; s0 = ns0; s1 = ns1; lenA = nlenA; lenB = nlenB;
+    }
+    if (bpA >= 0) {                                          // a candidate without predecessor is dropped
+      M.score_st(i, 0, bestA);
+      M.prev_st(2 * i, (uint32_t)bpA);
+      kept0 |= 1ull << i;
+    }
+    if (hasB && bpB >= 0) {
+      M.score_st(i, 1, bestB);
+      M.prev_st(2 * i + 1, (uint32_t)bpB);
+      kept1 |= 1ull << i;
+    }
+  }
+  // ---- best end node (quantize.cc:427-441): newest first, strict <, the sink takes part ----
+  int best = 0;
+  if ((kept0 | kept1) != 1ull) {
+    uint32_t best_score = 0xffffffffu;
+    const uint32_t d63 = M.disto_ld(63);
+    for (uint64_t m = kept0 | kept1; m != 0;) {
+      const int pp = find_last_set64(m);
+      m ^= 1ull << pp;
+      const uint32_t tail = d63 - M.disto_ld(pp);
+      uint32_t s0, s1;
+      M.score_ld(pp, s0, s1);
+      if ((kept1 >> pp) & 1) { const uint32_t sc = s1 + tail; if (sc < best_score) { best_score = sc; best = 2 * pp + 1; } }
+      if ((kept0 >> pp) & 1) { const uint32_t sc = s0 + tail; if (sc < best_score) { best_score = sc; best = 2 * pp; } }
+    }
+  }
+  // ---- read the path back; levels re-derived from the coefficients ----
+  int dcq;
+  {
+    int iq, cpos;
+    T.qt(0, iq, cpos);
+    dcq = quantize_coeff(sjb_half(raw[0], 0), iq, cpos);     // DC: plain quantiser
+  }
+  uint32_t mask = (dcq != 0) ? 1u : 0u;
+  // positions on the path, collected as a map; their candidate bits alongside
+  uint64_t on_path = 0, path_k = 0;
+  for (int node = best; node != 0; node = (int)M.prev_ld(node)) {
+    on_path |= 1ull << (node >> 1);
+    path_k |= (uint64_t)(node & 1) << (node >> 1);
+  }
+  M.out_zero();                                              // may overwrite disto: not needed any more
+  M.out_st(0, dcq);
+  for (uint64_t m = on_path; m; m &= m - 1) {
+    const int pos = find_first_set64(m);
+    const int x = sjb_half(M.coef_ld(pos >> 1), pos & 1);
+    const int sg = x >> 31;
+    const int V = (x ^ sg) - sg;
+    int iq, cpos;
+    T.qt(pos, iq, cpos);
+    int v = (V * iq + cpos) >> 20;
+    if ((path_k >> pos) & 1) v = (1 << (bit_length((uint32_t)v) - 1)) - 1;
+    M.out_st(pos, (v ^ sg) - sg);
+    mask |= 1u << (pos >> 3);
+  }
+  return mask;
+}
+
+// plain-array storage and tables for host code (CPU emulation of the kernel, tests/emul)
+struct TrellisHostMem {
+  uint32_t coef[32], disto[64], score[64][2], out[32];
+  uint8_t prev[128];
+  uint32_t coef_ld(int w) const { return coef[w]; }
+  void coef_st(int w, uint32_t v) { coef[w] = v; }
+  uint32_t disto_ld(int i) const { return disto[i]; }
+  void disto_st(int i, uint32_t v) { disto[i] = v; }
+  void score_ld(int pos, uint32_t& s0, uint32_t& s1) const { s0 = score[pos][0]; s1 = score[pos][1]; }
+  void score_st(int pos, int k, uint32_t v) { score[pos][k] = v; }
+  uint32_t prev_ld(int node) const { return prev[node]; }
+  void prev_st(int node, uint32_t v) { prev[node] = (uint8_t)v; }
+  void out_zero() { for (int i = 0; i < 32; ++i) out[i] = 0; }
+  void out_st(int pos, int v) {
+    const uint32_t h = (uint32_t)v & 0xffffu;
+    out[pos >> 1] = (pos & 1) ? ((out[pos >> 1] & 0xffffu) | (h << 16)) : ((out[pos >> 1] & 0xffff0000u) | h);
+  }
+};
+struct TrellisHostTab {
+  const int32_t (*qtab)[2];   // {iq, cpos} by zig-zag position
+  const uint8_t* qm;          // 8-bit matrix, natural order
+  const uint8_t* ac_len;
+  void qt(int i, int& iq, int& cpos) const { iq = qtab[i][0]; cpos = qtab[i][1]; }
+  int q16(int i) const { const int zz[64] = SJB_ZIGZAG_INIT; return (int)qm[zz[i]] << 4; }
+  uint32_t len(int sym) const { return ac_len[sym]; }
+};
+
 SJB_HD uint32_t sjb_minu(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 // Position inside a tile of `count` consecutive blocks starting at global block `first` of the

@@ -88,13 +88,14 @@ struct SmallLayout {
   int32_t hist[kMaxGroup][2 * 64 * kHistoStride];
   uint32_t freq[kMaxGroup][2 * 272];
   uint8_t quant[kMaxGroup][2][64];
+  uint32_t trellis_sort[kMaxGroup][128];
 };
 
 // one independent pipeline: a stream plus all the scratch one group needs
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  DeviceBuffer pix, coef, nzmask, words, out, state, small, raw;
+  DeviceBuffer pix, coef, nzmask, words, out, state, small, raw, perm;   // perm: block order of the trellis
   HostScratch* host = nullptr;
   GroupBuffers gb = {};
   int group_capacity = 0;        // pictures the buffers are laid out for
@@ -164,7 +165,7 @@ int InitLane(sjb_context* ctx, Lane* L) {
 
 void DestroyLane(Lane* L) {
   if (L->stream) cudaStreamSynchronize(L->stream);
-  for (DeviceBuffer* b : {&L->pix, &L->coef, &L->nzmask, &L->words, &L->out, &L->state, &L->small, &L->raw}) b->Release();
+  for (DeviceBuffer* b : {&L->pix, &L->coef, &L->nzmask, &L->words, &L->out, &L->state, &L->small, &L->raw, &L->perm}) b->Release();
   for (auto& e : L->ev) if (e) cudaEventDestroy(e);
   if (L->host) cudaFreeHost(L->host);
   if (L->stream) cudaStreamDestroy(L->stream);
@@ -219,6 +220,7 @@ int ReserveLane(sjb_context* ctx, Lane* L, const Plan& plan, int frames) {
   CU(L->words.Reserve(f * plan.stream_words * 4 + 64, true, &words_grew));   // zeroed once, then self-cleaning
   CU(L->out.Reserve(f * plan.out_capacity, false, &out_grew));
   CU(L->state.Reserve(f * (plan.nb_tiles + plan.ff_tiles) * sizeof(unsigned long long)));
+  if (plan.trellis) CU(L->perm.Reserve(f * nb * sizeof(uint32_t)));
   GroupBuffers& gb = L->gb;
   const bool relayout = out_grew || gb.out_pitch != plan.out_capacity || gb.words_pitch != plan.stream_words ||
                         L->group_capacity != frames;
@@ -441,7 +443,8 @@ int EncodeGroup(sjb_context* ctx, Lane* L, const FrameSet& fs, const Plan& plan,
       // rate model = default AC tables (enc.cc:334)
       CU(cudaMemcpyAsync(D->quant, H->quant, n * 128, cudaMemcpyHostToDevice, L->stream));
       RC(upload_tabs());
-      LaunchTrellis(fs, gb, nullptr, L->stream);
+      LaunchTrellis(fs, gb, nullptr, &D->trellis_sort[0][0], L->perm.as<uint32_t>(), g.nb_blocks(), L->stream);
+      L->launches += kTrellisLaunches - 1;
     } else {
       LaunchRequantize(fs, gb, nullptr, L->stream);
     }
@@ -590,7 +593,8 @@ int EncodeSearch(sjb_context* ctx, Lane* L, const FrameSet& fs, const Plan& plan
     RC(upload_quant());
     if (plan.trellis) {
       RC(upload_tabs());
-      LaunchTrellis(fs, gb, raw, L->stream);
+      LaunchTrellis(fs, gb, raw, &D->trellis_sort[0][0], L->perm.as<uint32_t>(), nb, L->stream);
+      L->launches += kTrellisLaunches - 1;
     } else {
       LaunchRequantize(fs, gb, raw, L->stream);
     }

@@ -1184,43 +1184,175 @@ stuff_kernel(GroupBuffers gb, const __grid_constant__ StuffArgs args) {
 }
 
 // -------------------------------------------------------------------------------------------
-// T1: trellis quantisation, one block per thread (quantize.cc:325-457); the dynamic programme is
-// block_ops.cuh::trellis_block (shared with the CPU emulation), its node arrays in local memory.
+// T1: trellis quantisation (quantize.cc:325-457), one block per thread; the dynamic programme is
+// block_ops.cuh::trellis_block_v2 (shared with the CPU emulation).  A thread's working storage --
+// the block, the prefix sums of V^2, two nodes per position -- is a private 1 KB column of SHARED
+// memory laid out [word][lane] (bank = lane: conflict-free whatever each lane indexes); nothing is
+// in local memory.  That is 32 KB per warp, so a CTA is 7 warps with 224 KB of dynamic shared
+// memory, one CTA per SM.  Thread t of the grid takes the block of rank t in the order left by the
+// counting sort below (heaviest first).
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
-trellis_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, const int16_t* __restrict__ raw_src) {
-  __shared__ uint8_t ac_len[2][256];
-  __shared__ uint8_t qm[2][64];
-  __shared__ int32_t qtab[2][64][2];
+enum { kTrWarps = 7, kTrThreads = 32 * kTrWarps };
+struct TrellisSmemMem {
+  uint32_t* coef;    // [32][32 lanes], this lane's column
+  uint32_t* disto;   // [64][32]
+  uint2* score;      // [64][32]  {candidate 0, candidate 1}
+  uint32_t* prev;    // [32][32] words = 128 bytes per lane
+  __device__ __forceinline__ uint32_t coef_ld(int w) const { return coef[w * 32]; }
+  __device__ __forceinline__ void coef_st(int w, uint32_t v) { coef[w * 32] = v; }
+  __device__ __forceinline__ uint32_t disto_ld(int i) const { return disto[i * 32]; }
+  __device__ __forceinline__ void disto_st(int i, uint32_t v) { disto[i * 32] = v; }
+  __device__ __forceinline__ void score_ld(int pos, uint32_t& s0, uint32_t& s1) const {
+    const uint2 v = score[pos * 32];
+    s0 = v.x;
+    s1 = v.y;
+  }
+  __device__ __forceinline__ void score_st(int pos, int k, uint32_t v) {
+    reinterpret_cast<uint32_t*>(&score[pos * 32])[k] = v;
+  }
+  __device__ __forceinline__ uint32_t prev_ld(int node) const {
+    return reinterpret_cast<const uint8_t*>(&prev[(node >> 2) * 32])[node & 3];
+  }
+  __device__ __forceinline__ void prev_st(int node, uint32_t v) {
+    reinterpret_cast<uint8_t*>(&prev[(node >> 2) * 32])[node & 3] = static_cast<uint8_t>(v);
+  }
+  // the quantised block goes where the prefix sums were (they are dead by then)
+  __device__ __forceinline__ void out_zero() {
+#pragma unroll
+    for (int w = 0; w < 32; ++w) disto[w * 32] = 0;
+  }
+  __device__ __forceinline__ void out_st(int pos, int v) {
+    reinterpret_cast<uint16_t*>(&disto[(pos >> 1) * 32])[pos & 1] = static_cast<uint16_t>(v);
+  }
+  __device__ __forceinline__ uint32_t out_ld(int w) const { return disto[w * 32]; }
+};
+struct TrellisSmemTab {
+  const int32_t* qtab;     // [64][2] of this block's matrix, zig-zag order
+  const uint16_t* q16s;    // [64] matrix entry << 4, zig-zag order
+  const uint8_t* ac_len;   // [256]
+  __device__ __forceinline__ void qt(int i, int& iq, int& cpos) const {
+    const int2 v = *reinterpret_cast<const int2*>(qtab + 2 * i);
+    iq = v.x;
+    cpos = v.y;
+  }
+  __device__ __forceinline__ int q16(int i) const { return q16s[i]; }
+  __device__ __forceinline__ uint32_t len(int sym) const { return ac_len[sym]; }
+};
+enum { kTrTableBytes = 2 * 64 * 2 * 4 + 2 * 64 * 2 + 2 * 256, kTrSmemBytes = kTrThreads * 1024 + kTrTableBytes };
+
+// Blocks are handed to the trellis threads SORTED by their number of non-zero AC positions,
+// heaviest first: the trip count of a warp is the largest count among its 32 blocks, and a busy
+// picture mixes luma blocks with 40 non-zeros and chroma blocks with 5 (measured on the 8K gen-A
+// picture: with blocks in scan order a CTA ran for as long as its heaviest block, 3.8 x the mean).
+// Counting sort in two small kernels: keys (0..63) into the bitmap array (free until T1 writes it)
+// plus a per-picture histogram; then every CTA ranks its blocks inside the buckets.
+// trellis_sort[frame]: [0,64) bucket counts, [64,128) bucket fill cursors; zero on entry.
+__global__ void __launch_bounds__(256)
+trellis_keys_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, const int16_t* __restrict__ raw_src,
+                    uint32_t* __restrict__ sort_state) {
+  __shared__ __align__(16) int32_t qtab[2][64][2];
+  __shared__ uint32_t hist[64];
   const int frame = blockIdx.y;
   {
-    const CodeTabs* tabs = gb.tabs + frame;
-    const uint8_t* quant = gb.quant + frame * 128;
     const int32_t* q = &gb.qtabs[frame].m[0].e[0][0];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) ac_len[i >> 8][i & 255] = static_cast<uint8_t>(tabs->ac[i >> 8][i & 255] & 0xff);
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) qm[i >> 6][i & 63] = quant[i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) (&qtab[0][0][0])[i] = q[i];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
   }
   __syncthreads();
   const size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (g >= fs.blocks_per_frame) return;
-  const int c = (static_cast<int>(g % fs.mcu_blocks) >= fs.luma_blocks) ? 1 : 0;
+  if (g < fs.blocks_per_frame) {
+    constexpr int zz[64] = SJB_ZIGZAG_INIT;
+    const int c = (block_in_mcu(g, fs.mcu_blocks) >= fs.luma_blocks) ? 1 : 0;
+    int v[64];
+    load_block_natural((raw_src ? raw_src : gb.coef) + frame * gb.coef_pitch + coef_block_base(g), v);
+    int n = 0;
+#pragma unroll
+    for (int i = 1; i < 64; ++i) {
+      const int a = abs(v[zz[i]]);
+      n += (a * qtab[c][i][0] + qtab[c][i][1] >= (1 << 20)) ? 1 : 0;
+    }
+    gb.nzmask[frame * gb.mask_pitch + g] = static_cast<uint8_t>(n);
+    atomicAdd(&hist[n], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 64 && hist[threadIdx.x]) atomicAdd(&sort_state[frame * 128 + threadIdx.x], hist[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256)
+trellis_rank_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, uint32_t* __restrict__ sort_state,
+                    uint32_t* __restrict__ perm, size_t perm_pitch) {
+  __shared__ uint32_t base[64], cnt[64], cta_base[64];
+  const int frame = blockIdx.y;
+  uint32_t* state = sort_state + frame * 128;
+  if (threadIdx.x < 64) {
+    // heaviest bucket first: base[k] = number of blocks with a larger key
+    uint32_t b = 0;
+    for (int k = 63; k > static_cast<int>(threadIdx.x); --k) b += state[k];
+    base[threadIdx.x] = b;
+    cnt[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  const size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  int key = 0;
+  uint32_t local = 0;
+  if (g < fs.blocks_per_frame) {
+    key = gb.nzmask[frame * gb.mask_pitch + g];
+    local = atomicAdd(&cnt[key], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 64 && cnt[threadIdx.x]) cta_base[threadIdx.x] = atomicAdd(&state[64 + threadIdx.x], cnt[threadIdx.x]);
+  __syncthreads();
+  if (g < fs.blocks_per_frame) perm[frame * perm_pitch + base[key] + cta_base[key] + local] = static_cast<uint32_t>(g);
+}
+
+__global__ void __launch_bounds__(kTrThreads, 1)
+trellis_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, const int16_t* __restrict__ raw_src,
+               const uint32_t* __restrict__ perm, size_t perm_pitch) {
+  extern __shared__ __align__(16) uint8_t trellis_smem[];
+  int32_t* qtab = reinterpret_cast<int32_t*>(trellis_smem);                   // [2][64][2]
+  uint16_t* q16s = reinterpret_cast<uint16_t*>(trellis_smem + 1024);         // [2][64]
+  uint8_t* ac_len = trellis_smem + 1024 + 256;                               // [2][256]
+  uint8_t* columns = trellis_smem + kTrTableBytes;                           // 32 KB per warp
+  const int frame = blockIdx.y;
+  {
+    constexpr int zz[64] = SJB_ZIGZAG_INIT;
+    const CodeTabs* tabs = gb.tabs + frame;
+    const uint8_t* quant = gb.quant + frame * 128;
+    const int32_t* q = &gb.qtabs[frame].m[0].e[0][0];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) ac_len[i] = static_cast<uint8_t>(tabs->ac[i >> 8][i & 255] & 0xff);
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) q16s[i] = static_cast<uint16_t>(quant[(i & 64) + zz[i & 63]]) << 4;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) qtab[i] = q[i];
+  }
+  __syncthreads();
+  const uint32_t rank = blockIdx.x * static_cast<uint32_t>(kTrThreads) + threadIdx.x;
+  if (rank >= fs.blocks_per_frame) return;
+  const size_t g = perm[frame * perm_pitch + rank];
+  const int c = (block_in_mcu(g, fs.mcu_blocks) >= fs.luma_blocks) ? 1 : 0;
   int16_t* blk = gb.coef + frame * gb.coef_pitch + coef_block_base(g);
-  __align__(16) int16_t in[64];
-  __align__(16) int16_t outv[64];
+  uint32_t raw[32];
   {
     const uint4* s = reinterpret_cast<const uint4*>(raw_src ? raw_src + frame * gb.coef_pitch + coef_block_base(g) : blk);
-    uint4* d = reinterpret_cast<uint4*>(in);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = s[coef_chunk_index(i)];
+    for (int i = 0; i < 8; ++i) {
+      const uint4 w = s[coef_chunk_index(i)];
+      raw[4 * i] = w.x; raw[4 * i + 1] = w.y; raw[4 * i + 2] = w.z; raw[4 * i + 3] = w.w;
+    }
   }
-  TrellisScratch scratch;     // local memory: 1.5 KB per thread
-  const uint32_t mask = trellis_block(in, qm[c], qtab[c], ac_len[c], outv, scratch);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* col = columns + warp * 32768;
+  TrellisSmemMem mem;
+  mem.coef = reinterpret_cast<uint32_t*>(col) + lane;                        // 4 KB
+  mem.disto = reinterpret_cast<uint32_t*>(col + 4096) + lane;                // 8 KB
+  mem.score = reinterpret_cast<uint2*>(col + 12288) + lane;                  // 16 KB
+  mem.prev = reinterpret_cast<uint32_t*>(col + 28672) + lane;                // 4 KB
+  const TrellisSmemTab tab = {qtab + c * 128, q16s + c * 64, ac_len + c * 256};
+  const uint32_t mask = trellis_block_v2(raw, mem, tab);
   {
-    const uint4* s = reinterpret_cast<const uint4*>(outv);
     uint4* d = reinterpret_cast<uint4*>(blk);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d[coef_chunk_index(i)] = s[i];
+    for (int i = 0; i < 8; ++i) {
+      d[coef_chunk_index(i)] = make_uint4(mem.out_ld(4 * i), mem.out_ld(4 * i + 1), mem.out_ld(4 * i + 2), mem.out_ld(4 * i + 3));
+    }
   }
   gb.nzmask[frame * gb.mask_pitch + g] = static_cast<uint8_t>(mask);
 }
@@ -1344,8 +1476,23 @@ void LaunchHistogram(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s)
   histogram_kernel<<<dim3(grid, fs.frames), 256, smem, s>>>(fs, gb);
 }
 
-void LaunchTrellis(const FrameSet& fs, const GroupBuffers& gb, const int16_t* raw_src, cudaStream_t s) {
-  trellis_kernel<<<dim3(cdiv(fs.blocks_per_frame, 64), fs.frames), 64, 0, s>>>(fs, gb, raw_src);
+void LaunchTrellis(const FrameSet& fs, const GroupBuffers& gb, const int16_t* raw_src, uint32_t* sort_state, uint32_t* perm,
+                   size_t perm_pitch, cudaStream_t s) {
+  static std::atomic<bool> init[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!init[dev].load(std::memory_order_acquire)) {
+    cudaFuncSetAttribute(trellis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTrSmemBytes));
+    init[dev].store(true, std::memory_order_release);
+  }
+  // counting sort of the blocks by their number of non-zero AC positions, then the dynamic programme
+  cudaMemsetAsync(sort_state, 0, static_cast<size_t>(fs.frames) * 128 * sizeof(uint32_t), s);
+  const dim3 grid256(cdiv(fs.blocks_per_frame, 256), fs.frames);
+  trellis_keys_kernel<<<grid256, 256, 0, s>>>(fs, gb, raw_src, sort_state);
+  trellis_rank_kernel<<<grid256, 256, 0, s>>>(fs, gb, sort_state, perm, perm_pitch);
+  trellis_kernel<<<dim3(cdiv(fs.blocks_per_frame, kTrThreads), fs.frames), kTrThreads, kTrSmemBytes, s>>>(fs, gb, raw_src, perm,
+                                                                                                       perm_pitch);
 }
 
 void LaunchSymbolStats(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {

@@ -111,7 +111,11 @@ void LaunchQuantError(const FrameSet& fs, const GroupBuffers& gb, const int16_t*
 void LaunchHistogram(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s);
 // T1: trellis quantisation of raw coefficients in place (quantize.cc:388-457) + bitmap; tables
 // gb.qtabs[frame], matrices gb.quant[frame], rate from the AC code lengths in gb.tabs[frame]
-void LaunchTrellis(const FrameSet& fs, const GroupBuffers& gb, const int16_t* raw_src, cudaStream_t s);
+// sort_state: uint32[frames][128] scratch; perm: uint32[frames][perm_pitch >= blocks] scratch (the order
+// in which the blocks are handed to the threads: sorted by work).  Three launches + one memset.
+enum { kTrellisLaunches = 3 };
+void LaunchTrellis(const FrameSet& fs, const GroupBuffers& gb, const int16_t* raw_src, uint32_t* sort_state, uint32_t* perm,
+                   size_t perm_pitch, cudaStream_t s);
 // S1: symbol statistics into gb.freq[frame] (slot < 256 AC symbol, 256+n DC size), pre-zeroed
 void LaunchSymbolStats(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s);
 

@@ -173,8 +173,18 @@ size_t emul_encode(const uint8_t* pix, int w, int h, long long stride, int mode,
   for (size_t b = 0; b < nb; ++b) {
     const int c = ((int)(b % g.mcu_blocks) >= g.luma_blocks) ? 1 : 0;
     if (trellis) {
+      // the kernel's dynamic programme (trellis_block_v2) on plain-array storage; the list-based
+      // form it was derived from (trellis_block) must agree with it on every block
+      uint32_t words[32];
+      for (int i = 0; i < 32; ++i) words[i] = (uint16_t)raw[b * 64 + 2 * i] | ((uint32_t)(uint16_t)raw[b * 64 + 2 * i + 1] << 16);
+      TrellisHostMem mem;
+      TrellisHostTab tab = {qt.m[c].e, quant[c], default_len[c]};
+      mask[b] = trellis_block_v2(words, mem, tab);
+      for (int i = 0; i < 64; ++i) zz[b * 64 + i] = (int16_t)sjb_half(mem.out[i >> 1], i & 1);
       TrellisScratch scratch;
-      mask[b] = trellis_block(&raw[b * 64], quant[c], qt.m[c].e, default_len[c], &zz[b * 64], scratch);
+      int16_t ref_out[64];
+      const uint32_t ref_mask = trellis_block(&raw[b * 64], quant[c], qt.m[c].e, default_len[c], ref_out, scratch);
+      if (ref_mask != mask[b] || memcmp(ref_out, &zz[b * 64], sizeof(ref_out)) != 0) return 0;
       continue;
     }
     int v[64];

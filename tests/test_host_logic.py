@@ -237,6 +237,9 @@ def test_hot_kernels_keep_their_resource_budget():
     assert len(f1) == 1 and len(ent) == 1, sorted(entries)
     assert f1[0]["regs"] <= 128 and f1[0]["spill"] == 0 and 16 * (f1[0]["smem"] + 1024) <= 228 * 1024, f1
     assert ent[0]["regs"] <= 40 and ent[0]["spill"] == 0 and 5 * (ent[0]["smem"] + 1024) <= 228 * 1024, ent
+    # the trellis keeps its node arrays in shared memory: no stack frame (local memory), no spill
+    tr = [v for k, v in entries.items() if "trellis_kernel" in k]
+    assert len(tr) == 1 and tr[0]["stack"] == 0 and tr[0]["spill"] == 0 and tr[0]["regs"] <= 128, tr
 
 
 def test_host_helpers_without_gpu():
