@@ -6,11 +6,18 @@
  * of sjpeg_b200.h; see INTEGRATION.md for what is and is not covered:
  *
  *   on the accelerated path : SjpegEncode, SjpegCompress, sjpeg::Encode (3 overloads),
- *                             sjpeg::EncodeRGBA / EncodeBGRA, yuv modes 420 / 444 / 400,
- *                             compression methods 0..8, custom matrices / bias / deltas
- *   host utilities          : SjpegVersion, SjpegFreeBuffer, SjpegQuantMatrix, MakeByteSink
- *   not provided (return failure): sharp-YUV, planar/NV inputs, target-size search, metadata
- *                             chunks, the riskiness analyser (YUV_AUTO falls back to 4:2:0)
+ *                             sjpeg::EncodeRGBA / EncodeBGRA, EncodeGray / EncodeYUV420 / EncodeYUV444 /
+ *                             EncodeNV12 / EncodeNV21 (planar and semi-planar input), yuv modes
+ *                             420 / 444 / 400 / SHARP / AUTO, compression methods 0..8, custom matrices /
+ *                             bias / deltas / trellis, the multi-pass target-size / PSNR search
+ *                             (EncoderParam::passes > 1, SearchHook), SjpegRiskiness
+ *   host utilities          : SjpegVersion, SjpegFreeBuffer, SjpegQuantMatrix, SjpegEstimateQuality,
+ *                             SjpegDimensions, SjpegFindQuantizer, MakeByteSink, metadata segments
+ *                             (EXIF / ICC / XMP / extended XMP / app markers)
+ *   one precondition        : SJPEG_YUV_AUTO, SjpegCompress and SjpegRiskiness look pixels up in the
+ *                             reference's generated score table (src/score_7.cc); sjpeg_b200.h says
+ *                             where the library finds it.  Without it those calls FAIL (0 / false /
+ *                             SJPEG_YUV_AUTO) rather than encode in a mode the reference would not pick.
  */
 #ifndef SJPEG_JPEG_H_
 #define SJPEG_JPEG_H_
@@ -143,7 +150,7 @@ bool EncodeRGBA(const uint8_t* rgba, int width, int height, int stride, const En
 bool EncodeRGBA(const uint8_t* rgba, int width, int height, int stride, const EncoderParam& param,
                 std::string* output);
 
-/* reference sjpeg.h:316-349 : other input layouts (not on the accelerated path: return false) */
+/* reference sjpeg.h:316-349 : planar / semi-planar input (encoders.cc:256-507), on the device through sjb_encode_planar */
 bool EncodeGray(const uint8_t* gray, int width, int height, int stride, const EncoderParam& param,
                 sjpeg::ByteSink* sink);
 bool EncodeGray(const uint8_t* gray, int width, int height, int stride, const EncoderParam& param,

@@ -112,9 +112,12 @@ int sjb_sharp_yuv(sjb_context* ctx, const uint8_t* rgb, int rgb_on_device, int w
  * recommends 4:2:0 / sharp 4:2:0 / 4:4:4 / 4:0:0 for a packed RGB picture and reports the 0..100
  * risk score.  The analyser looks pixel triples up in the reference's GENERATED 343 x 343 score
  * table (/root/reference/src/score_7.cc, sjpeg::kSharpnessScore); that table is a data asset of
- * the reference and is not reproduced here -- the host binding passes it once per process
- * (INTEGRATION.md), or SJPEG_B200_SCORE_TABLE names a file holding its 117649 bytes.
- * Without a table sjb_riskiness and SJB_YUV_AUTO return SJB_ERR_ARG.
+ * the reference and is not reproduced in this repository.  The library takes it from, in order:
+ * sjb_set_score_table() (the host binding passes its own array once per process);
+ * the file SJPEG_B200_SCORE_TABLE names (117649 bytes); sjpeg::kSharpnessScore of a reference libsjpeg
+ * loaded in the same process; sjpeg_score_table.bin next to libsjpeg_b200.so, which csrc/Makefile
+ * writes at build time from the reference's score_7.cc where that source tree is present.
+ * Without a table sjb_riskiness and SJB_YUV_AUTO return SJB_ERR_ARG (never another mode silently).
  */
 int sjb_set_score_table(const uint8_t* table, size_t size /* 343*343 */);   /* NULL clears */
 int sjb_has_score_table(void);

@@ -294,6 +294,16 @@ def set_score_table(table):
     return rc
 
 
+def default_score_table():
+    """The table the library finds on its own next to the .so (written at build time where the
+    reference sources are present), or None."""
+    path = os.path.join(os.path.dirname(LIB_PATH), "sjpeg_score_table.bin")
+    if not os.path.exists(path):
+        return None
+    t = np.fromfile(path, np.uint8)
+    return t if t.size == 343 * 343 else None
+
+
 def sjpeg_encode(rgb, width, height, stride, quality, method, yuv_mode, base=None):
     """The drop-in C entry point SjpegEncode() (api.cc:32-49) through the library's own symbol.
     Returns bytes, or None when it returns 0."""

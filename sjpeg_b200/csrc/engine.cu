@@ -8,6 +8,7 @@
 // (stream + scratch for one group); groups of a batch rotate over the lanes so that the copies
 // and kernels of different groups overlap.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1089,20 +1090,51 @@ std::vector<uint8_t> g_score_table;      // process-wide copy of the caller's 34
 int g_score_table_version = 0;           // bumped on every change; 0 = never set
 bool g_score_table_env_checked = false;
 
-// SJPEG_B200_SCORE_TABLE=<file with the 117649 table bytes> is honoured once, if no table was set
+// Where the 343 x 343 riskiness table comes from when the caller has not handed one over
+// (sjb_set_score_table), tried once, in this order:
+//   1. SJPEG_B200_SCORE_TABLE=<file holding the 117649 bytes>
+//   2. sjpeg::kSharpnessScore of a reference libsjpeg loaded in the same process (dlsym: the
+//      drop-in scenario of INTEGRATION.md, where our kernels replace the reference's loops)
+//   3. sjpeg_score_table.bin next to libsjpeg_b200.so -- written at BUILD time by csrc/Makefile from
+//      the reference's score_7.cc where that source tree is present (the table is a generated data
+//      asset of the reference, jpeg_tools.cc:204-206; it is not reproduced in this repository)
+// Without any of them sjb_riskiness / SJB_YUV_AUTO fail (SJB_ERR_ARG): never a silent other mode.
+bool ReadTableFile(const char* path, std::vector<uint8_t>* t) {
+  FILE* f = fopen(path, "rb");
+  if (f == nullptr) return false;
+  t->resize(kRiskTableBytes);
+  const bool ok = fread(t->data(), 1, t->size(), f) == t->size();
+  fclose(f);
+  return ok;
+}
+
 void LoadScoreTableFromEnvLocked() {
   if (g_score_table_env_checked) return;
   g_score_table_env_checked = true;
+  if (!g_score_table.empty()) return;
+  std::vector<uint8_t> t;
   const char* path = getenv("SJPEG_B200_SCORE_TABLE");
-  if (path == nullptr || !g_score_table.empty()) return;
-  FILE* f = fopen(path, "rb");
-  if (f == nullptr) return;
-  std::vector<uint8_t> t(kRiskTableBytes);
-  if (fread(t.data(), 1, t.size(), f) == t.size()) {
+  bool ok = path != nullptr && ReadTableFile(path, &t);
+  if (!ok) {
+    const void* sym = dlsym(RTLD_DEFAULT, "_ZN5sjpeg15kSharpnessScoreE");
+    if (sym != nullptr) {
+      t.assign(static_cast<const uint8_t*>(sym), static_cast<const uint8_t*>(sym) + kRiskTableBytes);
+      ok = true;
+    }
+  }
+  if (!ok) {
+    Dl_info info;
+    if (dladdr(reinterpret_cast<const void*>(&sjb_version), &info) != 0 && info.dli_fname != nullptr) {
+      std::string dir(info.dli_fname);
+      const size_t slash = dir.rfind('/');
+      dir = (slash == std::string::npos) ? std::string(".") : dir.substr(0, slash);
+      ok = ReadTableFile((dir + "/sjpeg_score_table.bin").c_str(), &t);
+    }
+  }
+  if (ok) {
     g_score_table.swap(t);
     ++g_score_table_version;
   }
-  fclose(f);
 }
 
 int EnsureSharpTabs(sjb_context* ctx, const uint32_t** g2l, const uint32_t** l2g) {
@@ -1121,7 +1153,8 @@ int EnsureScoreTable(sjb_context* ctx) {
   std::lock_guard<std::mutex> lock(g_table_mutex);
   LoadScoreTableFromEnvLocked();
   if (g_score_table.empty()) {
-    ctx->err = "no riskiness score table: call sjb_set_score_table() or set SJPEG_B200_SCORE_TABLE";
+    ctx->err = "no riskiness score table: call sjb_set_score_table(), set SJPEG_B200_SCORE_TABLE, load the reference "
+               "libsjpeg alongside, or build with the reference sources present (sjpeg_score_table.bin)";
     return SJB_ERR_ARG;
   }
   if (ctx->risk_table_version != g_score_table_version) {

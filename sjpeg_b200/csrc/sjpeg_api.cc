@@ -3,8 +3,10 @@
 // Argument checks, ownership (new[] buffers), sink protocol and error returns follow
 // /root/reference/src/api.cc:32-67,145-201; the per-MCU work is in kernels.cu.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 
 #include <algorithm>
 #include <new>
@@ -50,14 +52,27 @@ bool EncodeToSink(const uint8_t* pix, int width, int height, int stride, int fmt
                   sjpeg::ByteSink* sink, sjpeg::MemoryManager* memory, const std::string& meta = std::string(),
                   const sjpeg::EncoderParam* full = nullptr);
 // Encoder::InitFromParam, api.cc:145-181
+// true if the riskiness table is available; otherwise says so on stderr (once per process)
+bool HaveScoreTableOrComplain() {
+  if (sjb_has_score_table()) return true;
+  static std::atomic<bool> said(false);
+  if (!said.exchange(true)) {
+    fprintf(stderr, "sjpeg_b200: SJPEG_YUV_AUTO / SjpegCompress / SjpegRiskiness need the reference's riskiness score "
+                    "table and none was found (sjb_set_score_table, SJPEG_B200_SCORE_TABLE, a co-loaded libsjpeg, or "
+                    "sjpeg_score_table.bin next to the library): the call fails instead of picking another mode\n");
+  }
+  return false;
+}
 bool ParamsFromEncoderParam(const sjpeg::EncoderParam& param, const uint8_t quant[2][64],
                             const uint8_t min_quant[2][64], bool use_min_quant, int tolerance, int fmt,
                             sjb_params* out) {
   memset(out, 0, sizeof(*out));
   SjpegYUVMode mode = param.yuv_mode;
   // The riskiness analyser (jpeg_tools.cc:177-236) runs on the device but needs the reference's
-  // generated score table (sjb_set_score_table / SJPEG_B200_SCORE_TABLE); without it AUTO means 4:2:0.
-  if (mode == SJPEG_YUV_AUTO && !sjb_has_score_table()) mode = SJPEG_YUV_420;
+  // generated score table (include/sjpeg_b200.h: sjb_set_score_table and the places it is looked
+  // for).  Without it AUTO cannot be honoured and the call FAILS -- encoding in some other mode
+  // would be a silently different file.
+  if (mode == SJPEG_YUV_AUTO && !HaveScoreTableOrComplain()) return false;
   if (mode != SJPEG_YUV_AUTO && mode != SJPEG_YUV_420 && mode != SJPEG_YUV_SHARP && mode != SJPEG_YUV_444 &&
       mode != SJPEG_YUV_400) {
     return false;
@@ -402,7 +417,7 @@ size_t SjpegEncode(const uint8_t* rgb, int width, int height, int stride, uint8_
   if (rgb == nullptr || out_data == nullptr) return 0;
   if (width <= 0 || height <= 0 || abs(stride) < 3 * width) return 0;
   *out_data = nullptr;
-  if (yuv_mode == SJPEG_YUV_AUTO && !sjb_has_score_table()) yuv_mode = SJPEG_YUV_420;   // see ParamsFromEncoderParam
+  if (yuv_mode == SJPEG_YUV_AUTO && !HaveScoreTableOrComplain()) return 0;   // see ParamsFromEncoderParam
   if (yuv_mode != SJPEG_YUV_AUTO && yuv_mode != SJPEG_YUV_420 && yuv_mode != SJPEG_YUV_SHARP &&
       yuv_mode != SJPEG_YUV_444 && yuv_mode != SJPEG_YUV_400) {
     return 0;
@@ -512,10 +527,11 @@ int SjpegFindQuantizer(const uint8_t* d, size_t size, uint8_t quant[2][64]) {   
 }
 
 SjpegYUVMode SjpegRiskiness(const uint8_t* rgb, int width, int height, int stride, float* risk) {
-  // jpeg_tools.cc:177-236 on the device.  The generated score table comes from the host binding
-  // (sjb_set_score_table) or SJPEG_B200_SCORE_TABLE; without it the answer is 4:2:0 / risk 0.
+  // jpeg_tools.cc:177-236 on the device.  Without the generated score table there is no answer:
+  // SJPEG_YUV_AUTO ("undecided", never a value the reference returns) and a message on stderr.
   if (risk) *risk = 0.f;
-  if (rgb == nullptr || width <= 0 || height <= 0 || !sjb_has_score_table()) return SJPEG_YUV_420;
+  if (rgb == nullptr || width <= 0 || height <= 0) return SJPEG_YUV_420;
+  if (!HaveScoreTableOrComplain()) return SJPEG_YUV_AUTO;
   sjb_context* ctx = tls_context.get();
   int mode = SJPEG_YUV_420;
   float r = 0.f;

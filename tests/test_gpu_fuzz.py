@@ -80,7 +80,7 @@ def test_random_configurations_bit_exact(gpu_ctx):
             assert got == want, dict(case=case, w=w, h=h, mode=mode, method=method, quality=quality, fmt=fmt,
                                      pad=pad, lead=lead, flip=flip)
     finally:
-        S.set_score_table(None)
+        S.set_score_table(S.default_score_table())
 
 
 def test_pageable_upload_through_the_stager(gpu_ctx):

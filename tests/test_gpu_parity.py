@@ -365,8 +365,12 @@ def test_riskiness_and_auto_mode(gpu_ctx):
     assert S.lib().sjb_has_score_table() == 0
     with pytest.raises(S.SjpegB200Error):
         gpu_ctx.riskiness(rgb, 64, 48, 192)                  # loud without the table
-    # the drop-in facade's documented policy without a table: AUTO = 4:2:0
-    assert S.sjpeg_encode(rgb, 64, 48, 192, 75, 0, S.YUV_AUTO) == O.oracle_encode(rgb, 64, 48, 192, 75.0, 0, O.YUV_420)
+    # the drop-in facade without a table: AUTO is refused (0 / false), never silently another mode
+    assert S.sjpeg_encode(rgb, 64, 48, 192, 75, 0, S.YUV_AUTO) is None
+    out = C.POINTER(C.c_uint8)()
+    assert S.lib().SjpegCompress(rgb.ctypes.data, 64, 48, 75.0, C.byref(out)) == 0
+    assert S.lib().SjpegRiskiness(rgb.ctypes.data, 64, 48, 192, None) == S.YUV_AUTO
+    assert S.sjpeg_encode(rgb, 64, 48, 192, 75, 0, S.YUV_420) == O.oracle_encode(rgb, 64, 48, 192, 75.0, 0, O.YUV_420)
     S.set_score_table(table)
     try:
         seen = set()
@@ -388,7 +392,25 @@ def test_riskiness_and_auto_mode(gpu_ctx):
             mode, risk = gpu_ctx.riskiness(img, case["w"], case["h"], 3 * case["w"])
             assert mode == case["mode"] and risk == pytest.approx(case["risk"], abs=0, rel=0), case
     finally:
-        S.set_score_table(None)
+        S.set_score_table(S.default_score_table())
+
+
+def test_auto_mode_out_of_the_box(gpu_ctx):
+    """SjpegCompress() / default EncoderParam (AUTO + method 4) with the table the library finds by
+    itself next to the .so (csrc/Makefile writes it from the reference's score_7.cc at build time)"""
+    import sjpeg_b200 as S
+    if S.default_score_table() is None:
+        pytest.skip("library built without the reference sources: no sjpeg_score_table.bin")
+    S.set_score_table(S.default_score_table())
+    table = S.default_score_table()
+    for name, img in _sharp_images(203, 117):
+        want_mode = O.oracle_riskiness(img, 203, 117, 609, table)[0]
+        out = C.POINTER(C.c_uint8)()
+        n = S.lib().SjpegCompress(img.ctypes.data, 203, 117, 80.0, C.byref(out))
+        assert n > 0, name
+        data = C.string_at(out, n)
+        S.lib().SjpegFreeBuffer(out)
+        assert data == O.oracle_encode(img, 203, 117, 609, 80.0, 4, want_mode), (name, want_mode)
 
 
 def _api_shims():

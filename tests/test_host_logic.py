@@ -289,3 +289,20 @@ def test_host_stager_threading_is_race_free_and_exact():
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "wrong bytes: 0" in res.stdout
     assert "ThreadSanitizer" not in res.stderr, res.stderr[-4000:]
+
+
+def test_score_table_is_found_next_to_the_library():
+    """SJPEG_YUV_AUTO out of the box: csrc/Makefile leaves the reference's generated riskiness table
+    next to the .so where the reference sources are present; a fresh process finds it without any
+    call or environment variable, an explicit clear removes it (then AUTO fails loudly)."""
+    import subprocess
+    import sys
+    side = os.path.join(ROOT, "sjpeg_b200", "sjpeg_score_table.bin")
+    code = ("import sjpeg_b200 as S; L = S.lib(); a = L.sjb_has_score_table(); S.set_score_table(None); "
+            "print(a, L.sjb_has_score_table())")
+    env = {k: v for k, v in os.environ.items() if k != "SJPEG_B200_SCORE_TABLE"}
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == (["1", "0"] if os.path.exists(side) else ["0", "0"]), out.stdout
+    if os.path.exists(side) and O.ref() is not None:
+        assert np.array_equal(np.fromfile(side, np.uint8), O.score_table())
