@@ -194,6 +194,39 @@ int sjb_stripes_finish(sjb_stripes* s, const unsigned long long* bit_offsets, in
 int sjb_picture_header(const sjb_params* params, int width, int height, uint8_t* out, size_t out_capacity,
                        size_t* out_size);
 
+/*
+ * Row stripes with the exchange inside the library (NCCL over NVLink, bound at run time with
+ * dlopen("libnccl.so.2"); nothing of this is needed, or loaded, for single-GPU use).  One process
+ * per GPU.  Bootstrap like any NCCL program: rank 0 calls sjb_comm_unique_id(), the 128 bytes reach
+ * the other ranks by whatever channel the host program has (torch.distributed, MPI, a file), every
+ * rank calls sjb_comm_create() (collective).
+ *
+ * sjb_stripes_encode() is collective: rank r passes, for each of the n pictures, the pixel rows
+ * [y0, y1) that sjb_stripe_rows(height, yuv_mode, world, r, ...) assigns to it -- whole MCU rows,
+ * balanced, the last stripe owning a clipped MCU row; ranks beyond the number of MCU rows get an
+ * empty range and pass any non-NULL pointers -- and rank 0 receives the n complete JPEGs in out[]
+ * (host buffers of out_capacity bytes) and their sizes.  All compression methods 0..8: adapted
+ * matrices and optimised Huffman tables are derived from all-reduced histograms / symbol counts
+ * (SinglePassScanOptimized enc.cc:323-386, CollectHistograms histogram.cc:317-339), identically on
+ * every rank.  Output bytes equal the single-GPU encode of the whole picture.
+ */
+typedef struct sjb_comm sjb_comm;
+int sjb_comm_unique_id(uint8_t id[128]);
+int sjb_comm_create(sjb_context* ctx, const uint8_t id[128], int rank, int world, sjb_comm** comm);
+void sjb_comm_destroy(sjb_comm* comm);
+int sjb_stripe_rows(int height, int yuv_mode, int world, int rank, int* y0, int* y1);
+int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix_on_device, int width, int height,
+                       long long stride, const sjb_params* params, uint8_t* const* out, size_t out_capacity,
+                       size_t* sizes);
+/* Host-only merge used by rank 0 (exported for tests): header + the bytes each stripe emitted, in
+ * order, OR-merging the byte neighbouring stripes share and stuffing it (bit_writer.h:172-196).
+ * flags[r] = head_byte | tail_byte << 8 | tail_bits << 16 | head_open << 24: the stripe's share of
+ * the byte it begins in / ends in, the number of bits it owns of the latter (0 = ends on a byte
+ * boundary), and whether it ends inside its head byte (a stripe shorter than the gap it starts in). */
+int sjb_stripes_assemble(const uint8_t* header, size_t header_len, int stripes, const uint8_t* const* part,
+                         const size_t* size, const unsigned* flags, uint8_t* out, size_t out_capacity,
+                         size_t* out_size);
+
 /* Pinned host memory helpers (for callers that want async copies at PCIe speed). */
 void* sjb_host_alloc(size_t bytes);
 void sjb_host_free(void* p);
@@ -217,6 +250,13 @@ int sjb_stage_symbol_stats(sjb_context* ctx, const uint8_t* pix, int width, int 
 /* Time (ms, CUDA events on the context's stream) of the kernels of the last sjb_encode call:
  * [0] F1 (all launches), [1] entropy stage (memset + E + S), [2] whole device pipeline. */
 int sjb_last_timings(const sjb_context* ctx, float ms[3]);
+
+/* Per-kernel-stage times (ms, CUDA events recorded right before and after each stage's launches) of
+ * the last TIMED group on the context's first lane -- the group of a single sjb_encode, or the last
+ * lane-0 group of sjb_bench_device: [0] F1, [1] H1 histogram, [2] Q1 re-quantise or T1 trellis
+ * (incl. its block sort), [3] S1 symbol statistics, [4] E entropy coder, [5] S byte stuffing;
+ * -1 for a stage the method does not run.  *frames = pictures in that group (one launch each). */
+int sjb_last_stage_timings(sjb_context* ctx, float ms[6], int* frames);
 
 /* Device-resident benchmark loop: encodes the n device pictures round-robin 'iters' times with
  * inputs and outputs staying in HBM; returns total elapsed ms (CUDA events) and, optionally, the

@@ -68,6 +68,7 @@ _SIGNATURES = {
                                       C.POINTER(Params), C.c_void_p]),
     "sjb_stage_symbol_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
                                          C.POINTER(Params), C.c_void_p, C.c_void_p]),
+    "sjb_last_stage_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 6), C.POINTER(C.c_int)]),
     "sjb_last_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 3)]),
     "sjb_bench_device": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                    C.c_longlong, C.POINTER(Params), C.c_int, C.POINTER(C.c_float),
@@ -81,6 +82,14 @@ _SIGNATURES = {
     "sjb_stripes_code": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sjb_stripes_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_size_t,
                                      C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sjb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "sjb_comm_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "sjb_comm_destroy": (None, [C.c_void_p]),
+    "sjb_stripe_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "sjb_stripes_encode": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_longlong,
+                                     C.POINTER(Params), C.POINTER(C.c_void_p), C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sjb_stripes_assemble": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                       C.POINTER(C.c_uint), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "sjb_picture_header": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                      C.POINTER(C.c_size_t)]),
     # drop-in C entry points (include/sjpeg.h)
@@ -253,6 +262,14 @@ class Context:
         ms = (C.c_float * 3)()
         lib().sjb_last_timings(self._ctx, C.byref(ms))
         return list(ms)
+
+    def last_stage_timings(self):
+        """({stage: ms}, pictures in the timed group); stages the method does not run are left out"""
+        ms = (C.c_float * 6)()
+        frames = C.c_int(0)
+        lib().sjb_last_stage_timings(self._ctx, C.byref(ms), C.byref(frames))
+        names = ["F1", "H1", "Q1/T1", "S1", "E", "S"]
+        return {k: v for k, v in zip(names, ms) if v >= 0}, frames.value
 
     def bench_device(self, dev_ptrs, width, height, stride, params, iters):
         n = len(dev_ptrs)

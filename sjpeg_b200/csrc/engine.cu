@@ -23,15 +23,17 @@
 
 #include "../../include/sjpeg_b200.h"
 #include "host_codec.h"
+#include "host_pool.h"
 #include "host_stager.h"
 #include "kernels.cuh"
+#include "nccl_dyn.h"
 #include "sharp.cuh"
 
 using namespace sjb;
 
 namespace {
 
-enum { kMaxLanes = 4, kHeaderReserve = 2048, kWorstBitsPerBlock = 1696 };
+enum { kMaxLanes = 4, kHeaderReserve = 2048, kWorstBitsPerBlock = 1696, kHeadCopyBytes = 1 << 20 };
 // Pictures per launch = this budget / coefficient bytes per picture (at most kMaxGroup).  Measured
 // at 4K: 8 pictures per launch (200 MB) against 4 (100 MB) shorten the tail of the F1 grid (6.8
 // instead of 3.4 waves of CTAs: 13.8 -> 12.6 us per picture) and amortise the entropy stage's
@@ -96,6 +98,10 @@ struct SmallLayout {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t phase_ev = nullptr;   // end of the current phase of the group on this lane (GroupJob)
+  // timed groups: begin/end of each kernel stage -- 0 F1, 1 H1, 2 Q1 or T1, 3 S1, 4 E, 5 S
+  cudaEvent_t kev[6][2] = {};
+  bool kev_set[6] = {false, false, false, false, false, false};
   DeviceBuffer pix, coef, nzmask, words, out, state, small, raw, perm;   // perm: block order of the trellis
   HostScratch* host = nullptr;
   GroupBuffers gb = {};
@@ -108,6 +114,7 @@ struct Lane {
   size_t last_size = 0;          // size of the JPEG left in out slot 0 by the last sjb_encode
   float ms_f1 = 0, ms_entropy = 0, ms_total = 0;
   unsigned long long launches = 0;
+  int timed_frames = 0;          // pictures in the last timed group
   SmallLayout* d_small() const { return small.as<SmallLayout>(); }
 };
 
@@ -128,7 +135,13 @@ struct sjb_context {
   struct BenchSlot { int lane, slot, turn; };
   std::vector<BenchSlot> bench_slots;
   int bench_last_turn[4] = {-1, -1, -1, -1};
+  // Size queries (sjb_encode with out == NULL, what the drop-in facade does) copy the head of the
+  // JPEG into this pinned buffer in the same stream as the sizes, so that a typical file needs one
+  // synchronisation and no second device-to-host copy (sjb_fetch_output reads it from here).
+  uint8_t* head_copy = nullptr;              // pinned, kHeadCopyBytes
+  size_t head_valid = 0;                     // bytes of lane 0's out slot 0 mirrored in head_copy
   HostStager stager;                         // threaded upload of pageable pictures (host_stager.h)
+  HostPool pool;                             // per-picture host analysis of a group, in parallel (host_pool.h)
   bool many_uploads = false;                 // set by the batch / stripe entry points: uploads come back to back
 };
 
@@ -158,6 +171,8 @@ int InitLane(sjb_context* ctx, Lane* L) {
   if (L->stream) return SJB_OK;
   CU(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
   for (auto& e : L->ev) CU(cudaEventCreate(&e));
+  CU(cudaEventCreateWithFlags(&L->phase_ev, cudaEventDisableTiming));
+  for (auto& pair : L->kev) for (auto& e : pair) CU(cudaEventCreate(&e));
   CU(cudaMallocHost(reinterpret_cast<void**>(&L->host), sizeof(HostScratch)));
   memset(L->host, 0, sizeof(HostScratch));
   CU(L->small.Reserve(sizeof(SmallLayout), true));
@@ -168,6 +183,8 @@ void DestroyLane(Lane* L) {
   if (L->stream) cudaStreamSynchronize(L->stream);
   for (DeviceBuffer* b : {&L->pix, &L->coef, &L->nzmask, &L->words, &L->out, &L->state, &L->small, &L->raw, &L->perm}) b->Release();
   for (auto& e : L->ev) if (e) cudaEventDestroy(e);
+  if (L->phase_ev) cudaEventDestroy(L->phase_ev);
+  for (auto& pair : L->kev) for (auto& e : pair) if (e) cudaEventDestroy(e);
   if (L->host) cudaFreeHost(L->host);
   if (L->stream) cudaStreamDestroy(L->stream);
   *L = Lane();
@@ -245,6 +262,7 @@ int ReserveLane(sjb_context* ctx, Lane* L, const Plan& plan, int frames) {
   gb.freq = &s->freq[0][0];
   gb.quant = &s->quant[0][0][0];
   gb.dc_init = nullptr;
+  gb.bit_offsets = nullptr;
   if (relayout) L->header_valid = 0;   // out slots moved: headers must be sent again
   L->group_capacity = frames;
   return SJB_OK;
@@ -370,119 +388,86 @@ bool MakeQuantTabs(const Plan& plan, uint8_t quant[2][64], uint8_t min_quant[2][
   return true;
 }
 
-// Device pipeline for one group whose pixels are already in device memory (fs.pix[]).  On return
-// the JPEGs are (asynchronously) in the lane's out slots, header included, and host->info[] will
-// hold their sizes once the stream has drained.
-int EncodeGroup(sjb_context* ctx, Lane* L, const FrameSet& fs, const Plan& plan, bool timed) {
-  const FrameGeometry& g = plan.g;
+// ---------------------------------------------------------------------------------------------
+// Device pipeline for one group whose pixels are already in device memory (fs.pix[]).
+//
+// Methods >= 1 need the host between kernels -- histogram -> AnalyseHisto -> new matrices
+// (histogram.cc:126-315), symbol counts -> optimal Huffman tables (entropy.cc:254-444) -- so a group
+// is a small state machine (GroupJob): every phase enqueues work on the lane's stream, ends with an
+// event, and the next phase starts by waiting for that event.  A single encode just runs the phases
+// back to back; the batch entry points interleave the phases of several groups (one per lane) so
+// that the calling thread is enqueueing the next group's upload and kernels while an earlier group's
+// counters travel back, instead of idling in cudaStreamSynchronize with the GPU (and the PCIe link)
+// waiting for it.  Per-picture host work of a phase is spread over the context's worker threads.
+//   stage 0 -> [adaptive: F1 raw, H1, histogram D2H | else: F1 quantised]
+//   stage 1 -> (wait) AnalyseHistograms per picture, tables H2D, Q1 or T1
+//   stage 2 -> (wait) OptimalHuffSpec per picture
+//   finish  -> code tables + headers H2D, E, S, sizes D2H          => stage 3 (all enqueued)
+// ---------------------------------------------------------------------------------------------
+// brackets one kernel stage of a timed group with events (sjb_last_stage_timings)
+struct StageTimer {
+  Lane* L;
+  int idx;
+  bool on;
+  StageTimer(Lane* lane, int i, bool timed) : L(lane), idx(i), on(timed) {
+    if (on) cudaEventRecord(L->kev[idx][0], L->stream);
+  }
+  ~StageTimer() {
+    if (on) {
+      cudaEventRecord(L->kev[idx][1], L->stream);
+      L->kev_set[idx] = true;
+    }
+  }
+};
+
+struct GroupJob {
+  Lane* L = nullptr;
+  FrameSet fs;
+  const Plan* plan = nullptr;
+  bool timed = false;
+  int stage = 3;                   // 3 = nothing pending
+  uint8_t quant0[2][64], min_quant[2][64];
+  QuantTabs qt;
+  HuffSpec def_spec[4];            // dc0 dc1 ac0 ac1
+  CodeTabs def_tabs;
+  std::vector<uint8_t> quant;      // [n][2][64]: the matrices that go into each picture's DQT
+  std::vector<HuffSpec> spec;      // [n][4]
+  std::vector<CodeTabs> tabs;      // [n]
+};
+
+// Pinned staging (tables, headers) is only rewritten when its content changes, and then only after
+// the stream has drained: an earlier async copy may still be reading it.  (Right after a phase's
+// event wait the stream is idle and the synchronisation returns at once.)
+int UploadCodeTabs(sjb_context* ctx, GroupJob* J) {
+  Lane* L = J->L;
+  HostScratch* H = L->host;
+  const int n = J->fs.frames;
+  bool same = L->tabs_valid >= n;
+  for (int f = 0; same && f < n; ++f) same = memcmp(&H->tabs[f], &J->tabs[f], sizeof(CodeTabs)) == 0;
+  if (same) return SJB_OK;
+  CU(cudaStreamSynchronize(L->stream));
+  for (int f = 0; f < n; ++f) H->tabs[f] = J->tabs[f];
+  CU(cudaMemcpyAsync(L->d_small()->tabs, H->tabs, n * sizeof(CodeTabs), cudaMemcpyHostToDevice, L->stream));
+  L->tabs_valid = n;
+  return SJB_OK;
+}
+
+int FinishGroup(sjb_context* ctx, GroupJob* J) {
+  Lane* L = J->L;
+  const FrameSet& fs = J->fs;
+  const FrameGeometry& g = J->plan->g;
   const int n = fs.frames;
   HostScratch* H = L->host;
   SmallLayout* D = L->d_small();
   const GroupBuffers& gb = L->gb;
-
-  uint8_t quant0[2][64], min_quant[2][64];
-  QuantTabs qt;
-  if (!MakeQuantTabs(plan, quant0, min_quant, &qt)) {
-    ctx->err = "quantiser entry outside the range of the fused quantise form";
-    return SJB_ERR_ARG;
-  }
-  if (L->words_dirty) {
-    CU(cudaMemsetAsync(L->words.ptr, 0, L->words.bytes, L->stream));
-    L->words_dirty = false;
-  }
-  if (timed) CU(cudaEventRecord(L->ev[0], L->stream));
-
-  // default Huffman tables (entropy.cc:31-86)
-  HuffSpec def_spec[4];   // dc0 dc1 ac0 ac1
-  for (int i = 0; i < 4; ++i) DefaultHuffSpec(i >= 2, i & 1, &def_spec[i]);
-  CodeTabs def_tabs;
-  memset(&def_tabs, 0, sizeof(def_tabs));
-  for (int c = 0; c < 2; ++c) {
-    CodesFromSpec(def_spec[c], def_tabs.dc[c]);
-    CodesFromSpec(def_spec[2 + c], def_tabs.ac[c]);
-  }
-  // Pinned staging (tables, headers) is only rewritten when its content changes, and then only
-  // after the stream has drained: an earlier async copy may still be reading it.
-  std::vector<CodeTabs> tabs(n, def_tabs);
-  auto upload_tabs = [&]() -> int {
-    bool same = L->tabs_valid >= n;
-    for (int f = 0; same && f < n; ++f) same = memcmp(&H->tabs[f], &tabs[f], sizeof(CodeTabs)) == 0;
-    if (same) return SJB_OK;
-    CU(cudaStreamSynchronize(L->stream));
-    for (int f = 0; f < n; ++f) H->tabs[f] = tabs[f];
-    CU(cudaMemcpyAsync(D->tabs, H->tabs, n * sizeof(CodeTabs), cudaMemcpyHostToDevice, L->stream));
-    L->tabs_valid = n;
-    return SJB_OK;
-  };
-
-  std::vector<uint8_t> quant(static_cast<size_t>(n) * 128);
-  for (int f = 0; f < n; ++f) memcpy(&quant[f * 128], quant0, 128);
-
-  if (plan.adaptive) {
-    // enc.cc:425-429 : histogram pass over unquantised coefficients, matrices re-derived on host
-    LaunchF1(L, fs, g, /*raw=*/true, qt);
-    CU(cudaMemsetAsync(D->hist, 0, n * sizeof(D->hist[0]), L->stream));
-    LaunchHistogram(fs, gb, L->stream);
-    L->launches += 1;
-    CU(cudaMemcpyAsync(H->hist, D->hist, n * sizeof(D->hist[0]), cudaMemcpyDeviceToHost, L->stream));
-    if (timed) CU(cudaEventRecord(L->ev[1], L->stream));
-    CU(cudaStreamSynchronize(L->stream));
-    for (int f = 0; f < n; ++f) {
-      uint8_t q[2][64];
-      memcpy(q, quant0, 128);
-      AnalyseHistograms(H->hist[f], g.nb_comps, q, min_quant, plan.p.qdelta_max_luma, plan.p.qdelta_max_chroma);
-      QuantTabs qf = qt;
-      for (int i = (g.nb_comps > 1 ? 1 : 0); i >= 0; --i) {
-        if (!FinalizeQuantizer(q[i], min_quant[i], plan.p.q_bias, &qf.m[i])) return SJB_ERR_ARG;
-      }
-      H->qtabs[f] = qf;
-      memcpy(H->quant[f], q, 128);
-      memcpy(&quant[f * 128], q, 128);
-    }
-    CU(cudaMemcpyAsync(D->qtabs, H->qtabs, n * sizeof(QuantTabs), cudaMemcpyHostToDevice, L->stream));
-    if (plan.trellis) {
-      // rate model = default AC tables (enc.cc:334)
-      CU(cudaMemcpyAsync(D->quant, H->quant, n * 128, cudaMemcpyHostToDevice, L->stream));
-      RC(upload_tabs());
-      LaunchTrellis(fs, gb, nullptr, &D->trellis_sort[0][0], L->perm.as<uint32_t>(), g.nb_blocks(), L->stream);
-      L->launches += kTrellisLaunches - 1;
-    } else {
-      LaunchRequantize(fs, gb, nullptr, L->stream);
-    }
-    L->launches += 1;
-  } else {
-    LaunchF1(L, fs, g, /*raw=*/false, qt);
-    if (timed) CU(cudaEventRecord(L->ev[1], L->stream));
-  }
-
-  std::vector<HuffSpec> spec(static_cast<size_t>(n) * 4);
-  for (int f = 0; f < n; ++f) for (int i = 0; i < 4; ++i) spec[f * 4 + i] = def_spec[i];
-  if (plan.optimize) {
-    // enc.cc:344-374 : symbol statistics -> optimal tables
-    CU(cudaMemsetAsync(D->freq, 0, n * sizeof(D->freq[0]), L->stream));
-    LaunchSymbolStats(fs, gb, L->stream);
-    L->launches += 1;
-    CU(cudaMemcpyAsync(H->freq, D->freq, n * sizeof(D->freq[0]), cudaMemcpyDeviceToHost, L->stream));
-    CU(cudaStreamSynchronize(L->stream));
-    const int nb_tables = (g.nb_comps == 1) ? 1 : 2;
-    for (int f = 0; f < n; ++f) {
-      for (int c = 0; c < nb_tables; ++c) {
-        OptimalHuffSpec(H->freq[f] + 272 * c + 256, 12, &spec[f * 4 + c]);
-        OptimalHuffSpec(H->freq[f] + 272 * c, 256, &spec[f * 4 + 2 + c]);
-        CodesFromSpec(spec[f * 4 + c], tabs[f].dc[c]);
-        CodesFromSpec(spec[f * 4 + 2 + c], tabs[f].ac[c]);
-      }
-    }
-  }
-  RC(upload_tabs());
-
+  RC(UploadCodeTabs(ctx, J));
   // headers (host) -> start of each out slot
   {
     std::vector<std::vector<uint8_t> > headers(n);
     bool same = L->header_valid >= n;
     for (int f = 0; f < n; ++f) {
       headers[f].reserve(1024);
-      AppendHeaders(g, reinterpret_cast<const uint8_t(*)[64]>(&quant[f * 128]), &spec[f * 4], &headers[f]);
+      AppendHeaders(g, reinterpret_cast<const uint8_t(*)[64]>(&J->quant[f * 128]), &J->spec[f * 4], &headers[f]);
       if (headers[f].size() > kHeaderReserve) return SJB_ERR_ARG;
       same = same && L->header_len[f] == headers[f].size() &&
              memcmp(H->header[f], headers[f].data(), headers[f].size()) == 0;
@@ -498,10 +483,9 @@ int EncodeGroup(sjb_context* ctx, Lane* L, const FrameSet& fs, const Plan& plan,
       L->header_valid = n;
     }
   }
-
   L->words_dirty = true;
   CU(cudaMemsetAsync(L->state.ptr, 0, L->state.bytes, L->stream));   // look-back descriptors
-  LaunchEntropyPack(fs, gb, L->stream);
+  { StageTimer t(L, 4, J->timed); LaunchEntropyPack(fs, gb, L->stream); }
   {
     StuffArgs sa;
     memset(&sa, 0, sizeof(sa));
@@ -509,13 +493,145 @@ int EncodeGroup(sjb_context* ctx, Lane* L, const FrameSet& fs, const Plan& plan,
       sa.header_len[f] = L->header_len[f];
       sa.flags[f] = kStuffFirst | kStuffLast;
     }
+    StageTimer t(L, 5, J->timed);
     LaunchStuff(fs, gb, sa, L->stream);
   }
   L->launches += 2;
   CU(cudaGetLastError());
   L->words_dirty = false;   // the stuffing kernel zeroes every word it consumed
-  if (timed) CU(cudaEventRecord(L->ev[2], L->stream));
+  if (J->timed) CU(cudaEventRecord(L->ev[2], L->stream));
   CU(cudaMemcpyAsync(H->info, D->info, n * sizeof(StreamInfo), cudaMemcpyDeviceToHost, L->stream));
+  J->stage = 3;
+  return SJB_OK;
+}
+
+// coefficients are quantised: statistics pass for the optimised tables, or straight to the coder
+int AfterQuantise(sjb_context* ctx, GroupJob* J) {
+  Lane* L = J->L;
+  const int n = J->fs.frames;
+  if (!J->plan->optimize) return FinishGroup(ctx, J);
+  // enc.cc:344-374 : symbol statistics -> optimal tables
+  SmallLayout* D = L->d_small();
+  CU(cudaMemsetAsync(D->freq, 0, n * sizeof(D->freq[0]), L->stream));
+  { StageTimer t(L, 3, J->timed); LaunchSymbolStats(J->fs, L->gb, L->stream); }
+  L->launches += 1;
+  CU(cudaMemcpyAsync(L->host->freq, D->freq, n * sizeof(D->freq[0]), cudaMemcpyDeviceToHost, L->stream));
+  CU(cudaEventRecord(L->phase_ev, L->stream));
+  J->stage = 2;
+  return SJB_OK;
+}
+
+int StartGroup(sjb_context* ctx, GroupJob* J, Lane* L, const FrameSet& fs, const Plan& plan, bool timed) {
+  J->L = L;
+  J->fs = fs;
+  J->plan = &plan;
+  J->timed = timed;
+  J->stage = 3;
+  const FrameGeometry& g = plan.g;
+  const int n = fs.frames;
+  SmallLayout* D = L->d_small();
+  if (!MakeQuantTabs(plan, J->quant0, J->min_quant, &J->qt)) {
+    ctx->err = "quantiser entry outside the range of the fused quantise form";
+    return SJB_ERR_ARG;
+  }
+  if (L->words_dirty) {
+    CU(cudaMemsetAsync(L->words.ptr, 0, L->words.bytes, L->stream));
+    L->words_dirty = false;
+  }
+  if (timed) {
+    CU(cudaEventRecord(L->ev[0], L->stream));
+    for (bool& b : L->kev_set) b = false;
+    L->timed_frames = n;
+  }
+  // default Huffman tables (entropy.cc:31-86)
+  for (int i = 0; i < 4; ++i) DefaultHuffSpec(i >= 2, i & 1, &J->def_spec[i]);
+  memset(&J->def_tabs, 0, sizeof(J->def_tabs));
+  for (int c = 0; c < 2; ++c) {
+    CodesFromSpec(J->def_spec[c], J->def_tabs.dc[c]);
+    CodesFromSpec(J->def_spec[2 + c], J->def_tabs.ac[c]);
+  }
+  J->tabs.assign(n, J->def_tabs);
+  J->quant.resize(static_cast<size_t>(n) * 128);
+  for (int f = 0; f < n; ++f) memcpy(&J->quant[f * 128], J->quant0, 128);
+  J->spec.resize(static_cast<size_t>(n) * 4);
+  for (int f = 0; f < n; ++f) for (int i = 0; i < 4; ++i) J->spec[f * 4 + i] = J->def_spec[i];
+
+  if (plan.adaptive) {
+    // enc.cc:425-429 : histogram pass over unquantised coefficients, matrices re-derived on host
+    { StageTimer t(L, 0, timed); LaunchF1(L, fs, g, /*raw=*/true, J->qt); }
+    CU(cudaMemsetAsync(D->hist, 0, n * sizeof(D->hist[0]), L->stream));
+    { StageTimer t(L, 1, timed); LaunchHistogram(fs, L->gb, L->stream); }
+    L->launches += 1;
+    CU(cudaMemcpyAsync(L->host->hist, D->hist, n * sizeof(D->hist[0]), cudaMemcpyDeviceToHost, L->stream));
+    if (timed) CU(cudaEventRecord(L->ev[1], L->stream));
+    CU(cudaEventRecord(L->phase_ev, L->stream));
+    J->stage = 1;
+    return SJB_OK;
+  }
+  { StageTimer t(L, 0, timed); LaunchF1(L, fs, g, /*raw=*/false, J->qt); }
+  if (timed) CU(cudaEventRecord(L->ev[1], L->stream));
+  return AfterQuantise(ctx, J);
+}
+
+// runs the next host phase of a job (waits for the device first); no-op once everything is enqueued
+int AdvanceGroup(sjb_context* ctx, GroupJob* J) {
+  if (J->stage >= 3) return SJB_OK;
+  Lane* L = J->L;
+  const Plan& plan = *J->plan;
+  const FrameGeometry& g = plan.g;
+  const int n = J->fs.frames;
+  HostScratch* H = L->host;
+  SmallLayout* D = L->d_small();
+  CU(cudaEventSynchronize(L->phase_ev));
+  if (J->stage == 1) {
+    bool ok = true;
+    ctx->pool.ParallelFor(n, [&](int f) {
+      uint8_t q[2][64];
+      memcpy(q, J->quant0, 128);
+      AnalyseHistograms(H->hist[f], g.nb_comps, q, J->min_quant, plan.p.qdelta_max_luma, plan.p.qdelta_max_chroma);
+      QuantTabs qf = J->qt;
+      for (int i = (g.nb_comps > 1 ? 1 : 0); i >= 0; --i) {
+        if (!FinalizeQuantizer(q[i], J->min_quant[i], plan.p.q_bias, &qf.m[i])) ok = false;
+      }
+      H->qtabs[f] = qf;
+      memcpy(H->quant[f], q, 128);
+      memcpy(&J->quant[f * 128], q, 128);
+    });
+    if (!ok) return SJB_ERR_ARG;
+    CU(cudaMemcpyAsync(D->qtabs, H->qtabs, n * sizeof(QuantTabs), cudaMemcpyHostToDevice, L->stream));
+    if (plan.trellis) {
+      // rate model = default AC tables (enc.cc:334)
+      CU(cudaMemcpyAsync(D->quant, H->quant, n * 128, cudaMemcpyHostToDevice, L->stream));
+      RC(UploadCodeTabs(ctx, J));
+      StageTimer t(L, 2, J->timed);
+      LaunchTrellis(J->fs, L->gb, nullptr, &D->trellis_sort[0][0], L->perm.as<uint32_t>(), g.nb_blocks(), L->stream);
+      L->launches += kTrellisLaunches;
+    } else {
+      StageTimer t(L, 2, J->timed);
+      LaunchRequantize(J->fs, L->gb, nullptr, L->stream);
+      L->launches += 1;
+    }
+    return AfterQuantise(ctx, J);
+  }
+  // stage 2: optimal tables from the symbol counts
+  const int nb_tables = (g.nb_comps == 1) ? 1 : 2;
+  ctx->pool.ParallelFor(n, [&](int f) {
+    for (int c = 0; c < nb_tables; ++c) {
+      OptimalHuffSpec(H->freq[f] + 272 * c + 256, 12, &J->spec[f * 4 + c]);
+      OptimalHuffSpec(H->freq[f] + 272 * c, 256, &J->spec[f * 4 + 2 + c]);
+      CodesFromSpec(J->spec[f * 4 + c], J->tabs[f].dc[c]);
+      CodesFromSpec(J->spec[f * 4 + 2 + c], J->tabs[f].ac[c]);
+    }
+  });
+  return FinishGroup(ctx, J);
+}
+
+// one group, start to "everything enqueued": on return the JPEGs are (asynchronously) in the lane's
+// out slots, header included, and host->info[] will hold their sizes once the stream has drained
+int EncodeGroup(sjb_context* ctx, Lane* L, const FrameSet& fs, const Plan& plan, bool timed) {
+  GroupJob job;
+  RC(StartGroup(ctx, &job, L, fs, plan, timed));
+  while (job.stage < 3) RC(AdvanceGroup(ctx, &job));
   return SJB_OK;
 }
 
@@ -829,6 +945,7 @@ void sjb_context_destroy(sjb_context* ctx) {
     b->Release();
   }
   if (ctx->risk_host) cudaFreeHost(ctx->risk_host);
+  if (ctx->head_copy) cudaFreeHost(ctx->head_copy);
   delete ctx;
 }
 
@@ -898,6 +1015,10 @@ int sjb_fetch_output(sjb_context* ctx, uint8_t* out, int out_on_device, size_t o
   const size_t size = L->last_size;
   if (size == 0) return SJB_ERR_ARG;
   if (size > out_capacity) return SJB_ERR_CAPACITY;
+  if (!out_on_device && size <= ctx->head_valid) {      // already on the host (FinishSingle)
+    memcpy(out, ctx->head_copy, size);
+    return SJB_OK;
+  }
   CU(cudaSetDevice(ctx->device));
   CU(cudaMemcpyAsync(out, L->out.ptr, size, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                      L->stream));
@@ -934,10 +1055,17 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
     RC(ReserveLane(ctx, &ctx->lanes[l], plan, B));
     if (!pix_on_device) RC(ReservePix(ctx, &ctx->lanes[l], plan, stride, B));
   }
-  // software pipeline over the lanes: group k runs on lane k % nl; a lane is drained (sizes read,
-  // bytes copied out) right before it is reused.
+  // Software pipeline over the lanes: group k runs on lane k % nl.  At step k the lane is first
+  // freed (the group that used it is finished and drained: sizes read, bytes copied out), group k is
+  // started on it (upload + first kernels enqueued), and then every older group still in flight is
+  // advanced by one host phase, oldest first -- so the waits for histograms / symbol counts of one
+  // group happen while the uploads and kernels of the younger ones are already queued.
+  std::vector<GroupJob> jobs(nl);
+  for (int i = 0; i < n; ++i) sizes[i] = 0;
   auto drain = [&](int k) -> int {
     Lane* L = &ctx->lanes[k % nl];
+    GroupJob* J = &jobs[k % nl];
+    while (J->stage < 3) RC(AdvanceGroup(ctx, J));
     CU(cudaStreamSynchronize(L->stream));
     int rc = SJB_OK;
     for (int f = 0; f < B && k * B + f < n; ++f) {
@@ -954,7 +1082,6 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
     return rc;
   };
   int first_err = SJB_OK;
-  for (int i = 0; i < n; ++i) sizes[i] = 0;
   // A failure in the middle of the pipeline must not leave copies in flight that read the caller's
   // (pinned) inputs or write the caller's outputs after we return: every lane is drained first.
   auto abort_batch = [&](int rc) -> int {
@@ -969,7 +1096,7 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
     Lane* L = &ctx->lanes[k % nl];
     if (k >= nl) {
       const int rc = drain(k - nl);
-      if (rc == SJB_ERR_CUDA || rc == SJB_ERR_NOMEM) return abort_batch(rc);
+      if (rc != SJB_OK && rc != SJB_ERR_CAPACITY) return abort_batch(rc);
       if (rc != SJB_OK && first_err == SJB_OK) first_err = rc;
     }
     FrameSet fs;
@@ -984,12 +1111,13 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
         fs.stride = ds;
       }
     }
-    if (rc == SJB_OK) rc = EncodeGroup(ctx, L, fs, plan, false);
+    if (rc == SJB_OK) rc = StartGroup(ctx, &jobs[k % nl], L, fs, plan, false);
+    for (int j = std::max(0, k - nl + 1); j < k && rc == SJB_OK; ++j) rc = AdvanceGroup(ctx, &jobs[j % nl]);
     if (rc != SJB_OK) return abort_batch(rc);
   }
   for (int k = std::max(0, groups - nl); k < groups; ++k) {
     const int rc = drain(k);
-    if (rc == SJB_ERR_CUDA || rc == SJB_ERR_NOMEM) return abort_batch(rc);
+    if (rc != SJB_OK && rc != SJB_ERR_CAPACITY) return abort_batch(rc);
     if (rc != SJB_OK && first_err == SJB_OK) first_err = rc;
   }
   for (int l = 0; l < nl; ++l) {
@@ -1072,7 +1200,22 @@ int EncodePlanarOnLane(sjb_context* ctx, const uint8_t* y, long long y_stride, c
 // waits for lane 0, reports the size and copies the JPEG out (shared tail of the single-picture calls)
 int FinishSingle(sjb_context* ctx, uint8_t* out, int out_on_device, size_t out_capacity, size_t* out_size) {
   Lane* L = &ctx->lanes[0];
+  ctx->head_valid = 0;
+  size_t head = 0;
+  if (out == nullptr) {
+    if (ctx->head_copy == nullptr && cudaMallocHost(reinterpret_cast<void**>(&ctx->head_copy), kHeadCopyBytes) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->head_copy = nullptr;
+    }
+    if (ctx->head_copy != nullptr) {
+      // about 2 bits per pixel's worth: what a typical file needs, small enough not to weigh on small pictures
+      head = std::min<size_t>(std::min<size_t>(kHeadCopyBytes, std::max<size_t>(64 << 10, L->gb.mask_pitch * 16)),
+                              L->gb.out_pitch);
+      CU(cudaMemcpyAsync(ctx->head_copy, L->out.ptr, head, cudaMemcpyDeviceToHost, L->stream));
+    }
+  }
   CU(cudaStreamSynchronize(L->stream));
+  ctx->head_valid = head;
   FinishTimings(ctx, L);
   const size_t size = static_cast<size_t>(L->host->info[0].out_size);
   *out_size = size;
@@ -1410,6 +1553,22 @@ int sjb_stage_symbol_stats(sjb_context* ctx, const uint8_t* pix, int width, int 
   return SJB_OK;
 } SJB_NOTHROW_END
 
+int sjb_last_stage_timings(sjb_context* ctx, float ms[6], int* frames) {
+  if (ctx == nullptr || ms == nullptr) return SJB_ERR_ARG;
+  Lane* L = &ctx->lanes[0];
+  if (L->stream == nullptr) return SJB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(L->stream);
+  for (int i = 0; i < 6; ++i) {
+    float v = 0.f;
+    if (!L->kev_set[i] || cudaEventElapsedTime(&v, L->kev[i][0], L->kev[i][1]) != cudaSuccess) v = -1.f;
+    ms[i] = v;
+  }
+  cudaGetLastError();
+  if (frames) *frames = L->timed_frames;
+  return SJB_OK;
+}
+
 int sjb_last_timings(const sjb_context* ctx, float ms[3]) {
   if (ctx == nullptr || ms == nullptr) return SJB_ERR_ARG;
   ms[0] = ctx->lanes[0].ms_f1;
@@ -1452,9 +1611,12 @@ int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int
   CU(cudaEventRecord(t0, L0->stream));
   for (int l = 1; l < nl; ++l) CU(cudaStreamWaitEvent(ctx->lanes[l].stream, t0, 0));
   ctx->bench_slots.assign(n, sjb_context::BenchSlot{-1, -1, -1});
+  std::vector<GroupJob> jobs(nl);
   for (int it = 0, turn = 0; it < iters; ++it) {
     for (int k = 0; k < groups; ++k, ++turn) {
       Lane* L = &ctx->lanes[turn % nl];
+      GroupJob* J = &jobs[turn % nl];
+      while (J->stage < 3) RC(AdvanceGroup(ctx, J));       // the group that used this lane nl turns ago
       FrameSet fs;
       FillFrameSet(plan, stride, &fs);
       fs.frames = std::min(B, n - k * B);
@@ -1463,9 +1625,12 @@ int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int
         ctx->bench_slots[k * B + f] = sjb_context::BenchSlot{turn % nl, f, turn};
       }
       ctx->bench_last_turn[turn % nl] = turn;
-      RC(EncodeGroup(ctx, L, fs, plan, /*timed=*/turn % nl == 0));
+      RC(StartGroup(ctx, J, L, fs, plan, /*timed=*/turn % nl == 0));
+      // methods >= 1: one host phase of every older group in flight, oldest first (see sjb_encode_batch)
+      for (int j = std::max(0, turn - nl + 1); j < turn; ++j) RC(AdvanceGroup(ctx, &jobs[j % nl]));
     }
   }
+  for (int l = 0; l < nl; ++l) while (jobs[l].stage < 3) RC(AdvanceGroup(ctx, &jobs[l]));
   for (int l = 1; l < nl; ++l) {
     CU(cudaEventRecord(ctx->lanes[l].ev[3], ctx->lanes[l].stream));
     CU(cudaStreamWaitEvent(L0->stream, ctx->lanes[l].ev[3], 0));
@@ -1780,3 +1945,5 @@ int sjb_picture_header(const sjb_params* params, int width, int height, uint8_t*
 } SJB_NOTHROW_END
 
 }  // extern "C"
+
+#include "engine_stripes.inl"

@@ -36,6 +36,12 @@ __device__ __forceinline__ uint32_t pack16(int lo, int hi) {   // one PRMT
   return __byte_perm(static_cast<uint32_t>(lo), static_cast<uint32_t>(hi), 0x5410);
 }
 
+// block index inside its MCU without a run-time division (mcu_blocks is 6, 3 or 1)
+__device__ __forceinline__ int block_in_mcu(size_t g, int mcu_blocks) {
+  const unsigned gg = static_cast<unsigned>(g);
+  return (mcu_blocks == 6) ? static_cast<int>(gg % 6u) : (mcu_blocks == 3) ? static_cast<int>(gg % 3u) : 0;
+}
+
 // CTA-wide exclusive scan of one uint32 per thread (blockDim.x multiple of 32, <= 1024).
 // Returns the exclusive prefix; *total receives the CTA sum.  scratch: 33 words of smem.
 __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* scratch, uint32_t* total) {
@@ -571,39 +577,53 @@ quant_error_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, const i
 }
 
 // -------------------------------------------------------------------------------------------
-// H1: histogram of |coef| >> 2 (histogram.cc:99-108).  Each CTA keeps a private copy of the
-// 2 x 64 x 128 bins in 64 KB of shared memory and flushes the used ones with atomicAdd.
+// H1: histogram of |coef| >> 2 per matrix and position (histogram.cc:99-108).  Each CTA keeps a
+// private copy of the 2 x 64 x 128 bins in shared memory and flushes the used ones with atomicAdd.
+// A warp takes one block at a time, lane l owns natural positions 2l and 2l+1 (one 32-bit load;
+// the 32 lanes read the block's four 32-byte sectors), so the 32 shared-memory atomics of an
+// instruction go to 32 different rows of the table; rows are 129 words apart (as in the global
+// array), which spreads equal bin values of different rows over the banks.  (With 8 lanes per
+// block and rows 128 words apart the bank depended on the bin value only, and the small values that
+// dominate every histogram serialised the warp: 121 us for an 8K picture.)
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+enum { kH1Threads = 256, kH1Stride = 129, kH1SmemBytes = 2 * 64 * kH1Stride * 4 };
+__global__ void __launch_bounds__(kH1Threads)
 histogram_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
-  extern __shared__ int32_t hist[];   // [2][64][128]
-  for (int i = threadIdx.x; i < 2 * 64 * 128; i += blockDim.x) hist[i] = 0;
+  extern __shared__ int32_t hist[];   // [2][64][129]
+  for (int i = threadIdx.x; i < 2 * 64 * kH1Stride; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   const int frame = blockIdx.y;
   const int16_t* raw = gb.coef + frame * gb.coef_pitch;
-  const size_t nb_blocks = fs.blocks_per_frame;
-  // 8 lanes per block, each lane owns 8 consecutive natural positions (one 16-byte load):
-  // coalesced, and the 8 lanes of a block hit different rows of the table.
-  const size_t lanes_total = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; t < nb_blocks * 8;
-       t += lanes_total) {
-    const size_t g = t >> 3;
-    const int part = static_cast<int>(t & 7);
-    const int m = (static_cast<int>(g % fs.mcu_blocks) >= fs.luma_blocks) ? 1 : 0;
-    const uint4 w = reinterpret_cast<const uint4*>(raw + coef_block_base(g))[coef_chunk_index(part)];
-    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+  const uint32_t nb_blocks = fs.blocks_per_frame;
+  const int lane = threadIdx.x & 31;
+  // int16 offset of this lane's word inside a block: positions 2l, 2l+1 (sector-interleaved layout)
+  const int word_off = coef_pos_offset(2 * lane);
+  int32_t* row = hist + (2 * lane) * kH1Stride;
+  // eight consecutive blocks per warp iteration: eight independent loads in flight per lane (two
+  // groups of four blocks whose sectors share 128-byte lines, so every line fetched is used in full)
+  const uint32_t warps_total = gridDim.x * (kH1Threads / 32);
+  for (uint32_t g0 = (blockIdx.x * (kH1Threads / 32) + (threadIdx.x >> 5)) * 8; g0 < nb_blocks; g0 += warps_total * 8) {
+    uint32_t w[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = (j & 1) ? (static_cast<int>(ww[j >> 1]) >> 16) : static_cast<int16_t>(ww[j >> 1] & 0xffff);
-      const int a = abs(c) >> 2;
-      if (a < 128) atomicAdd(&hist[(m * 64 + part * 8 + j) * 128 + a], 1);
+    for (int e = 0; e < 8; ++e) {
+      w[e] = (g0 + e < nb_blocks) ? *reinterpret_cast<const uint32_t*>(raw + coef_block_base(g0 + e) + word_off) : 0u;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (g0 + e >= nb_blocks) break;
+      const int m = (block_in_mcu(g0 + e, fs.mcu_blocks) >= fs.luma_blocks) ? 1 : 0;
+      const int a0 = abs(static_cast<int>(static_cast<int16_t>(w[e] & 0xffffu))) >> 2;
+      const int a1 = abs(static_cast<int>(w[e]) >> 16) >> 2;
+      int32_t* r = row + m * 64 * kH1Stride;
+      if (a0 < 128) atomicAdd(&r[a0], 1);
+      if (a1 < 128) atomicAdd(&r[kH1Stride + a1], 1);
     }
   }
   __syncthreads();
   int32_t* counts = gb.hist + static_cast<size_t>(frame) * 2 * 64 * 129;
-  for (int i = threadIdx.x; i < 2 * 64 * 128; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 2 * 64 * kH1Stride; i += blockDim.x) {
     const int c = hist[i];
-    if (c) atomicAdd(&counts[(i >> 7) * 129 + (i & 127)], c);
+    if (c) atomicAdd(&counts[i], c);
   }
 }
 
@@ -679,12 +699,6 @@ __device__ __forceinline__ void load_code_tables(const CodeTabs* tabs, CodeTabs*
   __syncthreads();
 }
 
-// block index inside its MCU without a run-time division (mcu_blocks is 6, 3 or 1)
-__device__ __forceinline__ int block_in_mcu(size_t g, int mcu_blocks) {
-  const unsigned gg = static_cast<unsigned>(g);
-  return (mcu_blocks == 6) ? static_cast<int>(gg % 6u) : (mcu_blocks == 3) ? static_cast<int>(gg % 3u) : 0;
-}
-
 // Decoupled look-back (single-pass chained scan).  One 64-bit descriptor per tile:
 // [63:62] state (0 = not ready, 1 = tile aggregate, 2 = inclusive prefix), [61:0] value; the
 // value travels in the same word as the flag, so no fence is needed.  Executed by one full warp;
@@ -707,15 +721,20 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned 
 #define SJB_LOOK_PER_LANE 1
 #endif
 enum { kLookPerLane = SJB_LOOK_PER_LANE, kLookWindow = 32 * kLookPerLane };
+// first half of the look-back, callable early: makes the tile's aggregate visible to its successors
+__device__ __forceinline__ void lookback_publish(unsigned long long* state, long long tile, unsigned long long aggregate) {
+  st_volatile_u64(&state[tile], ((tile == 0 ? 2ull : 1ull) << 62) | aggregate);
+}
+template <bool kPublished = false>
 __device__ __forceinline__ unsigned long long warp_lookback(unsigned long long* state, long long tile,
                                                             unsigned long long aggregate) {
   const int lane = threadIdx.x & 31;
   const unsigned long long kValue = (1ull << 62) - 1;
   if (tile == 0) {
-    if (lane == 0) st_volatile_u64(&state[0], (2ull << 62) | aggregate);
+    if (!kPublished && lane == 0) st_volatile_u64(&state[0], (2ull << 62) | aggregate);
     return 0;
   }
-  if (lane == 0) st_volatile_u64(&state[tile], (1ull << 62) | aggregate);
+  if (!kPublished && lane == 0) st_volatile_u64(&state[tile], (1ull << 62) | aggregate);
   unsigned long long prefix = 0;
   long long base = tile - 1;
   while (true) {
@@ -890,7 +909,7 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
       const long long t = tile_id[b];
       if (t < 0) break;
       const uint32_t total = tile_total[b];
-      const unsigned long long p = warp_lookback(state, t, total);
+      const unsigned long long p = warp_lookback<false>(state, t, total);
       if ((threadIdx.x & 31) == 0) {
         tile_prefix[b] = p;
         if (t == ntiles - 1) {
@@ -898,6 +917,7 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
           gb.info[frame].head_byte = 0;      // stripe hand-over fields, set again by the stuffing kernel
           gb.info[frame].tail_byte = 0;
           gb.info[frame].tail_bits = 0;
+          gb.info[frame].head_open = 0;
         }
       }
       __threadfence_block();
@@ -1095,11 +1115,19 @@ __device__ __forceinline__ uint32_t stream_byte(const uint4& w, int i) {   // by
   return (v >> (8 * (3 - (i & 3)))) & 0xffu;
 }
 
+// what a thread keeps of its 16 stream bytes of a tile between the two halves of the tile's life
+struct StuffPiece {
+  uint4 w;             // the 16 bytes (padding applied)
+  uint32_t ex;         // 0xFF bytes before this thread inside the tile
+  uint32_t total;      // 0xFF bytes of the tile
+  int lo, hi;          // bytes [lo, hi) of w are emitted
+};
+
 __global__ void __launch_bounds__(kStuffThreads)
 stuff_kernel(GroupBuffers gb, const __grid_constant__ StuffArgs args) {
   __shared__ uint32_t scratch[33];
   __shared__ unsigned long long tile_prefix;
-  __shared__ unsigned long long claimed[2];
+  __shared__ unsigned long long claimed;
   const int frame = blockIdx.y;
   uint32_t* stream = gb.words + frame * gb.words_pitch;
   unsigned long long* state = gb.ff_state + frame * gb.ff_state_pitch;
@@ -1107,7 +1135,8 @@ stuff_kernel(GroupBuffers gb, const __grid_constant__ StuffArgs args) {
   // in the entropy kernel: a tile is only ever owned by a running CTA, so the look-back chain makes
   // progress whatever the grid size and whatever else occupies the SMs.
   unsigned long long* counter = state + (gb.ff_state_pitch - 1);
-  const unsigned shift = args.shift[frame], flags = args.flags[frame];
+  const unsigned shift = gb.bit_offsets ? static_cast<unsigned>(gb.bit_offsets[frame] & 7) : args.shift[frame];
+  const unsigned flags = args.flags[frame];
   const bool last = (flags & kStuffLast) != 0;
   const unsigned long long end_bits = gb.info[frame].total_bits + shift;
   // bytes [b0, b1) of R are emitted here; with kStuffLast the final partial byte is padded with
@@ -1117,69 +1146,95 @@ stuff_kernel(GroupBuffers gb, const __grid_constant__ StuffArgs args) {
   const unsigned pad = last ? static_cast<unsigned>((0 - end_bits) & 7) : 0;
   const unsigned long long tiles = (((end_bits + 7) >> 3) + kStuffTileBytes - 1) / kStuffTileBytes;
   uint8_t* out = gb.out + frame * gb.out_pitch + args.header_len[frame];
-  if (threadIdx.x == 0) claimed[0] = atomicAdd(counter, 1ull);
-  __syncthreads();
-  for (int it = 0;; ++it) {
-    const unsigned long long t = claimed[it & 1];
-    if (t >= tiles) break;
-    // the next claim travels while this tile is processed (read after the barriers below)
-    if (threadIdx.x == 0) claimed[(it + 1) & 1] = atomicAdd(counter, 1ull);
+
+  // first half of a tile: load, count, scan, PUBLISH the tile's 0xFF count.  Run for the next
+  // tile BEFORE the current one is written out: the lowest unclaimed tile is the one every later
+  // tile's look-back is about to wait for, so its count must be out within a microsecond of the
+  // claim -- not after the byte-wise scatter of a busy tile (claiming ahead and publishing late
+  // cost 15 % of the 4K gen-A pipeline).
+  auto first_half = [&](unsigned long long t, StuffPiece& p) {
     const unsigned long long byte0 = t * kStuffTileBytes + threadIdx.x * 16ull;
-    uint4 w = load_stream16(stream, byte0, end_bits, shift);
+    p.w = load_stream16(stream, byte0, end_bits, shift);
     if (pad && byte0 < b1 && b1 - byte0 <= 16) {             // the padded byte is in here
       const unsigned i = static_cast<unsigned>(b1 - 1 - byte0);
       const uint32_t m = ((1u << pad) - 1u) << (8 * (3 - (i & 3)));
-      if ((i >> 2) == 0) w.x |= m; else if ((i >> 2) == 1) w.y |= m; else if ((i >> 2) == 2) w.z |= m; else w.w |= m;
+      if ((i >> 2) == 0) p.w.x |= m; else if ((i >> 2) == 1) p.w.y |= m; else if ((i >> 2) == 2) p.w.z |= m; else p.w.w |= m;
     }
-    // bytes of this thread that are emitted: [lo, hi) relative to byte0
-    const int lo = (byte0 < b0) ? static_cast<int>(min(16ull, b0 - byte0)) : 0;
-    const int hi = (byte0 >= b1) ? 0 : static_cast<int>(min(16ull, b1 - byte0));
+    p.lo = (byte0 < b0) ? static_cast<int>(min(16ull, b0 - byte0)) : 0;
+    p.hi = (byte0 >= b1) ? 0 : static_cast<int>(min(16ull, b1 - byte0));
     uint32_t ff = 0;
-    if (lo == 0 && hi == 16) {
-      ff = static_cast<uint32_t>(count_ff(w.x) + count_ff(w.y) + count_ff(w.z) + count_ff(w.w));
+    if (p.lo == 0 && p.hi == 16) {
+      ff = static_cast<uint32_t>(count_ff(p.w.x) + count_ff(p.w.y) + count_ff(p.w.z) + count_ff(p.w.w));
     } else {
-      for (int i = lo; i < hi; ++i) ff += (stream_byte(w, i) == 0xffu) ? 1u : 0u;
+      for (int i = p.lo; i < p.hi; ++i) ff += (stream_byte(p.w, i) == 0xffu) ? 1u : 0u;
     }
-    uint32_t total;
-    const uint32_t ex = cta_exclusive_scan(ff, scratch, &total);
-    if (threadIdx.x < 32) {
-      const unsigned long long p = warp_lookback(state, static_cast<long long>(t), total);
-      if (threadIdx.x == 0) {
-        tile_prefix = p;
-        if (t == tiles - 1) {
-          gb.info[frame].stuffed_bytes = p + total;
-          gb.info[frame].out_size = args.header_len[frame] + (b1 - b0) + p + total + (last ? 2 : 0);
-        }
-      }
-    }
-    __syncthreads();
+    p.ex = cta_exclusive_scan(ff, scratch, &p.total);
+    if (threadIdx.x == 0) lookback_publish(state, static_cast<long long>(t), p.total);
     // shared bytes of a stripe: reported, not emitted
-    if (b0 == 1 && byte0 == 0) gb.info[frame].head_byte = static_cast<unsigned char>(stream_byte(w, 0));
+    if (b0 == 1 && byte0 == 0) {
+      gb.info[frame].head_byte = static_cast<unsigned char>(stream_byte(p.w, 0));
+      gb.info[frame].head_open = (!last && end_bits < 8) ? 1 : 0;
+    }
     if (!last && byte0 <= b1 && b1 < byte0 + 16) {
       gb.info[frame].tail_bits = static_cast<unsigned char>(end_bits & 7);
-      gb.info[frame].tail_byte = static_cast<unsigned char>((end_bits & 7) ? stream_byte(w, static_cast<int>(b1 - byte0)) : 0u);
+      gb.info[frame].tail_byte = static_cast<unsigned char>((end_bits & 7) ? stream_byte(p.w, static_cast<int>(b1 - byte0)) : 0u);
     }
     if (byte0 * 8 < end_bits && !(flags & kStuffKeepWords)) {
       // self-cleaning: the stream buffer must be all zero for the next encode's atomicOr
       // (only without a shift: shifted reads look one word back into the neighbour's words)
       *reinterpret_cast<uint4*>(stream + (byte0 >> 2)) = make_uint4(0, 0, 0, 0);
     }
-    if (hi > lo) {
-      uint8_t* dst = out + (byte0 + lo - b0) + tile_prefix + ex;
+  };
+
+  if (threadIdx.x == 0) claimed = atomicAdd(counter, 1ull);
+  __syncthreads();
+  unsigned long long t = claimed;
+  if (t >= tiles) return;
+  StuffPiece cur;
+  first_half(t, cur);
+  for (;;) {
+    // resolve this tile's prefix (its count has long been published) and claim the next tile
+    __syncthreads();                       // everybody has read `claimed`; tile_prefix is free
+    if (threadIdx.x < 32) {
+      const unsigned long long p = warp_lookback<true>(state, static_cast<long long>(t), cur.total);
+      if (threadIdx.x == 0) {
+        tile_prefix = p;
+        claimed = atomicAdd(counter, 1ull);
+        if (t == tiles - 1) {
+          gb.info[frame].stuffed_bytes = p + cur.total;
+          gb.info[frame].out_size = args.header_len[frame] + (b1 > b0 ? b1 - b0 : 0) + p + cur.total + (last ? 2 : 0);
+        }
+      }
+    }
+    __syncthreads();
+    const unsigned long long prefix = tile_prefix;
+    const unsigned long long t_next = claimed;
+    StuffPiece nxt;
+    if (t_next < tiles) first_half(t_next, nxt);     // uniform branch: the scan's barriers are safe
+    // second half: scatter with the 0x00 inserted
+    if (cur.hi > cur.lo) {
+      const unsigned long long byte0 = t * kStuffTileBytes + threadIdx.x * 16ull;
+      uint8_t* dst = out + (byte0 + cur.lo - b0) + prefix + cur.ex;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        if (i >= lo && i < hi) {
-          const uint32_t b = stream_byte(w, i);
+        if (i >= cur.lo && i < cur.hi) {
+          const uint32_t b = stream_byte(cur.w, i);
           *dst++ = static_cast<uint8_t>(b);
           if (b == 0xffu) *dst++ = 0;
         }
       }
-      if (last && byte0 + hi == b1) {   // EOI (headers.cc:262-268)
+      if (last && byte0 + cur.hi == b1) {   // EOI (headers.cc:262-268)
         dst[0] = 0xff;
         dst[1] = 0xd9;
       }
     }
-    __syncthreads();   // tile_prefix and the claim slots are reused next iteration
+    if (last && b1 <= b0 && t == 0 && threadIdx.x == 0) {   // a last stripe without a byte of its own: EOI only
+      out[0] = 0xff;
+      out[1] = 0xd9;
+    }
+    if (t_next >= tiles) break;
+    t = t_next;
+    cur = nxt;
   }
 }
 
@@ -1372,6 +1427,45 @@ __global__ void last_dc_kernel(const __grid_constant__ FrameSet fs, GroupBuffers
   out[t] = v;
 }
 
+// ---- row stripes: glue between the collectives ------------------------------------------------
+__global__ void stripe_bits_kernel(GroupBuffers gb, int frames, unsigned long long* bits) {
+  const int f = threadIdx.x;
+  if (f < frames) bits[f] = gb.info[f].total_bits;
+}
+__global__ void stripe_offsets_kernel(const unsigned long long* __restrict__ all_bits, int n, int rank,
+                                      unsigned long long* __restrict__ offsets) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long o = 0;
+  for (int r = 0; r < rank; ++r) o += all_bits[static_cast<size_t>(r) * n + i];
+  offsets[i] = o;
+}
+__global__ void stripe_meta_kernel(GroupBuffers gb, int frames, unsigned long long* meta) {
+  const int f = threadIdx.x;
+  if (f >= frames) return;
+  const StreamInfo& in = gb.info[f];
+  meta[2 * f] = in.out_size;
+  meta[2 * f + 1] = static_cast<unsigned long long>(in.head_byte) | (static_cast<unsigned long long>(in.tail_byte) << 8) |
+                    (static_cast<unsigned long long>(in.tail_bits) << 16) | (static_cast<unsigned long long>(in.head_open) << 24);
+}
+// gridDim.y = stripe of the group; CTAs stride over its bytes
+__global__ void __launch_bounds__(256)
+stripe_compact_kernel(const uint8_t* __restrict__ group_out, size_t out_pitch, int first,
+                      const unsigned long long* __restrict__ meta, uint8_t* __restrict__ dst) {
+  const int f = blockIdx.y;
+  __shared__ unsigned long long base;
+  if (threadIdx.x == 0) {
+    unsigned long long b = 0;
+    for (int i = 0; i < first + f; ++i) b += meta[2 * i];
+    base = b;
+  }
+  __syncthreads();
+  const unsigned long long size = meta[2 * (first + f)];
+  const uint8_t* src = group_out + f * out_pitch;
+  uint8_t* d = dst + base;
+  for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < size; i += gridDim.x * 256ull) d[i] = src[i];
+}
+
 unsigned cdiv(size_t a, size_t b) { return static_cast<unsigned>((a + b - 1) / b); }
 
 // SMs of the current device (grids of the persistent kernels are sized from it), cached per device;
@@ -1461,19 +1555,19 @@ void LaunchQuantError(const FrameSet& fs, const GroupBuffers& gb, const int16_t*
 void LaunchHistogram(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {
   // the attribute is per device; concurrent host threads may get here together (any of them may set it)
   static std::atomic<bool> init[64];
-  const size_t smem = 2 * 64 * 128 * sizeof(int32_t);
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
   if (!init[dev].load(std::memory_order_acquire)) {
-    cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kH1SmemBytes));
     init[dev].store(true, std::memory_order_release);
   }
-  unsigned grid = cdiv(static_cast<size_t>(fs.blocks_per_frame) * 8, 256 * 16);
+  // 3 CTAs (66 KB of counters each) per SM over all pictures of the group, at least 64 blocks per warp
+  unsigned grid = cdiv(fs.blocks_per_frame, (kH1Threads / 32) * 64);
   const unsigned cap = SmCount() * 3 / (fs.frames > 0 ? fs.frames : 1) + 1;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  histogram_kernel<<<dim3(grid, fs.frames), 256, smem, s>>>(fs, gb);
+  histogram_kernel<<<dim3(grid, fs.frames), kH1Threads, kH1SmemBytes, s>>>(fs, gb);
 }
 
 void LaunchTrellis(const FrameSet& fs, const GroupBuffers& gb, const int16_t* raw_src, uint32_t* sort_state, uint32_t* perm,
@@ -1513,6 +1607,20 @@ void LaunchEntropyPack(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t 
 
 void LaunchLastDc(const FrameSet& fs, const GroupBuffers& gb, int* out, cudaStream_t s) {
   last_dc_kernel<<<1, (3 * kMaxGroup + 31) / 32 * 32, 0, s>>>(fs, gb, out);
+}
+
+void LaunchStripeBits(const GroupBuffers& gb, int frames, unsigned long long* bits, cudaStream_t s) {
+  stripe_bits_kernel<<<1, 32, 0, s>>>(gb, frames, bits);
+}
+void LaunchStripeOffsets(const unsigned long long* all_bits, int n, int rank, unsigned long long* offsets, cudaStream_t s) {
+  stripe_offsets_kernel<<<cdiv(n, 128), 128, 0, s>>>(all_bits, n, rank, offsets);
+}
+void LaunchStripeMeta(const GroupBuffers& gb, int frames, unsigned long long* meta, cudaStream_t s) {
+  stripe_meta_kernel<<<1, 32, 0, s>>>(gb, frames, meta);
+}
+void LaunchStripeCompact(const uint8_t* group_out, size_t out_pitch, int first, int frames, const unsigned long long* meta_all_local,
+                         uint8_t* dst, cudaStream_t s) {
+  stripe_compact_kernel<<<dim3(16, frames), 256, 0, s>>>(group_out, out_pitch, first, meta_all_local, dst);
 }
 
 void LaunchStuff(const FrameSet& fs, const GroupBuffers& gb, const StuffArgs& args, cudaStream_t s) {

@@ -54,7 +54,8 @@ struct StreamInfo {
   unsigned char head_byte;          // stripe mode: first, shared byte (low 8-shift bits are ours)
   unsigned char tail_byte;          // stripe mode: last, shared byte (top tail_bits bits are ours)
   unsigned char tail_bits;          // 0 = no shared tail byte
-  unsigned char pad[5];
+  unsigned char head_open;          // stripe mode: the stripe ENDS inside its head byte (owns no byte boundary)
+  unsigned char pad[4];
 };
 
 // Per-lane device arrays, picture-major with fixed pitches (in elements of the pointed type).
@@ -72,6 +73,8 @@ struct GroupBuffers {
   uint32_t* freq;           // [frames][2][272]
   uint8_t* quant;           // [frames][2][64]
   const int* dc_init;       // [frames][3] DC predictors at the first MCU (Y,U,V); null = zeros
+  const unsigned long long* bit_offsets;   // stripes: [frames] global bit offset of each stripe (device); the
+                                           // stuffing kernel then takes shift = offset % 8 from here
 };
 
 // Per-picture arguments of the stuffing kernel.  A whole picture uses shift 0 and
@@ -127,5 +130,19 @@ void LaunchEntropyPack(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t 
 void LaunchStuff(const FrameSet& fs, const GroupBuffers& gb, const StuffArgs& args, cudaStream_t s);
 // quantised DC of the last Y / U / V block of every picture -> out[frames][3] (stripe hand-over)
 void LaunchLastDc(const FrameSet& fs, const GroupBuffers& gb, int* out, cudaStream_t s);
+
+// ---- row stripes across GPUs: the small device-side steps between the collectives (engine) ----
+// bits[f] = info[f].total_bits
+void LaunchStripeBits(const GroupBuffers& gb, int frames, unsigned long long* bits, cudaStream_t s);
+// offsets[i] = sum of all_bits[r][i] over the ranks r < rank (all_bits = [world][n], ranks without
+// rows contribute 0)
+void LaunchStripeOffsets(const unsigned long long* all_bits, int n, int rank, unsigned long long* offsets, cudaStream_t s);
+// meta[f] = {out_size, head_byte | tail_byte << 8 | tail_bits << 16}
+void LaunchStripeMeta(const GroupBuffers& gb, int frames, unsigned long long* meta, cudaStream_t s);
+// packs the emitted bytes of the n stripes (slot f of its group at src[f], sizes in meta[f*2]) back to
+// back into dst; one launch per group: dst_offset_base = where the group's first stripe goes is
+// computed on the device from the sizes of all stripes before it (meta of the whole batch)
+void LaunchStripeCompact(const uint8_t* group_out, size_t out_pitch, int first, int frames, const unsigned long long* meta_all_local,
+                         uint8_t* dst, cudaStream_t s);
 
 }  // namespace sjb

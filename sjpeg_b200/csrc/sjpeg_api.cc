@@ -321,12 +321,22 @@ bool EncodeToSink(const uint8_t* pix, int width, int height, int stride, int fmt
   sjb_context_set_search(ctx, nullptr);
   if (rc != SJB_ERR_CAPACITY || size == 0) return false;
   if (full != nullptr) FinishSearch(*full, &st, search, true);
-  // host staging goes through the caller's memory manager (sjpeg.h:410-415)
-  uint8_t* staging = static_cast<uint8_t*>(memory->Alloc(size));
-  if (staging == nullptr) return false;
-  bool ok = sjb_fetch_output(ctx, staging, 0, size) == SJB_OK;
-  ok = ok && CommitWithMetadata(staging, size, meta, sink);
-  memory->Free(staging);
+  bool ok;
+  if (meta.empty() && memory == &default_memory) {
+    // no segment to splice in and no caller-supplied allocator to honour: the JPEG goes straight
+    // from the device (or the context's pinned head copy) into the sink's own memory
+    uint8_t* dst = nullptr;
+    ok = sink->Commit(0, size, &dst) && dst != nullptr;
+    ok = ok && sjb_fetch_output(ctx, dst, 0, size) == SJB_OK;
+    ok = ok && sink->Commit(size, 0, &dst) && sink->Finalize();
+  } else {
+    // host staging goes through the caller's memory manager (sjpeg.h:410-415)
+    uint8_t* staging = static_cast<uint8_t*>(memory->Alloc(size));
+    if (staging == nullptr) return false;
+    ok = sjb_fetch_output(ctx, staging, 0, size) == SJB_OK;
+    ok = ok && CommitWithMetadata(staging, size, meta, sink);
+    memory->Free(staging);
+  }
   if (!ok) sink->Reset();                               // bit_writer.cc:99-105
   (void)fmt;
   return ok;

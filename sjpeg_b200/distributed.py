@@ -248,3 +248,73 @@ def assemble_striped(header, holders, all_meta, blobs):
             carry, carry_bits = t, tb
         out.append(bytes(buf))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# native path: the exchange runs inside the library over NCCL (csrc/engine_stripes.inl)
+# ------------------------------------------------------------------------------------------------
+def stripe_rows(height, yuv_mode, world_size, rank):
+    """(y0, y1) of a rank, from the library itself (same split as stripe_plan)."""
+    y0, y1 = C.c_int(0), C.c_int(0)
+    rc = lib().sjb_stripe_rows(height, yuv_mode, world_size, rank, C.byref(y0), C.byref(y1))
+    if rc != OK:
+        raise SjpegB200Error("sjb_stripe_rows rc=%d" % rc)
+    return y0.value, y1.value
+
+
+class NcclStripeEncoder:
+    """One per rank.  torch.distributed is used ONCE, to hand rank 0's NCCL unique id to the other
+    ranks; every encode after that is a single collective call into the library, which owns its
+    communicator, stream and buffers."""
+
+    def __init__(self, ctx, group=None, single=False):
+        self.ctx = ctx
+        self._comm = C.c_void_p()
+        if single:          # a communicator of one rank: no torch.distributed needed
+            self.rank, self.world = 0, 1
+            uid = np.zeros(128, np.uint8)
+            if lib().sjb_comm_unique_id(uid.ctypes.data) != OK:
+                raise SjpegB200Error("sjb_comm_unique_id failed (libnccl.so.2 not loadable?)")
+            rc = lib().sjb_comm_create(ctx._ctx, uid.ctypes.data, 0, 1, C.byref(self._comm))
+            if rc != OK:
+                raise SjpegB200Error("sjb_comm_create rc=%d %s" % (rc, lib().sjb_last_error(ctx._ctx)))
+            return
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        uid = np.zeros(128, np.uint8)
+        if self.rank == 0:
+            rc = lib().sjb_comm_unique_id(uid.ctypes.data)
+            if rc != OK:
+                raise SjpegB200Error("sjb_comm_unique_id rc=%d (libnccl.so.2 not loadable?)" % rc)
+        holder = [uid.tobytes()]
+        dist.broadcast_object_list(holder, src=0, group=group)
+        uid = np.frombuffer(holder[0], np.uint8).copy()
+        rc = lib().sjb_comm_create(ctx._ctx, uid.ctypes.data, self.rank, self.world, C.byref(self._comm))
+        if rc != OK:
+            raise SjpegB200Error("sjb_comm_create rc=%d %s" % (rc, lib().sjb_last_error(ctx._ctx)))
+
+    def rows(self, height, yuv_mode):
+        return stripe_rows(height, yuv_mode, self.world, self.rank)
+
+    def encode(self, stripe_ptrs, on_device, width, height, stride, params, capacity):
+        """stripe_ptrs: address of row y0 of this rank's stripe of each picture.  Returns the list
+        of JPEG byte strings on rank 0, None elsewhere."""
+        n = len(stripe_ptrs)
+        a = (C.c_void_p * n)(*stripe_ptrs)
+        if self.rank == 0:
+            outs = [np.empty(capacity, np.uint8) for _ in range(n)]
+            o = (C.c_void_p * n)(*[x.ctypes.data for x in outs])
+            sizes = (C.c_size_t * n)()
+        else:
+            outs, o, sizes = None, None, None
+        rc = lib().sjb_stripes_encode(self._comm, n, a, int(on_device), width, height, stride, C.byref(params), o,
+                                      capacity, sizes)
+        if rc != OK:
+            raise SjpegB200Error("sjb_stripes_encode rc=%d %s" % (rc, lib().sjb_last_error(self.ctx._ctx)))
+        if self.rank != 0:
+            return None
+        return [outs[i][:sizes[i]].tobytes() for i in range(n)]
+
+    def close(self):
+        if self._comm:
+            lib().sjb_comm_destroy(self._comm)
+            self._comm = C.c_void_p()

@@ -144,3 +144,85 @@ def test_plans():
     assert plan[0] == (0, 144) and plan[-1] == (960, 1080)
     assert all(a % 16 == 0 for a, _ in plan) and [b for _, b in plan[:-1]] == [a for a, _ in plan[1:]]
     assert D.stripe_plan(40, O.YUV_420, 8)[3:] == [(40, 40)] * 5
+
+
+# ---- the library's own host-side pieces of the native (NCCL) stripe path ----------------------
+def test_stripe_rows_match_the_python_plan():
+    """sjb_stripe_rows (C++, used by sjb_stripes_encode on every rank) == distributed.stripe_plan"""
+    from sjpeg_b200 import distributed as D
+    for height in (1, 7, 8, 16, 17, 135, 1080, 2160, 4320, 65535):
+        for mode in (O.YUV_420, O.YUV_444, O.YUV_400):
+            for world in (1, 2, 3, 4, 8):
+                plan = D.stripe_plan(height, mode, world)
+                for r in range(world):
+                    assert D.stripe_rows(height, mode, world, r) == plan[r], (height, mode, world, r)
+
+
+def _split_like_the_stuffing_kernel(scan_bits, cuts):
+    """What each rank's stuffing kernel reports for its stripe (kernels.cu stuff_kernel, stripe mode):
+    scan_bits = the unstuffed, padded scan as a 0/1 array (multiple of 8 long); cuts = bit positions
+    where one stripe ends and the next begins.  Returns [(bytes, flags)] in stripe order."""
+    R = np.packbits(scan_bits)
+    bounds = [0] + list(cuts) + [len(scan_bits)]
+    out = []
+    for r in range(len(bounds) - 1):
+        a, b = bounds[r], bounds[r + 1]
+        first, last = r == 0, r == len(bounds) - 2
+        shift, A = a % 8, a // 8
+        end_bits = shift + (b - a)
+        b0 = 1 if (shift != 0 and not first) else 0
+        b1 = (end_bits + 7) // 8 if last else end_bits // 8
+        own = np.zeros(len(scan_bits), np.uint8)
+        own[a:b] = scan_bits[a:b]
+        mine = np.packbits(own)                       # the stripe's bits alone, zeros elsewhere
+        body = bytearray()
+        for x in mine[A + b0:A + max(b1, b0)]:
+            body.append(int(x))
+            if x == 0xFF:
+                body.append(0)
+        if last:
+            body += b"\xff\xd9"
+        head = int(mine[A]) if b0 == 1 else 0
+        tail_bits = 0 if last else end_bits % 8
+        tail = int(mine[A + b1]) if tail_bits else 0
+        head_open = 1 if (b0 == 1 and not last and end_bits < 8) else 0
+        out.append((bytes(body), head | (tail << 8) | (tail_bits << 16) | (head_open << 24)))
+    return out
+
+
+def test_library_assembles_stripes_incl_several_in_one_byte():
+    """sjb_stripes_assemble (rank 0 of the native path): an oracle file cut at arbitrary bit positions
+    -- including stripes of one or two bits, three and more meeting inside one byte, cuts on byte
+    boundaries and next to 0xFF bytes -- must come back byte for byte."""
+    import sjpeg_b200 as S
+    L = S.lib()
+    rng = np.random.RandomState(12)
+    for (w, h, gen, q) in ((64, 48, "A", 75.0), (33, 21, "B", 50.0), (8, 8, "A", 100.0), (120, 16, "N", 95.0)):
+        rgb = rng.randint(0, 256, (h, w, 3)).astype(np.uint8) if gen == "N" else O.make_rgb(gen, w, h)
+        whole = O.oracle_encode(rgb, w, h, 3 * w, q, 0, O.YUV_420)
+        sos = whole.index(b"\xff\xda")
+        header, scan = whole[:sos + 14], whole[sos + 14:-2]
+        raw = scan.replace(b"\xff\x00", b"\xff")
+        bits = np.unpackbits(np.frombuffer(raw, np.uint8))
+        nbits = len(bits)
+        for trial in range(60):
+            k = int(rng.randint(1, 9))
+            if trial % 3 == 0:       # clusters of tiny stripes
+                base = int(rng.randint(1, nbits - 40))
+                cuts = sorted(set(int(base + d) for d in np.cumsum(rng.randint(1, 4, k))))
+            elif trial % 3 == 1:     # byte-aligned and near-aligned cuts
+                cuts = sorted(set(int(8 * rng.randint(1, nbits // 8) + rng.randint(-1, 2)) for _ in range(k)))
+            else:
+                cuts = sorted(set(int(c) for c in rng.randint(1, nbits, k)))
+            cuts = [c for c in cuts if 0 < c < nbits]
+            parts = _split_like_the_stuffing_kernel(bits, cuts)
+            n = len(parts)
+            bufs = [np.frombuffer(p, np.uint8).copy() if p else np.zeros(1, np.uint8) for p, _ in parts]
+            ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+            sizes = (C.c_size_t * n)(*[len(p) for p, _ in parts])
+            flags = (C.c_uint * n)(*[f for _, f in parts])
+            out = np.zeros(len(whole) + 64, np.uint8)
+            size = C.c_size_t(0)
+            rc = L.sjb_stripes_assemble(header, len(header), n, ptrs, sizes, flags, out.ctypes.data, out.nbytes, C.byref(size))
+            assert rc == 0
+            assert out[:size.value].tobytes() == whole, (w, h, gen, trial, cuts)

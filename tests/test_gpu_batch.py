@@ -153,3 +153,29 @@ def test_batch_error_leaves_no_copies_in_flight(gpu_ctx):
     got = _encode_batch_host(gpu_ctx, frames, w, h, p, 1 << 20)
     for i, f in enumerate(frames):
         assert got[i] == O.oracle_encode(f, w, h, 3 * w, 75.0, 0, O.YUV_420)
+
+
+@pytest.mark.parametrize("method", [0, 1, 3, 4, 7])
+def test_native_stripe_session_single_rank(gpu_ctx, method):
+    """sjb_stripes_encode with a one-rank NCCL communicator: the whole stream-ordered sequence
+    (all-reduce of histograms / symbol counts, all-gathers, offsets, stuffing, compaction, assembly)
+    runs with degenerate collectives; 11 pictures = groups of 8 + 3.  Multi-rank runs: bench.py
+    --gpus N (config 5) and tools/stripes_nccl.py."""
+    import sjpeg_b200 as S
+    from sjpeg_b200 import distributed as D
+    enc = D.NcclStripeEncoder(gpu_ctx, single=True)
+    try:
+        for (w, h, mode, q) in ((640, 360, S.YUV_420, 75), (203, 117, S.YUV_444, 90), (64, 200, S.YUV_400, 50)):
+            kinds = ["A", "B", "noise", "flat"]
+            frames = [_frame(kinds[i % 4], w, h, 50 + i) for i in range(11)]
+            p = S.default_params(q, method, mode)
+            assert enc.rows(h, mode) == (0, h)
+            got = enc.encode([f.ctypes.data for f in frames], False, w, h, 3 * w, p, 1 << 20)
+            for i, f in enumerate(frames):
+                assert got[i] == O.oracle_encode(f, w, h, 3 * w, float(q), method, mode), (w, h, mode, method, i)
+        # the context still encodes whole pictures afterwards
+        rgb = O.make_rgb("A", 320, 200)
+        assert gpu_ctx.encode(rgb, 320, 200, 960, S.default_params(75, 4, S.YUV_420)) == \
+            O.oracle_encode(rgb, 320, 200, 960, 75.0, 4, O.YUV_420)
+    finally:
+        enc.close()
