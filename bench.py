@@ -140,24 +140,28 @@ def bind_to_gpu_numa_node(index):
         return "unavailable (%s)" % type(e).__name__
 
 
-def cpu_reference_throughput(frames, seconds_budget=12.0):
+def cpu_reference_throughput(frames, seconds_budget=12.0, w=None, h=None, quality=None, method=None, mode=None):
     """Frame-parallel encode on all host cores with the reference's own code (oracle/_ref) or,
     if that library did not travel, the oracle port.  Returns (Mpix/s, kind, cores, sample)."""
     import oracle_lib as O
+    w, h = w or W, h or H
+    quality = QUALITY if quality is None else quality
+    method = METHOD if method is None else method
+    mode = O.YUV_420 if mode is None else mode
     kind = "reference" if O.ref() is not None else "port"
     enc = O.ref_encode if kind == "reference" else O.oracle_encode
     cores = os.cpu_count() or 1
     nthreads = min(cores, 64)
     # one frame per thread per round; rounds sized to the time budget from a probe
     t0 = time.perf_counter()
-    enc(frames[0], W, H, 3 * W, QUALITY, METHOD, O.YUV_420)
+    enc(frames[0], w, h, 3 * w, quality, method, mode)
     probe = time.perf_counter() - t0
     rounds = max(1, min(2000, int(seconds_budget / max(probe * 1.3, 1e-3))))
     done = [0] * nthreads
 
     def work(t):
         for r in range(rounds):
-            enc(frames[(t + r) % len(frames)], W, H, 3 * W, QUALITY, METHOD, O.YUV_420)
+            enc(frames[(t + r) % len(frames)], w, h, 3 * w, quality, method, mode)
             done[t] += 1
 
     ths = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
@@ -168,9 +172,184 @@ def cpu_reference_throughput(frames, seconds_budget=12.0):
         t.join()
     dt = time.perf_counter() - t0
     n = sum(done)
-    sample = "%d threads x %d frames of %s, frame-parallel SjpegEncode (ctypes releases the GIL), %.1f s" % (
-        nthreads, rounds, "3840x2160", dt)
-    return n * W * H / dt / 1e6, kind, nthreads, sample, dt, n
+    sample = "%d threads x %d frames of %dx%d, frame-parallel SjpegEncode (ctypes releases the GIL), %.1f s" % (
+        nthreads, rounds, w, h, dt)
+    return n * w * h / dt / 1e6, kind, nthreads, sample, dt, n
+
+
+# ---- the other configurations of BASELINE.json, as sub-records of the bench line -----------------
+# (name, generator, width, height, quality, method, yuv mode, distinct frames)
+CONFIGS = [
+    ("C2 4K q75 420 m0, busy content", "A", 3840, 2160, 75, 0, 1, 16),
+    ("C2 4K q75 420 m4 (the reference's default method), batch", "B", 3840, 2160, 75, 4, 1, 16),
+    ("C3 4K q90 444 m1 (optimised Huffman)", "A", 3840, 2160, 90, 1, 3, 4),
+    ("C3 4K q90 444 m1 (optimised Huffman)", "B", 3840, 2160, 90, 1, 3, 4),
+    ("C4 8K q75 420 m6 (literal compression_method=6)", "A", 7680, 4320, 75, 6, 1, 2),
+    ("C4 8K q75 420 m6 (literal compression_method=6)", "B", 7680, 4320, 75, 6, 1, 2),
+    ("C4 8K q75 420 m7 (trellis)", "A", 7680, 4320, 75, 7, 1, 2),
+    ("C4 8K q75 420 m7 (trellis)", "B", 7680, 4320, 75, 7, 1, 2),
+]
+STAGE_KERNEL = {"F1": "f1_fast_kernel (convert+fDCT[+quantise])", "H1": "histogram_kernel", "Q1/T1": "requantize / trellis",
+                "S1": "symbol_stats_kernel", "E": "entropy_pack_kernel", "S": "stuff_kernel"}
+
+
+def stage_bytes(stage, w, h, mode, jpeg_bytes):
+    """ALGORITHMIC bytes of one picture per kernel stage: pixels in, 128 bytes of
+    int16 coefficients per 8x8 block, the JPEG itself."""
+    mcu, mb = (16, 6) if mode == 1 else ((8, 3) if mode == 3 else (8, 1))
+    nb = ((w + mcu - 1) // mcu) * ((h + mcu - 1) // mcu) * mb
+    coef = 128 * nb
+    return {"F1": 3 * w * h + coef, "H1": coef, "Q1/T1": 2 * coef, "S1": coef, "E": coef + jpeg_bytes,
+            "S": 2 * jpeg_bytes}[stage]
+
+
+def run_config(ctx, name, gen, w, h, q, m, mode, nframes, peak, cpu_seconds):
+    import ctypes as C
+    import torch
+    import oracle_lib as O
+    import sjpeg_b200 as S
+    frames = [O.make_rgb(gen, w, h, 7654321 + f) for f in range(nframes)]
+    enc = O.ref_encode if O.ref() is not None else O.oracle_encode
+    want = [enc(f, w, h, 3 * w, float(q), m, mode) for f in frames]
+    dev = [torch.from_numpy(f.reshape(-1)).cuda() for f in frames]
+    ptrs = [t.data_ptr() for t in dev]
+    p = S.default_params(q, m, mode)
+    ctx.bench_device(ptrs, w, h, 3 * w, p, 2)
+    iters = 5
+    total_ms = min(ctx.bench_device(ptrs, w, h, 3 * w, p, iters)[0] for _ in range(2))
+    exact = all(ctx.bench_output(i) == want[i] for i in range(nframes))
+    _, fpl = ctx.last_stage_timings()
+    # one group alone on one stream: clean per-stage times
+    best = None
+    for _ in range(3):
+        ctx.bench_device(ptrs[:fpl], w, h, 3 * w, p, 1)
+        st, _ = ctx.last_stage_timings()
+        if best is None or sum(st.values()) < sum(best.values()):
+            best = st
+    mean_bytes = sum(len(x) for x in want) / len(want)
+    dom = max(best, key=best.get)
+    dom_bytes = fpl * stage_bytes(dom, w, h, mode, mean_bytes)
+    # end to end: pinned host input, host output
+    pinned = []
+    for f in frames:
+        ptr = S.lib().sjb_host_alloc(f.nbytes)
+        C.memmove(ptr, f.ctypes.data, f.nbytes)
+        pinned.append(ptr)
+    cap = int(max(len(x) for x in want) * 1.25) + 4096
+    outs = [S.lib().sjb_host_alloc(cap) for _ in frames]
+    ctx.encode_batch(pinned, False, w, h, 3 * w, p, outs, False, cap)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        sizes = ctx.encode_batch(pinned, False, w, h, 3 * w, p, outs, False, cap)
+    e2e_s = (time.perf_counter() - t0) / reps
+    exact = exact and all(bytes((C.c_uint8 * sizes[i]).from_address(outs[i])) == want[i] for i in range(nframes))
+    for ptr in pinned + outs:
+        S.lib().sjb_host_free(ptr)
+    del dev
+    torch.cuda.empty_cache()
+    cpu = None
+    if cpu_seconds > 0:
+        v, kind, cores, sample, _, _ = cpu_reference_throughput(frames, cpu_seconds, w, h, float(q), m, mode)
+        cpu = {"value": round(v, 1), "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample}
+    return {
+        "config": name, "content": "gen " + gen, "frames": nframes, "frames_per_launch": fpl,
+        "bit_exact_vs_reference": bool(exact), "md5_frame0": O.md5(want[0]), "jpeg_bytes_frame0": len(want[0]),
+        "device_mpix_s": round(nframes * iters * w * h / total_ms / 1e3, 1),
+        "device_us_per_picture": round(total_ms * 1e3 / (nframes * iters), 2),
+        "e2e_mpix_s": round(nframes * w * h / e2e_s / 1e6, 1),
+        "kernel_ms_per_launch": {k: round(v, 4) for k, v in best.items()},
+        "dominant": {"kernel": STAGE_KERNEL[dom], "ms": round(best[dom], 4), "algorithmic_bytes": int(dom_bytes),
+                     "achieved_gbs": round(dom_bytes / best[dom] / 1e6, 1), "frac_of_hbm_peak": round(dom_bytes / best[dom] / 1e6 / peak, 4)},
+        "cpu": cpu,
+    }
+
+
+def run_config5(ctx, rank, world, dist, barrier):
+    """BASELINE.json configs[4]: 64 x 1080p, as frames (each rank its own pictures) and as row stripes
+    (every picture split across the ranks; NCCL exchange inside the library, JPEGs complete on rank 0)."""
+    import ctypes as C
+    import hashlib
+    import numpy as np
+    import torch
+    import oracle_lib as O
+    import sjpeg_b200 as S
+    from sjpeg_b200 import distributed as D
+    w, h, n = 1920, 1080, 64
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_md5.json")))["config5"]
+    frames = [O.make_rgb("B", w, h, 7654321 + f) for f in range(n)]
+
+    def pin(arr):
+        ptr = S.lib().sjb_host_alloc(arr.nbytes)
+        C.memmove(ptr, arr.ctypes.data, arr.nbytes)
+        return ptr
+
+    def timed(fn, reps=4):
+        best = None
+        for rep in range(reps + 1):
+            barrier()
+            t0 = time.perf_counter()
+            res = fn()
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            if rep > 0:
+                best = float(dt.item()) if best is None else min(best, float(dt.item()))
+        return best, res
+
+    out = []
+    for method in (0, 4):
+        p = S.default_params(75, method, S.YUV_420)
+        # frames
+        a, b = D.shard_frames(n, world)[rank]
+        mine = [pin(f) for f in frames[a:b]]
+        cap = 1 << 20
+        outs = [S.lib().sjb_host_alloc(cap) for _ in mine]
+        t_frames, sizes = timed(lambda: ctx.encode_batch(mine, False, w, h, 3 * w, p, outs, False, cap))
+        digests = [O.md5(bytes((C.c_uint8 * sizes[i]).from_address(outs[i]))) for i in range(len(mine))]
+        ok_frames = digests == gold["frame_md5"][a:b] if method == 0 else all(
+            bytes((C.c_uint8 * sizes[i]).from_address(outs[i])) == O.oracle_encode(frames[a + i], w, h, 3 * w, 75.0, method, O.YUV_420)
+            for i in (0, len(mine) - 1))
+        for ptr in mine + outs:
+            S.lib().sjb_host_free(ptr)
+        # stripes
+        # NCCL prints its version banner on STDOUT when a communicator is created (NCCL_DEBUG=VERSION
+        # in this image): keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            enc = D.NcclStripeEncoder(ctx, single=(dist is None))
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        y0, y1 = enc.rows(h, S.YUV_420)
+        stripes = [pin(np.ascontiguousarray(f[y0:y1])) for f in frames]
+        t_stripes, jpegs = timed(lambda: enc.encode(stripes, False, w, h, 3 * w, p, cap))
+        ok_stripes = None
+        if rank == 0:
+            if method == 0:
+                dd = hashlib.md5("".join(O.md5(j) for j in jpegs).encode()).hexdigest().upper()
+                ok_stripes = dd == gold["md5_of_md5s"]
+            else:
+                ok_stripes = all(jpegs[i] == O.oracle_encode(frames[i], w, h, 3 * w, 75.0, method, O.YUV_420) for i in (0, 31, 63))
+        enc.close()
+        for ptr in stripes:
+            S.lib().sjb_host_free(ptr)
+        flags = torch.tensor([1.0 if ok_frames else 0.0], device="cuda")
+        if dist is not None:
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        out.append({"config": "C5 64 x 1920x1080 gen B q75 420 m%d, host buffers" % method, "n_gpus": world,
+                    "frames": {"mpix_s": round(n * w * h / t_frames / 1e6, 1), "ms": round(t_frames * 1e3, 3),
+                               "bit_exact_vs_reference": bool(flags.item() > 0.5),
+                               "what": "each rank encodes 64/N whole pictures (sjb_encode_batch), no data-path collective"},
+                    "stripes": {"mpix_s": round(n * w * h / t_stripes / 1e6, 1), "ms": round(t_stripes * 1e3, 3),
+                                "bit_exact_vs_reference": ok_stripes,
+                                "what": "every picture cut into N row stripes (sjb_stripes_encode): NCCL all-gathers of DCs / "
+                                        "bit counts / sizes%s, grouped send/recv of the compressed stripes to rank 0"
+                                        % (", all-reduces of histograms and symbol counts" if method else "")}})
+    return out
 
 
 def run_reference(args):
@@ -290,9 +469,10 @@ def run_ours(args):
     if bytes(out0) != want:
         raise SystemExit("bench.py: batch output differs from the oracle")
 
-    # what the host->device link itself delivers on this box (bare pinned copy of one step's input),
-    # so that the reader can see how far e2e is from the PCIe ceiling
-    link_gbs = None
+    # what the host->device link itself delivers on this box: a bare pinned copy of one step's input,
+    # (a) on this rank alone-ish (no barrier: ranks drift apart) and (b) with every rank copying at the
+    # same time (barrier before each repetition, max over ranks) -- the ceiling of the e2e figure
+    link_gbs = link_gbs_conc = None
     try:
         nbytes = n * 3 * W * H
         hbuf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
@@ -306,9 +486,29 @@ def run_ours(args):
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
         link_gbs = round(nbytes / best / 1e9, 2)
+        worst = []
+        for _ in range(5):
+            barrier()
+            t0 = time.perf_counter()
+            for _r in range(3):
+                dbuf.copy_(hbuf, non_blocking=True)
+            torch.cuda.synchronize()
+            dtt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(dtt, op=dist.ReduceOp.MAX)
+            worst.append(float(dtt.item()) / 3)
+        link_gbs_conc = round(nbytes / min(worst) / 1e9, 2)
         del hbuf, dbuf
     except Exception:
         pass
+
+    # ---- BASELINE.json configs[4] on all ranks (frames and NCCL row stripes) ---------------------
+    config5 = None
+    if not args.quick:
+        try:
+            config5 = run_config5(ctx, rank, world, dist, barrier)
+        except Exception as e:      # reported, not fatal: the headline stands on its own
+            config5 = [{"config": "C5", "error": "%s: %s" % (type(e).__name__, e)}]
 
     if rank != 0:
         if dist is not None:
@@ -331,10 +531,20 @@ def run_ours(args):
 
     # ---- CPU baseline (rank 0, N == 1 only) --------------------------------------------------
     cpu = None
+    configs = list(config5 or [])
     if world == 1:
         os.sched_setaffinity(0, all_cpus)      # the CPU arm gets every host core again
         v, kind, cores, sample, _, _ = cpu_reference_throughput(frames[:4], seconds_budget=12.0)
         cpu = {"value": round(v, 2), "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample}
+        # ---- the other single-GPU configurations (N == 1 only) -------------------------------
+        if not args.quick:
+            del dev
+            torch.cuda.empty_cache()
+            for cfg in CONFIGS:
+                try:
+                    configs.append(run_config(ctx, *cfg, peak=peak, cpu_seconds=2.0))
+                except Exception as e:
+                    configs.append({"config": cfg[0], "content": "gen " + cfg[1], "error": "%s: %s" % (type(e).__name__, e)})
 
     line = {
         "metric": "Mpixels/sec encode (4K RGB q75 yuv420)", "value": round(value, 1), "unit": "Mpix/s",
@@ -350,14 +560,19 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 1), "unit": "Mpix/s", "h2d_bytes_per_step": n * 3 * W * H,
                 "d2h_bytes_per_step": int(sum(sizes)), "api": "sjb_encode_batch, pinned host input, host output",
                 "h2d_gbs_achieved": round(n * 3 * W * H * args.steps * world / float(t.item()) / 1e9 / world, 2),
-                "h2d_gbs_bare_copy": link_gbs},
+                "h2d_gbs_bare_copy": link_gbs, "h2d_gbs_bare_copy_concurrent": link_gbs_conc,
+                "e2e_frac_of_concurrent_link": (round(n * 3 * W * H * args.steps / float(t.item()) / 1e9 / link_gbs_conc, 3)
+                                                if link_gbs_conc else None)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "f1_fast_kernel<420> (convert+fDCT+quantise)",
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": traffic, "peak_source": peak_kind, "algorithmic_bytes_per_launch": algo_bytes, "frames_per_launch": fpl,
+                     "traffic": traffic, "traffic_source": "profiles/f1_traffic.json: dram__bytes_read+write of this kernel from an "
+                     "ncu --set full capture, per launch of the same shape; not re-measured in this run",
+                     "peak_source": peak_kind, "algorithmic_bytes_per_launch": algo_bytes, "frames_per_launch": fpl,
                      "ms_per_launch": round(f1_ms, 5)},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
+        "configs": configs,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -370,6 +585,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="headline only: skip the configs sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -238,258 +238,289 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
   std::vector<CodeTabs> tabs(un, def_tabs);
   std::vector<FrameSet> fsets(groups);
 
+  // The batch is cut into chunks of kChunkGroups groups.  A chunk's uploads and first kernels run on
+  // its sets' own streams (phase 1); its collectives, host phases and the gather to rank 0 run on
+  // the communicator's stream (the rest).  Phase 1 of chunk c+1 is enqueued BEFORE the rest of
+  // chunk c, so the host-to-device copies of the next chunk -- what bounds a batch that comes from
+  // host memory -- proceed while this chunk's exchange waits for its small messages.
+  enum { kChunkGroups = 2 };
+  const int chunks = (groups + kChunkGroups - 1) / kChunkGroups;
+
   // ---- phase 1, every set on its own stream: upload, F1 (+ H1) ---------------------------------
-  for (int k = 0; k < groups; ++k) {
-    Lane* L = comm->sets[k];
-    const int frames = std::min<int>(kMaxGroup, n - k * kMaxGroup);
-    RC(ReserveLane(ctx, L, plan, frames));
-    FrameSet& fs = fsets[k];
-    FillFrameSet(plan, stride, &fs);
-    fs.frames = frames;
-    CU(cudaStreamWaitEvent(L->stream, comm->joined, 0));      // previous batch's last use of these buffers
-    if (L->words_dirty) {
-      CU(cudaMemsetAsync(L->words.ptr, 0, L->words.bytes, L->stream));
-      L->words_dirty = false;
-    }
-    if (active) {
-      if (!pix_on_device) RC(ReservePix(ctx, L, plan, stride, frames));
-      for (int f = 0; f < frames; ++f) {
-        const uint8_t* p = pix[k * kMaxGroup + f];
-        if (p == nullptr) return SJB_ERR_ARG;
-        fs.pix[f] = p;
-        if (!pix_on_device) {
-          long long ds = stride;
-          RC(UploadPicture(ctx, L, p, plan, stride, f, &fs.pix[f], &ds));
-          fs.stride = ds;
+  auto phase1 = [&](int c) -> int {
+    for (int k = c * kChunkGroups; k < std::min(groups, (c + 1) * kChunkGroups); ++k) {
+      Lane* L = comm->sets[k];
+      const int frames = std::min<int>(kMaxGroup, n - k * kMaxGroup);
+      RC(ReserveLane(ctx, L, plan, frames));
+      FrameSet& fs = fsets[k];
+      FillFrameSet(plan, stride, &fs);
+      fs.frames = frames;
+      CU(cudaStreamWaitEvent(L->stream, comm->joined, 0));      // previous batch's last use of these buffers
+      if (L->words_dirty) {
+        CU(cudaMemsetAsync(L->words.ptr, 0, L->words.bytes, L->stream));
+        L->words_dirty = false;
+      }
+      if (active) {
+        if (!pix_on_device) RC(ReservePix(ctx, L, plan, stride, frames));
+        for (int f = 0; f < frames; ++f) {
+          const uint8_t* p = pix[k * kMaxGroup + f];
+          if (p == nullptr) return SJB_ERR_ARG;
+          fs.pix[f] = p;
+          if (!pix_on_device) {
+            long long ds = stride;
+            RC(UploadPicture(ctx, L, p, plan, stride, f, &fs.pix[f], &ds));
+            fs.stride = ds;
+          }
         }
+        LaunchF1(L, fs, plan.g, /*raw=*/plan.adaptive, qt);
       }
-      LaunchF1(L, fs, plan.g, /*raw=*/plan.adaptive, qt);
-    }
-    if (plan.adaptive) {
-      CU(cudaMemsetAsync(L->d_small()->hist, 0, frames * sizeof(L->d_small()->hist[0]), L->stream));
-      if (active) LaunchHistogram(fs, L->gb, L->stream);
-    }
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(L->ev[3], L->stream));
-    CU(cudaStreamWaitEvent(st, L->ev[3], 0));
-    L->header_valid = 0;
-    L->tabs_valid = 0;
-  }
-  // from here on everything runs on the communicator's stream, in the same order on every rank
-
-  // ---- adaptive quantisation: all-reduce the histograms, every rank derives the same matrices ----
-  if (plan.adaptive) {
-    NC(api->GroupStart());
-    for (int k = 0; k < groups; ++k) {
-      SmallLayout* D = comm->sets[k]->d_small();
-      NC(api->AllReduce(D->hist, D->hist, static_cast<size_t>(fsets[k].frames) * 2 * 64 * kHistoStride, ncclInt32, ncclSum,
-                        comm->nccl, st));
-    }
-    NC(api->GroupEnd());
-    for (int k = 0; k < groups; ++k) {
-      Lane* L = comm->sets[k];
-      CU(cudaMemcpyAsync(L->host->hist, L->d_small()->hist, fsets[k].frames * sizeof(L->host->hist[0]),
-                         cudaMemcpyDeviceToHost, st));
-    }
-    CU(cudaStreamSynchronize(st));
-    bool ok = true;
-    ctx->pool.ParallelFor(n, [&](int i) {
-      Lane* L = comm->sets[i / kMaxGroup];
-      const int f = i % kMaxGroup;
-      uint8_t q[2][64];
-      memcpy(q, quant0, 128);
-      AnalyseHistograms(L->host->hist[f], full.g.nb_comps, q, min_quant, plan.p.qdelta_max_luma, plan.p.qdelta_max_chroma);
-      QuantTabs qf = qt;
-      for (int c = (full.g.nb_comps > 1 ? 1 : 0); c >= 0; --c) {
-        if (!FinalizeQuantizer(q[c], min_quant[c], plan.p.q_bias, &qf.m[c])) ok = false;
+      if (plan.adaptive) {
+        CU(cudaMemsetAsync(L->d_small()->hist, 0, frames * sizeof(L->d_small()->hist[0]), L->stream));
+        if (active) LaunchHistogram(fs, L->gb, L->stream);
       }
-      L->host->qtabs[f] = qf;
-      memcpy(L->host->quant[f], q, 128);
-      memcpy(&quant[static_cast<size_t>(i) * 128], q, 128);
-    });
-    if (!ok) return SJB_ERR_ARG;
-    for (int k = 0; k < groups; ++k) {
-      Lane* L = comm->sets[k];
-      SmallLayout* D = L->d_small();
-      const int frames = fsets[k].frames;
-      CU(cudaMemcpyAsync(D->qtabs, L->host->qtabs, frames * sizeof(QuantTabs), cudaMemcpyHostToDevice, st));
-      if (!active) continue;
-      if (plan.trellis) {
-        CU(cudaMemcpyAsync(D->quant, L->host->quant, frames * 128, cudaMemcpyHostToDevice, st));
-        for (int f = 0; f < frames; ++f) L->host->tabs[f] = def_tabs;      // rate model: default AC tables (enc.cc:334)
-        CU(cudaMemcpyAsync(D->tabs, L->host->tabs, frames * sizeof(CodeTabs), cudaMemcpyHostToDevice, st));
-        LaunchTrellis(fsets[k], L->gb, nullptr, &D->trellis_sort[0][0], L->perm.as<uint32_t>(), plan.g.nb_blocks(), st);
-      } else {
-        LaunchRequantize(fsets[k], L->gb, nullptr, st);
-      }
+      CU(cudaGetLastError());
+      CU(cudaEventRecord(L->ev[3], L->stream));
+      L->header_valid = 0;
+      L->tabs_valid = 0;
     }
-    CU(cudaGetLastError());
-  }
-
-  // ---- DC predictors: last quantised DC of every component, handed to the next stripe ----------
-  int* d_dc_local = comm->dc_local.as<int>();
-  if (active) {
-    for (int k = 0; k < groups; ++k) LaunchLastDc(fsets[k], comm->sets[k]->gb, d_dc_local + k * kMaxGroup * 3, st);
-  } else {
-    CU(cudaMemsetAsync(d_dc_local, 0, un * 3 * sizeof(int), st));
-  }
-  NC(api->AllGather(d_dc_local, comm->dc_all.ptr, un * 3, ncclInt32, comm->nccl, st));
-  auto dc_init_of = [&](int k) -> const int* {
-    return (prev_holder < 0) ? nullptr : comm->dc_all.as<int>() + (static_cast<size_t>(prev_holder) * n + k * kMaxGroup) * 3;
+    return SJB_OK;
   };
 
-  // ---- optimised Huffman tables: all-reduce the symbol counts ----------------------------------
-  if (plan.optimize) {
-    for (int k = 0; k < groups; ++k) {
+  // ---- the rest of a chunk: on the communicator's stream, in the same order on every rank -------
+  auto rest = [&](int c) -> int {
+    const int g0 = c * kChunkGroups, g1 = std::min(groups, (c + 1) * kChunkGroups);
+    const int i0 = g0 * kMaxGroup, i1 = std::min(n, g1 * kMaxGroup);
+    const int nc = i1 - i0;                                  // pictures of this chunk
+    const size_t unc = static_cast<size_t>(nc);
+    for (int k = g0; k < g1; ++k) CU(cudaStreamWaitEvent(st, comm->sets[k]->ev[3], 0));
+
+    // adaptive quantisation: all-reduce the histograms, every rank derives the same matrices
+    if (plan.adaptive) {
+      NC(api->GroupStart());
+      for (int k = g0; k < g1; ++k) {
+        SmallLayout* D = comm->sets[k]->d_small();
+        NC(api->AllReduce(D->hist, D->hist, static_cast<size_t>(fsets[k].frames) * 2 * 64 * kHistoStride, ncclInt32, ncclSum,
+                          comm->nccl, st));
+      }
+      NC(api->GroupEnd());
+      for (int k = g0; k < g1; ++k) {
+        Lane* L = comm->sets[k];
+        CU(cudaMemcpyAsync(L->host->hist, L->d_small()->hist, fsets[k].frames * sizeof(L->host->hist[0]),
+                           cudaMemcpyDeviceToHost, st));
+      }
+      CU(cudaStreamSynchronize(st));
+      bool ok = true;
+      ctx->pool.ParallelFor(nc, [&](int j) {
+        const int i = i0 + j;
+        Lane* L = comm->sets[i / kMaxGroup];
+        const int f = i % kMaxGroup;
+        uint8_t q[2][64];
+        memcpy(q, quant0, 128);
+        AnalyseHistograms(L->host->hist[f], full.g.nb_comps, q, min_quant, plan.p.qdelta_max_luma, plan.p.qdelta_max_chroma);
+        QuantTabs qf = qt;
+        for (int cc = (full.g.nb_comps > 1 ? 1 : 0); cc >= 0; --cc) {
+          if (!FinalizeQuantizer(q[cc], min_quant[cc], plan.p.q_bias, &qf.m[cc])) ok = false;
+        }
+        L->host->qtabs[f] = qf;
+        memcpy(L->host->quant[f], q, 128);
+        memcpy(&quant[static_cast<size_t>(i) * 128], q, 128);
+      });
+      if (!ok) return SJB_ERR_ARG;
+      for (int k = g0; k < g1; ++k) {
+        Lane* L = comm->sets[k];
+        SmallLayout* D = L->d_small();
+        const int frames = fsets[k].frames;
+        CU(cudaMemcpyAsync(D->qtabs, L->host->qtabs, frames * sizeof(QuantTabs), cudaMemcpyHostToDevice, st));
+        if (!active) continue;
+        if (plan.trellis) {
+          CU(cudaMemcpyAsync(D->quant, L->host->quant, frames * 128, cudaMemcpyHostToDevice, st));
+          for (int f = 0; f < frames; ++f) L->host->tabs[f] = def_tabs;      // rate model: default AC tables (enc.cc:334)
+          CU(cudaMemcpyAsync(D->tabs, L->host->tabs, frames * sizeof(CodeTabs), cudaMemcpyHostToDevice, st));
+          LaunchTrellis(fsets[k], L->gb, nullptr, &D->trellis_sort[0][0], L->perm.as<uint32_t>(), plan.g.nb_blocks(), st);
+        } else {
+          LaunchRequantize(fsets[k], L->gb, nullptr, st);
+        }
+      }
+      CU(cudaGetLastError());
+    }
+
+    // DC predictors: last quantised DC of every component, handed to the next stripe
+    int* d_dc_local = comm->dc_local.as<int>();
+    if (active) {
+      for (int k = g0; k < g1; ++k) LaunchLastDc(fsets[k], comm->sets[k]->gb, d_dc_local + (k - g0) * kMaxGroup * 3, st);
+    } else {
+      CU(cudaMemsetAsync(d_dc_local, 0, unc * 3 * sizeof(int), st));
+    }
+    NC(api->AllGather(d_dc_local, comm->dc_all.ptr, unc * 3, ncclInt32, comm->nccl, st));
+    auto dc_init_of = [&](int k) -> const int* {
+      return (prev_holder < 0) ? nullptr
+                               : comm->dc_all.as<int>() + (static_cast<size_t>(prev_holder) * nc + (k - g0) * kMaxGroup) * 3;
+    };
+
+    // optimised Huffman tables: all-reduce the symbol counts
+    if (plan.optimize) {
+      for (int k = g0; k < g1; ++k) {
+        Lane* L = comm->sets[k];
+        SmallLayout* D = L->d_small();
+        CU(cudaMemsetAsync(D->freq, 0, fsets[k].frames * sizeof(D->freq[0]), st));
+        if (!active) continue;
+        GroupBuffers gb = L->gb;
+        gb.dc_init = dc_init_of(k);
+        LaunchSymbolStats(fsets[k], gb, st);
+      }
+      CU(cudaGetLastError());
+      NC(api->GroupStart());
+      for (int k = g0; k < g1; ++k) {
+        SmallLayout* D = comm->sets[k]->d_small();
+        NC(api->AllReduce(D->freq, D->freq, static_cast<size_t>(fsets[k].frames) * 2 * 272, ncclUint32, ncclSum, comm->nccl, st));
+      }
+      NC(api->GroupEnd());
+      for (int k = g0; k < g1; ++k) {
+        Lane* L = comm->sets[k];
+        CU(cudaMemcpyAsync(L->host->freq, L->d_small()->freq, fsets[k].frames * sizeof(L->host->freq[0]),
+                           cudaMemcpyDeviceToHost, st));
+      }
+      CU(cudaStreamSynchronize(st));
+      const int nb_tables = (full.g.nb_comps == 1) ? 1 : 2;
+      ctx->pool.ParallelFor(nc, [&](int j) {
+        const int i = i0 + j;
+        const uint32_t* freq = comm->sets[i / kMaxGroup]->host->freq[i % kMaxGroup];
+        for (int cc = 0; cc < nb_tables; ++cc) {
+          OptimalHuffSpec(freq + 272 * cc + 256, 12, &spec[i * 4 + cc]);
+          OptimalHuffSpec(freq + 272 * cc, 256, &spec[i * 4 + 2 + cc]);
+          CodesFromSpec(spec[i * 4 + cc], tabs[i].dc[cc]);
+          CodesFromSpec(spec[i * 4 + 2 + cc], tabs[i].ac[cc]);
+        }
+      });
+    }
+
+    // entropy coding, bit counts, global bit offsets, byte stuffing
+    unsigned long long* d_bits = comm->bits_local.as<unsigned long long>();
+    CU(cudaMemsetAsync(d_bits, 0, unc * 8, st));
+    for (int k = g0; k < g1 && active; ++k) {
       Lane* L = comm->sets[k];
-      SmallLayout* D = L->d_small();
-      CU(cudaMemsetAsync(D->freq, 0, fsets[k].frames * sizeof(D->freq[0]), st));
-      if (!active) continue;
+      const int frames = fsets[k].frames;
+      // pinned staging: an earlier copy out of it (the trellis' default tables) must have completed;
+      // every method that runs the trellis also optimises, i.e. has synchronised since -- but be explicit
+      if (plan.trellis && !plan.optimize) CU(cudaStreamSynchronize(st));
+      for (int f = 0; f < frames; ++f) L->host->tabs[f] = tabs[k * kMaxGroup + f];
+      CU(cudaMemcpyAsync(L->d_small()->tabs, L->host->tabs, frames * sizeof(CodeTabs), cudaMemcpyHostToDevice, st));
+      CU(cudaMemsetAsync(L->state.ptr, 0, L->state.bytes, st));
       GroupBuffers gb = L->gb;
       gb.dc_init = dc_init_of(k);
-      LaunchSymbolStats(fsets[k], gb, st);
+      L->words_dirty = true;
+      LaunchEntropyPack(fsets[k], gb, st);
+      LaunchStripeBits(gb, frames, d_bits + (k - g0) * kMaxGroup, st);
     }
     CU(cudaGetLastError());
-    NC(api->GroupStart());
-    for (int k = 0; k < groups; ++k) {
-      SmallLayout* D = comm->sets[k]->d_small();
-      NC(api->AllReduce(D->freq, D->freq, static_cast<size_t>(fsets[k].frames) * 2 * 272, ncclUint32, ncclSum, comm->nccl, st));
-    }
-    NC(api->GroupEnd());
-    for (int k = 0; k < groups; ++k) {
+    NC(api->AllGather(d_bits, comm->bits_all.ptr, unc, ncclUint64, comm->nccl, st));
+    unsigned long long* d_off = comm->offsets.as<unsigned long long>();
+    LaunchStripeOffsets(comm->bits_all.as<unsigned long long>(), nc, rank, d_off, st);
+    unsigned long long* d_meta = comm->meta_local.as<unsigned long long>();
+    CU(cudaMemsetAsync(d_meta, 0, unc * 16, st));
+    for (int k = g0; k < g1 && active; ++k) {
       Lane* L = comm->sets[k];
-      CU(cudaMemcpyAsync(L->host->freq, L->d_small()->freq, fsets[k].frames * sizeof(L->host->freq[0]),
+      StuffArgs sa;
+      memset(&sa, 0, sizeof(sa));
+      for (int f = 0; f < fsets[k].frames; ++f) sa.flags[f] = (is_first ? kStuffFirst : 0) | (is_last ? kStuffLast : 0) | kStuffKeepWords;
+      GroupBuffers gb = L->gb;
+      gb.bit_offsets = d_off + (k - g0) * kMaxGroup;
+      LaunchStuff(fsets[k], gb, sa, st);
+      LaunchStripeMeta(gb, fsets[k].frames, d_meta + static_cast<size_t>(k - g0) * kMaxGroup * 2, st);
+    }
+    CU(cudaGetLastError());
+    NC(api->AllGather(d_meta, comm->meta_all.ptr, unc * 2, ncclUint64, comm->nccl, st));
+    CU(cudaMemcpyAsync(comm->h_meta, comm->meta_all.ptr, unc * 16 * world, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+
+    // gather the compressed stripes on rank 0: exact sizes, one grouped send/recv
+    std::vector<size_t> rank_bytes(world, 0);
+    for (int r = 0; r < world; ++r) {
+      for (int j = 0; j < nc; ++j) rank_bytes[r] += static_cast<size_t>(comm->h_meta[(static_cast<size_t>(r) * nc + j) * 2]);
+    }
+    size_t total = 0;
+    for (int r = 0; r < world; ++r) total += rank_bytes[r];
+    if (active && rank_bytes[rank] > 0) {
+      CU(comm->send.Reserve(rank_bytes[rank]));
+      for (int k = g0; k < g1; ++k) {
+        Lane* L = comm->sets[k];
+        LaunchStripeCompact(L->gb.out, L->gb.out_pitch, (k - g0) * kMaxGroup, fsets[k].frames, d_meta, comm->send.as<uint8_t>(), st);
+      }
+      CU(cudaGetLastError());
+    }
+    if (rank == 0) {
+      CU(comm->recv.Reserve(std::max<size_t>(total, 1)));
+      if (comm->h_recv_cap < total) {
+        if (comm->h_recv) cudaFreeHost(comm->h_recv);
+        comm->h_recv = nullptr;
+        comm->h_recv_cap = 0;
+        CU(cudaMallocHost(reinterpret_cast<void**>(&comm->h_recv), total + (total >> 2) + 4096));
+        comm->h_recv_cap = total + (total >> 2) + 4096;
+      }
+    }
+    std::vector<size_t> rank_base(world, 0);
+    for (int r = 1; r < world; ++r) rank_base[r] = rank_base[r - 1] + rank_bytes[r - 1];
+    if (world > 1) {
+      NC(api->GroupStart());
+      if (rank != 0 && rank_bytes[rank] > 0) NC(api->Send(comm->send.ptr, rank_bytes[rank], ncclUint8, 0, comm->nccl, st));
+      if (rank == 0) {
+        for (int r = 1; r < world; ++r) {
+          if (rank_bytes[r] > 0) NC(api->Recv(comm->recv.as<uint8_t>() + rank_base[r], rank_bytes[r], ncclUint8, r, comm->nccl, st));
+        }
+      }
+      NC(api->GroupEnd());
+    }
+    for (int k = g0; k < g1; ++k) comm->sets[k]->words_dirty = true;   // shifted reads cannot self-clean
+    if (rank != 0) {
+      CU(cudaStreamSynchronize(st));       // the send buffer is reused by the next chunk
+      return SJB_OK;
+    }
+    if (rank_bytes[0] > 0) CU(cudaMemcpyAsync(comm->h_recv, comm->send.ptr, rank_bytes[0], cudaMemcpyDeviceToHost, st));
+    if (total > rank_bytes[0]) {
+      CU(cudaMemcpyAsync(comm->h_recv + rank_bytes[0], comm->recv.as<uint8_t>() + rank_bytes[0], total - rank_bytes[0],
                          cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(st));
-    const int nb_tables = (full.g.nb_comps == 1) ? 1 : 2;
-    ctx->pool.ParallelFor(n, [&](int i) {
-      const uint32_t* freq = comm->sets[i / kMaxGroup]->host->freq[i % kMaxGroup];
-      for (int c = 0; c < nb_tables; ++c) {
-        OptimalHuffSpec(freq + 272 * c + 256, 12, &spec[i * 4 + c]);
-        OptimalHuffSpec(freq + 272 * c, 256, &spec[i * 4 + 2 + c]);
-        CodesFromSpec(spec[i * 4 + c], tabs[i].dc[c]);
-        CodesFromSpec(spec[i * 4 + 2 + c], tabs[i].ac[c]);
-      }
-    });
-  }
 
-  // ---- entropy coding, bit counts, global bit offsets, byte stuffing ---------------------------
-  unsigned long long* d_bits = comm->bits_local.as<unsigned long long>();
-  CU(cudaMemsetAsync(d_bits, 0, un * 8, st));
-  for (int k = 0; k < groups && active; ++k) {
-    Lane* L = comm->sets[k];
-    const int frames = fsets[k].frames;
-    // pinned staging: an earlier copy out of it (the trellis' default tables) must have completed;
-    // every method that runs the trellis also optimises, i.e. has synchronised since -- but be explicit
-    if (plan.trellis && !plan.optimize) CU(cudaStreamSynchronize(st));
-    for (int f = 0; f < frames; ++f) L->host->tabs[f] = tabs[k * kMaxGroup + f];
-    CU(cudaMemcpyAsync(L->d_small()->tabs, L->host->tabs, frames * sizeof(CodeTabs), cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(L->state.ptr, 0, L->state.bytes, st));
-    GroupBuffers gb = L->gb;
-    gb.dc_init = dc_init_of(k);
-    L->words_dirty = true;
-    LaunchEntropyPack(fsets[k], gb, st);
-    LaunchStripeBits(gb, frames, d_bits + k * kMaxGroup, st);
-  }
-  CU(cudaGetLastError());
-  NC(api->AllGather(d_bits, comm->bits_all.ptr, un, ncclUint64, comm->nccl, st));
-  unsigned long long* d_off = comm->offsets.as<unsigned long long>();
-  LaunchStripeOffsets(comm->bits_all.as<unsigned long long>(), n, rank, d_off, st);
-  unsigned long long* d_meta = comm->meta_local.as<unsigned long long>();
-  CU(cudaMemsetAsync(d_meta, 0, un * 16, st));
-  for (int k = 0; k < groups && active; ++k) {
-    Lane* L = comm->sets[k];
-    StuffArgs sa;
-    memset(&sa, 0, sizeof(sa));
-    for (int f = 0; f < fsets[k].frames; ++f) sa.flags[f] = (is_first ? kStuffFirst : 0) | (is_last ? kStuffLast : 0) | kStuffKeepWords;
-    GroupBuffers gb = L->gb;
-    gb.bit_offsets = d_off + k * kMaxGroup;
-    LaunchStuff(fsets[k], gb, sa, st);
-    LaunchStripeMeta(gb, fsets[k].frames, d_meta + static_cast<size_t>(k) * kMaxGroup * 2, st);
-  }
-  CU(cudaGetLastError());
-  NC(api->AllGather(d_meta, comm->meta_all.ptr, un * 2, ncclUint64, comm->nccl, st));
-  CU(cudaMemcpyAsync(comm->h_meta, comm->meta_all.ptr, un * 16 * world, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-
-  // ---- gather the compressed stripes on rank 0: exact sizes, one grouped send/recv -------------
-  std::vector<size_t> rank_bytes(world, 0);
-  for (int r = 0; r < world; ++r) {
-    for (int i = 0; i < n; ++i) rank_bytes[r] += static_cast<size_t>(comm->h_meta[(static_cast<size_t>(r) * n + i) * 2]);
-  }
-  size_t total = 0;
-  for (int r = 0; r < world; ++r) total += rank_bytes[r];
-  if (active && rank_bytes[rank] > 0) {
-    CU(comm->send.Reserve(rank_bytes[rank]));
-    for (int k = 0; k < groups; ++k) {
-      Lane* L = comm->sets[k];
-      LaunchStripeCompact(L->gb.out, L->gb.out_pitch, k * kMaxGroup, fsets[k].frames, d_meta, comm->send.as<uint8_t>(), st);
-    }
-    CU(cudaGetLastError());
-  }
-  if (rank == 0) {
-    CU(comm->recv.Reserve(std::max<size_t>(total, 1)));
-    if (comm->h_recv_cap < total) {
-      if (comm->h_recv) cudaFreeHost(comm->h_recv);
-      comm->h_recv = nullptr;
-      CU(cudaMallocHost(reinterpret_cast<void**>(&comm->h_recv), total + (total >> 2) + 4096));
-      comm->h_recv_cap = total + (total >> 2) + 4096;
-    }
-  }
-  std::vector<size_t> rank_base(world, 0);
-  for (int r = 1; r < world; ++r) rank_base[r] = rank_base[r - 1] + rank_bytes[r - 1];
-  if (world > 1) {
-    NC(api->GroupStart());
-    if (rank != 0 && rank_bytes[rank] > 0) NC(api->Send(comm->send.ptr, rank_bytes[rank], ncclUint8, 0, comm->nccl, st));
-    if (rank == 0) {
-      for (int r = 1; r < world; ++r) {
-        if (rank_bytes[r] > 0) NC(api->Recv(comm->recv.as<uint8_t>() + rank_base[r], rank_bytes[r], ncclUint8, r, comm->nccl, st));
+    // rank 0: header + stripes, boundary bytes merged
+    int rc = SJB_OK;
+    std::vector<size_t> cursor(rank_base);
+    std::vector<const uint8_t*> part(world);
+    std::vector<size_t> psize(world);
+    std::vector<unsigned> pflags(world);
+    std::vector<uint8_t> header;
+    for (int j = 0; j < nc; ++j) {
+      const int i = i0 + j;
+      header.clear();
+      AppendHeaders(full.g, reinterpret_cast<const uint8_t(*)[64]>(&quant[static_cast<size_t>(i) * 128]), &spec[i * 4], &header);
+      int holders = 0;
+      for (int r = 0; r <= last_holder; ++r) {
+        const unsigned long long* m = comm->h_meta + (static_cast<size_t>(r) * nc + j) * 2;
+        part[holders] = comm->h_recv + cursor[r];
+        psize[holders] = static_cast<size_t>(m[0]);
+        pflags[holders] = static_cast<unsigned>(m[1]);
+        cursor[r] += psize[holders];
+        ++holders;
       }
+      size_t size = 0;
+      const int arc = sjb_stripes_assemble(header.data(), header.size(), holders, part.data(), psize.data(), pflags.data(),
+                                           out[i], out[i] ? out_capacity : 0, &size);
+      sizes[i] = size;
+      if (arc != SJB_OK) rc = arc;
     }
-    NC(api->GroupEnd());
+    return rc;
+  };
+
+  int result = SJB_OK;
+  RC(phase1(0));
+  for (int c = 0; c < chunks; ++c) {
+    if (c + 1 < chunks) RC(phase1(c + 1));
+    const int rc = rest(c);
+    if (rc != SJB_OK && rc != SJB_ERR_CAPACITY) return rc;
+    if (rc != SJB_OK) result = rc;
   }
-  for (int k = 0; k < groups; ++k) comm->sets[k]->words_dirty = true;   // shifted reads cannot self-clean
   CU(cudaEventRecord(comm->joined, st));
-  if (rank != 0) {
-    CU(cudaStreamSynchronize(st));       // the caller may reuse its (pinned) inputs
-    return SJB_OK;
-  }
-  if (rank_bytes[0] > 0) {
-    CU(cudaMemcpyAsync(comm->h_recv, comm->send.ptr, rank_bytes[0], cudaMemcpyDeviceToHost, st));
-  }
-  if (total > rank_bytes[0]) {
-    CU(cudaMemcpyAsync(comm->h_recv + rank_bytes[0], comm->recv.as<uint8_t>() + rank_bytes[0], total - rank_bytes[0],
-                       cudaMemcpyDeviceToHost, st));
-  }
-  CU(cudaStreamSynchronize(st));
-
-  // ---- rank 0: header + stripes, boundary bytes merged ------------------------------------------
-  int rc = SJB_OK;
-  std::vector<size_t> cursor(rank_base);
-  std::vector<const uint8_t*> part(world);
-  std::vector<size_t> psize(world);
-  std::vector<unsigned> pflags(world);
-  std::vector<uint8_t> header;
-  for (int i = 0; i < n; ++i) {
-    header.clear();
-    AppendHeaders(full.g, reinterpret_cast<const uint8_t(*)[64]>(&quant[static_cast<size_t>(i) * 128]), &spec[i * 4], &header);
-    int holders = 0;
-    for (int r = 0; r <= last_holder; ++r) {
-      const unsigned long long* m = comm->h_meta + (static_cast<size_t>(r) * n + i) * 2;
-      part[holders] = comm->h_recv + cursor[r];
-      psize[holders] = static_cast<size_t>(m[0]);
-      pflags[holders] = static_cast<unsigned>(m[1]);
-      cursor[r] += psize[holders];
-      ++holders;
-    }
-    size_t size = 0;
-    const int arc = sjb_stripes_assemble(header.data(), header.size(), holders, part.data(), psize.data(), pflags.data(),
-                                         out[i], out[i] ? out_capacity : 0, &size);
-    sizes[i] = size;
-    if (arc != SJB_OK) rc = arc;
-  }
-  return rc;
+  return result;
 } SJB_NOTHROW_END
 
 }  // extern "C"
