@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <memory>
@@ -118,6 +119,15 @@ struct Lane {
   SmallLayout* d_small() const { return small.as<SmallLayout>(); }
 };
 
+}  // namespace
+
+// More hardware work queues than the default 8, so that the streams of a context (lanes, uploads,
+// collectives) do not share queues with each other or with the host program's own streams.  Only
+// effective if the library is loaded before the CUDA context exists; never overrides the user.
+namespace {
+struct MoreConnections {
+  MoreConnections() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+} g_more_connections;
 }  // namespace
 
 struct sjb_context {
@@ -301,7 +311,8 @@ int ReservePix(sjb_context* ctx, Lane* L, const Plan& plan, long long stride, in
 // Copies one host picture into slot `slot` of the lane's pixel buffer; returns the device
 // address of its row 0.
 int UploadPicture(sjb_context* ctx, Lane* L, const uint8_t* pix, const Plan& plan, long long stride, int slot,
-                  const uint8_t** d_row0, long long* d_stride) {
+                  const uint8_t** d_row0, long long* d_stride, cudaStream_t copy_stream = nullptr) {
+  if (copy_stream == nullptr) copy_stream = L->stream;
   const size_t row_bytes = static_cast<size_t>(plan.pstep) * plan.g.width;
   const long long astride = stride < 0 ? -stride : stride;
   const int h = plan.g.height;
@@ -320,21 +331,21 @@ int UploadPicture(sjb_context* ctx, Lane* L, const uint8_t* pix, const Plan& pla
       // with helper threads instead of the driver's single-threaded pageable path
       cudaPointerAttributes attr;
       if (cudaPointerGetAttributes(&attr, lowest) == cudaSuccess && attr.type == cudaMemoryTypeUnregistered) {
-        const cudaError_t e = ctx->stager.Upload(base, lowest, span, L->stream);
+        const cudaError_t e = ctx->stager.Upload(base, lowest, span, copy_stream);
         if (e == cudaSuccess) staged = true;
         else if (e != cudaErrorNotSupported) CU(e);
       } else {
         cudaGetLastError();
       }
     }
-    if (!staged) CU(cudaMemcpyAsync(base, lowest, span, cudaMemcpyHostToDevice, L->stream));
+    if (!staged) CU(cudaMemcpyAsync(base, lowest, span, cudaMemcpyHostToDevice, copy_stream));
     *d_row0 = base + ((stride < 0) ? static_cast<size_t>(astride) * (h - 1) : 0);
     *d_stride = stride;
   } else {
     // sparse rows: gather into a tight pitch
     const size_t pitch = (row_bytes + 15) & ~static_cast<size_t>(15);
     CU(cudaMemcpy2DAsync(base, pitch, lowest, static_cast<size_t>(astride), row_bytes, h, cudaMemcpyHostToDevice,
-                         L->stream));
+                         copy_stream));
     *d_row0 = base + ((stride < 0) ? pitch * (h - 1) : 0);
     *d_stride = (stride < 0) ? -static_cast<long long>(pitch) : static_cast<long long>(pitch);
   }
@@ -447,7 +458,7 @@ int UploadCodeTabs(sjb_context* ctx, GroupJob* J) {
   if (same) return SJB_OK;
   CU(cudaStreamSynchronize(L->stream));
   for (int f = 0; f < n; ++f) H->tabs[f] = J->tabs[f];
-  CU(cudaMemcpyAsync(L->d_small()->tabs, H->tabs, n * sizeof(CodeTabs), cudaMemcpyHostToDevice, L->stream));
+  LaunchCopySmall(L->d_small()->tabs, H->tabs, n * sizeof(CodeTabs), L->stream);   // not the copy engine: kernels.cu
   L->tabs_valid = n;
   return SJB_OK;
 }
@@ -477,8 +488,7 @@ int FinishGroup(sjb_context* ctx, GroupJob* J) {
       for (int f = 0; f < n; ++f) {
         memcpy(H->header[f], headers[f].data(), headers[f].size());
         L->header_len[f] = static_cast<unsigned>(headers[f].size());
-        CU(cudaMemcpyAsync(gb.out + f * gb.out_pitch, H->header[f], headers[f].size(), cudaMemcpyHostToDevice,
-                           L->stream));
+        LaunchCopySmall(gb.out + f * gb.out_pitch, H->header[f], headers[f].size(), L->stream);
       }
       L->header_valid = n;
     }
@@ -598,10 +608,10 @@ int AdvanceGroup(sjb_context* ctx, GroupJob* J) {
       memcpy(&J->quant[f * 128], q, 128);
     });
     if (!ok) return SJB_ERR_ARG;
-    CU(cudaMemcpyAsync(D->qtabs, H->qtabs, n * sizeof(QuantTabs), cudaMemcpyHostToDevice, L->stream));
+    LaunchCopySmall(D->qtabs, H->qtabs, n * sizeof(QuantTabs), L->stream);
     if (plan.trellis) {
       // rate model = default AC tables (enc.cc:334)
-      CU(cudaMemcpyAsync(D->quant, H->quant, n * 128, cudaMemcpyHostToDevice, L->stream));
+      LaunchCopySmall(D->quant, H->quant, n * 128, L->stream);
       RC(UploadCodeTabs(ctx, J));
       StageTimer t(L, 2, J->timed);
       LaunchTrellis(J->fs, L->gb, nullptr, &D->trellis_sort[0][0], L->perm.as<uint32_t>(), g.nb_blocks(), L->stream);

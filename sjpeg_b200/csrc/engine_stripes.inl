@@ -36,8 +36,9 @@ struct sjb_comm {
   sjb_context* ctx = nullptr;
   ncclComm_t nccl = nullptr;
   int rank = 0, world = 1;
-  cudaStream_t stream = nullptr;        // all collectives, and every kernel after the first one
-  std::vector<Lane*> sets;              // one buffer set (own stream for upload + F1) per group of stripes
+  cudaStream_t stream = nullptr;        // every kernel and every collective, in the same order on all ranks
+  cudaStream_t upload = nullptr;        // every host-to-device copy of the pixels, in order (see phase1)
+  std::vector<Lane*> sets;              // one buffer set per group of stripes (their own streams stay idle)
   DeviceBuffer dc_local, dc_all, bits_local, bits_all, offsets, meta_local, meta_all, send, recv, zeros;
   unsigned long long* h_meta = nullptr; // pinned [world][n][2]
   size_t h_meta_cap = 0;
@@ -86,6 +87,7 @@ int sjb_comm_create(sjb_context* ctx, const uint8_t id[128], int rank, int world
   memcpy(&u, id, 128);
   NC(api->CommInitRank(&c->nccl, world, u, rank));
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->upload, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->joined, cudaEventDisableTiming));
   *out = c.release();
   return SJB_OK;
@@ -109,6 +111,7 @@ void sjb_comm_destroy(sjb_comm* c) {
   const NcclApi* api = Nccl();
   if (api != nullptr && c->nccl != nullptr) api->CommDestroy(c->nccl);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->upload) cudaStreamDestroy(c->upload);
   delete c;
 }
 
@@ -247,6 +250,12 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
   const int chunks = (groups + kChunkGroups - 1) / kChunkGroups;
 
   // ---- phase 1, every set on its own stream: upload, F1 (+ H1) ---------------------------------
+  // Phase 1 enqueues COPIES only, all on one stream.  (Copies issued on several streams share the
+  // link concurrently, so every chunk's pixels would arrive at the end of the whole batch's upload;
+  // in order, chunk c is complete while c+1 is still being copied.  And no kernel of chunk c+1 is
+  // enqueued before the exchange of chunk c: a kernel waiting for pixels that are still in flight
+  // held up the collectives queued after it -- measured: every chunk's sizes arrived only when the
+  // next chunk's upload had finished.)
   auto phase1 = [&](int c) -> int {
     for (int k = c * kChunkGroups; k < std::min(groups, (c + 1) * kChunkGroups); ++k) {
       Lane* L = comm->sets[k];
@@ -255,11 +264,7 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
       FrameSet& fs = fsets[k];
       FillFrameSet(plan, stride, &fs);
       fs.frames = frames;
-      CU(cudaStreamWaitEvent(L->stream, comm->joined, 0));      // previous batch's last use of these buffers
-      if (L->words_dirty) {
-        CU(cudaMemsetAsync(L->words.ptr, 0, L->words.bytes, L->stream));
-        L->words_dirty = false;
-      }
+      CU(cudaStreamWaitEvent(comm->upload, comm->joined, 0));   // previous batch's last use of these buffers
       if (active) {
         if (!pix_on_device) RC(ReservePix(ctx, L, plan, stride, frames));
         for (int f = 0; f < frames; ++f) {
@@ -268,18 +273,12 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
           fs.pix[f] = p;
           if (!pix_on_device) {
             long long ds = stride;
-            RC(UploadPicture(ctx, L, p, plan, stride, f, &fs.pix[f], &ds));
+            RC(UploadPicture(ctx, L, p, plan, stride, f, &fs.pix[f], &ds, comm->upload));
             fs.stride = ds;
           }
         }
-        LaunchF1(L, fs, plan.g, /*raw=*/plan.adaptive, qt);
       }
-      if (plan.adaptive) {
-        CU(cudaMemsetAsync(L->d_small()->hist, 0, frames * sizeof(L->d_small()->hist[0]), L->stream));
-        if (active) LaunchHistogram(fs, L->gb, L->stream);
-      }
-      CU(cudaGetLastError());
-      CU(cudaEventRecord(L->ev[3], L->stream));
+      CU(cudaEventRecord(L->ev[2], comm->upload));
       L->header_valid = 0;
       L->tabs_valid = 0;
     }
@@ -287,12 +286,44 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
   };
 
   // ---- the rest of a chunk: on the communicator's stream, in the same order on every rank -------
+  static const bool trace = getenv("SJB_STRIPES_TRACE") != nullptr;
+  static const bool trace_sync = trace && atoi(getenv("SJB_STRIPES_TRACE")) >= 2;
+  auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
   auto rest = [&](int c) -> int {
+    double t_mark = now_us();
+    auto mark = [&](const char* what) {
+      if (!trace) return;
+      if (trace_sync) cudaStreamSynchronize(st);      // SJB_STRIPES_TRACE=2: device time of each step
+      const double t = now_us();
+      fprintf(stderr, "[stripes r%d c%d] %-22s %8.1f us\n", rank, c, what, t - t_mark);
+      t_mark = t;
+    };
     const int g0 = c * kChunkGroups, g1 = std::min(groups, (c + 1) * kChunkGroups);
     const int i0 = g0 * kMaxGroup, i1 = std::min(n, g1 * kMaxGroup);
     const int nc = i1 - i0;                                  // pictures of this chunk
     const size_t unc = static_cast<size_t>(nc);
-    for (int k = g0; k < g1; ++k) CU(cudaStreamWaitEvent(st, comm->sets[k]->ev[3], 0));
+    // colour conversion + fDCT (+ quantise | histogram) once the chunk's pixels have landed
+    for (int k = g0; k < g1; ++k) {
+      Lane* L = comm->sets[k];
+      CU(cudaStreamWaitEvent(st, L->ev[2], 0));
+      if (L->words_dirty) {
+        CU(cudaMemsetAsync(L->words.ptr, 0, L->words.bytes, st));
+        L->words_dirty = false;
+      }
+      if (active) {
+        Lane view;                       // LaunchF1 reads gb / stream / launches only
+        view.gb = L->gb;
+        view.stream = st;
+        LaunchF1(&view, fsets[k], plan.g, /*raw=*/plan.adaptive, qt);
+        view.stream = nullptr;
+      }
+      if (plan.adaptive) {
+        CU(cudaMemsetAsync(L->d_small()->hist, 0, fsets[k].frames * sizeof(L->d_small()->hist[0]), st));
+        if (active) LaunchHistogram(fsets[k], L->gb, st);
+      }
+    }
+    CU(cudaGetLastError());
+    mark("F1");
 
     // adaptive quantisation: all-reduce the histograms, every rank derives the same matrices
     if (plan.adaptive) {
@@ -330,12 +361,12 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
         Lane* L = comm->sets[k];
         SmallLayout* D = L->d_small();
         const int frames = fsets[k].frames;
-        CU(cudaMemcpyAsync(D->qtabs, L->host->qtabs, frames * sizeof(QuantTabs), cudaMemcpyHostToDevice, st));
+        LaunchCopySmall(D->qtabs, L->host->qtabs, frames * sizeof(QuantTabs), st);
         if (!active) continue;
         if (plan.trellis) {
-          CU(cudaMemcpyAsync(D->quant, L->host->quant, frames * 128, cudaMemcpyHostToDevice, st));
+          LaunchCopySmall(D->quant, L->host->quant, frames * 128, st);
           for (int f = 0; f < frames; ++f) L->host->tabs[f] = def_tabs;      // rate model: default AC tables (enc.cc:334)
-          CU(cudaMemcpyAsync(D->tabs, L->host->tabs, frames * sizeof(CodeTabs), cudaMemcpyHostToDevice, st));
+          LaunchCopySmall(D->tabs, L->host->tabs, frames * sizeof(CodeTabs), st);
           LaunchTrellis(fsets[k], L->gb, nullptr, &D->trellis_sort[0][0], L->perm.as<uint32_t>(), plan.g.nb_blocks(), st);
         } else {
           LaunchRequantize(fsets[k], L->gb, nullptr, st);
@@ -352,6 +383,7 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
       CU(cudaMemsetAsync(d_dc_local, 0, unc * 3 * sizeof(int), st));
     }
     NC(api->AllGather(d_dc_local, comm->dc_all.ptr, unc * 3, ncclInt32, comm->nccl, st));
+    mark("enqueue to AG(dc)");
     auto dc_init_of = [&](int k) -> const int* {
       return (prev_holder < 0) ? nullptr
                                : comm->dc_all.as<int>() + (static_cast<size_t>(prev_holder) * nc + (k - g0) * kMaxGroup) * 3;
@@ -404,7 +436,7 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
       // every method that runs the trellis also optimises, i.e. has synchronised since -- but be explicit
       if (plan.trellis && !plan.optimize) CU(cudaStreamSynchronize(st));
       for (int f = 0; f < frames; ++f) L->host->tabs[f] = tabs[k * kMaxGroup + f];
-      CU(cudaMemcpyAsync(L->d_small()->tabs, L->host->tabs, frames * sizeof(CodeTabs), cudaMemcpyHostToDevice, st));
+      LaunchCopySmall(L->d_small()->tabs, L->host->tabs, frames * sizeof(CodeTabs), st);
       CU(cudaMemsetAsync(L->state.ptr, 0, L->state.bytes, st));
       GroupBuffers gb = L->gb;
       gb.dc_init = dc_init_of(k);
@@ -413,7 +445,9 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
       LaunchStripeBits(gb, frames, d_bits + (k - g0) * kMaxGroup, st);
     }
     CU(cudaGetLastError());
+    mark("E");
     NC(api->AllGather(d_bits, comm->bits_all.ptr, unc, ncclUint64, comm->nccl, st));
+    mark("AG(bits)");
     unsigned long long* d_off = comm->offsets.as<unsigned long long>();
     LaunchStripeOffsets(comm->bits_all.as<unsigned long long>(), nc, rank, d_off, st);
     unsigned long long* d_meta = comm->meta_local.as<unsigned long long>();
@@ -430,8 +464,10 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
     }
     CU(cudaGetLastError());
     NC(api->AllGather(d_meta, comm->meta_all.ptr, unc * 2, ncclUint64, comm->nccl, st));
-    CU(cudaMemcpyAsync(comm->h_meta, comm->meta_all.ptr, unc * 16 * world, cudaMemcpyDeviceToHost, st));
+    LaunchCopySmall(comm->h_meta, comm->meta_all.ptr, unc * 16 * world, st);
+    mark("enqueue to AG(meta)");
     CU(cudaStreamSynchronize(st));
+    mark("sync after meta");
 
     // gather the compressed stripes on rank 0: exact sizes, one grouped send/recv
     std::vector<size_t> rank_bytes(world, 0);
@@ -471,6 +507,7 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
       NC(api->GroupEnd());
     }
     for (int k = g0; k < g1; ++k) comm->sets[k]->words_dirty = true;   // shifted reads cannot self-clean
+    mark("compact + send/recv enq");
     if (rank != 0) {
       CU(cudaStreamSynchronize(st));       // the send buffer is reused by the next chunk
       return SJB_OK;
@@ -481,6 +518,7 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
                          cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(st));
+    mark("sync after gather");
 
     // rank 0: header + stripes, boundary bytes merged
     int rc = SJB_OK;
@@ -508,13 +546,28 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
       sizes[i] = size;
       if (arc != SJB_OK) rc = arc;
     }
+    mark("assemble");
     return rc;
   };
 
+  // How far the uploads run ahead of the exchange: pinned (or device) pixels are copied
+  // asynchronously, so every chunk's copies are queued at once and the link never idles; pageable
+  // pixels go through the context's staging threads, which block the caller, one chunk ahead.
+  int ahead = 1;
+  if (pix_on_device) {
+    ahead = chunks;
+  } else if (active) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, pix[0]) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered) ahead = chunks;
+    cudaGetLastError();
+  }
   int result = SJB_OK;
-  RC(phase1(0));
+  const double t_begin = now_us();
+  int queued = 0;
+  for (; queued < std::min(chunks, ahead); ++queued) RC(phase1(queued));
   for (int c = 0; c < chunks; ++c) {
-    if (c + 1 < chunks) RC(phase1(c + 1));
+    if (queued < chunks && queued <= c + ahead) RC(phase1(queued++));
+    if (trace) fprintf(stderr, "[stripes r%d c%d] phase1 enqueued at     %8.1f us since entry\n", rank, c, now_us() - t_begin);
     const int rc = rest(c);
     if (rc != SJB_OK && rc != SJB_ERR_CAPACITY) return rc;
     if (rc != SJB_OK) result = rc;

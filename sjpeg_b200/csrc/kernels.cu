@@ -1448,6 +1448,26 @@ __global__ void stripe_meta_kernel(GroupBuffers gb, int frames, unsigned long lo
   meta[2 * f + 1] = static_cast<unsigned long long>(in.head_byte) | (static_cast<unsigned long long>(in.tail_byte) << 8) |
                     (static_cast<unsigned long long>(in.tail_bits) << 16) | (static_cast<unsigned long long>(in.head_open) << 24);
 }
+// Small copies between PINNED HOST and device memory done by a kernel (pinned memory is device-
+// accessible under unified addressing) instead of the copy engine.  The copy engine serves a
+// direction in FIFO order across streams: a 2 KB table upload enqueued after 50 MB of pixel uploads
+// of a LATER group waits for all of them (measured in the stripe exchange: the entropy stage of a
+// chunk started 0.86 ms late, exactly the next chunk's upload time).  A load/store from an SM does
+// not queue behind the engine.  Either pointer may be pinned host or device memory.
+__global__ void copy_small_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t bytes) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 7) == 0) {
+    const size_t words = bytes >> 3;
+    for (size_t i = t; i < words; i += stride) {
+      reinterpret_cast<unsigned long long*>(dst)[i] = reinterpret_cast<const unsigned long long*>(src)[i];
+    }
+    for (size_t i = (words << 3) + t; i < bytes; i += stride) dst[i] = src[i];
+  } else {
+    for (size_t i = t; i < bytes; i += stride) dst[i] = src[i];
+  }
+  __threadfence_system();
+}
 // gridDim.y = stripe of the group; CTAs stride over its bytes
 __global__ void __launch_bounds__(256)
 stripe_compact_kernel(const uint8_t* __restrict__ group_out, size_t out_pitch, int first,
@@ -1617,6 +1637,12 @@ void LaunchStripeOffsets(const unsigned long long* all_bits, int n, int rank, un
 }
 void LaunchStripeMeta(const GroupBuffers& gb, int frames, unsigned long long* meta, cudaStream_t s) {
   stripe_meta_kernel<<<1, 32, 0, s>>>(gb, frames, meta);
+}
+void LaunchCopySmall(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return;
+  unsigned grid = cdiv(bytes, 256 * 8);
+  if (grid > 32) grid = 32;
+  copy_small_kernel<<<grid, 256, 0, s>>>(static_cast<uint8_t*>(dst), static_cast<const uint8_t*>(src), bytes);
 }
 void LaunchStripeCompact(const uint8_t* group_out, size_t out_pitch, int first, int frames, const unsigned long long* meta_all_local,
                          uint8_t* dst, cudaStream_t s) {

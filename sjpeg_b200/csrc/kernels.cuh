@@ -139,6 +139,9 @@ void LaunchStripeBits(const GroupBuffers& gb, int frames, unsigned long long* bi
 void LaunchStripeOffsets(const unsigned long long* all_bits, int n, int rank, unsigned long long* offsets, cudaStream_t s);
 // meta[f] = {out_size, head_byte | tail_byte << 8 | tail_bits << 16}
 void LaunchStripeMeta(const GroupBuffers& gb, int frames, unsigned long long* meta, cudaStream_t s);
+// small copy between pinned host and device memory (either direction) done by a kernel, so that it
+// does not queue behind bulk transfers on the copy engine
+void LaunchCopySmall(void* dst, const void* src, size_t bytes, cudaStream_t s);
 // packs the emitted bytes of the n stripes (slot f of its group at src[f], sizes in meta[f*2]) back to
 // back into dst; one launch per group: dst_offset_base = where the group's first stripe goes is
 // computed on the device from the sizes of all stripes before it (meta of the whole batch)
