@@ -229,6 +229,10 @@ int sjb_stripes_assemble(const uint8_t* header, size_t header_len, int stripes, 
 
 /* Pinned host memory helpers (for callers that want async copies at PCIe speed). */
 void* sjb_host_alloc(size_t bytes);
+/* Same, write-combined (cudaHostAllocWriteCombined): not cached on the host side, so the device reads
+ * it over PCIe without snooping the CPU caches -- for input buffers the host only ever WRITES
+ * sequentially (reading them back on the host is very slow). */
+void* sjb_host_alloc_wc(size_t bytes);
 void sjb_host_free(void* p);
 
 /* ---- stage-level entry points (used by the parity tests and the benchmark) ---------------- */

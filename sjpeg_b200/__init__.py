@@ -61,6 +61,7 @@ _SIGNATURES = {
                                    C.c_longlong, C.POINTER(Params), C.POINTER(C.c_void_p), C.c_int,
                                    C.c_size_t, C.POINTER(C.c_size_t)]),
     "sjb_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "sjb_host_alloc_wc": (C.c_void_p, [C.c_size_t]),
     "sjb_host_free": (None, [C.c_void_p]),
     "sjb_stage_coefficients": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
                                          C.POINTER(Params), C.c_int, C.c_void_p, C.c_void_p]),

@@ -990,6 +990,14 @@ void* sjb_host_alloc(size_t bytes) {
   }
   return p;
 }
+void* sjb_host_alloc_wc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocWriteCombined) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
 void sjb_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
