@@ -247,9 +247,24 @@ SJB_HD uint32_t chunk_nonzero_bits(const Words4& q) {
 // symbol -- the trip count of a warp is the largest number of non-zeros among its 32 blocks (per
 // half of the block), not the number of (chunk, slot) pairs any of them touches.  Loader: operator()(chunk) -> Words4, value(pos) -> the
 // quantised value at zig-zag position pos.
+// map of the non-zero AC positions of a block (bits 1..31 of *lo = positions 1..31, *hi = 32..63),
+// assembled from the chunks the bitmap names (a short loop, usually one or two chunks)
+template <class Loader>
+SJB_HD void block_nz_maps(const Loader& load, uint32_t chunkmask, uint32_t* lo, uint32_t* hi) {
+  uint32_t nz_lo = 0, nz_hi = 0;
+  for (uint32_t m = chunkmask; m; m &= m - 1) {
+    const int c = find_first_set32(m);
+    const uint32_t b8 = chunk_nonzero_bits(load(c)) << (8 * (c & 3));
+    if (c < 4) nz_lo |= b8; else nz_hi |= b8;
+  }
+  *lo = nz_lo & ~1u;                       // position 0 is the DC
+  *hi = nz_hi;
+}
+
+// DC symbol, then ONE loop iteration per non-zero coefficient, then EOB
 template <class Loader, class Sink>
-SJB_HD void code_block(Loader load, uint32_t chunkmask, int dc, int dc_pred, const uint32_t* dc_codes,
-                       const uint32_t* ac_codes, Sink& sink) {
+SJB_HD void code_block_mapped(const Loader& load, uint32_t nz_lo, uint32_t nz_hi, int dc, int dc_pred,
+                              const uint32_t* dc_codes, const uint32_t* ac_codes, Sink& sink) {
   {
     const int diff = dc - dc_pred;
     int n = 0;
@@ -259,14 +274,6 @@ SJB_HD void code_block(Loader load, uint32_t chunkmask, int dc, int dc_pred, con
     // code then n suffix bits; at most 16 + 11 bits
     sink.put(((c >> 16) << n) | bits, (int)(c & 0xff) + n);
   }
-  // positions 0..31 and 32..63 as two 32-bit maps: cheaper to scan than one 64-bit word
-  uint32_t nz_lo = 0, nz_hi = 0;
-  for (uint32_t m = chunkmask; m; m &= m - 1) {
-    const int c = find_first_set32(m);
-    const uint32_t b8 = chunk_nonzero_bits(load(c)) << (8 * (c & 3));
-    if (c < 4) nz_lo |= b8; else nz_hi |= b8;
-  }
-  nz_lo &= ~1u;                            // position 0 is the DC
   const uint32_t zrl = ac_codes[0xf0];
   int prev = 0;                            // zig-zag position of the previous non-zero (0 = DC slot)
 #if defined(__CUDA_ARCH__)
@@ -303,6 +310,15 @@ SJB_HD void code_block(Loader load, uint32_t chunkmask, int dc, int dc_pred, con
     const uint32_t c = ac_codes[0x00];
     sink.put(c >> 16, (int)(c & 0xff));
   }
+}
+
+template <class Loader, class Sink>
+SJB_HD void code_block(Loader load, uint32_t chunkmask, int dc, int dc_pred, const uint32_t* dc_codes,
+                       const uint32_t* ac_codes, Sink& sink) {
+  // positions 0..31 and 32..63 as two 32-bit maps: cheaper to scan than one 64-bit word
+  uint32_t nz_lo, nz_hi;
+  block_nz_maps(load, chunkmask, &nz_lo, &nz_hi);
+  code_block_mapped(load, nz_lo, nz_hi, dc, dc_pred, dc_codes, ac_codes, sink);
 }
 
 struct BitCountSink {

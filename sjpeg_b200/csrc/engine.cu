@@ -35,16 +35,17 @@ using namespace sjb;
 namespace {
 
 enum { kMaxLanes = 4, kHeaderReserve = 2048, kWorstBitsPerBlock = 1696, kHeadCopyBytes = 1 << 20 };
-// Pictures per launch = this budget / coefficient bytes per picture (at most kMaxGroup).  Measured
-// at 4K: 8 pictures per launch (200 MB) against 4 (100 MB) shorten the tail of the F1 grid (6.8
-// instead of 3.4 waves of CTAs: 13.8 -> 12.6 us per picture) and amortise the entropy stage's
-// launches (13.6 -> 10.4 us per picture); what the entropy kernel really reads back -- bitmaps and
-// the non-zero sectors -- still fits the 126 MB L2.  SJB_GROUP_BUDGET_MB overrides the default.
+// Pictures per launch = this budget / coefficient bytes per picture (at most kMaxGroup = 16): 16
+// pictures at 4K and 1080p, 4 at 8K.  Measured at 4K: 8 pictures per launch against 4 shortened the
+// tail of the F1 grid (6.8 instead of 3.4 waves of CTAs: 13.8 -> 12.6 us per picture) and amortised
+// the entropy stage's launches (13.6 -> 10.4 us per picture); 16 against 8 gave another 3.5 % on the
+// whole pipeline.  What the entropy kernel really reads back -- bitmaps and the non-zero sectors --
+// still fits the 126 MB L2 for photographic content.  SJB_GROUP_BUDGET_MB overrides the default.
 size_t GroupCoefBudget() {
   static const size_t v = [] {
     const char* e = getenv("SJB_GROUP_BUDGET_MB");
-    const long mb = e ? atol(e) : 200;
-    return static_cast<size_t>(mb > 0 ? mb : 200) << 20;
+    const long mb = e ? atol(e) : 400;
+    return static_cast<size_t>(mb > 0 ? mb : 400) << 20;
   }();
   return v;
 }
@@ -371,7 +372,9 @@ void LaunchF1(Lane* L, const FrameSet& fs, const FrameGeometry& g, bool raw, con
   const int mx_full = g.width / g.mcu_size, my_full = g.height / g.mcu_size;
   int mx_fast = 0, my_fast = 0;
   if (F1FastEligible(fs)) {
-    mx_fast = (g.yuv_mode == kYuv420) ? mx_full : (mx_full & ~1);
+    // row bytes of a partial tile must be a multiple of 16: any MCU count for packed 4:2:0 (48 or 64
+    // bytes per MCU), an even one otherwise (8 / 24 bytes per MCU and plane)
+    mx_fast = (g.yuv_mode == kYuv420 && !fs.planar) ? mx_full : (mx_full & ~1);
     my_fast = my_full;
     if (mx_fast == 0) my_fast = 0;
     if (my_fast == 0) mx_fast = 0;

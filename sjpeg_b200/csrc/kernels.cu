@@ -496,6 +496,126 @@ f1_fast_kernel(const __grid_constant__ FrameSet fs, int mx_full, int my0,
 }
 
 // -------------------------------------------------------------------------------------------
+// F1 fast path for PLANAR sources (EncodeYUV420 / YUV444 / NV12 / NV21 / Gray, encoders.cc:256-507,
+// and the planes the sharp conversion leaves): no colour conversion, sample = pixel - 128
+// (Convert8To16b, colors_rgb.cc:1234-1260).  Same shape as the packed kernel: one warp per tile,
+// rows of the tile staged into shared memory by bulk-async copies (one row per lane, one mbarrier
+// for the whole tile), every lane owns one 8x8 block at a time with its 64 samples in registers.
+//   4:2:0 : tile = 16 MCUs: 16 luma rows x 256 bytes + 8 chroma rows (U | V side by side, or the
+//           interleaved plane of NV12 / NV21); lane = 2 * mcu + half does luma blocks half and
+//           2 + half, then the U (half 0) or V (half 1) block
+//   4:4:4 : tile = 32 MCUs, three 8-row strips, lane = MCU        4:0:0 : the luma strip only
+// Needs 16-byte aligned plane bases and strides and an even number of MCUs per tile row (chroma
+// rows of 8 bytes per MCU must be multiples of 16 bytes); engine.cu sends the rest to the generic kernel.
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void plane_block_from_smem(uint32_t addr, uint32_t row_stride, int (&x)[64]) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    uint32_t w[2];
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(addr + r * row_stride));
+#pragma unroll
+    for (int c = 0; c < 8; ++c) x[8 * r + c] = static_cast<int>(SJB_BYTE(w, c)) - 128;
+  }
+}
+// one component of an interleaved chroma row: bytes parity, parity + 2, ... of 16 bytes
+__device__ __forceinline__ void plane_block_from_smem_interleaved(uint32_t addr, uint32_t row_stride, int parity, int (&x)[64]) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    uint32_t w[4];
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr + r * row_stride));
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t even = SJB_BYTE(w, 2 * c), odd = SJB_BYTE(w, 2 * c + 1);
+      x[8 * r + c] = static_cast<int>(parity ? odd : even) - 128;
+    }
+  }
+}
+
+template <int kMode, bool kRaw>
+__global__ void __launch_bounds__(32, 16)
+f1_planar_kernel(const __grid_constant__ FrameSet fs, int mx_full, int my0,
+                 const __grid_constant__ QuantTabs qt, GroupBuffers gb) {
+  constexpr bool k420 = (kMode == kYuv420);
+  constexpr int kMcusPerTile = k420 ? 16 : 32;
+  constexpr int kYRows = k420 ? 16 : 8;
+  constexpr int kCBytes = (kMode == kYuv400) ? 16 : (k420 ? 8 * 256 : 2 * 8 * 256);
+  __shared__ __align__(128) uint8_t ybuf[kYRows * 256];
+  __shared__ __align__(128) uint8_t cbuf[kCBytes];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ __align__(16) int32_t qtab[2][64][2];      // zig-zag order {iq, cpos}
+  const int lane = threadIdx.x;
+  const int frame = blockIdx.y;
+  const uint32_t ys = smem_addr(ybuf), cs = smem_addr(cbuf), bar0 = smem_addr(&bar), tab0 = smem_addr(qtab);
+  int16_t* coef = gb.coef + frame * gb.coef_pitch;
+  uint8_t* nzmask = gb.nzmask + frame * gb.mask_pitch;
+  const int chunks_x = (mx_full + kMcusPerTile - 1) / kMcusPerTile;
+  const int cx = blockIdx.x % chunks_x, ry = my0 + blockIdx.x / chunks_x;
+  const int mcus = min(kMcusPerTile, mx_full - cx * kMcusPerTile);       // even (LaunchF1)
+  const bool interleaved = k420 && fs.uv_step == 2;
+  const uint32_t y_bytes = static_cast<uint32_t>(mcus) * (k420 ? 16u : 8u);
+  const uint32_t c_bytes = (kMode == kYuv400) ? 0u : static_cast<uint32_t>(mcus) * (interleaved ? 16u : 8u);
+  const int c_copies = (kMode == kYuv400) ? 0 : (interleaved ? 8 : 16);
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar0, kYRows * y_bytes + c_copies * c_bytes);
+  }
+  __syncwarp();
+  if (lane < kYRows) {
+    const long long py = static_cast<long long>(kYRows) * ry + lane;
+    bulk_g2s(ys + lane * 256, fs.pix[frame] + py * fs.stride + static_cast<long long>(cx) * 256, y_bytes, bar0);
+  } else if (lane < kYRows + c_copies) {
+    const int i = lane - kYRows;                  // chroma copy index
+    const long long py = 8LL * ry + (i & 7);
+    if (interleaved) {
+      const uint8_t* base = (fs.pix_u[frame] < fs.pix_v[frame]) ? fs.pix_u[frame] : fs.pix_v[frame];
+      bulk_g2s(cs + (i & 7) * 256, base + py * fs.stride_u + static_cast<long long>(cx) * 256, c_bytes, bar0);
+    } else if (i < 8) {
+      bulk_g2s(cs + (k420 ? (i & 7) * 256 : (i & 7) * 256), fs.pix_u[frame] + py * fs.stride_u + static_cast<long long>(cx) * (k420 ? 128 : 256),
+               c_bytes, bar0);
+    } else {
+      bulk_g2s(cs + (k420 ? (i & 7) * 256 + 128 : 2048 + (i & 7) * 256),
+               fs.pix_v[frame] + py * fs.stride_v + static_cast<long long>(cx) * (k420 ? 128 : 256), c_bytes, bar0);
+    }
+  }
+  if (!kRaw) {
+    const int32_t* q = &qt.m[0].e[0][0];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) (&qtab[0][0][0])[lane + 32 * i] = q[lane + 32 * i];
+  }
+  __syncwarp();
+  const uint32_t mcu0 = static_cast<uint32_t>(ry) * fs.mcus_x + static_cast<uint32_t>(cx) * kMcusPerTile;
+  mbar_wait(bar0, 0);
+  if (k420) {
+    const int m = lane >> 1, half = lane & 1;
+    const bool active = m < mcus;
+    const int u_parity = (fs.pix_u[frame] < fs.pix_v[frame]) ? 0 : 1;
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j) {
+      int x[64];
+      if (j < 2) {
+        plane_block_from_smem(ys + (8 * j) * 256 + m * 16 + half * 8, 256, x);
+      } else if (interleaved) {
+        plane_block_from_smem_interleaved(cs + m * 16, 256, half ? (1 - u_parity) : u_parity, x);
+      } else {
+        plane_block_from_smem(cs + half * 128 + m * 8, 256, x);
+      }
+      const uint32_t g = (mcu0 + m) * 6u + ((j < 2) ? 2 * j : 4) + half;
+      if (active) finish_block<kRaw>(x, tab0 + ((j < 2) ? 0u : 512u), coef, nzmask, g);
+    }
+  } else {
+    constexpr int kMcuBlocks = (kMode == kYuv444) ? 3 : 1;
+    const bool active = lane < mcus;
+#pragma unroll 1
+    for (int c = 0; c < kMcuBlocks; ++c) {
+      int x[64];
+      plane_block_from_smem((c == 0 ? ys : cs + (c - 1) * 2048) + lane * 8, 256, x);
+      if (active) finish_block<kRaw>(x, tab0 + (c ? 512u : 0u), coef, nzmask, (mcu0 + lane) * kMcuBlocks + c);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
 // Q1: quantise stored raw coefficients in place (per-picture tables from global memory)
 // -------------------------------------------------------------------------------------------
 __device__ __forceinline__ void load_block_natural(const int16_t* src, int (&v)[64]) {
@@ -891,6 +1011,8 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   __shared__ uint32_t tile_total[2];
   __shared__ unsigned long long tile_prefix[2];
   __shared__ uint32_t local[2][kTileBlocks][kLocalWords + 1];   // odd stride: conflict-free; word 16 = ex | bits << 20
+  __shared__ uint32_t sort_hist[64], sort_base[64];             // busy tiles: counting sort of the blocks by non-zeros
+  __shared__ uint8_t sort_order[kTileBlocks];
   const int frame = blockIdx.y;
   load_code_tables(gb.tabs + frame, &sh);
   const int16_t* zz = gb.coef + frame * gb.coef_pitch;
@@ -950,30 +1072,73 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
     // the thread that has just copied tile i-2 out of it: everybody must be done with that copy
     if (regroup && i >= 2) bar_sync(kBarWorkers, kEWorkers);
     if (t >= 0) {
-      // Which block of the tile this thread walks: luma blocks first, chroma blocks after them,
-      // so that the 32 walks of a warp have similar lengths (luma blocks carry several times the
-      // non-zeros of chroma blocks; interleaved as they are stored, a warp ran at 39 % lane
-      // efficiency on busy pictures).  Slots stay indexed by block, and the scan and the copy to
-      // the stream below run in block order with the identity mapping.
       const uint32_t first = static_cast<uint32_t>(t) * kTileBlocks;
       const uint32_t count = min(static_cast<uint32_t>(kTileBlocks), static_cast<uint32_t>(nb_blocks) - first);
-      if (threadIdx.x >= count) {
-        local[b][threadIdx.x][kLocalWords] = 0;
+      if (!regroup) {
+        // sparse tile: thread i walks block i
+        if (threadIdx.x >= count) {
+          local[b][threadIdx.x][kLocalWords] = 0;
+        } else {
+          const size_t g = static_cast<size_t>(first) + threadIdx.x;
+          uint32_t* mine = local[b][threadIdx.x];
+          const int k = block_in_mcu(g, fs.mcu_blocks);
+          const int c = (k >= fs.luma_blocks) ? 1 : 0;
+          const int16_t* blk = zz + coef_block_base(g);
+          const uint32_t mask = nzmask[g];
+          const PrefetchedChunkLoader loader(blk);
+          const int pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, dc_init);
+          const int dc = static_cast<int16_t>(loader.c0.x & 0xffffu);
+          LocalSink sink = {mine, 0, 0, 0, 0};
+          code_block(loader, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
+          sink.finish();
+          mine[kLocalWords] = sink.total;
+        }
       } else {
-        const uint32_t j = regroup ? walk_order(first, count, threadIdx.x, fs.mcu_blocks) : threadIdx.x;
-        const size_t g = static_cast<size_t>(first) + j;
-        uint32_t* mine = local[b][j];
-        const int k = block_in_mcu(g, fs.mcu_blocks);
-        const int c = (k >= fs.luma_blocks) ? 1 : 0;
-        const int16_t* blk = zz + coef_block_base(g);
-        const uint32_t mask = nzmask[g];
-        const PrefetchedChunkLoader loader(blk);
-        const int pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, dc_init);
-        const int dc = static_cast<int16_t>(loader.c0.x & 0xffffu);
-        LocalSink sink = {mine, 0, 0, 0, 0};
-        code_block(loader, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
-        sink.finish();
-        mine[kLocalWords] = sink.total;
+        // Busy tile: the trip count of a warp is the largest number of non-zeros among its 32
+        // blocks, and neighbouring blocks differ a lot (luma blocks carry several times the non-zeros
+        // of chroma blocks; lane efficiency was 14 of 32 on the 4K gen-A picture).  So every thread
+        // first builds the non-zero maps of ITS block (words 0, 1 of the block's slot), the blocks are
+        // counting-sorted by their number of non-zeros, and thread r walks the block of rank r,
+        // heaviest first.  Slots stay indexed by block; scan and copy-out keep the identity mapping.
+        if (threadIdx.x < 64) sort_hist[threadIdx.x] = 0;
+        bar_sync(kBarWorkers, kEWorkers);
+        uint32_t my_rank = 0, my_key = 0;
+        if (threadIdx.x < count) {
+          const size_t g = static_cast<size_t>(first) + threadIdx.x;
+          const ChunkLoader loader = {zz + coef_block_base(g)};
+          uint32_t lo, hi;
+          block_nz_maps(loader, nzmask[g], &lo, &hi);
+          local[b][threadIdx.x][0] = lo;
+          local[b][threadIdx.x][1] = hi;
+          my_key = static_cast<uint32_t>(__popc(lo) + __popc(hi));
+          my_rank = atomicAdd(&sort_hist[my_key], 1u);
+        } else {
+          local[b][threadIdx.x][kLocalWords] = 0;
+        }
+        bar_sync(kBarWorkers, kEWorkers);
+        if (threadIdx.x < 64) {
+          uint32_t base = 0;
+          for (int kk = 63; kk > static_cast<int>(threadIdx.x); --kk) base += sort_hist[kk];
+          sort_base[threadIdx.x] = base;
+        }
+        bar_sync(kBarWorkers, kEWorkers);
+        if (threadIdx.x < count) sort_order[sort_base[my_key] + my_rank] = static_cast<uint8_t>(threadIdx.x);
+        bar_sync(kBarWorkers, kEWorkers);
+        if (threadIdx.x < count) {
+          const uint32_t j = sort_order[threadIdx.x];
+          const size_t g = static_cast<size_t>(first) + j;
+          uint32_t* mine = local[b][j];
+          const uint32_t lo = mine[0], hi = mine[1];
+          const int k = block_in_mcu(g, fs.mcu_blocks);
+          const int c = (k >= fs.luma_blocks) ? 1 : 0;
+          const int16_t* blk = zz + coef_block_base(g);
+          const ChunkLoader loader = {blk};
+          const int pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, dc_init);
+          LocalSink sink = {mine, 0, 0, 0, 0};
+          code_block_mapped(loader, lo, hi, blk[0], pred, sh.dc[c], sh.ac[c], sink);
+          sink.finish();
+          mine[kLocalWords] = sink.total;
+        }
       }
       if (threadIdx.x == 0) next_id[b] = claim_tile();   // broadcast by the barriers below
       if (regroup) bar_sync(kBarWorkers, kEWorkers);     // every slot of the tile is filled
@@ -1518,9 +1683,21 @@ void LaunchF1Generic(const FrameSet& fs, int mx0, int my0, int mx1, int my1, boo
 }
 
 bool F1FastEligible(const FrameSet& fs) {
-  if (fs.planar || (fs.stride & 15) != 0) return false;
+  if ((fs.stride & 15) != 0) return false;
   for (int f = 0; f < fs.frames; ++f) {
     if ((reinterpret_cast<uintptr_t>(fs.pix[f]) & 15) != 0) return false;
+  }
+  if (!fs.planar) return true;
+  // planar sources: every plane 16-byte aligned; semi-planar: U and V one byte apart in one plane
+  if (fs.yuv_mode == kYuv400) return true;
+  if ((fs.stride_u & 15) != 0 || (fs.stride_v & 15) != 0) return false;
+  for (int f = 0; f < fs.frames; ++f) {
+    const uintptr_t u = reinterpret_cast<uintptr_t>(fs.pix_u[f]), v = reinterpret_cast<uintptr_t>(fs.pix_v[f]);
+    if (fs.uv_step == 2) {
+      if (fs.stride_u != fs.stride_v || (u > v ? u - v : v - u) != 1 || ((u < v ? u : v) & 15) != 0) return false;
+    } else if (fs.uv_step != 1 || (u & 15) != 0 || (v & 15) != 0) {
+      return false;
+    }
   }
   return true;
 }
@@ -1542,9 +1719,34 @@ static void LaunchF1FastF(const FrameSet& fs, int mx_full, int my0, int my1, con
   else LaunchF1FastT<kMode, kRaw, kFmtBGRA>(fs, mx_full, my0, my1, qt, gb, s);
 }
 
+template <int kMode, bool kRaw>
+static void LaunchF1PlanarT(const FrameSet& fs, int mx_full, int my0, int my1, const QuantTabs& qt,
+                            const GroupBuffers& gb, cudaStream_t s) {
+  const int per_tile = (kMode == kYuv420) ? 16 : 32;
+  const long long tiles = static_cast<long long>((mx_full + per_tile - 1) / per_tile) * (my1 - my0);
+  f1_planar_kernel<kMode, kRaw><<<dim3(static_cast<unsigned>(tiles), fs.frames), 32, 0, s>>>(fs, mx_full, my0, qt, gb);
+}
+
 void LaunchF1Fast(const FrameSet& fs, int mx_full, int my0, int my1, bool raw, const QuantTabs& qt,
                   const GroupBuffers& gb, cudaStream_t s) {
   if (mx_full <= 0 || my1 <= my0) return;
+  if (fs.planar) {
+    switch (fs.yuv_mode) {
+      case kYuv420:
+        if (raw) LaunchF1PlanarT<kYuv420, true>(fs, mx_full, my0, my1, qt, gb, s);
+        else     LaunchF1PlanarT<kYuv420, false>(fs, mx_full, my0, my1, qt, gb, s);
+        break;
+      case kYuv444:
+        if (raw) LaunchF1PlanarT<kYuv444, true>(fs, mx_full, my0, my1, qt, gb, s);
+        else     LaunchF1PlanarT<kYuv444, false>(fs, mx_full, my0, my1, qt, gb, s);
+        break;
+      default:
+        if (raw) LaunchF1PlanarT<kYuv400, true>(fs, mx_full, my0, my1, qt, gb, s);
+        else     LaunchF1PlanarT<kYuv400, false>(fs, mx_full, my0, my1, qt, gb, s);
+        break;
+    }
+    return;
+  }
   switch (fs.yuv_mode) {
     case kYuv420:
       if (raw) LaunchF1FastF<kYuv420, true>(fs, mx_full, my0, my1, qt, gb, s);

@@ -13,8 +13,10 @@
 
 namespace sjb {
 
+// 16 pictures per launch (8 in round 1): +3.5 % on the 16-frame 4K pipeline (458 -> 474 Gpix/s gen B,
+// 200 -> 205 gen A, same box), the last partly filled wave of CTAs of every kernel weighing half as much.
 #ifndef SJB_MAX_GROUP
-#define SJB_MAX_GROUP 8
+#define SJB_MAX_GROUP 16
 #endif
 enum { kMaxGroup = SJB_MAX_GROUP };
 #ifndef SJB_TILE_BLOCKS

@@ -60,9 +60,9 @@ def _encode_batch_host(ctx, frames, w, h, params, cap):
     return [outs[i][:sizes[i]].tobytes() for i in range(len(frames))]
 
 
-@pytest.mark.parametrize("shape", [(3840, 2160, 16), (1920, 1080, 17)], ids=["16x4K", "17x1080p"])
+@pytest.mark.parametrize("shape", [(3840, 2160, 16), (1920, 1080, 17), (1920, 1080, 40)], ids=["16x4K", "17x1080p", "40x1080p"])
 def test_device_resident_batches(gpu_ctx, shape):
-    """the configuration of the headline number: groups of 8 device-resident pictures per launch,
+    """the configuration of the headline number: groups of 16 device-resident pictures per launch,
     JPEGs left in device memory; 17 pictures leave a ragged last group of one"""
     import sjpeg_b200 as S
     w, h, n = shape
@@ -99,7 +99,7 @@ def test_batch_matrix_methods_modes_content(gpu_ctx, method, mode, content):
     import sjpeg_b200 as S
     w, h = (331, 203) if content != "noise" else (200, 120)
     p = S.default_params(75, method, mode)
-    for n in (3, 8, 9, 33):
+    for n in (3, 9, 17, 40):
         items = _content(content, n, w, h)
         frames = [f for _, f in items]
         want = [_want(k, f, w, h, 75, method, mode) for k, f in items]
@@ -179,3 +179,33 @@ def test_native_stripe_session_single_rank(gpu_ctx, method):
             O.oracle_encode(rgb, 320, 200, 960, 75.0, 4, O.YUV_420)
     finally:
         enc.close()
+
+
+@pytest.mark.parametrize("kind", [O.KIND_YUV420, O.KIND_YUV444, O.KIND_NV12, O.KIND_NV21, O.KIND_GRAY])
+def test_planar_fast_path_large_pictures(gpu_ctx, kind):
+    """planar / semi-planar sources through the bulk-copy F1 kernel (16-byte aligned planes): sizes
+    with several tiles per MCU row, a partial last tile, an odd MCU column and a clipped bottom
+    row left to the generic kernel; methods with and without the raw-coefficient pass"""
+    import sjpeg_b200 as S
+    for (w, h) in ((1920, 1080), (1040, 200), (1296, 72), (272, 528)):
+        for q, method in ((75, 0), (90, 4), (60, 7)):
+            planes = O.make_planes(kind, w, h, seed=w + q + kind, pad=(16 - w % 16 if w % 16 else 0, 0, 0))
+            # make every plane's stride a multiple of 16 so that the fast kernel is eligible
+            for name in ("y", "u", "v"):
+                a = planes[name]
+                if a is not None and a.strides[0] % 16:
+                    padded = np.zeros((a.shape[0], (a.shape[1] + 15) // 16 * 16), np.uint8)
+                    padded[:, :a.shape[1]] = a
+                    planes[name] = padded
+            p = S.default_params(q, method, O.KIND_MODE[kind])
+            got = gpu_ctx.encode_planar(*O.planar_args(kind, planes), w, h, p)
+            assert got == O.oracle_encode_planar(kind, planes, w, h, q, method), (kind, w, h, q, method)
+
+
+def test_sharp_4k_uses_planar_fast_path(gpu_ctx):
+    """SJPEG_YUV_SHARP at 4K: conversion on the device, then the planar 4:2:0 encoder on aligned planes"""
+    import sjpeg_b200 as S
+    w, h = 3840, 2160
+    rgb = O.make_rgb("A", w, h, 99)
+    got = gpu_ctx.encode(rgb, w, h, 3 * w, S.default_params(75, 4, S.YUV_SHARP))
+    assert got == O.oracle_encode(rgb, w, h, 3 * w, 75.0, 4, O.YUV_SHARP)

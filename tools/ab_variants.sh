@@ -19,7 +19,7 @@ if [ "$1" = build ]; then
     $NVCC $FLAGS $defs -c sjpeg_b200/csrc/kernels.cu -o build/ab/$name.kernels.o
     $NVCC $FLAGS $defs -c sjpeg_b200/csrc/engine.cu -o build/ab/$name.engine.o
     (cd sjpeg_b200/csrc && $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../../build/ab/$name.so \
-        ../../build/ab/$name.kernels.o sharp.o ../../build/ab/$name.engine.o host_codec.o host_stager.o sjpeg_api.o -lcudart -lpthread)
+        ../../build/ab/$name.kernels.o sharp.o ../../build/ab/$name.engine.o host_codec.o host_stager.o sjpeg_api.o -lcudart -lpthread -ldl)
     rm -f build/ab/$name.kernels.o build/ab/$name.engine.o
     echo "built build/ab/$name.so ($defs)"
   done
