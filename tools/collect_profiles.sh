@@ -1,24 +1,31 @@
-# Collects the round's measurement artefacts on the GPU box into gpurun_out/ (run under gpurun):
-#   bench line (N=1) and reference arm, per-config table, single-call latencies, sharp/riskiness times,
-#   ncu launch list of the bench command, ncu --set full captures of the main kernels.
+# Collects the round's measurement artefacts on the GPU box into gpurun_out/r02/ (run under gpurun,
+# one GPU).  Summaries are made from them HERE afterwards (tools/ncu_summary.py) and copied to profiles/.
 set -x
-mkdir -p gpurun_out
-python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench_n1.err
-python tools/configs.py > gpurun_out/configs.txt 2>&1
-python tools/latency.py > gpurun_out/latency.txt 2>&1
-python tools/sharp_bench.py > gpurun_out/sharp.txt 2>&1
-python tools/sharp_bench.py 1920 1080 >> gpurun_out/sharp.txt 2>&1
-python tools/bench_config5.py --reps 3 > gpurun_out/config5_n1.txt 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 400 --csv --log-file gpurun_out/launches_bench.csv \
-    python bench.py --steps 2 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'f1_fast|entropy_pack|stuff_kernel' -s 30 -c 3 \
-    -o gpurun_out/pipeline_full -f python tools/run_f1.py 8 3 full > gpurun_out/pipeline_full.log 2>&1
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,smsp__issue_active.avg.pct_of_peak_sustained_active \
-    --clock-control none -k regex:'f1_fast|entropy_pack|stuff_kernel' -s 30 -c 3 --csv --log-file gpurun_out/pipeline_light.csv \
-    python tools/run_f1.py 8 3 full > gpurun_out/pipeline_light.log 2>&1
-ncu --set full --clock-control none --cache-control none --import-source on -k regex:'entropy_pack|stuff_kernel' -s 20 -c 2 \
-    -o gpurun_out/entropy_warm -f python tools/run_f1.py 4 3 full > gpurun_out/entropy_warm.log 2>&1
-ncu --set full --clock-control none -k regex:'sharp_|riskiness' -c 5 -o gpurun_out/sharp_full -f \
-    python tools/sharp_bench.py 1920 1080 > gpurun_out/sharp_full.log 2>&1
-ls -la gpurun_out
+O=gpurun_out/r02
+mkdir -p $O
+python bench.py > $O/bench_n1.json 2> $O/bench_n1.err
+python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference_n1.json 2>> $O/bench_n1.err
+python tools/latency.py > $O/latency.txt 2>&1
+python tools/batch_methods.py B 16 > $O/batch_methods.txt 2>&1
+python tools/batch_methods.py A 16 >> $O/batch_methods.txt 2>&1
+python tools/planar_bench.py > $O/planar.txt 2>&1
+python tools/sharp_bench.py > $O/sharp.txt 2>&1
+# launch list of the bench command (headline part)
+ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 300 --csv --log-file $O/launches_bench.csv \
+    python bench.py --quick --steps 2 --warmup 3 > $O/bench_under_ncu.log 2>&1
+# --set full captures: F1 4:2:0 / 4:4:4 / planar, E + S (gen B and gen A), H1 + Q1 + S1 (m4), T1 (8K gen A m7)
+ncu --set full --clock-control none --import-source on -k regex:'f1_fast' -s 20 -c 1 -o $O/f1_420_full -f \
+    python tools/run_f1.py 16 3 f1 > $O/f1_420.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'f1_fast' -s 20 -c 1 -o $O/f1_444_full -f \
+    python tools/run_f1.py 16 3 f1 3840 2160 3 0 B > $O/f1_444.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'entropy_pack|stuff_kernel' -s 8 -c 2 -o $O/es_genB_full -f \
+    python tools/run_f1.py 16 3 full > $O/es_genB.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'entropy_pack|stuff_kernel' -s 8 -c 2 -o $O/es_genA_full -f \
+    python tools/run_f1.py 16 3 full 3840 2160 1 0 A > $O/es_genA.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'histogram_kernel|requantize|symbol_stats' -s 3 -c 3 -o $O/m4_full -f \
+    python tools/run_f1.py 16 2 full 3840 2160 1 4 B > $O/m4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'trellis' -s 3 -c 3 -o $O/trellis_full -f \
+    python tools/one_encode.py A 7680 4320 75 7 1 2 > $O/trellis.log 2>&1
+ncu --set full --clock-control none -k regex:'f1_planar' -s 4 -c 1 -o $O/f1_planar_full -f \
+    python tools/planar_bench.py > $O/f1_planar.log 2>&1
+ls -la $O
