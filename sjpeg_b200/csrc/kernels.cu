@@ -1314,6 +1314,7 @@ stuff_kernel(GroupBuffers gb, const __grid_constant__ StuffArgs args) {
   __shared__ uint32_t scratch[33];
   __shared__ unsigned long long tile_prefix;
   __shared__ unsigned long long claimed;
+  __shared__ __align__(16) uint8_t obuf[2 * kStuffTileBytes + 32];   // a tile's output: at most every byte stuffed, + EOI
   const int frame = blockIdx.y;
   uint32_t* stream = gb.words + frame * gb.words_pitch;
   unsigned long long* state = gb.ff_state + frame * gb.ff_state_pitch;
@@ -1397,22 +1398,53 @@ stuff_kernel(GroupBuffers gb, const __grid_constant__ StuffArgs args) {
     const unsigned long long t_next = claimed;
     StuffPiece nxt;
     if (t_next < tiles) first_half(t_next, nxt);     // uniform branch: the scan's barriers are safe
-    // second half: scatter with the 0x00 inserted
+    // second half: the tile's output bytes (0x00 inserted, EOI appended) are put together in shared
+    // memory and leave as aligned 16-byte stores.  (Written straight to global memory one byte at a
+    // time -- 17 to 33 scattered single-byte stores per thread -- the scatter was the whole cost of
+    // this kernel on busy pictures: 121 us per 16 gen-A 4K pictures, 25 % issue-slot use, warps
+    // waiting on the store path.)
+    const unsigned long long tile_lo = max(t * static_cast<unsigned long long>(kStuffTileBytes), b0);
+    const unsigned long long tile_hi = min((t + 1) * static_cast<unsigned long long>(kStuffTileBytes), b1);
+    uint32_t n_out = (tile_hi > tile_lo) ? static_cast<uint32_t>(tile_hi - tile_lo) + cur.total : 0u;
     if (cur.hi > cur.lo) {
       const unsigned long long byte0 = t * kStuffTileBytes + threadIdx.x * 16ull;
-      uint8_t* dst = out + (byte0 + cur.lo - b0) + prefix + cur.ex;
+      uint8_t* o = obuf + static_cast<uint32_t>(byte0 + cur.lo - tile_lo) + cur.ex;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         if (i >= cur.lo && i < cur.hi) {
           const uint32_t b = stream_byte(cur.w, i);
-          *dst++ = static_cast<uint8_t>(b);
-          if (b == 0xffu) *dst++ = 0;
+          *o++ = static_cast<uint8_t>(b);
+          if (b == 0xffu) *o++ = 0;
         }
       }
       if (last && byte0 + cur.hi == b1) {   // EOI (headers.cc:262-268)
-        dst[0] = 0xff;
-        dst[1] = 0xd9;
+        o[0] = 0xff;
+        o[1] = 0xd9;
       }
+    }
+    if (last && tile_hi == b1 && tile_hi > tile_lo) n_out += 2;
+    __syncthreads();
+    if (n_out != 0) {
+      uint8_t* dst = out + (tile_lo - b0) + prefix;
+      const uint32_t head = min(n_out, static_cast<uint32_t>((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u));
+      if (threadIdx.x < head) dst[threadIdx.x] = obuf[threadIdx.x];
+      const uint32_t body = (n_out - head) >> 4;          // aligned 16-byte pieces
+      const uint32_t* ow = reinterpret_cast<const uint32_t*>(obuf);
+      const uint32_t wsh = head >> 2, bsh = head & 3u;    // obuf is word aligned: uniform funnel shift
+      for (uint32_t k = threadIdx.x; k < body; k += kStuffThreads) {
+        const uint32_t* q = ow + wsh + 4 * k;
+        uint4 v;
+        if (bsh == 0) {
+          v = make_uint4(q[0], q[1], q[2], q[3]);
+        } else {
+          const uint32_t sel = 0x3210u + 0x1111u * bsh;   // bytes bsh..bsh+3 of the pair {lo, hi}
+          v = make_uint4(__byte_perm(q[0], q[1], sel), __byte_perm(q[1], q[2], sel), __byte_perm(q[2], q[3], sel),
+                         __byte_perm(q[3], q[4], sel));
+        }
+        *reinterpret_cast<uint4*>(dst + head + 16 * k) = v;
+      }
+      const uint32_t done = head + 16 * body;
+      if (threadIdx.x < n_out - done) dst[done + threadIdx.x] = obuf[done + threadIdx.x];
     }
     if (last && b1 <= b0 && t == 0 && threadIdx.x == 0) {   // a last stripe without a byte of its own: EOI only
       out[0] = 0xff;
