@@ -513,6 +513,13 @@ SJB_HD uint32_t trellis_block(const int16_t* in, const uint8_t* qm, const int32_
 // Result: quantised block in zig-zag order in Mem::out (two per word); returns the chunk bitmap.
 // ---------------------------------------------------------------------------------------------
 SJB_HD int sjb_half(uint32_t w, int hi) { return hi ? ((int32_t)w >> 16) : ((int32_t)(w << 16) >> 16); }
+SJB_HD uint32_t sjb_clz32(uint32_t m) {     // leading zeros, m != 0
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__clz((int)m);
+#else
+  return (uint32_t)__builtin_clz(m);
+#endif
+}
 SJB_HD int find_last_set64(uint64_t m) {   // index of highest set bit, m != 0
 #if defined(__CUDA_ARCH__)
   return 63 - __clzll((long long)m);
@@ -585,48 +592,85 @@ SJB_HD uint32_t trellis_block_v2(const uint32_t (&raw)[32], Mem& M, const Tab& T
     // both scores, both code lengths) are issued before the current one is evaluated, which takes
     // the shared-memory latency off the dependent chain of compares (few warps are resident, so
     // that chain is what bounds the kernel).  A load past the end re-reads the sink: harmless.
-    uint64_t m = (kept0 | kept1) & ((1ull << i) - 1ull);
-    int pp = find_last_set64(m);
-    m ^= 1ull << pp;
+    // The position masks are walked as two 32-bit halves, and the evaluation of a node is written
+    // without branches (selects on the two early-out / improvement conditions): on the device the
+    // loop body is straight-line code for the 32 blocks of a warp.
+    const uint32_t below_hi = (i > 32) ? ((1u << (i - 32)) - 1u) : 0u;
+    const uint32_t below_lo = (i >= 32) ? 0xffffffffu : ((1u << i) - 1u);
+    uint32_t mh = (static_cast<uint32_t>(kept0 >> 32) | static_cast<uint32_t>(kept1 >> 32)) & below_hi;
+    uint32_t ml = (static_cast<uint32_t>(kept0) | static_cast<uint32_t>(kept1)) & below_lo;
+    // next predecessor position (and whether its candidates 0 / 1 exist); (mh | ml) != 0 on entry
+    int pp;
+    uint32_t hbits;                        // bit 0: candidate 0 kept, bit 1: candidate 1 kept
+    {
+      const bool in_hi = mh != 0;
+      const uint32_t mm = in_hi ? mh : ml;
+      const int bpos = 31 - (int)sjb_clz32(mm);
+      if (in_hi) mh ^= 1u << bpos; else ml ^= 1u << bpos;
+      pp = bpos + (in_hi ? 32 : 0);
+      const uint32_t c0 = in_hi ? static_cast<uint32_t>(kept0 >> 32) : static_cast<uint32_t>(kept0);
+      const uint32_t c1 = in_hi ? static_cast<uint32_t>(kept1 >> 32) : static_cast<uint32_t>(kept1);
+      hbits = ((c0 >> bpos) & 1u) | (((c1 >> bpos) & 1u) << 1);
+    }
     uint32_t d0 = M.disto_ld(pp), s0, s1;
     M.score_ld(pp, s0, s1);
     uint32_t lenA = T.len((((i - 1 - pp) & 15) << 4) | nbA), lenB = T.len((((i - 1 - pp) & 15) << 4) | nbB);
     bool more = true;
     while (more && (actA || actB)) {
-      more = m != 0;
-      const int np = more ? find_last_set64(m) : 0;
-      m &= ~(1ull << np);
+      more = (mh | ml) != 0;
+      int np = 0;
+      uint32_t nhbits = 0;
+      {
+        const bool in_hi = mh != 0;
+        const uint32_t mm = in_hi ? mh : ml;
+        const int bpos = more ? 31 - (int)sjb_clz32(mm) : 0;
+        const uint32_t bit = more ? (1u << bpos) : 0u;
+        if (in_hi) mh ^= bit; else ml ^= bit;
+        np = bpos + (in_hi ? 32 : 0);
+        const uint32_t c0 = in_hi ? static_cast<uint32_t>(kept0 >> 32) : static_cast<uint32_t>(kept0);
+        const uint32_t c1 = in_hi ? static_cast<uint32_t>(kept1 >> 32) : static_cast<uint32_t>(kept1);
+        nhbits = ((c0 >> bpos) & 1u) | (((c1 >> bpos) & 1u) << 1);
+      }
       const uint32_t nd0 = M.disto_ld(np);
       uint32_t ns0, ns1;
       M.score_ld(np, ns0, ns1);
       const uint32_t nlenA = T.len((((i - 1 - np) & 15) << 4) | nbA), nlenB = T.len((((i - 1 - np) & 15) << 4) | nbB);
-      const bool h1 = (kept1 >> pp) & 1, h0 = (kept0 >> pp) & 1;
+      const bool h0 = (hbits & 1u) != 0, h1 = (hbits & 2u) != 0;
       const uint32_t zr = (uint32_t)((i - 1 - pp) >> 4) * zrl_len;
-      if (actA) {
+      {
+        // candidate A against node (pp, 1), then (pp, 0): quantize.cc:357-382 for two consecutive nodes
         const uint32_t thr = baseA - d0 + lambda * ((uint32_t)nbA + zr);
         const uint32_t full = thr + lambda * lenA;
-        if (h1) {
-          if (thr >= bestA) actA = false;
-          else { const uint32_t sc = full + s1; if (sc < bestA) { bestA = sc; bpA = 2 * pp + 1; } }
-        }
-        if (h0 && actA) {
-          if (thr >= bestA) actA = false;
-          else { const uint32_t sc = full + s0; if (sc < bestA) { bestA = sc; bpA = 2 * pp; } }
-        }
+        const bool stop1 = actA && h1 && thr >= bestA;
+        const uint32_t sc1 = full + s1;
+        const bool take1 = actA && h1 && !stop1 && sc1 < bestA;
+        bestA = take1 ? sc1 : bestA;
+        bpA = take1 ? 2 * pp + 1 : bpA;
+        actA = actA && !stop1;
+        const bool stop0 = actA && h0 && thr >= bestA;
+        const uint32_t sc0 = full + s0;
+        const bool take0 = actA && h0 && !stop0 && sc0 < bestA;
+        bestA = take0 ? sc0 : bestA;
+        bpA = take0 ? 2 * pp : bpA;
+        actA = actA && !stop0;
       }
-      if (actB) {
+      {
         const uint32_t thr = baseB - d0 + lambda * ((uint32_t)nbB + zr);
         const uint32_t full = thr + lambda * lenB;
-        if (h1) {
-          if (thr >= bestB) actB = false;
-          else { const uint32_t sc = full + s1; if (sc < bestB) { bestB = sc; bpB = 2 * pp + 1; } }
-        }
-        if (h0 && actB) {
-          if (thr >= bestB) actB = false;
-          else { const uint32_t sc = full + s0; if (sc < bestB) { bestB = sc; bpB = 2 * pp; } }
-        }
+        const bool stop1 = actB && h1 && thr >= bestB;
+        const uint32_t sc1 = full + s1;
+        const bool take1 = actB && h1 && !stop1 && sc1 < bestB;
+        bestB = take1 ? sc1 : bestB;
+        bpB = take1 ? 2 * pp + 1 : bpB;
+        actB = actB && !stop1;
+        const bool stop0 = actB && h0 && thr >= bestB;
+        const uint32_t sc0 = full + s0;
+        const bool take0 = actB && h0 && !stop0 && sc0 < bestB;
+        bestB = take0 ? sc0 : bestB;
+        bpB = take0 ? 2 * pp : bpB;
+        actB = actB && !stop0;
       }
-      pp = np; d0 = nd0; s0 = ns0; s1 = ns1; lenA = nlenA; lenB = nlenB;
+      pp = np; hbits = nhbits; d0 = nd0; s0 = ns0; s1 = ns1; lenA = nlenA; lenB = nlenB;
     }
     if (bpA >= 0) {                                          // a candidate without predecessor is dropped
       M.score_st(i, 0, bestA);
