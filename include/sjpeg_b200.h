@@ -158,11 +158,24 @@ int sjb_fetch_output(sjb_context* ctx, uint8_t* out, int out_on_device, size_t o
  * Batch of independent pictures with identical geometry and settings (config 5 of BASELINE.json:
  * frames are the unit of sharding).  pix[i] / out[i] as above; sizes[i] receives each size.
  * Pictures are processed in groups (one kernel launch covers a whole group) and the groups are
- * overlapped on the context's streams.
+ * overlapped on the context's streams; for methods >= 1 the host phases (matrices from the
+ * histograms, optimal Huffman tables) of one group run while younger groups are already queued.
+ * params->yuv_mode may also be SJB_YUV_AUTO (packed RGB: the analyser runs on every picture, the
+ * batch is split by the mode each one gets) or SJB_YUV_SHARP (conversions of several pictures run
+ * concurrently, then the planar pipeline) -- the batched form of SjpegCompress().
  */
 int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix_on_device, int width,
                      int height, long long stride, const sjb_params* params, uint8_t* const* out,
                      int out_on_device, size_t out_capacity, size_t* sizes);
+
+/* Batch of planar / semi-planar pictures of one geometry (layouts as sjb_encode_planar; the strides and
+ * uv_step are common to the batch): y[i] / u[i] / v[i] are the planes of picture i (u, v may be NULL for
+ * SJB_YUV_400).  Same pipeline, group sizes and overlap as sjb_encode_batch -- the hand-off for decoded
+ * video frames (NV12) that are already in device memory (on_device = 1). */
+int sjb_encode_planar_batch(sjb_context* ctx, int n, const uint8_t* const* y, long long y_stride, const uint8_t* const* u,
+                            long long u_stride, const uint8_t* const* v, long long v_stride, int uv_step, int on_device,
+                            int width, int height, const sjb_params* params, uint8_t* const* out, int out_on_device,
+                            size_t out_capacity, size_t* sizes);
 
 /*
  * Row stripes: a picture split into horizontal stripes of whole MCU rows, one stripe per GPU
@@ -218,6 +231,11 @@ int sjb_stripe_rows(int height, int yuv_mode, int world, int rank, int* y0, int*
 int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix_on_device, int width, int height,
                        long long stride, const sjb_params* params, uint8_t* const* out, size_t out_capacity,
                        size_t* sizes);
+/* Frames sharded across the ranks: collects on rank 0 the JPEGs every rank left in DEVICE memory
+ * (sjb_encode_batch with out_on_device = 1) -- rank order, back to back in blob (host memory), their
+ * sizes in out_sizes[0 .. *n_total).  Collective; blob / out_sizes / n_total are used on rank 0 only. */
+int sjb_gather_frames(sjb_comm* comm, int n_local, const uint8_t* const* dev_jpegs, const size_t* sizes_local,
+                      uint8_t* blob, size_t blob_capacity, size_t* out_sizes, int out_sizes_capacity, int* n_total);
 /* Host-only merge used by rank 0 (exported for tests): header + the bytes each stripe emitted, in
  * order, OR-merging the byte neighbouring stripes share and stuffing it (bit_writer.h:172-196).
  * flags[r] = head_byte | tail_byte << 8 | tail_bits << 16 | head_open << 24: the stripe's share of

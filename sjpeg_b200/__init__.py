@@ -60,6 +60,12 @@ _SIGNATURES = {
     "sjb_encode_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,
                                    C.c_longlong, C.POINTER(Params), C.POINTER(C.c_void_p), C.c_int,
                                    C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sjb_encode_planar_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_longlong, C.POINTER(C.c_void_p),
+                                          C.c_longlong, C.POINTER(C.c_void_p), C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p), C.c_int, C.c_size_t,
+                                          C.POINTER(C.c_size_t)]),
+    "sjb_gather_frames": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t,
+                                    C.POINTER(C.c_size_t), C.c_int, C.POINTER(C.c_int)]),
     "sjb_host_alloc": (C.c_void_p, [C.c_size_t]),
     "sjb_host_alloc_wc": (C.c_void_p, [C.c_size_t]),
     "sjb_host_free": (None, [C.c_void_p]),
@@ -207,6 +213,20 @@ class Context:
         rc = lib().sjb_encode_batch(self._ctx, n, a, int(on_device), width, height, stride, C.byref(params),
                                     o, int(out_on_device), cap, sizes)
         _check(self._ctx, rc, "sjb_encode_batch")
+        return list(sizes)
+
+    def encode_planar_batch(self, ys, y_stride, us, u_stride, vs, v_stride, uv_step, on_device, width, height, params,
+                            out_ptrs, out_on_device, cap):
+        """ys / us / vs: lists of plane addresses (us, vs may be None for 4:0:0)"""
+        n = len(ys)
+        ya = (C.c_void_p * n)(*ys)
+        ua = (C.c_void_p * n)(*us) if us is not None else None
+        va = (C.c_void_p * n)(*vs) if vs is not None else None
+        o = (C.c_void_p * n)(*out_ptrs)
+        sizes = (C.c_size_t * n)()
+        rc = lib().sjb_encode_planar_batch(self._ctx, n, ya, y_stride, ua, u_stride, va, v_stride, uv_step, int(on_device),
+                                           width, height, C.byref(params), o, int(out_on_device), cap, sizes)
+        _check(self._ctx, rc, "sjb_encode_planar_batch")
         return list(sizes)
 
     # -- stage-level --------------------------------------------------------------------------

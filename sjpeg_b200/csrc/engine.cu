@@ -139,6 +139,11 @@ struct sjb_context {
   sjb_search* search = nullptr;   // armed by sjb_context_set_search for the next single encode
   // whole-picture passes in front of the block pipeline (sharp.cu)
   DeviceBuffer sharp_scratch, sharp_planes, sharp_tabs, risk_table, risk_sums;
+  // batches in AUTO / SHARP mode: every picture resident, planes of the SHARP subset, one scratch + stream per
+  // concurrent conversion
+  DeviceBuffer batch_pix, batch_planes, sharp_scratch_n[4];
+  cudaStream_t sharp_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t risk_host_cap = 0;                  // unsigned long longs in risk_host
   unsigned long long* risk_host = nullptr;   // pinned, 3 sums
   int risk_table_version = 0;                // version of the process-wide table held in risk_table
   // where sjb_bench_device left each picture of its last round: {lane, slot, turn}; a picture can be
@@ -954,9 +959,12 @@ void sjb_context_destroy(sjb_context* ctx) {
   if (ctx == nullptr) return;
   cudaSetDevice(ctx->device);
   for (auto& L : ctx->lanes) DestroyLane(&L);
-  for (DeviceBuffer* b : {&ctx->sharp_scratch, &ctx->sharp_planes, &ctx->sharp_tabs, &ctx->risk_table, &ctx->risk_sums}) {
+  for (DeviceBuffer* b : {&ctx->sharp_scratch, &ctx->sharp_planes, &ctx->sharp_tabs, &ctx->risk_table, &ctx->risk_sums,
+                          &ctx->batch_pix, &ctx->batch_planes, &ctx->sharp_scratch_n[0], &ctx->sharp_scratch_n[1],
+                          &ctx->sharp_scratch_n[2], &ctx->sharp_scratch_n[3]}) {
     b->Release();
   }
+  for (auto& st : ctx->sharp_stream) if (st) cudaStreamDestroy(st);
   if (ctx->risk_host) cudaFreeHost(ctx->risk_host);
   if (ctx->head_copy) cudaFreeHost(ctx->head_copy);
   delete ctx;
@@ -1047,42 +1055,45 @@ int sjb_fetch_output(sjb_context* ctx, uint8_t* out, int out_on_device, size_t o
   return SJB_OK;
 } SJB_NOTHROW_END
 
-int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix_on_device, int width,
-                     int height, long long stride, const sjb_params* params, uint8_t* const* out,
-                     int out_on_device, size_t out_capacity, size_t* sizes) try {
-  if (ctx == nullptr || pix == nullptr || out == nullptr || sizes == nullptr || n < 0) return SJB_ERR_ARG;
-  ctx->err.clear();
-  ctx->lanes[0].last_size = 0;
-  Plan plan;
-  RC(MakePlan(width, height, stride, params, &plan));
-  for (int i = 0; i < n; ++i) if (pix[i] == nullptr) return SJB_ERR_ARG;
-  if (n == 0) return SJB_OK;
-  CU(cudaSetDevice(ctx->device));
-  const ManyUploads back_to_back(ctx, n > 1);
-  // Pictures that come from host memory arrive at PCIe speed (one 4K picture per 0.47 ms), far
-  // slower than the kernels consume them: small groups start computing as soon as their pictures
-  // have landed and leave a short tail after the last copy.  Device-resident batches use the
-  // large groups that suit the kernels.
-  static const int host_group = [] {
+}  // extern "C"
+
+namespace {
+
+// Pictures that come from host memory arrive at PCIe speed (one 4K picture per 0.47 ms), far
+// slower than the kernels consume them: small groups start computing as soon as their pictures
+// have landed and leave a short tail after the last copy.  Device-resident batches use the
+// large groups that suit the kernels.
+int HostBatchGroup() {
+  static const int v = [] {
     const char* e = getenv("SJB_HOST_BATCH_GROUP");
-    const int v = e ? atoi(e) : 2;
-    return v > 0 ? v : 2;
+    const int x = e ? atoi(e) : 2;
+    return x > 0 ? x : 2;
   }();
-  const int B = std::max(1, std::min(pix_on_device ? plan.group : std::min(plan.group, host_group), n));
+  return v;
+}
+
+// The batch pipeline over the context's lanes, independent of where the pictures come from:
+// fill(k, L, &fs) makes the pictures [k * B, k * B + fs.frames) of the batch available on lane L
+// (device pointers and strides into fs; uploads go on L's stream).  Picture j of the batch is
+// delivered to out[index ? index[j] : j] / sizes[...].
+//
+// Software pipeline: group k runs on lane k % nl.  At step k the lane is first freed (the group
+// that used it is finished and drained: sizes read, bytes copied out), group k is started on it
+// (upload + first kernels enqueued), and then every older group still in flight is advanced by
+// one host phase, oldest first -- so the waits for histograms / symbol counts of one group happen
+// while the uploads and kernels of the younger ones are already queued.
+template <class Fill>
+int RunBatch(sjb_context* ctx, const Plan& plan, long long stride, int n, int B, Fill fill, const int* index,
+             uint8_t* const* out, int out_on_device, size_t out_capacity, size_t* sizes) {
   const int groups = (n + B - 1) / B;
   const int nl = std::min<int>(kMaxLanes, std::max(1, groups));
   for (int l = 0; l < nl; ++l) {
     RC(InitLane(ctx, &ctx->lanes[l]));
     RC(ReserveLane(ctx, &ctx->lanes[l], plan, B));
-    if (!pix_on_device) RC(ReservePix(ctx, &ctx->lanes[l], plan, stride, B));
   }
-  // Software pipeline over the lanes: group k runs on lane k % nl.  At step k the lane is first
-  // freed (the group that used it is finished and drained: sizes read, bytes copied out), group k is
-  // started on it (upload + first kernels enqueued), and then every older group still in flight is
-  // advanced by one host phase, oldest first -- so the waits for histograms / symbol counts of one
-  // group happen while the uploads and kernels of the younger ones are already queued.
   std::vector<GroupJob> jobs(nl);
-  for (int i = 0; i < n; ++i) sizes[i] = 0;
+  auto where = [&](int j) { return index ? index[j] : j; };
+  for (int j = 0; j < n; ++j) sizes[where(j)] = 0;
   auto drain = [&](int k) -> int {
     Lane* L = &ctx->lanes[k % nl];
     GroupJob* J = &jobs[k % nl];
@@ -1090,7 +1101,7 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
     CU(cudaStreamSynchronize(L->stream));
     int rc = SJB_OK;
     for (int f = 0; f < B && k * B + f < n; ++f) {
-      const int i = k * B + f;
+      const int i = where(k * B + f);
       const size_t size = static_cast<size_t>(L->host->info[f].out_size);
       sizes[i] = size;
       if (out[i] == nullptr || size > out_capacity) {
@@ -1123,15 +1134,7 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
     FrameSet fs;
     FillFrameSet(plan, stride, &fs);
     fs.frames = std::min(B, n - k * B);
-    int rc = SJB_OK;
-    for (int f = 0; f < fs.frames && rc == SJB_OK; ++f) {
-      fs.pix[f] = pix[k * B + f];
-      if (!pix_on_device) {
-        long long ds = stride;
-        rc = UploadPicture(ctx, L, pix[k * B + f], plan, stride, f, &fs.pix[f], &ds);
-        fs.stride = ds;
-      }
-    }
+    int rc = fill(k, L, &fs);
     if (rc == SJB_OK) rc = StartGroup(ctx, &jobs[k % nl], L, fs, plan, false);
     for (int j = std::max(0, k - nl + 1); j < k && rc == SJB_OK; ++j) rc = AdvanceGroup(ctx, &jobs[j % nl]);
     if (rc != SJB_OK) return abort_batch(rc);
@@ -1148,6 +1151,267 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
     }
   }
   return first_err;
+}
+
+int EnsureSharpTabs(sjb_context* ctx, const uint32_t** g2l, const uint32_t** l2g);
+int EnsureScoreTable(sjb_context* ctx);
+
+// SJB_YUV_AUTO / SJB_YUV_SHARP for a batch of packed RGB pictures (what SjpegCompress and a default
+// EncoderParam ask for, api.cc:83-101, encoders.cc:546-568).  All pictures are made resident first;
+// AUTO runs the riskiness analyser on every picture (one launch each, one wait for all the sums) and
+// the batch is then split by the mode each picture got: the 4:2:0 / 4:4:4 / 4:0:0 subsets go through
+// the ordinary batch pipeline from their device copies, the SHARP subset is converted -- up to
+// kSharpStreams pictures at a time, each conversion on its own stream with its own scratch, because a
+// single conversion only occupies a fifth of the SMs -- into planes that then go through the planar
+// 4:2:0 pipeline.
+enum { kSharpStreams = 4 };
+int EncodeBatchAutoOrSharp(sjb_context* ctx, int n, const uint8_t* const* pix, int pix_on_device, int width, int height,
+                           long long stride, const sjb_params* params, uint8_t* const* out, int out_on_device,
+                           size_t out_capacity, size_t* sizes) {
+  if (params->pix_fmt != SJB_PIX_RGB) return SJB_ERR_ARG;   // api.cc:208,235: callers convert to RGB first
+  if (width > 65535 || height > 65535) return SJB_ERR_ARG;
+  sjb_params p420 = *params;
+  p420.yuv_mode = SJB_YUV_420;
+  Plan plan;
+  RC(MakePlan(width, height, stride, &p420, &plan));
+  RC(InitLane(ctx, &ctx->lanes[0]));
+  Lane* L0 = &ctx->lanes[0];
+  // 1. every picture resident on the device
+  std::vector<const uint8_t*> d_pix(n);
+  long long d_stride = stride;
+  if (pix_on_device) {
+    for (int i = 0; i < n; ++i) d_pix[i] = pix[i];
+  } else {
+    const size_t slot = PixSlotBytes(plan, stride);
+    CU(ctx->batch_pix.Reserve(slot * n));
+    Lane view;                                   // UploadPicture reads pix / pix_pitch / stream only
+    view.pix = ctx->batch_pix;
+    view.pix_pitch = slot;
+    view.stream = L0->stream;
+    int rc = SJB_OK;
+    for (int i = 0; i < n && rc == SJB_OK; ++i) rc = UploadPicture(ctx, &view, pix[i], plan, stride, i, &d_pix[i], &d_stride);
+    view.pix = DeviceBuffer();                   // not ours to release
+    view.stream = nullptr;
+    RC(rc);
+  }
+  // 2. the mode of every picture
+  std::vector<int> mode(n, params->yuv_mode);
+  if (params->yuv_mode == SJB_YUV_AUTO) {
+    RC(EnsureScoreTable(ctx));
+    CU(ctx->risk_sums.Reserve(static_cast<size_t>(n) * 3 * sizeof(unsigned long long)));
+    if (ctx->risk_host_cap < static_cast<size_t>(n) * 3) {
+      if (ctx->risk_host) cudaFreeHost(ctx->risk_host);
+      ctx->risk_host = nullptr;
+      ctx->risk_host_cap = 0;
+      CU(cudaMallocHost(reinterpret_cast<void**>(&ctx->risk_host), static_cast<size_t>(n) * 3 * sizeof(unsigned long long)));
+      ctx->risk_host_cap = static_cast<size_t>(n) * 3;
+    }
+    unsigned long long* d_sums = ctx->risk_sums.as<unsigned long long>();
+    for (int i = 0; i < n; ++i) {
+      CU(LaunchRiskiness(d_pix[i], d_stride, width, height, ctx->risk_table.as<uint8_t>(), d_sums + 3 * i, ctx->sm_count, L0->stream));
+    }
+    CU(cudaMemcpyAsync(ctx->risk_host, d_sums, static_cast<size_t>(n) * 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                       L0->stream));
+    CU(cudaStreamSynchronize(L0->stream));
+    for (int i = 0; i < n; ++i) {
+      float risk;
+      mode[i] = RiskinessDecision(ctx->risk_host[3 * i], ctx->risk_host[3 * i + 1], ctx->risk_host[3 * i + 2], width, height, &risk);
+    }
+  } else {
+    CU(cudaStreamSynchronize(L0->stream));     // the uploads: the lanes below read the pictures from their own streams
+  }
+  // 3. the block-pipeline modes, one sub-batch each
+  int result = SJB_OK;
+  for (int m : {SJB_YUV_420, SJB_YUV_444, SJB_YUV_400}) {
+    std::vector<int> idx;
+    for (int i = 0; i < n; ++i) if (mode[i] == m) idx.push_back(i);
+    if (idx.empty()) continue;
+    sjb_params pm = *params;
+    pm.yuv_mode = m;
+    Plan pl;
+    RC(MakePlan(width, height, d_stride, &pm, &pl));
+    const int cnt = static_cast<int>(idx.size());
+    const int B = std::max(1, std::min(pl.group, cnt));
+    auto fill = [&](int k, Lane*, FrameSet* fs) -> int {
+      fs->stride = d_stride;
+      for (int f = 0; f < fs->frames; ++f) fs->pix[f] = d_pix[idx[k * B + f]];
+      return SJB_OK;
+    };
+    const int rc = RunBatch(ctx, pl, d_stride, cnt, B, fill, idx.data(), out, out_on_device, out_capacity, sizes);
+    if (rc != SJB_OK && rc != SJB_ERR_CAPACITY) return rc;
+    if (rc != SJB_OK) result = rc;
+  }
+  // 4. the SHARP subset: conversions on kSharpStreams streams, then the planar 4:2:0 pipeline
+  std::vector<int> idx;
+  for (int i = 0; i < n; ++i) if (mode[i] == SJB_YUV_SHARP) idx.push_back(i);
+  if (!idx.empty()) {
+    const int cnt = static_cast<int>(idx.size());
+    const uint32_t *g2l, *l2g;
+    RC(EnsureSharpTabs(ctx, &g2l, &l2g));
+    // planes with 16-byte aligned pitches, so that the planar fast kernel takes them
+    const size_t ypitch = (static_cast<size_t>(width) + 15) & ~size_t(15);
+    const size_t cw = (static_cast<size_t>(width) + 1) / 2, ch = (static_cast<size_t>(height) + 1) / 2;
+    const bool tight = ypitch == static_cast<size_t>(width) && (cw & 15) == 0;   // the conversion writes tightly packed planes
+    const size_t ybytes = (static_cast<size_t>(width) * height + 255) & ~size_t(255), cbytes = (cw * ch + 255) & ~size_t(255);
+    const size_t per = ybytes + 2 * cbytes;
+    (void)tight;
+    CU(ctx->batch_planes.Reserve(per * cnt));
+    SharpLayout lay;
+    const size_t scratch = (width > 4 && height > 4) ? SharpScratchBytes(width, height, &lay) : 0;
+    const int ns = std::min<int>(kSharpStreams, cnt);
+    for (int s = 0; s < ns; ++s) {
+      if (ctx->sharp_stream[s] == nullptr) CU(cudaStreamCreateWithFlags(&ctx->sharp_stream[s], cudaStreamNonBlocking));
+      if (scratch) CU(ctx->sharp_scratch_n[s].Reserve(scratch));
+    }
+    for (int j = 0; j < cnt; ++j) {
+      uint8_t* y = ctx->batch_planes.as<uint8_t>() + per * j;
+      int launches = 0;
+      CU(LaunchSharpYuv(d_pix[idx[j]], d_stride, width, height, ctx->sharp_scratch_n[j % ns].as<uint8_t>(), g2l, l2g, y, y + ybytes,
+                        y + ybytes + cbytes, ctx->sharp_stream[j % ns], &launches));
+    }
+    for (int s = 0; s < ns; ++s) CU(cudaStreamSynchronize(ctx->sharp_stream[s]));
+    sjb_params pm = *params;
+    pm.yuv_mode = SJB_YUV_420;
+    Plan pl;
+    RC(MakePlan(width, height, 3LL * width, &pm, &pl));
+    const int B = std::max(1, std::min(pl.group, cnt));
+    auto fill = [&](int k, Lane*, FrameSet* fs) -> int {
+      fs->planar = 1;
+      fs->uv_step = 1;
+      fs->stride = width;
+      fs->stride_u = fs->stride_v = static_cast<long long>(cw);
+      for (int f = 0; f < fs->frames; ++f) {
+        const uint8_t* y = ctx->batch_planes.as<uint8_t>() + per * (k * B + f);
+        fs->pix[f] = y;
+        fs->pix_u[f] = y + ybytes;
+        fs->pix_v[f] = y + ybytes + cbytes;
+      }
+      return SJB_OK;
+    };
+    const int rc = RunBatch(ctx, pl, width, cnt, B, fill, idx.data(), out, out_on_device, out_capacity, sizes);
+    if (rc != SJB_OK && rc != SJB_ERR_CAPACITY) return rc;
+    if (rc != SJB_OK) result = rc;
+  }
+  return result;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix_on_device, int width,
+                     int height, long long stride, const sjb_params* params, uint8_t* const* out,
+                     int out_on_device, size_t out_capacity, size_t* sizes) try {
+  if (ctx == nullptr || pix == nullptr || out == nullptr || sizes == nullptr || n < 0 || params == nullptr) return SJB_ERR_ARG;
+  ctx->err.clear();
+  ctx->lanes[0].last_size = 0;
+  for (int i = 0; i < n; ++i) if (pix[i] == nullptr) return SJB_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  const ManyUploads back_to_back(ctx, n > 1);
+  if (params->yuv_mode == SJB_YUV_AUTO || params->yuv_mode == SJB_YUV_SHARP) {
+    if (n == 0) return SJB_OK;
+    return EncodeBatchAutoOrSharp(ctx, n, pix, pix_on_device, width, height, stride, params, out, out_on_device,
+                                  out_capacity, sizes);
+  }
+  Plan plan;
+  RC(MakePlan(width, height, stride, params, &plan));
+  if (n == 0) return SJB_OK;
+  const int B = std::max(1, std::min(pix_on_device ? plan.group : std::min(plan.group, HostBatchGroup()), n));
+  if (!pix_on_device) {
+    const int groups = (n + B - 1) / B;
+    for (int l = 0; l < std::min<int>(kMaxLanes, groups); ++l) {
+      RC(InitLane(ctx, &ctx->lanes[l]));
+      RC(ReservePix(ctx, &ctx->lanes[l], plan, stride, B));
+    }
+  }
+  auto fill = [&](int k, Lane* L, FrameSet* fs) -> int {
+    for (int f = 0; f < fs->frames; ++f) {
+      fs->pix[f] = pix[k * B + f];
+      if (!pix_on_device) {
+        long long ds = stride;
+        RC(UploadPicture(ctx, L, pix[k * B + f], plan, stride, f, &fs->pix[f], &ds));
+        fs->stride = ds;
+      }
+    }
+    return SJB_OK;
+  };
+  return RunBatch(ctx, plan, stride, n, B, fill, nullptr, out, out_on_device, out_capacity, sizes);
+} SJB_NOTHROW_END
+
+// A batch of planar / semi-planar pictures of one geometry (sjb_encode_planar for the layouts):
+// y[i] / u[i] / v[i] are the planes of picture i, strides common to the batch.
+int sjb_encode_planar_batch(sjb_context* ctx, int n, const uint8_t* const* y, long long y_stride, const uint8_t* const* u,
+                            long long u_stride, const uint8_t* const* v, long long v_stride, int uv_step, int on_device,
+                            int width, int height, const sjb_params* params, uint8_t* const* out, int out_on_device,
+                            size_t out_capacity, size_t* sizes) try {
+  if (ctx == nullptr || y == nullptr || out == nullptr || sizes == nullptr || params == nullptr || n < 0) return SJB_ERR_ARG;
+  ctx->err.clear();
+  ctx->lanes[0].last_size = 0;
+  const int mode = params->yuv_mode;
+  if (mode != SJB_YUV_420 && mode != SJB_YUV_444 && mode != SJB_YUV_400) return SJB_ERR_ARG;
+  if (width <= 0 || height <= 0) return SJB_ERR_ARG;
+  if (uv_step != 1 && !(uv_step == 2 && mode == SJB_YUV_420)) return SJB_ERR_ARG;
+  const int cw = (mode == SJB_YUV_420) ? (width + 1) / 2 : width, ch = (mode == SJB_YUV_420) ? (height + 1) / 2 : height;
+  auto absll = [](long long a) { return a < 0 ? -a : a; };
+  if (absll(y_stride) < width) return SJB_ERR_ARG;
+  if (mode != SJB_YUV_400) {
+    if (u == nullptr || v == nullptr) return SJB_ERR_ARG;
+    if (absll(u_stride) < static_cast<long long>(uv_step) * cw || absll(v_stride) < static_cast<long long>(uv_step) * cw)
+      return SJB_ERR_ARG;
+  }
+  for (int i = 0; i < n; ++i) {
+    if (y[i] == nullptr || (mode != SJB_YUV_400 && (u[i] == nullptr || v[i] == nullptr))) return SJB_ERR_ARG;
+  }
+  sjb_params p = *params;
+  p.pix_fmt = SJB_PIX_RGB;
+  Plan plan;
+  RC(MakePlan(width, height, 3LL * width, &p, &plan));
+  if (n == 0) return SJB_OK;
+  CU(cudaSetDevice(ctx->device));
+  const int B = std::max(1, std::min(on_device ? plan.group : std::min(plan.group, HostBatchGroup()), n));
+  const size_t ypitch = (static_cast<size_t>(width) + 15) & ~size_t(15);
+  const size_t crow = static_cast<size_t>(mode == SJB_YUV_420 ? uv_step : 1) * cw;
+  const size_t cpitch = (crow + 15) & ~size_t(15);
+  const size_t ybytes = ypitch * height, cbytes = (mode == SJB_YUV_400) ? 0 : cpitch * ch;
+  const size_t slot = (ybytes + 2 * cbytes + 255) & ~size_t(255);
+  if (!on_device) {
+    const int groups = (n + B - 1) / B;
+    for (int l = 0; l < std::min<int>(kMaxLanes, groups); ++l) {
+      RC(InitLane(ctx, &ctx->lanes[l]));
+      CU(ctx->lanes[l].pix.Reserve(slot * B));
+    }
+  }
+  auto fill = [&](int k, Lane* L, FrameSet* fs) -> int {
+    fs->planar = 1;
+    fs->uv_step = (mode == SJB_YUV_420) ? uv_step : 1;
+    fs->stride = y_stride;
+    fs->stride_u = u_stride;
+    fs->stride_v = v_stride;
+    for (int f = 0; f < fs->frames; ++f) {
+      const int i = k * B + f;
+      fs->pix[f] = y[i];
+      fs->pix_u[f] = (mode == SJB_YUV_400) ? nullptr : u[i];
+      fs->pix_v[f] = (mode == SJB_YUV_400) ? nullptr : v[i];
+      if (on_device) continue;
+      uint8_t* base = L->pix.as<uint8_t>() + slot * f;
+      RC(UploadPlane(ctx, L, base, y[i], y_stride, width, height, &fs->pix[f], &fs->stride));
+      if (mode == SJB_YUV_400) continue;
+      if (uv_step == 2) {
+        const uint8_t* first = (u[i] < v[i]) ? u[i] : v[i];
+        const uint8_t* d0;
+        long long ds;
+        RC(UploadPlane(ctx, L, base + ybytes, first, u_stride, crow, ch, &d0, &ds));
+        fs->pix_u[f] = d0 + (u[i] - first);
+        fs->pix_v[f] = d0 + (v[i] - first);
+        fs->stride_u = fs->stride_v = ds;
+      } else {
+        RC(UploadPlane(ctx, L, base + ybytes, u[i], u_stride, crow, ch, &fs->pix_u[f], &fs->stride_u));
+        RC(UploadPlane(ctx, L, base + ybytes + cbytes, v[i], v_stride, crow, ch, &fs->pix_v[f], &fs->stride_v));
+      }
+    }
+    return SJB_OK;
+  };
+  return RunBatch(ctx, plan, y_stride, n, B, fill, nullptr, out, out_on_device, out_capacity, sizes);
 } SJB_NOTHROW_END
 
 }  // extern "C"
@@ -1328,6 +1592,7 @@ int EnsureScoreTable(sjb_context* ctx) {
   }
   if (ctx->risk_host == nullptr) {
     CU(cudaMallocHost(reinterpret_cast<void**>(&ctx->risk_host), 3 * sizeof(unsigned long long)));
+    ctx->risk_host_cap = 3;
     CU(ctx->risk_sums.Reserve(256));
   }
   return SJB_OK;

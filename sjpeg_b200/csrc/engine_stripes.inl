@@ -576,5 +576,98 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
   return result;
 } SJB_NOTHROW_END
 
+// Frames sharded across the ranks (each rank encodes its own pictures; SURVEY.md 8e "frames"): the
+// finished JPEGs, left in DEVICE memory by sjb_encode_batch(out_on_device = 1), are collected on
+// rank 0 -- an all-gather of the counts, one of the sizes, then one grouped ncclSend/ncclRecv of the
+// exact bytes.  Rank 0 gets them in rank order, back to back in `blob` (host memory), their sizes in
+// out_sizes[0 .. *n_total).
+int sjb_gather_frames(sjb_comm* comm, int n_local, const uint8_t* const* dev_jpegs, const size_t* sizes_local,
+                      uint8_t* blob, size_t blob_capacity, size_t* out_sizes, int out_sizes_capacity, int* n_total) try {
+  if (comm == nullptr || n_local < 0 || (n_local > 0 && (dev_jpegs == nullptr || sizes_local == nullptr))) return SJB_ERR_ARG;
+  sjb_context* ctx = comm->ctx;
+  ctx->err.clear();
+  const NcclApi* api = Nccl();
+  if (api == nullptr) return SJB_ERR_CUDA;
+  const int rank = comm->rank, world = comm->world;
+  if (rank == 0 && (out_sizes == nullptr || n_total == nullptr)) return SJB_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = comm->stream;
+  // counts
+  CU(comm->bits_local.Reserve(8));
+  CU(comm->bits_all.Reserve(8 * static_cast<size_t>(world)));
+  if (comm->h_meta_cap < 8 * static_cast<size_t>(world)) {
+    if (comm->h_meta) cudaFreeHost(comm->h_meta);
+    comm->h_meta = nullptr;
+    comm->h_meta_cap = 0;
+    CU(cudaMallocHost(reinterpret_cast<void**>(&comm->h_meta), 4096));
+    comm->h_meta_cap = 4096;
+  }
+  comm->h_meta[0] = static_cast<unsigned long long>(n_local);
+  LaunchCopySmall(comm->bits_local.ptr, comm->h_meta, 8, st);
+  NC(api->AllGather(comm->bits_local.ptr, comm->bits_all.ptr, 1, ncclUint64, comm->nccl, st));
+  std::vector<unsigned long long> counts(world);
+  CU(cudaMemcpyAsync(counts.data(), comm->bits_all.ptr, 8 * static_cast<size_t>(world), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  size_t maxn = 1, total_n = 0;
+  for (int r = 0; r < world; ++r) {
+    maxn = std::max<size_t>(maxn, counts[r]);
+    total_n += counts[r];
+  }
+  // sizes, padded to the largest count
+  CU(comm->meta_local.Reserve(8 * maxn));
+  CU(comm->meta_all.Reserve(8 * maxn * world));
+  std::vector<unsigned long long> mine(maxn, 0), all(maxn * world);
+  size_t my_bytes = 0;
+  for (int i = 0; i < n_local; ++i) {
+    mine[i] = sizes_local[i];
+    my_bytes += sizes_local[i];
+  }
+  CU(cudaMemcpyAsync(comm->meta_local.ptr, mine.data(), 8 * maxn, cudaMemcpyHostToDevice, st));
+  NC(api->AllGather(comm->meta_local.ptr, comm->meta_all.ptr, maxn, ncclUint64, comm->nccl, st));
+  CU(cudaMemcpyAsync(all.data(), comm->meta_all.ptr, 8 * maxn * world, cudaMemcpyDeviceToHost, st));
+  // this rank's JPEGs back to back
+  CU(comm->send.Reserve(std::max<size_t>(my_bytes, 1)));
+  size_t off = 0;
+  for (int i = 0; i < n_local; ++i) {
+    if (dev_jpegs[i] == nullptr) return SJB_ERR_ARG;
+    CU(cudaMemcpyAsync(comm->send.as<uint8_t>() + off, dev_jpegs[i], sizes_local[i], cudaMemcpyDeviceToDevice, st));
+    off += sizes_local[i];
+  }
+  CU(cudaStreamSynchronize(st));
+  std::vector<size_t> rank_bytes(world, 0), rank_base(world, 0);
+  for (int r = 0; r < world; ++r) for (size_t i = 0; i < counts[r]; ++i) rank_bytes[r] += static_cast<size_t>(all[r * maxn + i]);
+  for (int r = 1; r < world; ++r) rank_base[r] = rank_base[r - 1] + rank_bytes[r - 1];
+  const size_t total = rank_base[world - 1] + rank_bytes[world - 1];
+  if (rank == 0) CU(comm->recv.Reserve(std::max<size_t>(total, 1)));
+  if (world > 1) {
+    NC(api->GroupStart());
+    if (rank != 0 && rank_bytes[rank] > 0) NC(api->Send(comm->send.ptr, rank_bytes[rank], ncclUint8, 0, comm->nccl, st));
+    if (rank == 0) {
+      for (int r = 1; r < world; ++r) {
+        if (rank_bytes[r] > 0) NC(api->Recv(comm->recv.as<uint8_t>() + rank_base[r], rank_bytes[r], ncclUint8, r, comm->nccl, st));
+      }
+    }
+    NC(api->GroupEnd());
+  }
+  if (rank != 0) {
+    CU(cudaStreamSynchronize(st));
+    return SJB_OK;
+  }
+  *n_total = static_cast<int>(total_n);
+  int rc = SJB_OK;
+  if (static_cast<size_t>(out_sizes_capacity) < total_n || blob == nullptr || blob_capacity < total) rc = SJB_ERR_CAPACITY;
+  if (rc == SJB_OK) {
+    size_t k = 0;
+    for (int r = 0; r < world; ++r) for (size_t i = 0; i < counts[r]; ++i) out_sizes[k++] = static_cast<size_t>(all[r * maxn + i]);
+    if (rank_bytes[0] > 0) CU(cudaMemcpyAsync(blob, comm->send.ptr, rank_bytes[0], cudaMemcpyDeviceToHost, st));
+    if (total > rank_bytes[0]) {
+      CU(cudaMemcpyAsync(blob + rank_bytes[0], comm->recv.as<uint8_t>() + rank_bytes[0], total - rank_bytes[0],
+                         cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CU(cudaStreamSynchronize(st));
+  return rc;
+} SJB_NOTHROW_END
+
 }  // extern "C"
 #undef NC

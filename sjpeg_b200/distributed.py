@@ -319,6 +319,31 @@ class NcclStripeEncoder:
             return None
         return [outs[i][:sizes[i]].tobytes() for i in range(n)]
 
+    def gather_frames(self, dev_ptrs, sizes, blob_capacity):
+        """Frame sharding: every rank passes the device addresses and sizes of the JPEGs it encoded
+        (sjb_encode_batch with out_on_device); returns the list of all JPEG byte strings in rank
+        order on rank 0, None elsewhere."""
+        n = len(dev_ptrs)
+        a = (C.c_void_p * max(n, 1))(*dev_ptrs)
+        sz = (C.c_size_t * max(n, 1))(*sizes)
+        if self.rank == 0:
+            blob = np.empty(blob_capacity, np.uint8)
+            cap = 1 << 16
+            out_sizes = (C.c_size_t * cap)()
+            total = C.c_int(0)
+            rc = lib().sjb_gather_frames(self._comm, n, a, sz, blob.ctypes.data, blob.nbytes, out_sizes, cap, C.byref(total))
+        else:
+            rc = lib().sjb_gather_frames(self._comm, n, a, sz, None, 0, None, 0, None)
+        if rc != OK:
+            raise SjpegB200Error("sjb_gather_frames rc=%d %s" % (rc, lib().sjb_last_error(self.ctx._ctx)))
+        if self.rank != 0:
+            return None
+        out, pos = [], 0
+        for i in range(total.value):
+            out.append(blob[pos:pos + out_sizes[i]].tobytes())
+            pos += out_sizes[i]
+        return out
+
     def close(self):
         if self._comm:
             lib().sjb_comm_destroy(self._comm)

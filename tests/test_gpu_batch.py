@@ -209,3 +209,85 @@ def test_sharp_4k_uses_planar_fast_path(gpu_ctx):
     rgb = O.make_rgb("A", w, h, 99)
     got = gpu_ctx.encode(rgb, w, h, 3 * w, S.default_params(75, 4, S.YUV_SHARP))
     assert got == O.oracle_encode(rgb, w, h, 3 * w, 75.0, 4, O.YUV_SHARP)
+
+
+def test_batch_auto_and_sharp_modes(gpu_ctx):
+    """sjb_encode_batch with SJB_YUV_AUTO (the batched SjpegCompress: riskiness per picture, then one
+    sub-batch per mode) and SJB_YUV_SHARP (several conversions in flight, then the planar pipeline):
+    a batch whose pictures land in all four modes, host and device-resident input."""
+    import torch
+    import sjpeg_b200 as S
+    table = S.default_score_table() if O.score_table() is None else O.score_table()
+    if table is None:
+        pytest.skip("no riskiness score table available")
+    S.set_score_table(table)
+    try:
+        w, h = 352, 208
+        rng = np.random.RandomState(4)
+        sat = np.zeros((h, w, 3), np.uint8)
+        sat[:, ::2, 0] = 255
+        sat[::2, :, 2] = 255
+        gray = np.repeat(rng.randint(0, 256, (h, w, 1)), 3, axis=2).astype(np.uint8)
+        base = [O.make_rgb("A", w, h, 3), O.make_rgb("B", w, h, 4), sat, gray, rng.randint(0, 256, (h, w, 3)).astype(np.uint8),
+                (rng.randint(0, 2, (h, w, 3)) * 255).astype(np.uint8)]
+        frames = [base[i % len(base)] if i < 2 * len(base) else O.make_rgb("A", w, h, 100 + i) for i in range(21)]
+        modes = [O.oracle_riskiness(f, w, h, 3 * w, table)[0] for f in frames]
+        assert len(set(modes)) >= 3, modes            # the batch really is split
+        for method in (4, 0):
+            p = S.default_params(80, method, S.YUV_AUTO)
+            want = [O.oracle_encode(f, w, h, 3 * w, 80.0, method, m) for f, m in zip(frames, modes)]
+            assert _encode_batch_host(gpu_ctx, frames, w, h, p, 1 << 20) == want, ("auto host", method)
+            assert _encode_batch_device(gpu_ctx, frames, w, h, p, 1 << 20) == want, ("auto device", method)
+            p = S.default_params(80, method, S.YUV_SHARP)
+            want = [O.oracle_encode(f, w, h, 3 * w, 80.0, method, O.YUV_SHARP) for f in frames[:9]]
+            assert _encode_batch_host(gpu_ctx, frames[:9], w, h, p, 1 << 20) == want, ("sharp host", method)
+        # sharp at a size the aligned planar fast path takes (width % 32 == 0), more pictures than streams
+        w, h = 640, 368
+        frames = [O.make_rgb("A", w, h, 7 + i) for i in range(6)]
+        p = S.default_params(75, 4, S.YUV_SHARP)
+        want = [O.oracle_encode(f, w, h, 3 * w, 75.0, 4, O.YUV_SHARP) for f in frames]
+        assert _encode_batch_device(gpu_ctx, frames, w, h, p, 1 << 20) == want
+    finally:
+        S.set_score_table(S.default_score_table())
+
+
+@pytest.mark.parametrize("kind", [O.KIND_YUV420, O.KIND_NV12, O.KIND_NV21, O.KIND_YUV444, O.KIND_GRAY])
+def test_planar_batch(gpu_ctx, kind):
+    """sjb_encode_planar_batch: planar / semi-planar pictures in groups (host planes with arbitrary strides,
+    and device-resident aligned planes as a video decoder leaves them), methods 0 and 4"""
+    import torch
+    import sjpeg_b200 as S
+    for (w, h, n) in ((640, 368, 19), (203, 117, 5)):
+        sets = [O.make_planes(kind, w, h, seed=50 + i, pad=(5, 3, 7) if w == 203 else (0, 0, 0)) for i in range(n)]
+        args = [O.planar_args(kind, pl) for pl in sets]
+        for method in (0, 4):
+            p = S.default_params(75, method, O.KIND_MODE[kind])
+            want = [O.oracle_encode_planar(kind, pl, w, h, 75, method) for pl in sets]
+            outs = [np.empty(1 << 20, np.uint8) for _ in range(n)]
+            ys = [a[0] for a in args]
+            us = [a[2] for a in args] if kind != O.KIND_GRAY else None
+            vs = [a[4] for a in args] if kind != O.KIND_GRAY else None
+            sizes = gpu_ctx.encode_planar_batch(ys, args[0][1], us, args[0][3], vs, args[0][5], args[0][6], False, w, h, p,
+                                                [o.ctypes.data for o in outs], False, 1 << 20)
+            got = [outs[i][:sizes[i]].tobytes() for i in range(n)]
+            assert got == want, (kind, w, h, method, "host")
+            if w % 32 == 0:      # device-resident planes
+                dev = []
+                for pl in sets:
+                    dev.append({k: (torch.from_numpy(v).cuda() if v is not None else None) for k, v in pl.items()})
+                torch.cuda.synchronize()
+                ys = [d["y"].data_ptr() for d in dev]
+                if kind == O.KIND_GRAY:
+                    us = vs = None
+                elif kind in (O.KIND_NV12, O.KIND_NV21):
+                    us = [d["u"].data_ptr() + (0 if kind == O.KIND_NV12 else 1) for d in dev]
+                    vs = [d["u"].data_ptr() + (1 if kind == O.KIND_NV12 else 0) for d in dev]
+                else:
+                    us = [d["u"].data_ptr() for d in dev]
+                    vs = [d["v"].data_ptr() for d in dev]
+                douts = [torch.zeros(1 << 20, dtype=torch.uint8, device="cuda") for _ in range(n)]
+                sizes = gpu_ctx.encode_planar_batch(ys, args[0][1], us, args[0][3], vs, args[0][5], args[0][6], True, w, h, p,
+                                                    [t.data_ptr() for t in douts], True, 1 << 20)
+                torch.cuda.synchronize()
+                got = [douts[i][:sizes[i]].cpu().numpy().tobytes() for i in range(n)]
+                assert got == want, (kind, w, h, method, "device")

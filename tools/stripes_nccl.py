@@ -49,6 +49,19 @@ if rank == 0:
     print(json.dumps({"check": "stripes over NCCL vs oracle, methods 0/1/3/4/7 x 5 geometries x 11 pictures", "n_gpus": world,
                       "mismatches": bad}), flush=True)
 
+# ---- frames sharded across the ranks, gathered on rank 0 inside the library ----
+frames = [O.make_rgb("A" if i % 2 else "B", 320, 200, 300 + i) for i in range(13)]
+a, b = D.shard_frames(len(frames), world)[rank]
+p = S.default_params(75, 4, S.YUV_420)
+dev = [torch.from_numpy(f.reshape(-1)).cuda() for f in frames[a:b]]
+douts = [torch.zeros(1 << 18, dtype=torch.uint8, device="cuda") for _ in dev]
+torch.cuda.synchronize()
+sizes = ctx.encode_batch([t.data_ptr() for t in dev], True, 320, 200, 960, p, [t.data_ptr() for t in douts], True, 1 << 18) if dev else []
+got = enc.gather_frames([t.data_ptr() for t in douts], sizes, 8 << 20)
+if rank == 0:
+    ok = got == [O.oracle_encode(f, 320, 200, 960, 75.0, 4, O.YUV_420) for f in frames]
+    print(json.dumps({"check": "frames sharded over ranks + sjb_gather_frames (NCCL) vs oracle", "n_gpus": world, "ok": ok}), flush=True)
+
 # ---- config 5 ----
 W, H, N = 1920, 1080, 64
 gold = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_md5.json")))["config5"]
