@@ -276,21 +276,32 @@ SJB_HD void code_block_mapped(const Loader& load, uint32_t nz_lo, uint32_t nz_hi
   }
   const uint32_t zrl = ac_codes[0xf0];
   int prev = 0;                            // zig-zag position of the previous non-zero (0 = DC slot)
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int half = 0; half < 2; ++half) {
-    uint32_t m = half ? nz_hi : nz_lo;
-    if (m == 0) continue;
+  // ONE loop over both halves of the map (positions 1..31, then 32..63): its trip count is the
+  // block's number of non-zeros, so a warp whose blocks carry similar numbers stays converged even
+  // when they split differently between the halves (two loops, one per half, ran max + max).
+  uint32_t m = nz_lo, rest = nz_hi;
+  int base = 0;
+  if (m == 0) {
+    m = rest;
+    rest = 0;
+    base = 32;
+  }
+  if (m) {
     // software pipeline: the value of the NEXT non-zero is requested before this one is coded
-    int next_pos = 32 * half + find_first_set32(m);
+    int next_pos = base + find_first_set32(m);
     int next_v = load.value(next_pos);
-    while (m) {
+    for (;;) {
       const int pos = next_pos;
       const int v = next_v;
       m &= m - 1;
-      if (m) {
-        next_pos = 32 * half + find_first_set32(m);
+      if (m == 0) {                        // first half exhausted: go on with the second (if any)
+        m = rest;
+        rest = 0;
+        base = 32;
+      }
+      const bool more = m != 0;
+      if (more) {
+        next_pos = base + find_first_set32(m);
         next_v = load.value(next_pos);
       }
       int run = pos - prev - 1;
@@ -304,6 +315,7 @@ SJB_HD void code_block_mapped(const Loader& load, uint32_t nz_lo, uint32_t nz_hi
       size_and_bits(v, &n, &bits);
       const uint32_t c = ac_codes[(run << 4) | n];
       sink.put(((c >> 16) << n) | bits, (int)(c & 0xff) + n);
+      if (!more) break;
     }
   }
   if (prev < 63) {                         // EOB, entropy.cc:195-197

@@ -831,6 +831,25 @@ struct PrefetchedChunkLoader {
   }
 };
 
+// The same opaque-address loads without the eager fetch (busy tiles: every chunk is visited anyway)
+struct AddrChunkLoader {
+  unsigned long long addr;
+  __device__ __forceinline__ explicit AddrChunkLoader(const int16_t* p) {
+    addr = static_cast<unsigned long long>(__cvta_generic_to_global(p));
+    asm volatile("" : "+l"(addr));
+  }
+  __device__ __forceinline__ Words4 operator()(int c) const {
+    Words4 r;
+    asm("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "l"(addr + 16ull * coef_chunk_index(c)));
+    return r;
+  }
+  __device__ __forceinline__ int value(int pos) const {
+    short v;
+    asm("ld.global.s16 %0, [%1];" : "=h"(v) : "l"(addr + 2ull * coef_pos_offset(pos)));
+    return v;
+  }
+};
+
 __device__ __forceinline__ void load_code_tables(const CodeTabs* tabs, CodeTabs* sh) {
   // 2176 bytes = 136 x 16 bytes: one vector copy per thread
   static_assert(sizeof(CodeTabs) % 16 == 0, "CodeTabs must be a multiple of 16 bytes");
@@ -930,24 +949,29 @@ struct StreamOut {
 #endif
 enum { kLocalWords = SJB_LOCAL_WORDS };   // 32-bit words per block kept (512 bits); longer blocks are re-walked
 struct LocalSink {
-  uint32_t* w;                        // slot of kLocalWords words
-  uint64_t acc;
-  int n, nw;
+  uint32_t* w;                        // slot of kLocalWords words (+ the word behind them, rewritten by the caller afterwards)
+  uint32_t hi, lo;                    // pending bits, top aligned in hi:lo
+  int n, nw;                          // pending bit count (< 32 between calls), words emitted
   uint32_t total;
-  __device__ __forceinline__ void put(uint32_t bits, int len) {
+  // 32-bit formulation (a 64-bit accumulator shifted by a variable amount cost 19 instructions per
+  // symbol): the symbol is first aligned to the top of a word, then spread over hi:lo by n
+  __device__ __forceinline__ void put(uint32_t bits, int len) {     // 1 <= len <= 27
     total += static_cast<uint32_t>(len);
-    acc |= static_cast<uint64_t>(bits) << (64 - n - len);
+    const uint32_t top = bits << (32 - len);
+    hi |= top >> n;
+    lo |= __funnelshift_r(0u, top, n);          // top << (32 - n); 0 for n == 0
     n += len;
     if (n >= 32) {
-      if (nw < kLocalWords) w[nw] = static_cast<uint32_t>(acc >> 32);
+      w[min(nw, static_cast<int>(kLocalWords))] = hi;   // words past the slot land on the spare word
       ++nw;
-      acc <<= 32;
+      hi = lo;
+      lo = 0;
       n -= 32;
     }
   }
   __device__ __forceinline__ void finish() {
     if (n > 0) {
-      if (nw < kLocalWords) w[nw] = static_cast<uint32_t>(acc >> 32);
+      w[min(nw, static_cast<int>(kLocalWords))] = hi;
       ++nw;
     }
   }
@@ -964,7 +988,10 @@ struct LocalSink {
 #ifndef SJB_E_PREFETCH
 #define SJB_E_PREFETCH 1
 #endif
-enum { kEWorkers = kTileBlocks, kEThreads = kTileBlocks + 32, kECtasPerSm = (kTileBlocks >= 512) ? 3 : (kTileBlocks >= 256) ? 5 : 10 };
+#ifndef SJB_E_CTAS_PER_SM
+#define SJB_E_CTAS_PER_SM ((kTileBlocks >= 512) ? 3 : (kTileBlocks >= 256) ? 5 : 10)
+#endif
+enum { kEWorkers = kTileBlocks, kEThreads = kTileBlocks + 32, kECtasPerSm = SJB_E_CTAS_PER_SM };
 enum { kBarWorkers = 1, kBarFull = 2 /* +buffer */, kBarReady = 4 /* +buffer */ };
 enum { kBusyTileBits = 32 * kTileBlocks };   // above 32 bits per block on average a tile counts as busy
 // barrier ids are immediates (a register id makes ptxas reserve all 16 hardware barriers per CTA,
@@ -1076,27 +1103,69 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
     const unsigned long long claimed = atomicAdd(counter, 1ull);
     return (claimed < static_cast<unsigned long long>(ntiles)) ? static_cast<long long>(claimed) : -1;
   };
+  // copies tile `tile`, walked into buffer pb, to the stream at its now known bit offset
+  auto copy_out = [&](long long tile, int pb) {
+    bar_sync(kBarReady + pb, kEThreads);
+    const size_t g = static_cast<size_t>(tile) * kTileBlocks + threadIdx.x;
+    if (g >= nb_blocks) return;
+    const uint32_t* mine = local[pb][threadIdx.x];
+    const uint32_t packed = mine[kLocalWords];
+    const uint32_t bits = packed >> 20;
+    const unsigned long long offset = tile_prefix[pb] + (packed & 0xfffffu);
+    const int nw = static_cast<int>((bits + 31) >> 5);
+    if (nw <= kLocalWords) {
+      // shifted copy; the first and the last stream word may be shared with the neighbouring
+      // blocks (OR), the others are owned
+      const int s = static_cast<int>(offset & 31);
+      uint32_t* dst = stream + (offset >> 5);
+      const int last = static_cast<int>((s + bits - 1) >> 5);   // index of the last stream word touched
+      uint32_t prev = 0;
+      for (int kk = 0; kk <= last; ++kk) {
+        const uint32_t cur = (kk < nw) ? mine[kk] : 0u;
+        const uint32_t v = __funnelshift_r(cur, prev, s);     // (prev << (32-s)) | (cur >> s)
+        prev = cur;
+        if (kk == 0 || kk == last) { if (v) atomicOr(&dst[kk], v); }
+        else dst[kk] = v;
+      }
+    } else {
+      // more than 512 bits: walk the block again, straight into the stream
+      const int k = block_in_mcu(g, fs.mcu_blocks);
+      const int c = (k >= fs.luma_blocks) ? 1 : 0;
+      const int16_t* blk = zz + coef_block_base(g);
+      StreamOut out = {stream};
+      BitPackSink<StreamOut> sink(out, offset);
+      code_block(ChunkLoader{blk}, nzmask[g], blk[0], dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, dc_init),
+                 sh.dc[c], sh.ac[c], sink);
+      sink.finish();
+    }
+  };
+  // bit counts of buffer pb (word kLocalWords of every slot) -> exclusive offsets inside the tile
+  auto scan_tile = [&](int pb) -> uint32_t {
+    uint32_t* mine = local[pb][threadIdx.x];
+    const uint32_t bits = mine[kLocalWords];
+    uint32_t total;
+    const uint32_t ex = workers_exclusive_scan(bits, scratch, &total);
+    mine[kLocalWords] = ex | (bits << 20);        // ex < 256 * 1696 < 2^20, bits < 2^11
+    if (threadIdx.x == 0) tile_total[pb] = total;
+    return total;
+  };
   if (threadIdx.x == 0) next_id[1] = claim_tile();
   bar_sync(kBarWorkers, kEWorkers);
   long long t = next_id[1];
   long long t_prev = -1;
   uint32_t prev_total = 0;
-  for (int i = 0;; ++i) {
+  for (int i = 0;;) {
     const int b = i & 1;
-    if (threadIdx.x == 0) tile_id[b] = t;           // for the look-back warp, published by the Full barrier
-    long long t_next = -1;
-    // Busy tiles are walked luma blocks first (below); sparse ones keep thread i on block i, which
-    // needs neither the index arithmetic nor the two extra barriers.  The previous tile's bit count
-    // decides (neighbouring tiles look alike); it is the same in every worker.
-    const bool regroup = prev_total > kBusyTileBits;
-    // slot j of this buffer is about to be refilled by whichever thread walks block j, which is not
-    // the thread that has just copied tile i-2 out of it: everybody must be done with that copy
-    if (regroup && i >= 2) bar_sync(kBarWorkers, kEWorkers);
-    if (t >= 0) {
-      const uint32_t first = static_cast<uint32_t>(t) * kTileBlocks;
-      const uint32_t count = min(static_cast<uint32_t>(kTileBlocks), static_cast<uint32_t>(nb_blocks) - first);
-      if (!regroup) {
-        // sparse tile: thread i walks block i
+    // The previous tile's bit count decides how this one is walked (neighbouring tiles look alike);
+    // it is the same in every worker.
+    if (t < 0 || prev_total <= kBusyTileBits) {
+      // ---- sparse tile (or the end): thread i walks block i; the copy-out of the previous tile is
+      // deferred behind this tile's walk, while the look-back warp resolves its prefix ----
+      if (threadIdx.x == 0) tile_id[b] = t;           // for the look-back warp, published by the Full barrier
+      long long t_next = -1;
+      if (t >= 0) {
+        const uint32_t first = static_cast<uint32_t>(t) * kTileBlocks;
+        const uint32_t count = min(static_cast<uint32_t>(kTileBlocks), static_cast<uint32_t>(nb_blocks) - first);
         if (threadIdx.x >= count) {
           local[b][threadIdx.x][kLocalWords] = 0;
         } else {
@@ -1109,124 +1178,101 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
           const PrefetchedChunkLoader loader(blk);
           const int pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, dc_init);
           const int dc = static_cast<int16_t>(loader.c0.x & 0xffffu);
-          LocalSink sink = {mine, 0, 0, 0, 0};
+          LocalSink sink = {mine, 0u, 0u, 0, 0, 0u};
           code_block(loader, mask, dc, pred, sh.dc[c], sh.ac[c], sink);
           sink.finish();
           mine[kLocalWords] = sink.total;
         }
-      } else {
-        // Busy tile: the trip count of a warp is the largest number of non-zeros among its 32
-        // blocks, and neighbouring blocks differ a lot (luma blocks carry several times the non-zeros
-        // of chroma blocks; lane efficiency was 14 of 32 on the 4K gen-A picture).  So every thread
-        // first builds the non-zero maps of ITS block (words 0, 1 of the block's slot), the blocks are
-        // counting-sorted by their number of non-zeros, and thread r walks the block of rank r,
-        // heaviest first.  Slots stay indexed by block; scan and copy-out keep the identity mapping.
-        if (threadIdx.x < 64) sort_hist[threadIdx.x] = 0;
-        bar_sync(kBarWorkers, kEWorkers);
-        uint32_t my_rank = 0, my_key = 0;
-        if (threadIdx.x < count) {
-          const size_t g = static_cast<size_t>(first) + threadIdx.x;
-          const ChunkLoader loader = {zz + coef_block_base(g)};
-          uint32_t lo, hi;
-          block_nz_maps(loader, nzmask[g], &lo, &hi);
-          local[b][threadIdx.x][0] = lo;
-          local[b][threadIdx.x][1] = hi;
-          my_key = static_cast<uint32_t>(__popc(lo) + __popc(hi));
-          my_rank = atomicAdd(&sort_hist[my_key], 1u);
-        } else {
-          local[b][threadIdx.x][kLocalWords] = 0;
-        }
-        bar_sync(kBarWorkers, kEWorkers);
-        if (threadIdx.x < 64) {
-          uint32_t base = 0;
-          for (int kk = 63; kk > static_cast<int>(threadIdx.x); --kk) base += sort_hist[kk];
-          sort_base[threadIdx.x] = base;
-        }
-        bar_sync(kBarWorkers, kEWorkers);
-        if (threadIdx.x < count) sort_order[sort_base[my_key] + my_rank] = static_cast<uint8_t>(threadIdx.x);
-        bar_sync(kBarWorkers, kEWorkers);
-        if (threadIdx.x < count) {
-          const uint32_t j = sort_order[threadIdx.x];
-          const size_t g = static_cast<size_t>(first) + j;
-          uint32_t* mine = local[b][j];
-          const uint32_t lo = mine[0], hi = mine[1];
-          const int k = block_in_mcu(g, fs.mcu_blocks);
-          const int c = (k >= fs.luma_blocks) ? 1 : 0;
-          const int16_t* blk = zz + coef_block_base(g);
-          const ChunkLoader loader = {blk};
-          const int pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, dc_init);
-          LocalSink sink = {mine, 0, 0, 0, 0};
-          code_block_mapped(loader, lo, hi, blk[0], pred, sh.dc[c], sh.ac[c], sink);
-          sink.finish();
-          mine[kLocalWords] = sink.total;
-        }
-      }
-      if (threadIdx.x == 0) next_id[b] = claim_tile();   // broadcast by the barriers below
-      if (regroup) bar_sync(kBarWorkers, kEWorkers);     // every slot of the tile is filled
-      uint32_t* mine = local[b][threadIdx.x];            // from here on: thread i <-> block i of the tile
-      const uint32_t bits = mine[kLocalWords];
-      uint32_t total;
-      const uint32_t ex = workers_exclusive_scan(bits, scratch, &total);
-      mine[kLocalWords] = ex | (bits << 20);        // ex < 256 * 1696 < 2^20, bits < 2^11
-      if (threadIdx.x == 0) tile_total[b] = total;
-      prev_total = total;
-      t_next = next_id[b];
+        if (threadIdx.x == 0) next_id[b] = claim_tile();   // broadcast by the barriers of the scan
+        prev_total = scan_tile(b);
+        t_next = next_id[b];
 #if SJB_E_PREFETCH
-      if (t_next >= 0) {
-        // the next tile's first sector and bitmap byte start their way to L1 now and arrive while
-        // this tile's prefix is resolved and the previous tile is written out
-        const size_t gn = static_cast<size_t>(t_next) * kTileBlocks + threadIdx.x;
-        if (gn < nb_blocks) {
-          // (four consecutive blocks share the line that holds their first sectors)
-          if ((threadIdx.x & 3) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(zz + coef_block_base(gn)));
-          if ((threadIdx.x & 31) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(nzmask + gn));
-        }
-      }
-#endif
-    }
-    __threadfence_block();
-    bar_arrive(kBarFull + b, kEThreads);            // t < 0 tells the look-back warp to stop
-    if (t_prev >= 0) {
-      // ---- copy tile i-1 to the stream at its now known bit offset ----
-      const int pb = b ^ 1;
-      bar_sync(kBarReady + pb, kEThreads);
-      const size_t g = static_cast<size_t>(t_prev) * kTileBlocks + threadIdx.x;
-      if (g < nb_blocks) {
-        const uint32_t* mine = local[pb][threadIdx.x];
-        const uint32_t packed = mine[kLocalWords];
-        const uint32_t bits = packed >> 20;
-        const unsigned long long offset = tile_prefix[pb] + (packed & 0xfffffu);
-        const int nw = static_cast<int>((bits + 31) >> 5);
-        if (nw <= kLocalWords) {
-          // shifted copy; the first and the last stream word may be shared with the neighbouring
-          // blocks (OR), the others are owned
-          const int s = static_cast<int>(offset & 31);
-          uint32_t* dst = stream + (offset >> 5);
-          const int last = static_cast<int>((s + bits - 1) >> 5);   // index of the last stream word touched
-          uint32_t prev = 0;
-          for (int kk = 0; kk <= last; ++kk) {
-            const uint32_t cur = (kk < nw) ? mine[kk] : 0u;
-            const uint32_t v = __funnelshift_r(cur, prev, s);     // (prev << (32-s)) | (cur >> s)
-            prev = cur;
-            if (kk == 0 || kk == last) { if (v) atomicOr(&dst[kk], v); }
-            else dst[kk] = v;
+        if (t_next >= 0) {
+          // the next tile's first sector and bitmap byte start their way to L1 now and arrive while
+          // this tile's prefix is resolved and the previous tile is written out
+          const size_t gn = static_cast<size_t>(t_next) * kTileBlocks + threadIdx.x;
+          if (gn < nb_blocks) {
+            // (four consecutive blocks share the line that holds their first sectors)
+            if ((threadIdx.x & 3) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(zz + coef_block_base(gn)));
+            if ((threadIdx.x & 31) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(nzmask + gn));
           }
-        } else {
-          // more than 512 bits: walk the block again, straight into the stream
-          const int k = block_in_mcu(g, fs.mcu_blocks);
-          const int c = (k >= fs.luma_blocks) ? 1 : 0;
-          const int16_t* blk = zz + coef_block_base(g);
-          StreamOut out = {stream};
-          BitPackSink<StreamOut> sink(out, offset);
-          code_block(ChunkLoader{blk}, nzmask[g], blk[0], dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, dc_init),
-                     sh.dc[c], sh.ac[c], sink);
-          sink.finish();
         }
+#endif
       }
+      __threadfence_block();
+      bar_arrive(kBarFull + b, kEThreads);            // t < 0 tells the look-back warp to stop
+      if (t_prev >= 0) copy_out(t_prev, b ^ 1);
+      if (t < 0) break;
+      t_prev = t;
+      t = t_next;
+      ++i;
+      continue;
     }
-    if (t < 0) break;
+    // ---- busy tile ----
+    // The trip count of a warp is the largest number of non-zeros among its 32 blocks, and blocks
+    // differ a lot (luma blocks carry several times the non-zeros of chroma blocks; lane efficiency
+    // was 14 of 32 on the 4K gen-A picture).  So every thread first builds the non-zero maps of ITS
+    // block (words 0, 1 of the block's slot), the blocks are counting-sorted by their number of
+    // non-zeros, and thread r walks the block of rank r, heaviest first.  Slots stay indexed by
+    // block; scan and copy-out keep the identity mapping.
+    // (Tried: two tiles sorted together, thread r walking rank r and then rank n-1-r so that all
+    // warps carry the same sum -- the barrier behind the walk is where a third of the stall samples
+    // sit.  The walk phase became balanced and the kernel no faster: the SM's other CTAs already use
+    // the issue slots a waiting warp leaves, and the pair cost the double buffering.)
+    if (threadIdx.x == 0) tile_id[b] = t;
+    if (threadIdx.x < 64) sort_hist[threadIdx.x] = 0;
+    // slot j of this buffer is about to be refilled by whichever thread walks block j, which is not
+    // the thread that copied tile i-2 out of it: everybody must be done with that copy
+    bar_sync(kBarWorkers, kEWorkers);
+    const uint32_t first = static_cast<uint32_t>(t) * kTileBlocks;
+    const uint32_t count = min(static_cast<uint32_t>(kTileBlocks), static_cast<uint32_t>(nb_blocks) - first);
+    uint32_t my_rank = 0, my_key = 0;
+    if (threadIdx.x < count) {
+      const size_t g = static_cast<size_t>(first) + threadIdx.x;
+      const AddrChunkLoader loader(zz + coef_block_base(g));
+      uint32_t lo, hi;
+      block_nz_maps(loader, nzmask[g], &lo, &hi);
+      local[b][threadIdx.x][0] = lo;
+      local[b][threadIdx.x][1] = hi;
+      my_key = static_cast<uint32_t>(__popc(lo) + __popc(hi));
+      my_rank = atomicAdd(&sort_hist[my_key], 1u);
+    } else {
+      local[b][threadIdx.x][kLocalWords] = 0;
+    }
+    bar_sync(kBarWorkers, kEWorkers);
+    if (threadIdx.x < 64) {
+      uint32_t base = 0;
+      for (int kk = 63; kk > static_cast<int>(threadIdx.x); --kk) base += sort_hist[kk];
+      sort_base[threadIdx.x] = base;
+    }
+    bar_sync(kBarWorkers, kEWorkers);
+    if (threadIdx.x < count) sort_order[sort_base[my_key] + my_rank] = static_cast<uint8_t>(threadIdx.x);
+    bar_sync(kBarWorkers, kEWorkers);
+    if (threadIdx.x < count) {
+      const uint32_t j = sort_order[threadIdx.x];
+      const size_t g = static_cast<size_t>(first) + j;
+      uint32_t* mine = local[b][j];
+      const uint32_t lo = mine[0], hi = mine[1];
+      const int k = block_in_mcu(g, fs.mcu_blocks);
+      const int c = (k >= fs.luma_blocks) ? 1 : 0;
+      const int16_t* blk = zz + coef_block_base(g);
+      const AddrChunkLoader loader(blk);
+      const int pred = dc_predictor(zz, g, k, fs.mcu_blocks, fs.luma_blocks, dc_init);
+      LocalSink sink = {mine, 0u, 0u, 0, 0, 0u};
+      code_block_mapped(loader, lo, hi, blk[0], pred, sh.dc[c], sh.ac[c], sink);
+      sink.finish();
+      mine[kLocalWords] = sink.total;
+    }
+    if (threadIdx.x == 0) next_id[b] = claim_tile();   // broadcast by the barriers below
+    bar_sync(kBarWorkers, kEWorkers);                  // every slot of the tile is filled
+    prev_total = scan_tile(b);
+    const long long t_next = next_id[b];
+    __threadfence_block();
+    bar_arrive(kBarFull + b, kEThreads);
+    if (t_prev >= 0) copy_out(t_prev, b ^ 1);
     t_prev = t;
     t = t_next;
+    ++i;
   }
 }
 
@@ -1839,7 +1885,8 @@ void LaunchHistogram(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s)
   }
   // 3 CTAs (66 KB of counters each) per SM over all pictures of the group, at least 64 blocks per warp
   unsigned grid = cdiv(fs.blocks_per_frame, (kH1Threads / 32) * 64);
-  const unsigned cap = SmCount() * 3 / (fs.frames > 0 ? fs.frames : 1) + 1;
+  unsigned cap = SmCount() * 3 / (fs.frames > 0 ? fs.frames : 1);   // rounded DOWN: a 445th CTA would run alone in a second wave
+  if (cap < 1) cap = 1;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   histogram_kernel<<<dim3(grid, fs.frames), kH1Threads, kH1SmemBytes, s>>>(fs, gb);
@@ -1866,7 +1913,8 @@ void LaunchTrellis(const FrameSet& fs, const GroupBuffers& gb, const int16_t* ra
 
 void LaunchSymbolStats(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s) {
   unsigned grid = cdiv(fs.blocks_per_frame, kTileBlocks);
-  const unsigned cap = SmCount() * 8 / (fs.frames > 0 ? fs.frames : 1) + 1;
+  unsigned cap = SmCount() * 8 / (fs.frames > 0 ? fs.frames : 1);   // rounded down: one wave
+  if (cap < 1) cap = 1;
   if (grid > cap) grid = cap;
   symbol_stats_kernel<<<dim3(grid, fs.frames), kTileBlocks, 0, s>>>(fs, gb);
 }
