@@ -99,6 +99,8 @@ struct SmallLayout {
 // one independent pipeline: a stream plus all the scratch one group needs
 struct Lane {
   cudaStream_t stream = nullptr;
+  cudaStream_t hi = nullptr;        // SJB_ES_PRIORITY: highest-priority stream for E + S
+  cudaEvent_t hi_ev = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t phase_ev = nullptr;   // end of the current phase of the group on this lane (GroupJob)
   // timed groups: begin/end of each kernel stage -- 0 F1, 1 H1, 2 Q1 or T1, 3 S1, 4 E, 5 S
@@ -197,6 +199,15 @@ int InitLane(sjb_context* ctx, Lane* L) {
 
 void DestroyLane(Lane* L) {
   if (L->stream) cudaStreamSynchronize(L->stream);
+  if (L->hi) {
+    cudaStreamSynchronize(L->hi);
+    cudaStreamDestroy(L->hi);
+    L->hi = nullptr;
+  }
+  if (L->hi_ev) {
+    cudaEventDestroy(L->hi_ev);
+    L->hi_ev = nullptr;
+  }
   for (DeviceBuffer* b : {&L->pix, &L->coef, &L->nzmask, &L->words, &L->out, &L->state, &L->small, &L->raw, &L->perm}) b->Release();
   for (auto& e : L->ev) if (e) cudaEventDestroy(e);
   if (L->phase_ev) cudaEventDestroy(L->phase_ev);
@@ -428,16 +439,29 @@ struct StageTimer {
   Lane* L;
   int idx;
   bool on;
-  StageTimer(Lane* lane, int i, bool timed) : L(lane), idx(i), on(timed) {
-    if (on) cudaEventRecord(L->kev[idx][0], L->stream);
+  cudaStream_t st;
+  StageTimer(Lane* lane, int i, bool timed, cudaStream_t stream = nullptr)
+      : L(lane), idx(i), on(timed), st(stream ? stream : lane->stream) {
+    if (on) cudaEventRecord(L->kev[idx][0], st);
   }
   ~StageTimer() {
     if (on) {
-      cudaEventRecord(L->kev[idx][1], L->stream);
+      cudaEventRecord(L->kev[idx][1], st);
       L->kev_set[idx] = true;
     }
   }
 };
+
+// SJB_ES_PRIORITY=1: the entropy and stuffing kernels of a group go to a highest-priority stream of
+// the lane, so that the block scheduler gives SM slots freed by another group's F1 to them first and
+// the two kinds of kernels share SMs (F1 is issue bound, E latency bound) instead of following each other.
+bool EsPriority() {
+  static const bool v = [] {
+    const char* e = getenv("SJB_ES_PRIORITY");
+    return e != nullptr && atoi(e) != 0;
+  }();
+  return v;
+}
 
 struct GroupJob {
   Lane* L = nullptr;
@@ -502,8 +526,20 @@ int FinishGroup(sjb_context* ctx, GroupJob* J) {
     }
   }
   L->words_dirty = true;
-  CU(cudaMemsetAsync(L->state.ptr, 0, L->state.bytes, L->stream));   // look-back descriptors
-  { StageTimer t(L, 4, J->timed); LaunchEntropyPack(fs, gb, L->stream); }
+  cudaStream_t es = L->stream;
+  if (EsPriority()) {
+    if (L->hi == nullptr) {
+      int lo = 0, hi = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CU(cudaStreamCreateWithPriority(&L->hi, cudaStreamNonBlocking, hi));
+      CU(cudaEventCreateWithFlags(&L->hi_ev, cudaEventDisableTiming));
+    }
+    es = L->hi;
+    CU(cudaEventRecord(L->hi_ev, L->stream));
+    CU(cudaStreamWaitEvent(es, L->hi_ev, 0));
+  }
+  CU(cudaMemsetAsync(L->state.ptr, 0, L->state.bytes, es));   // look-back descriptors
+  { StageTimer t(L, 4, J->timed, es); LaunchEntropyPack(fs, gb, es); }
   {
     StuffArgs sa;
     memset(&sa, 0, sizeof(sa));
@@ -511,8 +547,12 @@ int FinishGroup(sjb_context* ctx, GroupJob* J) {
       sa.header_len[f] = L->header_len[f];
       sa.flags[f] = kStuffFirst | kStuffLast;
     }
-    StageTimer t(L, 5, J->timed);
-    LaunchStuff(fs, gb, sa, L->stream);
+    StageTimer t(L, 5, J->timed, es);
+    LaunchStuff(fs, gb, sa, es);
+  }
+  if (es != L->stream) {
+    CU(cudaEventRecord(L->hi_ev, es));
+    CU(cudaStreamWaitEvent(L->stream, L->hi_ev, 0));
   }
   L->launches += 2;
   CU(cudaGetLastError());
