@@ -339,7 +339,9 @@ struct BitCountSink {
 };
 
 // symbol statistics of a block (entropy.cc:208-227); Add(table_slot) where slot < 256 is an AC
-// symbol and 256 + n a DC size.
+// symbol and 256 + n a DC size.  (Walking by non-zero like the coder -- map first, one value load
+// per non-zero -- was measured SLOWER here: 4K gen A 217 -> 257 us per 16 pictures, 4:4:4 q90 220 ->
+// 305; the chunk walk below keeps its values in registers and the counters' atomics dominate.)
 template <class LoadChunk, class Add>
 SJB_HD void block_symbol_stats(LoadChunk load_chunk, uint32_t chunkmask, int dc, int dc_pred, Add& add) {
   {

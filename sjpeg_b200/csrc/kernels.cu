@@ -1029,34 +1029,33 @@ __device__ __forceinline__ void bar_arrive(int id, int count) {
     default: bar_arrive_id<5>(count); break;
   }
 }
-// cta_exclusive_scan for the worker warps only (named barrier instead of __syncthreads)
-__device__ __forceinline__ uint32_t workers_exclusive_scan(uint32_t v, uint32_t* scratch, uint32_t* total) {
+// Exclusive scan over the worker warps with ONE named barrier: every warp leaves its total in the
+// half of `scratch` the caller's parity selects, and after the barrier every warp scans those few
+// totals itself with shuffles.  Two calls in a row must use different parities (a fast warp may be
+// writing the next scan's totals while a slow one still reads this one's); with the parity
+// alternating, the barrier of the call in between orders a half's reuse.
+__device__ __forceinline__ uint32_t workers_exclusive_scan(uint32_t v, uint32_t* scratch /*[2][8]*/, int parity, uint32_t* total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int nwarps = kEWorkers / 32;
+  static_assert(nwarps <= 32, "one lane per worker warp");
   uint32_t incl = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
     if (lane >= d) incl += t;
   }
-  if (lane == 31) scratch[warp] = incl;
+  uint32_t* mine = scratch + parity * nwarps;
+  if (lane == 31) mine[warp] = incl;
   bar_sync(kBarWorkers, kEWorkers);
-  if (warp == 0) {
-    const uint32_t w = (lane < nwarps) ? scratch[lane] : 0;
-    uint32_t wi = w;
+  const uint32_t w = (lane < nwarps) ? mine[lane] : 0u;
+  uint32_t wi = w;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
-      if (lane >= d) wi += t;
-    }
-    scratch[lane] = wi - w;
-    if (lane == 31) scratch[32] = wi;
+  for (int d = 1; d < nwarps; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+    if (lane >= d) wi += t;
   }
-  bar_sync(kBarWorkers, kEWorkers);
-  const uint32_t res = scratch[warp] + incl - v;
-  *total = scratch[32];
-  bar_sync(kBarWorkers, kEWorkers);   // scratch reusable afterwards
-  return res;
+  *total = __shfl_sync(0xffffffffu, wi, nwarps - 1);
+  return __shfl_sync(0xffffffffu, wi - w, warp) + incl - v;
 }
 
 __global__ void __launch_bounds__(kEThreads, kECtasPerSm)
@@ -1152,7 +1151,7 @@ entropy_pack_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
     uint32_t* mine = local[pb][threadIdx.x];
     const uint32_t bits = mine[kLocalWords];
     uint32_t total;
-    const uint32_t ex = workers_exclusive_scan(bits, scratch, &total);
+    const uint32_t ex = workers_exclusive_scan(bits, scratch, pb, &total);
     mine[kLocalWords] = ex | (bits << 20);        // ex < 256 * 1696 < 2^20, bits < 2^11
     if (threadIdx.x == 0) tile_total[pb] = total;
     return total;

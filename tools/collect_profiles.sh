@@ -6,6 +6,7 @@ mkdir -p $O
 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err
 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference_n1.json 2>> $O/bench_n1.err
 python tools/latency.py > $O/latency.txt 2>&1
+python tools/quick_perf.py > $O/quick_perf.txt 2>&1
 python tools/batch_methods.py B 16 > $O/batch_methods.txt 2>&1
 python tools/batch_methods.py A 16 >> $O/batch_methods.txt 2>&1
 python tools/planar_bench.py > $O/planar.txt 2>&1
