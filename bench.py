@@ -189,7 +189,7 @@ CONFIGS = [
     ("C4 8K q75 420 m7 (trellis)", "A", 7680, 4320, 75, 7, 1, 2),
     ("C4 8K q75 420 m7 (trellis)", "B", 7680, 4320, 75, 7, 1, 2),
 ]
-STAGE_KERNEL = {"F1": "f1_fast_kernel (convert+fDCT[+quantise])", "H1": "histogram_kernel", "Q1/T1": "requantize / trellis",
+STAGE_KERNEL = {"F1": "f1_fast_kernel (convert+fDCT[+quantise])", "H1": "histogram_kernel", "Q1/T1": "histogram analysis + requantize / trellis",
                 "S1": "symbol_stats_kernel", "E": "entropy_pack_kernel", "S": "stuff_kernel"}
 
 
@@ -326,7 +326,9 @@ def run_config5(ctx, rank, world, dist, barrier):
             os.close(saved)
         y0, y1 = enc.rows(h, S.YUV_420)
         stripes = [pin(np.ascontiguousarray(f[y0:y1])) for f in frames]
-        t_stripes, jpegs = timed(lambda: enc.encode(stripes, False, w, h, 3 * w, p, cap))
+        # like the frames arm, the timed call leaves the JPEGs in host buffers (no Python byte strings)
+        t_stripes, raw = timed(lambda: enc.encode(stripes, False, w, h, 3 * w, p, cap, raw=True))
+        jpegs = [raw[0][i][:raw[1][i]].tobytes() for i in range(n)] if rank == 0 else None
         ok_stripes = None
         if rank == 0:
             if method == 0:

@@ -772,6 +772,128 @@ struct TrellisHostTab {
 
 SJB_HD uint32_t sjb_minu(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
+// ---------------------------------------------------------------------------------------------
+// Adaptive quantisation: analysis of the coefficient histograms (histogram.cc:126-315) in a form
+// that runs on the device (kernels.cu: analyse_fit_kernel + analyse_pick_kernel) and, compiled by
+// g++, in the CPU emulation.  The arithmetic is the reference's: 32-bit wrapping integer products,
+// sums of integers far below 2^53 (exact in double whatever the order), then the SAME sequence of
+// double / float operations per position and over the positions in ascending order -- IEEE
+// operations without contraction give the same bits on the device as on the host (the library is
+// compiled with --fmad=false / -ffp-contract=off).
+//   histogram row h: int32[128] counts of |coef| >> 2 for one matrix and position
+//   candidate steps: q0 + d - 12 for d = 0..24; weights of the linear fit of distortion and rate
+//   against the step; lambda = -cov(dist) / cov(rate) summed over the positions that pass the
+//   density and correlation tests; per position the step minimising dist + lambda * rate
+// ---------------------------------------------------------------------------------------------
+enum { kAqDeltaMin = -12, kAqNumDelta = 25, kAqShift = 2, kAqBins = 128 };
+#define SJB_AQ_FLT_MAX 3.402823466e+38f
+
+struct AqFit {                 // what the fit of one position leaves for the pick
+  float rate[kAqNumDelta];
+  float dist[kAqNumDelta];
+  double cov, den;             // this position's terms of the two sums lambda is made of
+  int skip;                    // position keeps its step (never touched, too sparse, or uncorrelated)
+  int pad;
+};
+
+SJB_HD float aq_weight(int d) {
+  // histogram.cc:119-124
+  return d < 5 || d > 19 ? 0.f
+       : d == 5 || d == 19 ? 1.f : d == 6 || d == 18 ? 5.f : d == 7 || d == 17 ? 16.f : d == 8 || d == 16 ? 43.f
+       : d == 9 || d == 15 ? 94.f : d == 10 || d == 14 ? 164.f : d == 11 || d == 13 ? 228.f : 255.f;
+}
+// does candidate d of a position take part (as a fitted point or as a choice)?
+SJB_HD bool aq_candidate_used(int q0, int qmin, int delta_top, int d) {
+  const int q = q0 + d + kAqDeltaMin;
+  if (q < qmin || q > 255) return false;
+  if (d > delta_top && aq_weight(d) == 0.f) return false;
+  return true;
+}
+// sums over the bins [i0, i1) of count * bit length of the quantised level and count * squared
+// error, for step q (histogram.cc:236-247; products wrap at 32 bits like the compiled reference's)
+SJB_HD void aq_bin_sums(const int32_t* h, int i0, int i1, int q, long long* bits_sum, long long* dist_sum) {
+  const int recip = ((1 << 16) + q - 1) / q;
+  long long bs = 0, ds = 0;
+  for (int i = i0; i < i1; ++i) {
+    const int v = (i << kAqShift) + (1 << (kAqShift - 1));   // bin centre
+    const int level = (v * recip + 32768) >> 16;
+    const int e = v - level * q;
+    bs += (int32_t)((uint32_t)h[i] * (uint32_t)bit_length((uint32_t)level));
+    ds += (int32_t)((uint32_t)h[i] * (uint32_t)(e * e));
+  }
+  *bits_sum = bs;
+  *dist_sum = ds;
+}
+// the weighted linear fits of one position over its candidates, in candidate order
+SJB_HD void aq_fit_position(const long long* bits_sum, const long long* dist_sum, int q0, int qmin, int delta_top,
+                            AqFit* out) {
+  const double kCorrelation = 0.5;
+  double sw = 0., sx = 0., sxx = 0., syy1 = 0., sy1 = 0., sxy1 = 0., sy2 = 0., sxy2 = 0.;
+  for (int d = 0; d < kAqNumDelta; ++d) {
+    if (!aq_candidate_used(q0, qmin, delta_top, d)) {
+      out->dist[d] = SJB_AQ_FLT_MAX;
+      out->rate[d] = 0;
+      continue;
+    }
+    const double bsum = (double)bits_sum[d], dsum = (double)dist_sum[d];
+    out->dist[d] = (float)dsum;
+    out->rate[d] = (float)bsum;
+    const double w = aq_weight(d);
+    if (w > 0.) {
+      const double x = (double)(d + kAqDeltaMin);
+      sw += w;
+      sx += w * x;
+      sxx += w * x * x;
+      sy1 += w * dsum;
+      syy1 += w * dsum * dsum;
+      sy2 += w * bsum;
+      sxy1 += w * dsum * x;
+      sxy2 += w * bsum * x;
+    }
+  }
+  const double cov = sw * sxy1 - sx * sy1;
+  out->skip = (cov * cov < kCorrelation * (sw * sxx - sx * sx) * (sw * syy1 - sy1 * sy1)) ? 1 : 0;
+  out->cov = cov;
+  out->den = sw * sxy2 - sx * sy2;
+}
+SJB_HD double aq_lambda(double num, double den) {
+  double lambda = 128.;                    // fallback
+  if (num > 1000. && den < -10.) {
+    lambda = -num / den;
+    if (lambda < 1.) lambda = 1.;
+  }
+  return lambda;
+}
+SJB_HD int aq_best_delta(const AqFit& f, int delta_top, double lambda) {
+  float best = SJB_AQ_FLT_MAX;
+  int best_delta = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int d = 0; d < kAqNumDelta; ++d) {            // fixed trip count: candidates stay in registers on the device
+    if (d <= delta_top && f.dist[d] < SJB_AQ_FLT_MAX) {
+      const float score = (float)((double)f.dist[d] + lambda * (double)f.rate[d]);
+      if (score < best) {
+        best = score;
+        best_delta = d + kAqDeltaMin;
+      }
+    }
+  }
+  return best_delta;
+}
+// reciprocal / bias constants of one matrix entry (quantize.cc:116-148 in the fused form of the top
+// of this file); returns false when the entry cannot be expressed (the caller refuses the encode)
+SJB_HD bool aq_finalize_entry(uint32_t q, bool is_dc, int q_bias, int32_t* iq, int32_t* cpos_out) {
+  const uint32_t recip = (q == 1) ? 0xffffu : (((1u << 16) + q / 2) / q) & 0xffffu;
+  const uint32_t bias8 = (q == 1 || is_dc) ? 0x80u : (uint32_t)q_bias;
+  const uint32_t bias = ((((bias8 * q) << 4) + 128) >> 8) & 0xffffu;
+  const int thresh = (int)(((1u << 20) + recip - 1) / recip) - (int)bias;
+  const long long cpos = (long long)bias * recip;
+  *iq = (int32_t)recip;
+  *cpos_out = (int32_t)cpos;
+  return !(thresh < 0 || thresh > 0xffff || cpos + 17000LL * recip >= (1LL << 31));
+}
+
 // Position inside a tile of `count` consecutive blocks starting at global block `first` of the
 // block that worker `i` walks: the tile's luma blocks in order, then its chroma blocks.  Blocks
 // are stored MCU by MCU, `lb` luma blocks then `mb - lb` chroma blocks (6/4 for 4:2:0, 3/1 for

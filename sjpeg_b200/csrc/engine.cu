@@ -82,6 +82,8 @@ struct HostScratch {     // pinned, for small async up/downloads; one slot per p
   int32_t hist[kMaxGroup][2 * 64 * kHistoStride];
   uint32_t freq[kMaxGroup][2 * 272];
   uint8_t quant[kMaxGroup][2][64];
+  int aq_fail[kMaxGroup];
+  CodeTabs def_tabs[kMaxGroup];              // written once, before their only upload
   uint8_t header[kMaxGroup][kHeaderReserve];
 };
 
@@ -93,7 +95,11 @@ struct SmallLayout {
   int32_t hist[kMaxGroup][2 * 64 * kHistoStride];
   uint32_t freq[kMaxGroup][2 * 272];
   uint8_t quant[kMaxGroup][2][64];
+  int aq_fail[kMaxGroup];                    // A1: a derived matrix entry the fused quantiser cannot express (right behind
+                                             // quant, as in HostScratch: the two travel to the host in one copy)
   uint32_t trellis_sort[kMaxGroup][128];
+  CodeTabs def_tabs[kMaxGroup];              // the default tables, for the trellis' rate model (enc.cc:334); written once
+  AqFit aq_fit[kMaxGroup][2][64];            // A1 scratch
 };
 
 // one independent pipeline: a stream plus all the scratch one group needs
@@ -112,6 +118,7 @@ struct Lane {
   int group_capacity = 0;        // pictures the buffers are laid out for
   size_t pix_pitch = 0;
   bool words_dirty = false;
+  bool def_tabs_valid = false;   // d_small()->def_tabs hold the default code tables
   int tabs_valid = 0;            // number of leading device tabs[] slots that mirror host->tabs
   int header_valid = 0;          // same for the header bytes at the start of each out slot
   unsigned header_len[kMaxGroup] = {0};
@@ -421,17 +428,18 @@ bool MakeQuantTabs(const Plan& plan, uint8_t quant[2][64], uint8_t min_quant[2][
 // ---------------------------------------------------------------------------------------------
 // Device pipeline for one group whose pixels are already in device memory (fs.pix[]).
 //
-// Methods >= 1 need the host between kernels -- histogram -> AnalyseHisto -> new matrices
-// (histogram.cc:126-315), symbol counts -> optimal Huffman tables (entropy.cc:254-444) -- so a group
+// Methods that optimise the Huffman tables need the host between kernels -- symbol counts -> optimal
+// tables (entropy.cc:254-444); the adaptive ones did too until the histogram analysis
+// (histogram.cc:126-315) became a kernel, and still want their matrices on the host for the DQT -- so a group
 // is a small state machine (GroupJob): every phase enqueues work on the lane's stream, ends with an
 // event, and the next phase starts by waiting for that event.  A single encode just runs the phases
 // back to back; the batch entry points interleave the phases of several groups (one per lane) so
 // that the calling thread is enqueueing the next group's upload and kernels while an earlier group's
 // counters travel back, instead of idling in cudaStreamSynchronize with the GPU (and the PCIe link)
 // waiting for it.  Per-picture host work of a phase is spread over the context's worker threads.
-//   stage 0 -> [adaptive: F1 raw, H1, histogram D2H | else: F1 quantised]
-//   stage 1 -> (wait) AnalyseHistograms per picture, tables H2D, Q1 or T1
-//   stage 2 -> (wait) OptimalHuffSpec per picture
+//   stage 0 -> [adaptive: F1 raw, H1, A1 (analysis on the device), Q1 or T1, matrices D2H | else: F1 quantised]
+//   stage 1 -> (wait) adaptive methods without optimised tables: the matrices for the DQT have arrived
+//   stage 2 -> (wait) OptimalHuffSpec per picture (the matrices arrived with the symbol counts)
 //   finish  -> code tables + headers H2D, E, S, sizes D2H          => stage 3 (all enqueued)
 // ---------------------------------------------------------------------------------------------
 // brackets one kernel stage of a timed group with events (sjb_last_stage_timings)
@@ -492,6 +500,54 @@ int UploadCodeTabs(sjb_context* ctx, GroupJob* J) {
   for (int f = 0; f < n; ++f) H->tabs[f] = J->tabs[f];
   LaunchCopySmall(L->d_small()->tabs, H->tabs, n * sizeof(CodeTabs), L->stream);   // not the copy engine: kernels.cu
   L->tabs_valid = n;
+  return SJB_OK;
+}
+
+// the default code tables as the trellis' rate model (enc.cc:334): a device copy of their own, so that
+// the per-picture tables of the coder (d_small()->tabs) are only ever written with what the coder uses
+int EnsureDefaultTabs(Lane* L, const CodeTabs& def_tabs, cudaStream_t st) {
+  if (L->def_tabs_valid) return SJB_OK;
+  for (int f = 0; f < kMaxGroup; ++f) L->host->def_tabs[f] = def_tabs;
+  LaunchCopySmall(L->d_small()->def_tabs, L->host->def_tabs, sizeof(L->host->def_tabs), st);
+  L->def_tabs_valid = true;
+  return SJB_OK;
+}
+
+void FillAqParams(const Plan& plan, const uint8_t quant0[2][64], const uint8_t min_quant[2][64], AqParams* ap) {
+  memcpy(ap->quant0, quant0, 128);
+  memcpy(ap->min_quant, min_quant, 128);
+  ap->qdelta_max[0] = plan.p.qdelta_max_luma;
+  ap->qdelta_max[1] = plan.p.qdelta_max_chroma;
+  ap->q_bias = plan.p.q_bias;
+  ap->nb_comps = plan.g.nb_comps;
+}
+
+// Adaptive methods, everything after the histogram kernel up to the quantised coefficients, stream
+// ordered on st: analysis on the device (A1), the matrices for the DQT on their way to the host
+// (host->quant, host->aq_fail: valid once the stream has passed this point), Q1 or T1.
+int EnqueueAdaptiveQuantise(sjb_context* ctx, Lane* L, const FrameSet& fs, const Plan& plan, const uint8_t quant0[2][64],
+                            const uint8_t min_quant[2][64], const CodeTabs& def_tabs, bool run_kernels, cudaStream_t st) {
+  SmallLayout* D = L->d_small();
+  const int n = fs.frames;
+  AqParams ap;
+  FillAqParams(plan, quant0, min_quant, &ap);
+  LaunchAnalyseHistograms(n, L->gb, ap, &D->aq_fit[0][0][0], D->aq_fail, st);      // also clears aq_fail[0..n)
+  static_assert(offsetof(SmallLayout, aq_fail) == offsetof(SmallLayout, quant) + sizeof(D->quant) &&
+                offsetof(HostScratch, aq_fail) == offsetof(HostScratch, quant) + sizeof(D->quant), "quant and aq_fail are copied together");
+  CU(cudaMemcpyAsync(L->host->quant, D->quant, sizeof(D->quant) + sizeof(D->aq_fail), cudaMemcpyDeviceToHost, st));
+  L->launches += kAnalyseLaunches;
+  if (!run_kernels) return SJB_OK;
+  if (plan.trellis) {
+    RC(EnsureDefaultTabs(L, def_tabs, st));
+    GroupBuffers gb = L->gb;
+    gb.tabs = D->def_tabs;
+    LaunchTrellis(fs, gb, nullptr, &D->trellis_sort[0][0], L->perm.as<uint32_t>(), plan.g.nb_blocks(), st);
+    L->launches += kTrellisLaunches;
+  } else {
+    LaunchRequantize(fs, L->gb, nullptr, st);
+    L->launches += 1;
+  }
+  CU(cudaGetLastError());
   return SJB_OK;
 }
 
@@ -615,16 +671,25 @@ int StartGroup(sjb_context* ctx, GroupJob* J, Lane* L, const FrameSet& fs, const
   for (int f = 0; f < n; ++f) for (int i = 0; i < 4; ++i) J->spec[f * 4 + i] = J->def_spec[i];
 
   if (plan.adaptive) {
-    // enc.cc:425-429 : histogram pass over unquantised coefficients, matrices re-derived on host
+    // enc.cc:425-429 : histogram pass over unquantised coefficients; the matrices are re-derived ON
+    // THE DEVICE (A1) and the coefficients quantised with them without the host in between.  The host
+    // only needs the matrices for the DQT segment: they travel back behind the kernels and are picked
+    // up at the next wait the method has anyway (symbol counts), or at one of their own (stage 1).
     { StageTimer t(L, 0, timed); LaunchF1(L, fs, g, /*raw=*/true, J->qt); }
     CU(cudaMemsetAsync(D->hist, 0, n * sizeof(D->hist[0]), L->stream));
     { StageTimer t(L, 1, timed); LaunchHistogram(fs, L->gb, L->stream); }
     L->launches += 1;
-    CU(cudaMemcpyAsync(L->host->hist, D->hist, n * sizeof(D->hist[0]), cudaMemcpyDeviceToHost, L->stream));
     if (timed) CU(cudaEventRecord(L->ev[1], L->stream));
-    CU(cudaEventRecord(L->phase_ev, L->stream));
-    J->stage = 1;
-    return SJB_OK;
+    {
+      StageTimer t(L, 2, timed);
+      RC(EnqueueAdaptiveQuantise(ctx, L, fs, plan, J->quant0, J->min_quant, J->def_tabs, true, L->stream));
+    }
+    if (!plan.optimize) {
+      CU(cudaEventRecord(L->phase_ev, L->stream));
+      J->stage = 1;
+      return SJB_OK;
+    }
+    return AfterQuantise(ctx, J);
   }
   { StageTimer t(L, 0, timed); LaunchF1(L, fs, g, /*raw=*/false, J->qt); }
   if (timed) CU(cudaEventRecord(L->ev[1], L->stream));
@@ -641,36 +706,17 @@ int AdvanceGroup(sjb_context* ctx, GroupJob* J) {
   HostScratch* H = L->host;
   SmallLayout* D = L->d_small();
   CU(cudaEventSynchronize(L->phase_ev));
-  if (J->stage == 1) {
-    bool ok = true;
-    ctx->pool.ParallelFor(n, [&](int f) {
-      uint8_t q[2][64];
-      memcpy(q, J->quant0, 128);
-      AnalyseHistograms(H->hist[f], g.nb_comps, q, J->min_quant, plan.p.qdelta_max_luma, plan.p.qdelta_max_chroma);
-      QuantTabs qf = J->qt;
-      for (int i = (g.nb_comps > 1 ? 1 : 0); i >= 0; --i) {
-        if (!FinalizeQuantizer(q[i], J->min_quant[i], plan.p.q_bias, &qf.m[i])) ok = false;
+  if (plan.adaptive) {
+    // the matrices A1 derived, for the headers
+    for (int f = 0; f < n; ++f) {
+      if (H->aq_fail[f]) {
+        ctx->err = "adapted quantiser entry outside the range of the fused quantise form";
+        return SJB_ERR_ARG;
       }
-      H->qtabs[f] = qf;
-      memcpy(H->quant[f], q, 128);
-      memcpy(&J->quant[f * 128], q, 128);
-    });
-    if (!ok) return SJB_ERR_ARG;
-    LaunchCopySmall(D->qtabs, H->qtabs, n * sizeof(QuantTabs), L->stream);
-    if (plan.trellis) {
-      // rate model = default AC tables (enc.cc:334)
-      LaunchCopySmall(D->quant, H->quant, n * 128, L->stream);
-      RC(UploadCodeTabs(ctx, J));
-      StageTimer t(L, 2, J->timed);
-      LaunchTrellis(J->fs, L->gb, nullptr, &D->trellis_sort[0][0], L->perm.as<uint32_t>(), g.nb_blocks(), L->stream);
-      L->launches += kTrellisLaunches;
-    } else {
-      StageTimer t(L, 2, J->timed);
-      LaunchRequantize(J->fs, L->gb, nullptr, L->stream);
-      L->launches += 1;
+      memcpy(&J->quant[f * 128], H->quant[f], 128);
     }
-    return AfterQuantise(ctx, J);
   }
+  if (J->stage == 1) return FinishGroup(ctx, J);
   // stage 2: optimal tables from the symbol counts
   const int nb_tables = (g.nb_comps == 1) ? 1 : 2;
   ctx->pool.ParallelFor(n, [&](int f) {

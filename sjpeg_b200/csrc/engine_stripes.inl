@@ -69,7 +69,7 @@ int sjb_comm_unique_id(uint8_t id[128]) try {
 } SJB_NOTHROW_END
 
 int sjb_comm_create(sjb_context* ctx, const uint8_t id[128], int rank, int world, sjb_comm** out) try {
-  if (ctx == nullptr || id == nullptr || out == nullptr || world < 1 || rank < 0 || rank >= world) return SJB_ERR_ARG;
+  if (ctx == nullptr || id == nullptr || out == nullptr || world < 1 || world > 64 || rank < 0 || rank >= world) return SJB_ERR_ARG;
   *out = nullptr;
   ctx->err.clear();
   const NcclApi* api = Nccl();
@@ -246,7 +246,10 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
   // the communicator's stream (the rest).  Phase 1 of chunk c+1 is enqueued BEFORE the rest of
   // chunk c, so the host-to-device copies of the next chunk -- what bounds a batch that comes from
   // host memory -- proceed while this chunk's exchange waits for its small messages.
-  enum { kChunkGroups = 2 };
+  // One group (16 pictures) per chunk: what follows the LAST chunk's upload is exposed, the exchanges of
+  // the earlier ones hide under the next upload (two groups per chunk: 64 x 1080p on 4 GPUs 3.14 ms, of
+  // which 0.45 ms behind the last copy).
+  enum { kChunkGroups = 1 };
   const int chunks = (groups + kChunkGroups - 1) / kChunkGroups;
 
   // ---- phase 1, every set on its own stream: upload, F1 (+ H1) ---------------------------------
@@ -334,45 +337,11 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
                           comm->nccl, st));
       }
       NC(api->GroupEnd());
+      // every rank derives the same matrices from the same reduced counters, on the device (A1); the
+      // copies for the DQT segments are picked up behind a later wait (rank 0 only needs them)
       for (int k = g0; k < g1; ++k) {
-        Lane* L = comm->sets[k];
-        CU(cudaMemcpyAsync(L->host->hist, L->d_small()->hist, fsets[k].frames * sizeof(L->host->hist[0]),
-                           cudaMemcpyDeviceToHost, st));
+        RC(EnqueueAdaptiveQuantise(ctx, comm->sets[k], fsets[k], plan, quant0, min_quant, def_tabs, active, st));
       }
-      CU(cudaStreamSynchronize(st));
-      bool ok = true;
-      ctx->pool.ParallelFor(nc, [&](int j) {
-        const int i = i0 + j;
-        Lane* L = comm->sets[i / kMaxGroup];
-        const int f = i % kMaxGroup;
-        uint8_t q[2][64];
-        memcpy(q, quant0, 128);
-        AnalyseHistograms(L->host->hist[f], full.g.nb_comps, q, min_quant, plan.p.qdelta_max_luma, plan.p.qdelta_max_chroma);
-        QuantTabs qf = qt;
-        for (int cc = (full.g.nb_comps > 1 ? 1 : 0); cc >= 0; --cc) {
-          if (!FinalizeQuantizer(q[cc], min_quant[cc], plan.p.q_bias, &qf.m[cc])) ok = false;
-        }
-        L->host->qtabs[f] = qf;
-        memcpy(L->host->quant[f], q, 128);
-        memcpy(&quant[static_cast<size_t>(i) * 128], q, 128);
-      });
-      if (!ok) return SJB_ERR_ARG;
-      for (int k = g0; k < g1; ++k) {
-        Lane* L = comm->sets[k];
-        SmallLayout* D = L->d_small();
-        const int frames = fsets[k].frames;
-        LaunchCopySmall(D->qtabs, L->host->qtabs, frames * sizeof(QuantTabs), st);
-        if (!active) continue;
-        if (plan.trellis) {
-          LaunchCopySmall(D->quant, L->host->quant, frames * 128, st);
-          for (int f = 0; f < frames; ++f) L->host->tabs[f] = def_tabs;      // rate model: default AC tables (enc.cc:334)
-          LaunchCopySmall(D->tabs, L->host->tabs, frames * sizeof(CodeTabs), st);
-          LaunchTrellis(fsets[k], L->gb, nullptr, &D->trellis_sort[0][0], L->perm.as<uint32_t>(), plan.g.nb_blocks(), st);
-        } else {
-          LaunchRequantize(fsets[k], L->gb, nullptr, st);
-        }
-      }
-      CU(cudaGetLastError());
     }
 
     // DC predictors: last quantised DC of every component, handed to the next stripe
@@ -432,9 +401,6 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
     for (int k = g0; k < g1 && active; ++k) {
       Lane* L = comm->sets[k];
       const int frames = fsets[k].frames;
-      // pinned staging: an earlier copy out of it (the trellis' default tables) must have completed;
-      // every method that runs the trellis also optimises, i.e. has synchronised since -- but be explicit
-      if (plan.trellis && !plan.optimize) CU(cudaStreamSynchronize(st));
       for (int f = 0; f < frames; ++f) L->host->tabs[f] = tabs[k * kMaxGroup + f];
       LaunchCopySmall(L->d_small()->tabs, L->host->tabs, frames * sizeof(CodeTabs), st);
       CU(cudaMemsetAsync(L->state.ptr, 0, L->state.bytes, st));
@@ -468,6 +434,14 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
     mark("enqueue to AG(meta)");
     CU(cudaStreamSynchronize(st));
     mark("sync after meta");
+    if (plan.adaptive) {
+      for (int j = 0; j < nc; ++j) {
+        const int i = i0 + j;
+        Lane* L = comm->sets[i / kMaxGroup];
+        if (L->host->aq_fail[i % kMaxGroup]) return SJB_ERR_ARG;
+        memcpy(&quant[static_cast<size_t>(i) * 128], L->host->quant[i % kMaxGroup], 128);
+      }
+    }
 
     // gather the compressed stripes on rank 0: exact sizes, one grouped send/recv
     std::vector<size_t> rank_bytes(world, 0);
@@ -520,32 +494,41 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
     CU(cudaStreamSynchronize(st));
     mark("sync after gather");
 
-    // rank 0: header + stripes, boundary bytes merged
+    // rank 0: header + stripes, boundary bytes merged; the pictures are independent, so they are put
+    // together on the context's worker threads (one thread took 125-190 us per 32 pictures, all of it
+    // exposed behind the last chunk)
     int rc = SJB_OK;
-    std::vector<size_t> cursor(rank_base);
-    std::vector<const uint8_t*> part(world);
-    std::vector<size_t> psize(world);
-    std::vector<unsigned> pflags(world);
-    std::vector<uint8_t> header;
-    for (int j = 0; j < nc; ++j) {
+    std::vector<size_t> start(static_cast<size_t>(world) * nc);      // where stripe (r, j) begins in h_recv
+    for (int r = 0; r < world; ++r) {
+      size_t at = rank_base[r];
+      for (int j = 0; j < nc; ++j) {
+        start[static_cast<size_t>(r) * nc + j] = at;
+        at += static_cast<size_t>(comm->h_meta[(static_cast<size_t>(r) * nc + j) * 2]);
+      }
+    }
+    std::vector<int> arcs(nc, SJB_OK);
+    ctx->pool.ParallelFor(nc, [&](int j) {
       const int i = i0 + j;
-      header.clear();
+      std::vector<uint8_t> header;
+      header.reserve(1024);
       AppendHeaders(full.g, reinterpret_cast<const uint8_t(*)[64]>(&quant[static_cast<size_t>(i) * 128]), &spec[i * 4], &header);
+      const uint8_t* part[64];
+      size_t psize[64];
+      unsigned pflags[64];
       int holders = 0;
-      for (int r = 0; r <= last_holder; ++r) {
+      for (int r = 0; r <= last_holder && holders < 64; ++r) {
         const unsigned long long* m = comm->h_meta + (static_cast<size_t>(r) * nc + j) * 2;
-        part[holders] = comm->h_recv + cursor[r];
+        part[holders] = comm->h_recv + start[static_cast<size_t>(r) * nc + j];
         psize[holders] = static_cast<size_t>(m[0]);
         pflags[holders] = static_cast<unsigned>(m[1]);
-        cursor[r] += psize[holders];
         ++holders;
       }
       size_t size = 0;
-      const int arc = sjb_stripes_assemble(header.data(), header.size(), holders, part.data(), psize.data(), pflags.data(),
-                                           out[i], out[i] ? out_capacity : 0, &size);
+      arcs[j] = sjb_stripes_assemble(header.data(), header.size(), holders, part, psize, pflags, out[i], out[i] ? out_capacity : 0,
+                                     &size);
       sizes[i] = size;
-      if (arc != SJB_OK) rc = arc;
-    }
+    });
+    for (int j = 0; j < nc; ++j) if (arcs[j] != SJB_OK) rc = arcs[j];
     mark("assemble");
     return rc;
   };

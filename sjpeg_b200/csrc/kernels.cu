@@ -777,6 +777,130 @@ histogram_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
 }
 
 // -------------------------------------------------------------------------------------------
+// A1: the histogram analysis of the adaptive methods on the device (block_ops.cuh: aq_*).  Until
+// round 2 the histograms travelled to the host (66 KB per picture), were analysed there (0.05-0.12 ms
+// per 4K picture on a pool of threads) and the new quantiser tables travelled back, with the stream
+// drained in between; now the matrices never leave the device before the headers need them.
+//   analyse_fit_kernel   one CTA per (position, matrix, picture): 128 threads = 25 candidate steps x 4
+//                        quarters of the bins add up count x bits and count x error^2 (integers:
+//                        exact in any order); thread 0 runs the position's weighted fits in
+//                        candidate order, as the reference does
+//   analyse_pick_kernel  one CTA per (matrix, picture): thread 0 adds the positions' terms in
+//                        ascending order (double sums: the order is part of the result), lambda,
+//                        then one thread per position picks its step, clamps it and derives the
+//                        quantiser constants (FinalizeQuantizer)
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+analyse_fit_kernel(GroupBuffers gb, const __grid_constant__ AqParams ap, AqFit* __restrict__ fit, int* __restrict__ fail) {
+  __shared__ int32_t h[kAqBins];
+  __shared__ long long part_bits[4][kAqNumDelta], part_dist[4][kAqNumDelta];
+  __shared__ int red_total[4], red_last[4];
+  const int pos = blockIdx.x, idx = blockIdx.y, frame = blockIdx.z;
+  AqFit* out = fit + (static_cast<size_t>(frame) * 2 + idx) * 64 + pos;
+  if (pos == 0 || pos == 1 || pos == 8) {          // never touched (histogram.cc:139)
+    if (threadIdx.x == 0) {
+      out->skip = 1;
+      if (pos == 0 && idx == 0) fail[frame] = 0;   // the pick kernel (next launch) raises it
+    }
+    return;
+  }
+  const int32_t* row = gb.hist + (static_cast<size_t>(frame) * 2 + idx) * 64 * 129 + pos * 129;
+  const int c = row[threadIdx.x];
+  h[threadIdx.x] = c;
+  // total count and index of the last used bin + 1
+  int total = c, last = c ? static_cast<int>(threadIdx.x) + 1 : 0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    total += __shfl_xor_sync(0xffffffffu, total, d);
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, d));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red_total[threadIdx.x >> 5] = total;
+    red_last[threadIdx.x >> 5] = last;
+  }
+  __syncthreads();
+  total = red_total[0] + red_total[1] + red_total[2] + red_total[3];
+  last = max(max(red_last[0], red_last[1]), max(red_last[2], red_last[3]));
+  if (total < 0.5 * last) {                         // too sparse to fit (kDensity)
+    if (threadIdx.x == 0) out->skip = 1;
+    return;
+  }
+  const int q0 = ap.quant0[idx][pos], qmin = ap.min_quant[idx][pos];
+  const int delta_top = ap.qdelta_max[idx] - kAqDeltaMin;
+  const int d = threadIdx.x & 31, quarter = threadIdx.x >> 5;
+  if (d < kAqNumDelta) {
+    long long bs = 0, ds = 0;
+    if (aq_candidate_used(q0, qmin, delta_top, d)) {
+      aq_bin_sums(h, quarter * 32, min(last, quarter * 32 + 32), q0 + d + kAqDeltaMin, &bs, &ds);
+    }
+    part_bits[quarter][d] = bs;
+    part_dist[quarter][d] = ds;
+  }
+  __syncthreads();
+  if (threadIdx.x < kAqNumDelta) {
+    part_bits[0][threadIdx.x] += part_bits[1][threadIdx.x] + part_bits[2][threadIdx.x] + part_bits[3][threadIdx.x];
+    part_dist[0][threadIdx.x] += part_dist[1][threadIdx.x] + part_dist[2][threadIdx.x] + part_dist[3][threadIdx.x];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) aq_fit_position(part_bits[0], part_dist[0], q0, qmin, delta_top, out);
+}
+
+__global__ void __launch_bounds__(64)
+analyse_pick_kernel(GroupBuffers gb, const __grid_constant__ AqParams ap, const AqFit* __restrict__ fit, int* __restrict__ fail) {
+  __shared__ double lambda_sh;
+  __shared__ uint8_t q_sh[64];
+  const int idx = blockIdx.x, frame = blockIdx.y, pos = threadIdx.x;
+  const AqFit* f = fit + (static_cast<size_t>(frame) * 2 + idx) * 64;
+  // every thread fetches its position's terms (one round trip for all 64), thread 0 adds them in order
+  __shared__ double cov_sh[64], den_sh[64];
+  __shared__ int skip_sh[64];
+  const int skip = f[pos].skip;
+  skip_sh[pos] = skip;
+  cov_sh[pos] = skip ? 0. : f[pos].cov;
+  den_sh[pos] = skip ? 0. : f[pos].den;
+  __syncthreads();
+  if (pos == 0) {
+    double num = 0., den = 0.;
+    for (int p = 0; p < 64; ++p) {
+      if (skip_sh[p]) continue;
+      num += cov_sh[p];
+      den += den_sh[p];
+    }
+    lambda_sh = aq_lambda(num, den);
+  }
+  __syncthreads();
+  const int delta_top = ap.qdelta_max[idx] - kAqDeltaMin;
+  int q = ap.quant0[idx][pos];
+  if (!skip) {
+    AqFit mine;                                    // all 50 loads in flight at once, then the serial pick
+#pragma unroll
+    for (int d = 0; d < kAqNumDelta; ++d) {
+      mine.rate[d] = f[pos].rate[d];
+      mine.dist[d] = f[pos].dist[d];
+    }
+    q = static_cast<uint8_t>(q + aq_best_delta(mine, delta_top, lambda_sh));
+  }
+  if (q < ap.min_quant[idx][pos]) q = ap.min_quant[idx][pos];      // FinalizeQuantizer's clamp
+  q_sh[pos] = static_cast<uint8_t>(q);
+  gb.quant[static_cast<size_t>(frame) * 128 + idx * 64 + pos] = static_cast<uint8_t>(q);
+  __syncthreads();
+  // quantiser constants by ZIG-ZAG position: thread z
+  constexpr int zz[64] = SJB_ZIGZAG_INIT;
+  const int z = threadIdx.x, i = zz[z];
+  int32_t iq, cpos;
+  const bool ok = aq_finalize_entry(q_sh[i], i == 0, ap.q_bias, &iq, &cpos);
+  QuantTabs* qt = gb.qtabs + frame;
+  qt->m[idx].e[z][0] = iq;
+  qt->m[idx].e[z][1] = cpos;
+  if (ap.nb_comps == 1) {                       // grayscale: the chroma table is never used; keep it defined
+    qt->m[1].e[z][0] = iq;
+    qt->m[1].e[z][1] = cpos;
+    gb.quant[static_cast<size_t>(frame) * 128 + 64 + pos] = ap.quant0[1][pos];
+  }
+  if (!ok) fail[frame] = 1;
+}
+
+// -------------------------------------------------------------------------------------------
 // Entropy stage helpers
 // -------------------------------------------------------------------------------------------
 // quantised DC of the previous block of the same component in scan order (enc.cc:286-305:
@@ -1897,6 +2021,12 @@ void LaunchHistogram(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s)
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   histogram_kernel<<<dim3(grid, fs.frames), kH1Threads, kH1SmemBytes, s>>>(fs, gb);
+}
+
+void LaunchAnalyseHistograms(int frames, const GroupBuffers& gb, const AqParams& ap, AqFit* fit, int* fail, cudaStream_t s) {
+  const int comps = ap.nb_comps > 1 ? 2 : 1;
+  analyse_fit_kernel<<<dim3(64, comps, frames), 128, 0, s>>>(gb, ap, fit, fail);
+  analyse_pick_kernel<<<dim3(comps, frames), 64, 0, s>>>(gb, ap, fit, fail);
 }
 
 void LaunchTrellis(const FrameSet& fs, const GroupBuffers& gb, const int16_t* raw_src, uint32_t* sort_state, uint32_t* perm,

@@ -114,6 +114,21 @@ void LaunchQuantError(const FrameSet& fs, const GroupBuffers& gb, const int16_t*
                       cudaStream_t s);
 // H1: histogram of |coef| >> 2 per matrix and position into gb.hist[frame] (pre-zeroed)
 void LaunchHistogram(const FrameSet& fs, const GroupBuffers& gb, cudaStream_t s);
+// A1: adaptive quantisation, the analysis of the histograms on the device (histogram.cc:126-315 +
+// quantize.cc:116-148): gb.hist[frame] -> gb.quant[frame] (the matrices that go into the DQT, natural
+// order) and gb.qtabs[frame] (the quantiser constants Q1 / T1 read).  The settings are the same for
+// every picture of the group.  fit: scratch, AqFit[frames][2][64]; fail[frame] is set to 1 when a
+// derived matrix entry cannot be expressed by the fused quantiser (the host then refuses the encode,
+// as FinalizeQuantizer does).  Two launches.
+struct AqParams {
+  uint8_t quant0[2][64];      // starting matrices, natural order
+  uint8_t min_quant[2][64];
+  int qdelta_max[2];          // luma, chroma (enc.cc:48-49)
+  int q_bias;
+  int nb_comps;               // 1: luma only (the chroma table is filled with the luma one's constants)
+};
+enum { kAnalyseLaunches = 2 };
+void LaunchAnalyseHistograms(int frames, const GroupBuffers& gb, const AqParams& ap, AqFit* fit, int* fail, cudaStream_t s);
 // T1: trellis quantisation of raw coefficients in place (quantize.cc:388-457) + bitmap; tables
 // gb.qtabs[frame], matrices gb.quant[frame], rate from the AC code lengths in gb.tabs[frame]
 // sort_state: uint32[frames][128] scratch; perm: uint32[frames][perm_pitch >= blocks] scratch (the order

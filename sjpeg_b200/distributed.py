@@ -295,9 +295,10 @@ class NcclStripeEncoder:
     def rows(self, height, yuv_mode):
         return stripe_rows(height, yuv_mode, self.world, self.rank)
 
-    def encode(self, stripe_ptrs, on_device, width, height, stride, params, capacity):
+    def encode(self, stripe_ptrs, on_device, width, height, stride, params, capacity, raw=False):
         """stripe_ptrs: address of row y0 of this rank's stripe of each picture.  Returns the list
-        of JPEG byte strings on rank 0, None elsewhere."""
+        of JPEG byte strings on rank 0, None elsewhere; with raw=True the (reused) output arrays and
+        the sizes instead, without copying them into Python byte strings."""
         n = len(stripe_ptrs)
         a = (C.c_void_p * n)(*stripe_ptrs)
         if self.rank == 0:
@@ -317,6 +318,8 @@ class NcclStripeEncoder:
             raise SjpegB200Error("sjb_stripes_encode rc=%d %s" % (rc, lib().sjb_last_error(self.ctx._ctx)))
         if self.rank != 0:
             return None
+        if raw:
+            return outs, [int(sizes[i]) for i in range(n)]
         return [outs[i][:sizes[i]].tobytes() for i in range(n)]
 
     def gather_frames(self, dev_ptrs, sizes, blob_capacity):

@@ -111,6 +111,8 @@ struct Stats {
 }  // namespace
 
 extern "C" {
+static void AnalyseDeviceForm(const int32_t* counts, int nb_comps, uint8_t quant[2][64], const uint8_t min_quant[2][64],
+                              int qdl, int qdc);
 
 // raw (unquantised, natural order) coefficients of the whole picture
 void emul_coeffs(const uint8_t* pix, int w, int h, long long stride, int mode, int fmt, int16_t* out) {
@@ -157,8 +159,21 @@ size_t emul_encode(const uint8_t* pix, int w, int h, long long stride, int mode,
         if (a < 128) ++counts[(m * 64 + i) * kHistoStride + a];
       }
     }
-    AnalyseHistograms(counts.data(), g.nb_comps, quant, minq, qdl, qdc);
-    for (int i = (g.nb_comps > 1 ? 1 : 0); i >= 0; --i) if (!FinalizeQuantizer(quant[i], minq[i], q_bias, &qt.m[i])) return 0;
+    // the analysis in the form the device runs (block_ops.cuh aq_*), cross-checked against the host form
+    uint8_t quant_host[2][64];
+    memcpy(quant_host, quant, 128);
+    AnalyseHistograms(counts.data(), g.nb_comps, quant_host, minq, qdl, qdc);
+    AnalyseDeviceForm(counts.data(), g.nb_comps, quant, minq, qdl, qdc);
+    if (memcmp(quant, quant_host, 128) != 0) return 0;
+    for (int i = (g.nb_comps > 1 ? 1 : 0); i >= 0; --i) {
+      if (!FinalizeQuantizer(quant[i], minq[i], q_bias, &qt.m[i])) return 0;
+      const int zz[64] = SJB_ZIGZAG_INIT;
+      for (int z = 0; z < 64; ++z) {       // the device's form of the same constants
+        int32_t iq, cpos;
+        if (!aq_finalize_entry(quant[i][zz[z]], zz[z] == 0, q_bias, &iq, &cpos)) return 0;
+        if (iq != qt.m[i].e[z][0] || cpos != qt.m[i].e[z][1]) return 0;
+      }
+    }
   }
   // rate model of the trellis = code lengths of the DEFAULT AC tables (enc.cc:334)
   uint8_t default_len[2][256];
@@ -243,6 +258,61 @@ size_t emul_encode(const uint8_t* pix, int w, int h, long long stride, int mode,
 }
 
 void emul_free(uint8_t* p) { free(p); }
+
+// The analysis as the DEVICE runs it (kernels.cu: analyse_fit_kernel + analyse_pick_kernel), from the
+// same block_ops.cuh functions and in the same decomposition: per position four partial sums over
+// quarters of the bins, the fits in candidate order, the positions' terms added in ascending order,
+// then the pick.  quant is left UNCLAMPED (the clamp to min_quant belongs to FinalizeQuantizer).
+static void AnalyseDeviceForm(const int32_t* counts, int nb_comps, uint8_t quant[2][64], const uint8_t min_quant[2][64],
+                              int qdl, int qdc) {
+  for (int idx = (nb_comps > 1) ? 1 : 0; idx >= 0; --idx) {
+    static AqFit fit[64];
+    const int delta_top = (idx == 0 ? qdl : qdc) - kAqDeltaMin;
+    for (int pos = 0; pos < 64; ++pos) {
+      AqFit* out = &fit[pos];
+      out->skip = 0;
+      if (pos == 0 || pos == 1 || pos == 8) { out->skip = 1; continue; }
+      const int32_t* h = counts + (static_cast<size_t>(idx) * 64 + pos) * kHistoStride;
+      int total = 0, last = 0;
+      for (int i = 0; i < kAqBins; ++i) {
+        total += h[i];
+        if (h[i]) last = i + 1;
+      }
+      if (total < 0.5 * last) { out->skip = 1; continue; }
+      const int q0 = quant[idx][pos], qmin = min_quant[idx][pos];
+      long long bits[kAqNumDelta], dist[kAqNumDelta];
+      for (int d = 0; d < kAqNumDelta; ++d) {
+        bits[d] = dist[d] = 0;
+        if (!aq_candidate_used(q0, qmin, delta_top, d)) continue;
+        for (int quarter = 0; quarter < 4; ++quarter) {
+          long long bs = 0, ds = 0;
+          aq_bin_sums(h, quarter * 32, std::min(last, quarter * 32 + 32), q0 + d + kAqDeltaMin, &bs, &ds);
+          bits[d] += bs;
+          dist[d] += ds;
+        }
+      }
+      aq_fit_position(bits, dist, q0, qmin, delta_top, out);
+    }
+    double num = 0., den = 0.;
+    for (int pos = 0; pos < 64; ++pos) {
+      if (fit[pos].skip) continue;
+      num += fit[pos].cov;
+      den += fit[pos].den;
+    }
+    const double lambda = aq_lambda(num, den);
+    for (int pos = 0; pos < 64; ++pos) {
+      if (!fit[pos].skip) quant[idx][pos] = static_cast<uint8_t>(quant[idx][pos] + aq_best_delta(fit[pos], delta_top, lambda));
+    }
+  }
+}
+void emul_analyse_histo_device_form(const int32_t* counts, int nb_comps, uint8_t* quant /*[2][64]*/, const uint8_t* min_quant,
+                                    int qdl, int qdc) {
+  uint8_t q[2][64], mq[2][64];
+  memcpy(q, quant, 128);
+  memcpy(mq, min_quant, 128);
+  AnalyseDeviceForm(counts, nb_comps, q, mq, qdl, qdc);
+  memcpy(quant, q, 128);
+}
 
 // host_codec.cc::AnalyseHistograms on its own (the product's restatement of histogram.cc:126-315)
 void emul_analyse_histo(const int32_t* counts, int nb_comps, uint8_t* quant /*[2][64]*/, const uint8_t* min_quant,

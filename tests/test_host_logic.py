@@ -34,6 +34,7 @@ def emul():
     E.emul_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p]
     E.emul_sharp_yuv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
     E.emul_analyse_histo.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    E.emul_analyse_histo_device_form.argtypes = E.emul_analyse_histo.argtypes
     E.emul_riskiness.restype = C.c_int
     E.emul_riskiness.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.POINTER(C.c_float)]
     return E
@@ -214,6 +215,10 @@ def test_histogram_analysis_equals_oracle_on_hard_histograms(emul):
                     lib.sjo_analyse_histo(C.c_void_p(c32.ctypes.data), comps, C.c_void_p(b.ctypes.data),
                                           C.c_void_p(minq.ctypes.data), qdl, qdc)
                     assert a.tobytes() == b.tobytes(), (trial, quant_kind, qdl, qdc, comps)
+                    # the form the DEVICE runs (block_ops.cuh aq_*, decomposed like the kernels)
+                    d = np.ascontiguousarray(quant.copy())
+                    emul.emul_analyse_histo_device_form(c32.ctypes.data, comps, d.ctypes.data, minq.ctypes.data, qdl, qdc)
+                    assert d.tobytes() == b.tobytes(), ("device form", trial, quant_kind, qdl, qdc, comps)
                     cases += 1
     assert cases == 160 * 3 * 5 * 2
 
