@@ -1149,13 +1149,18 @@ namespace {
 // slower than the kernels consume them: small groups start computing as soon as their pictures
 // have landed and leave a short tail after the last copy.  Device-resident batches use the
 // large groups that suit the kernels.
-int HostBatchGroup() {
-  static const int v = [] {
+// Measured (B200, pinned host memory, Gpix/s): 16 x 4K  group 1/2/4/8 = 18.06/18.02/17.89/17.67 (m0),
+// 17.81/17.68/17.58/17.21 (m4); 64 x 1080p = 17.30/17.41/17.43/17.33 (m0), 12.5/15.2/17.0/16.8 (m4: a
+// group of two small pictures does not cover the host phase of the optimised tables).  So: two large
+// pictures or four small ones per group.  SJB_HOST_BATCH_GROUP overrides.
+int HostBatchGroup(const Plan& plan) {
+  static const int forced = [] {
     const char* e = getenv("SJB_HOST_BATCH_GROUP");
-    const int x = e ? atoi(e) : 2;
-    return x > 0 ? x : 2;
+    const int x = e ? atoi(e) : 0;
+    return x > 0 ? x : 0;
   }();
-  return v;
+  if (forced) return forced;
+  return (static_cast<long long>(plan.g.width) * plan.g.height <= (4LL << 20)) ? 4 : 2;
 }
 
 // The batch pipeline over the context's lanes, independent of where the pictures come from:
@@ -1402,7 +1407,7 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
   Plan plan;
   RC(MakePlan(width, height, stride, params, &plan));
   if (n == 0) return SJB_OK;
-  const int B = std::max(1, std::min(pix_on_device ? plan.group : std::min(plan.group, HostBatchGroup()), n));
+  const int B = std::max(1, std::min(pix_on_device ? plan.group : std::min(plan.group, HostBatchGroup(plan)), n));
   if (!pix_on_device) {
     const int groups = (n + B - 1) / B;
     for (int l = 0; l < std::min<int>(kMaxLanes, groups); ++l) {
@@ -1454,7 +1459,7 @@ int sjb_encode_planar_batch(sjb_context* ctx, int n, const uint8_t* const* y, lo
   RC(MakePlan(width, height, 3LL * width, &p, &plan));
   if (n == 0) return SJB_OK;
   CU(cudaSetDevice(ctx->device));
-  const int B = std::max(1, std::min(on_device ? plan.group : std::min(plan.group, HostBatchGroup()), n));
+  const int B = std::max(1, std::min(on_device ? plan.group : std::min(plan.group, HostBatchGroup(plan)), n));
   const size_t ypitch = (static_cast<size_t>(width) + 15) & ~size_t(15);
   const size_t crow = static_cast<size_t>(mode == SJB_YUV_420 ? uv_step : 1) * cw;
   const size_t cpitch = (crow + 15) & ~size_t(15);
