@@ -34,6 +34,13 @@ using namespace sjb;
 
 namespace {
 
+// Concurrent sharp conversions of a batch.  A 4K conversion is 4 iterations x a cluster of 4 CTAs = 16 SMs
+// of 148 and is bound by its row latency, so more of them in flight is free: 16 x 4K, device-resident,
+// 10.8 ms with 4 at a time, 6.2 ms with 8 (21.6 Gpix/s, above what PCIe delivers).
+#ifndef SJB_SHARP_STREAMS
+#define SJB_SHARP_STREAMS 8
+#endif
+enum { kSharpStreams = SJB_SHARP_STREAMS };
 enum { kMaxLanes = 4, kHeaderReserve = 2048, kWorstBitsPerBlock = 1696, kHeadCopyBytes = 1 << 20 };
 // Pictures per launch = this budget / coefficient bytes per picture (at most kMaxGroup = 16): 16
 // pictures at 4K and 1080p, 4 at 8K.  Measured at 4K: 8 pictures per launch against 4 shortened the
@@ -150,8 +157,8 @@ struct sjb_context {
   DeviceBuffer sharp_scratch, sharp_planes, sharp_tabs, risk_table, risk_sums;
   // batches in AUTO / SHARP mode: every picture resident, planes of the SHARP subset, one scratch + stream per
   // concurrent conversion
-  DeviceBuffer batch_pix, batch_planes, sharp_scratch_n[4];
-  cudaStream_t sharp_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  DeviceBuffer batch_pix, batch_planes, sharp_scratch_n[kSharpStreams];
+  cudaStream_t sharp_stream[kSharpStreams] = {};
   size_t risk_host_cap = 0;                  // unsigned long longs in risk_host
   unsigned long long* risk_host = nullptr;   // pinned, 3 sums
   int risk_table_version = 0;                // version of the process-wide table held in risk_table
@@ -1046,10 +1053,10 @@ void sjb_context_destroy(sjb_context* ctx) {
   cudaSetDevice(ctx->device);
   for (auto& L : ctx->lanes) DestroyLane(&L);
   for (DeviceBuffer* b : {&ctx->sharp_scratch, &ctx->sharp_planes, &ctx->sharp_tabs, &ctx->risk_table, &ctx->risk_sums,
-                          &ctx->batch_pix, &ctx->batch_planes, &ctx->sharp_scratch_n[0], &ctx->sharp_scratch_n[1],
-                          &ctx->sharp_scratch_n[2], &ctx->sharp_scratch_n[3]}) {
+                          &ctx->batch_pix, &ctx->batch_planes}) {
     b->Release();
   }
+  for (auto& b : ctx->sharp_scratch_n) b.Release();
   for (auto& st : ctx->sharp_stream) if (st) cudaStreamDestroy(st);
   if (ctx->risk_host) cudaFreeHost(ctx->risk_host);
   if (ctx->head_copy) cudaFreeHost(ctx->head_copy);
@@ -1252,10 +1259,9 @@ int EnsureScoreTable(sjb_context* ctx);
 // AUTO runs the riskiness analyser on every picture (one launch each, one wait for all the sums) and
 // the batch is then split by the mode each picture got: the 4:2:0 / 4:4:4 / 4:0:0 subsets go through
 // the ordinary batch pipeline from their device copies, the SHARP subset is converted -- up to
-// kSharpStreams pictures at a time, each conversion on its own stream with its own scratch, because a
+// kSharpStreams (8) pictures at a time, each conversion on its own stream with its own scratch, because a
 // single conversion only occupies a fifth of the SMs -- into planes that then go through the planar
 // 4:2:0 pipeline.
-enum { kSharpStreams = 4 };
 int EncodeBatchAutoOrSharp(sjb_context* ctx, int n, const uint8_t* const* pix, int pix_on_device, int width, int height,
                            long long stride, const sjb_params* params, uint8_t* const* out, int out_on_device,
                            size_t out_capacity, size_t* sizes) {
