@@ -277,7 +277,9 @@ int ReserveLane(sjb_context* ctx, Lane* L, const Plan& plan, int frames) {
   CU(L->coef.Reserve(f * coef_pitch * sizeof(int16_t)));
   CU(L->nzmask.Reserve(f * nb * sizeof(uint8_t) + 64));
   CU(L->words.Reserve(f * plan.stream_words * 4 + 64, true, &words_grew));   // zeroed once, then self-cleaning
-  CU(L->out.Reserve(f * plan.out_capacity, false, &out_grew));
+  // zeroed once at allocation: the head copy of a single encode (FinishSingle) reads a fixed 64 KB+ of the
+  // slot whatever the JPEG's size, and initcheck rightly flags reading bytes nobody ever wrote
+  CU(L->out.Reserve(f * plan.out_capacity, true, &out_grew));
   CU(L->state.Reserve(f * (plan.nb_tiles + plan.ff_tiles) * sizeof(unsigned long long)));
   if (plan.trellis) CU(L->perm.Reserve(f * nb * sizeof(uint32_t)));
   GroupBuffers& gb = L->gb;

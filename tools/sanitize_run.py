@@ -17,6 +17,17 @@ sizes = ctx.encode_batch([f.ctypes.data for f in frames], False, 320, 240, 960, 
                          [o.ctypes.data for o in outs], False, 1 << 18)
 for f, o, s in zip(frames, outs, sizes):
     ok &= o[:s].tobytes() == O.oracle_encode(f, 320, 240, 960, 75.0, 0, S.YUV_420)
+# batches of several pictures per launch at the adaptive / trellis methods (A1 analysis kernels with
+# gridDim.z > 1, per-picture tables), device-resident groups, a planar batch on the bulk-copy F1
+import torch
+framesA = [O.make_rgb("A", 320, 240, 40 + f) for f in range(5)]
+for method, mode in ((4, S.YUV_420), (7, S.YUV_420), (3, S.YUV_444), (6, S.YUV_400)):
+    dev = [torch.from_numpy(f.reshape(-1)).cuda() for f in framesA]
+    douts = [torch.zeros(1 << 18, dtype=torch.uint8, device="cuda") for _ in framesA]
+    sizes = ctx.encode_batch([t.data_ptr() for t in dev], True, 320, 240, 960, S.default_params(75, method, mode),
+                             [t.data_ptr() for t in douts], True, 1 << 18)
+    for f, o, s in zip(framesA, douts, sizes):
+        ok &= bytes(o[:s].cpu().numpy()) == O.oracle_encode(f, 320, 240, 960, 75.0, method, mode)
 # whole-picture passes: sharp conversion (cluster of 2 CTAs at 1100 px), AUTO with the score table
 for (w, h) in ((66, 34), (1100, 20)):
     rgb = O.make_rgb("A", w, h)
