@@ -265,6 +265,45 @@ def run_config(ctx, name, gen, w, h, q, m, mode, nframes, peak, cpu_seconds):
     }
 
 
+def run_dropin_threads(frames, want0, nthreads=8, seconds=1.5):
+    """The reference's own entry point, SjpegEncode(), called concurrently from T host threads on
+    pageable 4K frames (one lazily created GPU context per thread, sjpeg_api.cc): what a program gets
+    that relinks against this library without touching its code.  Whole-call throughput, host to host."""
+    import sjpeg_b200 as S
+    ok = [True] * nthreads
+    done = [0] * nthreads
+    gate = threading.Barrier(nthreads + 1)
+    until = [0.0]
+
+    def work(t):
+        # warm-up on the SAME thread that is timed: its context, lane and staging ring are thread-local
+        for i in range(3):
+            S.sjpeg_encode(frames[(t + i) % len(frames)], W, H, 3 * W, QUALITY, METHOD, S.YUV_420)
+        gate.wait(timeout=120)
+        i = t
+        while time.perf_counter() < until[0]:
+            got = S.sjpeg_encode(frames[i % len(frames)], W, H, 3 * W, QUALITY, METHOD, S.YUV_420)
+            if i % len(frames) == 0 and got != want0:
+                ok[t] = False
+            done[t] += 1
+            i += 1
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    for t in ths:
+        t.start()
+    until[0] = time.perf_counter() + 3600.0
+    gate.wait(timeout=120)
+    t0 = time.perf_counter()
+    until[0] = t0 + seconds
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    n = sum(done)
+    return {"config": "drop-in SjpegEncode(), 4K gen B q75 420 m0, pageable host memory, %d concurrent host threads" % nthreads,
+            "bit_exact_vs_reference": all(ok), "calls": n, "e2e_mpix_s": round(n * W * H / dt / 1e6, 1),
+            "ms_per_call_per_thread": round(1e3 * dt * nthreads / max(n, 1), 3)}
+
+
 def run_config5(ctx, rank, world, dist, barrier):
     """BASELINE.json configs[4]: 64 x 1080p, as frames (each rank its own pictures) and as row stripes
     (every picture split across the ranks; NCCL exchange inside the library, JPEGs complete on rank 0)."""
@@ -572,6 +611,11 @@ def run_ours(args):
                     configs.append(run_config(ctx, *cfg, peak=peak, cpu_seconds=2.0))
                 except Exception as e:
                     configs.append({"config": cfg[0], "content": "gen " + cfg[1], "error": "%s: %s" % (type(e).__name__, e)})
+            try:
+                for nt in (1, 8):
+                    configs.append(run_dropin_threads(frames[:4], want, nthreads=nt))
+            except Exception as e:
+                configs.append({"config": "drop-in SjpegEncode() threads", "error": "%s: %s" % (type(e).__name__, e)})
 
     line = {
         "metric": "Mpixels/sec encode (4K RGB q75 yuv420)", "value": round(value, 1), "unit": "Mpix/s",
