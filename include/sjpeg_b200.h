@@ -275,7 +275,7 @@ int sjb_last_timings(const sjb_context* ctx, float ms[3]);
 
 /* Per-kernel-stage times (ms, CUDA events recorded right before and after each stage's launches) of
  * the last TIMED group on the context's first lane -- the group of a single sjb_encode, or the last
- * lane-0 group of sjb_bench_device: [0] F1, [1] H1 histogram, [2] Q1 re-quantise or T1 trellis
+ * lane-0 group of sjb_bench_device: [0] F1, [1] H1 histogram, [2] A1 histogram analysis + Q1 re-quantise or T1 trellis
  * (incl. its block sort), [3] S1 symbol statistics, [4] E entropy coder, [5] S byte stuffing;
  * -1 for a stage the method does not run.  *frames = pictures in that group (one launch each). */
 int sjb_last_stage_timings(sjb_context* ctx, float ms[6], int* frames);

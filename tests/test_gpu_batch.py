@@ -159,7 +159,7 @@ def test_batch_error_leaves_no_copies_in_flight(gpu_ctx):
 def test_native_stripe_session_single_rank(gpu_ctx, method):
     """sjb_stripes_encode with a one-rank NCCL communicator: the whole stream-ordered sequence
     (all-reduce of histograms / symbol counts, all-gathers, offsets, stuffing, compaction, assembly)
-    runs with degenerate collectives; 11 pictures = groups of 8 + 3.  Multi-rank runs: bench.py
+    runs with degenerate collectives; 11 pictures = one chunk, 37 = three.  Multi-rank runs: bench.py
     --gpus N (config 5) and tools/stripes_nccl.py."""
     import sjpeg_b200 as S
     from sjpeg_b200 import distributed as D
@@ -173,6 +173,14 @@ def test_native_stripe_session_single_rank(gpu_ctx, method):
             got = enc.encode([f.ctypes.data for f in frames], False, w, h, 3 * w, p, 1 << 20)
             for i, f in enumerate(frames):
                 assert got[i] == O.oracle_encode(f, w, h, 3 * w, float(q), method, mode), (w, h, mode, method, i)
+        # several chunks (one group of 16 pictures each, pipelined: the next chunk's uploads are queued before
+        # this chunk's exchange): 37 pictures = 16 + 16 + 5, outputs left in the encoder's host buffers
+        w, h = 203, 117
+        frames = [_frame(["A", "B", "noise", "flat"][i % 4], w, h, 700 + i) for i in range(37)]
+        p = S.default_params(75, method, S.YUV_420)
+        outs, sizes = enc.encode([f.ctypes.data for f in frames], False, w, h, 3 * w, p, 1 << 18, raw=True)
+        for i, f in enumerate(frames):
+            assert outs[i][:sizes[i]].tobytes() == O.oracle_encode(f, w, h, 3 * w, 75.0, method, S.YUV_420), (method, i)
         # the context still encodes whole pictures afterwards
         rgb = O.make_rgb("A", 320, 200)
         assert gpu_ctx.encode(rgb, 320, 200, 960, S.default_params(75, 4, S.YUV_420)) == \
