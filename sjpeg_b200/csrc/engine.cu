@@ -355,10 +355,9 @@ int UploadPicture(sjb_context* ctx, Lane* L, const uint8_t* pix, const Plan& pla
     // one contiguous span, stride kept (sign included)
     const size_t span = static_cast<size_t>(astride) * (h - 1) + row_bytes;
     bool staged = false;
-    // Waking the helper threads costs ~0.1 ms: worth it from 4K pictures up for a lone call, from
-    // 4 MB up when the uploads of a batch follow each other (measured: 1080p alone 0.45 ms through
-    // the driver vs 0.54 ms staged; 64 x 1080p in a batch 3.0 vs 6.6 Gpix/s; 8K alone 9.0 vs 3.6 ms).
-    const size_t min_bytes = ctx->many_uploads ? HostStager::kMinBytes : 4 * HostStager::kMinBytes;
+    // From 4 MB up (below, the driver's own pageable path is as good).  Until the helper threads stayed
+    // awake between uploads a lone call only paid off from 4K pictures up: waking them cost ~0.25 ms.
+    const size_t min_bytes = HostStager::kMinBytes;
     if (span >= min_bytes && StagerEnabled()) {
       // malloc()ed memory (the normal case behind SjpegEncode): copy out through the pinned ring
       // with helper threads instead of the driver's single-threaded pageable path

@@ -28,11 +28,27 @@ namespace sjb {
 
 class HostStager {
  public:
-  // 3 helpers + the caller; 5 and 7 helpers measured slower at 4K (1.2 -> 1.4 -> 1.6 ms: more threads to wake)
-  enum { kHelpers = 3, kSlots = 4 };
-  static constexpr size_t kChunk = 2u << 20;       // bytes per pinned slot
-  static constexpr size_t kPiece = 128u << 10;     // unit of work claimed by a thread
+  // 3 helpers + the caller; 5 and 7 helpers measured slower at 4K (more threads to wake, more contention on the
+  // source's memory channels).  tools/micro/stager_bench.cu, 4K picture, uploads 0.25 ms apart: 2 MB chunks / 128 KB
+  // pieces / helpers asleep between uploads 0.91-0.96 ms (26-27 GB/s); helpers awake 0.61 ms (40 GB/s); 4 MB chunks /
+  // 256 KB pieces 0.575 ms (43 GB/s); the same from pinned memory 0.458 ms, through the driver's pageable path 1.2 ms.
+#ifndef SJB_STAGER_HELPERS
+#define SJB_STAGER_HELPERS 3
+#endif
+#ifndef SJB_STAGER_CHUNK_KB
+#define SJB_STAGER_CHUNK_KB 4096
+#endif
+#ifndef SJB_STAGER_PIECE_KB
+#define SJB_STAGER_PIECE_KB 256
+#endif
+  enum { kHelpers = SJB_STAGER_HELPERS, kSlots = 4 };
+  static constexpr size_t kChunk = static_cast<size_t>(SJB_STAGER_CHUNK_KB) << 10;   // bytes per pinned slot
+  static constexpr size_t kPiece = static_cast<size_t>(SJB_STAGER_PIECE_KB) << 10;   // unit of work claimed by a thread
   static constexpr size_t kMinBytes = 4u << 20;    // below this the driver's own path is as good
+#ifndef SJB_STAGER_GRACE_US
+#define SJB_STAGER_GRACE_US 1000
+#endif
+  enum { kGraceUs = SJB_STAGER_GRACE_US };          // how long the helpers stay awake after an upload
 
   HostStager() = default;
   ~HostStager();
