@@ -12,6 +12,7 @@ python tools/batch_methods.py A 16 >> $O/batch_methods.txt 2>&1
 python tools/planar_bench.py > $O/planar.txt 2>&1
 python tools/sharp_bench.py > $O/sharp.txt 2>&1
 python tools/sharp_batch.py > $O/sharp_batch.txt 2>&1
+python tools/pageable_batch.py > $O/pageable_batch.txt 2>&1
 # launch list of the bench command (headline part)
 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 300 --csv --log-file $O/launches_bench.csv \
     python bench.py --quick --steps 2 --warmup 3 > $O/bench_under_ncu.log 2>&1
