@@ -740,7 +740,10 @@ histogram_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   // lane: 140 us per 16 4K pictures with 256, 512 or 640 threads per CTA alike, the same for the
   // sparse and the noisy picture, and SLOWER (174 us) when the lanes whose value falls into bins 0..3
   // -- half of them on a photographic picture -- were counted in registers instead and predicated off
-  // the atomic: the instruction count went up and the number of ATOMS instructions stayed.
+  // the atomic: the instruction count went up and the number of ATOMS instructions stayed.  Bank
+  // conflicts are not it either: with the rows reordered so that the 32 lanes of an instruction own 32
+  // consecutive rows (32 different banks for equal bins; rows 2l put lanes l and l + 16 on one bank) the
+  // kernel took 145.4 us against 144.4.
   for (; g0 < full_end; g0 += step) {
     const int16_t* p = base + (static_cast<size_t>(g0 >> 2) << 8);
     uint32_t w[8];
