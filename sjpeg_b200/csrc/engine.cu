@@ -174,7 +174,6 @@ struct sjb_context {
   size_t head_valid = 0;                     // bytes of lane 0's out slot 0 mirrored in head_copy
   HostStager stager;                         // threaded upload of pageable pictures (host_stager.h)
   HostPool pool;                             // per-picture host analysis of a group, in parallel (host_pool.h)
-  bool many_uploads = false;                 // set by the batch / stripe entry points: uploads come back to back
 };
 
 namespace {
@@ -311,12 +310,6 @@ int ReserveLane(sjb_context* ctx, Lane* L, const Plan& plan, int frames) {
   return SJB_OK;
 }
 
-struct ManyUploads {     // scope guard for sjb_context::many_uploads
-  sjb_context* ctx;
-  bool before;
-  ManyUploads(sjb_context* c, bool on) : ctx(c), before(c->many_uploads) { c->many_uploads = on; }
-  ~ManyUploads() { ctx->many_uploads = before; }
-};
 
 bool StagerEnabled() {
   static const bool on = [] {
@@ -1405,7 +1398,6 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
   ctx->lanes[0].last_size = 0;
   for (int i = 0; i < n; ++i) if (pix[i] == nullptr) return SJB_ERR_ARG;
   CU(cudaSetDevice(ctx->device));
-  const ManyUploads back_to_back(ctx, n > 1);
   if (params->yuv_mode == SJB_YUV_AUTO || params->yuv_mode == SJB_YUV_SHARP) {
     if (n == 0) return SJB_OK;
     return EncodeBatchAutoOrSharp(ctx, n, pix, pix_on_device, width, height, stride, params, out, out_on_device,
@@ -2151,7 +2143,6 @@ int sjb_stripes_transform(sjb_stripes* s, const uint8_t* const* pix, int pix_on_
   s->plan = plan;
   s->stride = stride;
   CU(cudaSetDevice(ctx->device));
-  const ManyUploads back_to_back(ctx, s->n > 1);
   const int groups = (s->n + kMaxGroup - 1) / kMaxGroup;
   while (static_cast<int>(s->sets.size()) < groups) {
     Lane* L = new (std::nothrow) Lane();

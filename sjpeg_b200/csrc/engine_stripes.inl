@@ -199,7 +199,6 @@ int sjb_stripes_encode(sjb_comm* comm, int n, const uint8_t* const* pix, int pix
   if (active) RC(MakePlan(width, hs, stride, params, &plan));
   (void)pstep;
   CU(cudaSetDevice(ctx->device));
-  const ManyUploads back_to_back(ctx, n > 1);
   cudaStream_t st = comm->stream;
   const int groups = (n + kMaxGroup - 1) / kMaxGroup;
   while (static_cast<int>(comm->sets.size()) < groups) {
