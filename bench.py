@@ -214,8 +214,8 @@ def run_config(ctx, name, gen, w, h, q, m, mode, nframes, peak, cpu_seconds):
     dev = [torch.from_numpy(f.reshape(-1)).cuda() for f in frames]
     ptrs = [t.data_ptr() for t in dev]
     p = S.default_params(q, m, mode)
-    ctx.bench_device(ptrs, w, h, 3 * w, p, 4)
-    iters = 5
+    ctx.bench_device(ptrs, w, h, 3 * w, p, 8)
+    iters = 6
     total_ms = min(ctx.bench_device(ptrs, w, h, 3 * w, p, iters)[0] for _ in range(2))
     exact = all(ctx.bench_output(i) == want[i] for i in range(nframes))
     _, fpl = ctx.last_stage_timings()
@@ -460,11 +460,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident value ------------------------------------------------------------
-    # warm-up: W steps (at least 4) in ONE call, so that the groups rotate over all four lanes as they do
-    # in the timed call -- one-step calls only ever touch lane 0 and leave the first use of the other
-    # lanes' buffers (a 660 MB memset of the bit-stream words each, table and header uploads) inside
-    # the timed region: 443 instead of 475 Gpix/s
-    ctx.bench_device(dev_ptrs, W, H, 3 * W, params, max(args.warmup, 4))
+    # warm-up: W steps (at least 8) in ONE call, so that the groups rotate over all the context's lanes
+    # (six) as they do in the timed call -- one-step calls only ever touch lane 0 and leave the first use
+    # of the other lanes' buffers (a 660 MB memset of the bit-stream words each, table and header
+    # uploads) inside the timed region: 443 instead of 475 Gpix/s
+    ctx.bench_device(dev_ptrs, W, H, 3 * W, params, max(args.warmup, 8))
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
@@ -628,7 +628,7 @@ def run_ours(args):
                    "outputs_verified": "all %d outputs of the timed loop's last round, fetched from HBM, == oracle" % n,
                    "md5_of_md5s_rank0": digest_of_digests, "parallelism": "frames sharded across ranks, no collective",
                    "numa_binding_rank0": numa,
-                   "warmup_steps_run": max(args.warmup, 4)},
+                   "warmup_steps_run": max(args.warmup, 8)},
         "e2e": {"value": round(e2e_value, 1), "unit": "Mpix/s", "h2d_bytes_per_step": n * 3 * W * H,
                 "d2h_bytes_per_step": int(sum(sizes)), "api": "sjb_encode_batch, pinned host input, host output",
                 "h2d_gbs_achieved": round(n * 3 * W * H * args.steps * world / float(t.item()) / 1e9 / world, 2),

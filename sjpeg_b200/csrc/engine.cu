@@ -41,7 +41,16 @@ namespace {
 #define SJB_SHARP_STREAMS 8
 #endif
 enum { kSharpStreams = SJB_SHARP_STREAMS };
-enum { kMaxLanes = 4, kHeaderReserve = 2048, kWorstBitsPerBlock = 1696, kHeadCopyBytes = 1 << 20 };
+// Lanes (stream + scratch of one group) per context.  16-frame 4K device pipeline, gen B: 2 lanes 464, 4 lanes
+// 477, 6 lanes 487, 8 lanes 490 Gpix/s (gen A 223 / 222 / 228 / 227): the tail of one group's kernels overlaps
+// the head of the next ones'.  Lanes are only allocated when a batch has that many groups.
+#ifndef SJB_MAX_LANES
+#define SJB_MAX_LANES 6
+#endif
+// Batches that arrive from host memory keep to four: their uploads share the link, and with six streams
+// copying at once every group's pixels land later (e2e 16 x 4K 18.0 -> 16.8 Gpix/s with six).
+enum { kHostLanes = 4 };
+enum { kMaxLanes = SJB_MAX_LANES, kHeaderReserve = 2048, kWorstBitsPerBlock = 1696, kHeadCopyBytes = 1 << 20 };
 // Pictures per launch = this budget / coefficient bytes per picture (at most kMaxGroup = 16): 16
 // pictures at 4K and 1080p, 4 at 8K.  Measured at 4K: 8 pictures per launch against 4 shortened the
 // tail of the F1 grid (6.8 instead of 3.4 waves of CTAs: 13.8 -> 12.6 us per picture) and amortised
@@ -166,7 +175,7 @@ struct sjb_context {
   // fetched (sjb_bench_output) while no later group has reused its lane
   struct BenchSlot { int lane, slot, turn; };
   std::vector<BenchSlot> bench_slots;
-  int bench_last_turn[4] = {-1, -1, -1, -1};
+  int bench_last_turn[kMaxLanes];
   // Size queries (sjb_encode with out == NULL, what the drop-in facade does) copy the head of the
   // JPEG into this pinned buffer in the same stream as the sizes, so that a typical file needs one
   // synchronisation and no second device-to-host copy (sjb_fetch_output reads it from here).
@@ -1176,9 +1185,9 @@ int HostBatchGroup(const Plan& plan) {
 // while the uploads and kernels of the younger ones are already queued.
 template <class Fill>
 int RunBatch(sjb_context* ctx, const Plan& plan, long long stride, int n, int B, Fill fill, const int* index,
-             uint8_t* const* out, int out_on_device, size_t out_capacity, size_t* sizes) {
+             uint8_t* const* out, int out_on_device, size_t out_capacity, size_t* sizes, int max_lanes = kMaxLanes) {
   const int groups = (n + B - 1) / B;
-  const int nl = std::min<int>(kMaxLanes, std::max(1, groups));
+  const int nl = std::min<int>(std::min<int>(kMaxLanes, max_lanes), std::max(1, groups));
   for (int l = 0; l < nl; ++l) {
     RC(InitLane(ctx, &ctx->lanes[l]));
     RC(ReserveLane(ctx, &ctx->lanes[l], plan, B));
@@ -1409,7 +1418,7 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
   const int B = std::max(1, std::min(pix_on_device ? plan.group : std::min(plan.group, HostBatchGroup(plan)), n));
   if (!pix_on_device) {
     const int groups = (n + B - 1) / B;
-    for (int l = 0; l < std::min<int>(kMaxLanes, groups); ++l) {
+    for (int l = 0; l < std::min<int>(kHostLanes, groups); ++l) {
       RC(InitLane(ctx, &ctx->lanes[l]));
       RC(ReservePix(ctx, &ctx->lanes[l], plan, stride, B));
     }
@@ -1425,7 +1434,8 @@ int sjb_encode_batch(sjb_context* ctx, int n, const uint8_t* const* pix, int pix
     }
     return SJB_OK;
   };
-  return RunBatch(ctx, plan, stride, n, B, fill, nullptr, out, out_on_device, out_capacity, sizes);
+  return RunBatch(ctx, plan, stride, n, B, fill, nullptr, out, out_on_device, out_capacity, sizes,
+                  pix_on_device ? kMaxLanes : kHostLanes);
 } SJB_NOTHROW_END
 
 // A batch of planar / semi-planar pictures of one geometry (sjb_encode_planar for the layouts):
@@ -1466,7 +1476,7 @@ int sjb_encode_planar_batch(sjb_context* ctx, int n, const uint8_t* const* y, lo
   const size_t slot = (ybytes + 2 * cbytes + 255) & ~size_t(255);
   if (!on_device) {
     const int groups = (n + B - 1) / B;
-    for (int l = 0; l < std::min<int>(kMaxLanes, groups); ++l) {
+    for (int l = 0; l < std::min<int>(kHostLanes, groups); ++l) {
       RC(InitLane(ctx, &ctx->lanes[l]));
       CU(ctx->lanes[l].pix.Reserve(slot * B));
     }
@@ -1501,7 +1511,8 @@ int sjb_encode_planar_batch(sjb_context* ctx, int n, const uint8_t* const* y, lo
     }
     return SJB_OK;
   };
-  return RunBatch(ctx, plan, y_stride, n, B, fill, nullptr, out, out_on_device, out_capacity, sizes);
+  return RunBatch(ctx, plan, y_stride, n, B, fill, nullptr, out, out_on_device, out_capacity, sizes,
+                  on_device ? kMaxLanes : kHostLanes);
 } SJB_NOTHROW_END
 
 }  // extern "C"
@@ -1987,6 +1998,7 @@ int sjb_bench_device(sjb_context* ctx, int n, const uint8_t* const* dev_pix, int
   CU(cudaEventRecord(t0, L0->stream));
   for (int l = 1; l < nl; ++l) CU(cudaStreamWaitEvent(ctx->lanes[l].stream, t0, 0));
   ctx->bench_slots.assign(n, sjb_context::BenchSlot{-1, -1, -1});
+  for (int& t : ctx->bench_last_turn) t = -1;
   std::vector<GroupJob> jobs(nl);
   for (int it = 0, turn = 0; it < iters; ++it) {
     for (int k = 0; k < groups; ++k, ++turn) {

@@ -25,7 +25,7 @@ for case in cases:
     dev = [torch.from_numpy(f.reshape(-1)).cuda() for f in frames]
     ptrs = [t.data_ptr() for t in dev]
     p = S.default_params(q, method, mode)
-    ctx.bench_device(ptrs, w, h, 3 * w, p, 3)
+    ctx.bench_device(ptrs, w, h, 3 * w, p, 8)
     iters = 6
     total_ms = min(ctx.bench_device(ptrs, w, h, 3 * w, p, iters)[0] for _ in range(3))
     ok = all(ctx.bench_output(i) == O.oracle_encode(frames[i], w, h, 3 * w, float(q), method, mode) for i in (0, n - 1))
