@@ -36,4 +36,11 @@ for t in memcheck racecheck synccheck initcheck; do
   echo "== $t" >> $O/sanitizer.txt
   timeout 600 compute-sanitizer --tool $t python tools/sanitize_run.py 2>&1 | grep -E "parity|ERROR SUMMARY|RACECHECK SUMMARY|hazard" | tail -5 >> $O/sanitizer.txt
 done
+# gpurun brings back at most 64 MiB: keep the raw-metric CSV of every report (what tools/ncu_summary.py needs)
+# and drop reports, least needed first, until the directory fits
+for r in $O/*_full.ncu-rep; do ncu -i $r --page raw --csv > ${r%.ncu-rep}_raw.csv 2>/dev/null; done
+for r in f1_planar f1_444 f1_420 m4 trellis; do
+  [ "$(du -sm gpurun_out | cut -f1)" -lt 56 ] && break
+  rm -f $O/${r}_full.ncu-rep
+done
 ls -la $O

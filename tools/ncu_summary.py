@@ -21,7 +21,10 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 def main():
     rep, command = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "")
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):          # the raw page exported on the GPU box (tools/collect_profiles.sh)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}

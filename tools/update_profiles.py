@@ -14,6 +14,8 @@ DST = os.path.join(ROOT, "profiles")
 def summary(name, command):
     rep = os.path.join(SRC, name + "_full.ncu-rep")
     if not os.path.exists(rep):
+        rep = os.path.join(SRC, name + "_full_raw.csv")      # report dropped on the box to fit gpurun's size limit
+    if not os.path.exists(rep):
         return None
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, command],
                          capture_output=True, text=True).stdout
