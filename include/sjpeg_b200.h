@@ -265,6 +265,11 @@ int sjb_stage_coefficients(sjb_context* ctx, const uint8_t* pix, int width, int 
 /* histogram.cc:99-108 over the whole picture: counts = int32[2][64][129] (host) */
 int sjb_stage_histogram(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
                         const sjb_params* params, int32_t* counts);
+/* histogram.cc:126-315 on the device (kernels A1) after the histogram above: the matrices the adaptive
+ * methods (3..8) put into the DQT segment for this picture, quant[2][64] in natural order, clamped to
+ * params->min_quant as FinalizeQuantizer does (quantize.cc:116-148) */
+int sjb_stage_adapted_matrices(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
+                               const sjb_params* params, uint8_t quant[2][64]);
 /* entropy.cc:208-227 over the whole picture for the plain quantiser: freq_ac[2][256], freq_dc[2][12] */
 int sjb_stage_symbol_stats(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
                            const sjb_params* params, uint32_t* freq_ac, uint32_t* freq_dc);

@@ -73,6 +73,8 @@ _SIGNATURES = {
                                          C.POINTER(Params), C.c_int, C.c_void_p, C.c_void_p]),
     "sjb_stage_histogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
                                       C.POINTER(Params), C.c_void_p]),
+    "sjb_stage_adapted_matrices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
+                                             C.POINTER(Params), C.c_void_p]),
     "sjb_stage_symbol_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
                                          C.POINTER(Params), C.c_void_p, C.c_void_p]),
     "sjb_last_stage_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 6), C.POINTER(C.c_int)]),
@@ -250,6 +252,14 @@ class Context:
                                        counts.ctypes.data)
         _check(self._ctx, rc, "sjb_stage_histogram")
         return counts
+
+    def adapted_matrices(self, pix, width, height, stride, params):
+        """the matrices kernels A1 derive from the picture's histogram (natural order, clamped to min_quant)"""
+        quant = np.zeros((2, 64), dtype=np.uint8)
+        rc = lib().sjb_stage_adapted_matrices(self._ctx, pix.ctypes.data, width, height, stride, C.byref(params),
+                                              quant.ctypes.data)
+        _check(self._ctx, rc, "sjb_stage_adapted_matrices")
+        return quant
 
     def symbol_stats(self, pix, width, height, stride, params):
         ac = np.zeros((2, 256), dtype=np.uint32)

@@ -1920,6 +1920,30 @@ int sjb_stage_histogram(sjb_context* ctx, const uint8_t* pix, int width, int hei
   return SJB_OK;
 } SJB_NOTHROW_END
 
+int sjb_stage_adapted_matrices(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
+                               const sjb_params* params, uint8_t quant[2][64]) try {
+  if (ctx == nullptr || pix == nullptr || quant == nullptr) return SJB_ERR_ARG;
+  Plan plan;
+  FrameSet fs;
+  RC(StageF1(ctx, pix, width, height, stride, params, true, &plan, &fs));
+  Lane* L = &ctx->lanes[0];
+  SmallLayout* D = L->d_small();
+  uint8_t quant0[2][64], min_quant[2][64];
+  QuantTabs qt;
+  if (!MakeQuantTabs(plan, quant0, min_quant, &qt)) return SJB_ERR_ARG;
+  CU(cudaMemsetAsync(D->hist, 0, sizeof(D->hist[0]), L->stream));
+  LaunchHistogram(fs, L->gb, L->stream);
+  AqParams ap;
+  FillAqParams(plan, quant0, min_quant, &ap);
+  LaunchAnalyseHistograms(1, L->gb, ap, &D->aq_fit[0][0][0], D->aq_fail, L->stream);
+  CU(cudaGetLastError());
+  int fail = 0;
+  CU(cudaMemcpyAsync(quant, D->quant, 128, cudaMemcpyDeviceToHost, L->stream));
+  CU(cudaMemcpyAsync(&fail, D->aq_fail, sizeof(int), cudaMemcpyDeviceToHost, L->stream));
+  CU(cudaStreamSynchronize(L->stream));
+  return fail ? SJB_ERR_ARG : SJB_OK;
+} SJB_NOTHROW_END
+
 int sjb_stage_symbol_stats(sjb_context* ctx, const uint8_t* pix, int width, int height, long long stride,
                            const sjb_params* params, uint32_t* freq_ac, uint32_t* freq_dc) try {
   if (ctx == nullptr || pix == nullptr || freq_ac == nullptr || freq_dc == nullptr) return SJB_ERR_ARG;

@@ -178,6 +178,42 @@ def test_stage_histogram_and_symbol_stats(gpu_ctx):
             assert np.array_equal(ac, want_ac) and np.array_equal(dc, want_dc)
 
 
+def test_stage_adapted_matrices(gpu_ctx):
+    """kernels A1 (histogram analysis on the device) against the oracle's restatement of
+    histogram.cc:126-315 on the oracle's own histogram: the matrices that go into the DQT, for
+    several pictures, sizes, qualities, modes, delta limits and minimum matrices"""
+    import sjpeg_b200 as S
+    rng = np.random.RandomState(11)
+    cases = 0
+    for (kind, w, h) in (("A", 203, 117), ("B", 512, 512), ("noise", 331, 203), ("A", 1920, 1080), ("B", 64, 48)):
+        rgb = rng.randint(0, 256, (h, w, 3)).astype(np.uint8) if kind == "noise" else O.make_rgb(kind, w, h)
+        for mode in (O.YUV_420, O.YUV_444, O.YUV_400):
+            nm, mb = _nb(w, h, mode)
+            coeffs = _oracle_coeffs(rgb, w, h, 3 * w, mode)
+            counts = np.zeros((2, 64, 129), np.int32)
+            O.oracle().sjo_collect_histograms(coeffs.ctypes.data, nm, mode, counts.ctypes.data)
+            for (q, qdl, qdc, tol) in ((75, 12, 1, 0), (30, 12, 12, 0), (93, 4, 0, 0), (50, 12, 1, 40), (98, 12, 6, 0)):
+                p = S.default_params(q, 4, mode)
+                p.qdelta_max_luma, p.qdelta_max_chroma = qdl, qdc
+                quant = np.array([list(p.quant[0]), list(p.quant[1])], np.uint8)
+                if tol:     # a restrictive minimum matrix (EncoderParam::SetMinQuantization style)
+                    minq = np.maximum(1, (quant.astype(np.int32) * (256 - tol)) >> 8).astype(np.uint8)
+                    for m in range(2):
+                        for i in range(64):
+                            p.min_quant[m][i] = int(minq[m, i])
+                else:
+                    minq = np.array([list(p.min_quant[0]), list(p.min_quant[1])], np.uint8)
+                want = np.ascontiguousarray(quant.copy())
+                O.oracle().sjo_analyse_histo(C.c_void_p(counts.ctypes.data), 1 if mode == O.YUV_400 else 3,
+                                             C.c_void_p(want.ctypes.data), C.c_void_p(minq.ctypes.data), qdl, qdc)
+                want = np.maximum(want, minq)           # FinalizeQuantizer's clamp (quantize.cc:116-148)
+                got = gpu_ctx.adapted_matrices(rgb, w, h, 3 * w, p)
+                rows = 1 if mode == O.YUV_400 else 2
+                assert np.array_equal(got[:rows], want[:rows]), (kind, w, h, mode, q, qdl, qdc, tol)
+                cases += 1
+    assert cases == 5 * 3 * 5
+
+
 GOLD_GPU = [c for c in GOLD["cases"]]
 
 
