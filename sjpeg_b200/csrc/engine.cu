@@ -265,6 +265,9 @@ int MakePlan(int width, int height, long long stride, const sjb_params* params, 
   plan->optimize = p.method != 0 && p.method != 3;
   plan->trellis = p.method >= 7;
   if (p.q_bias < 0 || p.q_bias > 255) return SJB_ERR_ARG;
+  // the candidate steps are q0 - 12 .. q0 + 12: the reference asserts the limits stay inside (histogram.cc:179-183)
+  // and indexes past its tables otherwise; here such settings are refused
+  if (p.qdelta_max_luma > 12 || p.qdelta_max_chroma > 12) return SJB_ERR_ARG;
   const size_t nb = plan->g.nb_blocks();
   plan->stream_words = ((nb * kWorstBitsPerBlock / 32 + 64) + 3) & ~static_cast<size_t>(3);
   plan->out_capacity = (kHeaderReserve + 2 * plan->stream_words * 4 + 16 + 255) & ~static_cast<size_t>(255);

@@ -146,6 +146,22 @@ def test_invalid_arguments_are_refused(gpu_ctx):
     assert a == b and c == d
 
 
+def test_delta_limits_beyond_the_candidate_range_are_refused(gpu_ctx):
+    """the adaptive analysis tries steps q0 - 12 .. q0 + 12; the reference asserts the limits stay
+    inside (histogram.cc:179-183) and reads past its tables otherwise: refused here"""
+    import sjpeg_b200 as S
+    rgb = O.make_rgb("A", 64, 48)
+    for (dl, dc) in ((13, 1), (12, 13), (100, 100)):
+        p = S.default_params(75, 4, S.YUV_420)
+        p.qdelta_max_luma, p.qdelta_max_chroma = dl, dc
+        assert gpu_ctx.encode(rgb, 64, 48, 192, p) is None          # SJB_ERR_ARG
+    p = S.default_params(75, 4, S.YUV_420)
+    p.qdelta_max_luma, p.qdelta_max_chroma = -20, -13        # nothing to try: the starting matrices are kept
+    got = gpu_ctx.encode(rgb, 64, 48, 192, p)
+    want = O.oracle_encode_params(rgb, 64, 48, 192, O.SjoParams.from_buffer_copy(bytes(p)))    # same layout
+    assert got == want
+
+
 def test_large_dimension_limits(gpu_ctx):
     """65535 is legal, 65536 is not (unit_test.cc:393-410)"""
     import sjpeg_b200 as S
