@@ -46,7 +46,7 @@ typedef struct sjb_params {
   int method;               /* 0..8, clamped (enc.cc:121-129)                              */
   int pix_fmt;              /* SJB_PIX_*                                                   */
   uint8_t quant[2][64];     /* luma / chroma matrices, natural order (Encoder::quants_[].quant_) */
-  uint8_t min_quant[2][64]; /* lower bounds (Encoder::quants_[].min_quant_), 1 = none      */
+  uint8_t min_quant[2][64]; /* lower bounds (Encoder::quants_[].min_quant_), 1 (or 0) = none */
   int q_bias;               /* AC rounding bias, enc.cc:46 default 0x78                    */
   int qdelta_max_luma;      /* enc.cc:48 default 12; at most 12 (histogram.cc:179-183)     */
   int qdelta_max_chroma;    /* enc.cc:49 default 1;  at most 12                            */

@@ -268,6 +268,13 @@ int MakePlan(int width, int height, long long stride, const sjb_params* params, 
   // the candidate steps are q0 - 12 .. q0 + 12: the reference asserts the limits stay inside (histogram.cc:179-183)
   // and indexes past its tables otherwise; here such settings are refused
   if (p.qdelta_max_luma > 12 || p.qdelta_max_chroma > 12) return SJB_ERR_ARG;
+  // a quantiser step of 0 does not exist (the reference's matrices and minima start at 1): a lower bound of 0
+  // means "none", and entries below their bound are raised to it by the quantiser set-up as in the reference
+  for (int m = 0; m < 2; ++m) {
+    for (int i = 0; i < 64; ++i) {
+      if (p.min_quant[m][i] == 0) p.min_quant[m][i] = 1;
+    }
+  }
   const size_t nb = plan->g.nb_blocks();
   plan->stream_words = ((nb * kWorstBitsPerBlock / 32 + 64) + 3) & ~static_cast<size_t>(3);
   plan->out_capacity = (kHeaderReserve + 2 * plan->stream_words * 4 + 16 + 255) & ~static_cast<size_t>(255);

@@ -160,6 +160,19 @@ def test_delta_limits_beyond_the_candidate_range_are_refused(gpu_ctx):
     got = gpu_ctx.encode(rgb, 64, 48, 192, p)
     want = O.oracle_encode_params(rgb, 64, 48, 192, O.SjoParams.from_buffer_copy(bytes(p)))    # same layout
     assert got == want
+    # a step of 0 does not exist: zero lower bounds mean "none", zero matrix entries are raised to 1
+    for method in (0, 4):
+        pz = S.default_params(75, method, S.YUV_420)
+        p1 = S.default_params(75, method, S.YUV_420)
+        for m in range(2):
+            for i in range(64):
+                pz.quant[m][i] = 0
+                pz.min_quant[m][i] = 0
+                p1.quant[m][i] = 1
+                p1.min_quant[m][i] = 1
+        got = gpu_ctx.encode(rgb, 64, 48, 192, pz)
+        assert got is not None and got == gpu_ctx.encode(rgb, 64, 48, 192, p1)
+        assert got == O.oracle_encode_params(rgb, 64, 48, 192, O.SjoParams.from_buffer_copy(bytes(p1)))
 
 
 def test_large_dimension_limits(gpu_ctx):
