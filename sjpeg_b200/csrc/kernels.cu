@@ -5,9 +5,13 @@
 //       permutation).  Fast path: one warp per tile, strips of 8 pixel rows x 768 bytes staged
 //       into shared memory with bulk-async copies (TMA engine, cp.async.bulk + mbarrier).
 //       Generic path: clamped byte loads, handles edges / odd strides / BGRA / RGBA.
+//       Planar path: the same shape for YUV420 / YUV444 / NV12 / NV21 / gray planes (sample = pixel - 128).
 //   Q1  re-quantise stored raw coefficients (adaptive quantisation, methods >= 3)
 //   H1  coefficient histogram (methods >= 3), shared-memory privatised
-//   T1  trellis quantiser (methods 7, 8), one block per thread
+//   A1  analysis of the histograms -> adapted matrices and quantiser constants (methods >= 3): the
+//       reference's float / double arithmetic in the reference's order, two small kernels
+//   T1  trellis quantiser (methods 7, 8), one block per thread, working storage in shared-memory
+//       columns, blocks handed out sorted by their number of non-zeros
 //   S1  Huffman symbol statistics (optimised tables)
 //   E   entropy stage in one pass, persistent and warp-specialised: worker warps walk the blocks
 //       of a tile (bits + packed words per block) -> scan -> a dedicated warp runs the decoupled
