@@ -299,3 +299,29 @@ def test_planar_batch(gpu_ctx, kind):
                 torch.cuda.synchronize()
                 got = [douts[i][:sizes[i]].cpu().numpy().tobytes() for i in range(n)]
                 assert got == want, (kind, w, h, method, "device")
+
+
+def test_random_batches(gpu_ctx):
+    """seeded random batches: number of pictures (ragged groups, more groups than lanes), geometry, content
+    mixed inside the batch, method, mode, quality, device-resident or host buffers.  One-off longer runs:
+    SJB_BATCH_FUZZ_CASES=200 SJB_BATCH_FUZZ_SEED=5 python -m pytest tests/test_gpu_batch.py -m gpu -k random_batches"""
+    import os
+    import sjpeg_b200 as S
+    cases = int(os.environ.get("SJB_BATCH_FUZZ_CASES", "10"))
+    rng = np.random.RandomState(int(os.environ.get("SJB_BATCH_FUZZ_SEED", "424242")))
+    kinds = ["A", "B", "noise", "flat"]
+    for case in range(cases):
+        n = int(rng.choice([1, 2, 3, 5, 16, 17, 31, 50, 97, 130]))
+        w, h = int(rng.randint(1, 400)), int(rng.randint(1, 260))
+        mode = int(rng.choice([S.YUV_420, S.YUV_444, S.YUV_400]))
+        method = int(rng.randint(0, 9))
+        q = int(rng.choice([5, 50, 75, 90, 98]))
+        frames = [_frame(kinds[int(rng.randint(0, 4))], w, h, int(rng.randint(1, 1 << 30))) for _ in range(n)]
+        p = S.default_params(q, method, mode)
+        want = [O.oracle_encode(f, w, h, 3 * w, float(q), method, mode) for f in frames]
+        cap = max(len(x) for x in want) + 4096
+        if rng.randint(0, 2):
+            got = _encode_batch_device(gpu_ctx, frames, w, h, p, cap)
+        else:
+            got = _encode_batch_host(gpu_ctx, frames, w, h, p, cap)
+        assert got == want, (case, n, w, h, mode, method, q, [i for i in range(n) if got[i] != want[i]][:5])
