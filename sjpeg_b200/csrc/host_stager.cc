@@ -1,6 +1,8 @@
 // host_stager.cc -- see host_stager.h
 #include "host_stager.h"
 
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -180,15 +182,27 @@ cudaError_t HostStager::Upload(void* dst_device, const void* src_host, size_t by
   cudaError_t err = cudaSuccess;
   const uint8_t* src = static_cast<const uint8_t*>(src_host);
   uint8_t* dst = static_cast<uint8_t*>(dst_device);
-  int slot = 0;
-  for (size_t off = 0; off < bytes && err == cudaSuccess; off += kChunk, slot = (slot + 1) % kSlots) {
+  // SJB_STAGER_TRACE=1: where an upload's time goes (waiting for a ring slot / copying / CUDA calls), on stderr
+  static const bool trace = getenv("SJB_STAGER_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_wait = 0, t_copy = 0, t_api = 0, t0 = trace ? now() : 0;
+  const double t_begin = t0;
+  for (size_t off = 0; off < bytes && err == cudaSuccess; off += kChunk, next_slot_ = (next_slot_ + 1) % kSlots) {
+    const int slot = next_slot_;
     const size_t n = std::min(kChunk, bytes - off);
     uint8_t* stage = pinned_ + static_cast<size_t>(slot) * kChunk;
     err = cudaEventSynchronize(slot_free_[slot]);          // the DMA that last read this slot is done
     if (err != cudaSuccess) break;
+    if (trace) { const double t = now(); t_wait += t - t0; t0 = t; }
     CopyChunk(stage, src + off, n);
+    if (trace) { const double t = now(); t_copy += t - t0; t0 = t; }
     err = cudaMemcpyAsync(dst + off, stage, n, cudaMemcpyHostToDevice, stream);
     if (err == cudaSuccess) err = cudaEventRecord(slot_free_[slot], stream);
+    if (trace) { const double t = now(); t_api += t - t0; t0 = t; }
+  }
+  if (trace) {
+    fprintf(stderr, "[stager] %.1f MB in %.0f us: slot wait %.0f, copy %.0f, cuda calls %.0f; helped %d (in flight %d)\n", bytes / 1e6,
+            now() - t_begin, t_wait, t_copy, t_api, helped ? 1 : 0, in_flight.n);
   }
   if (helped) {
     spinning_.store(false, std::memory_order_release);

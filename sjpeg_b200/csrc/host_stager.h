@@ -28,12 +28,16 @@ namespace sjb {
 
 class HostStager {
  public:
-  // 3 helpers + the caller; 5 and 7 helpers measured slower at 4K (more threads to wake, more contention on the
-  // source's memory channels).  tools/micro/stager_bench.cu, 4K picture, uploads 0.25 ms apart: 2 MB chunks / 128 KB
-  // pieces / helpers asleep between uploads 0.91-0.96 ms (26-27 GB/s); helpers awake 0.61 ms (40 GB/s); 4 MB chunks /
-  // 256 KB pieces 0.575 ms (43 GB/s); the same from pinned memory 0.458 ms, through the driver's pageable path 1.2 ms.
+  // tools/micro/stager_bench.cu, uploads 0.25 ms apart, SOURCES ROTATING over more memory than the host's
+  // last-level cache (a stream of frames arrives from DRAM; the same buffer re-sent stays cache-warm and
+  // flatters every figure by 20-25 %), 4K / 8K picture:
+  //   driver's pageable path 2.3 / 8.8 ms;  pinned source 0.458 / 1.80 ms
+  //   3 helpers 0.71 / 2.62 ms (35 / 38 GB/s), 5 helpers 0.66-0.70 / 2.07-2.27 ms (up to 48 GB/s), 7 helpers 0.67 / 2.10 ms
+  //   (4 MB chunks, 256 KB pieces; 2 MB chunks: 0.76-0.83 / 2.6-2.9 ms)
+  // With the helpers asleep between uploads (no grace period) 5 and 7 helpers had been SLOWER than 3 at 4K:
+  // more threads to wake.  A cache-warm 4K source: 0.575 ms with 3 helpers.
 #ifndef SJB_STAGER_HELPERS
-#define SJB_STAGER_HELPERS 3
+#define SJB_STAGER_HELPERS 5
 #endif
 #ifndef SJB_STAGER_CHUNK_KB
 #define SJB_STAGER_CHUNK_KB 4096
@@ -79,6 +83,7 @@ class HostStager {
   std::atomic<unsigned> pieces_done_{0};
   std::atomic<bool> spinning_{false};
   unsigned ticket_ = 0;
+  int next_slot_ = 0;                               // the ring goes on where the previous upload stopped
   void Work();
   uint8_t* job_dst_ = nullptr;
   const uint8_t* job_src_ = nullptr;

@@ -9,8 +9,16 @@
 static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 int main() {
   for (size_t bytes : {size_t(3840) * 2160 * 3, size_t(7680) * 4320 * 3}) {
-    uint8_t* src = static_cast<uint8_t*>(malloc(bytes));
-    memset(src, 7, bytes);
+    // a rotation of sources larger than the host's last-level cache: pictures arrive from DRAM, as in a real
+    // stream of frames (the same buffer re-sent stays cache-warm and copies 20-25 % faster)
+    enum { kSources = 12 };
+    uint8_t* srcs[kSources];
+    for (auto& p : srcs) {
+      p = static_cast<uint8_t*>(malloc(bytes));
+      memset(p, 7, bytes);
+    }
+    uint8_t* src = srcs[0];
+    int turn = 0;
     uint8_t *dev, *pinned;
     cudaMalloc(&dev, bytes);
     cudaMallocHost(&pinned, bytes);
@@ -25,6 +33,7 @@ int main() {
       for (int k = 0; k < 3; ++k) {
         const double w = now() + 250e-6;
         while (now() < w) {}
+        src = srcs[turn++ % kSources];
         t0 = now();
         stager.Upload(dev, src, bytes, st);
         cudaStreamSynchronize(st);
@@ -42,7 +51,7 @@ int main() {
     printf("grace %d us helpers %d chunk %d KB piece %d KB | %.1f MB: stager %.3f ms (%.1f GB/s)  driver pageable %.3f ms  pinned %.3f ms\n",
            (int)sjb::HostStager::kGraceUs, (int)sjb::HostStager::kHelpers, (int)(sjb::HostStager::kChunk >> 10), (int)(sjb::HostStager::kPiece >> 10), bytes / 1e6,
            best[0] * 1e3, bytes / best[0] / 1e9, best[1] * 1e3, best[2] * 1e3);
-    free(src);
+    for (auto& p : srcs) free(p);
     cudaFree(dev);
     cudaFreeHost(pinned);
   }
