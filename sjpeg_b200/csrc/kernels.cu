@@ -649,7 +649,9 @@ requantize_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb, const in
   int v[64];
   load_block_natural(raw_src ? raw_src + frame * gb.coef_pitch + coef_block_base(g) : blk, v);
   const uint32_t tab = smem_addr(qtab) + ((static_cast<int>(g % fs.mcu_blocks) >= fs.luma_blocks) ? 512u : 0u);
-  quantize_store_block(v, SmemTab{tab}, blk, gb.nzmask + frame * gb.mask_pitch + g);
+  // all-zero sectors are not written back (as in the fast F1 path: the bitmap gates every later read; in place,
+  // such a sector keeps its raw values, which nobody looks at): a photographic picture writes a quarter of the bytes
+  quantize_store_block<true>(v, SmemTab{tab}, blk, gb.nzmask + frame * gb.mask_pitch + g);
 }
 
 // -------------------------------------------------------------------------------------------
