@@ -749,7 +749,9 @@ histogram_kernel(const __grid_constant__ FrameSet fs, GroupBuffers gb) {
   // the atomic: the instruction count went up and the number of ATOMS instructions stayed.  Bank
   // conflicts are not it either: with the rows reordered so that the 32 lanes of an instruction own 32
   // consecutive rows (32 different banks for equal bins; rows 2l put lanes l and l + 16 on one bank) the
-  // kernel took 145.4 us against 144.4.
+  // kernel took 145.4 us against 144.4.  Nor the flavour of the instruction: ptxas turns atomicAdd(.., 1) into
+  // ATOMS.POPC.INC (lanes with equal addresses are counted in one go); forced to plain ATOMS.ADD (an increment the
+  // compiler cannot see is 1) the kernel took 177 us.
   for (; g0 < full_end; g0 += step) {
     const int16_t* p = base + (static_cast<size_t>(g0 >> 2) << 8);
     uint32_t w[8];
