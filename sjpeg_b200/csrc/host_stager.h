@@ -3,17 +3,18 @@
 //
 // Why: the drop-in entry points (SjpegEncode, sjpeg::Encode; /root/reference/src/sjpeg.h:104,280)
 // receive whatever buffer the caller has, normally malloc()ed.  cudaMemcpyAsync from pageable
-// memory is staged by the driver on the calling thread at about 19 GB/s on the B200 boxes (24.9 MB
-// of 4K RGB: 1.3 ms), while the device pipeline for that picture takes 0.06 ms, so the copy IS
+// memory is staged by the driver on the calling thread at about 11-19 GB/s on the B200 boxes (24.9 MB
+// of 4K RGB: 1.2 ms cache-warm, 2.3 ms out of DRAM), while the device pipeline for that picture takes 0.06 ms, so the copy IS
 // the call.  Here the picture is cut into chunks; the caller and kHelpers helper threads copy
-// each chunk into pinned memory together -- in 128 KB pieces claimed from a shared cursor, so the
+// each chunk into pinned memory together -- in kPiece pieces claimed from a shared cursor, so the
 // caller never waits for a helper that is still waking up -- and the DMA of chunk c overlaps the
 // host copy of chunk c+1.  Pinned / registered / managed sources never come here (engine.cu checks the
 // pointer's type first).
 //
 // One stager per context; a context is used by one thread at a time (include/sjpeg_b200.h), so
-// Upload() is never entered concurrently.  The helpers spin only while an upload is running and
-// sleep on a condition variable otherwise.
+// Upload() is never entered concurrently.  The helpers spin while an upload is running and for kGraceUs
+// after it (the next upload of a stream of frames finds them awake), then sleep on a condition variable.
+// Across contexts, uploads only get helpers while callers x (kHelpers + 1) fits the hardware threads.
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
